@@ -1,0 +1,370 @@
+// builder.cpp -- topology, props and the repr(C) DataSet / ParamSet.
+// Restates crates/ppf-cts-solver/src/mesh.rs:66-293, scene.rs:1538-1930 (make_props),
+// main.rs:204-258 (non-rod edge props) and builder.rs:339-1681 (build, make_param) for
+// shell scenes (no rods / tets / PDRD / SAND / stitches, which none of the BASELINE
+// twist configs contain).  Edge and hinge numbering: the reference iterates a std HashMap
+// (random per process, mesh.rs:196-229,257-293); this host uses sorted-key order so a
+// scene is reproducible.  Both backends are always fed the same DataSet.
+#include "ppf_host.hpp"
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+
+namespace ppfh {
+
+template <class T> void OwnedVecVec<T>::from(const std::vector<std::vector<T>> &rows) {
+    offset.assign(rows.size() + 1, 0);
+    size_t n = 0;
+    for (size_t i = 0; i < rows.size(); ++i) {
+        offset[i] = (unsigned)n;
+        n += rows[i].size();
+    }
+    offset[rows.size()] = (unsigned)n;
+    data.clear();
+    data.reserve(n);
+    for (auto &r : rows) data.insert(data.end(), r.begin(), r.end());
+}
+template struct OwnedVecVec<unsigned>;
+template struct OwnedVecVec<PpfVec2u>;
+
+template <class V, class T> static void set_vec(V &dst, std::vector<T> &src) {
+    dst.data = src.empty() ? nullptr : reinterpret_cast<decltype(dst.data)>(src.data());
+    dst.size = dst.allocated = (unsigned)src.size();
+}
+template <class VV, class T> static void set_vecvec(VV &dst, OwnedVecVec<T> &src) {
+    dst.data = src.data.empty() ? nullptr : reinterpret_cast<decltype(dst.data)>(src.data.data());
+    dst.offset = src.offset.data();
+    dst.size = (unsigned)src.offset.size() - 1;
+    dst.nnz = dst.nnz_allocated = (unsigned)src.data.size();
+    dst.offset_allocated = (unsigned)src.offset.size();
+}
+
+static inline Vec3f sub(const Vec3f &a, const Vec3f &b) { return {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
+static inline Vec3f cross(const Vec3f &a, const Vec3f &b) {
+    return {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+}
+static inline float dot(const Vec3f &a, const Vec3f &b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline float norm(const Vec3f &a) { return std::sqrt(dot(a, a)); }
+
+template <class P> static unsigned dedup(std::vector<P> &store, const P &p) { // builder.rs:1749-1759
+    for (unsigned i = 0; i < store.size(); ++i)
+        if (std::memcmp(&store[i], &p, sizeof(P)) == 0) return i;
+    store.push_back(p);
+    return (unsigned)store.size() - 1;
+}
+
+void build_scene(const SceneSpec &spec, Built &b) {
+    b = Built{};
+    b.spec = spec;
+    const SimArgs &a = spec.args;
+
+    // ---- index map: global index = order of first appearance in the face rows, object by
+    // object; loose vertices follow (index_map.rs:68-153) ----
+    std::vector<std::vector<int>> l2g(spec.objects.size());
+    for (size_t o = 0; o < spec.objects.size(); ++o) l2g[o].assign(spec.objects[o].vert.size(), -1);
+    auto assign = [&](size_t o, unsigned lv) {
+        if (l2g[o][lv] < 0) {
+            l2g[o][lv] = (int)b.vert_origin.size();
+            b.vert_origin.push_back({(unsigned)o, lv});
+        }
+    };
+    for (size_t o = 0; o < spec.objects.size(); ++o)
+        for (auto &t : spec.objects[o].tri)
+            for (int k = 0; k < 3; ++k) assign(o, t[k]);
+    for (size_t o = 0; o < spec.objects.size(); ++o)
+        for (unsigned lv = 0; lv < spec.objects[o].vert.size(); ++lv) assign(o, lv);
+    const unsigned nv = b.n_vert = (unsigned)b.vert_origin.size();
+    b.vert.resize(nv);
+    b.vert_dmap.resize(nv);
+    const float ws = float(a.world_scaling);
+    for (unsigned g = 0; g < nv; ++g) {
+        auto [o, lv] = b.vert_origin[g];
+        const Vec3d &p = spec.objects[o].vert[lv];
+        const Vec3d &d = spec.objects[o].displacement;
+        b.vert[g] = Vec3f{float(p[0] + d[0]) * ws, float(p[1] + d[1]) * ws, float(p[2] + d[2]) * ws};
+        b.vert_dmap[g] = o;
+    }
+    std::vector<unsigned> face_object;
+    for (size_t o = 0; o < spec.objects.size(); ++o)
+        for (auto &t : spec.objects[o].tri) {
+            b.face.push_back(PpfVec3u{{(unsigned)l2g[o][t[0]], (unsigned)l2g[o][t[1]], (unsigned)l2g[o][t[2]]}});
+            face_object.push_back((unsigned)o);
+        }
+    const unsigned nf = (unsigned)b.face.size();
+
+    // ---- edges and hinges (mesh.rs:188-293), sorted-key order ----
+    struct ERec { unsigned a, b, f0; int f1; };
+    std::map<std::pair<unsigned, unsigned>, ERec> emap;
+    struct HRec { unsigned i0, i1, i2; int i3; unsigned f0; int f1; bool excluded; };
+    std::map<std::pair<unsigned, unsigned>, HRec> hmap;
+    for (unsigned i = 0; i < nf; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const unsigned e0 = b.face[i].v[j], e1 = b.face[i].v[(j + 1) % 3], e2 = b.face[i].v[(j + 2) % 3];
+            auto key = std::make_pair(std::min(e0, e1), std::max(e0, e1));
+            auto it = emap.find(key);
+            if (it == emap.end()) emap[key] = ERec{e0, e1, i, -1};
+            else if (it->second.f1 < 0) it->second.f1 = (int)i;
+            auto ht = hmap.find(key);
+            if (ht == hmap.end()) hmap[key] = HRec{e0, e1, e2, -1, i, -1, false};
+            else if (ht->second.i3 >= 0) ht->second.excluded = true;
+            else { ht->second.i3 = (int)e2; ht->second.f1 = (int)i; }
+        }
+    for (auto &kv : emap) {
+        b.edge.push_back(PpfVec2u{{kv.second.a, kv.second.b}});
+        if (kv.second.f1 >= 0) b.edge_face.push_back({kv.second.f0, (unsigned)kv.second.f1});
+        else b.edge_face.push_back({kv.second.f0});
+    }
+    for (auto &kv : hmap)
+        if (!kv.second.excluded && kv.second.i3 >= 0) {
+            b.hinge.push_back(PpfVec4u{{kv.second.i0, kv.second.i1, kv.second.i2, (unsigned)kv.second.i3}});
+            b.hinge_face.push_back({kv.second.f0, (unsigned)kv.second.f1});
+        }
+    const unsigned ne = (unsigned)b.edge.size(), nh = (unsigned)b.hinge.size();
+    b.v_face.assign(nv, {}); b.v_hinge.assign(nv, {}); b.v_edge.assign(nv, {}); b.v_rod.assign(nv, {});
+    for (unsigned i = 0; i < nf; ++i) for (int k = 0; k < 3; ++k) b.v_face[b.face[i].v[k]].push_back(i);
+    for (unsigned i = 0; i < nh; ++i) for (int k = 0; k < 4; ++k) b.v_hinge[b.hinge[i].v[k]].push_back(i);
+    for (unsigned i = 0; i < ne; ++i) for (int k = 0; k < 2; ++k) b.v_edge[b.edge[i].v[k]].push_back(i);
+
+    // ---- face props / params (scene.rs:1656-1830) ----
+    std::vector<float> face_area(nf);
+    for (unsigned i = 0; i < nf; ++i) { // triutils.rs:9-17
+        const Vec3f &x0 = b.vert[b.face[i].v[0]], &x1 = b.vert[b.face[i].v[1]], &x2 = b.vert[b.face[i].v[2]];
+        face_area[i] = 0.5f * norm(cross(sub(x1, x0), sub(x2, x0)));
+        if (!(face_area[i] > 0.0f)) throw std::runtime_error("degenerate face");
+    }
+    b.fprop.resize(nf);
+    for (unsigned i = 0; i < nf; ++i) {
+        const auto &pm = spec.objects[face_object[i]].param;
+        auto get = [&](const char *k) { return float(pm.at(k)); };
+        PpfFaceParam p;
+        std::memset(&p, 0, sizeof(p));
+        p.model = (PpfModel)(int)pm.at("model");
+        const float young = get("young-mod"), poiss = get("poiss-rat");
+        p.mu = young / (2.0f * (1.0f + poiss)); // builder.rs:1739-1743
+        p.lambda = young * poiss / ((1.0f + poiss) * (1.0f - 2.0f * poiss));
+        p.friction = get("friction"); p.ghat = get("contact-gap"); p.offset = get("contact-offset");
+        p.bend = get("bend"); p.strainlimit = get("strain-limit");
+        p.shrink_x = get("shrink-x"); p.shrink_y = get("shrink-y"); p.pressure = get("pressure");
+        PpfFaceProp fp;
+        std::memset(&fp, 0, sizeof(fp));
+        fp.area = face_area[i];
+        fp.mass = get("density") * face_area[i];
+        fp.param_index = dedup(b.fparam, p);
+        b.fprop[i] = fp;
+    }
+    // ---- non-rod edge props (main.rs:225-258, builder.rs:1800-1821) ----
+    b.eprop.resize(ne);
+    for (unsigned i = 0; i < ne; ++i) {
+        float gs = 0, os = 0, fs = 0, as = 0;
+        for (unsigned j : b.edge_face[i]) {
+            const PpfFaceParam &fp = b.fparam[b.fprop[j].param_index];
+            const float ar = face_area[j];
+            gs += ar * fp.ghat; os += ar * fp.offset; fs += ar * fp.friction; as += ar;
+        }
+        PpfEdgeParam p;
+        std::memset(&p, 0, sizeof(p));
+        p.ghat = gs / as; p.offset = os / as; p.friction = fs / as;
+        PpfEdgeProp ep;
+        std::memset(&ep, 0, sizeof(ep));
+        ep.length = ep.initial_length = norm(sub(b.vert[b.edge[i].v[1]], b.vert[b.edge[i].v[0]]));
+        ep.param_index = dedup(b.eparam, p);
+        b.eprop[i] = ep;
+    }
+
+    // ---- pins -> global indices; initial constraint at (t, t) (main.rs make_constraint(0,0)) ----
+    for (size_t o = 0; o < spec.objects.size(); ++o)
+        for (auto &pin : spec.objects[o].pins) {
+            Built::GPin g;
+            g.object = (unsigned)o; g.ops = pin.ops; g.pull_w = pin.pull_w; g.unpin_time = pin.unpin_time;
+            for (unsigned lv : pin.index) {
+                g.index.push_back((unsigned)l2g[o][lv]);
+                const Vec3d &p = spec.objects[o].vert[lv];
+                g.rest.push_back(Vec3f{float(p[0]) * ws, float(p[1]) * ws, float(p[2]) * ws});
+            }
+            b.pins.push_back(std::move(g));
+        }
+    make_constraint(b, 0.0, 0.0);
+
+    // ---- builder.rs:388-432 fixed flags ----
+    std::vector<char> is_fixed(nv, 0);
+    for (auto &f : b.fix) is_fixed[f.index] = 1;
+    for (unsigned i = 0; i < nf; ++i)
+        b.fprop[i].fixed = is_fixed[b.face[i].v[0]] && is_fixed[b.face[i].v[1]] && is_fixed[b.face[i].v[2]];
+    for (unsigned i = 0; i < ne; ++i) b.eprop[i].fixed = is_fixed[b.edge[i].v[0]] && is_fixed[b.edge[i].v[1]];
+
+    // ---- vertex props (builder.rs:468-644) and params (781-863) ----
+    b.vprop.assign(nv, PpfVertexProp{});
+    for (auto &vp : b.vprop) { std::memset(&vp, 0, sizeof(vp)); vp.rest_bend_angle = float(M_PI); }
+    for (unsigned i = 0; i < b.fix.size(); ++i) b.vprop[b.fix[i].index].fix_index = i + 1;
+    for (unsigned i = 0; i < b.pull.size(); ++i) b.vprop[b.pull[i].index].pull_index = i + 1;
+    for (unsigned i = 0; i < nf; ++i)
+        for (int k = 0; k < 3; ++k) b.vprop[b.face[i].v[k]].area += b.fprop[i].area / 3.0f;
+    for (unsigned i = 0; i < nf; ++i)
+        for (int k = 0; k < 3; ++k) b.vprop[b.face[i].v[k]].mass += b.fprop[i].mass / 3.0f;
+    for (unsigned j = 0; j < nv; ++j) {
+        float gs = 0, os = 0, fs = 0, wsum = 0;
+        for (unsigned fi : b.v_face[j]) {
+            const PpfFaceParam &fp = b.fparam[b.fprop[fi].param_index];
+            const float w = b.fprop[fi].area;
+            gs += w * fp.ghat; os += w * fp.offset; fs += w * fp.friction; wsum += w;
+        }
+        if (wsum > 0.0f) {
+            PpfVertexParam p{gs / wsum, os / wsum, fs / wsum};
+            b.vprop[j].param_index = dedup(b.vparam, p);
+        }
+    }
+    // ---- hinge props (builder.rs:865-1020) ----
+    b.hprop.resize(nh);
+    for (unsigned i = 0; i < nh; ++i) {
+        const PpfVec4u &h = b.hinge[i];
+        float os = 0, gs = 0, bs = 0, as = 0;
+        bool all_fixed = true;
+        for (unsigned j : b.hinge_face[i]) {
+            const PpfFaceParam &fp = b.fparam[b.fprop[j].param_index];
+            const float ar = b.fprop[j].area;
+            all_fixed = all_fixed && b.fprop[j].fixed;
+            os += ar * fp.offset; gs += ar * fp.ghat; bs += ar * fp.bend; as += ar;
+        }
+        PpfHingeParam p;
+        std::memset(&p, 0, sizeof(p));
+        p.bend = all_fixed ? 0.0f : bs / as;
+        p.ghat = gs / as; p.offset = os / as;
+        PpfHingeProp hp;
+        std::memset(&hp, 0, sizeof(hp));
+        hp.length = norm(sub(b.vert[h.v[0]], b.vert[h.v[1]]));
+        hp.area = as; hp.rest_angle = 0.0f; hp.uv_edge_sin2 = -1.0f; hp.fixed = all_fixed;
+        hp.param_index = dedup(b.hparam, p);
+        b.hprop[i] = hp;
+    }
+    // ---- inv_rest2x2 (builder.rs:157-229, no UV) ----
+    b.inv_rest2x2.resize(nf);
+    for (unsigned i = 0; i < nf; ++i) {
+        const Vec3f &x0 = b.vert[b.face[i].v[0]], &x1 = b.vert[b.face[i].v[1]], &x2 = b.vert[b.face[i].v[2]];
+        const Vec3f d0 = sub(x1, x0), d1 = sub(x2, x0);
+        const Vec3f n = cross(d0, d1);
+        Vec3f e2 = cross(n, d0);
+        const float e2n = norm(e2), d0n = norm(d0);
+        e2 = Vec3f{e2[0] / e2n, e2[1] / e2n, e2[2] / e2n};
+        const Vec3f e1 = Vec3f{d0[0] / d0n, d0[1] / d0n, d0[2] / d0n};
+        // d_mat = [e1; e2] * [d0 d1]  (2x2, column-major m[col*2+row])
+        const float m00 = dot(e1, d0), m10 = dot(e2, d0), m01 = dot(e1, d1), m11 = dot(e2, d1);
+        const float det = m00 * m11 - m01 * m10;
+        if (det == 0.0f) throw std::runtime_error("degenerate shell face");
+        PpfMat2x2f inv;
+        inv.m[0] = m11 / det;  // (0,0)
+        inv.m[1] = -m10 / det; // (1,0)
+        inv.m[2] = -m01 / det; // (0,1)
+        inv.m[3] = m00 / det;  // (1,1)
+        b.inv_rest2x2[i] = inv;
+    }
+    // ---- fixed_index_table / transpose_table / slot tables (builder.rs:1244-1496) ----
+    b.fixed_index_table.assign(nv, {});
+    {
+        std::vector<std::vector<unsigned>> &t = b.fixed_index_table;
+        auto ins = [&](unsigned i, unsigned j) { if (i <= j) t[i].push_back(j); };
+        for (unsigned i = 0; i < nv; ++i) ins(i, i);
+        for (auto &e : b.edge) for (int p = 0; p < 2; ++p) for (int q = 0; q < 2; ++q) ins(e.v[p], e.v[q]);
+        for (auto &f : b.face) for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) ins(f.v[p], f.v[q]);
+        for (auto &h : b.hinge) for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) ins(h.v[p], h.v[q]);
+        for (auto &row : t) { std::sort(row.begin(), row.end()); row.erase(std::unique(row.begin(), row.end()), row.end()); }
+    }
+    b.transpose_table.assign(nv, {});
+    std::vector<unsigned> row_offset(nv + 1, 0);
+    {
+        unsigned sum = 0;
+        for (unsigned i = 0; i < nv; ++i) {
+            row_offset[i] = sum;
+            for (unsigned k = 0; k < b.fixed_index_table[i].size(); ++k) {
+                const unsigned j = b.fixed_index_table[i][k];
+                if (i != j) b.transpose_table[j].push_back(PpfVec2u{{i, sum + k}});
+            }
+            sum += (unsigned)b.fixed_index_table[i].size();
+        }
+        row_offset[nv] = sum;
+    }
+    auto slot_of = [&](unsigned i, unsigned j) -> unsigned {
+        if (i > j) return 0xFFFFFFFFu;
+        const auto &row = b.fixed_index_table[i];
+        auto it = std::lower_bound(row.begin(), row.end(), j);
+        if (it == row.end() || *it != j) throw std::runtime_error("slot precompute: block missing");
+        return row_offset[i] + unsigned(it - row.begin());
+    };
+    for (auto &f : b.face) for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) b.face_slots.push_back(slot_of(f.v[p], f.v[q]));
+    for (auto &e : b.edge) for (int p = 0; p < 2; ++p) for (int q = 0; q < 2; ++q) b.edge_slots.push_back(slot_of(e.v[p], e.v[q]));
+    for (auto &h : b.hinge) {
+        const unsigned r[4] = {h.v[2], h.v[1], h.v[0], h.v[3]};
+        for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) b.hinge_slots.push_back(slot_of(r[p], r[q]));
+    }
+    b.rod_bend_slots.assign(size_t(9) * nv, 0xFFFFFFFFu);
+    b.type_face.assign(nf, 0); b.type_vertex.assign(nv, 0); b.type_hinge.assign(nh, 0);
+
+    // ---- vertex state (builder.rs:1571-1587) ----
+    const float dt = std::min(float(a.dt), 0.9999f / float(a.fps)); // builder.rs:273-275
+    b.curr.resize(nv); b.prev.resize(nv);
+    for (unsigned g = 0; g < nv; ++g) {
+        const Vec3d &vel = spec.objects[b.vert_origin[g].first].velocity;
+        for (int k = 0; k < 3; ++k) {
+            b.curr[g].v[k] = b.vert[g][k];
+            b.prev[g].v[k] = b.vert[g][k] - dt * float(vel[k]);
+        }
+    }
+    // ---- per-vertex zero arrays (builder.rs:748-762, 1079) ----
+    b.zero3.assign(nv, PpfVec3f{{0, 0, 0}});
+    b.zero1.assign(nv, 0.0f);
+    b.zero9.assign(nv, PpfMat3x3f{{0, 0, 0, 0, 0, 0, 0, 0, 0}});
+    b.lock_index.assign(nv, 0xFFFFFFFFu);
+
+    // ---- assemble the DataSet ----
+    b.f_v_face.from(b.v_face); b.f_v_hinge.from(b.v_hinge); b.f_v_edge.from(b.v_edge); b.f_v_rod.from(b.v_rod);
+    b.f_hinge_face.from(b.hinge_face); b.f_edge_face.from(b.edge_face);
+    b.f_fixed.from(b.fixed_index_table); b.f_transpose.from(b.transpose_table);
+    PpfDataSet &d = b.dataset;
+    std::memset(&d, 0, sizeof(d));
+    set_vec(d.vertex.prev, b.prev); set_vec(d.vertex.curr, b.curr);
+    set_vec(d.mesh.mesh.face, b.face); set_vec(d.mesh.mesh.hinge, b.hinge); set_vec(d.mesh.mesh.edge, b.edge);
+    set_vecvec(d.mesh.neighbor.vertex.face, b.f_v_face); set_vecvec(d.mesh.neighbor.vertex.hinge, b.f_v_hinge);
+    set_vecvec(d.mesh.neighbor.vertex.edge, b.f_v_edge); set_vecvec(d.mesh.neighbor.vertex.rod, b.f_v_rod);
+    set_vecvec(d.mesh.neighbor.hinge.face, b.f_hinge_face); set_vecvec(d.mesh.neighbor.edge.face, b.f_edge_face);
+    set_vec(d.mesh.type.face, b.type_face); set_vec(d.mesh.type.vertex, b.type_vertex); set_vec(d.mesh.type.hinge, b.type_hinge);
+    set_vec(d.prop.vertex, b.vprop); set_vec(d.prop.edge, b.eprop); set_vec(d.prop.face, b.fprop); set_vec(d.prop.hinge, b.hprop);
+    set_vec(d.param_arrays.vertex, b.vparam); set_vec(d.param_arrays.edge, b.eparam);
+    set_vec(d.param_arrays.face, b.fparam); set_vec(d.param_arrays.hinge, b.hparam);
+    set_vec(d.inv_rest2x2, b.inv_rest2x2);
+    d.constraint = b.constraint;
+    set_vecvec(d.fixed_index_table, b.f_fixed); set_vecvec(d.transpose_table, b.f_transpose);
+    d.rod_count = 0; d.shell_face_count = nf; d.surface_vert_count = nv;
+    set_vec(d.grain_omega, b.zero3); set_vec(d.grain_inv_inertia, b.zero1); set_vec(d.grain_torque, b.zero3);
+    set_vec(d.grain_ang_stiff, b.zero1); set_vec(d.grain_contact_normal, b.zero3);
+    set_vec(d.grain_inv_inertia_center, b.zero1); set_vec(d.grain_omega_prev, b.zero3);
+    set_vec(d.grain_A, b.zero9); set_vec(d.grain_B, b.zero9); set_vec(d.grain_grot, b.zero3);
+    set_vec(d.face_hess_slots, b.face_slots); set_vec(d.edge_hess_slots, b.edge_slots);
+    set_vec(d.hinge_hess_slots, b.hinge_slots); set_vec(d.rod_bend_hess_slots, b.rod_bend_slots);
+    set_vec(d.translation_lock_index, b.lock_index);
+
+    // ---- make_param (builder.rs:1629-1681) ----
+    PpfParamSet &p = b.param;
+    std::memset(&p, 0, sizeof(p));
+    p.time = 0.0;
+    p.air_friction = float(a.air_friction); p.air_density = float(a.air_density); p.constraint_tol = float(a.constraint_tol);
+    p.prev_dt = dt; p.dt = dt; p.playback = float(a.playback);
+    p.min_newton_steps = a.min_newton_steps; p.target_toi = float(a.target_toi);
+    p.stitch_length_factor = float(a.stitch_length_factor);
+    p.cg_max_iter = a.cg_max_iter; p.cg_tol = float(a.cg_tol); p.line_search_max_t = float(a.line_search_max_t);
+    p.ccd_eps = float(a.ccd_eps); p.max_dx = float(a.max_dx); p.eiganalysis_eps = float(a.eiganalysis_eps);
+    p.friction_eps = float(a.friction_eps); p.isotropic_air_friction = float(a.isotropic_air_friction);
+    for (int k = 0; k < 3; ++k) { p.gravity.v[k] = float(a.gravity[k]); p.wind.v[k] = float(a.wind[k]); }
+    p.barrier = a.barrier == "quad" ? PPF_BARRIER_QUAD : a.barrier == "log" ? PPF_BARRIER_LOG : PPF_BARRIER_CUBIC;
+    p.friction_mode = a.friction_mode == "max" ? PPF_FRICTION_MAX : a.friction_mode == "mean" ? PPF_FRICTION_MEAN : PPF_FRICTION_MIN;
+    p.csrmat_max_nnz = a.csrmat_max_nnz;
+    p.fix_xz = float(a.fix_xz * a.world_scaling);
+    p.disable_contact = a.disable_contact; p.inactive_momentum = a.inactive_momentum;
+    p.precond = a.precond == "schwarz" ? PPF_PRECOND_SCHWARZ : PPF_PRECOND_BLOCKJACOBI;
+    p.schwarz_levels = a.schwarz_levels; p.max_newton_steps = a.max_newton_steps;
+    p.disable_pin_dof_removal = false;
+    update_param(b, 0.0);
+}
+
+} // namespace ppfh

@@ -1,0 +1,283 @@
+// scene.cpp -- mesh generators, named scenes, pin operations.
+// See ppf_host.hpp for the reference files each function restates.
+#include "ppf_host.hpp"
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+
+namespace ppfh {
+
+// crates/ppf-cts-core/src/datamodel/mesh.rs:606-615 (dx, ny, dy) + :242-295 (verts, faces)
+void gen_cylinder(double r, double min_x, double max_x, unsigned n, std::vector<Vec3d> &V,
+                  std::vector<std::array<unsigned, 3>> &F) {
+    const double dx = (max_x - min_x) / double(n);
+    const double ny_f = 2.0 * M_PI * r / dx;
+    unsigned ny = (unsigned)ny_f;
+    if (ny < 3) ny = 3;
+    const double dy = 2.0 * M_PI / double(ny);
+    V.assign(size_t(n + 1) * ny, Vec3d{0, 0, 0});
+    for (unsigned j = 0; j < ny; ++j) {
+        const double theta = double(j) * dy, s = std::sin(theta), c = std::cos(theta);
+        for (unsigned i = 0; i <= n; ++i) V[size_t(n + 1) * j + i] = Vec3d{min_x + double(i) * dx, s * r, c * r};
+    }
+    F.assign(size_t(2) * n * ny, {0u, 0u, 0u});
+    for (unsigned j = 0; j < ny; ++j)
+        for (unsigned i = 0; i < n; ++i) {
+            const size_t idx = size_t(j) * n + i;
+            const unsigned v0 = (n + 1) * j + i, v1 = v0 + 1;
+            const unsigned v2 = (n + 1) * ((j + 1) % ny) + (i + 1), v3 = (n + 1) * ((j + 1) % ny) + i;
+            if ((i % 2) == (j % 2)) {
+                F[2 * idx] = {v1, v2, v0};
+                F[2 * idx + 1] = {v3, v0, v2};
+            } else {
+                F[2 * idx] = {v0, v1, v3};
+                F[2 * idx + 1] = {v2, v3, v1};
+            }
+        }
+}
+
+// mesh.rs:181-206 (faces) + :621-667 (verts); square(res, size) = rectangle(res, size, size)
+void gen_square(unsigned res, double size, Vec3d ex, Vec3d ey, std::vector<Vec3d> &V,
+                std::vector<std::array<unsigned, 3>> &F) {
+    const unsigned res_x = res;
+    unsigned res_y = (unsigned)(double(res_x) * 1.0);
+    if (res_y < 2) res_y = 2;
+    const double size_x = size, size_y = size * double(res_y) / double(res_x);
+    const double step = std::min(size_x / (double(res_x) - 1.0), size_y / (double(res_y) - 1.0));
+    V.assign(size_t(res_x) * res_y, Vec3d{0, 0, 0});
+    for (unsigned i = 0; i < res_x; ++i) {
+        const double x = -size_x / 2.0 + step * i;
+        for (unsigned j = 0; j < res_y; ++j) {
+            const double y = -size_y / 2.0 + step * j;
+            V[size_t(i) * res_y + j] = Vec3d{ex[0] * x + ey[0] * y, ex[1] * x + ey[1] * y, ex[2] * x + ey[2] * y};
+        }
+    }
+    F.clear();
+    for (unsigned j = 0; j + 1 < res_y; ++j)
+        for (unsigned i = 0; i + 1 < res_x; ++i) {
+            const unsigned v0 = i * res_y + j, v1 = v0 + 1, v2 = v0 + res_y, v3 = v2 + 1;
+            if ((i % 2) == (j % 2)) {
+                F.push_back({v0, v1, v3});
+                F.push_back({v0, v3, v2});
+            } else {
+                F.push_back({v0, v1, v2});
+                F.push_back({v1, v3, v2});
+            }
+        }
+}
+
+// crates/ppf-cts-core/src/kernels/scene_build/transform.rs:97-120
+std::vector<unsigned> grab(const std::vector<Vec3d> &V, Vec3d dir, double eps) {
+    std::vector<unsigned> out;
+    double max_dot = -1e300;
+    for (auto &v : V) max_dot = std::max(max_dot, v[0] * dir[0] + v[1] * dir[1] + v[2] * dir[2]);
+    for (unsigned i = 0; i < V.size(); ++i)
+        if (V[i][0] * dir[0] + V[i][1] * dir[1] + V[i][2] * dir[2] > max_dot - eps) out.push_back(i);
+    return out;
+}
+
+static std::map<std::string, double> tri_defaults() { // params.rs:295-420 (ObjectKind::Tri)
+    return {{"model", 2.0 /* baraff-witkin */}, {"density", 1.0}, {"young-mod", 1000.0}, {"poiss-rat", 0.35},
+            {"bend", 10.0}, {"shrink-x", 1.0}, {"shrink-y", 1.0}, {"contact-gap", 1e-3}, {"contact-offset", 0.0},
+            {"strain-limit", 0.0}, {"friction", 0.0}, {"pressure", 0.0}};
+}
+
+// The twist family (examples/twist.ipynb, examples/large-twist.ipynb): one cylinder, both end
+// rings pinned with spin -> scale -> move_by applied in declaration order.
+static SceneSpec twist_scene(const std::string &name, double r, double half_len, unsigned n, double bend, double gap,
+                             double young, double poiss, double density, double ang_vel, double move_delta,
+                             double t_end, double scale_rate, unsigned max_nnz, const char *friction_mode, int frames) {
+    SceneSpec s;
+    s.name = name;
+    ShellObject o;
+    gen_cylinder(r, -half_len, half_len, n, o.vert, o.tri);
+    o.param = tri_defaults();
+    o.param["bend"] = bend;
+    o.param["contact-gap"] = gap;
+    o.param["young-mod"] = young;
+    o.param["poiss-rat"] = poiss;
+    o.param["density"] = density;
+    const double scale = 1.0 - t_end * scale_rate;
+    for (int side = 0; side < 2; ++side) {
+        const double sg = side == 0 ? -1.0 : 1.0;
+        Pin p;
+        p.index = grab(o.vert, Vec3d{sg, 0, 0});
+        PinOp spin;  spin.kind = PinOp::Spin;  spin.axis = Vec3d{-sg, 0, 0}; spin.angular_velocity = ang_vel;
+        PinOp scl;   scl.kind = PinOp::Scale;  scl.factor = scale; scl.t_start = 0; scl.t_end = t_end;
+        PinOp mv;    mv.kind = PinOp::MoveBy;  mv.delta = Vec3d{-sg * move_delta, 0, 0}; mv.t_start = 0; mv.t_end = t_end;
+        p.ops = {spin, scl, mv};
+        o.pins.push_back(p);
+    }
+    s.objects.push_back(o);
+    s.args.dt = 1.0 / 60.0;
+    s.args.frames = frames;
+    s.args.gravity = Vec3d{0, 0, 0};
+    s.args.csrmat_max_nnz = max_nnz;
+    s.args.friction_mode = friction_mode;
+    return s;
+}
+
+SceneSpec make_scene(const std::string &name, unsigned n) {
+    if (name == "twist") // examples/twist.ipynb
+        return twist_scene(name, 0.5, 1.0, n ? n : 360, 500.0, 4e-3, 1e4, 0.35, 1.0, 360.0, 0.2, 10.0, 0.01, 35000000u, "min", 430);
+    if (name == "large-twist") // examples/large-twist.ipynb (headline)
+        return twist_scene(name, 0.9, 1.75, n ? n : 1410, 500.0 / 3.5, 1.75e-3, 1e4, 0.25, 3.5, 180.0, 0.5, 16.66, 0.015,
+                           160000000u, "max", 2000);
+    if (name == "fast-twist") { // small, contact-rich within ~1 s: test scene (same family, faster spin, larger gap)
+        unsigned nn = n ? n : 48;
+        SceneSpec s = twist_scene(name, 0.5, 1.0, nn, 500.0, 2.0 / nn * 0.35, 1e4, 0.35, 1.0, 720.0, 0.2, 10.0, 0.01, 4000000u, "min", 120);
+        return s;
+    }
+    if (name == "hang") { // examples/hang.ipynb
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_square(n ? n : 128, 2.0, Vec3d{1, 0, 0}, Vec3d{0, 1, 0}, o.vert, o.tri);
+        o.param = tri_defaults();
+        o.param["strain-limit"] = 0.01;
+        o.param["young-mod"] = 100.0;
+        o.param["bend"] = 1.0;
+        Pin p;
+        auto a = grab(o.vert, Vec3d{-1, 1, 0}), b = grab(o.vert, Vec3d{1, 1, 0});
+        p.index = a;
+        p.index.insert(p.index.end(), b.begin(), b.end());
+        o.pins.push_back(p);
+        s.objects.push_back(o);
+        s.args.frames = 200;
+        const double jitter = 0.35;
+        s.args.gravity_y_keys = {{0.0, -9.8}, {1.0, -9.8}, {1.0 + jitter, 9.8}, {2.0, -9.8}};
+        return s;
+    }
+    if (name == "sheet") { // free-hanging sheet without strain limit: elastic-only smoke scene
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_square(n ? n : 32, 2.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+        o.param = tri_defaults();
+        Pin p;
+        auto a = grab(o.vert, Vec3d{-1, 0, -1}), b = grab(o.vert, Vec3d{1, 0, -1});
+        p.index = a;
+        p.index.insert(p.index.end(), b.begin(), b.end());
+        o.pins.push_back(p);
+        s.objects.push_back(o);
+        s.args.frames = 60;
+        s.args.dt = 1e-2;
+        return s;
+    }
+    throw std::runtime_error("unknown scene: " + name);
+}
+
+// ---- pin operations: scene.rs:2747-2870 + pin_apply.rs:27-160 (f64 math, f32 in/out) ----
+static double progress_at(double time, double t0, double t1, bool smooth) {
+    const double den = t1 - t0;
+    const double raw = den != 0.0 ? (time - t0) / den : 0.0;
+    return smooth ? raw * raw * (3.0 - 2.0 * raw) : raw;
+}
+static bool apply_pin_op(const PinOp &op, Vec3f &pos, double time) {
+    const double p[3] = {pos[0], pos[1], pos[2]};
+    double r[3] = {0, 0, 0};
+    switch (op.kind) {
+    case PinOp::MoveBy: {
+        if (time < op.t_start) return false;
+        const double prog = time >= op.t_end ? 1.0 : progress_at(time, op.t_start, op.t_end, op.smooth);
+        // delta is stored as f32 per vertex in the reference (scene.rs:2769-2774)
+        for (int k = 0; k < 3; ++k) r[k] = p[k] + double(float(op.delta[k])) * prog;
+        break;
+    }
+    case PinOp::Spin: {
+        const double t_eff = std::min(time, op.t_end) - op.t_start;
+        const double angle = double(float(op.angular_velocity)) * (M_PI / 180.0) * t_eff;
+        if (angle <= 0.0) return false;
+        const double c[3] = {double(float(op.center[0])), double(float(op.center[1])), double(float(op.center[2]))};
+        const double ax0[3] = {double(float(op.axis[0])), double(float(op.axis[1])), double(float(op.axis[2]))};
+        const double an = std::sqrt(ax0[0] * ax0[0] + ax0[1] * ax0[1] + ax0[2] * ax0[2]);
+        const double inv = an > 0.0 ? 1.0 / an : 0.0;
+        const double ax[3] = {ax0[0] * inv, ax0[1] * inv, ax0[2] * inv};
+        const double ct = std::cos(angle), st = std::sin(angle), omc = 1.0 - ct;
+        const double px = p[0] - c[0], py = p[1] - c[1], pz = p[2] - c[2];
+        const double cx = ax[1] * pz - ax[2] * py, cy = ax[2] * px - ax[0] * pz, cz = ax[0] * py - ax[1] * px;
+        const double dp = px * ax[0] + py * ax[1] + pz * ax[2];
+        r[0] = px * ct + cx * st + ax[0] * dp * omc + c[0];
+        r[1] = py * ct + cy * st + ax[1] * dp * omc + c[1];
+        r[2] = pz * ct + cz * st + ax[2] * dp * omc + c[2];
+        break;
+    }
+    case PinOp::Scale: {
+        if (time < op.t_start) return false;
+        double cur;
+        const double target = double(float(op.factor));
+        if (time >= op.t_end) cur = target;
+        else cur = 1.0 + (target - 1.0) * progress_at(time, op.t_start, op.t_end, op.smooth);
+        for (int k = 0; k < 3; ++k) {
+            const double c = double(float(op.center[k]));
+            r[k] = (p[k] - c) * cur + c;
+        }
+        break;
+    }
+    }
+    pos = Vec3f{float(r[0]), float(r[1]), float(r[2])};
+    return true;
+}
+
+// scene.rs:1944-2130 (fix / pull pins only; collision mesh, spheres, floors, torque are out of scope)
+void make_constraint(Built &b, double time, double prev_time) {
+    b.fix.clear();
+    b.pull.clear();
+    for (auto &pin : b.pins) {
+        if (pin.unpin_time >= 0.0 && time >= pin.unpin_time) continue;
+        const Vec3d &d = b.spec.objects[pin.object].displacement;
+        const Vec3f dx{float(d[0]), float(d[1]), float(d[2])};
+        for (size_t i = 0; i < pin.index.size(); ++i) {
+            bool kinematic = false;
+            Vec3f position = pin.rest[i];
+            for (auto &op : pin.ops) kinematic = apply_pin_op(op, position, time) || kinematic;
+            Vec3f delta{0, 0, 0};
+            if (kinematic) {
+                Vec3f start = pin.rest[i];
+                for (auto &op : pin.ops) apply_pin_op(op, start, prev_time);
+                delta = Vec3f{position[0] - start[0], position[1] - start[1], position[2] - start[2]};
+            }
+            if (pin.pull_w > 0.0) {
+                PpfPullPair pp{};
+                for (int k = 0; k < 3; ++k) pp.position.v[k] = position[k] + dx[k];
+                pp.index = pin.index[i];
+                pp.weight = float(pin.pull_w);
+                b.pull.push_back(pp);
+            } else {
+                PpfFixPair fp{};
+                for (int k = 0; k < 3; ++k) {
+                    fp.position.v[k] = position[k] + dx[k];
+                    fp.step_delta.v[k] = delta[k];
+                }
+                fp.ghat = float(b.spec.args.constraint_ghat);
+                fp.index = pin.index[i];
+                fp.kinematic = kinematic;
+                b.fix.push_back(fp);
+            }
+        }
+    }
+    PpfConstraint &c = b.constraint;
+    c = PpfConstraint{};
+    c.fix.data = b.fix.data();
+    c.fix.size = c.fix.allocated = (unsigned)b.fix.size();
+    c.pull.data = b.pull.data();
+    c.pull.size = c.pull.allocated = (unsigned)b.pull.size();
+}
+
+// scene.rs update_param: time-varying session params (only gravity keyframes are needed here)
+void update_param(Built &b, double time) {
+    const auto &keys = b.spec.args.gravity_y_keys;
+    if (keys.empty()) return;
+    double g = keys.back().second;
+    if (time <= keys.front().first) g = keys.front().second;
+    else
+        for (size_t i = 0; i + 1 < keys.size(); ++i)
+            if (time >= keys[i].first && time < keys[i + 1].first) {
+                const double w = (time - keys[i].first) / (keys[i + 1].first - keys[i].first);
+                g = keys[i].second * (1.0 - w) + keys[i + 1].second * w;
+                break;
+            }
+    b.param.gravity.v[1] = float(g);
+}
+
+} // namespace ppfh
