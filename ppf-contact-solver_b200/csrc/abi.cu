@@ -1,0 +1,461 @@
+// abi.cu -- the exported C ABI (include/ppf_abi.h) of the B200 backend.
+//
+// Each extern "C" function replaces the same-named entry point of the reference backend
+// (crates/ppf-cts-solver/src/cpp/main/main.cu:1658-2350, cited per function in ppf_abi.h).
+// There is no CPU fallback: without a CUDA device initialize() stamps a fatal code and exits,
+// exactly like the reference (main.cu:1879-1893).
+#include "backend.hpp"
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+
+namespace ppf {
+State g;
+unsigned long long g_launches = 0;
+}
+using namespace ppf;
+
+extern "C" {
+__attribute__((visibility("default"))) unsigned char g_ppf_fatal_code = 0;
+__attribute__((visibility("default"))) char g_ppf_fatal_detail[512] = {0};
+// weak fallback; the host's #[no_mangle] print_rust wins when present (stub.cpp:8)
+__attribute__((weak, visibility("default"))) void print_rust(const char *msg) { (void)msg; }
+}
+
+namespace ppf {
+
+void log_info(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    print_rust(buf);
+}
+
+[[noreturn]] void fatal(unsigned char code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_ppf_fatal_detail, sizeof(g_ppf_fatal_detail), fmt, ap);
+    va_end(ap);
+    g_ppf_fatal_code = code;
+    fprintf(stderr, "PPF FATAL (%u): %s\n", (unsigned)code, g_ppf_fatal_detail);
+    fflush(stderr);
+    exit(1); // never abort(): the host's atexit hook reads the code (main/fatal.hpp:17-24)
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side maintenance kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_clear_pin_index(unsigned *fix_index, unsigned *pull_index, unsigned n) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { fix_index[i] = 0; pull_index[i] = 0; }
+}
+__global__ void k_set_fix_index(const PpfFixPair *fix, unsigned n, unsigned *fix_index) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fix_index[fix[i].index] = i + 1;
+}
+__global__ void k_set_pull_index(const PpfPullPair *pull, unsigned n, unsigned *pull_index) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pull_index[pull[i].index] = i + 1;
+}
+__global__ void k_fixed_flags(const unsigned *fix_index, const uint4 *face, const uint2 *edge, const uint4 *hinge,
+                              unsigned nv, unsigned nf, unsigned ne, unsigned nh, unsigned char *vfixed,
+                              unsigned char *ffixed, unsigned char *efixed, unsigned char *hfixed) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nv) vfixed[i] = fix_index[i] > 0;
+    if (i < nf) { uint4 f = face[i]; ffixed[i] = fix_index[f.x] > 0 && fix_index[f.y] > 0 && fix_index[f.z] > 0; }
+    if (i < ne) { uint2 e = edge[i]; efixed[i] = fix_index[e.x] > 0 && fix_index[e.y] > 0; }
+    if (i < nh) { uint4 h = hinge[i]; hfixed[i] = fix_index[h.x] > 0 && fix_index[h.y] > 0 && fix_index[h.z] > 0 && fix_index[h.w] > 0; }
+}
+
+// reference: update_constraint rebuilds fix_index / pull_index and every element's `fixed`
+// flag on the HOST and re-uploads all prop arrays (main.cu:2011-2076); here only the pin
+// arrays cross PCIe and the flags are recomputed on the device.
+void apply_constraint(State &s, const PpfConstraint *c) {
+    cudaStream_t q = s.stream;
+    s.host.constraint = *c;
+    s.nfix = c->fix.size;
+    s.npull = c->pull.size;
+    s.fix.upload(c->fix.data, c->fix.size, q);
+    s.pull.upload(c->pull.data, c->pull.size, q);
+    k_clear_pin_index<<<div_up(s.nv, 256), 256, 0, q>>>(s.fix_index.p, s.pull_index.p, s.nv);
+    if (s.nfix) k_set_fix_index<<<div_up(s.nfix, 256), 256, 0, q>>>(s.fix.p, s.nfix, s.fix_index.p);
+    if (s.npull) k_set_pull_index<<<div_up(s.npull, 256), 256, 0, q>>>(s.pull.p, s.npull, s.pull_index.p);
+    recompute_fixed_flags(s);
+    LAUNCH_COUNT(3);
+    CUDA_OK(cudaStreamSynchronize(q)); // the caller may free/reuse its arrays after we return
+}
+
+void recompute_fixed_flags(State &s) {
+    unsigned n = std::max(std::max(s.nv, s.nf), std::max(s.ne, s.nh));
+    k_fixed_flags<<<div_up(n, 256), 256, 0, s.stream>>>(s.fix_index.p, s.face.p, s.edge.p, s.hinge.p, s.nv, s.nf, s.ne,
+                                                       s.nh, s.vfixed.p, s.ffixed.p, s.efixed.p, s.hfixed.p);
+    LAUNCH_COUNT(1);
+}
+
+static void flatten_vecvec(const PpfVecVecU32 &vv, unsigned rows, std::vector<unsigned> &off, std::vector<unsigned> &idx) {
+    off.assign(rows + 1, 0);
+    idx.clear();
+    if (vv.size == 0) return;
+    for (unsigned i = 0; i <= rows && i <= vv.size; ++i) off[i] = vv.offset[i];
+    for (unsigned i = vv.size + 1; i <= rows; ++i) off[i] = off[vv.size];
+    idx.assign(vv.data, vv.data + off[rows]);
+}
+
+void upload_dataset(State &s) {
+    const PpfDataSet &d = s.host;
+    const PpfParamSet &prm = *s.param;
+    cudaStream_t q = s.stream;
+    const unsigned nv = s.nv = d.vertex.curr.size;
+    const unsigned nf = s.nf = d.mesh.mesh.face.size;
+    const unsigned ne = s.ne = d.mesh.mesh.edge.size;
+    const unsigned nh = s.nh = d.mesh.mesh.hinge.size;
+    s.nsv = d.surface_vert_count;
+
+    // ---- scope gate: refuse loudly what this backend does not implement (DESIGN.md "out of scope") ----
+    if (d.rod_count) fatal(4, "B200 backend: rod elements are not implemented (rod_count=%u)", d.rod_count);
+    if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
+    if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
+    if (d.constraint.stitch.size || d.constraint.sphere.size || d.constraint.floor.size || d.constraint.mesh.vertex.size ||
+        d.constraint.torque_vertices.size)
+        fatal(4, "B200 backend: stitches / analytic colliders / static collision meshes / torque pins are not implemented");
+    if (d.translation_lock.size) fatal(4, "B200 backend: translation/rotation locks are not implemented");
+    for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
+        if (d.grain_inv_inertia.data[i] > 0.0f) fatal(4, "B200 backend: SAND grains are not implemented");
+    if (prm.barrier != PPF_BARRIER_CUBIC) fatal(4, "B200 backend: only the cubic barrier is implemented");
+    if (nf != d.shell_face_count || s.nsv != nv) fatal(4, "B200 backend: only shell scenes are implemented");
+    if (prm.fix_xz != 0.0f) fatal(4, "B200 backend: fix-xz is not implemented");
+    for (unsigned i = 0; i < d.param_arrays.face.size; ++i) {
+        const PpfFaceParam &fp = d.param_arrays.face.data[i];
+        if (fp.model != PPF_MODEL_BARAFFWITKIN) fatal(4, "B200 backend: only the Baraff-Witkin shell model is implemented");
+        if (fp.strainlimit > 0.0f) fatal(4, "B200 backend: strain limiting is not implemented yet");
+        if (fp.pressure > 0.0f || fp.deform_damping > 0.0f || fp.bend_damping > 0.0f)
+            fatal(4, "B200 backend: inflation pressure / Rayleigh damping are not implemented");
+    }
+    if (d.face_hess_slots.size != 9u * nf || d.hinge_hess_slots.size != 16u * nh)
+        fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
+
+    // ---- positions ----
+    std::vector<float4> tmp4(nv);
+    for (unsigned i = 0; i < nv; ++i) tmp4[i] = make_float4(d.vertex.curr.data[i].v[0], d.vertex.curr.data[i].v[1], d.vertex.curr.data[i].v[2], 0.f);
+    s.curr.upload(tmp4.data(), nv, q);
+    CUDA_OK(cudaStreamSynchronize(q));
+    for (unsigned i = 0; i < nv; ++i) tmp4[i] = make_float4(d.vertex.prev.data[i].v[0], d.vertex.prev.data[i].v[1], d.vertex.prev.data[i].v[2], 0.f);
+    s.prev.upload(tmp4.data(), nv, q);
+    CUDA_OK(cudaStreamSynchronize(q));
+    s.eval_x.reserve(nv); s.target.reserve(nv); s.x_old.reserve(nv); s.velocity.reserve(nv);
+
+    // ---- topology ----
+    {
+        std::vector<uint4> f4(nf), h4(nh);
+        std::vector<uint2> e2(ne);
+        for (unsigned i = 0; i < nf; ++i) f4[i] = make_uint4(d.mesh.mesh.face.data[i].v[0], d.mesh.mesh.face.data[i].v[1], d.mesh.mesh.face.data[i].v[2], 0);
+        for (unsigned i = 0; i < nh; ++i) h4[i] = make_uint4(d.mesh.mesh.hinge.data[i].v[0], d.mesh.mesh.hinge.data[i].v[1], d.mesh.mesh.hinge.data[i].v[2], d.mesh.mesh.hinge.data[i].v[3]);
+        for (unsigned i = 0; i < ne; ++i) e2[i] = make_uint2(d.mesh.mesh.edge.data[i].v[0], d.mesh.mesh.edge.data[i].v[1]);
+        s.face.upload(f4.data(), nf, q); s.hinge.upload(h4.data(), nh, q); s.edge.upload(e2.data(), ne, q);
+        CUDA_OK(cudaStreamSynchronize(q));
+        std::vector<unsigned> off, idx;
+        flatten_vecvec(d.mesh.neighbor.vertex.face, nv, off, idx);
+        s.vf_off.upload(off.data(), off.size(), q); s.vf_idx.upload(idx.data(), idx.size(), q);
+        CUDA_OK(cudaStreamSynchronize(q));
+        flatten_vecvec(d.mesh.neighbor.vertex.edge, nv, off, idx);
+        s.ve_off.upload(off.data(), off.size(), q); s.ve_idx.upload(idx.data(), idx.size(), q);
+        CUDA_OK(cudaStreamSynchronize(q));
+        flatten_vecvec(d.mesh.neighbor.edge.face, ne, off, idx);
+        s.ef_off.upload(off.data(), off.size(), q); s.ef_idx.upload(idx.data(), idx.size(), q);
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
+    // ---- resolved per-primitive parameters ----
+    {
+        std::vector<float4> v(nv), e(ne), f(nf), fm(nf), ir(nf), hm(nh);
+        std::vector<float> va(nv), hs(nh);
+        std::vector<unsigned char> vc(nv), fsk(nf);
+        for (unsigned i = 0; i < nv; ++i) {
+            const PpfVertexProp &p = d.prop.vertex.data[i];
+            PpfVertexParam vp{0, 0, 0};
+            if (p.param_index < d.param_arrays.vertex.size) vp = d.param_arrays.vertex.data[p.param_index];
+            v[i] = make_float4(vp.ghat, vp.offset, vp.friction, p.mass);
+            va[i] = p.area;
+            vc[i] = p.collider;
+        }
+        for (unsigned i = 0; i < ne; ++i) {
+            const PpfEdgeProp &p = d.prop.edge.data[i];
+            const PpfEdgeParam &ep = d.param_arrays.edge.data[p.param_index];
+            e[i] = make_float4(ep.ghat, ep.offset, ep.friction, p.mass);
+        }
+        for (unsigned i = 0; i < nf; ++i) {
+            const PpfFaceProp &p = d.prop.face.data[i];
+            const PpfFaceParam &fp = d.param_arrays.face.data[p.param_index];
+            f[i] = make_float4(fp.ghat, fp.offset, fp.friction, p.mass);
+            fm[i] = make_float4(fp.mu, fp.lambda, p.mass, 0.0f);
+            const PpfMat2x2f &m = d.inv_rest2x2.data[i];
+            ir[i] = make_float4(m.m[0], m.m[1], m.m[2], m.m[3]);
+            fsk[i] = p.rest_excluded || p.collider;
+        }
+        for (unsigned i = 0; i < nh; ++i) {
+            const PpfHingeProp &p = d.prop.hinge.data[i];
+            const PpfHingeParam &hp = d.param_arrays.hinge.data[p.param_index];
+            // energy.cu:463-517
+            float areal = 0.0f;
+            int cnt = 0;
+            for (int k = 0; k < 4; ++k) {
+                const PpfVertexProp &vp = d.prop.vertex.data[d.mesh.mesh.hinge.data[i].v[k]];
+                if (vp.area > 0.0f) { areal += vp.mass / vp.area; ++cnt; }
+            }
+            if (cnt > 0) areal /= cnt;
+            float bend_dir = hp.bend;
+            if (!(p.uv_edge_sin2 < 0.0f)) bend_dir = hp.bend + hp.bend_warp * p.uv_edge_sin2 + hp.bend_weft * (1.0f - p.uv_edge_sin2);
+            const float BEND_SCALE = 1.28e-5f;
+            float k = (p.area > 1e-12f) ? BEND_SCALE * bend_dir * (p.length * p.length / p.area) * areal : 0.0f;
+            if (p.collider || (d.mesh.type.hinge.size > i && (d.mesh.type.hinge.data[i] & 1))) k = 0.0f;
+            hs[i] = k;
+            hm[i] = make_float4(p.length, p.area, p.rest_angle, bend_dir);
+        }
+        s.vcp.upload(v.data(), nv, q); s.ecp.upload(e.data(), ne, q); s.fcp.upload(f.data(), nf, q);
+        s.fmat.upload(fm.data(), nf, q); s.inv_rest.upload(ir.data(), nf, q); s.hmat.upload(hm.data(), nh, q);
+        s.varea.upload(va.data(), nv, q); s.hinge_stiff.upload(hs.data(), nh, q);
+        s.vcollider.upload(vc.data(), nv, q); s.fskip.upload(fsk.data(), nf, q);
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
+    s.fix_index.reserve(nv); s.pull_index.reserve(nv);
+    s.vfixed.reserve(nv); s.ffixed.reserve(nf); s.efixed.reserve(ne); s.hfixed.reserve(nh);
+    s.fix.reserve(std::max(1u, d.constraint.fix.allocated)); s.pull.reserve(std::max(1u, d.constraint.pull.allocated));
+
+    // ---- fixed matrix ----
+    {
+        const PpfVecVecU32 &t = d.fixed_index_table;
+        s.fixed_nnz = t.offset[t.size];
+        s.fx_off.upload(t.offset, t.size + 1, q);
+        s.fx_col.upload(t.data, s.fixed_nnz, q);
+        s.fx_val.reserve(size_t(9) * s.fixed_nnz); s.fx_el.reserve(size_t(9) * s.fixed_nnz);
+        s.face_slots.upload(d.face_hess_slots.data, d.face_hess_slots.size, q);
+        s.hinge_slots.upload(d.hinge_hess_slots.data, d.hinge_hess_slots.size, q);
+        std::vector<unsigned> ds(nv);
+        for (unsigned i = 0; i < nv; ++i) {
+            if (t.offset[i + 1] == t.offset[i] || t.data[t.offset[i]] != i) fatal(4, "fixed_index_table row %u lacks its diagonal", i);
+            ds[i] = t.offset[i];
+        }
+        s.fx_diag_slot.upload(ds.data(), nv, q);
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
+    s.diag.reserve(size_t(9) * nv); s.force.reserve(size_t(3) * nv); s.dx.reserve(size_t(3) * nv);
+    s.counters.reserve(64); s.scalars.reserve(64);
+    s.counters.zero(64, q); s.scalars.zero(64, q);
+    CUDA_OK(cudaMallocHost(&s.h_pinned, 256 * sizeof(float)));
+    s.isect_records.reserve(PPF_MAX_INTERSECTION_RECORDS);
+    s.h_isect.resize(PPF_MAX_INTERSECTION_RECORDS);
+    s.dyn_cap = prm.csrmat_max_nnz;
+    s.carried_offset.assign(nv + 1, 0);
+    s.carried_index.clear();
+
+    apply_constraint(s, &d.constraint);
+}
+
+} // namespace ppf
+
+// ---------------------------------------------------------------------------------------------
+// exported entry points
+// ---------------------------------------------------------------------------------------------
+#define PPF_EXPORT extern "C" __attribute__((visibility("default")))
+
+PPF_EXPORT unsigned char ppf_fatal_code(void) { return g_ppf_fatal_code; }
+PPF_EXPORT const char *ppf_fatal_detail(void) { return g_ppf_fatal_detail; }
+PPF_EXPORT void set_log_path(const char *data_dir) { simplelog_set_path(data_dir); }
+
+PPF_EXPORT bool initialize(PpfDataSet *dataset, PpfParamSet *param) {
+    int num_device = 0;
+    cudaError_t e = cudaGetDeviceCount(&num_device);
+    if (e != cudaSuccess || num_device == 0)
+        fatal(PPF_FATAL_CUDA_DRIVER, "no CUDA device is visible to this process (%s); this backend ships sm_100a code only and has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    cudaDeviceProp props;
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaGetDeviceProperties(&props, dev));
+    log_info("cuda: device %d is %s, compute capability %d.%d, %d SMs", dev, props.name, props.major, props.minor, props.multiProcessorCount);
+    if (props.major != 10) fatal(PPF_FATAL_CUDA_DRIVER, "this backend is built for sm_100a (B200) only; found compute capability %d.%d", props.major, props.minor);
+    State &s = g;
+    if (!s.stream) CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    s.host = *dataset;
+    s.param = param;
+    ScopeLog logging("initialize");
+    upload_dataset(s);
+    s.initialized = true;
+    bool result = true;
+    if (!param->disable_contact) {
+        logging.push("lbvh build");
+        bvh_build(s, s.bvh_face, 0, s.curr.p);
+        bvh_build(s, s.bvh_edge, 1, s.curr.p);
+        bvh_build(s, s.bvh_vert, 2, s.curr.p);
+        logging.pop();
+        logging.push("check intersection");
+        bvh_refit(s, s.bvh_face, 0, s.prev.p, s.prev.p, 1.0f);
+        bvh_refit(s, s.bvh_edge, 1, s.prev.p, s.prev.p, 1.0f);
+        bvh_refit(s, s.bvh_vert, 2, s.prev.p, s.prev.p, 1.0f);
+        bool ok_prev = check_intersection(s, s.prev.p, *param);
+        bvh_refit(s, s.bvh_face, 0, s.curr.p, s.curr.p, 1.0f);
+        bvh_refit(s, s.bvh_edge, 1, s.curr.p, s.curr.p, 1.0f);
+        bvh_refit(s, s.bvh_vert, 2, s.curr.p, s.curr.p, 1.0f);
+        bool ok_curr = ok_prev && check_intersection(s, s.curr.p, *param);
+        if (!ok_prev || !ok_curr) {
+            logging.message("### intersection detected");
+            snprintf(g_ppf_fatal_detail, sizeof(g_ppf_fatal_detail),
+                     "the scene is already self-intersecting at t=0; the solver advances from a separated configuration and cannot untangle one");
+            g_ppf_fatal_code = PPF_FATAL_INIT_INTERSECTION;
+            result = false;
+        }
+        logging.pop();
+    }
+    return result;
+}
+
+PPF_EXPORT void advance(PpfStepResult *result) {
+    if (!g.initialized) fatal(4, "advance() called before initialize()");
+    step_advance(g, result);
+}
+
+__global__ void k_unpack4(const float4 *src, float *dst, unsigned n) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 v = src[i]; dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; }
+}
+
+PPF_EXPORT void fetch(void) {
+    State &s = g;
+    cudaStream_t q = s.stream;
+    const unsigned nv = s.nv;
+    // reuse dx as staging (3 floats per vertex)
+    k_unpack4<<<div_up(nv, 256), 256, 0, q>>>(s.curr.p, s.dx.p, nv);
+    CUDA_OK(cudaMemcpyAsync(s.host.vertex.curr.data, s.dx.p, size_t(12) * nv, cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    k_unpack4<<<div_up(nv, 256), 256, 0, q>>>(s.prev.p, s.dx.p, nv);
+    CUDA_OK(cudaMemcpyAsync(s.host.vertex.prev.data, s.dx.p, size_t(12) * nv, cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    LAUNCH_COUNT(2);
+}
+// plasticity is out of scope, so the device never changes inv_rest or the rest angles: the host
+// arrays already hold what the reference would copy back (main.cu:1939-1968)
+PPF_EXPORT void fetch_inv_rest(void) {}
+PPF_EXPORT void fetch_rest_angles(void) {}
+
+PPF_EXPORT void fetch_dyn_counts(unsigned *n_value, unsigned *n_offset) {
+    State &s = g;
+    if (s.dyn_valid) build_fetch_pattern(s, s.carried_index, s.carried_offset), s.dyn_valid = false;
+    *n_offset = s.nv + 1;
+    *n_value = s.carried_offset.empty() ? 0 : s.carried_offset[s.nv];
+}
+PPF_EXPORT void fetch_dyn(unsigned *index, PpfMat3x3f *value, unsigned *offset) {
+    (void)value; // unused by the reference as well (csrmat.cu:136-144)
+    State &s = g;
+    if (s.dyn_valid) build_fetch_pattern(s, s.carried_index, s.carried_offset), s.dyn_valid = false;
+    memcpy(offset, s.carried_offset.data(), sizeof(unsigned) * (s.nv + 1));
+    if (!s.carried_index.empty()) memcpy(index, s.carried_index.data(), sizeof(unsigned) * s.carried_index.size());
+}
+PPF_EXPORT void update_dyn(unsigned *index, unsigned *offset) {
+    // The carried pattern only seeds the reference's slab reservation (csrmat.cu:146-153); this
+    // backend rebuilds the dynamic pattern from the detected pairs every assembly, so the restored
+    // pattern is kept solely so that fetch_dyn round-trips it until the next advance().
+    State &s = g;
+    s.carried_offset.assign(offset, offset + s.nv + 1);
+    s.carried_index.assign(index, index + offset[s.nv]);
+    s.dyn_valid = false;
+}
+
+PPF_EXPORT void update_constraint(const PpfConstraint *constraint) {
+    if (constraint->stitch.size || constraint->sphere.size || constraint->floor.size || constraint->mesh.vertex.size ||
+        constraint->torque_vertices.size)
+        fatal(4, "B200 backend: stitches / analytic colliders / static collision meshes / torque pins are not implemented");
+    apply_constraint(g, constraint);
+}
+PPF_EXPORT void update_rest_shape(const PpfRestShapeUpdate *update) {
+    State &s = g;
+    if (update->inv_rest3x3.size || update->exclude_tet.size) fatal(4, "B200 backend: tetrahedral rest shapes are not implemented");
+    if (update->inv_rest2x2.size) {
+        std::vector<float4> ir(update->inv_rest2x2.size);
+        for (unsigned i = 0; i < update->inv_rest2x2.size; ++i) {
+            const PpfMat2x2f &m = update->inv_rest2x2.data[i];
+            ir[i] = make_float4(m.m[0], m.m[1], m.m[2], m.m[3]);
+        }
+        s.inv_rest.upload(ir.data(), ir.size(), s.stream);
+        CUDA_OK(cudaStreamSynchronize(s.stream));
+    }
+    if (update->exclude_face.size) {
+        std::vector<unsigned char> fsk(s.nf);
+        for (unsigned i = 0; i < s.nf; ++i) {
+            const bool ex = i < update->exclude_face.size && update->exclude_face.data[i] != 0;
+            s.host.prop.face.data[i].rest_excluded = ex;
+            fsk[i] = ex || s.host.prop.face.data[i].collider;
+        }
+        s.fskip.upload(fsk.data(), s.nf, s.stream);
+        CUDA_OK(cudaStreamSynchronize(s.stream));
+    }
+}
+
+__global__ void k_override_velocity(const unsigned *idx, unsigned n, const float4 *curr, float4 *prev, float dx, float dy, float dz) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { unsigned v = idx[i]; float4 c = curr[v]; prev[v] = make_float4(c.x - dx, c.y - dy, c.z - dz, 0.f); }
+}
+PPF_EXPORT void override_velocity(const unsigned *indices, unsigned count, float vx, float vy, float vz, float dt) {
+    if (count == 0 || dt <= 0.0f) return;
+    State &s = g;
+    DBuf<unsigned> d;
+    d.upload(indices, count, s.stream);
+    k_override_velocity<<<div_up(count, 256), 256, 0, s.stream>>>(d.p, count, s.curr.p, s.prev.p, vx * dt, vy * dt, vz * dt);
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    d.free();
+}
+PPF_EXPORT void gather_current_positions(const unsigned *indices, unsigned count, float *out) {
+    if (count == 0) return;
+    State &s = g;
+    std::vector<float4> h(s.nv);
+    CUDA_OK(cudaMemcpy(h.data(), s.curr.p, sizeof(float4) * s.nv, cudaMemcpyDeviceToHost));
+    for (unsigned i = 0; i < count; ++i) { out[3 * i] = h[indices[i]].x; out[3 * i + 1] = h[indices[i]].y; out[3 * i + 2] = h[indices[i]].z; }
+}
+__global__ void k_override_angular(const unsigned *idx, unsigned n, const float4 *curr, float4 *prev, float wx, float wy, float wz,
+                                   float cx, float cy, float cz, float dt) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned v = idx[i];
+    float4 c = curr[v], p = prev[v];
+    float rx = c.x - cx, ry = c.y - cy, rz = c.z - cz;
+    float vwx = wy * rz - wz * ry, vwy = wz * rx - wx * rz, vwz = wx * ry - wy * rx;
+    prev[v] = make_float4(p.x - (vwx * dt), p.y - (vwy * dt), p.z - (vwz * dt), 0.f);
+}
+PPF_EXPORT void override_angular_velocity(const unsigned *indices, unsigned count, float wx, float wy, float wz, float cx,
+                                          float cy, float cz, float dt) {
+    if (count == 0 || dt <= 0.0f) return;
+    State &s = g;
+    DBuf<unsigned> d;
+    d.upload(indices, count, s.stream);
+    k_override_angular<<<div_up(count, 256), 256, 0, s.stream>>>(d.p, count, s.curr.p, s.prev.p, wx, wy, wz, cx, cy, cz, dt);
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    d.free();
+}
+PPF_EXPORT void init_collision_windows(const unsigned *vert_dmap, unsigned vert_count, const float *windows,
+                                       const unsigned *window_counts, unsigned n_groups) {
+    (void)vert_dmap; (void)vert_count; (void)windows;
+    for (unsigned i = 0; i < n_groups; ++i)
+        if (window_counts[i]) fatal(4, "B200 backend: collision windows are not implemented");
+}
+PPF_EXPORT void refresh_collision_active(float time) { (void)time; }
+
+PPF_EXPORT unsigned fetch_intersection_records(PpfIntersectionRecord *out, unsigned max_count) {
+    State &s = g;
+    unsigned count = std::min(s.h_isect_count, max_count);
+    if (count) memcpy(out, s.h_isect.data(), count * sizeof(PpfIntersectionRecord));
+    return count;
+}
+
+// ---- extensions ----
+PPF_EXPORT void ppf_b200_get_stats(PpfB200Stats *out) {
+    const State &s = g;
+    memset(out, 0, sizeof(*out));
+    out->ms_advance = s.tm.ms_advance; out->ms_lbvh_build = s.tm.ms_lbvh_build; out->ms_assembly = s.tm.ms_assembly;
+    out->ms_contact = s.tm.ms_contact; out->ms_linsolve = s.tm.ms_linsolve; out->ms_spmv = s.tm.ms_spmv;
+    out->ms_aabb_update = s.tm.ms_aabb_update; out->ms_line_search = s.tm.ms_line_search;
+    out->n_advance = s.tm.n_advance; out->n_newton = s.tm.n_newton; out->n_cg_iter = s.tm.n_cg_iter; out->n_spmv = s.tm.n_spmv;
+    out->n_kernel_launches = g_launches;
+    out->spmv_n_row = s.spmv_n_row; out->spmv_n_off = s.spmv_n_off;
+    for (int k = 0; k < 4; ++k) out->last_num_contact[k] = s.last_num_contact[k];
+}
+PPF_EXPORT void ppf_b200_reset_stats(void) { g.tm = Timers{}; g_launches = 0; }

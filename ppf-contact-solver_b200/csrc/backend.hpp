@@ -1,0 +1,203 @@
+// backend.hpp -- device-side state of the B200 backend and the interfaces between its phases.
+//
+// One process owns one dataset (like the reference, main/main.cu:40-44,117-124).  Everything
+// the per-step path touches lives in HBM in layouts chosen for the access pattern, converted
+// once at initialize():
+//   * positions are float4 (x,y,z,0): every random gather is one aligned 16-byte sector-local
+//     load instead of a 12-byte load straddling sectors;
+//   * faces are padded to uint4, edges uint2, hinges uint4;
+//   * per-primitive contact parameters are pre-resolved into float4 (ghat, offset, friction, mass)
+//     so narrow-phase kernels do one gather instead of prop -> param_index -> param chains;
+//   * the topology-fixed matrix keeps the reference's upper-triangle block-CSR (so the slot
+//     tables of the DataSet address it directly); the PCG works on a packed, permuted copy
+//     (pcg.cu) built once per Newton iteration.
+#pragma once
+#include "../../include/ppf_abi.h"
+#include "vecmath.cuh"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+namespace ppf {
+
+// ---- fatal / error handling (reference: main/fatal.hpp:48-89, main/cuda_utils.hpp:54-109) ----
+[[noreturn]] void fatal(unsigned char code, const char *fmt, ...);
+void log_info(const char *fmt, ...);
+#define CUDA_OK(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) ::ppf::fatal(_e == cudaErrorMemoryAllocation ? 2 : 3, "CUDA error %s at %s:%d (%s)", \
+                                            cudaGetErrorString(_e), __FILE__, __LINE__, #expr);        \
+    } while (0)
+
+extern unsigned long long g_launches; // kernels launched by this backend (PpfB200Stats.n_kernel_launches)
+#define LAUNCH_COUNT(n) (::ppf::g_launches += (n))
+
+inline unsigned div_up(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
+
+// grow-only device buffer (steady state performs no cudaMalloc, like the reference's pool)
+template <class T> struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n > cap) {
+            if (p) CUDA_OK(cudaFree(p));
+            size_t want = n + n / 4 + 16;
+            CUDA_OK(cudaMalloc(&p, want * sizeof(T)));
+            cap = want;
+        }
+    }
+    void reserve_keep(size_t n, cudaStream_t s) { // grow preserving contents
+        if (n > cap) {
+            size_t want = n + n / 2 + 16;
+            T *q = nullptr;
+            CUDA_OK(cudaMalloc(&q, want * sizeof(T)));
+            if (p) {
+                CUDA_OK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
+                CUDA_OK(cudaStreamSynchronize(s));
+                CUDA_OK(cudaFree(p));
+            }
+            p = q;
+            cap = want;
+        }
+    }
+    void upload(const T *h, size_t n, cudaStream_t s) {
+        reserve(n);
+        if (n) CUDA_OK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void zero(size_t n, cudaStream_t s) { if (n) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Bvh {
+    unsigned n = 0;             // primitives (leaves); nodes: [0,n-1) internal, [n-1, 2n-1) leaves
+    DBuf<unsigned> morton, morton_sorted, prim, prim_sorted; // prim_sorted[k] = primitive of sorted leaf k
+    DBuf<int2> child;           // per internal node: (left, right) node ids
+    DBuf<int> parent;           // per node
+    DBuf<float4> lo, hi;        // per node AABB (xyz)
+    DBuf<unsigned> flag;        // bottom-up arrival counters
+    DBuf<unsigned char> sort_tmp;
+    size_t sort_tmp_bytes = 0;
+    int root = 0;
+};
+
+struct PairList { // candidate or accepted primitive pairs
+    DBuf<uint2> pairs;
+    unsigned *d_count = nullptr; // device counter
+    unsigned count = 0;          // host copy after a sync
+};
+
+struct Timers {
+    double ms_advance = 0, ms_lbvh_build = 0, ms_assembly = 0, ms_contact = 0, ms_linsolve = 0, ms_spmv = 0,
+           ms_aabb_update = 0, ms_line_search = 0;
+    unsigned long long n_advance = 0, n_newton = 0, n_cg_iter = 0, n_spmv = 0;
+};
+
+struct State {
+    bool initialized = false;
+    cudaStream_t stream = nullptr;
+    PpfDataSet host;       // by-value copy of the caller's DataSet (host pointers inside)
+    PpfParamSet *param = nullptr;
+    unsigned nv = 0, nsv = 0, nf = 0, ne = 0, nh = 0, nfix = 0, npull = 0;
+    unsigned fixed_nnz = 0;
+
+    // geometry / topology
+    DBuf<float4> curr, prev, eval_x, target, x_old, velocity;
+    DBuf<uint4> face, hinge;
+    DBuf<uint2> edge;
+    DBuf<unsigned> vf_off, vf_idx, ve_off, ve_idx, ef_off, ef_idx; // vertex->faces, vertex->edges, edge->faces
+    // per-primitive resolved parameters
+    DBuf<float4> vcp, ecp, fcp;                  // (ghat, offset, friction, mass)
+    DBuf<float> varea;                            // vertex area
+    DBuf<unsigned> fix_index, pull_index;         // per vertex (1-based, 0 = none)
+    DBuf<unsigned char> vfixed, efixed, ffixed, hfixed, vcollider, fskip;
+    DBuf<float4> fmat;                            // per face (mu, lambda, mass, deform_damping)
+    DBuf<float4> inv_rest;                        // per face 2x2
+    DBuf<float4> hmat;                            // per hinge (length, area, rest_angle, bend_dir)
+    DBuf<float> hinge_stiff;                      // per hinge stiffness (energy.cu:510-517), 0 = skip
+    DBuf<PpfFixPair> fix;
+    DBuf<PpfPullPair> pull;
+    // ABI-layout copies kept for fetch_* (plasticity is out of scope, so they never change)
+    // fixed (topology) matrix: upper-triangle block CSR, AoS 3x3 column-major blocks
+    DBuf<unsigned> fx_off, fx_col;
+    DBuf<float> fx_val, fx_el;                    // 9 floats per block: assembled / elastic-only snapshot
+    DBuf<unsigned> face_slots, hinge_slots;
+    DBuf<unsigned> fx_diag_slot;                  // slot of (i,i) per row
+    DBuf<float> diag;                             // C: 9 floats per vertex
+    DBuf<float> force, dx;                        // 3 floats per vertex (ABI order)
+    // dynamic (contact) matrix of the last assembly: CSR over upper-triangle pairs not in the fixed pattern
+    DBuf<unsigned long long> dyn_keys, dyn_keys_sorted;
+    DBuf<unsigned> dyn_off, dyn_col;
+    DBuf<float> dyn_val;
+    unsigned dyn_nnz = 0;
+    unsigned long long dyn_cap = 0;
+    // carried pattern handed through fetch_dyn / update_dyn
+    std::vector<unsigned> carried_index, carried_offset;
+    bool dyn_valid = false;
+
+    Bvh bvh_face, bvh_edge, bvh_vert;
+    PairList cand[4];   // candidates: 0 vertex-face, 1 vertex-edge, 2 vertex-vertex, 3 edge-edge
+    PairList pairs[4];  // accepted contacts of the last assembly (pf, pe, pp, ee)
+    DBuf<unsigned> counters; // device scalars (pair counters etc.)
+    DBuf<float> scalars;     // device float scalars (reductions)
+    float *h_pinned = nullptr; // pinned host scratch
+
+    // intersection records (fetch_intersection_records)
+    DBuf<PpfIntersectionRecord> isect_records;
+    std::vector<PpfIntersectionRecord> h_isect;
+    unsigned h_isect_count = 0;
+
+    Timers tm;
+    unsigned last_num_contact[4] = {0, 0, 0, 0};
+    unsigned long long spmv_n_row = 0, spmv_n_off = 0;
+    std::string log_dir;
+};
+extern State g;
+
+// ---- logging (simplelog.cpp): the reference's SimpleLog side channel (SimpleLog.cpp:86-178) ----
+struct ScopeLog {
+    explicit ScopeLog(const char *name);
+    ~ScopeLog();
+    void push(const char *name);
+    void pop();
+    void mark(const char *name, double value);
+    void message(const char *fmt, ...);
+    struct Impl;
+    Impl *impl;
+};
+void simplelog_set_path(const char *dir);
+void simplelog_set_time(double t);
+
+// ---- phases ----
+void upload_dataset(State &s);                               // abi.cu
+void apply_constraint(State &s, const PpfConstraint *c);     // abi.cu
+void step_advance(State &s, PpfStepResult *result);          // step.cu
+
+// elastic.cu
+void assemble_momentum(State &s, float dt, const PpfParamSet &prm);
+void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
+void recompute_fixed_flags(State &s);
+
+// bvh.cu
+void bvh_build(State &s, Bvh &b, int kind, const float4 *x);      // kind: 0 face, 1 edge, 2 vertex
+void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate);
+
+// contact.cu
+unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed);
+float contact_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap);
+bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm);
+void build_fetch_pattern(State &s, std::vector<unsigned> &index, std::vector<unsigned> &offset);
+
+// pcg.cu
+struct SolveResult { bool ok; unsigned iter; float resid; };
+SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof_mask);
+void apply_dirichlet(State &s);
+
+// prims.cu -- reductions on the backend stream, result returned to the host
+float reduce_max_f(State &s, const float *d, size_t n, float init);
+float reduce_min_f(State &s, const float *d, size_t n, float init);
+unsigned reduce_sum_u(State &s, const unsigned *d, size_t n);
+
+} // namespace ppf

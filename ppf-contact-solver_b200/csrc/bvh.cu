@@ -1,0 +1,202 @@
+// bvh.cu -- LBVH build (once per step) and refit (once per Newton iteration) for faces, edges, vertices.
+//
+// Replaces lbvh::build_{face,edge,vertex}_bvh / update_*_aabb / propagate_aabbs
+// (crates/ppf-cts-solver/src/cpp/lbvh/lbvh.cu:863-1097).  Same tree family (30-bit Morton codes,
+// Karras 2012 radix tree, ties broken by sorted index) and the SAME leaf boxes (swept hull of x0 and
+// x0 + extrapolate*(x1-x0), inflated by 0.5*ghat + offset, lbvh.cu:623-731), but:
+//   * one radix sort (CUB) instead of 8 four-bit passes of 3 kernels each;
+//   * internal boxes are produced by ONE bottom-up kernel (second-arriver-continues with an atomic
+//     flag per node) instead of one launch per tree level plus a D2H copy of the level table;
+//   * no level table / depth pass at all (the reference's compute_depths_kernel is O(n * depth)).
+// Only conservativeness of the boxes matters for parity (the narrow phase decides), so the tree
+// shape is free to differ from the reference's.
+#include "bvh.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace ppf {
+
+__device__ __forceinline__ unsigned expand_bits(unsigned v) {
+    v = (v | (v << 16)) & 0x030000FF;
+    v = (v | (v << 8)) & 0x0300F00F;
+    v = (v | (v << 4)) & 0x030C30C3;
+    v = (v | (v << 2)) & 0x09249249;
+    return v;
+}
+
+// order-preserving float <-> uint mapping so scene bounds can use atomicMin/atomicMax
+__device__ __forceinline__ unsigned f2o(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float o2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u); }
+
+__device__ __forceinline__ float3 prim_centroid(int kind, unsigned i, const float4 *x, const uint4 *face, const uint2 *edge) {
+    if (kind == 0) {
+        const uint4 f = face[i];
+        const float4 a = x[f.x], b = x[f.y], c = x[f.z];
+        return make_float3((a.x + b.x + c.x) / 3.0f, (a.y + b.y + c.y) / 3.0f, (a.z + b.z + c.z) / 3.0f);
+    } else if (kind == 1) {
+        const uint2 e = edge[i];
+        const float4 a = x[e.x], b = x[e.y];
+        return make_float3((a.x + b.x) / 2.0f, (a.y + b.y) / 2.0f, (a.z + b.z) / 2.0f);
+    }
+    const float4 a = x[i];
+    return make_float3(a.x, a.y, a.z);
+}
+
+__global__ void k_bounds(int kind, unsigned n, const float4 *x, const uint4 *face, const uint2 *edge, unsigned *bounds) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 c = make_float3(0.f, 0.f, 0.f);
+    const bool on = i < n;
+    if (on) c = prim_centroid(kind, i, x, face, edge);
+    float lo[3] = {on ? c.x : FLT_MAX, on ? c.y : FLT_MAX, on ? c.z : FLT_MAX};
+    float hi[3] = {on ? c.x : -FLT_MAX, on ? c.y : -FLT_MAX, on ? c.z : -FLT_MAX};
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(bounds + k, f2o(lo[k]));
+            atomicMax(bounds + 3 + k, f2o(hi[k]));
+        }
+}
+
+__global__ void k_morton(int kind, unsigned n, const float4 *x, const uint4 *face, const uint2 *edge, const unsigned *bounds,
+                         unsigned *code, unsigned *prim) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float3 c = prim_centroid(kind, i, x, face, edge);
+    const float lo[3] = {o2f(bounds[0]), o2f(bounds[1]), o2f(bounds[2])};
+    const float hi[3] = {o2f(bounds[3]), o2f(bounds[4]), o2f(bounds[5])};
+    const float cc[3] = {c.x, c.y, c.z};
+    unsigned q[3];
+    for (int k = 0; k < 3; ++k) {
+        const float ext = hi[k] - lo[k];
+        const float sc = ext > 1e-10f ? 1023.0f / ext : 0.0f;
+        q[k] = (unsigned)fminf(1023.0f, fmaxf(0.0f, (cc[k] - lo[k]) * sc));
+    }
+    code[i] = expand_bits(q[0]) | (expand_bits(q[1]) << 1) | (expand_bits(q[2]) << 2);
+    prim[i] = i;
+}
+
+// Karras 2012: common-prefix length of sorted keys i and j (index as tie-break)
+__device__ __forceinline__ int delta(const unsigned *code, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned a = code[i], b = code[j];
+    if (a == b) return 32 + __clz((unsigned)i ^ (unsigned)j);
+    return __clz(a ^ b);
+}
+
+__global__ void k_radix_tree(int n, const unsigned *code, int2 *child, int *parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(code, n, i, i + 1) - delta(code, n, i, i - 1)) > 0 ? 1 : -1;
+    const int dmin = delta(code, n, i, i - d);
+    int lmax = 2;
+    while (delta(code, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(code, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(code, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(code, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
+    child[i] = make_int2(left, right);
+    parent[left] = i;
+    parent[right] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+struct LeafParams {
+    const float4 *x0, *x1;
+    float extrapolate;
+    const uint4 *face;
+    const uint2 *edge;
+    const float4 *cp; // (ghat, offset, friction, mass) of this primitive kind
+};
+
+// leaf boxes (lbvh.cu:623-731) + bottom-up merge: the second thread to reach a node owns it
+__global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_sorted, const int2 *child, const int *parent,
+                      float4 *lo, float4 *hi, unsigned *flag) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned prim = prim_sorted[k];
+    const float4 cp = P.cp[prim];
+    const float margin = 0.5f * cp.x + cp.y;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    unsigned vidx[3];
+    int nvx;
+    if (kind == 0) { const uint4 f = P.face[prim]; vidx[0] = f.x; vidx[1] = f.y; vidx[2] = f.z; nvx = 3; }
+    else if (kind == 1) { const uint2 e = P.edge[prim]; vidx[0] = e.x; vidx[1] = e.y; vidx[2] = 0; nvx = 2; }
+    else { vidx[0] = prim; vidx[1] = vidx[2] = 0; nvx = 1; }
+    for (int a = 0; a < nvx; ++a) {
+        const float4 y0 = P.x0[vidx[a]], y1 = P.x1[vidx[a]];
+        const float z[3] = {P.extrapolate * (y1.x - y0.x) + y0.x, P.extrapolate * (y1.y - y0.y) + y0.y, P.extrapolate * (y1.z - y0.z) + y0.z};
+        const float y[3] = {y0.x, y0.y, y0.z};
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = fminf(mn[d], fminf(y[d], z[d]));
+            mx[d] = fmaxf(mx[d], fmaxf(y[d], z[d]));
+        }
+    }
+    float4 blo = make_float4(mn[0] - margin, mn[1] - margin, mn[2] - margin, 0.f);
+    float4 bhi = make_float4(mx[0] + margin, mx[1] + margin, mx[2] + margin, 0.f);
+    int node = (int)(n - 1 + k);
+    lo[node] = blo;
+    hi[node] = bhi;
+    if (n == 1) return;
+    int p = parent[node];
+    while (p >= 0) {
+        __threadfence();
+        if (atomicAdd(flag + p, 1u) == 0u) return; // first arrival: the sibling's thread will finish this node
+        const int2 c = child[p];
+        const int other = (c.x == node) ? c.y : c.x;
+        // the sibling subtree's box was published before its atomicAdd; read through L2
+        const float4 olo = __ldcg(lo + other), ohi = __ldcg(hi + other);
+        blo = make_float4(fminf(blo.x, olo.x), fminf(blo.y, olo.y), fminf(blo.z, olo.z), 0.f);
+        bhi = make_float4(fmaxf(bhi.x, ohi.x), fmaxf(bhi.y, ohi.y), fmaxf(bhi.z, ohi.z), 0.f);
+        lo[p] = blo;
+        hi[p] = bhi;
+        node = p;
+        p = parent[p];
+    }
+}
+
+static void fit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate) {
+    if (b.n == 0) return;
+    LeafParams P{x0, x1, extrapolate, s.face.p, s.edge.p, kind == 0 ? s.fcp.p : (kind == 1 ? s.ecp.p : s.vcp.p)};
+    if (b.n > 1) CUDA_OK(cudaMemsetAsync(b.flag.p, 0, sizeof(unsigned) * (b.n - 1), s.stream));
+    k_fit<<<div_up(b.n, 256), 256, 0, s.stream>>>(kind, b.n, P, b.prim_sorted.p, b.child.p, b.parent.p, b.lo.p, b.hi.p, b.flag.p);
+    LAUNCH_COUNT(1);
+}
+
+void bvh_build(State &s, Bvh &b, int kind, const float4 *x) {
+    const unsigned n = kind == 0 ? s.nf : (kind == 1 ? s.ne : s.nsv);
+    b.n = n;
+    if (n == 0) return;
+    cudaStream_t q = s.stream;
+    b.morton.reserve(n); b.morton_sorted.reserve(n); b.prim.reserve(n); b.prim_sorted.reserve(n);
+    b.child.reserve(n); b.parent.reserve(2 * size_t(n)); b.lo.reserve(2 * size_t(n)); b.hi.reserve(2 * size_t(n)); b.flag.reserve(n);
+    unsigned *bounds = s.counters.p + 40; // 6 words
+    const unsigned init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    CUDA_OK(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, q));
+    k_bounds<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, s.face.p, s.edge.p, bounds);
+    k_morton<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, s.face.p, s.edge.p, bounds, b.morton.p, b.prim.p);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, (int)n, 0, 30, q);
+    if (need > b.sort_tmp_bytes) { b.sort_tmp.reserve(need); b.sort_tmp_bytes = need; }
+    cub::DeviceRadixSort::SortPairs(b.sort_tmp.p, need, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, (int)n, 0, 30, q);
+    if (n > 1) k_radix_tree<<<div_up(n - 1, 256), 256, 0, q>>>((int)n, b.morton_sorted.p, b.child.p, b.parent.p);
+    LAUNCH_COUNT(4);
+    fit(s, b, kind, x, x, 1.0f);
+}
+
+void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate) { fit(s, b, kind, x0, x1, extrapolate); }
+
+} // namespace ppf

@@ -1,0 +1,959 @@
+// contact.cu -- broad phase, contact-pair generation, barrier assembly, ACCD line search,
+// intersection check.
+//
+// Replaces contact::embed_contact_force_hessian (crates/ppf-cts-solver/src/cpp/contact/contact.cu:1398-1787
+// with its functors 432-887 and embed_contact_force_hess<N> 263-354), contact::line_search
+// (2472-2740, CCD functors 2095-2316) and contact::check_intersection (3056-3175), plus the
+// DynCSRMat count/fill/finalize protocol of csrmat/csrmat.cu:19-488.
+//
+// Execution model (B200): the reference runs the narrow phase INSIDE a per-thread BVH traversal
+// (divergent, latency bound) and walks its dynamic matrix through per-row pointer structs.  Here
+//   1. a broad-phase kernel per query kind only emits candidate pairs (box overlap + index filters),
+//      queries issued in Morton order so a warp walks the same subtree;
+//   2. narrow-phase kernels run one candidate per thread (uniform work, coalesced candidate reads)
+//      with the reference's fp32 predicates (math_distance.cuh) and compact accepted pairs with a
+//      warp scan + one atomic per warp;
+//   3. the dynamic matrix pattern is the sorted unique set of (row, col) keys the accepted pairs
+//      touch outside the fixed pattern (one radix sort), values are accumulated by bisection into it.
+// Pair acceptance is independent of the candidate superset, so the accepted sets equal the
+// reference's for the same positions.
+#include "bvh.cuh"
+#include "math_accd.cuh"
+#include "math_contact.cuh"
+#include "math_distance.cuh"
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+namespace ppf {
+
+__device__ __forceinline__ V3 ld3c(const float4 *p, unsigned i) { const float4 v = p[i]; return mk(v.x, v.y, v.z); }
+__device__ __forceinline__ float sqr(float x) { return x * x; }
+
+// warp-cooperative slot allocation: every lane of a full warp calls this with its own k
+__device__ __forceinline__ unsigned warp_alloc(unsigned *counter, unsigned k) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned base = 0;
+    if (lane == 31 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// broad phase
+// ---------------------------------------------------------------------------------------------
+struct Emit { // per-thread staging of candidate pairs, flushed with one atomic per 8 pairs
+    uint2 buf[8];
+    unsigned n = 0;
+    uint2 *out;
+    unsigned *counter;
+    unsigned cap;
+    __device__ __forceinline__ void flush() {
+        if (!n) return;
+        const unsigned base = atomicAdd(counter, n);
+        for (unsigned k = 0; k < n; ++k)
+            if (base + k < cap) out[base + k] = buf[k];
+        n = 0;
+    }
+    __device__ __forceinline__ void push(unsigned a, unsigned b) {
+        buf[n++] = make_uint2(a, b);
+        if (n == 8) flush();
+    }
+};
+
+struct BpArgs {
+    BvhView face, edge, vert;
+    const float4 *x0, *x1; // query positions; sweep to x0 + sweep_t*(x1-x0) when sweep
+    float sweep_t;
+    int sweep;             // 0: assembly boxes around x0, 1: CCD swept boxes
+    const float4 *vcp, *ecp;
+    const uint4 *faces;
+    const uint2 *edges;
+    uint2 *out[4];
+    unsigned *cnt; // 4 counters
+    unsigned cap[4];
+    unsigned *error;
+};
+
+__global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const unsigned v = A.vert.prim[t];
+    const float4 cp = A.vcp[v];
+    const float ext = 0.5f * cp.x + cp.y;
+    const float4 p0 = A.x0[v];
+    Box q;
+    if (A.sweep) {
+        const float4 p1 = A.x1[v];
+        const float zx = A.sweep_t * (p1.x - p0.x) + p0.x, zy = A.sweep_t * (p1.y - p0.y) + p0.y, zz = A.sweep_t * (p1.z - p0.z) + p0.z;
+        q.lx = fminf(p0.x, zx) - ext; q.ly = fminf(p0.y, zy) - ext; q.lz = fminf(p0.z, zz) - ext;
+        q.hx = fmaxf(p0.x, zx) + ext; q.hy = fmaxf(p0.y, zy) + ext; q.hz = fmaxf(p0.z, zz) + ext;
+    } else {
+        q.lx = p0.x - ext; q.ly = p0.y - ext; q.lz = p0.z - ext;
+        q.hx = p0.x + ext; q.hy = p0.y + ext; q.hz = p0.z + ext;
+    }
+    bool ok = true;
+    {
+        Emit em; em.out = A.out[0]; em.counter = A.cnt + 0; em.cap = A.cap[0];
+        const int sweep = A.sweep;
+        ok &= bvh_query(A.face, q, [&](unsigned f) {
+            if (!sweep) { const uint4 fv = A.faces[f]; if (fv.x == v || fv.y == v || fv.z == v) return; }
+            em.push(v, f);
+        });
+        em.flush();
+    }
+    if (!A.sweep) {
+        Emit em; em.out = A.out[1]; em.counter = A.cnt + 1; em.cap = A.cap[1];
+        ok &= bvh_query(A.edge, q, [&](unsigned e) {
+            const uint2 ev = A.edges[e];
+            if (ev.x == v || ev.y == v) return;
+            em.push(v, e);
+        });
+        em.flush();
+    }
+    {
+        Emit em; em.out = A.out[2]; em.counter = A.cnt + 2; em.cap = A.cap[2];
+        ok &= bvh_query(A.vert, q, [&](unsigned w) { if (w < v) em.push(v, w); });
+        em.flush();
+    }
+    if (!ok) atomicExch(A.error, 1u);
+}
+
+__global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned nq) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const unsigned e = A.edge.prim[t];
+    const uint2 ev = A.edges[e];
+    const float4 cp = A.ecp[e];
+    const float ext = 0.5f * cp.x + cp.y;
+    const float4 a0 = A.x0[ev.x], b0 = A.x0[ev.y];
+    Box q;
+    q.lx = fminf(a0.x, b0.x) - ext; q.ly = fminf(a0.y, b0.y) - ext; q.lz = fminf(a0.z, b0.z) - ext;
+    q.hx = fmaxf(a0.x, b0.x) + ext; q.hy = fmaxf(a0.y, b0.y) + ext; q.hz = fmaxf(a0.z, b0.z) + ext;
+    if (A.sweep) {
+        const float4 a1 = A.x1[ev.x], b1 = A.x1[ev.y];
+        const float s = A.sweep_t;
+        const float ax = s * (a1.x - a0.x) + a0.x, ay = s * (a1.y - a0.y) + a0.y, az = s * (a1.z - a0.z) + a0.z;
+        const float bx = s * (b1.x - b0.x) + b0.x, by = s * (b1.y - b0.y) + b0.y, bz = s * (b1.z - b0.z) + b0.z;
+        q.lx = fminf(q.lx, fminf(ax, bx) - ext); q.ly = fminf(q.ly, fminf(ay, by) - ext); q.lz = fminf(q.lz, fminf(az, bz) - ext);
+        q.hx = fmaxf(q.hx, fmaxf(ax, bx) + ext); q.hy = fmaxf(q.hy, fmaxf(ay, by) + ext); q.hz = fmaxf(q.hz, fmaxf(az, bz) + ext);
+    }
+    Emit em; em.out = A.out[3]; em.counter = A.cnt + 3; em.cap = A.cap[3];
+    const int sweep = A.sweep;
+    const bool ok = bvh_query(A.edge, q, [&](unsigned f) {
+        if (!(e < f)) return;
+        if (!sweep) { const uint2 fv = A.edges[f]; if (fv.x == ev.x || fv.x == ev.y || fv.y == ev.x || fv.y == ev.y) return; }
+        em.push(e, f);
+    });
+    em.flush();
+    if (!ok) atomicExch(A.error, 1u);
+}
+
+// runs the broad phase; grows candidate buffers and retries on overflow
+static void broad_phase(State &s, const float4 *x0, const float4 *x1, bool sweep, float sweep_t) {
+    cudaStream_t q = s.stream;
+    unsigned *cnt = s.counters.p; // [0..3] candidate counters, [4] error
+    const size_t init_cap[4] = {size_t(24) * s.nsv + 1024, size_t(32) * s.nsv + 1024, size_t(8) * s.nsv + 1024, size_t(24) * s.ne + 1024};
+    for (int k = 0; k < 4; ++k)
+        if (s.cand[k].pairs.cap < init_cap[k]) s.cand[k].pairs.reserve(init_cap[k]);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        CUDA_OK(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned), q));
+        BpArgs A;
+        A.face = view_of(s.bvh_face); A.edge = view_of(s.bvh_edge); A.vert = view_of(s.bvh_vert);
+        A.x0 = x0; A.x1 = x1; A.sweep_t = sweep_t; A.sweep = sweep ? 1 : 0;
+        A.vcp = s.vcp.p; A.ecp = s.ecp.p; A.faces = s.face.p; A.edges = s.edge.p;
+        for (int k = 0; k < 4; ++k) { A.out[k] = s.cand[k].pairs.p; A.cap[k] = (unsigned)std::min<size_t>(s.cand[k].pairs.cap, 0xFFFFFFF0u); }
+        A.cnt = cnt; A.error = cnt + 4;
+        if (s.nsv) k_bp_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(A, s.nsv);
+        if (s.ne) k_bp_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);
+        LAUNCH_COUNT(2);
+        unsigned h[5];
+        CUDA_OK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaStreamSynchronize(q));
+        if (h[4]) fatal(4, "BVH traversal stack overflow (depth > %d)", PPF_BVH_STACK);
+        bool again = false;
+        for (int k = 0; k < 4; ++k) {
+            s.cand[k].count = h[k];
+            if (h[k] > s.cand[k].pairs.cap) { s.cand[k].pairs.reserve(size_t(h[k]) + h[k] / 4); again = true; }
+        }
+        if (!again) return;
+    }
+    fatal(4, "broad phase: candidate buffers kept overflowing");
+}
+
+// ---------------------------------------------------------------------------------------------
+// narrow phase predicates (shared by detection and fill)
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    const float4 *x;    // eval_x
+    const float4 *x0;   // start-of-step positions (data.vertex.curr)
+    const float4 *vcp, *ecp, *fcp;
+    const uint4 *face;
+    const uint2 *edge;
+    const unsigned char *vfixed, *efixed, *ffixed, *vcollider;
+    const unsigned *vf_off, *vf_idx, *ve_off, *ve_idx, *ef_off, *ef_idx;
+    int friction_mode;
+    float friction_eps;
+    // matrices
+    const unsigned *fx_off, *fx_col;
+    const float *fx_el; // elastic-only snapshot
+    float *fx_val;      // accumulating fixed matrix
+    const unsigned *dyn_off, *dyn_col;
+    float *dyn_val;
+    float *force;
+};
+
+template <int N> struct Prox {
+    unsigned idx[N];
+    float w[N];
+    float ghat, offset, friction;
+    unsigned count;
+    bool include_friction;
+};
+
+__device__ __forceinline__ bool eval_pf(const Ctx &c, unsigned v, unsigned fi, Prox<4> &o) {
+    const uint4 f = c.face[fi];
+    if (f.x == v || f.y == v || f.z == v) return false;
+    const bool either_dyn = !c.vfixed[v] || !c.ffixed[fi];
+    const bool both_collider = c.vcollider[v] && c.vcollider[f.x];
+    if (!either_dyn || both_collider) return false;
+    const V3 p = ld3c(c.x, v), t0 = ld3c(c.x, f.x), t1 = ld3c(c.x, f.y), t2 = ld3c(c.x, f.z);
+    const C3 cf = point_triangle_coeff(p, t0, t1, t2);
+    if (!strictly_interior(cf)) return false;
+    const V3 e = cf.a * (p - t0) + cf.b * (p - t1) + cf.c * (p - t2);
+    const float4 vp = c.vcp[v], fp = c.fcp[fi];
+    const float offset = vp.y + fp.y;
+    const float ghat = 0.5f * (vp.x + fp.x);
+    if (!(sqnorm(e) < sqr(ghat + offset))) return false;
+    o.idx[0] = v; o.idx[1] = f.x; o.idx[2] = f.y; o.idx[3] = f.z;
+    o.w[0] = 1.0f; o.w[1] = -cf.a; o.w[2] = -cf.b; o.w[3] = -cf.c;
+    o.ghat = ghat; o.offset = offset; o.friction = combine_friction(vp.z, fp.z, c.friction_mode);
+    o.count = 1; o.include_friction = true;
+    return true;
+}
+
+__device__ __forceinline__ bool eval_pe(const Ctx &c, unsigned v, unsigned ei, Prox<3> &o) {
+    const uint2 f = c.edge[ei];
+    if (f.x == v || f.y == v) return false;
+    const bool either_dyn = !c.vfixed[v] || !c.efixed[ei];
+    const bool both_collider = c.vcollider[v] && c.vcollider[f.x];
+    if (!either_dyn || both_collider) return false;
+    const V3 p = ld3c(c.x, v), t0 = ld3c(c.x, f.x), t1 = ld3c(c.x, f.y);
+    const C2 cf = point_edge_coeff(p, t0, t1);
+    if (!strictly_interior(cf)) return false;
+    const V3 e = cf.a * (p - t0) + cf.b * (p - t1);
+    const float4 vp = c.vcp[v], ep = c.ecp[ei];
+    const float offset = vp.y + ep.y;
+    const float ghat = 0.5f * (vp.x + ep.x);
+    if (!(sqnorm(e) < sqr(ghat + offset))) return false;
+    unsigned count = 0;
+    bool include_friction = true;
+    const unsigned b0 = c.ef_off[ei], b1 = c.ef_off[ei + 1];
+    if (b1 > b0) {
+        for (unsigned j = b0; j < b1; ++j) {
+            const uint4 ff = c.face[c.ef_idx[j]];
+            if (ff.x == v || ff.y == v || ff.z == v) { ++count; include_friction = false; }
+            else {
+                const C3 cc = point_triangle_coeff(p, ld3c(c.x, ff.x), ld3c(c.x, ff.y), ld3c(c.x, ff.z));
+                if (strictly_interior(cc)) continue;
+                ++count;
+            }
+        }
+    } else count = 1u;
+    if (!count) return false;
+    o.idx[0] = v; o.idx[1] = f.x; o.idx[2] = f.y;
+    o.w[0] = 1.0f; o.w[1] = -cf.a; o.w[2] = -cf.b;
+    o.ghat = ghat; o.offset = offset; o.friction = combine_friction(vp.z, ep.z, c.friction_mode);
+    o.count = count; o.include_friction = include_friction;
+    return true;
+}
+
+__device__ __forceinline__ bool eval_pp(const Ctx &c, unsigned v, unsigned w, Prox<2> &o) {
+    if (!(w < v)) return false;
+    const bool either_dyn = !c.vfixed[v] || !c.vfixed[w];
+    const bool both_collider = c.vcollider[v] && c.vcollider[w];
+    if (!either_dyn || both_collider) return false;
+    const V3 x = ld3c(c.x, v), y = ld3c(c.x, w);
+    const V3 e = x - y;
+    const float4 vp = c.vcp[v], wp = c.vcp[w];
+    const float offset = vp.y + wp.y;
+    const float ghat = 0.5f * (vp.x + wp.x);
+    if (!(sqnorm(e) < sqr(ghat + offset))) return false;
+    unsigned count = 0;
+    bool include_friction = true;
+    const unsigned e0 = c.ve_off[w], e1 = c.ve_off[w + 1];
+    if (e1 > e0) {
+        for (unsigned j = e0; j < e1; ++j) {
+            const uint2 f = c.edge[c.ve_idx[j]];
+            if (f.x == v || f.y == v) { ++count; include_friction = false; }
+            else {
+                const C2 cc = point_edge_coeff(x, ld3c(c.x, f.x), ld3c(c.x, f.y));
+                if (strictly_interior(cc)) continue;
+                ++count;
+            }
+        }
+        const unsigned f0 = c.vf_off[w], f1 = c.vf_off[w + 1];
+        for (unsigned j = f0; j < f1; ++j) {
+            const uint4 f = c.face[c.vf_idx[j]];
+            if (f.x == v || f.y == v || f.z == v) { ++count; include_friction = false; }
+            else {
+                const C3 cc = point_triangle_coeff(x, ld3c(c.x, f.x), ld3c(c.x, f.y), ld3c(c.x, f.z));
+                if (strictly_interior(cc)) continue;
+                ++count;
+            }
+        }
+    } else count = 1u;
+    if (!count) return false;
+    o.idx[0] = v; o.idx[1] = w;
+    o.w[0] = 1.0f; o.w[1] = -1.0f;
+    o.ghat = ghat; o.offset = offset; o.friction = combine_friction(vp.z, wp.z, c.friction_mode);
+    o.count = count; o.include_friction = include_friction;
+    return true;
+}
+
+__device__ __forceinline__ bool eval_ee(const Ctx &c, unsigned ea, unsigned eb, Prox<4> &o) {
+    if (!(ea < eb)) return false;
+    const uint2 e0 = c.edge[ea], e1 = c.edge[eb];
+    if (e0.x == e1.x || e0.x == e1.y || e0.y == e1.x || e0.y == e1.y) return false;
+    const bool either_dyn = !c.efixed[ea] || !c.efixed[eb];
+    const bool both_collider = c.vcollider[e0.x] && c.vcollider[e1.x];
+    if (!either_dyn || both_collider) return false;
+    const V3 p0 = ld3c(c.x, e0.x), p1 = ld3c(c.x, e0.y), q0 = ld3c(c.x, e1.x), q1 = ld3c(c.x, e1.y);
+    const C4 cf = edge_edge_coeff(p0, p1, q0, q1);
+    if (!strictly_interior(cf)) return false;
+    const V3 xa = cf.a * p0 + cf.b * p1;
+    const V3 xb = cf.c * q0 + cf.d * q1;
+    const V3 e = xa - xb;
+    const float4 ap = c.ecp[ea], bp = c.ecp[eb];
+    const float offset = ap.y + bp.y;
+    const float ghat = 0.5f * (ap.x + bp.x);
+    if (!(sqnorm(e) < sqr(ghat + offset))) return false;
+    o.idx[0] = e0.x; o.idx[1] = e0.y; o.idx[2] = e1.x; o.idx[3] = e1.y;
+    o.w[0] = cf.a; o.w[1] = cf.b; o.w[2] = -cf.c; o.w[3] = -cf.d;
+    o.ghat = ghat; o.offset = offset; o.friction = combine_friction(ap.z, bp.z, c.friction_mode);
+    o.count = 1; o.include_friction = true;
+    return true;
+}
+
+template <int KIND> __global__ void __launch_bounds__(256) k_narrow(Ctx c, const uint2 *cand, unsigned n, uint2 *out, unsigned *counter, unsigned cap) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool acc = false;
+    uint2 pr = make_uint2(0, 0);
+    if (t < n) {
+        pr = cand[t];
+        if (KIND == 0) { Prox<4> o; acc = eval_pf(c, pr.x, pr.y, o); }
+        else if (KIND == 1) { Prox<3> o; acc = eval_pe(c, pr.x, pr.y, o); }
+        else if (KIND == 2) { Prox<2> o; acc = eval_pp(c, pr.x, pr.y, o); }
+        else { Prox<4> o; acc = eval_ee(c, pr.x, pr.y, o); }
+    }
+    const unsigned slot = warp_alloc(counter, acc ? 1u : 0u);
+    if (acc && slot < cap) out[slot] = pr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// matrix lookups
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fixed_find(const Ctx &c, unsigned i, unsigned j) { // i <= j
+    const unsigned b0 = c.fx_off[i], b1 = c.fx_off[i + 1];
+    for (unsigned k = b0; k < b1; ++k) {
+        const unsigned col = c.fx_col[k];
+        if (col == j) return k;
+        if (col > j) break;
+    }
+    return 0xFFFFFFFFu;
+}
+__device__ __forceinline__ unsigned dyn_find(const Ctx &c, unsigned i, unsigned j) {
+    unsigned lo = c.dyn_off[i], hi = c.dyn_off[i + 1];
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        const unsigned col = c.dyn_col[mid];
+        if (col < j) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int N> __device__ __forceinline__ unsigned emit_keys(const Ctx &c, const unsigned *idx, unsigned long long *keys, unsigned shift) {
+    unsigned n = 0;
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = a + 1; b < N; ++b) {
+            const unsigned i = min(idx[a], idx[b]), j = max(idx[a], idx[b]);
+            if (fixed_find(c, i, j) == 0xFFFFFFFFu) keys[n++] = ((unsigned long long)i << shift) | j;
+        }
+    return n;
+}
+
+template <int KIND> __global__ void __launch_bounds__(256) k_keys(Ctx c, const uint2 *pairs, unsigned n, unsigned long long *out, unsigned *counter, unsigned shift) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long keys[6];
+    unsigned k = 0;
+    if (t < n) {
+        const uint2 pr = pairs[t];
+        if (KIND == 0) { const uint4 f = c.face[pr.y]; const unsigned idx[4] = {pr.x, f.x, f.y, f.z}; k = emit_keys<4>(c, idx, keys, shift); }
+        else if (KIND == 1) { const uint2 e = c.edge[pr.y]; const unsigned idx[3] = {pr.x, e.x, e.y}; k = emit_keys<3>(c, idx, keys, shift); }
+        else if (KIND == 2) { const unsigned idx[2] = {pr.x, pr.y}; k = emit_keys<2>(c, idx, keys, shift); }
+        else { const uint2 a = c.edge[pr.x], b = c.edge[pr.y]; const unsigned idx[4] = {a.x, a.y, b.x, b.y}; k = emit_keys<4>(c, idx, keys, shift); }
+    }
+    const unsigned base = warp_alloc(counter, k);
+    for (unsigned q = 0; q < k; ++q) out[base + q] = keys[q];
+}
+
+__global__ void k_dyn_structure(unsigned nv, unsigned nnz, const unsigned long long *keys, unsigned shift, unsigned *off, unsigned *col) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nnz) col[t] = (unsigned)(keys[t] & ((1ull << shift) - 1ull));
+    if (t <= nv) { // off[t] = first key with row >= t
+        const unsigned long long target = (unsigned long long)t << shift;
+        unsigned lo = 0, hi = nnz;
+        while (lo < hi) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (keys[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        off[t] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fill: barrier force / Hessian of one contact (embed_contact_force_hess<N>, contact.cu:263-354)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ M3 load_block(const float *val, unsigned slot) {
+    M3 m;
+    const float *p = val + size_t(9) * slot;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m.m[i] = p[i];
+    return m;
+}
+
+template <int N> __device__ __forceinline__ void embed_contact(const Ctx &c, const Prox<N> &pr) {
+    float mass[N];
+    V3 ex0 = mk(0.f, 0.f, 0.f), ex = mk(0.f, 0.f, 0.f);
+    const V3 anchor0 = ld3c(c.x0, pr.idx[0]), anchor = ld3c(c.x, pr.idx[0]);
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii) {
+        mass[ii] = c.vcp[pr.idx[ii]].w;
+        ex0 += pr.w[ii] * (ld3c(c.x0, pr.idx[ii]) - anchor0);
+        ex += pr.w[ii] * (ld3c(c.x, pr.idx[ii]) - anchor);
+    }
+    const V3 dxs = ex - ex0;
+    const V3 normal = normalized(ex);
+    // ---- elasticity-inclusive stiffness (barrier.cu:50-86), upper blocks gathered once ----
+    const float nrm = norm(ex);
+    const float g = nrm - pr.offset;
+    const float sqr_x = g * g;
+    float m_max = 0.0f;
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii) m_max = fmaxf(m_max, mass[ii]);
+    V3 wv[N];
+    float wsq = 0.0f;
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii) { wv[ii] = pr.w[ii] * ex; wsq += sqnorm(wv[ii]); }
+    const float wn = sqrtf(wsq);
+    if (wn > 0.0f) {
+#pragma unroll
+        for (int ii = 0; ii < N; ++ii) wv[ii] = wv[ii] / wn;
+    }
+    float kappa = 0.0f;
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii) {
+        const float m_ii = mass[ii] > 0.0f ? mass[ii] : m_max;
+        kappa += (m_ii / sqr_x) * sqnorm(wv[ii]);
+#pragma unroll
+        for (int jj = ii; jj < N; ++jj) {
+            const unsigned i = pr.idx[ii], j = pr.idx[jj];
+            const bool swap = i > j;
+            const unsigned slot = fixed_find(c, swap ? j : i, swap ? i : j);
+            if (slot == 0xFFFFFFFFu) continue;
+            const M3 B = load_block(c.fx_el, slot);
+            // block (ii,jj) of the local Hessian is B (or B^T when stored as (j,i))
+            const V3 Bw = swap ? mul_t(B, wv[jj]) : mul(B, wv[jj]);
+            const float t = dot(wv[ii], Bw);
+            kappa += (ii == jj) ? t : 2.0f * t;
+        }
+    }
+    V3 f = kappa * barrier_edge_gradient(ex, pr.ghat, pr.offset);
+    M3 H = kappa * barrier_edge_hessian(ex, pr.ghat, pr.offset);
+    if (pr.include_friction) {
+        const FrictionOut fr = friction_eval(f, dxs, normal, pr.friction, c.friction_eps);
+        f += fr.grad;
+        H += fr.hess;
+    }
+    const float cnt = (float)pr.count;
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii) {
+        const V3 fi = (cnt * pr.w[ii]) * f;
+        float *dst = c.force + size_t(3) * pr.idx[ii];
+        if (fi.x) atomicAdd(dst + 0, fi.x);
+        if (fi.y) atomicAdd(dst + 1, fi.y);
+        if (fi.z) atomicAdd(dst + 2, fi.z);
+    }
+#pragma unroll
+    for (int ii = 0; ii < N; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < N; ++jj) {
+            const unsigned i = pr.idx[ii], j = pr.idx[jj];
+            if (!(i <= j)) continue;
+            const float sc = cnt * (pr.w[ii] * pr.w[jj]);
+            float *dst;
+            const unsigned slot = fixed_find(c, i, j);
+            if (slot != 0xFFFFFFFFu) dst = c.fx_val + size_t(9) * slot;
+            else dst = c.dyn_val + size_t(9) * dyn_find(c, i, j);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                const float y = sc * H.m[e];
+                if (y) atomicAdd(dst + e, y);
+            }
+        }
+}
+
+template <int KIND> __global__ void __launch_bounds__(128) k_fill(Ctx c, const uint2 *pairs, unsigned n) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint2 pr = pairs[t];
+    if (KIND == 0) { Prox<4> o; if (eval_pf(c, pr.x, pr.y, o)) embed_contact<4>(c, o); }
+    else if (KIND == 1) { Prox<3> o; if (eval_pe(c, pr.x, pr.y, o)) embed_contact<3>(c, o); }
+    else if (KIND == 2) { Prox<2> o; if (eval_pp(c, pr.x, pr.y, o)) embed_contact<2>(c, o); }
+    else { Prox<4> o; if (eval_ee(c, pr.x, pr.y, o)) embed_contact<4>(c, o); }
+}
+
+static Ctx make_ctx(State &s, const PpfParamSet &prm) {
+    Ctx c;
+    c.x = s.eval_x.p; c.x0 = s.curr.p;
+    c.vcp = s.vcp.p; c.ecp = s.ecp.p; c.fcp = s.fcp.p;
+    c.face = s.face.p; c.edge = s.edge.p;
+    c.vfixed = s.vfixed.p; c.efixed = s.efixed.p; c.ffixed = s.ffixed.p; c.vcollider = s.vcollider.p;
+    c.vf_off = s.vf_off.p; c.vf_idx = s.vf_idx.p; c.ve_off = s.ve_off.p; c.ve_idx = s.ve_idx.p; c.ef_off = s.ef_off.p; c.ef_idx = s.ef_idx.p;
+    c.friction_mode = (int)prm.friction_mode; c.friction_eps = prm.friction_eps;
+    c.fx_off = s.fx_off.p; c.fx_col = s.fx_col.p; c.fx_el = s.fx_el.p; c.fx_val = s.fx_val.p;
+    c.dyn_off = s.dyn_off.p; c.dyn_col = s.dyn_col.p; c.dyn_val = s.dyn_val.p;
+    c.force = s.force.p;
+    return c;
+}
+
+static DBuf<unsigned char> g_cub_tmp;
+static DBuf<unsigned> g_row_len;
+
+unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed) {
+    (void)dt;
+    cudaStream_t q = s.stream;
+    max_nnz_row = 0;
+    dyn_consumed = 0.0f;
+    // ---- detect ----
+    broad_phase(s, s.eval_x.p, s.eval_x.p, false, 0.0f);
+    Ctx c = make_ctx(s, prm);
+    unsigned *acc_cnt = s.counters.p + 8; // [8..11]
+    CUDA_OK(cudaMemsetAsync(acc_cnt, 0, 8 * sizeof(unsigned), q));
+    for (int k = 0; k < 4; ++k) {
+        const unsigned n = s.cand[k].count;
+        s.pairs[k].pairs.reserve(std::max<size_t>(n, 16));
+        if (!n) continue;
+        const unsigned cap = (unsigned)std::min<size_t>(s.pairs[k].pairs.cap, 0xFFFFFFF0u);
+        const unsigned grid = div_up(n, 256);
+        if (k == 0) k_narrow<0><<<grid, 256, 0, q>>>(c, s.cand[k].pairs.p, n, s.pairs[k].pairs.p, acc_cnt + k, cap);
+        if (k == 1) k_narrow<1><<<grid, 256, 0, q>>>(c, s.cand[k].pairs.p, n, s.pairs[k].pairs.p, acc_cnt + k, cap);
+        if (k == 2) k_narrow<2><<<grid, 256, 0, q>>>(c, s.cand[k].pairs.p, n, s.pairs[k].pairs.p, acc_cnt + k, cap);
+        if (k == 3) k_narrow<3><<<grid, 256, 0, q>>>(c, s.cand[k].pairs.p, n, s.pairs[k].pairs.p, acc_cnt + k, cap);
+        LAUNCH_COUNT(1);
+    }
+    unsigned hc[4];
+    CUDA_OK(cudaMemcpyAsync(hc, acc_cnt, sizeof(hc), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    unsigned total = 0;
+    for (int k = 0; k < 4; ++k) { s.pairs[k].count = hc[k]; s.last_num_contact[k] = hc[k]; total += hc[k]; }
+
+    // ---- dynamic pattern: sorted unique keys outside the fixed pattern ----
+    unsigned shift = 1;
+    while ((1ull << shift) < (unsigned long long)s.nv) ++shift;
+    const size_t max_keys = size_t(6) * hc[0] + size_t(3) * hc[1] + size_t(1) * hc[2] + size_t(6) * hc[3] + 32;
+    s.dyn_keys.reserve(max_keys); s.dyn_keys_sorted.reserve(max_keys);
+    s.dyn_off.reserve(s.nv + 2);
+    unsigned *key_cnt = s.counters.p + 16;
+    CUDA_OK(cudaMemsetAsync(key_cnt, 0, 2 * sizeof(unsigned), q));
+    if (hc[0]) k_keys<0><<<div_up(hc[0], 256), 256, 0, q>>>(c, s.pairs[0].pairs.p, hc[0], s.dyn_keys.p, key_cnt, shift);
+    if (hc[1]) k_keys<1><<<div_up(hc[1], 256), 256, 0, q>>>(c, s.pairs[1].pairs.p, hc[1], s.dyn_keys.p, key_cnt, shift);
+    if (hc[2]) k_keys<2><<<div_up(hc[2], 256), 256, 0, q>>>(c, s.pairs[2].pairs.p, hc[2], s.dyn_keys.p, key_cnt, shift);
+    if (hc[3]) k_keys<3><<<div_up(hc[3], 256), 256, 0, q>>>(c, s.pairs[3].pairs.p, hc[3], s.dyn_keys.p, key_cnt, shift);
+    LAUNCH_COUNT(4);
+    unsigned nkeys = 0;
+    CUDA_OK(cudaMemcpyAsync(&nkeys, key_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    unsigned nnz = 0;
+    if (nkeys) {
+        size_t need = 0, need2 = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, need, s.dyn_keys.p, s.dyn_keys_sorted.p, (int)nkeys, 0, (int)(2 * shift), q);
+        cub::DeviceSelect::Unique(nullptr, need2, s.dyn_keys_sorted.p, s.dyn_keys.p, key_cnt + 1, (int)nkeys, q);
+        g_cub_tmp.reserve(std::max(need, need2));
+        cub::DeviceRadixSort::SortKeys(g_cub_tmp.p, need, s.dyn_keys.p, s.dyn_keys_sorted.p, (int)nkeys, 0, (int)(2 * shift), q);
+        cub::DeviceSelect::Unique(g_cub_tmp.p, need2, s.dyn_keys_sorted.p, s.dyn_keys.p, key_cnt + 1, (int)nkeys, q);
+        LAUNCH_COUNT(8);
+        CUDA_OK(cudaMemcpyAsync(&nnz, key_cnt + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
+    if (nnz >= s.dyn_cap) fatal(4, "dynamic contact matrix needs %u blocks but csrmat-max-nnz is %llu", nnz, s.dyn_cap);
+    s.dyn_nnz = nnz;
+    s.dyn_col.reserve(std::max<size_t>(nnz, 16)); s.dyn_val.reserve(size_t(9) * std::max<size_t>(nnz, 16));
+    k_dyn_structure<<<div_up(std::max<size_t>(nnz, s.nv + 1), 256), 256, 0, q>>>(s.nv, nnz, s.dyn_keys.p, shift, s.dyn_off.p, s.dyn_col.p);
+    if (nnz) CUDA_OK(cudaMemsetAsync(s.dyn_val.p, 0, sizeof(float) * 9 * size_t(nnz), q));
+    LAUNCH_COUNT(1);
+    dyn_consumed = (float)nnz / (float)s.dyn_cap;
+
+    // ---- fill ----
+    c = make_ctx(s, prm); // buffers may have been re-allocated
+    if (hc[0]) k_fill<0><<<div_up(hc[0], 128), 128, 0, q>>>(c, s.pairs[0].pairs.p, hc[0]);
+    if (hc[1]) k_fill<1><<<div_up(hc[1], 128), 128, 0, q>>>(c, s.pairs[1].pairs.p, hc[1]);
+    if (hc[2]) k_fill<2><<<div_up(hc[2], 128), 128, 0, q>>>(c, s.pairs[2].pairs.p, hc[2]);
+    if (hc[3]) k_fill<3><<<div_up(hc[3], 128), 128, 0, q>>>(c, s.pairs[3].pairs.p, hc[3]);
+    LAUNCH_COUNT(4);
+    s.dyn_valid = true;
+    return total;
+}
+
+// pattern handed out by fetch_dyn: per row, the sorted columns whose accumulated block is not
+// "zero" in the reference's sense (SMat::isZero, |m| <= 1e-5 for all entries; row_dedupe.hpp:96-150)
+void build_fetch_pattern(State &s, std::vector<unsigned> &index, std::vector<unsigned> &offset) {
+    const unsigned nv = s.nv, nnz = s.dyn_nnz;
+    offset.assign(nv + 1, 0);
+    index.clear();
+    if (!nnz) return;
+    std::vector<unsigned> off(nv + 1), col(nnz);
+    std::vector<float> val(size_t(9) * nnz);
+    CUDA_OK(cudaMemcpy(off.data(), s.dyn_off.p, sizeof(unsigned) * (nv + 1), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(col.data(), s.dyn_col.p, sizeof(unsigned) * nnz, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(val.data(), s.dyn_val.p, sizeof(float) * 9 * size_t(nnz), cudaMemcpyDeviceToHost));
+    for (unsigned i = 0; i < nv; ++i) {
+        offset[i] = (unsigned)index.size();
+        for (unsigned k = off[i]; k < off[i + 1]; ++k) {
+            bool zero = true;
+            for (int e = 0; e < 9; ++e)
+                if (!(fabsf(val[size_t(9) * k + e]) <= 1e-5f)) { zero = false; break; }
+            if (!zero) index.push_back(col[k]);
+        }
+    }
+    offset[nv] = (unsigned)index.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// ACCD line search
+// ---------------------------------------------------------------------------------------------
+struct CcdCtx {
+    const float4 *x0, *x1;
+    const float4 *vcp, *ecp, *fcp;
+    const uint4 *face;
+    const uint2 *edge;
+    const unsigned char *vfixed, *efixed, *ffixed, *vcollider;
+    float max_t, ccd_eps;
+    unsigned *toi_bits; // positive floats order like unsigned ints
+    unsigned *overlap;  // [0] flag, [1] v0, [2] v1, [3] kind
+};
+
+__device__ __forceinline__ void ccd_commit(const CcdCtx &c, float result, const CcdOverlap &ov, unsigned v0, unsigned v1, unsigned kind) {
+    if (ov.flag) atomicExch(c.overlap, 1u);
+    if (result < c.max_t) {
+        atomicMin(c.toi_bits, __float_as_uint(result));
+        if (result == 0.0f && atomicCAS(c.overlap + 1, 0xFFFFFFFFu, v0) == 0xFFFFFFFFu) { c.overlap[2] = v1; c.overlap[3] = kind; }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ccd_pf(CcdCtx c, const uint2 *cand, unsigned n) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const unsigned v = cand[t].x, fi = cand[t].y;
+    const uint4 f = c.face[fi];
+    const bool either_dyn = !c.vfixed[v] || !c.ffixed[fi];
+    const bool both_collider = c.vcollider[v] && c.vcollider[f.x];
+    if (!either_dyn || both_collider) return;
+    const unsigned fv[3] = {f.x, f.y, f.z};
+    int dup = -1;
+    for (int i = 0; i < 3; ++i)
+        if (fv[i] == v) { dup = i; break; }
+    CcdOverlap ov{0u, -1.0f, -1.0f};
+    float result;
+    const float4 vp = c.vcp[v];
+    if (dup == -1) {
+        const float4 fp = c.fcp[fi];
+        const float offset = vp.y + fp.y, ghat = 0.5f * (vp.x + fp.x);
+        result = point_triangle_ccd(ld3c(c.x0, v), ld3c(c.x1, v), ld3c(c.x0, f.x), ld3c(c.x0, f.y), ld3c(c.x0, f.z), ld3c(c.x1, f.x),
+                                    ld3c(c.x1, f.y), ld3c(c.x1, f.z), offset, ghat, c.max_t, c.ccd_eps, ov);
+    } else {
+        const float offset = 2.0f * vp.y, ghat = vp.x;
+        const unsigned i = fv[dup], j = fv[(dup + 1) % 3], k = fv[(dup + 2) % 3];
+        result = point_edge_ccd(ld3c(c.x0, i), ld3c(c.x1, i), ld3c(c.x0, j), ld3c(c.x0, k), ld3c(c.x1, j), ld3c(c.x1, k), offset, ghat,
+                                c.max_t, c.ccd_eps, ov);
+    }
+    ccd_commit(c, result, ov, v, f.x, 0u);
+}
+
+__global__ void __launch_bounds__(128) k_ccd_pp(CcdCtx c, const uint2 *cand, unsigned n) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const unsigned v = cand[t].x, w = cand[t].y;
+    const bool either_dyn = !c.vfixed[v] || !c.vfixed[w];
+    const bool both_collider = c.vcollider[v] && c.vcollider[w];
+    if (!(w < v) || !either_dyn || both_collider) return;
+    const float4 a = c.vcp[v], b = c.vcp[w];
+    CcdOverlap ov{0u, -1.0f, -1.0f};
+    const float result = point_point_ccd(ld3c(c.x0, v), ld3c(c.x1, v), ld3c(c.x0, w), ld3c(c.x1, w), a.y + b.y, 0.5f * (a.x + b.x),
+                                         c.max_t, c.ccd_eps, ov);
+    ccd_commit(c, result, ov, v, w, 2u);
+}
+
+__global__ void __launch_bounds__(128) k_ccd_ee(CcdCtx c, const uint2 *cand, unsigned n) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const unsigned ea = cand[t].x, eb = cand[t].y;
+    const bool either_dyn = !c.efixed[ea] || !c.efixed[eb];
+    const uint2 e0 = c.edge[ea], e1 = c.edge[eb];
+    const bool both_collider = c.vcollider[e0.x] && c.vcollider[e1.x];
+    if (!(ea < eb) || !either_dyn || both_collider) return;
+    const float4 ap = c.ecp[ea], bp = c.ecp[eb];
+    const float offset = ap.y + bp.y, ghat = 0.5f * (ap.x + bp.x);
+    CcdOverlap ov{0u, -1.0f, -1.0f};
+    float result = c.max_t;
+    const unsigned a[2] = {e0.x, e0.y}, b[2] = {e1.x, e1.y};
+    const bool shared = a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1];
+    if (!shared) {
+        result = edge_edge_ccd(ld3c(c.x0, a[0]), ld3c(c.x0, a[1]), ld3c(c.x0, b[0]), ld3c(c.x0, b[1]), ld3c(c.x1, a[0]), ld3c(c.x1, a[1]),
+                               ld3c(c.x1, b[0]), ld3c(c.x1, b[1]), offset, ghat, c.max_t, c.ccd_eps, ov);
+    } else {
+        const int ij[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+        for (int k = 0; k < 4; ++k) {
+            const int i = ij[k][0], j = ij[k][1];
+            if (a[i] == b[j]) {
+                const unsigned i0 = a[i], i1 = a[1 - i], i2 = b[1 - j];
+                const float t0 = point_edge_ccd(ld3c(c.x0, i1), ld3c(c.x1, i1), ld3c(c.x0, i0), ld3c(c.x0, i2), ld3c(c.x1, i0), ld3c(c.x1, i2),
+                                                offset, ghat, c.max_t, c.ccd_eps, ov);
+                const float t1 = point_edge_ccd(ld3c(c.x0, i2), ld3c(c.x1, i2), ld3c(c.x0, i0), ld3c(c.x0, i1), ld3c(c.x1, i0), ld3c(c.x1, i1),
+                                                offset, ghat, c.max_t, c.ccd_eps, ov);
+                result = fminf(t0, t1);
+                break;
+            }
+        }
+    }
+    ccd_commit(c, result, ov, e0.x, e1.x, 1u);
+}
+
+static unsigned g_last_overlap[4] = {0, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+
+float contact_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap) {
+    cudaStream_t q = s.stream;
+    broad_phase(s, x0, x1, true, prm.line_search_max_t);
+    CcdCtx c;
+    c.x0 = x0; c.x1 = x1; c.vcp = s.vcp.p; c.ecp = s.ecp.p; c.fcp = s.fcp.p; c.face = s.face.p; c.edge = s.edge.p;
+    c.vfixed = s.vfixed.p; c.efixed = s.efixed.p; c.ffixed = s.ffixed.p; c.vcollider = s.vcollider.p;
+    c.max_t = prm.line_search_max_t; c.ccd_eps = prm.ccd_eps;
+    unsigned *w = s.counters.p + 20; // [20] toi bits, [21..24] overlap info
+    const float max_t = prm.line_search_max_t;
+    unsigned init[5];
+    memcpy(&init[0], &max_t, sizeof(float));
+    init[1] = 0u; init[2] = 0xFFFFFFFFu; init[3] = 0xFFFFFFFFu; init[4] = 0xFFFFFFFFu;
+    CUDA_OK(cudaMemcpyAsync(w, init, sizeof(init), cudaMemcpyHostToDevice, q));
+    c.toi_bits = w; c.overlap = w + 1;
+    if (s.cand[0].count) k_ccd_pf<<<div_up(s.cand[0].count, 128), 128, 0, q>>>(c, s.cand[0].pairs.p, s.cand[0].count);
+    if (s.cand[2].count) k_ccd_pp<<<div_up(s.cand[2].count, 128), 128, 0, q>>>(c, s.cand[2].pairs.p, s.cand[2].count);
+    if (s.cand[3].count) k_ccd_ee<<<div_up(s.cand[3].count, 128), 128, 0, q>>>(c, s.cand[3].pairs.p, s.cand[3].count);
+    LAUNCH_COUNT(3);
+    unsigned h[5];
+    CUDA_OK(cudaMemcpyAsync(h, w, sizeof(h), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    float toi;
+    memcpy(&toi, &h[0], sizeof(float));
+    overlap = h[1] != 0u;
+    for (int k = 0; k < 4; ++k) g_last_overlap[k] = h[1 + k];
+    return toi / prm.line_search_max_t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// intersection check (contact.cu:3056-3175, intersect_core.hpp:21-79)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool point_triangle_inside(const float *p, const float *d1, const float *d2) {
+    const float a00 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
+    const float a01 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
+    const float a11 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
+    const float b0 = d1[0] * p[0] + d1[1] * p[1] + d1[2] * p[2];
+    const float b1 = d2[0] * p[0] + d2[1] * p[1] + d2[2] * p[2];
+    const float det = a00 * a11 - a01 * a01;
+    if (det == 0.0f) return false;
+    const float w0 = (a11 * b0 - a01 * b1) / det;
+    const float w1 = (a00 * b1 - a01 * b0) / det;
+    const float w2 = 1.0f - w0 - w1;
+    float wmin = w0 < w1 ? w0 : w1;
+    wmin = wmin < w2 ? wmin : w2;
+    float wmax = w0 > w1 ? w0 : w1;
+    wmax = wmax > w2 ? wmax : w2;
+    return wmin >= 0.0f && wmax <= 1.0f;
+}
+__device__ __forceinline__ bool edge_triangle_intersect(const V3 &a0, const V3 &a1, const V3 &b0, const V3 &b1, const V3 &b2) {
+    // wrapper of contact.cu:2745-2759: everything relative to b0, then the shared predicate with v0 = 0
+    const V3 d1v = b1 - b0, d2v = b2 - b0, e0v = a0 - b0, e1v = a1 - b0;
+    const float d1[3] = {d1v.x - 0.0f, d1v.y - 0.0f, d1v.z - 0.0f}, d2[3] = {d2v.x - 0.0f, d2v.y - 0.0f, d2v.z - 0.0f};
+    const float A0[3] = {e0v.x - 0.0f, e0v.y - 0.0f, e0v.z - 0.0f}, A1[3] = {e1v.x - 0.0f, e1v.y - 0.0f, e1v.z - 0.0f};
+    const float nx = d1[1] * d2[2] - d1[2] * d2[1], ny = d1[2] * d2[0] - d1[0] * d2[2], nz = d1[0] * d2[1] - d1[1] * d2[0];
+    const float s1 = A0[0] * nx + A0[1] * ny + A0[2] * nz;
+    const float s2 = A1[0] * nx + A1[1] * ny + A1[2] * nz;
+    if (s1 * s2 < 0.0f) {
+        const float t = s1 / (s1 - s2);
+        const float r[3] = {(1.0f - t) * A0[0] + t * A1[0], (1.0f - t) * A0[1] + t * A1[1], (1.0f - t) * A0[2] + t * A1[2]};
+        return point_triangle_inside(r, d1, d2);
+    }
+    return false;
+}
+
+struct IsectArgs {
+    BvhView face, edge, vert;
+    const float4 *x;
+    const uint4 *faces;
+    const uint2 *edges;
+    const float4 *vcp, *ecp, *fcp;
+    const unsigned char *vfixed, *efixed, *ffixed, *vcollider;
+    PpfIntersectionRecord *records;
+    unsigned *counter; // [0] record counter, [1] error
+    int check_offsets;
+};
+
+__device__ void record_isect(const IsectArgs &A, unsigned type, unsigned e0, unsigned e1, const V3 *v0, unsigned n0, const V3 *v1, unsigned n1) {
+    const unsigned slot = atomicAdd(A.counter, 1u);
+    if (slot < PPF_MAX_INTERSECTION_RECORDS) {
+        PpfIntersectionRecord &r = A.records[slot];
+        r.type = type; r.elem0 = e0; r.elem1 = e1; r.num_verts0 = n0; r.num_verts1 = n1;
+        unsigned k = 0;
+        for (unsigned i = 0; i < n0; ++i) { r.positions[k++] = v0[i].x; r.positions[k++] = v0[i].y; r.positions[k++] = v0[i].z; }
+        for (unsigned i = 0; i < n1; ++i) { r.positions[k++] = v1[i].x; r.positions[k++] = v1[i].y; r.positions[k++] = v1[i].z; }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const unsigned e = A.edge.prim[t];
+    const uint2 ev = A.edges[e];
+    const V3 y0 = ld3c(A.x, ev.x), y1 = ld3c(A.x, ev.y);
+    Box q;
+    q.lx = fminf(y0.x, y1.x); q.ly = fminf(y0.y, y1.y); q.lz = fminf(y0.z, y1.z);
+    q.hx = fmaxf(y0.x, y1.x); q.hy = fmaxf(y0.y, y1.y); q.hz = fmaxf(y0.z, y1.z);
+    const float emass = A.ecp[e].w;
+    bool ok = bvh_query(A.face, q, [&](unsigned fi) {
+        const bool either_dyn = !A.ffixed[fi] || !A.efixed[e];
+        const bool either_nonzero = A.fcp[fi].w > 0.0f || emass > 0.0f;
+        const uint4 f = A.faces[fi];
+        const bool both_collider = A.vcollider[ev.x] && A.vcollider[f.x];
+        if (!either_dyn || !either_nonzero || both_collider) return;
+        if (ev.x == f.x || ev.x == f.y || ev.x == f.z || ev.y == f.x || ev.y == f.y || ev.y == f.z) return;
+        const V3 x0 = ld3c(A.x, f.x), x1 = ld3c(A.x, f.y), x2 = ld3c(A.x, f.z);
+        if (edge_triangle_intersect(y0, y1, x0, x1, x2)) {
+            const V3 fv[3] = {x0, x1, x2}, evv[2] = {y0, y1};
+            record_isect(A, 0, fi, e, fv, 3, evv, 2);
+        }
+    });
+    if (A.check_offsets) {
+        const float4 ep = A.ecp[e];
+        ok &= bvh_query(A.edge, q, [&](unsigned e2) {
+            if (!(e2 < e)) return;
+            const uint2 fv = A.edges[e2];
+            const bool either_dyn = !A.efixed[e] || !A.efixed[e2];
+            const bool either_nonzero = emass > 0.0f || A.ecp[e2].w > 0.0f;
+            const bool both_collider = A.vcollider[ev.x] && A.vcollider[fv.x];
+            if (!either_dyn || !either_nonzero || both_collider) return;
+            const float offset = ep.y + A.ecp[e2].y;
+            const bool shared = fv.x == ev.x || fv.x == ev.y || fv.y == ev.x || fv.y == ev.y;
+            bool hit = false;
+            const V3 q0 = ld3c(A.x, fv.x), q1 = ld3c(A.x, fv.y);
+            if (!shared) {
+                const C4 c = edge_edge_coeff(y0, y1, q0, q1);
+                const V3 d = (c.a * y0 + c.b * y1) - (c.c * q0 + c.d * q1);
+                hit = dot(d, d) < offset * offset;
+            } else {
+                const unsigned a[2] = {ev.x, ev.y}, b[2] = {fv.x, fv.y};
+                for (int i = 0; i < 2 && !hit; ++i)
+                    for (int j = 0; j < 2 && !hit; ++j)
+                        if (a[i] == b[j]) {
+                            const V3 p0 = ld3c(A.x, a[i]), p1 = ld3c(A.x, a[1 - i]), p2 = ld3c(A.x, b[1 - j]);
+                            const C2 c0 = point_edge_coeff_unclassified(p1, p0, p2), c1 = point_edge_coeff_unclassified(p2, p0, p1);
+                            const V3 d0 = (c0.a * p0 + c0.b * p2) - p1, d1 = (c1.a * p0 + c1.b * p1) - p2;
+                            hit = fminf(dot(d0, d0), dot(d1, d1)) < offset * offset;
+                        }
+            }
+            if (hit) {
+                const V3 a0[2] = {y0, y1}, a1[2] = {q0, q1};
+                record_isect(A, 1, e, e2, a0, 2, a1, 2);
+            }
+        });
+    }
+    if (!ok) atomicExch(A.counter + 1, 1u);
+}
+
+__global__ void __launch_bounds__(128) k_isect_vertex(IsectArgs A, unsigned nq) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    const unsigned v = A.vert.prim[t];
+    const float4 vp = A.vcp[v];
+    const V3 p = ld3c(A.x, v);
+    Box q;
+    q.lx = p.x - vp.y; q.ly = p.y - vp.y; q.lz = p.z - vp.y; q.hx = p.x + vp.y; q.hy = p.y + vp.y; q.hz = p.z + vp.y;
+    const bool ok = bvh_query(A.vert, q, [&](unsigned w) {
+        if (!(w < v)) return;
+        const float4 wp = A.vcp[w];
+        const bool either_dyn = !A.vfixed[v] || !A.vfixed[w];
+        const bool either_nonzero = vp.w > 0.0f || wp.w > 0.0f;
+        const bool both_collider = A.vcollider[v] && A.vcollider[w];
+        if (!either_dyn || !either_nonzero || both_collider) return;
+        const float offset = vp.y + wp.y;
+        const V3 qv = ld3c(A.x, w);
+        const V3 e = p - qv;
+        if (dot(e, e) < offset * offset) record_isect(A, 3, v, w, &p, 1, &qv, 1);
+    });
+    if (!ok) atomicExch(A.counter + 1, 1u);
+}
+
+static int g_has_offsets = -1;
+
+bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm) {
+    (void)prm;
+    cudaStream_t q = s.stream;
+    if (g_has_offsets < 0) {
+        g_has_offsets = 0;
+        for (unsigned i = 0; i < s.host.param_arrays.face.size; ++i)
+            if (s.host.param_arrays.face.data[i].offset > 0.0f) g_has_offsets = 1;
+    }
+    IsectArgs A;
+    A.face = view_of(s.bvh_face); A.edge = view_of(s.bvh_edge); A.vert = view_of(s.bvh_vert);
+    A.x = x; A.faces = s.face.p; A.edges = s.edge.p; A.vcp = s.vcp.p; A.ecp = s.ecp.p; A.fcp = s.fcp.p;
+    A.vfixed = s.vfixed.p; A.efixed = s.efixed.p; A.ffixed = s.ffixed.p; A.vcollider = s.vcollider.p;
+    A.records = s.isect_records.p;
+    A.counter = s.counters.p + 26;
+    A.check_offsets = g_has_offsets;
+    CUDA_OK(cudaMemsetAsync(A.counter, 0, 2 * sizeof(unsigned), q));
+    if (s.ne) k_isect_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);
+    if (g_has_offsets && s.nsv) k_isect_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(A, s.nsv);
+    LAUNCH_COUNT(2);
+    unsigned h[2];
+    CUDA_OK(cudaMemcpyAsync(h, A.counter, sizeof(h), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    if (h[1]) fatal(4, "BVH traversal stack overflow in the intersection check");
+    s.h_isect_count = std::min<unsigned>(h[0], PPF_MAX_INTERSECTION_RECORDS);
+    if (s.h_isect_count) CUDA_OK(cudaMemcpy(s.h_isect.data(), s.isect_records.p, sizeof(PpfIntersectionRecord) * s.h_isect_count, cudaMemcpyDeviceToHost));
+    return h[0] == 0;
+}
+
+} // namespace ppf
+
+// sorted contact-pair lists of the last assembly (extension used by the parity tests)
+extern "C" __attribute__((visibility("default"))) unsigned ppf_b200_fetch_pairs(unsigned kind, unsigned *out, unsigned cap) {
+    using namespace ppf;
+    State &s = g;
+    if (kind >= 4) return 0;
+    const unsigned n = s.pairs[kind].count;
+    if (!out || !cap || !n) return n;
+    std::vector<uint2> h(n);
+    CUDA_OK(cudaMemcpy(h.data(), s.pairs[kind].pairs.p, sizeof(uint2) * n, cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end(), [](const uint2 &a, const uint2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    for (unsigned i = 0; i < std::min(n, cap); ++i) { out[2 * i] = h[i].x; out[2 * i + 1] = h[i].y; }
+    return n;
+}

@@ -1,0 +1,165 @@
+// elastic.cu -- inertia/air and FEM (membrane + hinge bending) gradient/Hessian assembly into the
+// topology-fixed 3x3 block matrix.
+//
+// Replaces energy::embed_momentum_force_hessian (crates/ppf-cts-solver/src/cpp/energy/energy.cu:700-716,
+// per-vertex body 182-270) and energy::embed_elastic_force_hessian (energy.cu:718-794; face body
+// 304-364, hinge body 448-553).  One thread per element; the per-element math lives in
+// math_elastic.cuh / math_hinge.cuh; blocks are scattered through the DataSet's precomputed slot
+// tables (builder.rs:1368-1496) with fp32 atomics exactly like the reference's push_at
+// (csrmat.cu:586-594), lower-triangle sentinels skipped.
+#include "backend.hpp"
+#include "math_elastic.cuh"
+#include "math_hinge.cuh"
+
+namespace ppf {
+
+__device__ __forceinline__ V3 ld3(const float4 *p, unsigned i) { const float4 v = p[i]; return mk(v.x, v.y, v.z); }
+__device__ __forceinline__ void atomic_add3(float *dst, const V3 &v) {
+    if (v.x) atomicAdd(dst + 0, v.x);
+    if (v.y) atomicAdd(dst + 1, v.y);
+    if (v.z) atomicAdd(dst + 2, v.z);
+}
+__device__ __forceinline__ void atomic_add_block(float *val, unsigned slot, const float *m) {
+    if (slot == 0xFFFFFFFFu) return;
+    float *dst = val + size_t(9) * slot;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+        if (m[i]) atomicAdd(dst + i, m[i]);
+}
+
+struct MomentumArgs {
+    float dt, air_density, air_friction, iso_air, wind_w;
+    float3 wind;
+    int inactive_momentum;
+};
+
+__global__ void k_momentum(unsigned nv, const float4 *__restrict__ curr, const float4 *__restrict__ eval_x,
+                           const float4 *__restrict__ target, const float4 *__restrict__ vcp, const float *__restrict__ varea,
+                           const unsigned *__restrict__ fix_index, const unsigned *__restrict__ pull_index,
+                           const PpfPullPair *__restrict__ pull, const unsigned *__restrict__ vf_off,
+                           const unsigned *__restrict__ vf_idx, const uint4 *__restrict__ face, MomentumArgs a,
+                           float *__restrict__ force, float *__restrict__ diag) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv || fix_index[i] != 0) return;
+    const float mass = vcp[i].w, area = varea[i];
+    const V3 x = ld3(curr, i), y = ld3(eval_x, i);
+    V3 normal = mk(0.f, 0.f, 0.f);
+    for (unsigned k = vf_off[i]; k < vf_off[i + 1]; ++k) {
+        const uint4 f = face[vf_idx[k]];
+        const V3 z0 = ld3(eval_x, f.x), z1 = ld3(eval_x, f.y), z2 = ld3(eval_x, f.z);
+        normal += cross(z1 - z0, z2 - z0);
+    }
+    if (sqnorm(normal)) normal = normalized(normal);
+    V3 f = mk(0.f, 0.f, 0.f);
+    M3 H = m3_zero();
+    const float idt2 = 1.0f / (a.dt * a.dt);
+    const bool normal_nonzero = !(fabsf(normal.x) <= 1e-5f && fabsf(normal.y) <= 1e-5f && fabsf(normal.z) <= 1e-5f);
+    if (normal_nonzero && a.air_density) {
+        V3 wind = mk(0.f, 0.f, 0.f);
+        if (!a.inactive_momentum) wind = a.wind_w * mk(a.wind.x, a.wind.y, a.wind.z);
+        const V3 z = (y - x) - a.dt * wind;
+        const M3 nn = m3_outer(normal, normal);
+        const M3 P = m3_identity() - nn;
+        const float c = area * a.air_density;
+        f += c * ((normal * dot(normal, z)) * idt2 + (a.air_friction * idt2) * mul(P, z));
+        H += c * (idt2 * nn + (a.air_friction * idt2) * P);
+    }
+    const unsigned pi = pull_index[i];
+    if (pi) {
+        const PpfPullPair pp = pull[pi - 1];
+        f += pp.weight * (y - mk(pp.position.v[0], pp.position.v[1], pp.position.v[2]));
+        H += pp.weight * m3_identity();
+    } else {
+        f += (mass * idt2) * (y - ld3(target, i));
+        H += (mass * idt2) * m3_identity();
+    }
+    if (a.iso_air) {
+        f += (a.iso_air * idt2) * (y - x);
+        H += (a.iso_air * idt2) * m3_identity();
+    }
+    float *fo = force + size_t(3) * i; // one thread owns vertex i in this kernel
+    fo[0] += f.x; fo[1] += f.y; fo[2] += f.z;
+    float *dg = diag + size_t(9) * i;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dg[k] += H.m[k];
+}
+
+__global__ void __launch_bounds__(128) k_face(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ eval_x,
+                                              const float4 *__restrict__ fmat, const float4 *__restrict__ inv_rest,
+                                              const unsigned char *__restrict__ ffixed, const unsigned char *__restrict__ fskip,
+                                              const unsigned *__restrict__ slots, float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || ffixed[i] || fskip[i]) return;
+    const float4 m = fmat[i];
+    if (!(m.x > 0.0f)) return;
+    const uint4 f = face[i];
+    const float4 ir = inv_rest[i];
+    const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+    FaceElastic fe;
+    bw_face(ld3(eval_x, f.x), ld3(eval_x, f.y), ld3(eval_x, f.z), irv, m.x, m.y, m.z, fe);
+    const unsigned vi[3] = {f.x, f.y, f.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], fe.f[a]);
+    const unsigned *sl = slots + size_t(9) * i;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) atomic_add_block(val, sl[a * 3 + b], fe.H[a][b].m);
+}
+
+__global__ void __launch_bounds__(128) k_hinge(unsigned nh, const uint4 *__restrict__ hinge, const float4 *__restrict__ eval_x,
+                                               const float4 *__restrict__ hmat, const float *__restrict__ stiff,
+                                               const unsigned char *__restrict__ hfixed, const unsigned *__restrict__ slots,
+                                               float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nh || hfixed[i]) return;
+    const float k = stiff[i];
+    if (!(k > 0.0f)) return;
+    const uint4 h = hinge[i];
+    const unsigned vi[4] = {h.z, h.y, h.x, h.w}; // remap (dihedral_angle.hpp:15-17)
+    V3 X[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) X[a] = ld3(eval_x, vi[a]);
+    HingeElastic he;
+    hinge_force_hessian(X, hmat[i].z, he);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) atomic_add3(force + size_t(3) * vi[a], k * he.f[a]);
+    const unsigned *sl = slots + size_t(16) * i;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            const unsigned slot = sl[a * 4 + b];
+            if (slot == 0xFFFFFFFFu) continue;
+            float blk[9];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) blk[c * 3 + r] = k * he.H[(3 * b + c) * 12 + (3 * a + r)];
+            atomic_add_block(val, slot, blk);
+        }
+}
+
+void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
+    MomentumArgs a;
+    a.dt = dt; a.air_density = prm.air_density; a.air_friction = prm.air_friction; a.iso_air = prm.isotropic_air_friction;
+    a.wind = make_float3(prm.wind.v[0], prm.wind.v[1], prm.wind.v[2]);
+    a.inactive_momentum = prm.inactive_momentum;
+    { // utility.cu get_wind_weight (float time)
+        const float time = (float)prm.time;
+        const float angle = 30.0f * time, t = 0.25f;
+        a.wind_w = t * (0.5f * (1.0f + sinf(angle))) + (1.0f - t);
+    }
+    k_momentum<<<div_up(s.nv, 128), 128, 0, s.stream>>>(s.nv, s.curr.p, s.eval_x.p, s.target.p, s.vcp.p, s.varea.p, s.fix_index.p,
+                                                        s.pull_index.p, s.pull.p, s.vf_off.p, s.vf_idx.p, s.face.p, a, s.force.p, s.diag.p);
+    LAUNCH_COUNT(1);
+}
+
+void assemble_elastic(State &s, float dt, const PpfParamSet &prm) {
+    (void)dt; (void)prm;
+    if (s.nf) k_face<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.fmat.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
+                                                             s.face_slots.p, s.force.p, s.fx_val.p);
+    if (s.nh) k_hinge<<<div_up(s.nh, 128), 128, 0, s.stream>>>(s.nh, s.hinge.p, s.eval_x.p, s.hmat.p, s.hinge_stiff.p, s.hfixed.p,
+                                                              s.hinge_slots.p, s.force.p, s.fx_val.p);
+    LAUNCH_COUNT(2);
+}
+
+} // namespace ppf

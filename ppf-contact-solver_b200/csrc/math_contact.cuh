@@ -1,0 +1,107 @@
+// math_contact.cuh -- cubic barrier, elasticity-inclusive contact stiffness, lagged Coulomb friction.
+//
+// Restates (fp32, same evaluation order):
+//   cubic barrier          crates/ppf-cts-solver/src/cpp/barrier/cubic.hpp:13-41
+//   edge gradient/hessian  barrier/barrier.cu:103-114
+//   compute_stiffness<N>   barrier/barrier.cu:50-86   kappa = w^T (H_elastic,local + diag(m/g^2)) w
+//   Friction               energy/model/friction.hpp:19-82
+// Only the cubic barrier is implemented (Barrier::Cubic is the default and the only one the
+// BASELINE configs use); the backend refuses quad/log loudly at initialize.
+#pragma once
+#include "vecmath.cuh"
+
+namespace ppf {
+
+PPF_HD float cubic_gradient(float g, float ghat, float offset) {
+    g -= offset;
+    const float y = g - ghat;
+    return y < 0.0f ? -2.0f * y * y / ghat : 0.0f;
+}
+PPF_HD float cubic_curvature(float g, float ghat, float offset) {
+    g -= offset;
+    return (g - ghat < 0.0f) ? 4.0f * (1.0f - g / ghat) : 0.0f;
+}
+PPF_HD V3 barrier_edge_gradient(const V3 &e, float ghat, float offset) {
+    const float g = norm(e);
+    const V3 n = e / g;
+    return n * cubic_gradient(g, ghat, offset);
+}
+PPF_HD M3 barrier_edge_hessian(const V3 &e, float ghat, float offset) {
+    const float c = cubic_curvature(norm(e), ghat, offset);
+    // c * e * e^T / |e|^2  evaluated left to right: ((c*e) e^T) / sq
+    const V3 ce = c * e;
+    const float sq = sqnorm(e);
+    M3 o = m3_outer(ce, e);
+    for (int i = 0; i < 9; ++i) o.m[i] = o.m[i] / sq;
+    return o;
+}
+
+// kappa = w^T L w, L(ii,jj) = Hel(ii,jj) + [ii==jj] (m_ii / g^2) I, w = normalize([value_ii * e]).
+// `blk` holds the N*N gathered elastic blocks Hel(index[ii], index[jj]) (zero where absent).
+template <int N> PPF_HD float contact_stiffness(const float *value, const float *mass, const M3 *blk, const V3 &e, float offset) {
+    const float nrm = norm(e);
+    const float g = nrm - offset;
+    const float sqr_x = g * g;
+    float m_max = 0.0f;
+    for (int ii = 0; ii < N; ++ii)
+        if (mass[ii] > m_max) m_max = mass[ii];
+    float w[3 * N];
+    for (int ii = 0; ii < N; ++ii) {
+        const float val = value[ii];
+        w[3 * ii + 0] = val * e.x; w[3 * ii + 1] = val * e.y; w[3 * ii + 2] = val * e.z;
+    }
+    float acc = 0.0f;
+    for (int i = 0; i < 3 * N; ++i) acc = acc + w[i] * w[i];
+    const float wn = sqrtf(acc);
+    if (wn > 0.0f)
+        for (int i = 0; i < 3 * N; ++i) w[i] = w[i] / wn;
+    // r = L * w accumulated column by column (smat.hpp operator*), then r . w
+    float r[3 * N];
+    for (int i = 0; i < 3 * N; ++i) r[i] = 0.0f;
+    for (int jj = 0; jj < N; ++jj)
+        for (int kc = 0; kc < 3; ++kc) {
+            const float bkc = w[3 * jj + kc];
+            for (int ii = 0; ii < N; ++ii) {
+                const float m_ii = mass[ii] > 0.0f ? mass[ii] : m_max;
+                for (int kr = 0; kr < 3; ++kr) {
+                    float a = 0.0f + blk[ii * N + jj].m[kr + kc * 3];
+                    if (ii == jj) a = a + (m_ii / sqr_x) * (kr == kc ? 1.0f : 0.0f);
+                    r[3 * ii + kr] = r[3 * ii + kr] + a * bkc;
+                }
+            }
+        }
+    float kappa = 0.0f;
+    for (int i = 0; i < 3 * N; ++i) kappa = kappa + r[i] * w[i];
+    return kappa;
+}
+
+struct FrictionOut {
+    V3 grad;
+    M3 hess;
+    float lambda;
+};
+// friction.hpp:19-82
+PPF_HD FrictionOut friction_eval(const V3 &force_contact, const V3 &dx, const V3 &normal, float mu, float min_dx) {
+    FrictionOut o;
+    const float contact = -dot(normal, force_contact);
+    const V3 u = dx - normal * dot(normal, dx);
+    const float u_norm = sqrtf(sqnorm(u));
+    const bool kinetic = u_norm > min_dx;
+    const V3 slip_dir = kinetic ? u / u_norm : mk(0.0f, 0.0f, 0.0f);
+    o.lambda = mu > 0.0f ? mu * contact / fmaxf(min_dx, u_norm) : 0.0f;
+    o.grad = o.lambda * u;
+    if (kinetic) {
+        const V3 w = cross(normal, slip_dir);
+        o.hess = o.lambda * m3_outer(w, w);
+    } else {
+        const M3 P = m3_identity() - m3_outer(normal, normal);
+        o.hess = o.lambda * P;
+    }
+    return o;
+}
+
+PPF_HD float combine_friction(float a, float b, int mode) { // contact.cu:64-74 (Min=0, Max=1, Mean=2)
+    return mode == 1 ? fmaxf(a, b) : (mode == 2 ? 0.5f * (a + b) : fminf(a, b));
+}
+
+} // namespace ppf

@@ -1,0 +1,648 @@
+// pcg.cu -- block-Jacobi preconditioned conjugate gradients on the assembled Newton system
+//   (A_dyn + B_fixed + C_diag) dx = force        (reference: solver/solver.cu:2180-2321, cg_device 921-1383)
+//
+// B200 design (SpMV algorithmic bytes 40*N_off + 60*N_row):
+//  * Once per Newton iteration the assembled matrices are re-packed into a solver-private
+//    coordinate form: every strictly-upper 3x3 block of B_fixed and A_dyn appears ONCE as
+//    (row, col, nine SoA value planes); diagonals A_ii + B_ii + C_i are merged, symmetrised and kept
+//    as six SoA planes, as is the block-Jacobi inverse.  Every load of the streaming kernels is a
+//    fully coalesced 128-byte line; nothing is 36-byte AoS.
+//  * SpMV is nnz-parallel: one lane per stored block, a persistent grid (SMs x 8 CTAs) striding
+//    over the block list.  H p_col is combined across the lanes of a warp that share a row with a
+//    segmented shuffle scan and leaves as one 16-byte vector reduction (red.global.add.v4.f32,
+//    sm_90+) per row run; H^T p_row leaves as one vector reduction per block.  No lane idles on
+//    short rows (cloth rows hold ~5 blocks), which is what bounded a lanes-per-row CSR kernel.
+//    p.Ap and sum|terms| are fused in.  The diagonal product y = D p is produced by the kernel that
+//    writes p, so y needs no separate zero-fill.
+//  * An iteration is 3 kernels (SpMV+dots; fused x/r/z update + r.z, |r|_1; direction update +
+//    y = D p + scalar tail).  alpha, beta, residual and the breakdown verdicts never leave the
+//    device; each kernel folds its partial sums with ONE double atomic per CTA of a persistent grid.
+//    Iterations are replayed from a CUDA graph in batches; the host polls a pinned status word per batch.
+//  * Semantics kept from the reference: L1 relative residual against the SEEDED initial residual
+//    (solver.cu:1002-1030), curvature-noise verdict 256*eps*sum|terms| (solver.cu:66-114),
+//    truncate-on-noise returns success, negative curvature / r.z <= 0 are fatal, block-Jacobi
+//    inverse through a floored symmetric eigendecomposition (solver.cu:357-400).
+#include "backend.hpp"
+#include <algorithm>
+#include <cmath>
+
+namespace ppf {
+
+static constexpr int PCG_BLOCK = 256;
+static constexpr float CG_NOISE_SLACK = 256.0f;
+static constexpr float CG_FLOAT_EPS = 1.19209290e-7f;
+
+enum { ST_RUNNING = 0, ST_CONVERGED = 1, ST_TRUNCATED = 2, ST_CAP = 3, ST_FATAL_PAP = 4, ST_FATAL_RZ = 5, ST_NONFINITE = 6 };
+
+struct CgScalars {                 // device-resident control block
+    double acc_pap[2], acc_abs[2]; // per-parity accumulators of p.Ap and sum|terms|
+    double rz[2], err[2];          // r.z and |r|_1, double-buffered by iteration parity
+    double err0;
+    int iter;                      // completed iterations
+    int status;                    // ST_*
+    int breakdown;                 // latched in the update kernel: 0 none, 1 noise, 2 negative/NaN
+    float break_val;
+    float tol;
+    int max_iter;
+    float last_resid;
+    unsigned done_counter;
+};
+
+struct PackedMatrix {
+    unsigned n = 0;
+    unsigned nnz_f = 0, nnz_d = 0;   // strictly-upper blocks of the fixed / dynamic parts
+    size_t cap = 0;                  // plane stride of `val`
+    DBuf<unsigned> row, col;         // per stored block
+    DBuf<float> val;                 // 9 planes x cap
+    DBuf<unsigned> fx_pos;           // per ORIGINAL fixed slot: position in the block list, 0xFFFFFFFF for diagonals
+    DBuf<float> D, Pinv;             // 6 planes x n: (00, 11, 22, 01, 02, 12)
+    DBuf<float4> x, r, z, p, y;
+    DBuf<CgScalars> sc;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    unsigned graph_nnz = ~0u;
+    const void *graph_val = nullptr;
+    int *h_status = nullptr;         // pinned mirror of {iter, status, last_resid}
+    unsigned grid = 0;               // persistent grid size
+    bool ready = false;
+};
+static PackedMatrix P;
+
+static void pcg_init(State &s) {
+    const unsigned n = s.nv;
+    P.n = n;
+    const PpfVecVecU32 &t = s.host.fixed_index_table;
+    const unsigned nnz = t.offset[n];
+    std::vector<unsigned> pos(nnz, 0xFFFFFFFFu), row, col;
+    row.reserve(nnz); col.reserve(nnz);
+    for (unsigned i = 0; i < n; ++i)
+        for (unsigned k = t.offset[i]; k < t.offset[i + 1]; ++k) {
+            const unsigned j = t.data[k];
+            if (j == i) continue;
+            pos[k] = (unsigned)row.size();
+            row.push_back(i);
+            col.push_back(j);
+        }
+    P.nnz_f = (unsigned)row.size();
+    cudaStream_t q = s.stream;
+    P.cap = size_t(P.nnz_f) + 1024;
+    P.row.reserve(P.cap); P.col.reserve(P.cap); P.val.reserve(size_t(9) * P.cap);
+    P.cap = P.row.cap; // DBuf over-allocates; use what we really have for all three
+    P.col.reserve(P.cap); P.val.reserve(size_t(9) * P.cap);
+    CUDA_OK(cudaMemcpyAsync(P.row.p, row.data(), sizeof(unsigned) * row.size(), cudaMemcpyHostToDevice, q));
+    CUDA_OK(cudaMemcpyAsync(P.col.p, col.data(), sizeof(unsigned) * col.size(), cudaMemcpyHostToDevice, q));
+    P.fx_pos.upload(pos.data(), nnz, q);
+    CUDA_OK(cudaStreamSynchronize(q));
+    P.D.reserve(size_t(6) * n); P.Pinv.reserve(size_t(6) * n);
+    P.x.reserve(n); P.r.reserve(n); P.z.reserve(n); P.p.reserve(n); P.y.reserve(n);
+    P.sc.reserve(1);
+    CUDA_OK(cudaMallocHost(&P.h_status, 64));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    P.grid = (unsigned)sms * 8u;
+    if (const char *e = getenv("PPF_B200_PCG_GRID")) P.grid = (unsigned)atoi(e);
+    P.ready = true;
+}
+
+// make room for nnz_d dynamic blocks behind the fixed ones (plane stride may change)
+static void pcg_reserve(State &s, unsigned nnz_d) {
+    const size_t need = size_t(P.nnz_f) + nnz_d;
+    if (need <= P.cap) return;
+    const size_t want = need + need / 4 + 1024;
+    P.row.reserve_keep(want, s.stream);
+    P.col.reserve_keep(want, s.stream);
+    P.val.reserve(size_t(9) * want); // values are re-packed every solve
+    P.cap = want;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dirichlet elimination of pinned rows (reference: main/main.cu:954-1049) on the assembled
+// original-order structures: lift, zero blocks, identity diagonal, prescribed rhs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lift_sub(float *force, unsigned row, const float *blk, float px, float py, float pz, bool transposed) {
+    float c0, c1, c2;
+    if (transposed) {
+        c0 = blk[0] * px + blk[1] * py + blk[2] * pz;
+        c1 = blk[3] * px + blk[4] * py + blk[5] * pz;
+        c2 = blk[6] * px + blk[7] * py + blk[8] * pz;
+    } else {
+        c0 = blk[0] * px + blk[3] * py + blk[6] * pz;
+        c1 = blk[1] * px + blk[4] * py + blk[7] * pz;
+        c2 = blk[2] * px + blk[5] * py + blk[8] * pz;
+    }
+    atomicAdd(force + 3 * size_t(row) + 0, -c0);
+    atomicAdd(force + 3 * size_t(row) + 1, -c1);
+    atomicAdd(force + 3 * size_t(row) + 2, -c2);
+}
+
+__global__ void k_dirichlet_rows(unsigned n, const unsigned char *__restrict__ mask, const unsigned *__restrict__ off,
+                                 const unsigned *__restrict__ col, float *__restrict__ val, const float4 *__restrict__ eval_x,
+                                 const float4 *__restrict__ target, float *__restrict__ force) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool mi = mask[i] != 0;
+    for (unsigned k = off[i]; k < off[i + 1]; ++k) {
+        const unsigned j = col[k];
+        const bool mj = mask[j] != 0;
+        float *blk = val + size_t(9) * k;
+        if (mi != mj) {
+            if (mj) {
+                const float4 e = eval_x[j], t = target[j];
+                lift_sub(force, i, blk, e.x - t.x, e.y - t.y, e.z - t.z, false);
+            } else {
+                const float4 e = eval_x[i], t = target[i];
+                lift_sub(force, j, blk, e.x - t.x, e.y - t.y, e.z - t.z, true);
+            }
+        }
+        if (mi || mj)
+            for (int c = 0; c < 9; ++c) blk[c] = 0.0f;
+    }
+}
+__global__ void k_dirichlet_diag(unsigned n, const unsigned char *__restrict__ mask, const float4 *__restrict__ eval_x,
+                                 const float4 *__restrict__ target, float *__restrict__ diag, float *__restrict__ force) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !mask[i]) return;
+    float *d = diag + size_t(9) * i;
+    for (int c = 0; c < 9; ++c) d[c] = (c == 0 || c == 4 || c == 8) ? 1.0f : 0.0f;
+    const float4 e = eval_x[i], t = target[i];
+    force[3 * size_t(i) + 0] = e.x - t.x;
+    force[3 * size_t(i) + 1] = e.y - t.y;
+    force[3 * size_t(i) + 2] = e.z - t.z;
+}
+
+void apply_dirichlet(State &s) {
+    cudaStream_t q = s.stream;
+    const unsigned n = s.nv;
+    if (s.dyn_nnz) k_dirichlet_rows<<<div_up(n, 128), 128, 0, q>>>(n, s.vfixed.p, s.dyn_off.p, s.dyn_col.p, s.dyn_val.p, s.eval_x.p, s.target.p, s.force.p);
+    k_dirichlet_rows<<<div_up(n, 128), 128, 0, q>>>(n, s.vfixed.p, s.fx_off.p, s.fx_col.p, s.fx_val.p, s.eval_x.p, s.target.p, s.force.p);
+    k_dirichlet_diag<<<div_up(n, 128), 128, 0, q>>>(n, s.vfixed.p, s.eval_x.p, s.target.p, s.diag.p, s.force.p);
+    LAUNCH_COUNT(3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_fixed(unsigned nnz, const float *__restrict__ val, const unsigned *__restrict__ pos,
+                             float *__restrict__ out, size_t plane) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const unsigned d = pos[k];
+    if (d == 0xFFFFFFFFu) return;
+    const float *m = val + size_t(9) * k;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) out[size_t(e) * plane + d] = m[e];
+}
+
+__global__ void k_pack_dyn(unsigned n, const unsigned *__restrict__ off, const unsigned *__restrict__ col, const float *__restrict__ val,
+                           unsigned base, unsigned *__restrict__ out_row, unsigned *__restrict__ out_col, float *__restrict__ out,
+                           size_t plane) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (unsigned k = off[i]; k < off[i + 1]; ++k) {
+        const unsigned d = base + k;
+        out_row[d] = i;
+        out_col[d] = col[k];
+        const float *m = val + size_t(9) * k;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) out[size_t(e) * plane + d] = m[e];
+    }
+}
+
+// symmetric 3x3 inverse through a Jacobi eigendecomposition with eigenvalues floored at 1e-6*lmax
+// (the reference floors the same way after its closed-form eigen solve, solver.cu:357-400)
+__device__ void sym3_inverse_floored(const float *s6, float *out6) {
+    float a[3][3];
+    a[0][0] = s6[0]; a[1][1] = s6[1]; a[2][2] = s6[2];
+    a[0][1] = a[1][0] = s6[3]; a[0][2] = a[2][0] = s6[4]; a[1][2] = a[2][1] = s6[5];
+    float v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    float scale = 0.0f;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) scale = fmaxf(scale, fabsf(a[r][c]));
+    const float tiny = 1e-9f * scale;
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        const float off = fmaxf(fabsf(a[0][1]), fmaxf(fabsf(a[0][2]), fabsf(a[1][2])));
+        if (off <= tiny) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            const float apq = a[p][q];
+            if (fabsf(apq) <= tiny) continue;
+            const float tau = (a[q][q] - a[p][p]) / (2.0f * apq);
+            const float t = (tau >= 0.0f ? 1.0f : -1.0f) / (fabsf(tau) + sqrtf(1.0f + tau * tau));
+            const float c = 1.0f / sqrtf(1.0f + t * t), sn = t * c;
+            const float app = a[p][p], aqq = a[q][q];
+            a[p][p] = c * c * app - 2.0f * sn * c * apq + sn * sn * aqq;
+            a[q][q] = sn * sn * app + 2.0f * sn * c * apq + c * c * aqq;
+            a[p][q] = a[q][p] = 0.0f;
+            const int k = 3 - p - q;
+            const float akp = a[k][p], akq = a[k][q];
+            a[k][p] = a[p][k] = c * akp - sn * akq;
+            a[k][q] = a[q][k] = sn * akp + c * akq;
+            for (int r = 0; r < 3; ++r) {
+                const float vrp = v[r][p], vrq = v[r][q];
+                v[r][p] = c * vrp - sn * vrq;
+                v[r][q] = sn * vrp + c * vrq;
+            }
+        }
+    }
+    const float lmax = fmaxf(a[0][0], fmaxf(a[1][1], a[2][2]));
+    const float floor_l = lmax * 1.0e-6f;
+    float inv[3];
+    for (int k = 0; k < 3; ++k) inv[k] = 1.0f / fmaxf(a[k][k], floor_l);
+    const int rr[6] = {0, 1, 2, 0, 0, 1}, cc[6] = {0, 1, 2, 1, 2, 2};
+    for (int e = 0; e < 6; ++e) out6[e] = inv[0] * v[rr[e]][0] * v[cc[e]][0] + inv[1] * v[rr[e]][1] * v[cc[e]][1] + inv[2] * v[rr[e]][2] * v[cc[e]][2];
+}
+
+__global__ void k_pack_diag(unsigned n, const unsigned *__restrict__ diag_slot, const float *__restrict__ fx_val,
+                            const float *__restrict__ diag, float *__restrict__ D, float *__restrict__ Pinv, int *__restrict__ bad) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *f = fx_val + size_t(9) * diag_slot[i];
+    const float *c = diag + size_t(9) * i;
+    float m[9];
+    for (int e = 0; e < 9; ++e) m[e] = f[e] + c[e];
+    // exact fp32 symmetry (the assembled block is symmetric only up to atomic-accumulation order)
+    const float s6[6] = {m[0], m[4], m[8], 0.5f * (m[3] + m[1]), 0.5f * (m[6] + m[2]), 0.5f * (m[7] + m[5])};
+    float inv6[6];
+    sym3_inverse_floored(s6, inv6);
+    bool fin = true;
+    for (int e = 0; e < 6; ++e) {
+        D[size_t(e) * n + i] = s6[e];
+        Pinv[size_t(e) * n + i] = inv6[e];
+        fin = fin && isfinite(s6[e]) && isfinite(inv6[e]);
+    }
+    if (!fin || !(s6[0] + s6[1] + s6[2] > 0.0f)) atomicExch(bad, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels of the iteration
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.0f) : "memory");
+}
+
+// one double atomic per CTA for each of two partial sums
+__device__ __forceinline__ void block_accumulate2(float a, float b, double *dst_a, double *dst_b) {
+    __shared__ float sm_a[PCG_BLOCK / 32], sm_b[PCG_BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm_a[w] = a; sm_b[w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = l < PCG_BLOCK / 32 ? sm_a[l] : 0.f;
+        b = l < PCG_BLOCK / 32 ? sm_b[l] : 0.f;
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (l == 0) {
+            atomicAdd(dst_a, (double)a);
+            atomicAdd(dst_b, (double)b);
+        }
+    }
+}
+
+// y += (L + L^T) p over the stored strictly-upper blocks; fused partial p.(L+L^T)p and sum|terms|.
+// y already holds D p (written by the kernel that produced p).
+__global__ void __launch_bounds__(PCG_BLOCK) k_spmv(unsigned nnz, const unsigned *__restrict__ row, const unsigned *__restrict__ col,
+                                                    const float *__restrict__ val, size_t plane, const float4 *__restrict__ p,
+                                                    float4 *__restrict__ y, CgScalars *sc, int with_dots) {
+    if (with_dots && sc->status != ST_RUNNING) return;
+    const unsigned lane = threadIdx.x & 31;
+    float dot = 0.f, absdot = 0.f;
+    const unsigned stride = gridDim.x * blockDim.x;
+    // every lane of a warp iterates the same number of times (warp-uniform trip count) so the shuffles stay converged
+    const unsigned nnz_pad = (nnz + 31u) & ~31u;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz_pad; k += stride) {
+        const bool on = k < nnz;
+        unsigned a = 0xFFFFFFFFu;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if (on) {
+            a = __ldg(row + k);
+            const unsigned b = __ldg(col + k);
+            const float h0 = __ldg(val + k), h1 = __ldg(val + plane + k), h2 = __ldg(val + 2 * plane + k);
+            const float h3 = __ldg(val + 3 * plane + k), h4 = __ldg(val + 4 * plane + k), h5 = __ldg(val + 5 * plane + k);
+            const float h6 = __ldg(val + 6 * plane + k), h7 = __ldg(val + 7 * plane + k), h8 = __ldg(val + 8 * plane + k);
+            const float4 pa = p[a], pb = p[b];
+            s0 = h0 * pb.x + h3 * pb.y + h6 * pb.z;
+            s1 = h1 * pb.x + h4 * pb.y + h7 * pb.z;
+            s2 = h2 * pb.x + h5 * pb.y + h8 * pb.z;
+            red_add_v4(y + b, h0 * pa.x + h1 * pa.y + h2 * pa.z, h3 * pa.x + h4 * pa.y + h5 * pa.z, h6 * pa.x + h7 * pa.y + h8 * pa.z);
+            const float term = 2.0f * (pa.x * s0 + pa.y * s1 + pa.z * s2);
+            dot += term;
+            absdot += fabsf(term);
+        }
+        // segmented inclusive scan over lanes that share a row (runs are contiguous: blocks are row-sorted)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ra = __shfl_up_sync(0xffffffffu, a, o);
+            const float t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+            if (lane >= (unsigned)o && ra == a) { s0 += t0; s1 += t1; s2 += t2; }
+        }
+        const unsigned next = __shfl_down_sync(0xffffffffu, a, 1);
+        if (on && (lane == 31 || next != a)) red_add_v4(y + a, s0, s1, s2);
+    }
+    if (!with_dots) return;
+    const int par = sc->iter & 1;
+    block_accumulate2(dot, absdot, &sc->acc_pap[par], &sc->acc_abs[par]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // slots the NEXT update kernel accumulates into
+        sc->rz[par ^ 1] = 0.0;
+        sc->err[par ^ 1] = 0.0;
+    }
+}
+
+__device__ __forceinline__ float4 sym6_mul(const float *__restrict__ M, size_t n, size_t i, const float4 v) {
+    const float m00 = __ldg(M + i), m11 = __ldg(M + n + i), m22 = __ldg(M + 2 * n + i);
+    const float m01 = __ldg(M + 3 * n + i), m02 = __ldg(M + 4 * n + i), m12 = __ldg(M + 5 * n + i);
+    return make_float4(m00 * v.x + m01 * v.y + m02 * v.z, m01 * v.x + m11 * v.y + m12 * v.z, m02 * v.x + m12 * v.y + m22 * v.z, 0.f);
+}
+
+// fused x/r/z update with in-thread alpha (reference: cg_fused_update_kernel, solver.cu:431-514)
+__global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, const float4 *__restrict__ p, const float4 *__restrict__ y, float4 *__restrict__ x,
+                                                      float4 *__restrict__ r, float4 *__restrict__ z, const float *__restrict__ Pinv, CgScalars *sc) {
+    if (sc->status != ST_RUNNING) return;
+    const int par = sc->iter & 1;
+    const float pAp = (float)sc->acc_pap[par];
+    const float noise = CG_NOISE_SLACK * CG_FLOAT_EPS * (float)sc->acc_abs[par];
+    const float rz0 = (float)sc->rz[par];
+    float alpha;
+    int verdict = 0; // 0 ok, 1 truncate, 2 fatal
+    if (pAp > noise) alpha = rz0 / pAp;
+    else { alpha = 0.0f; verdict = (pAp < -noise || pAp != pAp) ? 2 : 1; }
+    float rz = 0.f, err = 0.f;
+    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const float4 pa = p[a], ya = y[a];
+        float4 xa = x[a], ra = r[a];
+        xa.x += alpha * pa.x; xa.y += alpha * pa.y; xa.z += alpha * pa.z;
+        ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
+        x[a] = xa; r[a] = ra;
+        const float4 za = sym6_mul(Pinv, n, a, ra);
+        z[a] = za;
+        rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
+        err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+    }
+    block_accumulate2(rz, err, &sc->rz[par ^ 1], &sc->err[par ^ 1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (verdict) { sc->breakdown = verdict; sc->break_val = pAp; }
+        sc->acc_pap[par ^ 1] = 0.0; // accumulators of the NEXT iteration (direction kernel + SpMV)
+        sc->acc_abs[par ^ 1] = 0.0;
+    }
+}
+
+// p = z + beta p;  y = D p (start value of the next SpMV) with the diagonal's share of p.Ap;  scalar tail
+__global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float4 *__restrict__ z, float4 *__restrict__ p, float4 *__restrict__ y,
+                                                         const float *__restrict__ D, CgScalars *sc) {
+    if (sc->status != ST_RUNNING) return;
+    const int par = sc->iter & 1;
+    const float rz0 = (float)sc->rz[par], rz1 = (float)sc->rz[par ^ 1];
+    const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
+    float dot = 0.f, absdot = 0.f;
+    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        const float4 za = z[a];
+        float4 pa = p[a];
+        pa.x = za.x + beta * pa.x; pa.y = za.y + beta * pa.y; pa.z = za.z + beta * pa.z;
+        p[a] = pa;
+        const float4 v = sym6_mul(D, n, a, pa);
+        y[a] = v;
+        const float term = pa.x * v.x + pa.y * v.y + pa.z * v.z;
+        dot += term;
+        absdot += fabsf(term);
+    }
+    block_accumulate2(dot, absdot, &sc->acc_pap[par ^ 1], &sc->acc_abs[par ^ 1]);
+    // the LAST block to finish runs the scalar tail, after every block has read this iteration's scalars
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&sc->done_counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        sc->done_counter = 0;
+        const int it = sc->iter + 1;
+        const double reresid = sc->err[par ^ 1] / sc->err0;
+        sc->last_resid = (float)reresid;
+        int st = ST_RUNNING;
+        if (reresid < (double)sc->tol) st = ST_CONVERGED;
+        else if (sc->breakdown == 1) st = ST_TRUNCATED;
+        else if (sc->breakdown == 2) st = ST_FATAL_PAP;
+        else if (!(rz0 > 0.0f)) st = ST_FATAL_RZ;
+        else if (!isfinite(reresid)) st = ST_NONFINITE;
+        else if (it >= sc->max_iter) st = ST_CAP;
+        sc->iter = it;
+        __threadfence();
+        sc->status = st;
+    }
+}
+
+// setup helpers -------------------------------------------------------------------------------
+__global__ void k_load(unsigned n, const float *__restrict__ force, const float *__restrict__ dx, float4 *__restrict__ r, float4 *__restrict__ x,
+                       float4 *__restrict__ p, float4 *__restrict__ y, const float *__restrict__ D) {
+    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const size_t i = a;
+    r[a] = make_float4(force[3 * i], force[3 * i + 1], force[3 * i + 2], 0.f);
+    const float4 x0 = make_float4(dx[3 * i], dx[3 * i + 1], dx[3 * i + 2], 0.f);
+    x[a] = x0;
+    p[a] = x0;                   // SpMV input
+    y[a] = sym6_mul(D, n, a, x0); // y = D x0
+}
+// r = b - A x0; z = P r; p = z; y = D p; rz0, err0, diagonal share of the first p.Ap
+__global__ void k_residual_init(unsigned n, float4 *__restrict__ y, float4 *__restrict__ r, float4 *__restrict__ z, float4 *__restrict__ p,
+                                const float *__restrict__ Pinv, const float *__restrict__ D, CgScalars *sc) {
+    float rz = 0.f, err = 0.f, dot = 0.f, absdot = 0.f;
+    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+        float4 ra = r[a];
+        const float4 ya = y[a];
+        ra.x -= ya.x; ra.y -= ya.y; ra.z -= ya.z;
+        r[a] = ra;
+        const float4 za = sym6_mul(Pinv, n, a, ra);
+        z[a] = za;
+        p[a] = za;
+        const float4 v = sym6_mul(D, n, a, za);
+        y[a] = v;
+        rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
+        err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+        const float term = za.x * v.x + za.y * v.y + za.z * v.z;
+        dot += term;
+        absdot += fabsf(term);
+    }
+    block_accumulate2(rz, err, &sc->rz[0], &sc->err0);
+    __syncthreads();
+    block_accumulate2(dot, absdot, &sc->acc_pap[0], &sc->acc_abs[0]);
+}
+__global__ void k_store(unsigned n, const float4 *__restrict__ x, float *__restrict__ dx) {
+    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const float4 v = x[a];
+    dx[3 * size_t(a)] = v.x; dx[3 * size_t(a) + 1] = v.y; dx[3 * size_t(a) + 2] = v.z;
+}
+
+static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
+    const unsigned nnz = P.nnz_f + P.nnz_d;
+    if (!nnz) return;
+    const unsigned grid = std::min(P.grid, div_up(nnz, PCG_BLOCK));
+    k_spmv<<<grid, PCG_BLOCK, 0, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+}
+
+static void issue_iteration(State &s) {
+    const unsigned n = P.n;
+    const unsigned gv = std::min(P.grid, div_up(n, PCG_BLOCK));
+    launch_spmv(s, P.p.p, P.y.p, 1);
+    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.p.p, P.y.p, P.x.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p);
+    k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.z.p, P.p.p, P.y.p, P.D.p, P.sc.p);
+}
+
+// PPF_B200_PCG_TUNE=1: time the kernels of the iteration in isolation on the first packed system
+// (CUDA events on the backend stream, 20 launches each after 3 warm-ups).  Diagnostic only.
+static void pcg_tune(State &s) {
+    cudaStream_t q = s.stream;
+    const unsigned n = P.n;
+    const unsigned gv = std::min(P.grid, div_up(n, PCG_BLOCK));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const double nnz = double(P.nnz_f) + P.nnz_d;
+    auto time_it = [&](const char *name, double bytes, auto &&fn) {
+        for (int k = 0; k < 3; ++k) fn();
+        cudaEventRecord(e0, q);
+        for (int k = 0; k < 20; ++k) fn();
+        cudaEventRecord(e1, q);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("[pcg-tune] %-28s %8.1f us/launch  %8.1f GB/s\n", name, 1e3 * ms / 20, bytes / (ms / 20 * 1e-3) * 1e-9);
+    };
+    CgScalars h{};
+    h.status = ST_RUNNING; h.tol = 0.f; h.max_iter = 1 << 30; h.err0 = 1.0; h.rz[0] = h.rz[1] = 1.0; h.acc_pap[0] = h.acc_pap[1] = 1e30;
+    cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q);
+    const unsigned grid_save = P.grid;
+    for (unsigned g : {148u * 4, 148u * 8, 148u * 16, 148u * 32}) {
+        P.grid = g;
+        char nm[64];
+        snprintf(nm, sizeof(nm), "spmv offdiag grid=%u", g);
+        time_it(nm, 40.0 * nnz + 24.0 * n, [&] { launch_spmv(s, P.p.p, P.y.p, 1); });
+    }
+    P.grid = grid_save;
+    time_it("update (x,r,z,dots)", 136.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, P.p.p, P.y.p, P.x.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p); });
+    time_it("direction (p,y=Dp,dots)", 88.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, P.z.p, P.p.p, P.y.p, P.D.p, P.sc.p); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
+    printf("[pcg-tune] n_row=%u n_off=%.0f (fixed %u + dyn %u); SpMV algorithmic bytes (40*n_off + 60*n_row) = %.1f MB\n", n, nnz, P.nnz_f, P.nnz_d,
+           (40.0 * nnz + 60.0 * n + 4.0 * (n + 1)) * 1e-6);
+    fflush(stdout);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof_mask) {
+    (void)dof_mask;
+    cudaStream_t q = s.stream;
+    if (!P.ready) pcg_init(s);
+    const unsigned n = P.n;
+    const unsigned gv_full = div_up(n, PCG_BLOCK);
+    const unsigned gv = std::min(P.grid, gv_full);
+
+    // ---- pack the assembled system ----
+    P.nnz_d = s.dyn_nnz;
+    pcg_reserve(s, P.nnz_d);
+    k_pack_fixed<<<div_up(s.fixed_nnz, 256), 256, 0, q>>>(s.fixed_nnz, s.fx_val.p, P.fx_pos.p, P.val.p, P.cap);
+    if (P.nnz_d) k_pack_dyn<<<div_up(n, 256), 256, 0, q>>>(n, s.dyn_off.p, s.dyn_col.p, s.dyn_val.p, P.nnz_f, P.row.p, P.col.p, P.val.p, P.cap);
+    int *d_bad = reinterpret_cast<int *>(s.counters.p + 32);
+    CUDA_OK(cudaMemsetAsync(d_bad, 0, sizeof(int), q));
+    k_pack_diag<<<gv_full, PCG_BLOCK, 0, q>>>(n, s.fx_diag_slot.p, s.fx_val.p, s.diag.p, P.D.p, P.Pinv.p, d_bad);
+    LAUNCH_COUNT(3);
+    s.spmv_n_row = n;
+    s.spmv_n_off = (unsigned long long)P.nnz_f + P.nnz_d;
+
+    // ---- setup: r = b - A x0, z = P r, p = z, y = D p, rz0, err0 ----
+    CgScalars init{};
+    init.tol = prm.cg_tol;
+    init.max_iter = (int)prm.cg_max_iter;
+    init.status = ST_RUNNING;
+    CUDA_OK(cudaMemcpyAsync(P.sc.p, &init, sizeof(init), cudaMemcpyHostToDevice, q));
+    k_load<<<gv_full, PCG_BLOCK, 0, q>>>(n, s.force.p, s.dx.p, P.r.p, P.x.p, P.p.p, P.y.p, P.D.p);
+    {
+        static bool tuned = false;
+        if (!tuned && getenv("PPF_B200_PCG_TUNE")) {
+            tuned = true;
+            pcg_tune(s);
+            CUDA_OK(cudaMemcpyAsync(P.sc.p, &init, sizeof(init), cudaMemcpyHostToDevice, q));
+            k_load<<<gv_full, PCG_BLOCK, 0, q>>>(n, s.force.p, s.dx.p, P.r.p, P.x.p, P.p.p, P.y.p, P.D.p);
+        }
+    }
+    launch_spmv(s, P.p.p, P.y.p, 0);
+    k_residual_init<<<gv, PCG_BLOCK, 0, q>>>(n, P.y.p, P.r.p, P.z.p, P.p.p, P.Pinv.p, P.D.p, P.sc.p);
+    LAUNCH_COUNT(3);
+    CgScalars h{};
+    CUDA_OK(cudaMemcpyAsync(&h, P.sc.p, sizeof(h), cudaMemcpyDeviceToHost, q));
+    int bad = 0;
+    CUDA_OK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    if (bad) fatal(4, "PCG: a block-Jacobi diagonal block is non-finite or non-positive; the assembly is broken upstream");
+    SolveResult res{true, 1u, 0.0f};
+    if (h.err0 == 0.0) {
+        k_store<<<gv_full, PCG_BLOCK, 0, q>>>(n, P.x.p, s.dx.p);
+        LAUNCH_COUNT(1);
+        return res;
+    }
+    if (!(h.rz[0] > 0.0)) fatal(4, "PCG breakdown: r^T M^-1 r = %.6e is not positive at setup; the preconditioner is not SPD", h.rz[0]);
+
+    // ---- iterate: batches of ITER_PER_GRAPH iterations replayed from a CUDA graph ----
+    const int ITER_PER_GRAPH = 8;
+    const unsigned nnz = P.nnz_f + P.nnz_d;
+    if (P.exec && (P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p)) { // kernel parameters changed: re-capture
+        cudaGraphExecDestroy(P.exec); cudaGraphDestroy(P.graph);
+        P.exec = nullptr; P.graph = nullptr;
+    }
+    if (!P.exec) {
+        CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < ITER_PER_GRAPH; ++k) issue_iteration(s);
+        CUDA_OK(cudaStreamEndCapture(q, &P.graph));
+        CUDA_OK(cudaGraphInstantiate(&P.exec, P.graph, 0ull));
+        P.graph_nnz = nnz;
+        P.graph_val = (const void *)P.val.p;
+    }
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    CUDA_OK(cudaEventRecord(e0, q));
+    int status = ST_RUNNING, iter = 0;
+    float resid = 0.f;
+    while (status == ST_RUNNING) {
+        CUDA_OK(cudaGraphLaunch(P.exec, q));
+        LAUNCH_COUNT(3 * ITER_PER_GRAPH);
+        CUDA_OK(cudaMemcpyAsync(P.h_status, &P.sc.p->iter, 2 * sizeof(int), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaMemcpyAsync(P.h_status + 2, &P.sc.p->last_resid, sizeof(float), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaStreamSynchronize(q));
+        iter = P.h_status[0];
+        status = P.h_status[1];
+        memcpy(&resid, P.h_status + 2, sizeof(float));
+    }
+    CUDA_OK(cudaEventRecord(e1, q));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    CUDA_OK(cudaEventDestroy(e0)); CUDA_OK(cudaEventDestroy(e1));
+    s.tm.ms_spmv += ms; // device time of the iteration loop (split per kernel by the ncu launch list)
+    s.tm.n_cg_iter += iter;
+    s.tm.n_spmv += iter + 1;
+    res.iter = (unsigned)iter;
+    res.resid = resid;
+    switch (status) {
+    case ST_CONVERGED: res.ok = true; break;
+    case ST_TRUNCATED:
+        printf("* cg truncated: curvature within round-off of its own reduction at iter %d (reresid %.3e)\n", iter, resid);
+        res.ok = true;
+        break;
+    case ST_CAP:
+    case ST_NONFINITE: res.ok = false; break;
+    case ST_FATAL_PAP: fatal(4, "PCG breakdown -- p^T A p is negative beyond its round-off bound at iter %d (reresid %.3e): the assembled Newton matrix is not SPD", iter, resid);
+    case ST_FATAL_RZ: fatal(4, "PCG breakdown -- r^T M^-1 r is non-positive at iter %d (reresid %.3e): the preconditioner is not SPD", iter, resid);
+    default: res.ok = false;
+    }
+    k_store<<<gv_full, PCG_BLOCK, 0, q>>>(n, P.x.p, s.dx.p);
+    LAUNCH_COUNT(1);
+    return res;
+}
+
+} // namespace ppf

@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Compare two assembled Newton systems dumped with PPF_DUMP_LINSYS (reference format,
+crates/ppf-cts-solver/src/cpp/main/dump_linsys.hpp:93-190): block pattern (exact set
+equality), block values, merged diagonals and right-hand side (relative tolerances)."""
+import json
+import sys
+
+import numpy as np
+
+
+def load_linsys(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = raw[:12].view(np.uint32)
+    assert hdr[0] == 0x4C535953, "bad magic"
+    nrow, n_off = int(hdr[1]), int(hdr[2])
+    rec = np.dtype([("row", "<u4"), ("col", "<u4"), ("val", "<f4", (9,))])
+    off = 12
+    ent = raw[off:off + rec.itemsize * n_off].view(rec)
+    off += rec.itemsize * n_off
+    diag = raw[off:off + 36 * nrow].view(np.float32).reshape(nrow, 9)
+    off += 36 * nrow
+    rhs = raw[off:off + 12 * nrow].view(np.float32).reshape(nrow, 3)
+    return nrow, ent, diag, rhs
+
+
+def as_map(ent, drop_zero=True):
+    key = ent["row"].astype(np.uint64) << np.uint64(32) | ent["col"].astype(np.uint64)
+    order = np.argsort(key, kind="stable")
+    key, val = key[order], ent["val"][order].astype(np.float64)
+    uk, start = np.unique(key, return_index=True)
+    summed = np.add.reduceat(val, start, axis=0) if len(key) else np.zeros((0, 9))
+    if drop_zero and len(uk):
+        keep = ~np.all(np.abs(summed) <= 1e-5, axis=1)  # SMat::isZero tolerance of the reference
+        uk, summed = uk[keep], summed[keep]
+    return uk, summed
+
+
+def compare(ref_path, our_path, verbose=True):
+    n0, e0, d0, b0 = load_linsys(ref_path)
+    n1, e1, d1, b1 = load_linsys(our_path)
+    res = {"nrow": (n0, n1)}
+    k0, v0 = as_map(e0)
+    k1, v1 = as_map(e1)
+    only0 = np.setdiff1d(k0, k1)
+    only1 = np.setdiff1d(k1, k0)
+    res["n_blocks"] = (int(k0.size), int(k1.size))
+    res["only_ref"] = int(only0.size)
+    res["only_ours"] = int(only1.size)
+    common, i0, i1 = np.intersect1d(k0, k1, return_indices=True)
+    scale = float(np.abs(v0).max()) if v0.size else 1.0
+    dv = np.abs(v0[i0] - v1[i1])
+    res["offdiag_max_abs_diff"] = float(dv.max()) if dv.size else 0.0
+    res["offdiag_scale"] = scale
+    # per-block relative error (against the block's own magnitude, floored at 1e-6 of the global scale)
+    bs = np.maximum(np.abs(v0[i0]).max(axis=1), 1e-6 * scale) if dv.size else np.ones(0)
+    res["offdiag_max_rel_block_diff"] = float((dv.max(axis=1) / bs).max()) if dv.size else 0.0
+    dscale = float(np.abs(d0).max())
+    res["diag_max_rel_diff"] = float((np.abs(d0.astype(np.float64) - d1).max(axis=1) / np.maximum(np.abs(d0).max(axis=1), 1e-6 * dscale)).max())
+    bscale = float(np.abs(b0).max())
+    res["rhs_max_abs_diff_over_scale"] = float(np.abs(b0.astype(np.float64) - b1).max() / max(bscale, 1e-30))
+    if only0.size:
+        res["only_ref_examples"] = [(int(k >> np.uint64(32)), int(k & np.uint64(0xFFFFFFFF))) for k in only0[:8]]
+        res["only_ref_maxabs"] = [float(np.abs(v0[np.searchsorted(k0, k)]).max()) for k in only0[:8]]
+    if only1.size:
+        res["only_ours_examples"] = [(int(k >> np.uint64(32)), int(k & np.uint64(0xFFFFFFFF))) for k in only1[:8]]
+        res["only_ours_maxabs"] = [float(np.abs(v1[np.searchsorted(k1, k)]).max()) for k in only1[:8]]
+    if verbose:
+        print(json.dumps(res))
+    return res
+
+
+if __name__ == "__main__":
+    compare(sys.argv[1], sys.argv[2])
