@@ -1,0 +1,244 @@
+#!/usr/bin/env python3
+"""bench.py -- frames/sec of the per-step hot path on the large-twist scene (BASELINE.json headline).
+
+A "step" is one advance() of the backend (BVH build, Newton loop {FEM + barrier assembly,
+block-Jacobi PCG, ACCD line search}, intersection check) on the 3.2 M-vertex twisted cylinder of
+examples/large-twist.ipynb, driven through the reference's C ABI by the C++ host.
+
+  value   frames/sec with everything resident in HBM: simulated time advanced * fps / device time of
+          advance() (CUDA events on the backend's launch stream, read through ppf_b200_get_stats).
+  e2e     the same metric through the ABI with HOST buffers: each timed step includes
+          update_constraint (pins, host -> device) and fetch() (positions, device -> host).
+  roofline  the dominant kernel, the PCG SpMV (k_spmv), timed alone with CUDA events on the live
+          packed system of the last solve; bytes per launch = 40*N_off + 24*N_row.
+  cpu_baseline  the CPU oracle port (oracle/) timed on a bounded sample on rank 0.
+
+--impl reference runs the UNMODIFIED reference CUDA backend (oracle/_ref, built from /root/reference
+by oracle/Makefile.ref) through the same host on the same scene.  The reference has no CPU physics
+path, so its "own implementation of the path" is that CUDA build on this B200.
+
+N > 1 (torchrun): the path does not shard yet, so every rank runs an independent replica of the
+scene on its own GPU ("replicas only", weak scaling); torch.distributed (NCCL) provides the barrier
+and the max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "ppf-contact-solver_b200"))
+
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+if WORLD > 1:  # one process per GPU: each rank sees exactly its own device as cuda:0
+    os.environ["CUDA_VISIBLE_DEVICES"] = str(LOCAL_RANK)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self):
+        super().__init__(daemon=True)
+        self.stop_flag = False
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        idx = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", idx, "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def peak_hbm():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(scene, n):
+    """CPU oracle port timed on a bounded sample (rank 0, N=1 only)."""
+    exe = os.path.join(REPO, "oracle", "build", "ppf_oracle_bench")
+    if not os.path.exists(exe):
+        return {"value": None, "unit": "frames/sec", "cores": os.cpu_count(), "kind": "port", "sample": "oracle/build/ppf_oracle_bench missing"}
+    try:
+        out = subprocess.run([exe, "--scene", scene, "--n", str(n), "--budget-sec", "25"], capture_output=True, text=True, timeout=600).stdout
+        return json.loads(out.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "frames/sec", "cores": os.cpu_count(), "kind": "port", "sample": "oracle run failed: %s" % e}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="large-twist")
+    ap.add_argument("--n", type=int, default=0, help="resolution override (0 = the config's own: n=1410 for large-twist)")
+    args = ap.parse_args()
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    import ppf_b200
+
+    if args.impl == "reference":
+        if RANK != 0:
+            return
+        if not os.path.exists(ppf_b200.LIB_REF):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsimbackend_cuda.so is not built (needs /root/reference; see oracle/Makefile.ref)"}))
+            return
+        lib = ppf_b200.LIB_REF
+    else:
+        lib = ppf_b200.LIB_OURS
+        if not os.path.exists(lib):
+            raise SystemExit("the CUDA backend %s is missing; there is no CPU fallback (run __graft_entry__.build())" % lib)
+
+    dist = None
+    if WORLD > 1 and args.impl == "ours":
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(0)
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+
+    os.environ.setdefault("PPF_HOST_QUIET", "1")
+    os.environ.setdefault("PPF_B200_QUIET", "1")
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved_stdout = os.dup(1)
+    os.dup2(devnull, 1)  # the backends narrate on stdout; keep ours for the JSON line
+    try:
+        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK)
+        fps = 60.0
+        for _ in range(W):
+            ok, _ms = s.step()
+            assert ok, "warm-up step failed"
+            s.fetch(want=False)
+
+        def barrier():
+            if dist is not None:
+                import torch
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        barrier()
+        clocks = ClockSampler()
+        clocks.start()
+        st0 = s.stats() if s.is_b200 else None
+        t_sim0 = s.time
+        wall_e2e = 0.0
+        wall_adv = 0.0
+        for _ in range(K):
+            t0 = time.perf_counter()
+            ok, ms = s.step()          # update_constraint (H2D pins) + advance
+            assert ok, "timed step failed"
+            s.fetch(want=False)        # D2H positions into the host DataSet arrays
+            wall_e2e += time.perf_counter() - t0
+            wall_adv += ms * 1e-3
+        barrier()
+        clocks.stop_flag = True
+        clocks.join(timeout=2)
+        st1 = s.stats() if s.is_b200 else None
+        frames = (s.time - t_sim0) * fps
+        spmv = s.measure_spmv(20) if s.is_b200 else None
+        h2d, d2h = s.io_bytes()
+    finally:
+        os.dup2(saved_stdout, 1)
+
+    if st0 is not None:
+        dev_s = (st1["ms_advance"] - st0["ms_advance"]) * 1e-3
+        n_newton = st1["n_newton"] - st0["n_newton"]
+        launches = st1["n_kernel_launches"] - st0["n_kernel_launches"]
+        n_cg = st1["n_cg_iter"] - st0["n_cg_iter"]
+    else:
+        dev_s, n_newton, launches, n_cg = wall_adv, None, None, None
+
+    # max over ranks of the timed region, sum of the frames all ranks advanced
+    t_dev, t_e2e, tot_frames = dev_s, wall_e2e, frames
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_s, wall_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        f = torch.tensor([frames], device="cuda", dtype=torch.float64)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+        t_dev, t_e2e, tot_frames = float(t[0]), float(t[1]), float(f[0])
+    if RANK != 0:
+        return
+
+    line = {
+        "metric": "frames/sec (large-twist per-step hot path)" if args.scene == "large-twist" else "frames/sec (%s)" % args.scene,
+        "value": tot_frames / t_dev,
+        "unit": "frames/sec",
+        "n_gpus": WORLD,
+        "steps": K,
+        "warmup": W,
+        "ms_per_step": 1e3 * t_dev / K,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "%s: cylinder n=%s, V=%d F=%d E=%d hinges=%d, dt=1/60, steps from t=0; %s" % (
+            args.scene, args.n or "config default", s.n_vert, s.n_face, s.n_edge, s.n_hinge,
+            "replicas only (one independent scene per GPU)" if WORLD > 1 else "single GPU"),
+            "l2": "inputs larger than L2 (packed matrix %.0f MB per SpMV)" % ((40.0 * (st1["spmv_n_off"] if st1 else 0) + 60.0 * s.n_vert) * 1e-6)},
+        "e2e": {"value": tot_frames / t_e2e, "unit": "frames/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks.result(),
+    }
+    if n_newton:
+        line["ms_per_newton_step"] = 1e3 * dev_s / n_newton
+        line["pcg_iters_per_newton_step"] = n_cg / n_newton
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["value"] = tot_frames / wall_adv
+        line["ms_per_step"] = 1e3 * wall_adv / K
+        line["gpu_launches"] = None
+        line["e2e"] = {"value": line["value"], "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        line["cpu_baseline"] = {"value": line["value"], "unit": "frames/sec", "cores": os.cpu_count(), "kind": "reference",
+                                "sample": "the reference has no CPU physics path (cpp_emul does no physics); this is its own CUDA build "
+                                          "(oracle/_ref, sm_100 cubin) on one B200, wall-clock around advance()"}
+        print(json.dumps(line))
+        return
+    if spmv:
+        us, n_row, n_off = spmv
+        peak, how = peak_hbm()
+        bytes_per_launch = 40.0 * n_off + 24.0 * n_row
+        achieved = bytes_per_launch / (us * 1e-6) * 1e-9
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line["roofline"] = {"bound": "hbm", "kernel": "ppf::k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic, "peak_source": how, "us_per_launch": us, "n_row": n_row, "n_off": n_off,
+                            "bytes_per_launch": bytes_per_launch}
+    if WORLD == 1:
+        line["cpu_baseline"] = cpu_baseline(args.scene, args.n)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -283,6 +283,8 @@ void ppf_b200_reset_stats(void);
  * kind: 0 point-face, 1 point-edge, 2 point-point, 3 edge-edge.  Returns the
  * pair count; copies min(count, cap) pairs (a,b) into out[2*i], out[2*i+1]. */
 unsigned ppf_b200_fetch_pairs(unsigned kind, unsigned *out, unsigned cap);
+/* Average microseconds of the SpMV kernel alone on the last packed system (CUDA events, `reps` launches). */
+double ppf_b200_measure_spmv(unsigned reps, unsigned long long *n_row, unsigned long long *n_off);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,285 @@
+/* oracle_math.h -- TEST INFRASTRUCTURE.  CPU restatement (plain C-style, float arrays) of the
+ * per-element math of the reference's per-Newton-step path.  Nothing under ppf-contact-solver_b200/
+ * includes, links or executes this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg use the oracle.
+ *
+ * Each function cites the reference file:line it follows (paths under
+ * /root/reference/crates/ppf-cts-solver/src/cpp/).  fp32 throughout, same operation order as the
+ * reference so that the contact predicates and the ACCD time of impact can be compared bit for bit
+ * (tests/test_oracle_cpu.py pins every function here against the reference's own headers compiled
+ * for the host, oracle/_ref/libref_host.so).
+ */
+#ifndef PPF_ORACLE_MATH_H
+#define PPF_ORACLE_MATH_H
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+typedef float o3[3];
+
+static inline void o_sub(const float *a, const float *b, float *r) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+/* linalg/smat.hpp:330-335 -- accumulator starts at 0 */
+static inline float o_dot(const float *a, const float *b) {
+    float acc = 0.0f;
+    for (int i = 0; i < 3; ++i) acc = acc + a[i] * b[i];
+    return acc;
+}
+static inline void o_cross(const float *a, const float *b, float *r) { /* smat.hpp:337-343 */
+    const float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    r[0] = x; r[1] = y; r[2] = z;
+}
+static inline float o_min_coeff(const float *m, int n) { float b = m[0]; for (int i = 1; i < n; ++i) if (m[i] < b) b = m[i]; return b; }
+static inline float o_max_coeff(const float *m, int n) { float b = m[0]; for (int i = 1; i < n; ++i) if (b < m[i]) b = m[i]; return b; }
+static inline int o_interior(const float *c, int n) { return o_max_coeff(c, n) < 1.0f && o_min_coeff(c, n) > 0.0f; }
+
+/* contact/distance.hpp:15-27 */
+static inline void o_point_edge_coeff(const float *p, const float *e0, const float *e1, float *c) {
+    o3 r, d;
+    o_sub(e1, e0, r);
+    const float dd = o_dot(r, r);
+    if (dd > 0.0f) {
+        o_sub(p, e0, d);
+        const float t = o_dot(r, d) / dd;
+        c[0] = 1.0f - t; c[1] = t;
+    } else { c[0] = 0.5f; c[1] = 0.5f; }
+}
+/* contact/distance.hpp:47-84 */
+static inline void o_point_triangle_coeff(const float *p, const float *t0, const float *t1, const float *t2, float *c) {
+    o3 r0, r1, d, nrm, tmp;
+    o_sub(t1, t0, r0); o_sub(t2, t0, r1); o_sub(p, t0, d);
+    o_cross(r0, r1, nrm);
+    const float nn = o_dot(nrm, nrm);
+    if (nn > 0.0f) {
+        const float inv = 1.0f / nn;
+        o_cross(d, r1, tmp);
+        const float u = o_dot(tmp, nrm) * inv;
+        o_cross(r0, d, tmp);
+        const float v = o_dot(tmp, nrm) * inv;
+        c[0] = 1.0f - u - v; c[1] = u; c[2] = v;
+    } else {
+        o3 e1, e2;
+        float w[2];
+        o_sub(t2, t1, e1); o_sub(t0, t2, e2);
+        const float l0 = o_dot(r0, r0), l1 = o_dot(e1, e1), l2 = o_dot(e2, e2);
+        if (l0 >= l1 && l0 >= l2) { o_point_edge_coeff(p, t0, t1, w); c[0] = w[0]; c[1] = w[1]; c[2] = 0.0f; }
+        else if (l1 >= l2) { o_point_edge_coeff(p, t1, t2, w); c[0] = 0.0f; c[1] = w[0]; c[2] = w[1]; }
+        else { o_point_edge_coeff(p, t2, t0, w); c[0] = w[1]; c[1] = 0.0f; c[2] = w[0]; }
+    }
+}
+static inline float o_clamp_unit(float v) { return v > 0.0f ? (v < 1.0f ? v : 1.0f) : 0.0f; } /* distance.hpp:90-92 */
+/* contact/distance.hpp:113-196 */
+static inline void o_edge_edge_coeff(const float *a0, const float *a1, const float *b0, const float *b1, float *out) {
+    o3 r0, r1, d, n, tmp;
+    o_sub(a1, a0, r0); o_sub(b1, b0, r1); o_sub(a0, b0, d);
+    const float a = o_dot(r0, r0), e = o_dot(r1, r1), b = o_dot(r0, r1), c = o_dot(r0, d), f = o_dot(r1, d);
+    const float inv_a = a > 0.0f ? 1.0f / a : 0.0f, inv_e = e > 0.0f ? 1.0f / e : 0.0f;
+    o_cross(r0, r1, n);
+    const float nn = o_dot(n, n);
+    const float inv_nn = nn > 0.0f ? 1.0f / nn : 0.0f;
+    o_cross(r1, d, tmp);
+    const float s_stat = o_clamp_unit(o_dot(n, tmp) * inv_nn);
+    const float t_stat = o_clamp_unit((b * s_stat + f) * inv_e);
+    const float cs[5] = {s_stat, 0.0f, 1.0f, o_clamp_unit(-c * inv_a), o_clamp_unit((b - c) * inv_a)};
+    const float ct[5] = {t_stat, o_clamp_unit(f * inv_e), o_clamp_unit((f + b) * inv_e), 0.0f, 1.0f};
+    float bs = 0.0f, bt = 0.0f, best = FLT_MAX;
+    for (int i = 0; i < 5; ++i) {
+        o3 v;
+        for (int k = 0; k < 3; ++k) v[k] = d[k] + cs[i] * r0[k] - ct[i] * r1[k];
+        const float dist = o_dot(v, v);
+        if (dist < best) { best = dist; bs = cs[i]; bt = ct[i]; }
+    }
+    out[0] = 1.0f - bs; out[1] = bs; out[2] = 1.0f - bt; out[3] = bt;
+}
+/* contact/distance.hpp:224-283 */
+static inline void o_point_triangle_coeff_unclassified(const float *p, const float *t0, const float *t1, const float *t2, float *out) {
+    o3 r0, r1, d;
+    o_sub(t1, t0, r0); o_sub(t2, t0, r1); o_sub(p, t0, d);
+    float cand[4][3], w[2];
+    int adm[4] = {0, 1, 1, 1};
+    o_point_triangle_coeff(p, t0, t1, t2, cand[0]);
+    adm[0] = o_min_coeff(cand[0], 3) >= 0.0f;
+    o_point_edge_coeff(p, t0, t1, w); const float s01 = o_clamp_unit(w[1]);
+    o_point_edge_coeff(p, t1, t2, w); const float s12 = o_clamp_unit(w[1]);
+    o_point_edge_coeff(p, t2, t0, w); const float s20 = o_clamp_unit(w[1]);
+    cand[1][0] = 1.0f - s01; cand[1][1] = s01; cand[1][2] = 0.0f;
+    cand[2][0] = 0.0f; cand[2][1] = 1.0f - s12; cand[2][2] = s12;
+    cand[3][0] = s20; cand[3][1] = 0.0f; cand[3][2] = 1.0f - s20;
+    int bi = 1;
+    float best = FLT_MAX;
+    for (int i = 0; i < 4; ++i) {
+        if (!adm[i]) continue;
+        o3 v;
+        for (int k = 0; k < 3; ++k) v[k] = d[k] - cand[i][1] * r0[k] - cand[i][2] * r1[k];
+        const float dist = o_dot(v, v);
+        if (dist < best) { best = dist; bi = i; }
+    }
+    memcpy(out, cand[bi], 3 * sizeof(float));
+}
+/* contact/distance.hpp:285-299 */
+static inline void o_point_edge_coeff_unclassified(const float *p, const float *e0, const float *e1, float *c) {
+    o_point_edge_coeff(p, e0, e1, c);
+    if (c[0] >= 0.0f && c[0] <= 1.0f) return;
+    if (c[0] > 1.0f) { c[0] = 1.0f; c[1] = 0.0f; }
+    else { c[0] = 0.0f; c[1] = 1.0f; }
+}
+
+/* ---- ACCD (contact/accd.hpp) : columns x[c][3], nc columns, the first `split` belong to primitive A ---- */
+enum { O_CCD_PT = 0, O_CCD_EE = 1, O_CCD_PE = 2, O_CCD_PP = 3 };
+
+static inline float o_accd_sqdist(int kind, const float (*x)[3], float *dir) { /* accd.hpp:473-561 */
+    if (kind == O_CCD_PT) {
+        float c[3];
+        o_point_triangle_coeff_unclassified(x[0], x[1], x[2], x[3], c);
+        for (int k = 0; k < 3; ++k) dir[k] = c[0] * (x[1][k] - x[0][k]) + c[1] * (x[2][k] - x[0][k]) + c[2] * (x[3][k] - x[0][k]);
+    } else if (kind == O_CCD_EE) {
+        float c[4];
+        o_edge_edge_coeff(x[0], x[1], x[2], x[3], c);
+        for (int k = 0; k < 3; ++k) {
+            const float a = c[0] * x[0][k] + c[1] * x[1][k], b = c[2] * x[2][k] + c[3] * x[3][k];
+            dir[k] = b - a;
+        }
+    } else if (kind == O_CCD_PE) {
+        float c[2];
+        o_point_edge_coeff_unclassified(x[0], x[1], x[2], c);
+        for (int k = 0; k < 3; ++k) dir[k] = (c[0] * x[1][k] + c[1] * x[2][k]) - x[0][k];
+    } else {
+        for (int k = 0; k < 3; ++k) dir[k] = x[1][k] - x[0][k];
+    }
+    return o_dot(dir, dir);
+}
+
+static inline float o_accd_directional(int nc, int split, const float (*x)[3], const float (*dx)[3], const float *w, float w_norm, float dip,
+                                       float park, float max_t) { /* accd.hpp:242-282 */
+    const float round_slack = 2.0f * FLT_EPSILON, coord_slack = 6.2e-7f;
+    const float w_abs[3] = {fabsf(w[0]), fabsf(w[1]), fabsf(w[2])};
+    const float dip_w = dip * w_norm, park_w = park * w_norm;
+    float step = FLT_MAX;
+    for (int i = 0; i < split; ++i)
+        for (int j = split; j < nc; ++j) {
+            o3 gap, rel, ga, ra;
+            for (int k = 0; k < 3; ++k) { gap[k] = x[j][k] - x[i][k]; rel[k] = dx[i][k] - dx[j][k]; ga[k] = fabsf(gap[k]); ra[k] = fabsf(rel[k]); }
+            const float err = round_slack * (o_dot(w_abs, ga) + max_t * o_dot(w_abs, ra) + park_w) + coord_slack * w_norm;
+            const float projected = o_dot(w, gap) - err;
+            if (!(projected - dip_w > 0.0f)) return 0.0f;
+            const float rate = o_dot(w, rel);
+            if (rate > 0.0f) step = fminf(step, fmaxf(0.0f, projected - park_w) / rate);
+        }
+    return step;
+}
+
+/* full driver: centerize 65-74, rescale 77-120, max_relative_u 142-151, ccd_helper 292-471, *_ccd 565-696.
+ * x0/x1: nc points at t=0 and t=1.  *overlap is set when the reference would latch g_ccd_overlap. */
+static inline float o_accd(int kind, int nc, int split, const float (*p0)[3], const float (*p1)[3], float offset, float ghat, float max_t,
+                           float ccd_eps, unsigned *overlap) {
+    float x0[4][3], dx[4][3], x[4][3];
+    for (int c = 0; c < nc; ++c)
+        for (int k = 0; k < 3; ++k) { x0[c][k] = p0[c][k]; dx[c][k] = p1[c][k] - p0[c][k]; }
+    for (int pass = 0; pass < 2; ++pass) { /* centerize x0 then dx */
+        float(*m)[3] = pass ? dx : x0;
+        float mov[3] = {0.0f, 0.0f, 0.0f};
+        const float sc = (float)(1.0 / nc);
+        for (int c = 0; c < nc; ++c)
+            for (int k = 0; k < 3; ++k) mov[k] = mov[k] + sc * m[c][k];
+        for (int c = 0; c < nc; ++c)
+            for (int k = 0; k < 3; ++k) m[c][k] = m[c][k] - mov[k];
+    }
+    float m0 = fabsf(x0[0][0]), m1 = fabsf(x0[0][0] + max_t * dx[0][0]);
+    for (int c = 0; c < nc; ++c)
+        for (int k = 0; k < 3; ++k) {
+            const float a = fabsf(x0[c][k]), b = fabsf(x0[c][k] + max_t * dx[c][k]);
+            if (m0 < a) m0 = a;
+            if (m1 < b) m1 = b;
+        }
+    float scale = 0.99f / fmaxf(m0, m1);
+    if (!(scale > 0.0f) || !isfinite(scale)) { *overlap = 1u; return 0.0f; }
+    float scaled = 1.0f;
+    for (;;) {
+        const float s = 8.0f;
+        if (scale > s) {
+            for (int c = 0; c < nc; ++c) for (int k = 0; k < 3; ++k) { x0[c][k] *= s; dx[c][k] *= s; }
+            scaled *= s; scale /= s;
+        } else {
+            for (int c = 0; c < nc; ++c) for (int k = 0; k < 3; ++k) { x0[c][k] *= scale; dx[c][k] *= scale; }
+            scaled *= scale;
+            break;
+        }
+    }
+    float max_u = 0.0f;
+    for (int i = 0; i < split; ++i)
+        for (int j = split; j < nc; ++j) {
+            o3 du;
+            o_sub(dx[i], dx[j], du);
+            const float sq = o_dot(du, du);
+            if (max_u < sq) max_u = sq;
+        }
+    const float u_max = sqrtf(max_u);
+    if (!u_max) return max_t;
+    const float off = scaled * offset, eps = scaled * ccd_eps, floor_gap = scaled * (1e-2f * ghat);
+    /* ccd_helper */
+    float w[3], lower_t = 0.0f, toi = 0.0f;
+    memcpy(x, x0, sizeof(x));
+    float d2 = o_accd_sqdist(kind, x0, w);
+    if (!(d2 > off * off)) { *overlap = 1u; return 0.0f; }
+    const float clearance = sqrtf(d2) - off;
+    const float floor_clear = fmaxf(2.0f * eps, floor_gap);
+    const float park = off + fminf(floor_clear, fmaxf(clearance - 0.5f * eps, 0.5f * clearance));
+    const float overshoot = fmaxf(0.0f, (park - off) - 0.5f * floor_clear);
+    const float dip = park - overshoot;
+    const float park_sq = fminf(park * park, nextafterf(d2, 0.0f));
+    const float inv_u = 1.0f / u_max;
+    unsigned probes = 0;
+    for (;;) {
+        if (!(d2 > park_sq)) break;
+        lower_t = toi;
+        const float dist = sqrtf(d2);
+        float step = (dist - dip) * inv_u;
+        if (toi + step <= max_t) step = fmaxf(step, o_accd_directional(nc, split, x, dx, w, dist * (1.0f + 2.0f * FLT_EPSILON), dip, park, max_t));
+        toi += step;
+        if (toi > max_t) return max_t;
+        else if (++probes > 4096u) return lower_t;
+        for (int c = 0; c < nc; ++c) for (int k = 0; k < 3; ++k) x[c][k] = x0[c][k] + toi * dx[c][k];
+        d2 = o_accd_sqdist(kind, x, w);
+    }
+    float upper_t = toi, window = upper_t - lower_t;
+    for (;;) {
+        float tmp[3];
+        toi = 0.5f * (upper_t + lower_t);
+        for (int c = 0; c < nc; ++c) for (int k = 0; k < 3; ++k) x[c][k] = x0[c][k] + toi * dx[c][k];
+        d2 = o_accd_sqdist(kind, x, tmp);
+        if (d2 > park_sq) lower_t = toi; else upper_t = toi;
+        const float nw = upper_t - lower_t;
+        if (nw == window) break;
+        window = nw;
+    }
+    if (!(lower_t > 0.0f)) { *overlap = 1u; return 0.0f; }
+    return lower_t;
+}
+
+/* ---- cubic barrier (barrier/cubic.hpp:13-41) ---- */
+static inline float o_cubic_gradient(float g, float ghat, float offset) { g -= offset; const float y = g - ghat; return y < 0.0f ? -2.0f * y * y / ghat : 0.0f; }
+static inline float o_cubic_curvature(float g, float ghat, float offset) { g -= offset; return (g - ghat < 0.0f) ? 4.0f * (1.0f - g / ghat) : 0.0f; }
+
+/* ---- edge-triangle pierce test (contact/intersect_core.hpp:21-79 through contact.cu:2745-2759) ---- */
+static inline int o_edge_triangle_intersect(const float *a0, const float *a1, const float *b0, const float *b1, const float *b2) {
+    o3 d1, d2, A0, A1, n;
+    o_sub(b1, b0, d1); o_sub(b2, b0, d2); o_sub(a0, b0, A0); o_sub(a1, b0, A1);
+    o_cross(d1, d2, n);
+    const float s1 = A0[0] * n[0] + A0[1] * n[1] + A0[2] * n[2], s2 = A1[0] * n[0] + A1[1] * n[1] + A1[2] * n[2];
+    if (s1 * s2 < 0.0f) {
+        const float t = s1 / (s1 - s2);
+        o3 r;
+        for (int k = 0; k < 3; ++k) r[k] = (1.0f - t) * A0[k] + t * A1[k];
+        const float a00 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], a01 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
+        const float a11 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
+        const float q0 = d1[0] * r[0] + d1[1] * r[1] + d1[2] * r[2], q1 = d2[0] * r[0] + d2[1] * r[1] + d2[2] * r[2];
+        const float det = a00 * a11 - a01 * a01;
+        if (det == 0.0f) return 0;
+        const float w0 = (a11 * q0 - a01 * q1) / det, w1 = (a00 * q1 - a01 * q0) / det, w2 = 1.0f - w0 - w1;
+        float wmin = w0 < w1 ? w0 : w1; wmin = wmin < w2 ? wmin : w2;
+        float wmax = w0 > w1 ? w0 : w1; wmax = wmax > w2 ? wmax : w2;
+        return wmin >= 0.0f && wmax <= 1.0f;
+    }
+    return 0;
+}
+
+#endif

@@ -646,3 +646,25 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
 }
 
 } // namespace ppf
+
+// Extension used by bench.py: average duration (microseconds) of the SpMV kernel alone on the last
+// packed system, `reps` launches after 3 warm-ups, CUDA events on the backend stream.
+extern "C" __attribute__((visibility("default"))) double ppf_b200_measure_spmv(unsigned reps, unsigned long long *n_row, unsigned long long *n_off) {
+    using namespace ppf;
+    State &s = g;
+    if (!P.ready || !(P.nnz_f + P.nnz_d) || !reps) return 0.0;
+    if (n_row) *n_row = P.n;
+    if (n_off) *n_off = (unsigned long long)P.nnz_f + P.nnz_d;
+    cudaStream_t q = s.stream;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    for (int k = 0; k < 3; ++k) launch_spmv(s, P.p.p, P.y.p, 0);
+    CUDA_OK(cudaEventRecord(e0, q));
+    for (unsigned k = 0; k < reps; ++k) launch_spmv(s, P.p.p, P.y.p, 0);
+    CUDA_OK(cudaEventRecord(e1, q));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    CUDA_OK(cudaEventDestroy(e0)); CUDA_OK(cudaEventDestroy(e1));
+    return 1e3 * double(ms) / reps;
+}

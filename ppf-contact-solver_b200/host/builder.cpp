@@ -96,32 +96,31 @@ void build_scene(const SceneSpec &spec, Built &b) {
     const unsigned nf = (unsigned)b.face.size();
 
     // ---- edges and hinges (mesh.rs:188-293), sorted-key order ----
-    struct ERec { unsigned a, b, f0; int f1; };
-    std::map<std::pair<unsigned, unsigned>, ERec> emap;
-    struct HRec { unsigned i0, i1, i2; int i3; unsigned f0; int f1; bool excluded; };
-    std::map<std::pair<unsigned, unsigned>, HRec> hmap;
+    // One record per (face, side); sorting by the undirected key groups the faces around an edge in
+    // ascending face order, which reproduces "first face seen owns the record" of the reference.
+    struct Side { unsigned long long key; unsigned face, e0, e1, e2; };
+    std::vector<Side> sides;
+    sides.reserve(size_t(3) * nf);
     for (unsigned i = 0; i < nf; ++i)
         for (int j = 0; j < 3; ++j) {
             const unsigned e0 = b.face[i].v[j], e1 = b.face[i].v[(j + 1) % 3], e2 = b.face[i].v[(j + 2) % 3];
-            auto key = std::make_pair(std::min(e0, e1), std::max(e0, e1));
-            auto it = emap.find(key);
-            if (it == emap.end()) emap[key] = ERec{e0, e1, i, -1};
-            else if (it->second.f1 < 0) it->second.f1 = (int)i;
-            auto ht = hmap.find(key);
-            if (ht == hmap.end()) hmap[key] = HRec{e0, e1, e2, -1, i, -1, false};
-            else if (ht->second.i3 >= 0) ht->second.excluded = true;
-            else { ht->second.i3 = (int)e2; ht->second.f1 = (int)i; }
+            const unsigned lo = std::min(e0, e1), hi = std::max(e0, e1);
+            sides.push_back(Side{((unsigned long long)lo << 32) | hi, i, e0, e1, e2});
         }
-    for (auto &kv : emap) {
-        b.edge.push_back(PpfVec2u{{kv.second.a, kv.second.b}});
-        if (kv.second.f1 >= 0) b.edge_face.push_back({kv.second.f0, (unsigned)kv.second.f1});
-        else b.edge_face.push_back({kv.second.f0});
+    std::sort(sides.begin(), sides.end(), [](const Side &x, const Side &y) { return x.key != y.key ? x.key < y.key : x.face < y.face; });
+    for (size_t k = 0; k < sides.size();) {
+        size_t m = k;
+        while (m < sides.size() && sides[m].key == sides[k].key) ++m;
+        const Side &s0 = sides[k];
+        b.edge.push_back(PpfVec2u{{s0.e0, s0.e1}});
+        if (m - k >= 2) b.edge_face.push_back({s0.face, sides[k + 1].face});
+        else b.edge_face.push_back({s0.face});
+        if (m - k == 2) { // interior edge with exactly two faces -> hinge (more than two: excluded, mesh.rs:268-279)
+            b.hinge.push_back(PpfVec4u{{s0.e0, s0.e1, s0.e2, sides[k + 1].e2}});
+            b.hinge_face.push_back({s0.face, sides[k + 1].face});
+        }
+        k = m;
     }
-    for (auto &kv : hmap)
-        if (!kv.second.excluded && kv.second.i3 >= 0) {
-            b.hinge.push_back(PpfVec4u{{kv.second.i0, kv.second.i1, kv.second.i2, (unsigned)kv.second.i3}});
-            b.hinge_face.push_back({kv.second.f0, (unsigned)kv.second.f1});
-        }
     const unsigned ne = (unsigned)b.edge.size(), nh = (unsigned)b.hinge.size();
     b.v_face.assign(nv, {}); b.v_hinge.assign(nv, {}); b.v_edge.assign(nv, {}); b.v_rod.assign(nv, {});
     for (unsigned i = 0; i < nf; ++i) for (int k = 0; k < 3; ++k) b.v_face[b.face[i].v[k]].push_back(i);

@@ -1,0 +1,120 @@
+// capi.cpp -- flat C API over the C++ host (libppf_host.so) so that Python (ctypes) can drive a
+// backend in-process: tests, bench.py and __graft_entry__.smoke() use it.  Every call below maps
+// onto the run loop of crates/ppf-cts-solver/src/backend.rs:626-1025 as restated in backend.cpp.
+#include "ppf_host.hpp"
+#include <chrono>
+#include <cstring>
+
+using namespace ppfh;
+
+struct Session {
+    Built b;
+    Backend be;
+    Runner r;
+    std::string err;
+    std::vector<float> curr, prev;
+    std::vector<unsigned> dyn_index, dyn_offset;
+};
+
+extern "C" {
+
+__attribute__((visibility("default"))) void print_rust(const char *msg) {
+    if (getenv("PPF_HOST_QUIET") == nullptr) fprintf(stderr, "[backend] %s\n", msg);
+}
+
+Session *ppfh_create(const char *scene, unsigned n) {
+    Session *s = new Session;
+    try {
+        build_scene(make_scene(scene, n), s->b);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "ppfh_create: %s\n", e.what());
+        delete s;
+        return nullptr;
+    }
+    s->r.b = &s->b;
+    s->r.be = &s->be;
+    return s;
+}
+void ppfh_destroy(Session *s) { delete s; }
+const char *ppfh_error(Session *s) { return s->err.c_str(); }
+// counts: [n_vert, n_face, n_edge, n_hinge, n_fix, fixed_nnz]
+void ppfh_counts(Session *s, unsigned *out) {
+    out[0] = s->b.n_vert; out[1] = (unsigned)s->b.face.size(); out[2] = (unsigned)s->b.edge.size();
+    out[3] = (unsigned)s->b.hinge.size(); out[4] = (unsigned)s->b.fix.size(); out[5] = (unsigned)s->b.f_fixed.data.size();
+}
+void ppfh_set_args(Session *s, unsigned cg_max_iter, float cg_tol, int disable_contact) {
+    if (cg_max_iter) s->b.param.cg_max_iter = cg_max_iter;
+    if (cg_tol > 0) s->b.param.cg_tol = cg_tol;
+    if (disable_contact >= 0) s->b.param.disable_contact = disable_contact != 0;
+}
+int ppfh_load_state(Session *s, const char *path) {
+    double t; float prev_dt;
+    std::vector<float> c, p;
+    if (!load_state(path, t, prev_dt, c, p, s->dyn_index, s->dyn_offset) || c.size() != size_t(3) * s->b.n_vert) return 0;
+    memcpy(s->b.curr.data(), c.data(), c.size() * sizeof(float));
+    memcpy(s->b.prev.data(), p.data(), p.size() * sizeof(float));
+    s->b.param.time = t;
+    s->b.param.prev_dt = prev_dt;
+    return 1;
+}
+int ppfh_open(Session *s, const char *lib) { return s->be.open(lib, s->err) ? 1 : 0; }
+int ppfh_init(Session *s, const char *log_dir) {
+    const bool ok = s->r.init(log_dir);
+    if (ok && !s->dyn_offset.empty() && s->dyn_offset.size() == size_t(s->b.n_vert) + 1 && !s->b.param.disable_contact)
+        s->be.update_dyn(s->dyn_index.data(), s->dyn_offset.data());
+    return ok ? 1 : 0;
+}
+// one step through the ABI; returns 1 on success.  wall_ms covers update_constraint + advance.
+int ppfh_step(Session *s, double *wall_ms) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool ok = s->r.step();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (wall_ms) *wall_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    return ok ? 1 : 0;
+}
+double ppfh_time(Session *s) { return s->r.time; }
+int ppfh_frame(Session *s) { return s->r.curr_frame; }
+unsigned ppfh_last_flags(Session *s) {
+    if (s->r.steps.empty()) return 0;
+    const PpfStepResult &r = s->r.steps.back().result;
+    return (unsigned)r.ccd_success | ((unsigned)r.pcg_success << 1) | ((unsigned)r.intersection_free << 2) |
+           ((unsigned)r.newton_progress << 3) | ((unsigned)r.pin_feasible << 4) | ((unsigned)r.contact_separated << 5);
+}
+// D2H of the positions through fetch(); out arrays of 3*n_vert floats (may be null to only time the transfer)
+void ppfh_fetch(Session *s, float *curr, float *prev) {
+    s->r.fetch_positions(s->curr, s->prev);
+    if (curr) memcpy(curr, s->curr.data(), s->curr.size() * sizeof(float));
+    if (prev) memcpy(prev, s->prev.data(), s->prev.size() * sizeof(float));
+}
+unsigned ppfh_fetch_dyn(Session *s) {
+    s->r.fetch_dyn_pattern(s->dyn_index, s->dyn_offset);
+    return (unsigned)s->dyn_index.size();
+}
+void ppfh_copy_dyn(Session *s, unsigned *index, unsigned *offset) {
+    memcpy(index, s->dyn_index.data(), s->dyn_index.size() * sizeof(unsigned));
+    memcpy(offset, s->dyn_offset.data(), s->dyn_offset.size() * sizeof(unsigned));
+}
+int ppfh_save_state(Session *s, const char *path) {
+    s->r.fetch_positions(s->curr, s->prev);
+    s->r.fetch_dyn_pattern(s->dyn_index, s->dyn_offset);
+    return save_state(path, s->r, s->curr, s->prev, s->dyn_index, s->dyn_offset, s->b.param.prev_dt) ? 1 : 0;
+}
+int ppfh_has_b200_ext(Session *s) { return s->be.b200_get_stats != nullptr; }
+void ppfh_b200_stats(Session *s, PpfB200Stats *out) {
+    memset(out, 0, sizeof(*out));
+    if (s->be.b200_get_stats) s->be.b200_get_stats(out);
+}
+void ppfh_b200_reset_stats(Session *s) { if (s->be.b200_reset_stats) s->be.b200_reset_stats(); }
+unsigned ppfh_b200_pairs(Session *s, unsigned kind, unsigned *out, unsigned cap) {
+    return s->be.b200_fetch_pairs ? s->be.b200_fetch_pairs(kind, out, cap) : 0;
+}
+// bytes a step moves across the ABI: H2D pins (update_constraint), D2H positions (fetch)
+void ppfh_io_bytes(Session *s, unsigned long long *h2d, unsigned long long *d2h) {
+    *h2d = (unsigned long long)s->b.fix.size() * sizeof(PpfFixPair) + (unsigned long long)s->b.pull.size() * sizeof(PpfPullPair);
+    *d2h = 2ull * s->b.n_vert * 12ull;
+}
+void *ppfh_backend_symbol(Session *s, const char *name);
+}
+
+#include <dlfcn.h>
+extern "C" void *ppfh_backend_symbol(Session *s, const char *name) { return s->be.handle ? dlsym(s->be.handle, name) : nullptr; }

@@ -1,0 +1,193 @@
+"""ppf_b200 -- Python view of the C++ host (libppf_host.so) that drives a backend through the
+reference's C ABI (include/ppf_abi.h).
+
+This module is plumbing for tests, bench.py and __graft_entry__.py: it owns no physics.  A
+`Session` builds the DataSet of a named synthetic scene (the restatement of the reference's Rust
+host, ppf-contact-solver_b200/host/*.cpp), dlopens ONE backend shared library -- the B200 backend
+(ppf-contact-solver_b200/lib/libsimbackend_cuda.so) or the unmodified reference build
+(oracle/_ref/libsimbackend_cuda.so) -- and steps it exactly the way
+crates/ppf-cts-solver/src/backend.rs:837-935 does: update_constraint -> refresh_collision_active ->
+advance, then fetch / fetch_dyn for results.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(ROOT)
+LIB_OURS = os.path.join(ROOT, "lib", "libsimbackend_cuda.so")
+LIB_REF = os.path.join(REPO, "oracle", "_ref", "libsimbackend_cuda.so")
+LIB_HOST = os.path.join(ROOT, "lib", "libppf_host.so")
+HOST_BIN = os.path.join(ROOT, "bin", "ppf_host")
+
+ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"
+    "initialize", "advance", "fetch", "fetch_inv_rest", "fetch_rest_angles", "fetch_dyn_counts", "fetch_dyn",
+    "update_dyn", "update_constraint", "update_rest_shape", "override_velocity", "gather_current_positions",
+    "override_angular_velocity", "init_collision_windows", "refresh_collision_active", "fetch_intersection_records",
+    "set_log_path", "ppf_fatal_code", "ppf_fatal_detail", "g_ppf_fatal_code", "g_ppf_fatal_detail", "print_rust",
+]
+EXT_SYMBOLS = ["ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_measure_spmv"]
+
+
+class B200Stats(ctypes.Structure):  # PpfB200Stats
+    _fields_ = [(n, ctypes.c_double) for n in ("ms_advance", "ms_lbvh_build", "ms_assembly", "ms_contact", "ms_linsolve", "ms_spmv",
+                                               "ms_aabb_update", "ms_line_search")] + \
+               [(n, ctypes.c_ulonglong) for n in ("n_advance", "n_newton", "n_cg_iter", "n_spmv", "n_kernel_launches", "spmv_n_row",
+                                                  "spmv_n_off")] + [("last_num_contact", ctypes.c_uint * 4)]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "last_num_contact"}
+        d["last_num_contact"] = list(self.last_num_contact)
+        return d
+
+
+def build_native(verbose=False):
+    """Compile the backend (nvcc, sm_100a) and the host in-tree."""
+    r = subprocess.run(["make", "-C", ROOT, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("native build failed")
+
+
+_host = None
+
+
+def host():
+    global _host
+    if _host is None:
+        if not os.path.exists(LIB_HOST):
+            raise RuntimeError("%s is missing; run __graft_entry__.build() first" % LIB_HOST)
+        h = ctypes.CDLL(LIB_HOST)
+        h.ppfh_create.restype = ctypes.c_void_p
+        h.ppfh_create.argtypes = [ctypes.c_char_p, ctypes.c_uint]
+        h.ppfh_error.restype = ctypes.c_char_p
+        h.ppfh_time.restype = ctypes.c_double
+        h.ppfh_backend_symbol.restype = ctypes.c_void_p
+        h.ppfh_backend_symbol.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        _host = h
+    return _host
+
+
+class Session:
+    """One scene + one backend library (one per process: the backends keep global state)."""
+
+    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0):
+        if not os.path.exists(lib):
+            raise RuntimeError("backend library %s is missing (no CPU fallback exists)" % lib)
+        self.h = host()
+        self.p = ctypes.c_void_p(self.h.ppfh_create(scene.encode(), ctypes.c_uint(n)))
+        if not self.p:
+            raise RuntimeError("unknown scene %s" % scene)
+        c = (ctypes.c_uint * 6)()
+        self.h.ppfh_counts(self.p, c)
+        self.n_vert, self.n_face, self.n_edge, self.n_hinge, self.n_fix, self.fixed_nnz = [int(v) for v in c]
+        if cg_tol or cg_max_iter:
+            self.h.ppfh_set_args(self.p, ctypes.c_uint(cg_max_iter), ctypes.c_float(cg_tol), ctypes.c_int(-1))
+        if state is not None and not self.h.ppfh_load_state(self.p, state.encode()):
+            raise RuntimeError("cannot load state %s" % state)
+        if not self.h.ppfh_open(self.p, lib.encode()):
+            raise RuntimeError("cannot open backend: %s" % self.h.ppfh_error(self.p).decode())
+        self.log_dir = log_dir or "/tmp/ppf_b200_logs_%d" % os.getpid()
+        os.makedirs(self.log_dir, exist_ok=True)
+        if not self.h.ppfh_init(self.p, self.log_dir.encode()):
+            raise RuntimeError("backend initialize() failed")
+        self.is_b200 = bool(self.h.ppfh_has_b200_ext(self.p))
+
+    def step(self):
+        """update_constraint + advance through the ABI; returns (ok, wall_ms)."""
+        ms = ctypes.c_double(0.0)
+        ok = self.h.ppfh_step(self.p, ctypes.byref(ms))
+        return bool(ok), ms.value
+
+    @property
+    def time(self):
+        return self.h.ppfh_time(self.p)
+
+    @property
+    def frame(self):
+        return int(self.h.ppfh_frame(self.p))
+
+    def fetch(self, want=True):
+        if not want:
+            self.h.ppfh_fetch(self.p, None, None)
+            return None, None
+        curr = np.empty((self.n_vert, 3), dtype=np.float32)
+        prev = np.empty((self.n_vert, 3), dtype=np.float32)
+        self.h.ppfh_fetch(self.p, curr.ctypes.data_as(ctypes.c_void_p), prev.ctypes.data_as(ctypes.c_void_p))
+        return curr, prev
+
+    def fetch_dyn(self):
+        nnz = int(self.h.ppfh_fetch_dyn(self.p))
+        index = np.empty(nnz, dtype=np.uint32)
+        offset = np.empty(self.n_vert + 1, dtype=np.uint32)
+        self.h.ppfh_copy_dyn(self.p, index.ctypes.data_as(ctypes.c_void_p), offset.ctypes.data_as(ctypes.c_void_p))
+        return index, offset
+
+    def save_state(self, path):
+        return bool(self.h.ppfh_save_state(self.p, path.encode()))
+
+    def stats(self):
+        st = B200Stats()
+        self.h.ppfh_b200_stats(self.p, ctypes.byref(st))
+        return st.as_dict()
+
+    def reset_stats(self):
+        self.h.ppfh_b200_reset_stats(self.p)
+
+    def pairs(self, kind):
+        n = int(self.h.ppfh_b200_pairs(self.p, ctypes.c_uint(kind), None, ctypes.c_uint(0)))
+        out = np.empty((n, 2), dtype=np.uint32)
+        if n:
+            self.h.ppfh_b200_pairs(self.p, ctypes.c_uint(kind), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(n))
+        return out
+
+    def io_bytes(self):
+        a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        self.h.ppfh_io_bytes(self.p, ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
+
+    def measure_spmv(self, reps=20):
+        """Times the SpMV kernel alone on the last packed system (CUDA events on the backend stream).
+        Returns (avg_us, n_row, n_off) or None when the backend has no such extension."""
+        addr = self.h.ppfh_backend_symbol(self.p, b"ppf_b200_measure_spmv")
+        if not addr:
+            return None
+        fn = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_uint, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong))(addr)
+        nr, no = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        us = fn(reps, ctypes.byref(nr), ctypes.byref(no))
+        return float(us), int(nr.value), int(no.value)
+
+    def read_log(self, channel):
+        p = os.path.join(self.log_dir, "advance.%s.out" % channel)
+        if not os.path.exists(p):
+            return []
+        return [float(l.split()[1]) for l in open(p) if len(l.split()) == 2]
+
+
+def exported_symbols(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    return {l.split()[-1] for l in out.splitlines() if l.strip()}
+
+
+# ---- result comparison helpers (shared by tests and scripts) ---------------------------------
+def pattern_keys(index, offset):
+    rows = np.repeat(np.arange(offset.size - 1, dtype=np.uint64), np.diff(offset.astype(np.int64)))
+    return rows << np.uint64(32) | index.astype(np.uint64)
+
+
+def load_state_file(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    hdr = raw[:16].view(np.uint32)
+    assert hdr[0] == 0x54535050
+    nv, ni, no = int(hdr[1]), int(hdr[2]), int(hdr[3])
+    off = 16
+    time = raw[off:off + 8].view(np.float64)[0]; off += 8
+    prev_dt = raw[off:off + 4].view(np.float32)[0]; off += 4
+    curr = raw[off:off + 12 * nv].view(np.float32).reshape(nv, 3); off += 12 * nv
+    prev = raw[off:off + 12 * nv].view(np.float32).reshape(nv, 3); off += 12 * nv
+    index = raw[off:off + 4 * ni].view(np.uint32); off += 4 * ni
+    offset = raw[off:off + 4 * no].view(np.uint32)
+    return dict(time=float(time), prev_dt=float(prev_dt), curr=curr, prev=prev, dyn_index=index, dyn_offset=offset)

@@ -1,0 +1,40 @@
+#!/bin/bash
+# make_golden.sh -- regenerates tests/golden/ from the UNMODIFIED reference backend
+# (oracle/_ref/libsimbackend_cuda.so, built by oracle/Makefile.ref from /root/reference).
+# Needs a GPU: run it through gpurun, then copy gpurun_out/golden/* into tests/golden/.
+#   /usr/local/graft/bin/gpurun -- 'bash tests/golden/make_golden.sh'
+# For every case: a reference state (positions + carried dynamic pattern), the first assembled
+# Newton system of the next step (PPF_DUMP_LINSYS=0, main/dump_linsys.hpp), and the reference's
+# result after that step (positions, dynamic-CSR pattern, per-iteration logs).
+set -e
+H=./ppf-contact-solver_b200/bin/ppf_host
+REF=oracle/_ref/libsimbackend_cuda.so
+export PPF_HOST_QUIET=1
+gen() { # name n steps save_every states...
+  name=$1; n=$2; steps=$3; every=$4; shift 4
+  O=gpurun_out/golden/$name
+  rm -rf $O; mkdir -p $O
+  $H --lib $REF --scene fast-twist --n $n --steps $steps --save-every $every --out $O/traj > $O/traj.log 2>&1
+  cases=""
+  for st in "$@"; do
+    cp $O/traj/state_$st.bin $O/state_$st.bin
+    mkdir -p $O/ref_$st
+    PPF_DUMP_LINSYS=0 PPF_DUMP_DIR=$O/ref_$st $H --lib $REF --scene fast-twist --n $n --steps 1 --load $O/state_$st.bin --out $O/ref_$st > $O/ref_$st.log 2>&1
+    python - "$O/ref_$st" <<'PY'
+import json, os, sys
+d = sys.argv[1]
+logs = {}
+for ch in ("num_contact", "iter", "toi", "newton_steps", "toi_advanced", "final_dt", "max_dx", "reresid", "dyn_consumed"):
+    p = os.path.join(d, "data", "advance.%s.out" % ch)
+    logs[ch] = [float(l.split()[1]) for l in open(p)] if os.path.exists(p) else []
+json.dump(logs, open(os.path.join(d, "logs.json"), "w"))
+PY
+    rm -rf $O/ref_$st/data $O/ref_$st/final_prev.bin $O/ref_$st/state_final.bin $O/ref_$st/steps.jsonl
+    cases="$cases{\"state\": \"state_$st.bin\", \"dir\": \"ref_$st\"},"
+  done
+  rm -rf $O/traj $O/*.log
+  echo "{\"scene\": \"fast-twist\", \"n\": $n, \"cases\": [${cases%,}]}" > $O/meta.json
+}
+gen fast_twist_n16 16 90 30 00030 00060 00090
+gen fast_twist_n24 24 80 40 00040 00080
+du -sh gpurun_out/golden/*
