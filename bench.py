@@ -78,16 +78,47 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(scene, n):
-    """CPU oracle port timed on a bounded sample (rank 0, N=1 only)."""
-    exe = os.path.join(REPO, "oracle", "build", "ppf_oracle_bench")
-    if not os.path.exists(exe):
-        return {"value": None, "unit": "frames/sec", "cores": os.cpu_count(), "kind": "port", "sample": "oracle/build/ppf_oracle_bench missing"}
+def cpu_baseline(scene, n, full_v):
+    """CPU oracle port (oracle/build/libppf_oracle.so, OpenMP on all host cores) timed on a bounded
+    sample of the same workload: the same scene generator at 1/4 of the linear resolution (1/16 of the
+    elements), 3 frames from t=0, scaled to the full element count (work per frame is at least linear
+    in the element count; PCG iteration counts grow with resolution, so the scaling favours the CPU)."""
+    base = {"unit": "frames/sec", "cores": os.cpu_count(), "kind": "port"}
     try:
-        out = subprocess.run([exe, "--scene", scene, "--n", str(n), "--budget-sec", "25"], capture_output=True, text=True, timeout=600).stdout
-        return json.loads(out.strip().splitlines()[-1])
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-worker", "--scene", scene, "--n", str(n), "--full-v", str(full_v)],
+                             capture_output=True, text=True, timeout=900)
+        return dict(base, **json.loads(out.stdout.strip().splitlines()[-1]))
     except Exception as e:  # noqa: BLE001
-        return {"value": None, "unit": "frames/sec", "cores": os.cpu_count(), "kind": "port", "sample": "oracle run failed: %s" % e}
+        return dict(base, value=None, sample="oracle run failed: %s" % e)
+
+
+def cpu_baseline_worker(args):
+    import ppf_b200
+
+    full = {"n_vert": args.full_v}
+    n_full = args.n or ppf_b200.DEFAULT_RESOLUTION[args.scene]
+    n_small = max(16, n_full // 4)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        s = ppf_b200.Session(args.scene, n=n_small, lib=ppf_b200.LIB_ORACLE, log_dir="/tmp/ppf_bench_oracle_logs")
+        t0 = time.perf_counter()
+        frames = 0
+        t_sim0 = s.time
+        while frames < 3 and time.perf_counter() - t0 < 60.0:
+            ok, _ = s.step()
+            assert ok
+            frames += 1
+        wall = time.perf_counter() - t0
+        sim_frames = (s.time - t_sim0) * 60.0
+        small_v = s.n_vert
+    finally:
+        os.dup2(saved, 1)
+    scale = small_v / float(full["n_vert"])
+    print(json.dumps({"value": sim_frames / wall * scale, "cores": os.cpu_count(),
+                      "sample": "%s at n=%d (V=%d, %.4f of the full V=%d), %d frames from t=0 in %.1f s on the CPU oracle; "
+                                "frames/sec scaled by the vertex ratio" % (args.scene, n_small, small_v, scale, full["n_vert"], frames, wall)}))
 
 
 def main():
@@ -98,7 +129,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="large-twist")
     ap.add_argument("--n", type=int, default=0, help="resolution override (0 = the config's own: n=1410 for large-twist)")
+    ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--full-v", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_baseline_worker:
+        return cpu_baseline_worker(args)
     W = max(3, args.warmup)
     K = max(1, args.steps)
 
@@ -116,14 +151,9 @@ def main():
         if not os.path.exists(lib):
             raise SystemExit("the CUDA backend %s is missing; there is no CPU fallback (run __graft_entry__.build())" % lib)
 
-    dist = None
-    if WORLD > 1 and args.impl == "ours":
-        import torch
-        import torch.distributed as dist_mod
+    import replicas
 
-        torch.cuda.set_device(0)
-        dist_mod.init_process_group("nccl")
-        dist = dist_mod
+    ranks = replicas.Ranks("nccl") if args.impl == "ours" else None
 
     os.environ.setdefault("PPF_HOST_QUIET", "1")
     os.environ.setdefault("PPF_B200_QUIET", "1")
@@ -139,10 +169,8 @@ def main():
             s.fetch(want=False)
 
         def barrier():
-            if dist is not None:
-                import torch
-                dist.barrier()
-                torch.cuda.synchronize()
+            if ranks is not None:
+                ranks.barrier()
 
         barrier()
         clocks = ClockSampler()
@@ -178,13 +206,9 @@ def main():
 
     # max over ranks of the timed region, sum of the frames all ranks advanced
     t_dev, t_e2e, tot_frames = dev_s, wall_e2e, frames
-    if dist is not None:
-        import torch
-        t = torch.tensor([dev_s, wall_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        f = torch.tensor([frames], device="cuda", dtype=torch.float64)
-        dist.all_reduce(f, op=dist.ReduceOp.SUM)
-        t_dev, t_e2e, tot_frames = float(t[0]), float(t[1]), float(f[0])
+    if ranks is not None:
+        t_dev, t_e2e, tot_frames = ranks.reduce(dev_s, wall_e2e, frames)
+        ranks.close()
     if RANK != 0:
         return
 
@@ -236,7 +260,7 @@ def main():
                             "traffic": traffic, "peak_source": how, "us_per_launch": us, "n_row": n_row, "n_off": n_off,
                             "bytes_per_launch": bytes_per_launch}
     if WORLD == 1:
-        line["cpu_baseline"] = cpu_baseline(args.scene, args.n)
+        line["cpu_baseline"] = cpu_baseline(args.scene, args.n, s.n_vert)
     print(json.dumps(line))
 
 

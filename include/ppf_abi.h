@@ -283,6 +283,11 @@ void ppf_b200_reset_stats(void);
  * kind: 0 point-face, 1 point-edge, 2 point-point, 3 edge-edge.  Returns the
  * pair count; copies min(count, cap) pairs (a,b) into out[2*i], out[2*i+1]. */
 unsigned ppf_b200_fetch_pairs(unsigned kind, unsigned *out, unsigned cap);
+/* Contact detection alone (BVH refit + broad + narrow phase) at caller-provided positions, 3 floats
+ * per vertex; the lists are then read with ppf_b200_fetch_pairs.  Returns the total pair count, or
+ * 0xFFFFFFFF when n_vert does not match the initialized scene.  Clobbers the backend's evaluation
+ * positions: call it between steps only. */
+unsigned ppf_b200_detect_pairs(const float *x, unsigned n_vert);
 /* Average microseconds of the SpMV kernel alone on the last packed system (CUDA events, `reps` launches). */
 double ppf_b200_measure_spmv(unsigned reps, unsigned long long *n_row, unsigned long long *n_off);
 

@@ -1,0 +1,37 @@
+/* oracle_shim.c -- TEST INFRASTRUCTURE: exports the oracle's leaf math (oracle_math.h,
+ * oracle_elastic.h) as plain C symbols so tests/test_oracle_cpu.py can pin it, bit for bit,
+ * against the reference's own headers compiled for the host (oracle/_ref/libref_host.so) and
+ * against the committed known-answer vectors in tests/golden/leaf_math.npz. */
+#include "oracle_elastic.h"
+#include "oracle_math.h"
+#define SHIM __attribute__((visibility("default")))
+
+SHIM void orc_point_triangle_coeff(const float *p, const float *t0, const float *t1, const float *t2, float *o) { o_point_triangle_coeff(p, t0, t1, t2, o); }
+SHIM void orc_point_triangle_coeff_unclassified(const float *p, const float *t0, const float *t1, const float *t2, float *o) { o_point_triangle_coeff_unclassified(p, t0, t1, t2, o); }
+SHIM void orc_point_edge_coeff(const float *p, const float *e0, const float *e1, float *o) { o_point_edge_coeff(p, e0, e1, o); }
+SHIM void orc_edge_edge_coeff(const float *a0, const float *a1, const float *b0, const float *b1, float *o) { o_edge_edge_coeff(a0, a1, b0, b1, o); }
+/* kind: 0 point-triangle, 1 edge-edge, 2 point-edge, 3 point-point; x0/x1: vertex-major positions at t=0 / t=1 */
+SHIM float orc_ccd(int kind, const float *x0, const float *x1, float offset, float ghat, float max_t, float ccd_eps, unsigned *overlap) {
+    static const int nc[4] = {4, 4, 3, 2}, split[4] = {1, 2, 1, 1};
+    float a[4][3], b[4][3];
+    for (int c = 0; c < nc[kind]; ++c) for (int k = 0; k < 3; ++k) { a[c][k] = x0[3 * c + k]; b[c][k] = x1[3 * c + k]; }
+    unsigned ov = 0;
+    const float r = o_accd(kind, nc[kind], split[kind], a, b, offset, ghat, max_t, ccd_eps, &ov);
+    if (overlap) *overlap = ov;
+    return r;
+}
+SHIM int orc_edge_triangle_intersect(const float *a0, const float *a1, const float *b0, const float *b1, const float *b2) { return o_edge_triangle_intersect(a0, a1, b0, b1, b2); }
+SHIM void orc_cubic(float g, float ghat, float offset, float *out2) { out2[0] = o_cubic_gradient(g, ghat, offset); out2[1] = o_cubic_curvature(g, ghat, offset); }
+SHIM void orc_bw_face(const float *x9, const float *ir4, float mu, float lmd, float mass, float *g9, float *H81) {
+    float g[3][3];
+    o_bw_face(x9, x9 + 3, x9 + 6, ir4, mu, lmd, mass, g, H81);
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) g9[3 * a + k] = g[a][k];
+}
+/* x12: hinge vertices in ORIGINAL order h0..h3; outputs in the remapped order (h2,h1,h0,h3) like the reference scatters */
+SHIM void orc_hinge(const float *x12, float rest_angle, float *f12, float *H144) {
+    static const int map[4] = {2, 1, 0, 3};
+    float X[4][3], f[4][3];
+    for (int a = 0; a < 4; ++a) for (int k = 0; k < 3; ++k) X[a][k] = x12[3 * map[a] + k];
+    o_hinge(X, rest_angle, f, H144);
+    for (int a = 0; a < 4; ++a) for (int k = 0; k < 3; ++k) f12[3 * a + k] = f[a][k];
+}

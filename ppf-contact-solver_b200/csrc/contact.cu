@@ -541,12 +541,9 @@ static Ctx make_ctx(State &s, const PpfParamSet &prm) {
 static DBuf<unsigned char> g_cub_tmp;
 static DBuf<unsigned> g_row_len;
 
-unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed) {
-    (void)dt;
+// broad + narrow phase at eval_x: fills s.pairs[0..3] (unsorted) and returns the four counts
+static unsigned detect_contacts(State &s, const PpfParamSet &prm, unsigned hc[4]) {
     cudaStream_t q = s.stream;
-    max_nnz_row = 0;
-    dyn_consumed = 0.0f;
-    // ---- detect ----
     broad_phase(s, s.eval_x.p, s.eval_x.p, false, 0.0f);
     Ctx c = make_ctx(s, prm);
     unsigned *acc_cnt = s.counters.p + 8; // [8..11]
@@ -563,11 +560,22 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
         if (k == 3) k_narrow<3><<<grid, 256, 0, q>>>(c, s.cand[k].pairs.p, n, s.pairs[k].pairs.p, acc_cnt + k, cap);
         LAUNCH_COUNT(1);
     }
-    unsigned hc[4];
-    CUDA_OK(cudaMemcpyAsync(hc, acc_cnt, sizeof(hc), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaMemcpyAsync(hc, acc_cnt, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, q));
     CUDA_OK(cudaStreamSynchronize(q));
     unsigned total = 0;
     for (int k = 0; k < 4; ++k) { s.pairs[k].count = hc[k]; s.last_num_contact[k] = hc[k]; total += hc[k]; }
+    return total;
+}
+
+unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed) {
+    (void)dt;
+    cudaStream_t q = s.stream;
+    max_nnz_row = 0;
+    dyn_consumed = 0.0f;
+    // ---- detect ----
+    unsigned hc[4];
+    const unsigned total = detect_contacts(s, prm, hc);
+    Ctx c = make_ctx(s, prm);
 
     // ---- dynamic pattern: sorted unique keys outside the fixed pattern ----
     unsigned shift = 1;
@@ -943,6 +951,30 @@ bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm) {
 }
 
 } // namespace ppf
+
+// contact detection alone at caller-provided positions (3 floats per vertex): uploads them as the
+// evaluation positions, refits the three BVHs and runs the broad + narrow phase.  Extension used by
+// the parity tests (pair sets against the CPU oracle); returns the total number of accepted pairs.
+__global__ void k_upload_positions(unsigned n, const float *__restrict__ x, float4 *__restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.0f);
+}
+extern "C" __attribute__((visibility("default"))) unsigned ppf_b200_detect_pairs(const float *x, unsigned n_vert) {
+    using namespace ppf;
+    State &s = g;
+    if (!x || n_vert != s.nv) return 0xFFFFFFFFu;
+    float *tmp = nullptr;
+    CUDA_OK(cudaMalloc(&tmp, sizeof(float) * 3 * size_t(n_vert)));
+    CUDA_OK(cudaMemcpyAsync(tmp, x, sizeof(float) * 3 * size_t(n_vert), cudaMemcpyHostToDevice, s.stream));
+    k_upload_positions<<<div_up(n_vert, 256), 256, 0, s.stream>>>(n_vert, tmp, s.eval_x.p);
+    bvh_refit(s, s.bvh_face, 0, s.eval_x.p, s.eval_x.p, 1.0f);
+    bvh_refit(s, s.bvh_edge, 1, s.eval_x.p, s.eval_x.p, 1.0f);
+    bvh_refit(s, s.bvh_vert, 2, s.eval_x.p, s.eval_x.p, 1.0f);
+    unsigned hc[4];
+    const unsigned total = detect_contacts(s, *s.param, hc);
+    CUDA_OK(cudaFree(tmp));
+    return total;
+}
 
 // sorted contact-pair lists of the last assembly (extension used by the parity tests)
 extern "C" __attribute__((visibility("default"))) unsigned ppf_b200_fetch_pairs(unsigned kind, unsigned *out, unsigned cap) {

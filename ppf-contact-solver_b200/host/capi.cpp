@@ -114,6 +114,23 @@ void ppfh_io_bytes(Session *s, unsigned long long *h2d, unsigned long long *d2h)
     *d2h = 2ull * s->b.n_vert * 12ull;
 }
 void *ppfh_backend_symbol(Session *s, const char *name);
+// pins of the last update_constraint: vertex indices + target positions; returns the count
+unsigned ppfh_fix_targets(Session *s, unsigned *index, float *pos) {
+    const unsigned n = (unsigned)s->b.fix.size();
+    if (index && pos)
+        for (unsigned i = 0; i < n; ++i) { index[i] = s->b.fix[i].index; memcpy(pos + 3 * i, s->b.fix[i].position.v, 12); }
+    return n;
+}
+// mesh topology in global order: faces (3 per), edges (2 per), per-vertex (ghat, offset)
+void ppfh_topology(Session *s, unsigned *face, unsigned *edge, float *vparam2) {
+    if (face) memcpy(face, s->b.face.data(), s->b.face.size() * sizeof(PpfVec3u));
+    if (edge) memcpy(edge, s->b.edge.data(), s->b.edge.size() * sizeof(PpfVec2u));
+    if (vparam2)
+        for (unsigned i = 0; i < s->b.n_vert; ++i) {
+            const PpfVertexParam &vp = s->b.vparam[s->b.vprop[i].param_index];
+            vparam2[2 * i] = vp.ghat; vparam2[2 * i + 1] = vp.offset;
+        }
+}
 }
 
 #include <dlfcn.h>

@@ -20,6 +20,9 @@ REPO = os.path.dirname(ROOT)
 LIB_OURS = os.path.join(ROOT, "lib", "libsimbackend_cuda.so")
 LIB_REF = os.path.join(REPO, "oracle", "_ref", "libsimbackend_cuda.so")
 LIB_HOST = os.path.join(ROOT, "lib", "libppf_host.so")
+# the CPU oracle (TEST INFRASTRUCTURE): tests, smoke() and bench.py's cpu_baseline leg only
+LIB_ORACLE = os.path.join(REPO, "oracle", "build", "libppf_oracle.so")
+DEFAULT_RESOLUTION = {"twist": 360, "large-twist": 1410, "fast-twist": 48, "hang": 128, "sheet": 32}  # host/scene.cpp
 HOST_BIN = os.path.join(ROOT, "bin", "ppf_host")
 
 ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"
@@ -28,7 +31,7 @@ ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"
     "override_angular_velocity", "init_collision_windows", "refresh_collision_active", "fetch_intersection_records",
     "set_log_path", "ppf_fatal_code", "ppf_fatal_detail", "g_ppf_fatal_code", "g_ppf_fatal_detail", "print_rust",
 ]
-EXT_SYMBOLS = ["ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_measure_spmv"]
+EXT_SYMBOLS = ["ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_detect_pairs", "ppf_b200_measure_spmv"]
 
 
 class B200Stats(ctypes.Structure):  # PpfB200Stats
@@ -159,6 +162,50 @@ class Session:
         nr, no = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
         us = fn(reps, ctypes.byref(nr), ctypes.byref(no))
         return float(us), int(nr.value), int(no.value)
+
+    def _sym(self, name, restype, *argtypes):
+        addr = self.h.ppfh_backend_symbol(self.p, name.encode())
+        return ctypes.CFUNCTYPE(restype, *argtypes)(addr) if addr else None
+
+    def _pair_list(self, fn, kind):
+        n = int(fn(kind, None, 0))
+        out = np.empty((n, 2), dtype=np.uint32)
+        if n:
+            fn(kind, out.ctypes.data_as(ctypes.c_void_p), n)
+        return out
+
+    def detect_pairs(self, x):
+        """Contact detection alone at positions x (n_vert x 3 float32), on whichever backend is loaded.
+        Returns (total, accepted[4], fragile[4] or None): sorted (a, b) index pairs per kind
+        (0 point-face, 1 point-edge, 2 point-point, 3 edge-edge).  `fragile` exists on the oracle only."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.shape == (self.n_vert, 3)
+        fetch_t = (ctypes.c_uint, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint)
+        gpu = self._sym("ppf_b200_detect_pairs", ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint)
+        if gpu:
+            total = int(gpu(x.ctypes.data_as(ctypes.c_void_p), self.n_vert))
+            assert total != 0xFFFFFFFF
+            fetch = self._sym("ppf_b200_fetch_pairs", *fetch_t)
+            return total, [self._pair_list(fetch, k) for k in range(4)], None
+        orc = self._sym("oracle_detect_pairs", ctypes.c_uint, ctypes.c_void_p)
+        if not orc:
+            raise RuntimeError("the loaded backend has no contact-detection entry point")
+        total = int(orc(x.ctypes.data_as(ctypes.c_void_p)))
+        fetch = self._sym("oracle_fetch_pairs", *fetch_t)
+        frag = self._sym("oracle_fetch_fragile", *fetch_t)
+        return total, [self._pair_list(fetch, k) for k in range(4)], [self._pair_list(frag, k) for k in range(4)]
+
+    def fix_targets(self):
+        n = int(self.h.ppfh_fix_targets(self.p, None, None))
+        idx = np.empty(n, np.uint32); pos = np.empty((n, 3), np.float32)
+        if n:
+            self.h.ppfh_fix_targets(self.p, idx.ctypes.data_as(ctypes.c_void_p), pos.ctypes.data_as(ctypes.c_void_p))
+        return idx, pos
+
+    def topology(self):
+        face = np.empty((self.n_face, 3), np.uint32); edge = np.empty((self.n_edge, 2), np.uint32); vp = np.empty((self.n_vert, 2), np.float32)
+        self.h.ppfh_topology(self.p, face.ctypes.data_as(ctypes.c_void_p), edge.ctypes.data_as(ctypes.c_void_p), vp.ctypes.data_as(ctypes.c_void_p))
+        return face, edge, vp
 
     def read_log(self, channel):
         p = os.path.join(self.log_dir, "advance.%s.out" % channel)

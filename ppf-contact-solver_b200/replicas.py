@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, "replicas only".
+
+The per-step path of one scene does not shard (DESIGN.md section "multi-GPU"): each rank owns an
+independent scene on its own device, there is no data-path collective, and torch.distributed is
+used only for the barrier around the timed region and for the max-over-ranks / sum-over-ranks of
+the measurements.  NCCL on the GPU box, gloo in the CPU tests (tests/test_dist_gloo.py).
+"""
+import os
+
+
+class Ranks:
+    def __init__(self, backend=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dist = None
+        self.device = "cpu"
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            backend = backend or "nccl"
+            if backend == "nccl":
+                torch.cuda.set_device(0)  # CUDA_VISIBLE_DEVICES was narrowed to this rank's GPU
+                self.device = "cuda"
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group(backend)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            import torch
+
+            self.dist.barrier()
+            if self.device == "cuda":
+                torch.cuda.synchronize()
+
+    def reduce(self, dev_s, e2e_s, frames):
+        """(max over ranks of the device time, max of the end-to-end time, sum of the frames advanced)."""
+        if self.dist is None:
+            return dev_s, e2e_s, frames
+        import torch
+
+        t = torch.tensor([dev_s, e2e_s], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        f = torch.tensor([frames], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(f, op=self.dist.ReduceOp.SUM)
+        return float(t[0]), float(t[1]), float(f[0])
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()

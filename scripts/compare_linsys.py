@@ -54,10 +54,12 @@ def compare(ref_path, our_path, verbose=True):
     # per-block relative error (against the block's own magnitude, floored at 1e-6 of the global scale)
     bs = np.maximum(np.abs(v0[i0]).max(axis=1), 1e-6 * scale) if dv.size else np.ones(0)
     res["offdiag_max_rel_block_diff"] = float((dv.max(axis=1) / bs).max()) if dv.size else 0.0
+    res["frac_blocks_off"] = float(((dv.max(axis=1) / bs) > 1e-3).mean()) if dv.size else 0.0
     dscale = float(np.abs(d0).max())
     res["diag_max_rel_diff"] = float((np.abs(d0.astype(np.float64) - d1).max(axis=1) / np.maximum(np.abs(d0).max(axis=1), 1e-6 * dscale)).max())
     bscale = float(np.abs(b0).max())
     res["rhs_max_abs_diff_over_scale"] = float(np.abs(b0.astype(np.float64) - b1).max() / max(bscale, 1e-30))
+    res["frac_rhs_rows_off"] = float((np.abs(b0.astype(np.float64) - b1).max(axis=1) > 1e-3 * max(bscale, 1e-30)).mean())
     if only0.size:
         res["only_ref_examples"] = [(int(k >> np.uint64(32)), int(k & np.uint64(0xFFFFFFFF))) for k in only0[:8]]
         res["only_ref_maxabs"] = [float(np.abs(v0[np.searchsorted(k0, k)]).max()) for k in only0[:8]]

@@ -1,0 +1,78 @@
+"""Runs one backend job (a backend library keeps global state, so one Session per library per process).
+
+job = {"lib": "ours"|"reference"|"oracle", "scene": ..., "n": ..., "state": path|None, "steps": k,
+       "dump_linsys": bool, "detect": "state"|"final"|None, "detect_twice": bool, "out": directory}
+Writes out/result.npz (+ out/linsys_0.bin) and returns the dict of arrays.  Used in-process by the
+tests for the first job on a library (so the CUDA .so is loaded by the pytest process itself) and as
+`python tests/_worker.py job.json` in a subprocess for every further job.
+"""
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "ppf-contact-solver_b200"))
+
+CHANNELS = ("num_contact", "iter", "toi", "newton_steps", "toi_advanced", "max_dx", "reresid")
+
+
+def run(job):
+    import ppf_b200
+
+    lib = {"ours": ppf_b200.LIB_OURS, "reference": ppf_b200.LIB_REF, "oracle": ppf_b200.LIB_ORACLE}[job["lib"]]
+    out = job["out"]
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out, exist_ok=True)
+    os.environ["PPF_HOST_QUIET"] = "1"
+    os.environ["PPF_B200_QUIET"] = "1"
+    if job.get("dump_linsys"):
+        os.environ["PPF_DUMP_LINSYS"] = "0"
+        os.environ["PPF_DUMP_DIR"] = out
+    else:
+        os.environ.pop("PPF_DUMP_LINSYS", None)
+    s = ppf_b200.Session(job["scene"], n=job.get("n", 0), lib=lib, log_dir=os.path.join(out, "logs"), state=job.get("state"))
+    res = {"counts": np.array([s.n_vert, s.n_face, s.n_edge, s.n_hinge, s.n_fix], np.int64)}
+    if job.get("detect") == "state":
+        x0, _ = s.fetch()
+        _pairs(s, x0, res, "state", job.get("detect_twice"))
+    oks, walls = [], []
+    for _ in range(job.get("steps", 1)):
+        ok, ms = s.step()
+        oks.append(ok); walls.append(ms)
+        if not ok:
+            break
+    curr, prev = s.fetch()
+    res["ok"] = np.array(oks); res["wall_ms"] = np.array(walls)
+    res["curr"] = curr; res["prev"] = prev; res["time"] = np.array([s.time])
+    idx, off = s.fetch_dyn()
+    res["dyn_index"] = idx; res["dyn_offset"] = off
+    for ch in CHANNELS:
+        res["log_" + ch] = np.array(s.read_log(ch), np.float64)
+    if s.is_b200:
+        st = s.stats()
+        res["stats_json"] = np.array(json.dumps(st))
+    if job.get("detect") == "final":
+        _pairs(s, curr, res, "final", job.get("detect_twice"))
+    if job.get("fix_positions"):
+        res["fix_index"], res["fix_target"] = s.fix_targets()
+    np.savez(os.path.join(out, "result.npz"), **res)
+    return res
+
+
+def _pairs(s, x, res, tag, twice):
+    total, acc, frag = s.detect_pairs(x)
+    res["%s_total" % tag] = np.array([total])
+    for k in range(4):
+        res["%s_pairs%d" % (tag, k)] = acc[k]
+        if frag is not None:
+            res["%s_fragile%d" % (tag, k)] = frag[k]
+    if twice:
+        total2, acc2, _ = s.detect_pairs(x)
+        res["%s_repeat_equal" % tag] = np.array([total2 == total and all(np.array_equal(a, b) for a, b in zip(acc, acc2))])
+
+
+if __name__ == "__main__":
+    run(json.load(open(sys.argv[1])))

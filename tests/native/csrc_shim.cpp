@@ -1,0 +1,42 @@
+// csrc_shim.cpp -- exports the BACKEND's per-element math (ppf-contact-solver_b200/csrc/math_*.cuh,
+// compiled for the host in the tests only, -ffp-contract=off) under the same C signatures as
+// oracle/oracle_shim.c, so tests/test_oracle_cpu.py runs one set of known-answer checks over both.
+#include "../../ppf-contact-solver_b200/csrc/math_accd.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_contact.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
+using namespace ppf;
+#define SHIM extern "C" __attribute__((visibility("default")))
+static V3 v(const float *p) { return mk(p[0], p[1], p[2]); }
+
+SHIM void orc_point_triangle_coeff(const float *p, const float *t0, const float *t1, const float *t2, float *o) { const C3 c = point_triangle_coeff(v(p), v(t0), v(t1), v(t2)); o[0] = c.a; o[1] = c.b; o[2] = c.c; }
+SHIM void orc_point_triangle_coeff_unclassified(const float *p, const float *t0, const float *t1, const float *t2, float *o) { const C3 c = point_triangle_coeff_unclassified(v(p), v(t0), v(t1), v(t2)); o[0] = c.a; o[1] = c.b; o[2] = c.c; }
+SHIM void orc_point_edge_coeff(const float *p, const float *e0, const float *e1, float *o) { const C2 c = point_edge_coeff(v(p), v(e0), v(e1)); o[0] = c.a; o[1] = c.b; }
+SHIM void orc_edge_edge_coeff(const float *a0, const float *a1, const float *b0, const float *b1, float *o) { const C4 c = edge_edge_coeff(v(a0), v(a1), v(b0), v(b1)); o[0] = c.a; o[1] = c.b; o[2] = c.c; o[3] = c.d; }
+SHIM float orc_ccd(int kind, const float *x0, const float *x1, float offset, float ghat, float max_t, float ccd_eps, unsigned *overlap) {
+    CcdOverlap ov{0u, 0.0f, 0.0f};
+    float r;
+    if (kind == 0) r = point_triangle_ccd(v(x0), v(x1), v(x0 + 3), v(x0 + 6), v(x0 + 9), v(x1 + 3), v(x1 + 6), v(x1 + 9), offset, ghat, max_t, ccd_eps, ov);
+    else if (kind == 1) r = edge_edge_ccd(v(x0), v(x0 + 3), v(x0 + 6), v(x0 + 9), v(x1), v(x1 + 3), v(x1 + 6), v(x1 + 9), offset, ghat, max_t, ccd_eps, ov);
+    else if (kind == 2) r = point_edge_ccd(v(x0), v(x1), v(x0 + 3), v(x0 + 6), v(x1 + 3), v(x1 + 6), offset, ghat, max_t, ccd_eps, ov);
+    else r = point_point_ccd(v(x0), v(x1), v(x0 + 3), v(x1 + 3), offset, ghat, max_t, ccd_eps, ov);
+    if (overlap) *overlap = ov.flag;
+    return r;
+}
+SHIM void orc_cubic(float g, float ghat, float offset, float *out2) { out2[0] = cubic_gradient(g, ghat, offset); out2[1] = cubic_curvature(g, ghat, offset); }
+SHIM void orc_bw_face(const float *x9, const float *ir4, float mu, float lmd, float mass, float *g9, float *H81) {
+    FaceElastic fe;
+    bw_face(v(x9), v(x9 + 3), v(x9 + 6), ir4, mu, lmd, mass, fe);
+    for (int a = 0; a < 3; ++a) { g9[3 * a] = fe.f[a].x; g9[3 * a + 1] = fe.f[a].y; g9[3 * a + 2] = fe.f[a].z; }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) H81[(3 * b + c) * 9 + 3 * a + r] = fe.H[a][b].m[c * 3 + r];
+}
+SHIM void orc_hinge(const float *x12, float rest_angle, float *f12, float *H144) {
+    static const int map[4] = {2, 1, 0, 3};
+    V3 X[4];
+    for (int a = 0; a < 4; ++a) X[a] = v(x12 + 3 * map[a]);
+    HingeElastic he;
+    hinge_force_hessian(X, rest_angle, he);
+    for (int a = 0; a < 4; ++a) { f12[3 * a] = he.f[a].x; f12[3 * a + 1] = he.f[a].y; f12[3 * a + 2] = he.f[a].z; }
+    for (int i = 0; i < 144; ++i) H144[i] = he.H[i];
+}

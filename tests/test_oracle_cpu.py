@@ -1,0 +1,169 @@
+"""Pins the oracle's leaf math (oracle/oracle_math.h, oracle_elastic.h) against the reference.
+
+Known-answer vectors: tests/golden/leaf_math.npz, produced by tests/golden/make_leaf_golden.py from
+the reference's own headers compiled for the host (oracle/_ref/libref_host.so).  Integer results and
+fp32 payloads of the contact predicates are compared BIT FOR BIT (both sides are built with
+-ffp-contract=off, so the operation order is the only degree of freedom); the elastic energies are
+compared within 2e-4 of the per-case scale (the oracle evaluates them in x space, the vectors are in
+F space, so the chain rule is applied here in float64).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FP = C.POINTER(C.c_float)
+
+
+def fp(a):
+    return a.ctypes.data_as(FP)
+
+
+def _build_csrc_shim():
+    """The backend's own math headers (csrc/math_*.cuh) compiled for the host, same C signatures."""
+    out = os.path.join(REPO, "tests", "native", "build", "libcsrc_math.so")
+    src = os.path.join(REPO, "tests", "native", "csrc_shim.cpp")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    deps = [src] + [os.path.join(REPO, "ppf-contact-solver_b200", "csrc", f) for f in os.listdir(os.path.join(REPO, "ppf-contact-solver_b200", "csrc")) if f.endswith(".cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-shared", "-x", "c++", src, "-o", out], check=True)
+    return out
+
+
+@pytest.fixture(scope="module", params=["oracle", "backend-math"])
+def orc(built, request):
+    """Both implementations of the leaf math run the same known-answer checks: the oracle's plain-C
+    restatement and the CUDA backend's headers compiled for the host."""
+    path = os.path.join(REPO, "oracle", "build", "liboracle_math.so") if request.param == "oracle" else _build_csrc_shim()
+    lib = C.CDLL(path)
+    lib.orc_ccd.restype = C.c_float
+    if request.param == "oracle":
+        lib.orc_edge_triangle_intersect.restype = C.c_int
+    lib.which = request.param
+    return lib
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(REPO, "tests", "golden", "leaf_math.npz"))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def same_bits(a, b):
+    """bitwise equality, NaN payloads treated as equal when both are NaN"""
+    a = np.ascontiguousarray(a, np.float32); b = np.ascontiguousarray(b, np.float32)
+    return (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
+
+
+def test_distance_coefficients_bit_exact(orc, gold):
+    pts = gold["dist_pts"]
+    m = len(pts)
+    pt = np.zeros((m, 3), np.float32); ptu = np.zeros((m, 3), np.float32); pe = np.zeros((m, 2), np.float32); ee = np.zeros((m, 4), np.float32)
+    for i in range(m):
+        q = [fp(pts[i, k]) for k in range(4)]
+        orc.orc_point_triangle_coeff(q[0], q[1], q[2], q[3], fp(pt[i]))
+        orc.orc_point_triangle_coeff_unclassified(q[0], q[1], q[2], q[3], fp(ptu[i]))
+        orc.orc_point_edge_coeff(q[0], q[1], q[2], fp(pe[i]))
+        orc.orc_edge_edge_coeff(q[0], q[1], q[2], q[3], fp(ee[i]))
+    for name, mine in (("pt_coeff", pt), ("pt_coeff_unclassified", ptu), ("pe_coeff", pe), ("ee_coeff", ee)):
+        ok = same_bits(mine, gold[name])
+        assert ok.all(), "%s: %d of %d cases differ from the reference" % (name, int((~ok.all(axis=1)).sum()), m)
+
+
+def test_edge_triangle_intersection_exact(orc, gold):
+    if orc.which != "oracle":
+        pytest.skip("the backend's intersection test is device code (covered by the gpu step tests)")
+    p5 = gold["isect_pts"]
+    mine = np.array([orc.orc_edge_triangle_intersect(*[fp(p5[i, k]) for k in range(5)]) for i in range(len(p5))], np.int32)
+    assert (mine == gold["isect"]).all()
+    assert 0 < mine.sum() < len(mine)  # both outcomes are exercised
+
+
+@pytest.mark.parametrize("name,kind", [("pt", 0), ("ee", 1), ("pe", 2), ("pp", 3)])
+def test_accd_bit_exact(orc, gold, name, kind):
+    x0 = gold["ccd_%s_x0" % name]; x1 = gold["ccd_%s_x1" % name]
+    toi = np.zeros(len(x0), np.float32); ov = np.zeros(len(x0), np.uint32)
+    for i in range(len(x0)):
+        o = C.c_uint(0)
+        toi[i] = orc.orc_ccd(kind, fp(x0[i]), fp(x1[i]), C.c_float(0.0), C.c_float(1e-3), C.c_float(1.25), C.c_float(1e-2), C.byref(o))
+        ov[i] = o.value
+    ok = same_bits(toi, gold["ccd_%s_toi" % name])
+    assert ok.all(), "%d of %d TOIs differ" % (int((~ok).sum()), len(ok))
+    assert (ov == gold["ccd_%s_overlap" % name]).all()
+    t = gold["ccd_%s_toi" % name]
+    assert (t < 1.25).any() and (t == np.float32(1.25)).any()  # hits and misses are both exercised
+
+
+def test_cubic_barrier_bit_exact(orc, gold):
+    g = gold["cubic_g"]
+    mine = np.zeros((len(g), 2), np.float32)
+    for i in range(len(g)):
+        orc.orc_cubic(C.c_float(g[i]), C.c_float(1e-3), C.c_float(2e-4), fp(mine[i]))
+    assert same_bits(mine, gold["cubic"]).all()
+
+
+def test_baraff_witkin_matches_reference_energy(orc, gold):
+    F = gold["bw_F"].astype(np.float64)
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for i in range(len(F)):
+        # a triangle whose deformation gradient is F[i]: rest triangle with inverse rest matrix IR (2x2, col-major)
+        ir = np.array([[1.3, -0.2], [0.1, 0.9]])                 # IR (row, col)
+        Fm = F[i].reshape(2, 3).T                                  # 3x2, column-major input
+        D = Fm @ np.linalg.inv(ir)                                 # [x1-x0, x2-x0]
+        x0 = rng.uniform(-1, 1, 3)
+        x = np.stack([x0, x0 + D[:, 0], x0 + D[:, 1]]).astype(np.float32)
+        ir32 = np.array([ir[0, 0], ir[1, 0], ir[0, 1], ir[1, 1]], np.float32)
+        g = np.zeros(9, np.float32); H = np.zeros(81, np.float32)
+        orc.orc_bw_face(fp(x), fp(ir32), C.c_float(1.3), C.c_float(0.7), C.c_float(2.0), fp(g), fp(H))
+        # chain rule in float64 from the exact float32 inputs the oracle saw
+        D32 = np.stack([x[1] - x[0], x[2] - x[0]], axis=1).astype(np.float64)
+        ir64 = np.array([[ir32[0], ir32[2]], [ir32[1], ir32[3]]], np.float64)
+        # dF/dx: F = D * IR, D columns = x1-x0, x2-x0 ; vec(F) column-major (3x2)
+        dD = np.zeros((6, 9))
+        for k in range(3):
+            dD[k, 3 + k] = 1; dD[k, k] -= 1
+            dD[3 + k, 6 + k] = 1; dD[3 + k, k] -= 1
+        dF = np.kron(ir64.T, np.eye(3)) @ dD
+        # the vectors were produced at F[i]; the float32 round trip moves F slightly, so compare with a tolerance
+        gref = 2.0 * dF.T @ gold["bw_dedF"][i].astype(np.float64)
+        Href = 2.0 * dF.T @ gold["bw_d2edF2"][i].astype(np.float64).reshape(6, 6).T @ dF
+        assert np.abs(D32 @ ir64 - Fm).max() < 1e-5
+        sg = max(np.abs(gref).max(), 1e-3); sH = np.abs(Href).max()
+        worst = max(worst, np.abs(g - gref).max() / sg, np.abs(H.reshape(9, 9).T - Href).max() / sH)
+    assert worst < 2e-4, worst
+
+
+def test_hinge_matches_reference(orc, gold):
+    hx = gold["hinge_x"]; rest = gold["hinge_rest"]
+    worst_f = worst_H = 0.0
+    for i in range(len(hx)):
+        f = np.zeros(12, np.float32); H = np.zeros(144, np.float32)
+        orc.orc_hinge(fp(hx[i]), C.c_float(rest[i]), fp(f), fp(H))
+        fr = gold["hinge_f"][i]; Hr = gold["hinge_H"][i]
+        worst_f = max(worst_f, np.abs(f - fr).max() / max(np.abs(fr).max(), 1e-6))
+        worst_H = max(worst_H, np.abs(H - Hr).max() / max(np.abs(Hr).max(), 1e-6))
+    assert worst_f < 1e-5 and worst_H < 1e-4, (worst_f, worst_H)
+
+
+def test_oracle_agrees_with_live_reference_headers(orc, gold):
+    """When oracle/_ref/libref_host.so is present (build container), cross-check fresh random cases too."""
+    path = os.path.join(REPO, "oracle", "_ref", "libref_host.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_host.so not built (no /root/reference here)")
+    ref = C.CDLL(path)
+    rng = np.random.default_rng(77)
+    pts = rng.uniform(-1, 1, size=(2000, 4, 3)).astype(np.float32)
+    a = np.zeros(4, np.float32); b = np.zeros(4, np.float32)
+    for i in range(len(pts)):
+        q = [fp(pts[i, k]) for k in range(4)]
+        orc.orc_edge_edge_coeff(q[0], q[1], q[2], q[3], fp(a)); ref.ref_edge_edge_coeff(q[0], q[1], q[2], q[3], fp(b))
+        assert same_bits(a, b).all()
+        orc.orc_point_triangle_coeff(q[0], q[1], q[2], q[3], fp(a)); ref.ref_point_triangle_coeff(q[0], q[1], q[2], q[3], fp(b))
+        assert same_bits(a[:3], b[:3]).all()
