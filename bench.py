@@ -235,7 +235,10 @@ def main():
     }
     if n_newton:
         line["ms_per_newton_step"] = 1e3 * dev_s / n_newton
+        line["newton_steps_per_step"] = n_newton / K
         line["pcg_iters_per_newton_step"] = n_cg / n_newton
+        line["phase_ms_per_step"] = {k[3:]: (st1[k] - st0[k]) / K for k in
+                                     ("ms_lbvh_build", "ms_assembly", "ms_contact", "ms_linsolve", "ms_aabb_update", "ms_line_search")}
     if args.impl == "reference":
         line["impl"] = "reference"
         line["value"] = tot_frames / wall_adv
