@@ -77,6 +77,7 @@ struct Bvh {
     DBuf<int2> child;           // per internal node: (left, right) node ids
     DBuf<int> parent;           // per node
     DBuf<float4> lo, hi;        // per node AABB (xyz)
+    DBuf<float4> ulo, uhi;      // per node interval of sweep displacements t_max*(x1-x0) (relative-motion sweeps only)
     DBuf<unsigned> flag;        // bottom-up arrival counters
     DBuf<unsigned char> sort_tmp;
     size_t sort_tmp_bytes = 0;
@@ -139,6 +140,9 @@ struct State {
 
     Bvh bvh_face, bvh_edge, bvh_vert;
     PairList cand[4];   // candidates: 0 vertex-face, 1 vertex-edge, 2 vertex-vertex, 3 edge-edge
+    bool bvh_relative = false;    // the trees carry displacement intervals (last refit was bvh_refit_relative)
+    bool bvh_cover_eval = false;  // the BVH boxes bound the primitives at the current eval_x (false after a relative refit)
+    bool cand_cover_eval = false; // the candidate lists of the last line-search sweep cover the current eval_x (see contact.cu)
     PairList pairs[4];  // accepted contacts of the last assembly (pf, pe, pp, ee)
     DBuf<unsigned> counters; // device scalars (pair counters etc.)
     DBuf<float> scalars;     // device float scalars (reductions)
@@ -183,6 +187,8 @@ void recompute_fixed_flags(State &s);
 // bvh.cu
 void bvh_build(State &s, Bvh &b, int kind, const float4 *x);      // kind: 0 face, 1 edge, 2 vertex
 void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate);
+// boxes at x0 plus per-node displacement intervals t_max*(x1-x0) for relative-motion sweep queries
+void bvh_refit_relative(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float t_max);
 
 // contact.cu
 unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed);

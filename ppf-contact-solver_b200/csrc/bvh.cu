@@ -123,8 +123,10 @@ struct LeafParams {
 };
 
 // leaf boxes (lbvh.cu:623-731) + bottom-up merge: the second thread to reach a node owns it
+// With ulo/uhi the leaf box is the box at x0 and the node additionally carries the component-wise
+// interval of its vertices' sweep displacements extrapolate*(x1-x0) (see bvh_query_relative).
 __global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_sorted, const int2 *child, const int *parent,
-                      float4 *lo, float4 *hi, unsigned *flag) {
+                      float4 *lo, float4 *hi, unsigned *flag, float4 *ulo, float4 *uhi) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const unsigned prim = prim_sorted[k];
@@ -136,20 +138,32 @@ __global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_s
     if (kind == 0) { const uint4 f = P.face[prim]; vidx[0] = f.x; vidx[1] = f.y; vidx[2] = f.z; nvx = 3; }
     else if (kind == 1) { const uint2 e = P.edge[prim]; vidx[0] = e.x; vidx[1] = e.y; vidx[2] = 0; nvx = 2; }
     else { vidx[0] = prim; vidx[1] = vidx[2] = 0; nvx = 1; }
+    const bool rel = ulo != nullptr;
+    float un[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ux[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int a = 0; a < nvx; ++a) {
         const float4 y0 = P.x0[vidx[a]], y1 = P.x1[vidx[a]];
-        const float z[3] = {P.extrapolate * (y1.x - y0.x) + y0.x, P.extrapolate * (y1.y - y0.y) + y0.y, P.extrapolate * (y1.z - y0.z) + y0.z};
         const float y[3] = {y0.x, y0.y, y0.z};
-        for (int d = 0; d < 3; ++d) {
-            mn[d] = fminf(mn[d], fminf(y[d], z[d]));
-            mx[d] = fmaxf(mx[d], fmaxf(y[d], z[d]));
+        if (rel) {
+            const float u[3] = {P.extrapolate * (y1.x - y0.x), P.extrapolate * (y1.y - y0.y), P.extrapolate * (y1.z - y0.z)};
+            for (int d = 0; d < 3; ++d) {
+                mn[d] = fminf(mn[d], y[d]); mx[d] = fmaxf(mx[d], y[d]);
+                un[d] = fminf(un[d], u[d]); ux[d] = fmaxf(ux[d], u[d]);
+            }
+        } else {
+            const float z[3] = {P.extrapolate * (y1.x - y0.x) + y0.x, P.extrapolate * (y1.y - y0.y) + y0.y, P.extrapolate * (y1.z - y0.z) + y0.z};
+            for (int d = 0; d < 3; ++d) {
+                mn[d] = fminf(mn[d], fminf(y[d], z[d]));
+                mx[d] = fmaxf(mx[d], fmaxf(y[d], z[d]));
+            }
         }
     }
     float4 blo = make_float4(mn[0] - margin, mn[1] - margin, mn[2] - margin, 0.f);
     float4 bhi = make_float4(mx[0] + margin, mx[1] + margin, mx[2] + margin, 0.f);
+    float4 dlo = make_float4(un[0], un[1], un[2], 0.f), dhi = make_float4(ux[0], ux[1], ux[2], 0.f);
     int node = (int)(n - 1 + k);
     lo[node] = blo;
     hi[node] = bhi;
+    if (rel) { ulo[node] = dlo; uhi[node] = dhi; }
     if (n == 1) return;
     int p = parent[node];
     while (p >= 0) {
@@ -163,16 +177,25 @@ __global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_s
         bhi = make_float4(fmaxf(bhi.x, ohi.x), fmaxf(bhi.y, ohi.y), fmaxf(bhi.z, ohi.z), 0.f);
         lo[p] = blo;
         hi[p] = bhi;
+        if (rel) {
+            const float4 qlo = __ldcg(ulo + other), qhi = __ldcg(uhi + other);
+            dlo = make_float4(fminf(dlo.x, qlo.x), fminf(dlo.y, qlo.y), fminf(dlo.z, qlo.z), 0.f);
+            dhi = make_float4(fmaxf(dhi.x, qhi.x), fmaxf(dhi.y, qhi.y), fmaxf(dhi.z, qhi.z), 0.f);
+            ulo[p] = dlo;
+            uhi[p] = dhi;
+        }
         node = p;
         p = parent[p];
     }
 }
 
-static void fit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate) {
+static void fit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate, bool relative = false) {
     if (b.n == 0) return;
+    if (relative) { b.ulo.reserve(2 * size_t(b.n)); b.uhi.reserve(2 * size_t(b.n)); }
     LeafParams P{x0, x1, extrapolate, s.face.p, s.edge.p, kind == 0 ? s.fcp.p : (kind == 1 ? s.ecp.p : s.vcp.p)};
     if (b.n > 1) CUDA_OK(cudaMemsetAsync(b.flag.p, 0, sizeof(unsigned) * (b.n - 1), s.stream));
-    k_fit<<<div_up(b.n, 256), 256, 0, s.stream>>>(kind, b.n, P, b.prim_sorted.p, b.child.p, b.parent.p, b.lo.p, b.hi.p, b.flag.p);
+    k_fit<<<div_up(b.n, 256), 256, 0, s.stream>>>(kind, b.n, P, b.prim_sorted.p, b.child.p, b.parent.p, b.lo.p, b.hi.p, b.flag.p,
+                                                   relative ? b.ulo.p : nullptr, relative ? b.uhi.p : nullptr);
     LAUNCH_COUNT(1);
 }
 
@@ -195,8 +218,19 @@ void bvh_build(State &s, Bvh &b, int kind, const float4 *x) {
     if (n > 1) k_radix_tree<<<div_up(n - 1, 256), 256, 0, q>>>((int)n, b.morton_sorted.p, b.child.p, b.parent.p);
     LAUNCH_COUNT(4);
     fit(s, b, kind, x, x, 1.0f);
+    s.bvh_cover_eval = true;
+    s.bvh_relative = false;
 }
 
-void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate) { fit(s, b, kind, x0, x1, extrapolate); }
+void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate) {
+    fit(s, b, kind, x0, x1, extrapolate);
+    s.bvh_cover_eval = true; // also true for a swept hull: eval_x lies on the swept segment
+    s.bvh_relative = false;
+}
+void bvh_refit_relative(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float t_max) {
+    fit(s, b, kind, x0, x1, t_max, true);
+    s.bvh_cover_eval = false;
+    s.bvh_relative = true;
+}
 
 } // namespace ppf

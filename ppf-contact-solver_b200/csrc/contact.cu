@@ -90,37 +90,45 @@ __global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
     const float ext = 0.5f * cp.x + cp.y;
     const float4 p0 = A.x0[v];
     Box q;
-    if (A.sweep) {
+    q.lx = p0.x - ext; q.ly = p0.y - ext; q.lz = p0.z - ext;
+    q.hx = p0.x + ext; q.hy = p0.y + ext; q.hz = p0.z + ext;
+    DispInterval u = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int sweep = A.sweep;
+    const bool rel = sweep == 1;
+    if (rel) { // relative-motion sweep (bvh.cuh): start box + displacement interval of the query
+        const float4 p1 = A.x1[v];
+        u.lx = u.hx = A.sweep_t * (p1.x - p0.x); u.ly = u.hy = A.sweep_t * (p1.y - p0.y); u.lz = u.hz = A.sweep_t * (p1.z - p0.z);
+    } else if (sweep == 2) { // the reference's swept hull (A/B switch PPF_B200_SWEPT_HULL, lbvh.cu:623-731)
         const float4 p1 = A.x1[v];
         const float zx = A.sweep_t * (p1.x - p0.x) + p0.x, zy = A.sweep_t * (p1.y - p0.y) + p0.y, zz = A.sweep_t * (p1.z - p0.z) + p0.z;
         q.lx = fminf(p0.x, zx) - ext; q.ly = fminf(p0.y, zy) - ext; q.lz = fminf(p0.z, zz) - ext;
         q.hx = fmaxf(p0.x, zx) + ext; q.hy = fmaxf(p0.y, zy) + ext; q.hz = fmaxf(p0.z, zz) + ext;
-    } else {
-        q.lx = p0.x - ext; q.ly = p0.y - ext; q.lz = p0.z - ext;
-        q.hx = p0.x + ext; q.hy = p0.y + ext; q.hz = p0.z + ext;
     }
     bool ok = true;
     {
         Emit em; em.out = A.out[0]; em.counter = A.cnt + 0; em.cap = A.cap[0];
-        const int sweep = A.sweep;
-        ok &= bvh_query(A.face, q, [&](unsigned f) {
+        auto emit = [&](unsigned f) {
             if (!sweep) { const uint4 fv = A.faces[f]; if (fv.x == v || fv.y == v || fv.z == v) return; }
             em.push(v, f);
-        });
+        };
+        ok &= rel ? bvh_query_relative(A.face, q, u, emit) : bvh_query(A.face, q, emit);
         em.flush();
     }
-    if (!A.sweep) {
+    { // vertex-edge: only the assembly evaluates these pairs; the sweep lists them so that the next
+      // assembly can reuse the sweep's candidates instead of traversing again (detect_contacts)
         Emit em; em.out = A.out[1]; em.counter = A.cnt + 1; em.cap = A.cap[1];
-        ok &= bvh_query(A.edge, q, [&](unsigned e) {
+        auto emit = [&](unsigned e) {
             const uint2 ev = A.edges[e];
             if (ev.x == v || ev.y == v) return;
             em.push(v, e);
-        });
+        };
+        ok &= rel ? bvh_query_relative(A.edge, q, u, emit) : bvh_query(A.edge, q, emit);
         em.flush();
     }
     {
         Emit em; em.out = A.out[2]; em.counter = A.cnt + 2; em.cap = A.cap[2];
-        ok &= bvh_query(A.vert, q, [&](unsigned w) { if (w < v) em.push(v, w); });
+        auto emit = [&](unsigned w) { if (w < v) em.push(v, w); };
+        ok &= rel ? bvh_query_relative(A.vert, q, u, emit) : bvh_query(A.vert, q, emit);
         em.flush();
     }
     if (!ok) atomicExch(A.error, 1u);
@@ -137,21 +145,29 @@ __global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned nq) {
     Box q;
     q.lx = fminf(a0.x, b0.x) - ext; q.ly = fminf(a0.y, b0.y) - ext; q.lz = fminf(a0.z, b0.z) - ext;
     q.hx = fmaxf(a0.x, b0.x) + ext; q.hy = fmaxf(a0.y, b0.y) + ext; q.hz = fmaxf(a0.z, b0.z) + ext;
-    if (A.sweep) {
+    DispInterval u = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int sweep = A.sweep;
+    const bool rel = sweep == 1;
+    if (sweep) {
         const float4 a1 = A.x1[ev.x], b1 = A.x1[ev.y];
         const float s = A.sweep_t;
-        const float ax = s * (a1.x - a0.x) + a0.x, ay = s * (a1.y - a0.y) + a0.y, az = s * (a1.z - a0.z) + a0.z;
-        const float bx = s * (b1.x - b0.x) + b0.x, by = s * (b1.y - b0.y) + b0.y, bz = s * (b1.z - b0.z) + b0.z;
-        q.lx = fminf(q.lx, fminf(ax, bx) - ext); q.ly = fminf(q.ly, fminf(ay, by) - ext); q.lz = fminf(q.lz, fminf(az, bz) - ext);
-        q.hx = fmaxf(q.hx, fmaxf(ax, bx) + ext); q.hy = fmaxf(q.hy, fmaxf(ay, by) + ext); q.hz = fmaxf(q.hz, fmaxf(az, bz) + ext);
+        const float ax = s * (a1.x - a0.x), ay = s * (a1.y - a0.y), az = s * (a1.z - a0.z);
+        const float bx = s * (b1.x - b0.x), by = s * (b1.y - b0.y), bz = s * (b1.z - b0.z);
+        if (rel) {
+            u.lx = fminf(ax, bx); u.ly = fminf(ay, by); u.lz = fminf(az, bz);
+            u.hx = fmaxf(ax, bx); u.hy = fmaxf(ay, by); u.hz = fmaxf(az, bz);
+        } else { // swept hull
+            q.lx = fminf(q.lx, fminf(ax + a0.x, bx + b0.x) - ext); q.ly = fminf(q.ly, fminf(ay + a0.y, by + b0.y) - ext); q.lz = fminf(q.lz, fminf(az + a0.z, bz + b0.z) - ext);
+            q.hx = fmaxf(q.hx, fmaxf(ax + a0.x, bx + b0.x) + ext); q.hy = fmaxf(q.hy, fmaxf(ay + a0.y, by + b0.y) + ext); q.hz = fmaxf(q.hz, fmaxf(az + a0.z, bz + b0.z) + ext);
+        }
     }
     Emit em; em.out = A.out[3]; em.counter = A.cnt + 3; em.cap = A.cap[3];
-    const int sweep = A.sweep;
-    const bool ok = bvh_query(A.edge, q, [&](unsigned f) {
+    auto emit = [&](unsigned f) {
         if (!(e < f)) return;
         if (!sweep) { const uint2 fv = A.edges[f]; if (fv.x == ev.x || fv.x == ev.y || fv.y == ev.x || fv.y == ev.y) return; }
         em.push(e, f);
-    });
+    };
+    const bool ok = rel ? bvh_query_relative(A.edge, q, u, emit) : bvh_query(A.edge, q, emit);
     em.flush();
     if (!ok) atomicExch(A.error, 1u);
 }
@@ -167,7 +183,7 @@ static void broad_phase(State &s, const float4 *x0, const float4 *x1, bool sweep
         CUDA_OK(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned), q));
         BpArgs A;
         A.face = view_of(s.bvh_face); A.edge = view_of(s.bvh_edge); A.vert = view_of(s.bvh_vert);
-        A.x0 = x0; A.x1 = x1; A.sweep_t = sweep_t; A.sweep = sweep ? 1 : 0;
+        A.x0 = x0; A.x1 = x1; A.sweep_t = sweep_t; A.sweep = sweep ? (s.bvh_relative ? 1 : 2) : 0;
         A.vcp = s.vcp.p; A.ecp = s.ecp.p; A.faces = s.face.p; A.edges = s.edge.p;
         for (int k = 0; k < 4; ++k) { A.out[k] = s.cand[k].pairs.p; A.cap[k] = (unsigned)std::min<size_t>(s.cand[k].pairs.cap, 0xFFFFFFF0u); }
         A.cnt = cnt; A.error = cnt + 4;
@@ -542,9 +558,52 @@ static DBuf<unsigned char> g_cub_tmp;
 static DBuf<unsigned> g_row_len;
 
 // broad + narrow phase at eval_x: fills s.pairs[0..3] (unsorted) and returns the four counts
+static std::vector<uint2> sorted_pairs_host(State &s, int k) {
+    std::vector<uint2> h(s.pairs[k].count);
+    if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), s.pairs[k].pairs.p, sizeof(uint2) * h.size(), cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end(), [](const uint2 &a, const uint2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    return h;
+}
+
+static unsigned detect_contacts_impl(State &s, const PpfParamSet &prm, unsigned hc[4], bool allow_reuse);
+
+// PPF_B200_VERIFY_CAND=1 (tests): whenever the sweep's candidates are reused, detect again with a fresh
+// static traversal at eval_x and demand the two accepted pair sets to be identical.
 static unsigned detect_contacts(State &s, const PpfParamSet &prm, unsigned hc[4]) {
+    static const bool verify = getenv("PPF_B200_VERIFY_CAND") != nullptr;
+    static const bool no_reuse = getenv("PPF_B200_NO_CAND_REUSE") != nullptr;
+    const bool reuse = s.cand_cover_eval && !no_reuse;
+    if (!(verify && reuse)) return detect_contacts_impl(s, prm, hc, reuse);
+    unsigned h1[4];
+    detect_contacts_impl(s, prm, h1, true);
+    std::vector<uint2> a[4];
+    for (int k = 0; k < 4; ++k) a[k] = sorted_pairs_host(s, k);
+    const unsigned total = detect_contacts_impl(s, prm, hc, false);
+    s.cand_cover_eval = false; // the candidate lists now are the static ones (still valid for eval_x; keep it simple)
+    for (int k = 0; k < 4; ++k) {
+        const std::vector<uint2> b = sorted_pairs_host(s, k);
+        bool same = a[k].size() == b.size();
+        for (size_t i = 0; same && i < b.size(); ++i) same = a[k][i].x == b[i].x && a[k][i].y == b[i].y;
+        if (!same) fatal(4, "candidate reuse changed the accepted pair set of kind %d: %zu (reused sweep candidates) vs %zu (fresh traversal)", k, a[k].size(), b.size());
+    }
+    static unsigned long long n_ok = 0;
+    if ((++n_ok % 16) == 1) fprintf(stderr, "[verify-cand] %llu assemblies verified identical (last: %u pairs)\n", n_ok, total);
+    return total;
+}
+
+static unsigned detect_contacts_impl(State &s, const PpfParamSet &prm, unsigned hc[4], bool allow_reuse) {
     cudaStream_t q = s.stream;
-    broad_phase(s, s.eval_x.p, s.eval_x.p, false, 0.0f);
+    // The candidate lists of the last line-search sweep x_old -> x_old + t_max*(x_new - x_old) cover every
+    // pair that is within the contact gap anywhere on that segment (bvh.cuh), and eval_x is a point of
+    // the segment (x_old + toi*(x_new - x_old), toi <= 1 <= t_max): no second traversal is needed.
+    if (!allow_reuse) {
+        if (!s.bvh_cover_eval) { // the trees hold start boxes of the last relative sweep: refit at eval_x first
+            bvh_refit(s, s.bvh_face, 0, s.eval_x.p, s.eval_x.p, 1.0f);
+            bvh_refit(s, s.bvh_edge, 1, s.eval_x.p, s.eval_x.p, 1.0f);
+            bvh_refit(s, s.bvh_vert, 2, s.eval_x.p, s.eval_x.p, 1.0f);
+        }
+        broad_phase(s, s.eval_x.p, s.eval_x.p, false, 0.0f);
+    }
     Ctx c = make_ctx(s, prm);
     unsigned *acc_cnt = s.counters.p + 8; // [8..11]
     CUDA_OK(cudaMemsetAsync(acc_cnt, 0, 8 * sizeof(unsigned), q));
@@ -753,6 +812,7 @@ static unsigned g_last_overlap[4] = {0, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
 float contact_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap) {
     cudaStream_t q = s.stream;
     broad_phase(s, x0, x1, true, prm.line_search_max_t);
+    s.cand_cover_eval = prm.line_search_max_t >= 1.0f; // valid for eval_x = x0 + toi*(x1 - x0) after the lerp
     CcdCtx c;
     c.x0 = x0; c.x1 = x1; c.vcp = s.vcp.p; c.ecp = s.ecp.p; c.fcp = s.fcp.p; c.face = s.face.p; c.edge = s.edge.p;
     c.vfixed = s.vfixed.p; c.efixed = s.efixed.p; c.ffixed = s.ffixed.p; c.vcollider = s.vcollider.p;
@@ -971,6 +1031,7 @@ extern "C" __attribute__((visibility("default"))) unsigned ppf_b200_detect_pairs
     bvh_refit(s, s.bvh_edge, 1, s.eval_x.p, s.eval_x.p, 1.0f);
     bvh_refit(s, s.bvh_vert, 2, s.eval_x.p, s.eval_x.p, 1.0f);
     unsigned hc[4];
+    s.cand_cover_eval = false; // arbitrary positions: traverse
     const unsigned total = detect_contacts(s, *s.param, hc);
     CUDA_OK(cudaFree(tmp));
     return total;

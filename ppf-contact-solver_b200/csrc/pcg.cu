@@ -56,17 +56,30 @@ struct PackedMatrix {
     DBuf<float> val;                 // 9 planes x cap
     DBuf<unsigned> fx_pos;           // per ORIGINAL fixed slot: position in the block list, 0xFFFFFFFF for diagonals
     DBuf<float> D, Pinv;             // 6 planes x n: (00, 11, 22, 01, 02, 12)
-    DBuf<float4> x, r, z, p, y;
+    DBuf<float> x, r, z;             // three SoA planes of n floats each
+    DBuf<float4> p, y;
     DBuf<CgScalars> sc;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     unsigned graph_nnz = ~0u;
     const void *graph_val = nullptr;
     int *h_status = nullptr;         // pinned mirror of {iter, status, last_resid}
-    unsigned grid = 0;               // persistent grid size
+    unsigned grid = 0;               // persistent grid size of the vector kernels
+    unsigned spmv_grid = 0;          // persistent grid of the staged SpMV (SMs x resident CTAs)
     bool ready = false;
 };
 static PackedMatrix P;
+
+// The SpMV stages whole chunks of the block list through shared memory with bulk copies, so every
+// plane is padded to a whole number of chunks (and the plane stride keeps 16-byte alignment).
+static constexpr int SPMV_T = 256;                       // threads per CTA
+static constexpr int SPMV_U = 2;                         // blocks per thread per chunk
+static constexpr int SPMV_CHUNK = SPMV_T * SPMV_U;       // blocks per stage
+static constexpr int SPMV_STAGES = 2;
+static constexpr int SPMV_ARRAYS = 11;                   // row, col, nine value planes
+static constexpr unsigned SPMV_STAGE_BYTES = SPMV_ARRAYS * SPMV_CHUNK * 4;
+static constexpr size_t SPMV_SMEM = size_t(SPMV_STAGES) * SPMV_STAGE_BYTES + 128;
+static size_t round_cap(size_t n) { return (n + SPMV_CHUNK - 1) / SPMV_CHUNK * SPMV_CHUNK + SPMV_CHUNK; }
 
 static void pcg_init(State &s) {
     const unsigned n = s.nv;
@@ -85,16 +98,14 @@ static void pcg_init(State &s) {
         }
     P.nnz_f = (unsigned)row.size();
     cudaStream_t q = s.stream;
-    P.cap = size_t(P.nnz_f) + 1024;
+    P.cap = round_cap(size_t(P.nnz_f) + 1024);
     P.row.reserve(P.cap); P.col.reserve(P.cap); P.val.reserve(size_t(9) * P.cap);
-    P.cap = P.row.cap; // DBuf over-allocates; use what we really have for all three
-    P.col.reserve(P.cap); P.val.reserve(size_t(9) * P.cap);
     CUDA_OK(cudaMemcpyAsync(P.row.p, row.data(), sizeof(unsigned) * row.size(), cudaMemcpyHostToDevice, q));
     CUDA_OK(cudaMemcpyAsync(P.col.p, col.data(), sizeof(unsigned) * col.size(), cudaMemcpyHostToDevice, q));
     P.fx_pos.upload(pos.data(), nnz, q);
     CUDA_OK(cudaStreamSynchronize(q));
     P.D.reserve(size_t(6) * n); P.Pinv.reserve(size_t(6) * n);
-    P.x.reserve(n); P.r.reserve(n); P.z.reserve(n); P.p.reserve(n); P.y.reserve(n);
+    P.x.reserve(size_t(3) * n); P.r.reserve(size_t(3) * n); P.z.reserve(size_t(3) * n); P.p.reserve(n); P.y.reserve(n);
     P.sc.reserve(1);
     CUDA_OK(cudaMallocHost(&P.h_status, 64));
     int dev = 0, sms = 148;
@@ -102,6 +113,8 @@ static void pcg_init(State &s) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     P.grid = (unsigned)sms * 8u;
     if (const char *e = getenv("PPF_B200_PCG_GRID")) P.grid = (unsigned)atoi(e);
+    P.spmv_grid = (unsigned)sms * 4u;
+    if (const char *e = getenv("PPF_B200_SPMV_GRID")) P.spmv_grid = (unsigned)atoi(e);
     P.ready = true;
 }
 
@@ -109,7 +122,7 @@ static void pcg_init(State &s) {
 static void pcg_reserve(State &s, unsigned nnz_d) {
     const size_t need = size_t(P.nnz_f) + nnz_d;
     if (need <= P.cap) return;
-    const size_t want = need + need / 4 + 1024;
+    const size_t want = round_cap(need + need / 4 + 1024);
     P.row.reserve_keep(want, s.stream);
     P.col.reserve_keep(want, s.stream);
     P.val.reserve(size_t(9) * want); // values are re-packed every solve
@@ -355,33 +368,167 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_spmv(unsigned nnz, const unsigned
     }
 }
 
+// ---- the same product with the block list staged through shared memory by bulk async copies ----
+// One elected thread per CTA streams chunks of SPMV_CHUNK blocks (eleven contiguous 2 KB segments:
+// row, col and the nine value planes) into a ring of shared-memory stages with cp.async.bulk
+// (SASS UBLKCP), completion tracked by one mbarrier per stage.  The copy engine keeps
+// SPMV_STAGES x 22.5 KB per CTA in flight independent of register pressure, so the dependent part of
+// the loop (gather p_row / p_col from L2, 3x3 products, segmented scan, vector reductions) no longer
+// serialises behind the streaming loads, which is what bounded k_spmv (ncu: long-scoreboard stalls,
+// 67 % of DRAM peak).  Each thread handles SPMV_U blocks per chunk to have four gathers in flight.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done = 0;
+    const unsigned addr = smem_u32(bar);
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const unsigned *__restrict__ row, const unsigned *__restrict__ col,
+                                                          const float *__restrict__ val, size_t plane, const float4 *__restrict__ p,
+                                                          float4 *__restrict__ y, CgScalars *sc, int with_dots) {
+    if (with_dots && sc->status != ST_RUNNING) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + size_t(SPMV_STAGES) * SPMV_STAGE_BYTES);
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned n_chunks = (nnz + SPMV_CHUNK - 1) / SPMV_CHUNK;
+    if (tid == 0) {
+        for (int st = 0; st < SPMV_STAGES; ++st) mbar_init(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto fill = [&](int st, unsigned chunk) {
+        unsigned *dst = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
+        const size_t base = size_t(chunk) * SPMV_CHUNK;
+        mbar_expect_tx(&full[st], SPMV_STAGE_BYTES);
+        bulk_g2s(dst, row + base, SPMV_CHUNK * 4, &full[st]);
+        bulk_g2s(dst + SPMV_CHUNK, col + base, SPMV_CHUNK * 4, &full[st]);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) bulk_g2s(dst + (2 + e) * SPMV_CHUNK, val + size_t(e) * plane + base, SPMV_CHUNK * 4, &full[st]);
+    };
+    if (tid == 0)
+        for (int st = 0; st < SPMV_STAGES; ++st) {
+            const unsigned c = blockIdx.x + unsigned(st) * gridDim.x;
+            if (c < n_chunks) fill(st, c);
+        }
+    float dot = 0.f, absdot = 0.f;
+    unsigned it = 0;
+    for (unsigned chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+        const int st = int(it % SPMV_STAGES);
+        mbar_wait(&full[st], (it / SPMV_STAGES) & 1u);
+        const unsigned *sm = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
+        unsigned a[SPMV_U], b[SPMV_U];
+        float h[SPMV_U][9];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            const unsigned j = u * SPMV_T + tid;
+            a[u] = sm[j];
+            b[u] = sm[SPMV_CHUNK + j];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) h[u][e] = __uint_as_float(sm[(2 + e) * SPMV_CHUNK + j]);
+        }
+        __syncthreads(); // every thread holds its blocks in registers: the stage can be refilled
+        if (tid == 0) {
+            const unsigned nc = chunk + unsigned(SPMV_STAGES) * gridDim.x;
+            if (nc < n_chunks) fill(st, nc);
+        }
+        const size_t k0 = size_t(chunk) * SPMV_CHUNK;
+        bool on[SPMV_U];
+        float4 pa[SPMV_U], pb[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            on[u] = k0 + u * SPMV_T + tid < nnz;
+            if (!on[u]) { a[u] = 0xFFFFFFFFu; b[u] = 0; }
+            pa[u] = on[u] ? p[a[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            pb[u] = on[u] ? p[b[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            const float *hh = h[u];
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            if (on[u]) {
+                s0 = hh[0] * pb[u].x + hh[3] * pb[u].y + hh[6] * pb[u].z;
+                s1 = hh[1] * pb[u].x + hh[4] * pb[u].y + hh[7] * pb[u].z;
+                s2 = hh[2] * pb[u].x + hh[5] * pb[u].y + hh[8] * pb[u].z;
+                red_add_v4(y + b[u], hh[0] * pa[u].x + hh[1] * pa[u].y + hh[2] * pa[u].z, hh[3] * pa[u].x + hh[4] * pa[u].y + hh[5] * pa[u].z,
+                           hh[6] * pa[u].x + hh[7] * pa[u].y + hh[8] * pa[u].z);
+                const float term = 2.0f * (pa[u].x * s0 + pa[u].y * s1 + pa[u].z * s2);
+                dot += term;
+                absdot += fabsf(term);
+            }
+            const unsigned ra_self = a[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned ra = __shfl_up_sync(0xffffffffu, ra_self, o);
+                const float t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+                if (lane >= (unsigned)o && ra == ra_self) { s0 += t0; s1 += t1; s2 += t2; }
+            }
+            const unsigned next = __shfl_down_sync(0xffffffffu, ra_self, 1);
+            if (on[u] && (lane == 31 || next != ra_self)) red_add_v4(y + ra_self, s0, s1, s2);
+        }
+    }
+    if (!with_dots) return;
+    const int par = sc->iter & 1;
+    block_accumulate2(dot, absdot, &sc->acc_pap[par], &sc->acc_abs[par]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rz[par ^ 1] = 0.0;
+        sc->err[par ^ 1] = 0.0;
+    }
+}
+
 __device__ __forceinline__ float4 sym6_mul(const float *__restrict__ M, size_t n, size_t i, const float4 v) {
     const float m00 = __ldg(M + i), m11 = __ldg(M + n + i), m22 = __ldg(M + 2 * n + i);
     const float m01 = __ldg(M + 3 * n + i), m02 = __ldg(M + 4 * n + i), m12 = __ldg(M + 5 * n + i);
     return make_float4(m00 * v.x + m01 * v.y + m02 * v.z, m01 * v.x + m11 * v.y + m12 * v.z, m02 * v.x + m12 * v.y + m22 * v.z, 0.f);
 }
 
-// fused x/r/z update with in-thread alpha (reference: cg_fused_update_kernel, solver.cu:431-514)
-__global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, const float4 *__restrict__ p, const float4 *__restrict__ y, float4 *__restrict__ x,
-                                                      float4 *__restrict__ r, float4 *__restrict__ z, const float *__restrict__ Pinv, CgScalars *sc) {
-    if (sc->status != ST_RUNNING) return;
-    const int par = sc->iter & 1;
+// x, r and z are never gathered, so they live as three SoA planes of n floats (12 B per row per
+// access instead of a padded 16 B float4); p and y stay float4 (16-byte gathers / vector reductions).
+struct V3Planes { float *x, *y, *z; };
+__device__ __forceinline__ float4 ld_planes(const float *__restrict__ v, size_t n, size_t a) { return make_float4(v[a], v[n + a], v[2 * n + a], 0.f); }
+__device__ __forceinline__ void st_planes(float *__restrict__ v, size_t n, size_t a, const float4 w) { v[a] = w.x; v[n + a] = w.y; v[2 * n + a] = w.z; }
+
+// step length of the current iteration from the device-resident scalars (reference: cg_fused_update_kernel,
+// solver.cu:431-514, and its curvature-noise verdict 66-114).  verdict: 0 ok, 1 truncate, 2 fatal
+__device__ __forceinline__ float cg_alpha(const CgScalars *sc, int par, int &verdict, float &pAp_out) {
     const float pAp = (float)sc->acc_pap[par];
     const float noise = CG_NOISE_SLACK * CG_FLOAT_EPS * (float)sc->acc_abs[par];
     const float rz0 = (float)sc->rz[par];
-    float alpha;
-    int verdict = 0; // 0 ok, 1 truncate, 2 fatal
-    if (pAp > noise) alpha = rz0 / pAp;
-    else { alpha = 0.0f; verdict = (pAp < -noise || pAp != pAp) ? 2 : 1; }
+    pAp_out = pAp;
+    verdict = 0;
+    if (pAp > noise) return rz0 / pAp;
+    verdict = (pAp < -noise || pAp != pAp) ? 2 : 1;
+    return 0.0f;
+}
+
+// r -= alpha A p;  z = Pinv r;  r.z and |r|_1.   (x += alpha p is applied by k_direction, which reads p anyway)
+__global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, const float4 *__restrict__ y, float *__restrict__ r, float *__restrict__ z,
+                                                      const float *__restrict__ Pinv, CgScalars *sc) {
+    if (sc->status != ST_RUNNING) return;
+    const int par = sc->iter & 1;
+    int verdict;
+    float pAp;
+    const float alpha = cg_alpha(sc, par, verdict, pAp);
     float rz = 0.f, err = 0.f;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        const float4 pa = p[a], ya = y[a];
-        float4 xa = x[a], ra = r[a];
-        xa.x += alpha * pa.x; xa.y += alpha * pa.y; xa.z += alpha * pa.z;
+        const float4 ya = y[a];
+        float4 ra = ld_planes(r, n, a);
         ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
-        x[a] = xa; r[a] = ra;
+        st_planes(r, n, a, ra);
         const float4 za = sym6_mul(Pinv, n, a, ra);
-        z[a] = za;
+        st_planes(z, n, a, za);
         rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
         err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
     }
@@ -393,17 +540,23 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, const float4 *
     }
 }
 
-// p = z + beta p;  y = D p (start value of the next SpMV) with the diagonal's share of p.Ap;  scalar tail
-__global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float4 *__restrict__ z, float4 *__restrict__ p, float4 *__restrict__ y,
-                                                         const float *__restrict__ D, CgScalars *sc) {
+// x += alpha p;  p = z + beta p;  y = D p (start value of the next SpMV) with the diagonal's share of p.Ap;  scalar tail
+__global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float *__restrict__ z, float4 *__restrict__ p, float4 *__restrict__ y,
+                                                         float *__restrict__ x, const float *__restrict__ D, CgScalars *sc) {
     if (sc->status != ST_RUNNING) return;
     const int par = sc->iter & 1;
+    int verdict;
+    float pAp;
+    const float alpha = cg_alpha(sc, par, verdict, pAp);
     const float rz0 = (float)sc->rz[par], rz1 = (float)sc->rz[par ^ 1];
     const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
     float dot = 0.f, absdot = 0.f;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        const float4 za = z[a];
+        const float4 za = ld_planes(z, n, a);
         float4 pa = p[a];
+        float4 xa = ld_planes(x, n, a);
+        xa.x += alpha * pa.x; xa.y += alpha * pa.y; xa.z += alpha * pa.z;
+        st_planes(x, n, a, xa);
         pa.x = za.x + beta * pa.x; pa.y = za.y + beta * pa.y; pa.z = za.z + beta * pa.z;
         p[a] = pa;
         const float4 v = sym6_mul(D, n, a, pa);
@@ -439,29 +592,29 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float
     }
 }
 
-// setup helpers -------------------------------------------------------------------------------
-__global__ void k_load(unsigned n, const float *__restrict__ force, const float *__restrict__ dx, float4 *__restrict__ r, float4 *__restrict__ x,
+// setup: r = b, x = x0 (seed), p = x0 (SpMV input), y = D x0
+__global__ void k_load(unsigned n, const float *__restrict__ force, const float *__restrict__ dx, float *__restrict__ r, float *__restrict__ x,
                        float4 *__restrict__ p, float4 *__restrict__ y, const float *__restrict__ D) {
     const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const size_t i = a;
-    r[a] = make_float4(force[3 * i], force[3 * i + 1], force[3 * i + 2], 0.f);
+    st_planes(r, n, a, make_float4(force[3 * i], force[3 * i + 1], force[3 * i + 2], 0.f));
     const float4 x0 = make_float4(dx[3 * i], dx[3 * i + 1], dx[3 * i + 2], 0.f);
-    x[a] = x0;
+    st_planes(x, n, a, x0);
     p[a] = x0;                   // SpMV input
     y[a] = sym6_mul(D, n, a, x0); // y = D x0
 }
 // r = b - A x0; z = P r; p = z; y = D p; rz0, err0, diagonal share of the first p.Ap
-__global__ void k_residual_init(unsigned n, float4 *__restrict__ y, float4 *__restrict__ r, float4 *__restrict__ z, float4 *__restrict__ p,
+__global__ void k_residual_init(unsigned n, float4 *__restrict__ y, float *__restrict__ r, float *__restrict__ z, float4 *__restrict__ p,
                                 const float *__restrict__ Pinv, const float *__restrict__ D, CgScalars *sc) {
     float rz = 0.f, err = 0.f, dot = 0.f, absdot = 0.f;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        float4 ra = r[a];
+        float4 ra = ld_planes(r, n, a);
         const float4 ya = y[a];
         ra.x -= ya.x; ra.y -= ya.y; ra.z -= ya.z;
-        r[a] = ra;
+        st_planes(r, n, a, ra);
         const float4 za = sym6_mul(Pinv, n, a, ra);
-        z[a] = za;
+        st_planes(z, n, a, za);
         p[a] = za;
         const float4 v = sym6_mul(D, n, a, za);
         y[a] = v;
@@ -475,26 +628,37 @@ __global__ void k_residual_init(unsigned n, float4 *__restrict__ y, float4 *__re
     __syncthreads();
     block_accumulate2(dot, absdot, &sc->acc_pap[0], &sc->acc_abs[0]);
 }
-__global__ void k_store(unsigned n, const float4 *__restrict__ x, float *__restrict__ dx) {
+__global__ void k_store(unsigned n, const float *__restrict__ x, float *__restrict__ dx) {
     const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
-    const float4 v = x[a];
+    const float4 v = ld_planes(x, n, a);
     dx[3 * size_t(a)] = v.x; dx[3 * size_t(a) + 1] = v.y; dx[3 * size_t(a) + 2] = v.z;
 }
 
 static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
     const unsigned nnz = P.nnz_f + P.nnz_d;
     if (!nnz) return;
-    const unsigned grid = std::min(P.grid, div_up(nnz, PCG_BLOCK));
-    k_spmv<<<grid, PCG_BLOCK, 0, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+    static const bool legacy = getenv("PPF_B200_SPMV_LEGACY") != nullptr; // the register-only kernel, kept for A/B timing
+    if (legacy) {
+        const unsigned grid = std::min(P.grid, div_up(nnz, PCG_BLOCK));
+        k_spmv<<<grid, PCG_BLOCK, 0, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+        return;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(k_spmv_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_SMEM));
+        attr_set = true;
+    }
+    const unsigned grid = std::min(P.spmv_grid, div_up(nnz, SPMV_CHUNK));
+    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
 }
 
 static void issue_iteration(State &s) {
     const unsigned n = P.n;
     const unsigned gv = std::min(P.grid, div_up(n, PCG_BLOCK));
     launch_spmv(s, P.p.p, P.y.p, 1);
-    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.p.p, P.y.p, P.x.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p);
-    k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.z.p, P.p.p, P.y.p, P.D.p, P.sc.p);
+    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p);
+    k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p);
 }
 
 // PPF_B200_PCG_TUNE=1: time the kernels of the iteration in isolation on the first packed system
@@ -519,16 +683,19 @@ static void pcg_tune(State &s) {
     CgScalars h{};
     h.status = ST_RUNNING; h.tol = 0.f; h.max_iter = 1 << 30; h.err0 = 1.0; h.rz[0] = h.rz[1] = 1.0; h.acc_pap[0] = h.acc_pap[1] = 1e30;
     cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q);
-    const unsigned grid_save = P.grid;
-    for (unsigned g : {148u * 4, 148u * 8, 148u * 16, 148u * 32}) {
-        P.grid = g;
+    const unsigned grid_save = P.spmv_grid;
+    for (unsigned g : {148u * 2, 148u * 3, 148u * 4}) {
+        P.spmv_grid = g;
         char nm[64];
-        snprintf(nm, sizeof(nm), "spmv offdiag grid=%u", g);
+        snprintf(nm, sizeof(nm), "spmv staged grid=%u", g);
         time_it(nm, 40.0 * nnz + 24.0 * n, [&] { launch_spmv(s, P.p.p, P.y.p, 1); });
     }
-    P.grid = grid_save;
-    time_it("update (x,r,z,dots)", 136.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, P.p.p, P.y.p, P.x.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p); });
-    time_it("direction (p,y=Dp,dots)", 88.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, P.z.p, P.p.p, P.y.p, P.D.p, P.sc.p); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
+    P.spmv_grid = grid_save;
+    time_it("spmv register-only (legacy)", 40.0 * nnz + 24.0 * n, [&] {
+        k_spmv<<<std::min(P.grid, div_up((unsigned)nnz, PCG_BLOCK)), PCG_BLOCK, 0, q>>>((unsigned)nnz, P.row.p, P.col.p, P.val.p, P.cap, P.p.p, P.y.p, P.sc.p, 1);
+    });
+    time_it("update (r,z,dots)", 76.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p); });
+    time_it("direction (x,p,y=Dp,dots)", 108.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
     printf("[pcg-tune] n_row=%u n_off=%.0f (fixed %u + dyn %u); SpMV algorithmic bytes (40*n_off + 60*n_row) = %.1f MB\n", n, nnz, P.nnz_f, P.nnz_d,
            (40.0 * nnz + 60.0 * n + 4.0 * (n + 1)) * 1e-6);
     fflush(stdout);

@@ -281,9 +281,11 @@ void step_advance(State &s, PpfStepResult *out) {
         if (!prm.disable_contact) {
             logging.push("aabb update");
             t_ph.start();
-            bvh_refit(s, s.bvh_face, 0, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
-            bvh_refit(s, s.bvh_edge, 1, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
-            bvh_refit(s, s.bvh_vert, 2, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
+            static const bool swept_hull = getenv("PPF_B200_SWEPT_HULL") != nullptr; // A/B: the reference's swept-hull boxes
+            auto refit = swept_hull ? bvh_refit : bvh_refit_relative;
+            refit(s, s.bvh_face, 0, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
+            refit(s, s.bvh_edge, 1, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
+            refit(s, s.bvh_vert, 2, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
             s.tm.ms_aabb_update += t_ph.stop();
             logging.pop();
             logging.push("line search");

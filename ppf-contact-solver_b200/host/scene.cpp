@@ -128,6 +128,45 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         SceneSpec s = twist_scene(name, 0.5, 1.0, nn, 500.0, 2.0 / nn * 0.35, 1e4, 0.35, 1.0, 720.0, 0.2, 10.0, 0.01, 4000000u, "min", 120);
         return s;
     }
+    if (name == "five-twist") { // examples/five-twist.ipynb (.jitter() left out: SURVEY.md 8d asks for a fixed scene)
+        SceneSpec s;
+        s.name = name;
+        const double half_length = 2.6;
+        const unsigned nn = n ? n : 180;
+        for (int i = 0; i < 5; ++i) {
+            const double t = 2.0 * i / 5.0 * M_PI;
+            const double x = 0.0, y = std::cos(t), z = std::sin(t); // .at(0, x, y) of the notebook
+            ShellObject o;
+            gen_cylinder(0.55, -half_length, half_length, nn, o.vert, o.tri);
+            o.param = tri_defaults();
+            o.param["bend"] = 500.0 / 3.5;
+            o.param["contact-gap"] = n ? 5.2 / nn * 0.14 : 4e-3; // the notebook's 4e-3 at n=180 (0.14 edge lengths), scaled when n is overridden
+            o.param["young-mod"] = 1e4;
+            o.param["poiss-rat"] = 0.25;
+            o.param["density"] = 3.5;
+            o.displacement = Vec3d{x, y, z};
+            const double ang = 360.0, move_delta = 1.0, scale = 0.75, t_end = 25.0, t_wait = 5.0;
+            for (int side = 0; side < 2; ++side) {
+                const double sg = side == 0 ? -1.0 : 1.0; // left pin first
+                Pin p;
+                p.index = grab(o.vert, Vec3d{sg, 0, 0});
+                PinOp spin; spin.kind = PinOp::Spin; spin.axis = Vec3d{-sg, 0, 0}; spin.angular_velocity = ang; spin.t_start = 0; spin.t_end = t_wait;
+                PinOp mv; mv.kind = PinOp::MoveBy; mv.delta = Vec3d{-sg * move_delta, 0, 0}; mv.t_start = 0; mv.t_end = t_end;
+                PinOp scl; scl.kind = PinOp::Scale; scl.factor = scale; scl.t_start = 0; scl.t_end = t_wait; scl.center = Vec3d{-x + sg * half_length, -y, -z};
+                PinOp orbit; orbit.kind = PinOp::Spin; orbit.center = Vec3d{-x, -y, -z}; orbit.axis = Vec3d{-sg, 0, 0}; orbit.angular_velocity = 180.0;
+                orbit.t_start = t_wait; orbit.t_end = 15.0;
+                p.ops = {spin, mv, scl, orbit};
+                o.pins.push_back(p);
+            }
+            s.objects.push_back(o);
+        }
+        s.args.dt = 1.0 / 60.0;
+        s.args.frames = 480;
+        s.args.gravity = Vec3d{0, 0, 0};
+        s.args.friction_mode = "max";
+        s.args.csrmat_max_nnz = 40000000u;
+        return s;
+    }
     if (name == "hang") { // examples/hang.ipynb
         SceneSpec s;
         s.name = name;

@@ -28,6 +28,8 @@ def run(job):
     os.makedirs(out, exist_ok=True)
     os.environ["PPF_HOST_QUIET"] = "1"
     os.environ["PPF_B200_QUIET"] = "1"
+    for k, v in (job.get("env") or {}).items():
+        os.environ[k] = v
     if job.get("dump_linsys"):
         os.environ["PPF_DUMP_LINSYS"] = "0"
         os.environ["PPF_DUMP_DIR"] = out
