@@ -10,16 +10,16 @@ set -e
 H=./ppf-contact-solver_b200/bin/ppf_host
 REF=oracle/_ref/libsimbackend_cuda.so
 export PPF_HOST_QUIET=1
-gen() { # name n steps save_every states...
-  name=$1; n=$2; steps=$3; every=$4; shift 4
+gen() { # name scene n steps save_every states...
+  name=$1; scene=$2; n=$3; steps=$4; every=$5; shift 5
   O=gpurun_out/golden/$name
   rm -rf $O; mkdir -p $O
-  $H --lib $REF --scene fast-twist --n $n --steps $steps --save-every $every --out $O/traj > $O/traj.log 2>&1
+  $H --lib $REF --scene $scene --n $n --steps $steps --save-every $every --out $O/traj > $O/traj.log 2>&1
   cases=""
   for st in "$@"; do
     cp $O/traj/state_$st.bin $O/state_$st.bin
     mkdir -p $O/ref_$st
-    PPF_DUMP_LINSYS=0 PPF_DUMP_DIR=$O/ref_$st $H --lib $REF --scene fast-twist --n $n --steps 1 --load $O/state_$st.bin --out $O/ref_$st > $O/ref_$st.log 2>&1
+    PPF_DUMP_LINSYS=0 PPF_DUMP_DIR=$O/ref_$st $H --lib $REF --scene $scene --n $n --steps 1 --load $O/state_$st.bin --out $O/ref_$st > $O/ref_$st.log 2>&1
     python - "$O/ref_$st" <<'PY'
 import json, os, sys
 d = sys.argv[1]
@@ -33,8 +33,11 @@ PY
     cases="$cases{\"state\": \"state_$st.bin\", \"dir\": \"ref_$st\"},"
   done
   rm -rf $O/traj $O/*.log
-  echo "{\"scene\": \"fast-twist\", \"n\": $n, \"cases\": [${cases%,}]}" > $O/meta.json
+  echo "{\"scene\": \"$scene\", \"n\": $n, \"cases\": [${cases%,}]}" > $O/meta.json
 }
-gen fast_twist_n16 16 90 30 00030 00060 00090
-gen fast_twist_n24 24 80 40 00040 00080
+if [ "$1" != "five-only" ]; then
+gen fast_twist_n16 fast-twist 16 90 30 00030 00060 00090
+gen fast_twist_n24 fast-twist 24 80 40 00040 00080
+fi
+gen five_twist_n24 five-twist 24 100 50 00050 00100
 du -sh gpurun_out/golden/*
