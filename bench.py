@@ -17,9 +17,11 @@ examples/large-twist.ipynb, driven through the reference's C ABI by the C++ host
 by oracle/Makefile.ref) through the same host on the same scene.  The reference has no CPU physics
 path, so its "own implementation of the path" is that CUDA build on this B200.
 
-N > 1 (torchrun): the path does not shard yet, so every rank runs an independent replica of the
-scene on its own GPU ("replicas only", weak scaling); torch.distributed (NCCL) provides the barrier
-and the max-over-ranks time.
+N > 1 (torchrun): every rank holds the same scene and the rows of the PCG solve (>90 % of the step)
+are sharded over the GPUs inside the backend -- NCCL halo exchange of the search direction plus two
+2-double all-reduces per iteration, captured in the iteration graph (csrc/dist.hpp).  "scaling" is
+"strong": `value` = frames of the ONE scene / max-over-ranks device time.  --replicas instead runs N
+independent scenes (weak scaling).
 """
 import argparse
 import json
@@ -35,8 +37,8 @@ sys.path.insert(0, os.path.join(REPO, "ppf-contact-solver_b200"))
 RANK = int(os.environ.get("RANK", "0"))
 LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
 WORLD = int(os.environ.get("WORLD_SIZE", "1"))
-if WORLD > 1:  # one process per GPU: each rank sees exactly its own device as cuda:0
-    os.environ["CUDA_VISIBLE_DEVICES"] = str(LOCAL_RANK)
+if WORLD > 1:  # one process per GPU; all GPUs stay visible so that NCCL / peer mappings can use NVLink
+    os.environ["PPF_B200_DEVICE"] = str(LOCAL_RANK)
 
 
 class ClockSampler(threading.Thread):
@@ -52,7 +54,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        idx = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
+        idx = os.environ.get("PPF_B200_DEVICE", os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", idx, "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -129,6 +131,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="large-twist")
     ap.add_argument("--n", type=int, default=0, help="resolution override (0 = the config's own: n=1410 for large-twist)")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent scenes (weak scaling) instead of sharding ONE scene's PCG rows over the GPUs")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--full-v", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -153,7 +156,24 @@ def main():
 
     import replicas
 
-    ranks = replicas.Ranks("nccl") if args.impl == "ours" else None
+    # N > 1: ONE scene, the rows of its PCG solve sharded over the GPUs with NCCL inside the backend
+    # (csrc/dist.hpp; strong scaling).  torch.distributed (gloo) only carries the NCCL id, the barrier
+    # around the timed region and the max-over-ranks of the timings.  --replicas: N independent scenes.
+    shard = None
+    ranks = None
+    if args.impl == "ours":
+        sharded = WORLD > 1 and not args.replicas
+        ranks = replicas.Ranks("gloo" if sharded else "nccl")
+        if sharded:
+            ident = [ppf_b200.nccl_unique_id() if RANK == 0 else None]
+            ranks.dist.broadcast_object_list(ident, src=0)
+
+            def allgather(b):
+                out = [None] * WORLD
+                ranks.dist.all_gather_object(out, b)
+                return out
+
+            shard = (RANK, WORLD, ident[0], allgather)
 
     os.environ.setdefault("PPF_HOST_QUIET", "1")
     os.environ.setdefault("PPF_B200_QUIET", "1")
@@ -161,7 +181,7 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(devnull, 1)  # the backends narrate on stdout; keep ours for the JSON line
     try:
-        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK)
+        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK, shard=shard)
         fps = 60.0
         for _ in range(W):
             ok, _ms = s.step()
@@ -208,6 +228,8 @@ def main():
     t_dev, t_e2e, tot_frames = dev_s, wall_e2e, frames
     if ranks is not None:
         t_dev, t_e2e, tot_frames = ranks.reduce(dev_s, wall_e2e, frames)
+        if shard is not None:
+            tot_frames = frames  # every rank advanced the SAME scene
         ranks.close()
     if RANK != 0:
         return
@@ -221,13 +243,14 @@ def main():
         "warmup": W,
         "ms_per_step": 1e3 * t_dev / K,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if shard is not None else "weak",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "%s: cylinder n=%s, V=%d F=%d E=%d hinges=%d, dt=1/60, steps from t=0; %s" % (
             args.scene, args.n or "config default", s.n_vert, s.n_face, s.n_edge, s.n_hinge,
-            "replicas only (one independent scene per GPU)" if WORLD > 1 else "single GPU"),
+            ("one scene, PCG rows sharded over %d GPUs (NCCL halo exchange + 2 all-reduces per iteration)" % WORLD) if shard is not None
+            else ("replicas (one independent scene per GPU)" if WORLD > 1 else "single GPU")),
             "l2": "inputs larger than L2 (packed matrix %.0f MB per SpMV)" % ((40.0 * (st1["spmv_n_off"] if st1 else 0) + 60.0 * s.n_vert) * 1e-6)},
         "e2e": {"value": tot_frames / t_e2e, "unit": "frames/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,

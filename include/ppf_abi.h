@@ -288,6 +288,17 @@ unsigned ppf_b200_fetch_pairs(unsigned kind, unsigned *out, unsigned cap);
  * 0xFFFFFFFF when n_vert does not match the initialized scene.  Clobbers the backend's evaluation
  * positions: call it between steps only. */
 unsigned ppf_b200_detect_pairs(const float *x, unsigned n_vert);
+/* Multi-GPU (one process per GPU, csrc/dist.hpp): rank 0 creates a 128-byte NCCL id, the launcher
+ * distributes it, every rank calls ppf_b200_dist_init after initialize() and before the first
+ * advance().  All ranks must hold the same scene; the PCG rows are then sharded over the ranks.
+ * Return 0 on success (unique_id: the id length). */
+int ppf_b200_dist_unique_id(unsigned char *out, unsigned cap);
+int ppf_b200_dist_init(int rank, int world, const unsigned char *id_bytes, unsigned len);
+/* Optional peer-memory fast path: every rank exports 128 bytes of CUDA IPC handles, the launcher
+ * all-gathers them in rank order and hands the concatenation to every rank.  connect returns 1 when the
+ * per-iteration collectives now run over NVLink peer memory, 0/negative when NCCL stays in use. */
+int ppf_b200_dist_export(unsigned char *out, unsigned cap);
+int ppf_b200_dist_connect(const unsigned char *all, unsigned len);
 /* Average microseconds of the SpMV kernel alone on the last packed system (CUDA events, `reps` launches). */
 double ppf_b200_measure_spmv(unsigned reps, unsigned long long *n_row, unsigned long long *n_off);
 

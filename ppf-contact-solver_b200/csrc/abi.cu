@@ -271,6 +271,13 @@ PPF_EXPORT bool initialize(PpfDataSet *dataset, PpfParamSet *param) {
               e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     cudaDeviceProp props;
     int dev = 0;
+    // One process per GPU: the launcher picks the device with PPF_B200_DEVICE (all GPUs stay visible so that
+    // NCCL / peer mappings between the ranks can use NVLink); unset = the reference's behaviour (device 0).
+    if (const char *dv = getenv("PPF_B200_DEVICE")) {
+        const int want = atoi(dv);
+        if (want < 0 || want >= num_device) fatal(PPF_FATAL_CUDA_DRIVER, "PPF_B200_DEVICE=%d but %d devices are visible", want, num_device);
+        CUDA_OK(cudaSetDevice(want));
+    }
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaGetDeviceProperties(&props, dev));
     log_info("cuda: device %d is %s, compute capability %d.%d, %d SMs", dev, props.name, props.major, props.minor, props.multiProcessorCount);

@@ -1,0 +1,50 @@
+// dist.hpp -- multi-GPU plumbing of the backend: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// The reference is single-GPU; this is new.  Only the PCG solve is sharded (it is >90 %
+// of the headline step): every rank keeps the full scene and runs the cheap phases redundantly --
+// their only inputs are the positions, which stay bitwise identical on all ranks because the solved
+// step dx is all-gathered -- while the rows of the linear system are split into contiguous ranges
+// (pcg.cu).  Exchanges per PCG iteration: the rows of the search direction p that other ranks read
+// (known from the block pattern) and two 2-double sums (p.Ap | sum|terms|,  r.z | |r|_1).  All of them
+// run on the backend stream inside the iteration CUDA graph.
+//
+// libnccl is dlopen'ed on first use, so the single-GPU drop-in has no NCCL dependency.
+#pragma once
+#include <cstddef>
+#include <cuda_runtime.h>
+
+namespace ppf {
+
+struct Dist {
+    int rank = 0, world = 1;
+    bool on() const { return world > 1; }
+};
+extern Dist g_dist;
+
+// ---- peer-memory path (NVLink loads/stores between the ranks' own kernels) ----------------------------
+// NCCL costs ~60 us per small collective inside the iteration graph, three of them per PCG iteration --
+// more than the sharded compute.  Once the ranks have exchanged CUDA IPC handles of (a) a small mailbox
+// buffer and (b) their search-direction array p, the per-iteration exchanges are done by the PCG kernels
+// themselves: partial sums are stored straight into every peer's mailbox and summed in rank order by each
+// rank (bitwise identical results everywhere); the kernel that writes p also stores the rows other ranks
+// read into their p arrays and the last CTA raises / awaits epoch flags.  NCCL remains for the
+// once-per-solve operations and as the fallback (PPF_B200_DIST_NCCL=1 or no peer mapping: all-gather of p).
+constexpr int PPF_MAX_RANKS = 8;
+struct Mail { double v[2]; unsigned long long epoch; unsigned long long pad; };
+struct CommBuf {
+    Mail mail[2][2][PPF_MAX_RANKS];      // [slot: 0 p.Ap|abs, 1 r.z|err][parity][source rank]
+    unsigned long long halo_flag[PPF_MAX_RANKS]; // [q]: epoch of the last push of p rows received from rank q
+    unsigned long long red_epoch[2];     // local counters (never reset, identical on all ranks by construction)
+    unsigned long long halo_epoch;
+};
+struct PeerView {
+    CommBuf *comm[PPF_MAX_RANKS];        // comm[r]: rank r's mailbox buffer mapped into this process (own buffer at [rank])
+    float4 *p[PPF_MAX_RANKS];            // p[r]:   rank r's search-direction array
+    int rank, world, enabled;
+};
+const PeerView &dist_peers();
+
+void dist_allreduce_sum_f64(double *buf, size_t count, cudaStream_t q);                          // in place
+void dist_allgather(const void *send, void *recv, size_t bytes_per_rank, cudaStream_t q);        // recv = world * bytes_per_rank
+
+} // namespace ppf

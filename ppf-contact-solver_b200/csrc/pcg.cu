@@ -23,6 +23,7 @@
 //    truncate-on-noise returns success, negative curvature / r.z <= 0 are fatal, block-Jacobi
 //    inverse through a floored symmetric eigendecomposition (solver.cu:357-400).
 #include "backend.hpp"
+#include "dist.hpp"
 #include <algorithm>
 #include <cmath>
 
@@ -35,8 +36,8 @@ static constexpr float CG_FLOAT_EPS = 1.19209290e-7f;
 enum { ST_RUNNING = 0, ST_CONVERGED = 1, ST_TRUNCATED = 2, ST_CAP = 3, ST_FATAL_PAP = 4, ST_FATAL_RZ = 5, ST_NONFINITE = 6 };
 
 struct CgScalars {                 // device-resident control block
-    double acc_pap[2], acc_abs[2]; // per-parity accumulators of p.Ap and sum|terms|
-    double rz[2], err[2];          // r.z and |r|_1, double-buffered by iteration parity
+    double acc[2][2];              // [parity][0: p.Ap, 1: sum|terms|]   (pairs are contiguous: one 2-double all-reduce)
+    double rzerr[2][2];            // [parity][0: r.z,  1: |r|_1]
     double err0;
     int iter;                      // completed iterations
     int status;                    // ST_*
@@ -63,12 +64,19 @@ struct PackedMatrix {
     cudaGraphExec_t exec = nullptr;
     unsigned graph_nnz = ~0u;
     const void *graph_val = nullptr;
+    unsigned long long graph_part = 0;
     int *h_status = nullptr;         // pinned mirror of {iter, status, last_resid}
     unsigned grid = 0;               // persistent grid size of the vector kernels
     unsigned spmv_grid = 0;          // persistent grid of the staged SpMV (SMs x resident CTAs)
+    unsigned rpr = 0;                // rows per rank (dist.hpp)
+    unsigned n_foreign_fixed = 0;    // foreign blocks of the fixed segment (see Part)
+    DBuf<unsigned> foreign;          // list positions of this rank's foreign blocks: fixed ones first, then this solve's dynamic ones
+    DBuf<unsigned> mask_fixed, mask; // per row: bit q set = rank q reads p[row] (fixed part / this solve)
+    size_t n_pad = 0;                // rpr * world
     bool ready = false;
 };
 static PackedMatrix P;
+static std::vector<unsigned> g_fx_rowptr; // packed fixed blocks with row < i (host, n+1 entries)
 
 // The SpMV stages whole chunks of the block list through shared memory with bulk copies, so every
 // plane is padded to a whole number of chunks (and the plane stride keeps 16-byte alignment).
@@ -98,6 +106,32 @@ static void pcg_init(State &s) {
         }
     P.nnz_f = (unsigned)row.size();
     cudaStream_t q = s.stream;
+    // partition of the rows over the ranks (dist.hpp): equal contiguous ranges, padded to a multiple of 4
+    const unsigned world = (unsigned)std::max(1, g_dist.world);
+    P.rpr = ((n + world - 1) / world + 3u) & ~3u;
+    P.n_pad = size_t(P.rpr) * world;
+    g_fx_rowptr.assign(n + 1, 0);
+    for (size_t k = 0; k < row.size(); ++k) {
+        ++g_fx_rowptr[row[k] + 1];
+    }
+    for (unsigned i = 0; i < n; ++i) g_fx_rowptr[i + 1] += g_fx_rowptr[i];
+    if (world > 1) { // static part of the exchange pattern (see Part): foreign blocks of this rank and the push masks
+        const unsigned me = (unsigned)g_dist.rank;
+        std::vector<unsigned> foreign, mask(n, 0u);
+        for (size_t k = 0; k < row.size(); ++k) {
+            const unsigned ri = row[k] / P.rpr, rj = col[k] / P.rpr;
+            if (ri == rj) continue;
+            mask[row[k]] |= 1u << rj;
+            mask[col[k]] |= 1u << ri;
+            if (rj == me) foreign.push_back((unsigned)k);
+        }
+        P.n_foreign_fixed = (unsigned)foreign.size();
+        P.foreign.reserve(foreign.size() + 1024);
+        if (!foreign.empty()) CUDA_OK(cudaMemcpyAsync(P.foreign.p, foreign.data(), sizeof(unsigned) * foreign.size(), cudaMemcpyHostToDevice, q));
+        P.mask_fixed.upload(mask.data(), n, q);
+        P.mask.reserve(n);
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
     P.cap = round_cap(size_t(P.nnz_f) + 1024);
     P.row.reserve(P.cap); P.col.reserve(P.cap); P.val.reserve(size_t(9) * P.cap);
     CUDA_OK(cudaMemcpyAsync(P.row.p, row.data(), sizeof(unsigned) * row.size(), cudaMemcpyHostToDevice, q));
@@ -105,7 +139,8 @@ static void pcg_init(State &s) {
     P.fx_pos.upload(pos.data(), nnz, q);
     CUDA_OK(cudaStreamSynchronize(q));
     P.D.reserve(size_t(6) * n); P.Pinv.reserve(size_t(6) * n);
-    P.x.reserve(size_t(3) * n); P.r.reserve(size_t(3) * n); P.z.reserve(size_t(3) * n); P.p.reserve(n); P.y.reserve(n);
+    P.x.reserve(size_t(3) * n); P.r.reserve(size_t(3) * n); P.z.reserve(size_t(3) * n); P.p.reserve(P.n_pad); P.y.reserve(P.n_pad);
+    if (world > 1) s.dx.reserve_keep(size_t(3) * P.n_pad, q); // the solved step is all-gathered in place, in equal slices
     P.sc.reserve(1);
     CUDA_OK(cudaMallocHost(&P.h_status, 64));
     int dev = 0, sms = 148;
@@ -361,11 +396,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_spmv(unsigned nnz, const unsigned
     }
     if (!with_dots) return;
     const int par = sc->iter & 1;
-    block_accumulate2(dot, absdot, &sc->acc_pap[par], &sc->acc_abs[par]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { // slots the NEXT update kernel accumulates into
-        sc->rz[par ^ 1] = 0.0;
-        sc->err[par ^ 1] = 0.0;
-    }
+    block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
 }
 
 // ---- the same product with the block list staged through shared memory by bulk async copies ----
@@ -395,7 +426,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 
-__global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const unsigned *__restrict__ row, const unsigned *__restrict__ col,
+// Blocks [k_first, nnz) of the list are processed (staging starts at k_begin <= k_first, a multiple of SPMV_CHUNK); results are
+// accumulated only into rows [row_lo, row_hi) -- the rows this rank owns (everything on one GPU).  A
+// block's share of p.Ap is counted by the owner of its row.
+__global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned k_begin, unsigned k_first, unsigned nnz, unsigned row_lo, unsigned row_hi,
+                                                          const unsigned *__restrict__ row, const unsigned *__restrict__ col,
                                                           const float *__restrict__ val, size_t plane, const float4 *__restrict__ p,
                                                           float4 *__restrict__ y, CgScalars *sc, int with_dots) {
     if (with_dots && sc->status != ST_RUNNING) return;
@@ -403,6 +438,7 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const u
     unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + size_t(SPMV_STAGES) * SPMV_STAGE_BYTES);
     const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned c_begin = k_begin / SPMV_CHUNK;
     const unsigned n_chunks = (nnz + SPMV_CHUNK - 1) / SPMV_CHUNK;
     if (tid == 0) {
         for (int st = 0; st < SPMV_STAGES; ++st) mbar_init(&full[st], 1);
@@ -420,12 +456,12 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const u
     };
     if (tid == 0)
         for (int st = 0; st < SPMV_STAGES; ++st) {
-            const unsigned c = blockIdx.x + unsigned(st) * gridDim.x;
+            const unsigned c = c_begin + blockIdx.x + unsigned(st) * gridDim.x;
             if (c < n_chunks) fill(st, c);
         }
     float dot = 0.f, absdot = 0.f;
     unsigned it = 0;
-    for (unsigned chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    for (unsigned chunk = c_begin + blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
         const int st = int(it % SPMV_STAGES);
         mbar_wait(&full[st], (it / SPMV_STAGES) & 1u);
         const unsigned *sm = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
@@ -449,7 +485,7 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const u
         float4 pa[SPMV_U], pb[SPMV_U];
 #pragma unroll
         for (int u = 0; u < SPMV_U; ++u) {
-            on[u] = k0 + u * SPMV_T + tid < nnz;
+            on[u] = k0 + u * SPMV_T + tid < nnz && k0 + u * SPMV_T + tid >= k_first;
             if (!on[u]) { a[u] = 0xFFFFFFFFu; b[u] = 0; }
             pa[u] = on[u] ? p[a[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
             pb[u] = on[u] ? p[b[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -458,15 +494,19 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const u
         for (int u = 0; u < SPMV_U; ++u) {
             const float *hh = h[u];
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            const bool own_a = on[u] && a[u] >= row_lo && a[u] < row_hi;
             if (on[u]) {
-                s0 = hh[0] * pb[u].x + hh[3] * pb[u].y + hh[6] * pb[u].z;
-                s1 = hh[1] * pb[u].x + hh[4] * pb[u].y + hh[7] * pb[u].z;
-                s2 = hh[2] * pb[u].x + hh[5] * pb[u].y + hh[8] * pb[u].z;
-                red_add_v4(y + b[u], hh[0] * pa[u].x + hh[1] * pa[u].y + hh[2] * pa[u].z, hh[3] * pa[u].x + hh[4] * pa[u].y + hh[5] * pa[u].z,
-                           hh[6] * pa[u].x + hh[7] * pa[u].y + hh[8] * pa[u].z);
-                const float term = 2.0f * (pa[u].x * s0 + pa[u].y * s1 + pa[u].z * s2);
-                dot += term;
-                absdot += fabsf(term);
+                if (b[u] >= row_lo && b[u] < row_hi)
+                    red_add_v4(y + b[u], hh[0] * pa[u].x + hh[1] * pa[u].y + hh[2] * pa[u].z, hh[3] * pa[u].x + hh[4] * pa[u].y + hh[5] * pa[u].z,
+                               hh[6] * pa[u].x + hh[7] * pa[u].y + hh[8] * pa[u].z);
+                if (own_a) {
+                    s0 = hh[0] * pb[u].x + hh[3] * pb[u].y + hh[6] * pb[u].z;
+                    s1 = hh[1] * pb[u].x + hh[4] * pb[u].y + hh[7] * pb[u].z;
+                    s2 = hh[2] * pb[u].x + hh[5] * pb[u].y + hh[8] * pb[u].z;
+                    const float term = 2.0f * (pa[u].x * s0 + pa[u].y * s1 + pa[u].z * s2);
+                    dot += term;
+                    absdot += fabsf(term);
+                }
             }
             const unsigned ra_self = a[u];
 #pragma unroll
@@ -476,16 +516,12 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned nnz, const u
                 if (lane >= (unsigned)o && ra == ra_self) { s0 += t0; s1 += t1; s2 += t2; }
             }
             const unsigned next = __shfl_down_sync(0xffffffffu, ra_self, 1);
-            if (on[u] && (lane == 31 || next != ra_self)) red_add_v4(y + ra_self, s0, s1, s2);
+            if (own_a && (lane == 31 || next != ra_self)) red_add_v4(y + ra_self, s0, s1, s2);
         }
     }
     if (!with_dots) return;
     const int par = sc->iter & 1;
-    block_accumulate2(dot, absdot, &sc->acc_pap[par], &sc->acc_abs[par]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->rz[par ^ 1] = 0.0;
-        sc->err[par ^ 1] = 0.0;
-    }
+    block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
 }
 
 __device__ __forceinline__ float4 sym6_mul(const float *__restrict__ M, size_t n, size_t i, const float4 v) {
@@ -503,9 +539,9 @@ __device__ __forceinline__ void st_planes(float *__restrict__ v, size_t n, size_
 // step length of the current iteration from the device-resident scalars (reference: cg_fused_update_kernel,
 // solver.cu:431-514, and its curvature-noise verdict 66-114).  verdict: 0 ok, 1 truncate, 2 fatal
 __device__ __forceinline__ float cg_alpha(const CgScalars *sc, int par, int &verdict, float &pAp_out) {
-    const float pAp = (float)sc->acc_pap[par];
-    const float noise = CG_NOISE_SLACK * CG_FLOAT_EPS * (float)sc->acc_abs[par];
-    const float rz0 = (float)sc->rz[par];
+    const float pAp = (float)sc->acc[par][0];
+    const float noise = CG_NOISE_SLACK * CG_FLOAT_EPS * (float)sc->acc[par][1];
+    const float rz0 = (float)sc->rzerr[par][0];
     pAp_out = pAp;
     verdict = 0;
     if (pAp > noise) return rz0 / pAp;
@@ -514,15 +550,15 @@ __device__ __forceinline__ float cg_alpha(const CgScalars *sc, int par, int &ver
 }
 
 // r -= alpha A p;  z = Pinv r;  r.z and |r|_1.   (x += alpha p is applied by k_direction, which reads p anyway)
-__global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, const float4 *__restrict__ y, float *__restrict__ r, float *__restrict__ z,
-                                                      const float *__restrict__ Pinv, CgScalars *sc) {
+__global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, unsigned hi, const float4 *__restrict__ y, float *__restrict__ r,
+                                                      float *__restrict__ z, const float *__restrict__ Pinv, CgScalars *sc) {
     if (sc->status != ST_RUNNING) return;
     const int par = sc->iter & 1;
     int verdict;
     float pAp;
     const float alpha = cg_alpha(sc, par, verdict, pAp);
     float rz = 0.f, err = 0.f;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += gridDim.x * blockDim.x) {
         const float4 ya = y[a];
         float4 ra = ld_planes(r, n, a);
         ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
@@ -532,26 +568,30 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, const float4 *
         rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
         err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
     }
-    block_accumulate2(rz, err, &sc->rz[par ^ 1], &sc->err[par ^ 1]);
+    block_accumulate2(rz, err, &sc->rzerr[par ^ 1][0], &sc->rzerr[par ^ 1][1]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (verdict) { sc->breakdown = verdict; sc->break_val = pAp; }
-        sc->acc_pap[par ^ 1] = 0.0; // accumulators of the NEXT iteration (direction kernel + SpMV)
-        sc->acc_abs[par ^ 1] = 0.0;
+        sc->acc[par ^ 1][0] = 0.0; // accumulators of the NEXT iteration (direction kernel + SpMV)
+        sc->acc[par ^ 1][1] = 0.0;
     }
 }
 
 // x += alpha p;  p = z + beta p;  y = D p (start value of the next SpMV) with the diagonal's share of p.Ap;  scalar tail
-__global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float *__restrict__ z, float4 *__restrict__ p, float4 *__restrict__ y,
-                                                         float *__restrict__ x, const float *__restrict__ D, CgScalars *sc) {
+// With peer memory (dist.hpp) a row that other ranks read (push_mask) is also stored straight into their p
+// arrays over NVLink, and the last CTA raises every peer's epoch flag and waits for theirs, so the next SpMV
+// finds its remote rows in place: the exchange costs no extra launch.
+__global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo, unsigned hi, const float *__restrict__ z, float4 *__restrict__ p,
+                                                         float4 *__restrict__ y, float *__restrict__ x, const float *__restrict__ D, CgScalars *sc,
+                                                         PeerView pv, const unsigned *__restrict__ push_mask) {
     if (sc->status != ST_RUNNING) return;
     const int par = sc->iter & 1;
     int verdict;
     float pAp;
     const float alpha = cg_alpha(sc, par, verdict, pAp);
-    const float rz0 = (float)sc->rz[par], rz1 = (float)sc->rz[par ^ 1];
+    const float rz0 = (float)sc->rzerr[par][0], rz1 = (float)sc->rzerr[par ^ 1][0];
     const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
     float dot = 0.f, absdot = 0.f;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += gridDim.x * blockDim.x) {
         const float4 za = ld_planes(z, n, a);
         float4 pa = p[a];
         float4 xa = ld_planes(x, n, a);
@@ -559,15 +599,24 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float
         st_planes(x, n, a, xa);
         pa.x = za.x + beta * pa.x; pa.y = za.y + beta * pa.y; pa.z = za.z + beta * pa.z;
         p[a] = pa;
+        if (push_mask) { // ranks that own a block partner of row a read p[a]: store it into their arrays over NVLink
+            unsigned m = push_mask[a];
+            while (m) {
+                const int q = __ffs(m) - 1;
+                m &= m - 1;
+                pv.p[q][a] = pa;
+            }
+        }
         const float4 v = sym6_mul(D, n, a, pa);
         y[a] = v;
         const float term = pa.x * v.x + pa.y * v.y + pa.z * v.z;
         dot += term;
         absdot += fabsf(term);
     }
-    block_accumulate2(dot, absdot, &sc->acc_pap[par ^ 1], &sc->acc_abs[par ^ 1]);
+    block_accumulate2(dot, absdot, &sc->acc[par ^ 1][0], &sc->acc[par ^ 1][1]);
     // the LAST block to finish runs the scalar tail, after every block has read this iteration's scalars
     __shared__ bool last;
+    if (push_mask) __threadfence_system(); // peer stores of this thread are ordered before the flags raised below
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -577,7 +626,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float
     if (last && threadIdx.x == 0) {
         sc->done_counter = 0;
         const int it = sc->iter + 1;
-        const double reresid = sc->err[par ^ 1] / sc->err0;
+        const double reresid = sc->rzerr[par ^ 1][1] / sc->err0;
         sc->last_resid = (float)reresid;
         int st = ST_RUNNING;
         if (reresid < (double)sc->tol) st = ST_CONVERGED;
@@ -586,10 +635,54 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, const float
         else if (!(rz0 > 0.0f)) st = ST_FATAL_RZ;
         else if (!isfinite(reresid)) st = ST_NONFINITE;
         else if (it >= sc->max_iter) st = ST_CAP;
+        sc->rzerr[par][0] = 0.0; // slots the NEXT iteration's update kernel accumulates into
+        sc->rzerr[par][1] = 0.0;
+        if (push_mask && st == ST_RUNNING) { // every rank reaches the same verdict, so either all exchange or none does
+            CommBuf *mine = pv.comm[pv.rank];
+            const unsigned long long e = ++mine->halo_epoch;
+            __threadfence_system();
+            for (int q = 0; q < pv.world; ++q)
+                if (q != pv.rank) *(volatile unsigned long long *)&pv.comm[q]->halo_flag[pv.rank] = e;
+            for (int q = 0; q < pv.world; ++q)
+                if (q != pv.rank) while (*(volatile unsigned long long *)&mine->halo_flag[q] < e) {}
+            __threadfence_system();
+        }
         sc->iter = it;
         __threadfence();
         sc->status = st;
     }
+}
+
+// Sum of a 2-double partial over the ranks through peer mailboxes (dist.hpp): every rank stores its partial
+// into every rank's mailbox, waits for all of them, and adds them in rank order -- the same bits everywhere.
+__global__ void k_allreduce2(PeerView pv, CgScalars *sc, int slot, int parity) {
+    if (sc->status != ST_RUNNING) return; // the verdict is identical on all ranks
+    double *loc = slot == 0 ? sc->acc[parity] : sc->rzerr[parity];
+    CommBuf *mine = pv.comm[pv.rank];
+    const int lane = threadIdx.x;
+    unsigned long long e = 0;
+    if (lane == 0) e = ++mine->red_epoch[slot];
+    e = __shfl_sync(0xffffffffu, e, 0);
+    const double v0 = loc[0], v1 = loc[1];
+    double a = 0.0, b = 0.0;
+    if (lane < pv.world) {
+        Mail *m = &pv.comm[lane]->mail[slot][parity][pv.rank];
+        ((volatile double *)m->v)[0] = v0;
+        ((volatile double *)m->v)[1] = v1;
+        __threadfence_system();
+        *(volatile unsigned long long *)&m->epoch = e;
+        const Mail *in = &mine->mail[slot][parity][lane];
+        while (*(volatile const unsigned long long *)&in->epoch < e) {}
+        __threadfence_system();
+        a = ((volatile const double *)in->v)[0];
+        b = ((volatile const double *)in->v)[1];
+    }
+    double sa = 0.0, sb = 0.0;
+    for (int r = 0; r < pv.world; ++r) {
+        sa += __shfl_sync(0xffffffffu, a, r);
+        sb += __shfl_sync(0xffffffffu, b, r);
+    }
+    if (lane == 0) { loc[0] = sa; loc[1] = sb; }
 }
 
 // setup: r = b, x = x0 (seed), p = x0 (SpMV input), y = D x0
@@ -605,10 +698,10 @@ __global__ void k_load(unsigned n, const float *__restrict__ force, const float 
     y[a] = sym6_mul(D, n, a, x0); // y = D x0
 }
 // r = b - A x0; z = P r; p = z; y = D p; rz0, err0, diagonal share of the first p.Ap
-__global__ void k_residual_init(unsigned n, float4 *__restrict__ y, float *__restrict__ r, float *__restrict__ z, float4 *__restrict__ p,
-                                const float *__restrict__ Pinv, const float *__restrict__ D, CgScalars *sc) {
+__global__ void k_residual_init(unsigned n, unsigned lo, unsigned hi, float4 *__restrict__ y, float *__restrict__ r, float *__restrict__ z,
+                                float4 *__restrict__ p, const float *__restrict__ Pinv, const float *__restrict__ D, CgScalars *sc) {
     float rz = 0.f, err = 0.f, dot = 0.f, absdot = 0.f;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
+    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += gridDim.x * blockDim.x) {
         float4 ra = ld_planes(r, n, a);
         const float4 ya = y[a];
         ra.x -= ya.x; ra.y -= ya.y; ra.z -= ya.z;
@@ -624,41 +717,154 @@ __global__ void k_residual_init(unsigned n, float4 *__restrict__ y, float *__res
         dot += term;
         absdot += fabsf(term);
     }
-    block_accumulate2(rz, err, &sc->rz[0], &sc->err0);
+    block_accumulate2(rz, err, &sc->rzerr[0][0], &sc->rzerr[0][1]);
     __syncthreads();
-    block_accumulate2(dot, absdot, &sc->acc_pap[0], &sc->acc_abs[0]);
+    block_accumulate2(dot, absdot, &sc->acc[0][0], &sc->acc[0][1]);
 }
-__global__ void k_store(unsigned n, const float *__restrict__ x, float *__restrict__ dx) {
-    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
+__global__ void k_set_err0(CgScalars *sc) { sc->err0 = sc->rzerr[0][1]; }
+__global__ void k_store(unsigned n, unsigned lo, unsigned hi, const float *__restrict__ x, float *__restrict__ dx) {
+    const unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= hi) return;
     const float4 v = ld_planes(x, n, a);
     dx[3 * size_t(a)] = v.x; dx[3 * size_t(a) + 1] = v.y; dx[3 * size_t(a) + 2] = v.z;
 }
 
-static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
-    const unsigned nnz = P.nnz_f + P.nnz_d;
-    if (!nnz) return;
-    static const bool legacy = getenv("PPF_B200_SPMV_LEGACY") != nullptr; // the register-only kernel, kept for A/B timing
-    if (legacy) {
-        const unsigned grid = std::min(P.grid, div_up(nnz, PCG_BLOCK));
-        k_spmv<<<grid, PCG_BLOCK, 0, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+// ---- this rank's share of the system (everything when there is one rank; see dist.hpp) ----
+// A rank processes (1) the blocks of its own rows -- contiguous in the row-sorted list, streamed by the staged
+// kernel, which adds B p_col to the owned row and B^T p_row to the column if that is owned too -- and (2) the
+// "foreign" blocks: stored under somebody else's row but with an owned column (index list, gathered), which
+// only contribute B^T p_row.  Which rows of p a rank must send where follows from the same pattern: row a
+// carries a bit mask of the ranks that own a block partner of a.  Nothing assumes a mesh numbering: the
+// seam of a closed surface or a contact between distant rows simply sets more bits.
+struct Part {
+    unsigned lo = 0, hi = 0;            // owned rows
+    unsigned rpr = 0;                   // rows per rank (padded to a multiple of 4)
+    unsigned kf_first = 0, kf_end = 0;  // own-row blocks of the fixed segment of the list
+    unsigned kd_first = 0, kd_end = 0;  // own-row blocks of the dynamic segment (absolute list positions)
+    unsigned n_foreign = 0;             // entries of P.foreign
+    bool push = false;                  // rows are pushed to peers by k_direction (peer memory) -- else p is all-gathered
+};
+static Part R;
+
+// dynamic blocks that cross a partition boundary: set the push bits of both rows, list the block when its column is mine
+__global__ void k_dyn_cross(unsigned n, unsigned rpr, unsigned me, const unsigned *__restrict__ off, const unsigned *__restrict__ col, unsigned base,
+                            unsigned *__restrict__ mask, unsigned *__restrict__ foreign, unsigned *counter, unsigned cap) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned ri = i / rpr;
+    for (unsigned k = off[i]; k < off[i + 1]; ++k) {
+        const unsigned j = col[k], rj = j / rpr;
+        if (rj == ri) continue;
+        atomicOr(mask + i, 1u << rj);
+        atomicOr(mask + j, 1u << ri);
+        if (rj == me) {
+            const unsigned slot = atomicAdd(counter, 1u);
+            if (slot < cap) foreign[slot] = base + k;
+        }
+    }
+}
+
+static void pcg_partition(State &s) {
+    const unsigned n = P.n, nnz = P.nnz_f + P.nnz_d;
+    if (!g_dist.on()) {
+        R = Part{};
+        R.lo = 0; R.hi = n; R.rpr = n;
+        R.kf_first = 0; R.kf_end = nnz; // one launch over the whole list
         return;
     }
+    cudaStream_t q = s.stream;
+    const unsigned rank = (unsigned)g_dist.rank;
+    R.rpr = P.rpr;
+    R.lo = std::min(n, rank * R.rpr);
+    R.hi = std::min(n, R.lo + R.rpr);
+    R.kf_first = g_fx_rowptr[R.lo];
+    R.kf_end = g_fx_rowptr[R.hi];
+    R.kd_first = R.kd_end = P.nnz_f;
+    R.n_foreign = P.n_foreign_fixed;
+    R.push = dist_peers().enabled != 0;
+    CUDA_OK(cudaMemcpyAsync(P.mask.p, P.mask_fixed.p, sizeof(unsigned) * n, cudaMemcpyDeviceToDevice, q));
+    if (P.nnz_d) {
+        unsigned *d_cnt = s.counters.p + 33;
+        CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned), q));
+        P.foreign.reserve_keep(size_t(P.n_foreign_fixed) + P.nnz_d + 16, q);
+        k_dyn_cross<<<div_up(n, 256), 256, 0, q>>>(n, R.rpr, rank, s.dyn_off.p, s.dyn_col.p, P.nnz_f, P.mask.p, P.foreign.p + P.n_foreign_fixed, d_cnt, P.nnz_d);
+        unsigned h[3] = {0, 0, 0};
+        CUDA_OK(cudaMemcpyAsync(&h[0], d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaMemcpyAsync(&h[1], s.dyn_off.p + R.lo, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaMemcpyAsync(&h[2], s.dyn_off.p + R.hi, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaStreamSynchronize(q));
+        R.n_foreign += h[0];
+        R.kd_first = P.nnz_f + h[1];
+        R.kd_end = P.nnz_f + h[2];
+    }
+    static const bool debug = getenv("PPF_B200_DIST_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "[dist %u/%d] rows [%u,%u)  own blocks: fixed [%u,%u) of %u, dyn [%u,%u) of %u;  foreign blocks %u (%u fixed);  push %d\n", rank, g_dist.world,
+                R.lo, R.hi, R.kf_first, R.kf_end, P.nnz_f, R.kd_first - P.nnz_f, R.kd_end - P.nnz_f, P.nnz_d, R.n_foreign, P.n_foreign_fixed, (int)R.push);
+}
+
+// foreign blocks (stored under another rank's row, column owned here): y_col += B^T p_row
+__global__ void __launch_bounds__(256) k_spmv_foreign(unsigned count, const unsigned *__restrict__ idx, const unsigned *__restrict__ row,
+                                                      const unsigned *__restrict__ col, const float *__restrict__ val, size_t plane,
+                                                      const float4 *__restrict__ p, float4 *__restrict__ y, const CgScalars *sc, int with_dots) {
+    if (with_dots && sc->status != ST_RUNNING) return;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const unsigned k = idx[t];
+        const unsigned a = row[k], b = col[k];
+        const float4 pa = p[a];
+        const float h0 = val[k], h1 = val[plane + k], h2 = val[2 * plane + k], h3 = val[3 * plane + k], h4 = val[4 * plane + k];
+        const float h5 = val[5 * plane + k], h6 = val[6 * plane + k], h7 = val[7 * plane + k], h8 = val[8 * plane + k];
+        red_add_v4(y + b, h0 * pa.x + h1 * pa.y + h2 * pa.z, h3 * pa.x + h4 * pa.y + h5 * pa.z, h6 * pa.x + h7 * pa.y + h8 * pa.z);
+    }
+}
+
+static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const float4 *p, float4 *y, int with_dots) {
+    if (k_end <= k_first) return;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_OK(cudaFuncSetAttribute(k_spmv_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_SMEM));
         attr_set = true;
     }
-    const unsigned grid = std::min(P.spmv_grid, div_up(nnz, SPMV_CHUNK));
-    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+    const unsigned k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
+    const unsigned grid = std::min(P.spmv_grid, div_up(k_end - k_begin, SPMV_CHUNK));
+    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(k_begin, k_first, k_end, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
 }
 
-static void issue_iteration(State &s) {
+static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
+    const unsigned nnz = P.nnz_f + P.nnz_d;
+    if (!nnz) return;
+    static const bool legacy = getenv("PPF_B200_SPMV_LEGACY") != nullptr; // the register-only kernel, kept for A/B timing (one rank only)
+    if (legacy && !g_dist.on()) {
+        const unsigned grid = std::min(P.grid, div_up(nnz, PCG_BLOCK));
+        k_spmv<<<grid, PCG_BLOCK, 0, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+        return;
+    }
+    launch_spmv_range(s, R.kf_first, R.kf_end, p, y, with_dots);
+    launch_spmv_range(s, R.kd_first, R.kd_end, p, y, with_dots);
+    if (R.n_foreign)
+        k_spmv_foreign<<<std::min(P.grid, div_up(R.n_foreign, 256)), 256, 0, s.stream>>>(R.n_foreign, P.foreign.p, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+}
+
+// NCCL fallback (no peer mapping): every rank gets every slice of p
+static void exchange_p(State &s) {
+    if (!g_dist.on()) return;
+    dist_allgather(P.p.p + R.lo, P.p.p, sizeof(float4) * size_t(R.rpr), s.stream);
+}
+
+static void issue_iteration(State &s, int parity) {
     const unsigned n = P.n;
-    const unsigned gv = std::min(P.grid, div_up(n, PCG_BLOCK));
+    const unsigned rows = R.hi - R.lo;
+    const unsigned gv = std::max(1u, std::min(P.grid, div_up(rows, PCG_BLOCK)));
+    const PeerView &pv = dist_peers();
+    const bool p2p = g_dist.on() && R.push; // reductions through peer mailboxes, rows of p pushed by k_direction
     launch_spmv(s, P.p.p, P.y.p, 1);
-    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p);
-    k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p);
+    if (p2p) k_allreduce2<<<1, 32, 0, s.stream>>>(pv, P.sc.p, 0, parity);
+    else dist_allreduce_sum_f64(&P.sc.p->acc[parity][0], 2, s.stream);
+    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p);
+    if (p2p) k_allreduce2<<<1, 32, 0, s.stream>>>(pv, P.sc.p, 1, parity ^ 1);
+    else dist_allreduce_sum_f64(&P.sc.p->rzerr[parity ^ 1][0], 2, s.stream);
+    k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, pv, p2p ? P.mask.p : nullptr);
+    if (!p2p) exchange_p(s);
 }
 
 // PPF_B200_PCG_TUNE=1: time the kernels of the iteration in isolation on the first packed system
@@ -681,7 +887,7 @@ static void pcg_tune(State &s) {
         printf("[pcg-tune] %-28s %8.1f us/launch  %8.1f GB/s\n", name, 1e3 * ms / 20, bytes / (ms / 20 * 1e-3) * 1e-9);
     };
     CgScalars h{};
-    h.status = ST_RUNNING; h.tol = 0.f; h.max_iter = 1 << 30; h.err0 = 1.0; h.rz[0] = h.rz[1] = 1.0; h.acc_pap[0] = h.acc_pap[1] = 1e30;
+    h.status = ST_RUNNING; h.tol = 0.f; h.max_iter = 1 << 30; h.err0 = 1.0; h.rzerr[0][0] = h.rzerr[1][0] = 1.0; h.acc[0][0] = h.acc[1][0] = 1e30;
     cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q);
     const unsigned grid_save = P.spmv_grid;
     for (unsigned g : {148u * 2, 148u * 3, 148u * 4}) {
@@ -694,12 +900,17 @@ static void pcg_tune(State &s) {
     time_it("spmv register-only (legacy)", 40.0 * nnz + 24.0 * n, [&] {
         k_spmv<<<std::min(P.grid, div_up((unsigned)nnz, PCG_BLOCK)), PCG_BLOCK, 0, q>>>((unsigned)nnz, P.row.p, P.col.p, P.val.p, P.cap, P.p.p, P.y.p, P.sc.p, 1);
     });
-    time_it("update (r,z,dots)", 76.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p); });
-    time_it("direction (x,p,y=Dp,dots)", 108.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
+    time_it("update (r,z,dots)", 76.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p); });
+    time_it("direction (x,p,y=Dp,dots)", 108.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, PeerView{}, nullptr); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
     printf("[pcg-tune] n_row=%u n_off=%.0f (fixed %u + dyn %u); SpMV algorithmic bytes (40*n_off + 60*n_row) = %.1f MB\n", n, nnz, P.nnz_f, P.nnz_d,
            (40.0 * nnz + 60.0 * n + 4.0 * (n + 1)) * 1e-6);
     fflush(stdout);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+float4 *pcg_search_direction_buffer(State &s) {
+    if (!P.ready) pcg_init(s);
+    return P.p.p;
 }
 
 SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof_mask) {
@@ -708,7 +919,6 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     if (!P.ready) pcg_init(s);
     const unsigned n = P.n;
     const unsigned gv_full = div_up(n, PCG_BLOCK);
-    const unsigned gv = std::min(P.grid, gv_full);
 
     // ---- pack the assembled system ----
     P.nnz_d = s.dyn_nnz;
@@ -721,6 +931,8 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     LAUNCH_COUNT(3);
     s.spmv_n_row = n;
     s.spmv_n_off = (unsigned long long)P.nnz_f + P.nnz_d;
+    pcg_partition(s);
+    const unsigned gv_own = std::max(1u, std::min(P.grid, div_up(R.hi - R.lo, PCG_BLOCK)));
 
     // ---- setup: r = b - A x0, z = P r, p = z, y = D p, rz0, err0 ----
     CgScalars init{};
@@ -739,8 +951,12 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
         }
     }
     launch_spmv(s, P.p.p, P.y.p, 0);
-    k_residual_init<<<gv, PCG_BLOCK, 0, q>>>(n, P.y.p, P.r.p, P.z.p, P.p.p, P.Pinv.p, P.D.p, P.sc.p);
-    LAUNCH_COUNT(3);
+    k_residual_init<<<gv_own, PCG_BLOCK, 0, q>>>(n, R.lo, R.hi, P.y.p, P.r.p, P.z.p, P.p.p, P.Pinv.p, P.D.p, P.sc.p);
+    dist_allreduce_sum_f64(&P.sc.p->rzerr[0][0], 2, q);
+    // acc[0] keeps this rank's diagonal share: the first iteration's SpMV adds to it and reduces once
+    k_set_err0<<<1, 1, 0, q>>>(P.sc.p);
+    exchange_p(s);
+    LAUNCH_COUNT(4);
     CgScalars h{};
     CUDA_OK(cudaMemcpyAsync(&h, P.sc.p, sizeof(h), cudaMemcpyDeviceToHost, q));
     int bad = 0;
@@ -748,27 +964,34 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     CUDA_OK(cudaStreamSynchronize(q));
     if (bad) fatal(4, "PCG: a block-Jacobi diagonal block is non-finite or non-positive; the assembly is broken upstream");
     SolveResult res{true, 1u, 0.0f};
-    if (h.err0 == 0.0) {
-        k_store<<<gv_full, PCG_BLOCK, 0, q>>>(n, P.x.p, s.dx.p);
+    auto store_solution = [&] { // dx = x on the owned rows, then every rank gets every slice (bitwise identical positions on all ranks)
+        k_store<<<std::max(1u, div_up(R.hi - R.lo, PCG_BLOCK)), PCG_BLOCK, 0, q>>>(n, R.lo, R.hi, P.x.p, s.dx.p);
+        if (g_dist.on()) dist_allgather(s.dx.p + size_t(3) * R.lo, s.dx.p, sizeof(float) * 3 * size_t(R.rpr), q);
         LAUNCH_COUNT(1);
+    };
+    if (h.err0 == 0.0) {
+        store_solution();
         return res;
     }
-    if (!(h.rz[0] > 0.0)) fatal(4, "PCG breakdown: r^T M^-1 r = %.6e is not positive at setup; the preconditioner is not SPD", h.rz[0]);
+    if (!(h.rzerr[0][0] > 0.0)) fatal(4, "PCG breakdown: r^T M^-1 r = %.6e is not positive at setup; the preconditioner is not SPD", h.rzerr[0][0]);
 
     // ---- iterate: batches of ITER_PER_GRAPH iterations replayed from a CUDA graph ----
     const int ITER_PER_GRAPH = 8;
     const unsigned nnz = P.nnz_f + P.nnz_d;
-    if (P.exec && (P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p)) { // kernel parameters changed: re-capture
+    const unsigned long long part_sig = (unsigned long long)R.kd_first ^ ((unsigned long long)R.kd_end << 20) ^ ((unsigned long long)R.n_foreign << 40) ^
+                                        (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7);
+    if (P.exec && (P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p || P.graph_part != part_sig)) { // kernel parameters changed: re-capture
         cudaGraphExecDestroy(P.exec); cudaGraphDestroy(P.graph);
         P.exec = nullptr; P.graph = nullptr;
     }
     if (!P.exec) {
         CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal));
-        for (int k = 0; k < ITER_PER_GRAPH; ++k) issue_iteration(s);
+        for (int k = 0; k < ITER_PER_GRAPH; ++k) issue_iteration(s, k & 1);
         CUDA_OK(cudaStreamEndCapture(q, &P.graph));
         CUDA_OK(cudaGraphInstantiate(&P.exec, P.graph, 0ull));
         P.graph_nnz = nnz;
         P.graph_val = (const void *)P.val.p;
+        P.graph_part = part_sig;
     }
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
@@ -807,8 +1030,7 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     case ST_FATAL_RZ: fatal(4, "PCG breakdown -- r^T M^-1 r is non-positive at iter %d (reresid %.3e): the preconditioner is not SPD", iter, resid);
     default: res.ok = false;
     }
-    k_store<<<gv_full, PCG_BLOCK, 0, q>>>(n, P.x.p, s.dx.p);
-    LAUNCH_COUNT(1);
+    store_solution();
     return res;
 }
 

@@ -31,7 +31,8 @@ ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"
     "override_angular_velocity", "init_collision_windows", "refresh_collision_active", "fetch_intersection_records",
     "set_log_path", "ppf_fatal_code", "ppf_fatal_detail", "g_ppf_fatal_code", "g_ppf_fatal_detail", "print_rust",
 ]
-EXT_SYMBOLS = ["ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_detect_pairs", "ppf_b200_measure_spmv"]
+EXT_SYMBOLS = ["ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_detect_pairs", "ppf_b200_measure_spmv",
+               "ppf_b200_dist_unique_id", "ppf_b200_dist_init", "ppf_b200_dist_export", "ppf_b200_dist_connect"]
 
 
 class B200Stats(ctypes.Structure):  # PpfB200Stats
@@ -77,7 +78,11 @@ def host():
 class Session:
     """One scene + one backend library (one per process: the backends keep global state)."""
 
-    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0):
+    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None):
+        """shard = (rank, world, nccl_id_bytes[, allgather]): row-shard the PCG solve of this scene over `world`
+        GPUs (every rank builds the same scene; see csrc/dist.hpp).  `allgather(bytes) -> [bytes per rank]` is
+        the launcher's object all-gather; with it the ranks also exchange CUDA IPC handles and the per-iteration
+        collectives go through peer memory instead of NCCL.  None: single GPU."""
         if not os.path.exists(lib):
             raise RuntimeError("backend library %s is missing (no CPU fallback exists)" % lib)
         self.h = host()
@@ -98,6 +103,23 @@ class Session:
         if not self.h.ppfh_init(self.p, self.log_dir.encode()):
             raise RuntimeError("backend initialize() failed")
         self.is_b200 = bool(self.h.ppfh_has_b200_ext(self.p))
+        if shard is not None and shard[1] > 1:
+            fn = self._sym("ppf_b200_dist_init", ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
+            if not fn:
+                raise RuntimeError("backend %s has no multi-GPU entry point" % lib)
+            rc = fn(int(shard[0]), int(shard[1]), bytes(shard[2]), len(shard[2]))
+            if rc != 0:
+                raise RuntimeError("ppf_b200_dist_init failed (%d)" % rc)
+            self.p2p = False
+            if len(shard) > 3 and shard[3] is not None:
+                exp = self._sym("ppf_b200_dist_export", ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
+                con = self._sym("ppf_b200_dist_connect", ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
+                buf = ctypes.create_string_buffer(256)
+                m = exp(buf, 256)
+                blobs = shard[3](buf.raw[:m] if m > 0 else b"")
+                if all(len(b) == m and m > 0 for b in blobs):
+                    blob = b"".join(blobs)
+                    self.p2p = con(blob, len(blob)) == 1
 
     def step(self):
         """update_constraint + advance through the ABI; returns (ok, wall_ms)."""
@@ -212,6 +234,16 @@ class Session:
         if not os.path.exists(p):
             return []
         return [float(l.split()[1]) for l in open(p) if len(l.split()) == 2]
+
+
+def nccl_unique_id(lib=LIB_OURS):
+    """128-byte NCCL id created by the backend on rank 0; broadcast it to the other ranks before Session(shard=...)."""
+    l = ctypes.CDLL(lib)
+    buf = ctypes.create_string_buffer(256)
+    n = l.ppf_b200_dist_unique_id(buf, 256)
+    if n <= 0:
+        raise RuntimeError("the backend could not create an NCCL id (libnccl.so.2 not found?)")
+    return buf.raw[:n]
 
 
 def exported_symbols(lib):

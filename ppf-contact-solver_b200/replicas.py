@@ -21,7 +21,7 @@ class Ranks:
 
             backend = backend or "nccl"
             if backend == "nccl":
-                torch.cuda.set_device(0)  # CUDA_VISIBLE_DEVICES was narrowed to this rank's GPU
+                torch.cuda.set_device(self.local_rank)
                 self.device = "cuda"
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group(backend)

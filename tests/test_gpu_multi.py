@@ -1,0 +1,37 @@
+"""Sharded PCG over 2 GPUs (csrc/dist.hpp): needs two B200s, skipped otherwise.  Every rank must end with
+bitwise identical positions and logs (scripts/dist_check.py asserts it), and the result must agree with the
+single-GPU run of the same steps like two single-GPU runs agree with each other."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+pytestmark = pytest.mark.gpu
+
+
+def _launch(world, scene, n, steps, env=None):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(REPO, "scripts", "dist_check.py"), scene, str(n), str(steps)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line), np.load("/tmp/dist_check_curr_w%d.npy" % world)
+
+
+def test_two_gpu_sharded_pcg_matches_single_gpu(built):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    one, x1 = _launch(1, "fast-twist", 24, 6)
+    for env in ({}, {"PPF_B200_DIST_ALLGATHER": "1"}):      # neighbour-halo path, all-gather path
+        two, x2 = _launch(2, "fast-twist", 24, 6, env)
+        assert two["world"] == 2
+        assert abs(two["n_cg_iter"] - one["n_cg_iter"]) <= 0.02 * one["n_cg_iter"] + 4
+        d = np.abs(x1 - x2).max(axis=1)
+        assert float(np.median(d)) < 5e-5 and float(d.max()) < 5e-3   # 6 chained steps (see test_gpu_parity)
