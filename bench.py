@@ -249,7 +249,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "%s: cylinder n=%s, V=%d F=%d E=%d hinges=%d, dt=1/60, steps from t=0; %s" % (
             args.scene, args.n or "config default", s.n_vert, s.n_face, s.n_edge, s.n_hinge,
-            ("one scene, PCG rows sharded over %d GPUs (NCCL halo exchange + 2 all-reduces per iteration)" % WORLD) if shard is not None
+            ("one scene, PCG rows sharded over %d GPUs (rows of p pushed + two 2-double sums per iteration over NVLink peer memory)" % WORLD) if shard is not None
             else ("replicas (one independent scene per GPU)" if WORLD > 1 else "single GPU")),
             "l2": "inputs larger than L2 (packed matrix %.0f MB per SpMV)" % ((40.0 * (st1["spmv_n_off"] if st1 else 0) + 60.0 * s.n_vert) * 1e-6)},
         "e2e": {"value": tot_frames / t_e2e, "unit": "frames/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -282,7 +282,7 @@ def main():
         tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        line["roofline"] = {"bound": "hbm", "kernel": "ppf::k_spmv", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        line["roofline"] = {"bound": "hbm", "kernel": "ppf::k_spmv_staged" + (" (rank 0's share of the rows)" if shard is not None else ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "peak_source": how, "us_per_launch": us, "n_row": n_row, "n_off": n_off,
                             "bytes_per_launch": bytes_per_launch}
     if WORLD == 1:

@@ -289,4 +289,163 @@ static inline void o_hinge(const float (*X)[3], float rest_angle, float f[4][3],
                 for (int j = 0; j < 3; ++j) H[(3 * perm[b2] + j) * 12 + 3 * perm[a2] + i] = Hp[(3 * b2 + j) * 12 + 3 * a2 + i];
 }
 
+
+/* ---- strain limiting (strainlimiting/strainlimiting.cu:18-120, 250-307; utility/utility.cu:60-150, 185-250;
+ *      barrier/barrier.cu:116-131; eigenanalysis/eigenanalysis.cu:11-85; linalg/eigsolve.hpp:40-94) ---- */
+typedef struct { float U[3][2], S[2], Vt[2][2]; } o_svd32;
+static inline void o_jacobi_svd32(const float F[3][2], o_svd32 *o) { /* one-sided Jacobi, one sweep, ascending singular values */
+    float A[3][2], V[2][2] = {{1.0f, 0.0f}, {0.0f, 1.0f}};
+    float a = 0.0f, b = 0.0f, g = 0.0f;
+    for (int r = 0; r < 3; ++r) { A[r][0] = F[r][0]; A[r][1] = F[r][1]; }
+    for (int r = 0; r < 3; ++r) { a = a + A[r][0] * A[r][0]; b = b + A[r][1] * A[r][1]; g = g + A[r][0] * A[r][1]; }
+    const float zeta = (b - a) / (2.0f * g);
+    const float t = (g == 0.0f) ? 0.0f : (zeta >= 0.0f ? 1.0f : -1.0f) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+    const float c = 1.0f / sqrtf(1.0f + t * t), s = c * t;
+    for (int r = 0; r < 3; ++r) { const float p = A[r][0], q = A[r][1]; A[r][0] = c * p - s * q; A[r][1] = s * p + c * q; }
+    for (int r = 0; r < 2; ++r) { const float p = V[r][0], q = V[r][1]; V[r][0] = c * p - s * q; V[r][1] = s * p + c * q; }
+    float sv[2], u[3][2];
+    for (int k = 0; k < 2; ++k) {
+        float n2 = 0.0f;
+        for (int r = 0; r < 3; ++r) n2 = n2 + A[r][k] * A[r][k];
+        sv[k] = sqrtf(n2);
+        const float inv = sv[k] > 0.0f ? 1.0f / sv[k] : 0.0f;
+        for (int r = 0; r < 3; ++r) u[r][k] = A[r][k] * inv;
+    }
+    const int i0 = sv[1] < sv[0] ? 1 : 0, idx[2] = {i0, 1 - i0};
+    for (int k = 0; k < 2; ++k) {
+        o->S[k] = sv[idx[k]];
+        for (int r = 0; r < 3; ++r) o->U[r][k] = u[r][idx[k]];
+        for (int r = 0; r < 2; ++r) o->Vt[k][r] = V[r][idx[k]];
+    }
+}
+static inline void o_defgrad32(const float *x0, const float *x1, const float *x2, const float *ir, float F[3][2]) {
+    for (int r = 0; r < 3; ++r) {
+        const float e0 = x1[r] - x0[r], e1 = x2[r] - x0[r];
+        F[r][0] = e0 * ir[0] + e1 * ir[1];
+        F[r][1] = e0 * ir[2] + e1 * ir[3];
+    }
+}
+static inline float o_max_strain_at(const float F0[3][2], const float dF[3][2], float t) {
+    float F[3][2];
+    o_svd32 svd;
+    for (int r = 0; r < 3; ++r) { F[r][0] = F0[r][0] + t * dF[r][0]; F[r][1] = F0[r][1] + t * dF[r][1]; }
+    o_jacobi_svd32(F, &svd);
+    const float s0 = svd.S[0] - 1.0f, s1 = svd.S[1] - 1.0f;
+    return s0 < s1 ? s1 : s0;
+}
+/* xa/xb: face vertex positions at the start / end of the candidate step (3 x 3) */
+static inline float o_strain_face_toi(const float (*xa)[3], const float (*xb)[3], const float *ir, float limit, float max_t) {
+    float F0[3][2], F1[3][2], dF[3][2];
+    o_defgrad32(xa[0], xa[1], xa[2], ir, F0);
+    o_defgrad32(xb[0], xb[1], xb[2], ir, F1);
+    for (int r = 0; r < 3; ++r) { dF[r][0] = F1[r][0] - F0[r][0]; dF[r][1] = F1[r][1] - F0[r][1]; }
+    float t = max_t;
+    if (o_max_strain_at(F0, dF, t) >= limit) {
+        float hi = t, lo = 0.0f, window = hi - lo;
+        for (;;) {
+            t = 0.5f * (hi + lo);
+            if (o_max_strain_at(F0, dF, t) - limit < 0.0f) lo = t; else hi = t;
+            const float nw = hi - lo;
+            if (nw == window) break;
+            window = nw;
+        }
+        t = lo;
+    }
+    return t;
+}
+static inline void o_symm2x2(float a00, float a01, float a11, float *val, float vec[2][2]) {
+    const float scale = fmaxf(fmaxf(fabsf(a00), fabsf(a01)), fabsf(a11));
+    if (scale <= 0.0f) { val[0] = val[1] = 0.0f; vec[0][0] = vec[1][1] = 1.0f; vec[0][1] = vec[1][0] = 0.0f; return; }
+    const float b00 = a00 / scale, b01 = a01 / scale, b11 = a11 / scale;
+    const float d = b00 - b11, D = 0.5f * sqrtf(d * d + 4.0f * b01 * b01), mid = 0.5f * (b00 + b11);
+    const float l0 = mid - D, l1 = mid + D;
+    const float r0[2] = {b01, -(b00 - l0)}, r1[2] = {b11 - l0, -b01};
+    const float n0 = r0[0] * r0[0] + r0[1] * r0[1], n1 = r1[0] * r1[0] + r1[1] * r1[1];
+    float u[2] = {1.0f, -0.0f};
+    if (n0 > 1e-14f) { const float n = sqrtf(n0); u[0] = r0[0] / n; u[1] = r0[1] / n; }
+    else if (n1 > 1e-14f) { const float n = sqrtf(n1); u[0] = r1[0] / n; u[1] = r1[1] / n; }
+    val[0] = scale * l0; val[1] = scale * l1;
+    vec[0][0] = u[0]; vec[1][0] = u[1]; vec[0][1] = u[1]; vec[1][1] = -u[0];
+}
+/* One face.  xe: evaluation positions, xc: start-of-step positions, Hel[a][b][9]: elastic-only blocks (column-major).
+ * Outputs are already scaled by the stiffness; returns 0 when the face is not stretched. */
+static inline int o_strain_face(const float (*xe)[3], const float (*xc)[3], const float *ir, float strainlimit, float limit, float mass,
+                                const float Hel[3][3][9], float eig_eps, float f[3][3], float H[3][3][9]) {
+    float F[3][2];
+    o_svd32 svd;
+    o_defgrad32(xe[0], xe[1], xe[2], ir, F);
+    o_jacobi_svd32(F, &svd);
+    float S[2] = {svd.S[0] - 1.0f, svd.S[1] - 1.0f};
+    const float smax = S[0] < S[1] ? S[1] : S[0];
+    if (!(smax > 0.0f)) return 0;
+    float deda[2] = {0.0f, 0.0f}, d2[2] = {0.0f, 0.0f};
+    for (int i = 0; i < 2; ++i)
+        if (S[i] > 0.0f) {
+            const float y = strainlimit - S[i];
+            deda[i] = -o_cubic_gradient(y, strainlimit, 0.0f);
+            d2[i] = o_cubic_curvature(y, strainlimit, 0.0f);
+        }
+    const float third = 1.0f / 3.0f;
+    float w[3][3], wHw = 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        const float c = third * xc[0][k] + third * xc[1][k] + third * xc[2][k];
+        for (int a = 0; a < 3; ++a) w[a][k] = xc[a][k] - c;
+    }
+    for (int a = 0; a < 3; ++a) {
+        float row[3] = {0.0f, 0.0f, 0.0f};
+        for (int b = 0; b < 3; ++b)
+            for (int r = 0; r < 3; ++r) row[r] += Hel[a][b][r] * w[b][0] + Hel[a][b][3 + r] * w[b][1] + Hel[a][b][6 + r] * w[b][2];
+        wHw += w[a][0] * row[0] + w[a][1] * row[1] + w[a][2] * row[2];
+    }
+    const float dgap = limit - smax, stiffness = wHw + mass / (dgap * dgap);
+    S[0] += 1.0f; S[1] += 1.0f;
+    float dedF[3][2];
+    for (int r = 0; r < 3; ++r)
+        for (int j = 0; j < 2; ++j) dedF[r][j] = (svd.U[r][0] * deda[0]) * svd.Vt[0][j] + (svd.U[r][1] * deda[1]) * svd.Vt[1][j];
+    float ev[2], evec[2][2];
+    o_symm2x2(d2[0], 0.0f, d2[1], ev, evec);
+    const float is2 = 0.7071067811865475f;
+    float U3[3][3], Q[6][3][2];
+    for (int r = 0; r < 3; ++r) { U3[r][0] = svd.U[r][0]; U3[r][1] = svd.U[r][1]; }
+    U3[0][2] = svd.U[1][0] * svd.U[2][1] - svd.U[2][0] * svd.U[1][1];
+    U3[1][2] = svd.U[2][0] * svd.U[0][1] - svd.U[0][0] * svd.U[2][1];
+    U3[2][2] = svd.U[0][0] * svd.U[1][1] - svd.U[1][0] * svd.U[0][1];
+    memset(Q, 0, sizeof(Q));
+    Q[0][0][1] = is2; Q[0][1][0] = -is2; Q[1][0][1] = is2; Q[1][1][0] = is2; Q[2][2][0] = 1.0f; Q[3][2][1] = 1.0f;
+    for (int i = 0; i < 2; ++i) { Q[4][i][i] = evec[i][0]; Q[5][i][i] = evec[i][1]; }
+    const float a0 = S[0], a1 = S[1], den = a0 - a1;
+    float lam[6];
+    lam[0] = fmaxf(0.0f, (deda[0] + deda[1]) / (a0 + a1));
+    lam[1] = fmaxf(0.0f, fabsf(den) > eig_eps ? (deda[0] - deda[1]) / den : 0.5f * (d2[0] + d2[1]));
+    lam[2] = fmaxf(0.0f, deda[0] / a0);
+    lam[3] = fmaxf(0.0f, deda[1] / a1);
+    lam[4] = fmaxf(0.0f, ev[0]);
+    lam[5] = fmaxf(0.0f, ev[1]);
+    float d2F[6][6];
+    memset(d2F, 0, sizeof(d2F));
+    for (int i = 0; i < 6; ++i) {
+        if (!lam[i]) continue;
+        float q[6];
+        for (int j = 0; j < 2; ++j)
+            for (int r = 0; r < 3; ++r) {
+                const float t0 = U3[r][0] * Q[i][0][0] + U3[r][1] * Q[i][1][0] + U3[r][2] * Q[i][2][0];
+                const float t1 = U3[r][0] * Q[i][0][1] + U3[r][1] * Q[i][1][1] + U3[r][2] * Q[i][2][1];
+                q[3 * j + r] = t0 * svd.Vt[0][j] + t1 * svd.Vt[1][j];
+            }
+        for (int x = 0; x < 6; ++x) for (int y = 0; y < 6; ++y) d2F[x][y] += lam[i] * q[x] * q[y];
+    }
+    const float g[3][2] = {{-ir[0] - ir[1], -ir[2] - ir[3]}, {ir[0], ir[2]}, {ir[1], ir[3]}};
+    for (int a = 0; a < 3; ++a)
+        for (int dim = 0; dim < 3; ++dim) f[a][dim] = stiffness * (g[a][0] * dedF[dim][0] + g[a][1] * dedF[dim][1]);
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r) {
+                    float v = 0.0f;
+                    for (int dd = 0; dd < 2; ++dd) for (int ee = 0; ee < 2; ++ee) v += (g[a][dd] * g[b][ee]) * d2F[3 * dd + r][3 * ee + c];
+                    H[a][b][c * 3 + r] = stiffness * v;
+                }
+    return 1;
+}
+
 #endif

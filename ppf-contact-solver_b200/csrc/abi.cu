@@ -129,7 +129,6 @@ void upload_dataset(State &s) {
     for (unsigned i = 0; i < d.param_arrays.face.size; ++i) {
         const PpfFaceParam &fp = d.param_arrays.face.data[i];
         if (fp.model != PPF_MODEL_BARAFFWITKIN) fatal(4, "B200 backend: only the Baraff-Witkin shell model is implemented");
-        if (fp.strainlimit > 0.0f) fatal(4, "B200 backend: strain limiting is not implemented yet");
         if (fp.pressure > 0.0f || fp.deform_damping > 0.0f || fp.bend_damping > 0.0f)
             fatal(4, "B200 backend: inflation pressure / Rayleigh damping are not implemented");
     }
@@ -169,6 +168,8 @@ void upload_dataset(State &s) {
     // ---- resolved per-primitive parameters ----
     {
         std::vector<float4> v(nv), e(ne), f(nf), fm(nf), ir(nf), hm(nh);
+        std::vector<float2> fs(nf);
+        s.has_strainlimit = false;
         std::vector<float> va(nv), hs(nh);
         std::vector<unsigned char> vc(nv), fsk(nf);
         for (unsigned i = 0; i < nv; ++i) {
@@ -189,6 +190,9 @@ void upload_dataset(State &s) {
             const PpfFaceParam &fp = d.param_arrays.face.data[p.param_index];
             f[i] = make_float4(fp.ghat, fp.offset, fp.friction, p.mass);
             fm[i] = make_float4(fp.mu, fp.lambda, p.mass, 0.0f);
+            // strainlimiting.cu:63-64: the limit is relaxed by the smallest shrink factor
+            fs[i] = make_float2(fp.strainlimit, fp.strainlimit > 0.0f ? (fp.strainlimit + 1.0f) / fminf(fp.shrink_x, fp.shrink_y) - 1.0f : 0.0f);
+            if (fp.strainlimit > 0.0f && !(p.rest_excluded || p.collider)) s.has_strainlimit = true;
             const PpfMat2x2f &m = d.inv_rest2x2.data[i];
             ir[i] = make_float4(m.m[0], m.m[1], m.m[2], m.m[3]);
             fsk[i] = p.rest_excluded || p.collider;
@@ -214,6 +218,7 @@ void upload_dataset(State &s) {
         }
         s.vcp.upload(v.data(), nv, q); s.ecp.upload(e.data(), ne, q); s.fcp.upload(f.data(), nf, q);
         s.fmat.upload(fm.data(), nf, q); s.inv_rest.upload(ir.data(), nf, q); s.hmat.upload(hm.data(), nh, q);
+        s.fstrain.upload(fs.data(), nf, q);
         s.varea.upload(va.data(), nv, q); s.hinge_stiff.upload(hs.data(), nh, q);
         s.vcollider.upload(vc.data(), nv, q); s.fskip.upload(fsk.data(), nf, q);
         CUDA_OK(cudaStreamSynchronize(q));

@@ -115,6 +115,8 @@ struct State {
     DBuf<unsigned> fix_index, pull_index;         // per vertex (1-based, 0 = none)
     DBuf<unsigned char> vfixed, efixed, ffixed, hfixed, vcollider, fskip;
     DBuf<float4> fmat;                            // per face (mu, lambda, mass, deform_damping)
+    DBuf<float2> fstrain;                         // per face (strain-limit parameter, shrink-adjusted limit); 0 = off
+    bool has_strainlimit = false;
     DBuf<float4> inv_rest;                        // per face 2x2
     DBuf<float4> hmat;                            // per hinge (length, area, rest_angle, bend_dir)
     DBuf<float> hinge_stiff;                      // per hinge stiffness (energy.cu:510-517), 0 = skip
@@ -182,6 +184,8 @@ void step_advance(State &s, PpfStepResult *result);          // step.cu
 // elastic.cu
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm);
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
+void assemble_strainlimit(State &s, const PpfParamSet &prm);                                  // after the elastic snapshot
+float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // fraction in (0, 1]
 void recompute_fixed_flags(State &s);
 
 // bvh.cu

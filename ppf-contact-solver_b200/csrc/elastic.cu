@@ -10,6 +10,7 @@
 #include "backend.hpp"
 #include "math_elastic.cuh"
 #include "math_hinge.cuh"
+#include "math_strain.cuh"
 
 namespace ppf {
 
@@ -136,6 +137,106 @@ __global__ void __launch_bounds__(128) k_hinge(unsigned nh, const uint4 *__restr
                 for (int r = 0; r < 3; ++r) blk[c * 3 + r] = k * he.H[(3 * b + c) * 12 + (3 * a + r)];
             atomic_add_block(val, slot, blk);
         }
+}
+
+// ---- strain limiting (strainlimiting.cu:46-120, 250-307; math_strain.cuh) ----
+__device__ __forceinline__ unsigned fixed_slot(const unsigned *__restrict__ off, const unsigned *__restrict__ col, unsigned i, unsigned j) { // i <= j
+    for (unsigned k = off[i]; k < off[i + 1]; ++k) {
+        const unsigned c = col[k];
+        if (c == j) return k;
+        if (c > j) break;
+    }
+    return 0xFFFFFFFFu;
+}
+__global__ void __launch_bounds__(128) k_strainlimit(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ eval_x,
+                                                     const float4 *__restrict__ curr, const float4 *__restrict__ fmat,
+                                                     const float2 *__restrict__ fstrain, const float4 *__restrict__ inv_rest,
+                                                     const unsigned char *__restrict__ ffixed, const unsigned char *__restrict__ fskip,
+                                                     const unsigned *__restrict__ fx_off, const unsigned *__restrict__ fx_col,
+                                                     const float *__restrict__ fx_el, const unsigned *__restrict__ slots, float eig_eps,
+                                                     float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || ffixed[i] || fskip[i]) return;
+    const float2 sl2 = fstrain[i];
+    if (!(sl2.x > 0.0f)) return;
+    const uint4 f = face[i];
+    const unsigned vi[3] = {f.x, f.y, f.z};
+    const float4 ir = inv_rest[i];
+    const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+    V3 xe[3], xc[3];
+    for (int a = 0; a < 3; ++a) { xe[a] = ld3(eval_x, vi[a]); xc[a] = ld3(curr, vi[a]); }
+    // cheap exit before gathering the nine elastic blocks: is the face stretched at all?
+    {
+        float F[3][2];
+        deformation_grad32(xe[0], xe[1], xe[2], irv, F);
+        Svd32 svd;
+        jacobi_svd32(F, svd);
+        if (!(fmaxf(svd.S[0], svd.S[1]) - 1.0f > 0.0f)) return;
+    }
+    M3 Hel[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            const unsigned ia = vi[a], ib = vi[b];
+            const bool swap = ia > ib;
+            const unsigned slot = fixed_slot(fx_off, fx_col, swap ? ib : ia, swap ? ia : ib);
+            M3 m = m3_zero();
+            if (slot != 0xFFFFFFFFu) {
+                const float *p = fx_el + size_t(9) * slot;
+                if (!swap) for (int e = 0; e < 9; ++e) m.m[e] = p[e];
+                else for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) m.m[c * 3 + r] = p[r * 3 + c];
+            }
+            Hel[a][b] = m;
+        }
+    StrainFace sf;
+    if (!strain_face(xe, xc, irv, sl2.x, sl2.y, fmat[i].z, Hel, eig_eps, sf)) return;
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], sf.f[a]);
+    const unsigned *sl = slots + size_t(9) * i;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) atomic_add_block(val, sl[a * 3 + b], sf.H[a][b].m);
+}
+// per-face largest admissible step fraction; folded into *toi_bits (positive floats order like their bit patterns)
+__global__ void __launch_bounds__(128) k_strain_toi(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ x0,
+                                                    const float4 *__restrict__ x1, const float2 *__restrict__ fstrain,
+                                                    const float4 *__restrict__ inv_rest, const unsigned char *__restrict__ ffixed,
+                                                    const unsigned char *__restrict__ fskip, float max_t, unsigned *toi_bits) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float t = max_t;
+    if (i < nf && !ffixed[i] && !fskip[i]) {
+        const float2 sl2 = fstrain[i];
+        if (sl2.x > 0.0f) {
+            const uint4 f = face[i];
+            const float4 ir = inv_rest[i];
+            const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+            const V3 xa[3] = {ld3(x0, f.x), ld3(x0, f.y), ld3(x0, f.z)}, xb[3] = {ld3(x1, f.x), ld3(x1, f.y), ld3(x1, f.z)};
+            t = strain_face_toi(xa, xb, irv, sl2.y, max_t);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
+}
+
+void assemble_strainlimit(State &s, const PpfParamSet &prm) {
+    if (!s.has_strainlimit || !s.nf) return;
+    k_strainlimit<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.curr.p, s.fmat.p, s.fstrain.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
+                                                           s.fx_off.p, s.fx_col.p, s.fx_el.p, s.face_slots.p, prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+    LAUNCH_COUNT(1);
+}
+// strainlimiting::line_search: fraction of the step x0 -> x1 that keeps every face below its strain limit
+float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm) {
+    if (!s.has_strainlimit || !s.nf) return 1.0f;
+    unsigned *w = s.counters.p + 26;
+    const float max_t = prm.line_search_max_t;
+    unsigned init;
+    memcpy(&init, &max_t, sizeof(float));
+    CUDA_OK(cudaMemcpyAsync(w, &init, sizeof(unsigned), cudaMemcpyHostToDevice, s.stream));
+    k_strain_toi<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, x0, x1, s.fstrain.p, s.inv_rest.p, s.ffixed.p, s.fskip.p, max_t, w);
+    LAUNCH_COUNT(1);
+    unsigned h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, w, sizeof(unsigned), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    float t;
+    memcpy(&t, &h, sizeof(float));
+    return t / max_t;
 }
 
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {

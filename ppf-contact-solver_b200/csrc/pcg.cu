@@ -33,7 +33,7 @@ static constexpr int PCG_BLOCK = 256;
 static constexpr float CG_NOISE_SLACK = 256.0f;
 static constexpr float CG_FLOAT_EPS = 1.19209290e-7f;
 
-enum { ST_RUNNING = 0, ST_CONVERGED = 1, ST_TRUNCATED = 2, ST_CAP = 3, ST_FATAL_PAP = 4, ST_FATAL_RZ = 5, ST_NONFINITE = 6 };
+enum { ST_RUNNING = 0, ST_CONVERGED = 1, ST_TRUNCATED = 2, ST_CAP = 3, ST_FATAL_PAP = 4, ST_FATAL_RZ = 5, ST_NONFINITE = 6, ST_PEER_TIMEOUT = 7 };
 
 struct CgScalars {                 // device-resident control block
     double acc[2][2];              // [parity][0: p.Ap, 1: sum|terms|]   (pairs are contiguous: one 2-double all-reduce)
@@ -65,6 +65,7 @@ struct PackedMatrix {
     unsigned graph_nnz = ~0u;
     const void *graph_val = nullptr;
     unsigned long long graph_part = 0;
+    int graph_iters = 0;
     int *h_status = nullptr;         // pinned mirror of {iter, status, last_resid}
     unsigned grid = 0;               // persistent grid size of the vector kernels
     unsigned spmv_grid = 0;          // persistent grid of the staged SpMV (SMs x resident CTAs)
@@ -577,6 +578,22 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
 }
 
 // x += alpha p;  p = z + beta p;  y = D p (start value of the next SpMV) with the diagonal's share of p.Ap;  scalar tail
+// Wait until a peer has raised *flag to at least e.  A rank that died or took a different branch must not hang
+// the GPU: after 2 s of wall time the wait gives up and the solve ends with ST_PEER_TIMEOUT on this rank.
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long e) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (*(volatile const unsigned long long *)flag < e) {
+        if ((++spins & 0xFFFFu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            else if (now - t0 > 2000000000ull) return false;
+        }
+    }
+    return true;
+}
+
 // With peer memory (dist.hpp) a row that other ranks read (push_mask) is also stored straight into their p
 // arrays over NVLink, and the last CTA raises every peer's epoch flag and waits for theirs, so the next SpMV
 // finds its remote rows in place: the exchange costs no extra launch.
@@ -644,7 +661,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
             for (int q = 0; q < pv.world; ++q)
                 if (q != pv.rank) *(volatile unsigned long long *)&pv.comm[q]->halo_flag[pv.rank] = e;
             for (int q = 0; q < pv.world; ++q)
-                if (q != pv.rank) while (*(volatile unsigned long long *)&mine->halo_flag[q] < e) {}
+                if (q != pv.rank && !spin_until(&mine->halo_flag[q], e)) st = ST_PEER_TIMEOUT;
             __threadfence_system();
         }
         sc->iter = it;
@@ -672,7 +689,7 @@ __global__ void k_allreduce2(PeerView pv, CgScalars *sc, int slot, int parity) {
         __threadfence_system();
         *(volatile unsigned long long *)&m->epoch = e;
         const Mail *in = &mine->mail[slot][parity][lane];
-        while (*(volatile const unsigned long long *)&in->epoch < e) {}
+        if (!spin_until(&in->epoch, e)) sc->status = ST_PEER_TIMEOUT;
         __threadfence_system();
         a = ((volatile const double *)in->v)[0];
         b = ((volatile const double *)in->v)[1];
@@ -976,11 +993,13 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     if (!(h.rzerr[0][0] > 0.0)) fatal(4, "PCG breakdown: r^T M^-1 r = %.6e is not positive at setup; the preconditioner is not SPD", h.rzerr[0][0]);
 
     // ---- iterate: batches of ITER_PER_GRAPH iterations replayed from a CUDA graph ----
-    const int ITER_PER_GRAPH = 8;
+    // iterations per graph launch: the host polls one status word per batch; after convergence the rest of a
+    // batch early-exits (~10 us per iteration), so small systems use short batches and large ones long ones
+    const int ITER_PER_GRAPH = n >= 500000u ? 32 : 8; // even: the iteration parity inside a batch is known on the host
     const unsigned nnz = P.nnz_f + P.nnz_d;
     const unsigned long long part_sig = (unsigned long long)R.kd_first ^ ((unsigned long long)R.kd_end << 20) ^ ((unsigned long long)R.n_foreign << 40) ^
                                         (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7);
-    if (P.exec && (P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p || P.graph_part != part_sig)) { // kernel parameters changed: re-capture
+    if (P.exec && (P.graph_iters != ITER_PER_GRAPH || P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p || P.graph_part != part_sig)) { // kernel parameters changed: re-capture
         cudaGraphExecDestroy(P.exec); cudaGraphDestroy(P.graph);
         P.exec = nullptr; P.graph = nullptr;
     }
@@ -992,6 +1011,7 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
         P.graph_nnz = nnz;
         P.graph_val = (const void *)P.val.p;
         P.graph_part = part_sig;
+        P.graph_iters = ITER_PER_GRAPH;
     }
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
@@ -1024,6 +1044,7 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
         printf("* cg truncated: curvature within round-off of its own reduction at iter %d (reresid %.3e)\n", iter, resid);
         res.ok = true;
         break;
+    case ST_PEER_TIMEOUT: fatal(3, "multi-GPU PCG: a peer rank did not answer within 2 s at iter %d (it died or diverged); giving up instead of hanging the GPU", iter);
     case ST_CAP:
     case ST_NONFINITE: res.ok = false; break;
     case ST_FATAL_PAP: fatal(4, "PCG breakdown -- p^T A p is negative beyond its round-off bound at iter %d (reresid %.3e): the assembled Newton matrix is not SPD", iter, resid);
@@ -1042,8 +1063,9 @@ extern "C" __attribute__((visibility("default"))) double ppf_b200_measure_spmv(u
     using namespace ppf;
     State &s = g;
     if (!P.ready || !(P.nnz_f + P.nnz_d) || !reps) return 0.0;
-    if (n_row) *n_row = P.n;
-    if (n_off) *n_off = (unsigned long long)P.nnz_f + P.nnz_d;
+    // this rank's share: owned rows, blocks of owned rows plus foreign blocks (everything on one GPU)
+    if (n_row) *n_row = R.hi - R.lo;
+    if (n_off) *n_off = (unsigned long long)(R.kf_end - R.kf_first) + (R.kd_end - R.kd_first) + R.n_foreign;
     cudaStream_t q = s.stream;
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));

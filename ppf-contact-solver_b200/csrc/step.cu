@@ -227,6 +227,9 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.push("asm copy");
         CUDA_OK(cudaMemcpyAsync(s.fx_el.p, s.fx_val.p, sizeof(float) * 9 * size_t(s.fixed_nnz), cudaMemcpyDeviceToDevice, q));
         logging.pop();
+        logging.push("asm strainlimit");
+        assemble_strainlimit(s, prm);
+        logging.pop();
         unsigned num_contact = 0, max_nnz_row = 0;
         float dyn_consumed = 0.0f;
         logging.push("asm contact");
@@ -302,6 +305,11 @@ void step_advance(State &s, PpfStepResult *out) {
                 return;
             }
             logging.pop();
+        }
+        if (s.has_strainlimit) { // strainlimiting::line_search (main.cu:1321-1335)
+            const float sl_toi = strain_line_search(s, s.x_old.p, s.eval_x.p, prm);
+            toi = fminf(toi, sl_toi);
+            logging.mark("SL_toi", sl_toi);
         }
         logging.mark("toi", toi);
         last_toi = toi;
