@@ -35,3 +35,31 @@ SHIM void orc_hinge(const float *x12, float rest_angle, float *f12, float *H144)
     o_hinge(X, rest_angle, f, H144);
     for (int a = 0; a < 4; ++a) for (int k = 0; k < 3; ++k) f12[3 * a + k] = f[a][k];
 }
+
+/* strain limiting of one face: xe9/xc9 evaluation / start-of-step positions, Hel81 = 3x3 blocks [a][b][9] (column-major);
+ * outputs scaled by the stiffness; returns 0 when the face is not stretched.  svd6: U(3x2, column-major) S Vt(2x2 row-major) */
+SHIM int orc_strain_face(const float *xe9, const float *xc9, const float *ir4, float strainlimit, float limit, float mass, const float *Hel81,
+                         float eig_eps, float *f9, float *H81) {
+    float xe[3][3], xc[3][3], Hel[3][3][9], f[3][3], H[3][3][9];
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) { xe[a][k] = xe9[3 * a + k]; xc[a][k] = xc9[3 * a + k]; }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int e = 0; e < 9; ++e) Hel[a][b][e] = Hel81[(a * 3 + b) * 9 + e];
+    const int on = o_strain_face(xe, xc, ir4, strainlimit, limit, mass, Hel, eig_eps, f, H);
+    if (!on) return 0;
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) f9[3 * a + k] = f[a][k];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int e = 0; e < 9; ++e) H81[(a * 3 + b) * 9 + e] = H[a][b][e];
+    return 1;
+}
+SHIM float orc_strain_toi(const float *xa9, const float *xb9, const float *ir4, float limit, float max_t) {
+    float xa[3][3], xb[3][3];
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) { xa[a][k] = xa9[3 * a + k]; xb[a][k] = xb9[3 * a + k]; }
+    return o_strain_face_toi(xa, xb, ir4, limit, max_t);
+}
+SHIM void orc_svd32(const float *F6 /* row-major 3x2 */, float *U6, float *S2, float *Vt4) {
+    float F[3][2];
+    o_svd32 s;
+    for (int r = 0; r < 3; ++r) { F[r][0] = F6[2 * r]; F[r][1] = F6[2 * r + 1]; }
+    o_jacobi_svd32(F, &s);
+    for (int r = 0; r < 3; ++r) { U6[2 * r] = s.U[r][0]; U6[2 * r + 1] = s.U[r][1]; }
+    S2[0] = s.S[0]; S2[1] = s.S[1];
+    Vt4[0] = s.Vt[0][0]; Vt4[1] = s.Vt[0][1]; Vt4[2] = s.Vt[1][0]; Vt4[3] = s.Vt[1][1];
+}

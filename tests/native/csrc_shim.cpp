@@ -6,6 +6,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_strain.cuh"
 using namespace ppf;
 #define SHIM extern "C" __attribute__((visibility("default")))
 static V3 v(const float *p) { return mk(p[0], p[1], p[2]); }
@@ -39,4 +40,31 @@ SHIM void orc_hinge(const float *x12, float rest_angle, float *f12, float *H144)
     hinge_force_hessian(X, rest_angle, he);
     for (int a = 0; a < 4; ++a) { f12[3 * a] = he.f[a].x; f12[3 * a + 1] = he.f[a].y; f12[3 * a + 2] = he.f[a].z; }
     for (int i = 0; i < 144; ++i) H144[i] = he.H[i];
+}
+
+SHIM int orc_strain_face(const float *xe9, const float *xc9, const float *ir4, float strainlimit, float limit, float mass, const float *Hel81,
+                         float eig_eps, float *f9, float *H81) {
+    V3 xe[3], xc[3];
+    M3 Hel[3][3];
+    for (int a = 0; a < 3; ++a) { xe[a] = v(xe9 + 3 * a); xc[a] = v(xc9 + 3 * a); }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int e = 0; e < 9; ++e) Hel[a][b].m[e] = Hel81[(a * 3 + b) * 9 + e];
+    StrainFace sf;
+    if (!strain_face(xe, xc, ir4, strainlimit, limit, mass, Hel, eig_eps, sf)) return 0;
+    for (int a = 0; a < 3; ++a) { f9[3 * a] = sf.f[a].x; f9[3 * a + 1] = sf.f[a].y; f9[3 * a + 2] = sf.f[a].z; }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int e = 0; e < 9; ++e) H81[(a * 3 + b) * 9 + e] = sf.H[a][b].m[e];
+    return 1;
+}
+SHIM float orc_strain_toi(const float *xa9, const float *xb9, const float *ir4, float limit, float max_t) {
+    V3 xa[3], xb[3];
+    for (int a = 0; a < 3; ++a) { xa[a] = v(xa9 + 3 * a); xb[a] = v(xb9 + 3 * a); }
+    return strain_face_toi(xa, xb, ir4, limit, max_t);
+}
+SHIM void orc_svd32(const float *F6, float *U6, float *S2, float *Vt4) {
+    float F[3][2];
+    Svd32 s;
+    for (int r = 0; r < 3; ++r) { F[r][0] = F6[2 * r]; F[r][1] = F6[2 * r + 1]; }
+    jacobi_svd32(F, s);
+    for (int r = 0; r < 3; ++r) { U6[2 * r] = s.U[r][0]; U6[2 * r + 1] = s.U[r][1]; }
+    S2[0] = s.S[0]; S2[1] = s.S[1];
+    Vt4[0] = s.Vt[0][0]; Vt4[1] = s.Vt[0][1]; Vt4[2] = s.Vt[1][0]; Vt4[3] = s.Vt[1][1];
 }

@@ -152,6 +152,87 @@ def test_hinge_matches_reference(orc, gold):
     assert worst_f < 1e-5 and worst_H < 1e-4, (worst_f, worst_H)
 
 
+def _strain_case(rng, stretch):
+    """a rest triangle in the plane, deformed by a random rotation times a stretch"""
+    rest = np.array([[0.0, 0.0], [1.0, 0.1], [0.2, 0.9]]) * 0.05
+    Dm = np.stack([rest[1] - rest[0], rest[2] - rest[0]], axis=1)
+    ir = np.linalg.inv(Dm)                                    # (row, col)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    Fm = q[:, :2] @ np.diag(stretch) @ np.array([[np.cos(0.3), -np.sin(0.3)], [np.sin(0.3), np.cos(0.3)]])
+    x0 = rng.uniform(-1, 1, 3)
+    x = np.stack([x0, x0 + Fm @ Dm[:, 0], x0 + Fm @ Dm[:, 1]]).astype(np.float32)
+    ir32 = np.array([ir[0, 0], ir[1, 0], ir[0, 1], ir[1, 1]], np.float32)   # column-major like the ABI
+    return x, ir32
+
+
+def test_strain_limit_svd_and_gradient(orc):
+    """Jacobi SVD reconstructs F; the strain-limit force is the gradient of the barrier energy on the
+    singular values (checked against float64 finite differences of numpy's SVD); the Hessian is symmetric PSD."""
+    orc.orc_strain_toi.restype = C.c_float
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        F = rng.normal(size=(3, 2)).astype(np.float32)
+        U = np.zeros(6, np.float32); S = np.zeros(2, np.float32); Vt = np.zeros(4, np.float32)
+        orc.orc_svd32(fp(F), fp(U), fp(S), fp(Vt))
+        rec = U.reshape(3, 2) @ np.diag(S) @ Vt.reshape(2, 2)
+        assert np.abs(rec - F).max() < 5e-6 and S[0] <= S[1]
+        assert np.allclose(S, np.linalg.svd(F.astype(np.float64), compute_uv=False)[::-1], atol=5e-6)
+    strainlimit = 0.05
+    worst = 0.0
+    for trial in range(40):
+        x, ir = _strain_case(rng, [1.0 + rng.uniform(0.002, 0.03), 1.0 + rng.uniform(-0.02, 0.04)])
+        Hel = np.zeros(81, np.float32)
+        f = np.zeros(9, np.float32); H = np.zeros(81, np.float32)
+        on = orc.orc_strain_face(fp(x), fp(x), fp(ir), C.c_float(strainlimit), C.c_float(strainlimit), C.c_float(2.0), fp(Hel), C.c_float(1e-2), fp(f), fp(H))
+        assert on == 1
+        irm = np.array([[ir[0], ir[2]], [ir[1], ir[3]]], np.float64)
+
+        def energy(xx):
+            Fm = np.stack([xx[1] - xx[0], xx[2] - xx[0]], axis=1) @ irm
+            sv = np.linalg.svd(Fm, compute_uv=False) - 1.0
+            e = 0.0
+            for g in sv:
+                if g > 0:
+                    y = strainlimit - g                       # cubic barrier energy (cubic.hpp): -2/(3 ghat) (y - ghat)^3 for y < ghat
+                    e += -2.0 * (y - strainlimit) ** 3 / (3.0 * strainlimit)
+            return e
+
+        x64 = x.astype(np.float64)
+        Fm = np.stack([x64[1] - x64[0], x64[2] - x64[0]], axis=1) @ irm
+        smax = np.linalg.svd(Fm, compute_uv=False).max() - 1.0
+        stiffness = 2.0 / (strainlimit - smax) ** 2            # elastic blocks are zero here: mass / d^2
+        gnum = np.zeros((3, 3))
+        h = 1e-6
+        for a in range(3):
+            for k in range(3):
+                xp = x64.copy(); xm = x64.copy(); xp[a, k] += h; xm[a, k] -= h
+                gnum[a, k] = (energy(xp) - energy(xm)) / (2 * h)
+        scale = max(np.abs(gnum).max() * stiffness, 1e-9)
+        worst = max(worst, np.abs(f.reshape(3, 3) - stiffness * gnum).max() / scale)
+        Hm = np.zeros((9, 9))
+        for a in range(3):
+            for b in range(3):
+                Hm[3 * a:3 * a + 3, 3 * b:3 * b + 3] = H[(a * 3 + b) * 9:(a * 3 + b) * 9 + 9].reshape(3, 3).T
+        assert np.abs(Hm - Hm.T).max() <= 1e-4 * np.abs(Hm).max()
+        assert np.linalg.eigvalsh(0.5 * (Hm + Hm.T)).min() >= -1e-4 * np.abs(Hm).max()
+    assert worst < 2e-3, worst
+
+
+def test_strain_limit_line_search(orc):
+    orc.orc_strain_toi.restype = C.c_float
+    rng = np.random.default_rng(12)
+    for trial in range(40):
+        xa, ir = _strain_case(rng, [1.0, 1.0])
+        grow = 1.0 + rng.uniform(0.0, 0.2)
+        xb = (xa[0] + (xa - xa[0]) * grow).astype(np.float32)   # uniform scaling about vertex 0: strain = t (grow - 1)
+        limit = 0.05
+        t = orc.orc_strain_toi(fp(xa), fp(xb), fp(ir), C.c_float(limit), C.c_float(1.25))
+        if 1.25 * (grow - 1.0) < limit * 0.999:
+            assert t == np.float32(1.25)
+        elif 1.25 * (grow - 1.0) > limit * 1.001:
+            assert abs(t * (grow - 1.0) - limit) < 2e-4 and t * (grow - 1.0) <= limit * (1 + 1e-5)
+
+
 def test_oracle_agrees_with_live_reference_headers(orc, gold):
     """When oracle/_ref/libref_host.so is present (build container), cross-check fresh random cases too."""
     path = os.path.join(REPO, "oracle", "_ref", "libref_host.so")
