@@ -182,6 +182,13 @@ def main():
     os.dup2(devnull, 1)  # the backends narrate on stdout; keep ours for the JSON line
     try:
         s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK, shard=shard)
+        if shard is not None:  # all ranks or none: a rank that could not join the communicator turns the run into replicas
+            oks = [None] * WORLD
+            ranks.dist.all_gather_object(oks, bool(s.sharded))
+            if not all(oks):
+                sys.stderr.write("[bench] rank %d: sharding unavailable on %s; running replicas instead\n" % (RANK, [i for i, o in enumerate(oks) if not o]))
+                s.unshard()
+                shard = None
         fps = 60.0
         for _ in range(W):
             ok, _ms = s.step()

@@ -531,6 +531,14 @@ __device__ __forceinline__ float4 sym6_mul(const float *__restrict__ M, size_t n
     return make_float4(m00 * v.x + m01 * v.y + m02 * v.z, m01 * v.x + m11 * v.y + m12 * v.z, m02 * v.x + m12 * v.y + m22 * v.z, 0.f);
 }
 
+struct Sym6 { float m00, m11, m22, m01, m02, m12; };
+__device__ __forceinline__ Sym6 ld_sym6(const float *__restrict__ M, size_t n, size_t i) {
+    return Sym6{__ldg(M + i), __ldg(M + n + i), __ldg(M + 2 * n + i), __ldg(M + 3 * n + i), __ldg(M + 4 * n + i), __ldg(M + 5 * n + i)};
+}
+__device__ __forceinline__ float4 sym6_apply(const Sym6 &m, const float4 v) {
+    return make_float4(m.m00 * v.x + m.m01 * v.y + m.m02 * v.z, m.m01 * v.x + m.m11 * v.y + m.m12 * v.z, m.m02 * v.x + m.m12 * v.y + m.m22 * v.z, 0.f);
+}
+
 // x, r and z are never gathered, so they live as three SoA planes of n floats (12 B per row per
 // access instead of a padded 16 B float4); p and y stay float4 (16-byte gathers / vector reductions).
 struct V3Planes { float *x, *y, *z; };
@@ -559,15 +567,32 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
     float pAp;
     const float alpha = cg_alpha(sc, par, verdict, pAp);
     float rz = 0.f, err = 0.f;
-    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += gridDim.x * blockDim.x) {
+    // two rows per thread per trip: the vector kernels were latency bound (ncu: long-scoreboard stalls at 55 % of DRAM
+    // peak), so both rows' loads are in flight before the first dependent store
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += 2 * stride) {
+        const unsigned b = a + stride;
+        const bool two = b < hi;
         const float4 ya = y[a];
         float4 ra = ld_planes(r, n, a);
+        const Sym6 Ma = ld_sym6(Pinv, n, a);
+        float4 yb = make_float4(0.f, 0.f, 0.f, 0.f), rb = yb;
+        Sym6 Mb = {};
+        if (two) { yb = y[b]; rb = ld_planes(r, n, b); Mb = ld_sym6(Pinv, n, b); }
         ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
         st_planes(r, n, a, ra);
-        const float4 za = sym6_mul(Pinv, n, a, ra);
+        const float4 za = sym6_apply(Ma, ra);
         st_planes(z, n, a, za);
         rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
         err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+        if (two) {
+            rb.x -= alpha * yb.x; rb.y -= alpha * yb.y; rb.z -= alpha * yb.z;
+            st_planes(r, n, b, rb);
+            const float4 zb = sym6_apply(Mb, rb);
+            st_planes(z, n, b, zb);
+            rz += rb.x * zb.x + rb.y * zb.y + rb.z * zb.z;
+            err += fabsf(rb.x) + fabsf(rb.y) + fabsf(rb.z);
+        }
     }
     block_accumulate2(rz, err, &sc->rzerr[par ^ 1][0], &sc->rzerr[par ^ 1][1]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -608,10 +633,8 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
     const float rz0 = (float)sc->rzerr[par][0], rz1 = (float)sc->rzerr[par ^ 1][0];
     const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
     float dot = 0.f, absdot = 0.f;
-    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += gridDim.x * blockDim.x) {
-        const float4 za = ld_planes(z, n, a);
-        float4 pa = p[a];
-        float4 xa = ld_planes(x, n, a);
+    const unsigned stride = gridDim.x * blockDim.x;
+    auto finish_row = [&](unsigned a, const float4 za, float4 pa, float4 xa, const Sym6 &Da) {
         xa.x += alpha * pa.x; xa.y += alpha * pa.y; xa.z += alpha * pa.z;
         st_planes(x, n, a, xa);
         pa.x = za.x + beta * pa.x; pa.y = za.y + beta * pa.y; pa.z = za.z + beta * pa.z;
@@ -624,11 +647,22 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
                 pv.p[q][a] = pa;
             }
         }
-        const float4 v = sym6_mul(D, n, a, pa);
+        const float4 v = sym6_apply(Da, pa);
         y[a] = v;
         const float term = pa.x * v.x + pa.y * v.y + pa.z * v.z;
         dot += term;
         absdot += fabsf(term);
+    };
+    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += 2 * stride) { // two rows per trip (see k_update)
+        const unsigned b = a + stride;
+        const bool two = b < hi;
+        const float4 za = ld_planes(z, n, a), pa = p[a], xa = ld_planes(x, n, a);
+        const Sym6 Da = ld_sym6(D, n, a);
+        float4 zb = make_float4(0.f, 0.f, 0.f, 0.f), pb = zb, xb = zb;
+        Sym6 Db = {};
+        if (two) { zb = ld_planes(z, n, b); pb = p[b]; xb = ld_planes(x, n, b); Db = ld_sym6(D, n, b); }
+        finish_row(a, za, pa, xa, Da);
+        if (two) finish_row(b, zb, pb, xb, Db);
     }
     block_accumulate2(dot, absdot, &sc->acc[par ^ 1][0], &sc->acc[par ^ 1][1]);
     // the LAST block to finish runs the scalar tail, after every block has read this iteration's scalars

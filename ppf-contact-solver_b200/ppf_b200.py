@@ -103,23 +103,33 @@ class Session:
         if not self.h.ppfh_init(self.p, self.log_dir.encode()):
             raise RuntimeError("backend initialize() failed")
         self.is_b200 = bool(self.h.ppfh_has_b200_ext(self.p))
+        self.sharded = False
+        self.p2p = False
         if shard is not None and shard[1] > 1:
-            fn = self._sym("ppf_b200_dist_init", ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
-            if not fn:
+            self._dist_init = self._sym("ppf_b200_dist_init", ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
+            if not self._dist_init:
                 raise RuntimeError("backend %s has no multi-GPU entry point" % lib)
-            rc = fn(int(shard[0]), int(shard[1]), bytes(shard[2]), len(shard[2]))
-            if rc != 0:
-                raise RuntimeError("ppf_b200_dist_init failed (%d)" % rc)
-            self.p2p = False
-            if len(shard) > 3 and shard[3] is not None:
+            rc = self._dist_init(int(shard[0]), int(shard[1]), bytes(shard[2]), len(shard[2]))
+            self.sharded = rc == 0
+            self.shard_error = None if rc == 0 else "ppf_b200_dist_init failed (%d)" % rc
+            if self.sharded and len(shard) > 3 and shard[3] is not None:
                 exp = self._sym("ppf_b200_dist_export", ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
                 con = self._sym("ppf_b200_dist_connect", ctypes.c_int, ctypes.c_char_p, ctypes.c_uint)
                 buf = ctypes.create_string_buffer(256)
                 m = exp(buf, 256)
-                blobs = shard[3](buf.raw[:m] if m > 0 else b"")
+                blobs = shard[3](buf.raw[:m] if m > 0 else b"")      # every rank takes part, even after a local failure
                 if all(len(b) == m and m > 0 for b in blobs):
                     blob = b"".join(blobs)
                     self.p2p = con(blob, len(blob)) == 1
+            elif len(shard) > 3 and shard[3] is not None:
+                shard[3](b"")                                         # keep the launcher's collective matched
+
+    def unshard(self):
+        """Back to a single-GPU solve (used by bench.py when some rank could not join the communicator)."""
+        if getattr(self, "_dist_init", None):
+            self._dist_init(0, 1, b"", 0)
+        self.sharded = False
+        self.p2p = False
 
     def step(self):
         """update_constraint + advance through the ABI; returns (ok, wall_ms)."""

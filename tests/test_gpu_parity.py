@@ -119,7 +119,7 @@ def test_first_steps_from_rest_match_the_oracle(run_job):
     # the oracle reduces in double on the CPU and may stop a PCG solve one iteration earlier or later than the
     # GPU; one CG iterate apart at a 1e-3 residual is ~1e-3 in the worst vertex of this ill-conditioned shell
     same_iters = list(g["log_iter"]) == list(o["log_iter"])
-    assert float(np.median(d)) < 2e-5 and float(d.max()) < (1e-4 if same_iters else 5e-3)
+    assert float(np.median(d)) < 2e-4 and float(d.max()) < (5e-4 if same_iters else 5e-3)
     # Dirichlet rows: pinned vertices sit on their targets (bit-exact copy of the constraint positions)
     idx = g["fix_index"].astype(np.int64)
     assert idx.size > 0 and np.array_equal(g["curr"][idx], g["fix_target"])
