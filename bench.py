@@ -42,7 +42,11 @@ if WORLD > 1:  # one process per GPU; all GPUs stay visible so that NCCL / peer 
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs.  NVML in-process (nvidia_ml_py) rather
+    than spawning nvidia-smi: a forked nvidia-smi every 200 ms takes driver locks and was measured to slow the
+    timed steps themselves; falls back to nvidia-smi at a 1 s period when NVML cannot be imported."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self):
         super().__init__(daemon=True)
@@ -50,14 +54,30 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.index = int(os.environ.get("PPF_B200_DEVICE", os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0] or 0))
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(get_reasons(h))
+            for name, bit in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            time.sleep(0.25)
+        pynvml.nvmlShutdown()
+
+    def _run_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        idx = os.environ.get("PPF_B200_DEVICE", os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", idx, "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 self.samples.append(float(f[0]))
                 self.max_mhz = float(f[1])
@@ -66,7 +86,13 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(1.0)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def result(self):
         s = sorted(self.samples)

@@ -22,6 +22,7 @@
 #include "math_contact.cuh"
 #include "math_distance.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
@@ -555,7 +556,6 @@ static Ctx make_ctx(State &s, const PpfParamSet &prm) {
 }
 
 static DBuf<unsigned char> g_cub_tmp;
-static DBuf<unsigned> g_row_len;
 
 // broad + narrow phase at eval_x: fills s.pairs[0..3] (unsorted) and returns the four counts
 static std::vector<uint2> sorted_pairs_host(State &s, int k) {
@@ -631,10 +631,17 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
     cudaStream_t q = s.stream;
     max_nnz_row = 0;
     dyn_consumed = 0.0f;
+    // PPF_B200_CONTACT_PROF=1: wall-clock split of this call (stream drained at the marks), diagnostic only
+    static const bool prof = getenv("PPF_B200_CONTACT_PROF") != nullptr;
+    auto now = [&] { if (prof) cudaStreamSynchronize(q); return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point t0, std::chrono::steady_clock::time_point t1) { return std::chrono::duration<double, std::milli>(t1 - t0).count(); };
+    const auto t0 = now();
+    const bool reused = s.cand_cover_eval;
     // ---- detect ----
     unsigned hc[4];
     const unsigned total = detect_contacts(s, prm, hc);
     Ctx c = make_ctx(s, prm);
+    const auto t1 = now();
 
     // ---- dynamic pattern: sorted unique keys outside the fixed pattern ----
     unsigned shift = 1;
@@ -672,6 +679,7 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
     LAUNCH_COUNT(1);
     dyn_consumed = (float)nnz / (float)s.dyn_cap;
 
+    const auto t2 = now();
     // ---- fill ----
     c = make_ctx(s, prm); // buffers may have been re-allocated
     if (hc[0]) k_fill<0><<<div_up(hc[0], 128), 128, 0, q>>>(c, s.pairs[0].pairs.p, hc[0]);
@@ -680,6 +688,12 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
     if (hc[3]) k_fill<3><<<div_up(hc[3], 128), 128, 0, q>>>(c, s.pairs[3].pairs.p, hc[3]);
     LAUNCH_COUNT(4);
     s.dyn_valid = true;
+    if (prof) {
+        const auto t3 = now();
+        fprintf(stderr, "[contact-prof] detect %.2f ms (reuse %d; candidates %u %u %u %u -> pairs %u %u %u %u)  pattern %.2f ms (%u keys -> %u blocks)  fill %.2f ms\n",
+                ms_since(t0, t1), (int)reused, s.cand[0].count, s.cand[1].count, s.cand[2].count, s.cand[3].count, hc[0], hc[1], hc[2], hc[3], ms_since(t1, t2), nkeys, nnz,
+                ms_since(t2, t3));
+    }
     return total;
 }
 
@@ -807,7 +821,6 @@ __global__ void __launch_bounds__(128) k_ccd_ee(CcdCtx c, const uint2 *cand, uns
     ccd_commit(c, result, ov, e0.x, e1.x, 1u);
 }
 
-static unsigned g_last_overlap[4] = {0, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
 
 float contact_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap) {
     cudaStream_t q = s.stream;
@@ -834,7 +847,6 @@ float contact_line_search(State &s, const float4 *x0, const float4 *x1, const Pp
     float toi;
     memcpy(&toi, &h[0], sizeof(float));
     overlap = h[1] != 0u;
-    for (int k = 0; k < 4; ++k) g_last_overlap[k] = h[1 + k];
     return toi / prm.line_search_max_t;
 }
 

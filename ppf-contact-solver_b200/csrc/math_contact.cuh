@@ -36,45 +36,6 @@ PPF_HD M3 barrier_edge_hessian(const V3 &e, float ghat, float offset) {
     return o;
 }
 
-// kappa = w^T L w, L(ii,jj) = Hel(ii,jj) + [ii==jj] (m_ii / g^2) I, w = normalize([value_ii * e]).
-// `blk` holds the N*N gathered elastic blocks Hel(index[ii], index[jj]) (zero where absent).
-template <int N> PPF_HD float contact_stiffness(const float *value, const float *mass, const M3 *blk, const V3 &e, float offset) {
-    const float nrm = norm(e);
-    const float g = nrm - offset;
-    const float sqr_x = g * g;
-    float m_max = 0.0f;
-    for (int ii = 0; ii < N; ++ii)
-        if (mass[ii] > m_max) m_max = mass[ii];
-    float w[3 * N];
-    for (int ii = 0; ii < N; ++ii) {
-        const float val = value[ii];
-        w[3 * ii + 0] = val * e.x; w[3 * ii + 1] = val * e.y; w[3 * ii + 2] = val * e.z;
-    }
-    float acc = 0.0f;
-    for (int i = 0; i < 3 * N; ++i) acc = acc + w[i] * w[i];
-    const float wn = sqrtf(acc);
-    if (wn > 0.0f)
-        for (int i = 0; i < 3 * N; ++i) w[i] = w[i] / wn;
-    // r = L * w accumulated column by column (smat.hpp operator*), then r . w
-    float r[3 * N];
-    for (int i = 0; i < 3 * N; ++i) r[i] = 0.0f;
-    for (int jj = 0; jj < N; ++jj)
-        for (int kc = 0; kc < 3; ++kc) {
-            const float bkc = w[3 * jj + kc];
-            for (int ii = 0; ii < N; ++ii) {
-                const float m_ii = mass[ii] > 0.0f ? mass[ii] : m_max;
-                for (int kr = 0; kr < 3; ++kr) {
-                    float a = 0.0f + blk[ii * N + jj].m[kr + kc * 3];
-                    if (ii == jj) a = a + (m_ii / sqr_x) * (kr == kc ? 1.0f : 0.0f);
-                    r[3 * ii + kr] = r[3 * ii + kr] + a * bkc;
-                }
-            }
-        }
-    float kappa = 0.0f;
-    for (int i = 0; i < 3 * N; ++i) kappa = kappa + r[i] * w[i];
-    return kappa;
-}
-
 struct FrictionOut {
     V3 grad;
     M3 hess;
