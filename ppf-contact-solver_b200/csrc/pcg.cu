@@ -46,8 +46,11 @@ struct CgScalars {                 // device-resident control block
     float tol;
     int max_iter;
     float last_resid;
-    unsigned done_counter;
+    unsigned done_counter;         // k_direction's last-CTA detection
+    unsigned done_spmv, done_update; // same for the kernels that publish a partial sum to the peers
 };
+
+struct ChunkDesc { unsigned base, first, end; }; // stage blocks [base, base + SPMV_CHUNK), use those in [first, end)
 
 struct PackedMatrix {
     unsigned n = 0;
@@ -73,6 +76,7 @@ struct PackedMatrix {
     unsigned n_foreign_fixed = 0;    // foreign blocks of the fixed segment (see Part)
     DBuf<unsigned> foreign;          // list positions of this rank's foreign blocks: fixed ones first, then this solve's dynamic ones
     DBuf<unsigned> mask_fixed, mask; // per row: bit q set = rank q reads p[row] (fixed part / this solve)
+    DBuf<ChunkDesc> chunks;          // chunk list of this rank's SpMV launch (several ranks only)
     size_t n_pad = 0;                // rpr * world
     bool ready = false;
 };
@@ -156,7 +160,8 @@ static void pcg_init(State &s) {
 
 // make room for nnz_d dynamic blocks behind the fixed ones (plane stride may change)
 static void pcg_reserve(State &s, unsigned nnz_d) {
-    const size_t need = size_t(P.nnz_f) + nnz_d;
+    // several ranks: room for the chunk-aligned copies of the foreign blocks behind the list (at most every crossing block)
+    const size_t need = size_t(P.nnz_f) + nnz_d + (g_dist.on() ? size_t(P.n_foreign_fixed) + nnz_d + 2 * SPMV_CHUNK : 0);
     if (need <= P.cap) return;
     const size_t want = round_cap(need + need / 4 + 1024);
     P.row.reserve_keep(want, s.stream);
@@ -430,25 +435,81 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // Blocks [k_first, nnz) of the list are processed (staging starts at k_begin <= k_first, a multiple of SPMV_CHUNK); results are
 // accumulated only into rows [row_lo, row_hi) -- the rows this rank owns (everything on one GPU).  A
 // block's share of p.Ap is counted by the owner of its row.
-__global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned k_begin, unsigned k_first, unsigned nnz, unsigned row_lo, unsigned row_hi,
-                                                          const unsigned *__restrict__ row, const unsigned *__restrict__ col,
-                                                          const float *__restrict__ val, size_t plane, const float4 *__restrict__ p,
-                                                          float4 *__restrict__ y, CgScalars *sc, int with_dots) {
+// Wait until a peer has raised *flag to at least e.  A rank that died or took a different branch must not hang
+// the GPU: after 2 s of wall time the wait gives up and the solve ends with ST_PEER_TIMEOUT on this rank.
+__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long e) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (*(volatile const unsigned long long *)flag < e) {
+        if ((++spins & 0xFFFFu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            else if (now - t0 > 2000000000ull) return false;
+        }
+    }
+    return true;
+}
+
+// ---- 2-double sums over the ranks through peer mailboxes, fused into the PCG kernels (dist.hpp) ----
+// The LAST CTA of the producing kernel publishes this rank's partial to every rank's mailbox; every CTA of the
+// consuming kernel waits for all mailboxes and adds them in rank order -- the same bits on every rank, no extra
+// launch.  Mailboxes are double-buffered by iteration parity; a rank can be at most one reduction ahead of another.
+__device__ __forceinline__ void publish_partial(const PeerView &pv, CgScalars *sc, int slot, int parity) {
+    volatile double *loc = slot == 0 ? sc->acc[parity] : sc->rzerr[parity];
+    const double v0 = loc[0], v1 = loc[1];
+    CommBuf *mine = pv.comm[pv.rank];
+    const unsigned long long e = ++mine->red_epoch[slot];
+    for (int q = 0; q < pv.world; ++q) {
+        Mail *m = &pv.comm[q]->mail[slot][parity][pv.rank];
+        ((volatile double *)m->v)[0] = v0;
+        ((volatile double *)m->v)[1] = v1;
+    }
+    __threadfence_system();
+    for (int q = 0; q < pv.world; ++q) *(volatile unsigned long long *)&pv.comm[q]->mail[slot][parity][pv.rank].epoch = e;
+}
+// one thread per CTA; false = a peer did not answer (ST_PEER_TIMEOUT)
+__device__ __forceinline__ bool gather_sum(const PeerView &pv, int slot, int parity, double out[2]) {
+    const CommBuf *mine = pv.comm[pv.rank];
+    const unsigned long long e = *(volatile const unsigned long long *)&mine->red_epoch[slot];
+    bool ok = true;
+    for (int q = 0; q < pv.world; ++q) ok = spin_until(&mine->mail[slot][parity][q].epoch, e) && ok;
+    // no fence here: the writer ordered data before flag with a system fence, the mailbox lives in THIS device's
+    // memory and is read with volatile (L1-bypassing) loads.  A system fence per CTA cost ~40 us per kernel.
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < pv.world; ++q) {
+        a += ((volatile const double *)mine->mail[slot][parity][q].v)[0];
+        b += ((volatile const double *)mine->mail[slot][parity][q].v)[1];
+    }
+    out[0] = a; out[1] = b;
+    return ok;
+}
+
+// With a chunk list (several ranks) the launch walks the listed chunks instead of one contiguous range: this rank's
+// own-row blocks of the fixed and of the dynamic segment plus the copies of its foreign blocks, all in ONE launch.
+// publish != 0 (peer memory): the last CTA sends this rank's partial p.Ap | sum|terms| to every peer's mailbox.
+
+__global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__restrict__ chunks, unsigned n_desc, unsigned k_begin, unsigned k_first,
+                                                          unsigned nnz, unsigned row_lo, unsigned row_hi, const unsigned *__restrict__ row,
+                                                          const unsigned *__restrict__ col, const float *__restrict__ val, size_t plane,
+                                                          const float4 *__restrict__ p, float4 *__restrict__ y, CgScalars *sc, int with_dots,
+                                                          PeerView pv, int publish) {
     if (with_dots && sc->status != ST_RUNNING) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + size_t(SPMV_STAGES) * SPMV_STAGE_BYTES);
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const unsigned c_begin = k_begin / SPMV_CHUNK;
-    const unsigned n_chunks = (nnz + SPMV_CHUNK - 1) / SPMV_CHUNK;
+    const unsigned n_list = chunks ? n_desc : (nnz + SPMV_CHUNK - 1) / SPMV_CHUNK - c_begin;
+    auto desc = [&](unsigned ci) { return chunks ? chunks[ci] : ChunkDesc{(c_begin + ci) * SPMV_CHUNK, k_first, nnz}; };
     if (tid == 0) {
         for (int st = 0; st < SPMV_STAGES; ++st) mbar_init(&full[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto fill = [&](int st, unsigned chunk) {
+    auto fill = [&](int st, unsigned ci) {
         unsigned *dst = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
-        const size_t base = size_t(chunk) * SPMV_CHUNK;
+        const size_t base = desc(ci).base;
         mbar_expect_tx(&full[st], SPMV_STAGE_BYTES);
         bulk_g2s(dst, row + base, SPMV_CHUNK * 4, &full[st]);
         bulk_g2s(dst + SPMV_CHUNK, col + base, SPMV_CHUNK * 4, &full[st]);
@@ -457,12 +518,13 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned k_begin, uns
     };
     if (tid == 0)
         for (int st = 0; st < SPMV_STAGES; ++st) {
-            const unsigned c = c_begin + blockIdx.x + unsigned(st) * gridDim.x;
-            if (c < n_chunks) fill(st, c);
+            const unsigned c = blockIdx.x + unsigned(st) * gridDim.x;
+            if (c < n_list) fill(st, c);
         }
     float dot = 0.f, absdot = 0.f;
     unsigned it = 0;
-    for (unsigned chunk = c_begin + blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    for (unsigned chunk = blockIdx.x; chunk < n_list; chunk += gridDim.x, ++it) {
+        const ChunkDesc cd = desc(chunk);
         const int st = int(it % SPMV_STAGES);
         mbar_wait(&full[st], (it / SPMV_STAGES) & 1u);
         const unsigned *sm = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
@@ -479,14 +541,14 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned k_begin, uns
         __syncthreads(); // every thread holds its blocks in registers: the stage can be refilled
         if (tid == 0) {
             const unsigned nc = chunk + unsigned(SPMV_STAGES) * gridDim.x;
-            if (nc < n_chunks) fill(st, nc);
+            if (nc < n_list) fill(st, nc);
         }
-        const size_t k0 = size_t(chunk) * SPMV_CHUNK;
+        const size_t k0 = cd.base;
         bool on[SPMV_U];
         float4 pa[SPMV_U], pb[SPMV_U];
 #pragma unroll
         for (int u = 0; u < SPMV_U; ++u) {
-            on[u] = k0 + u * SPMV_T + tid < nnz && k0 + u * SPMV_T + tid >= k_first;
+            on[u] = k0 + u * SPMV_T + tid < cd.end && k0 + u * SPMV_T + tid >= cd.first;
             if (!on[u]) { a[u] = 0xFFFFFFFFu; b[u] = 0; }
             pa[u] = on[u] ? p[a[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
             pb[u] = on[u] ? p[b[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -523,6 +585,13 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(unsigned k_begin, uns
     if (!with_dots) return;
     const int par = sc->iter & 1;
     block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
+    if (publish && tid == 0) { // thread 0 issued this CTA's atomics above
+        __threadfence();
+        if (atomicAdd(&sc->done_spmv, 1u) == gridDim.x - 1) {
+            sc->done_spmv = 0;
+            publish_partial(pv, sc, 0, par);
+        }
+    }
 }
 
 __device__ __forceinline__ float4 sym6_mul(const float *__restrict__ M, size_t n, size_t i, const float4 v) {
@@ -547,10 +616,10 @@ __device__ __forceinline__ void st_planes(float *__restrict__ v, size_t n, size_
 
 // step length of the current iteration from the device-resident scalars (reference: cg_fused_update_kernel,
 // solver.cu:431-514, and its curvature-noise verdict 66-114).  verdict: 0 ok, 1 truncate, 2 fatal
-__device__ __forceinline__ float cg_alpha(const CgScalars *sc, int par, int &verdict, float &pAp_out) {
-    const float pAp = (float)sc->acc[par][0];
-    const float noise = CG_NOISE_SLACK * CG_FLOAT_EPS * (float)sc->acc[par][1];
-    const float rz0 = (float)sc->rzerr[par][0];
+__device__ __forceinline__ float cg_alpha(double pap_sum, double abs_sum, double rz_sum, int &verdict, float &pAp_out) {
+    const float pAp = (float)pap_sum;
+    const float noise = CG_NOISE_SLACK * CG_FLOAT_EPS * (float)abs_sum;
+    const float rz0 = (float)rz_sum;
     pAp_out = pAp;
     verdict = 0;
     if (pAp > noise) return rz0 / pAp;
@@ -560,12 +629,22 @@ __device__ __forceinline__ float cg_alpha(const CgScalars *sc, int par, int &ver
 
 // r -= alpha A p;  z = Pinv r;  r.z and |r|_1.   (x += alpha p is applied by k_direction, which reads p anyway)
 __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, unsigned hi, const float4 *__restrict__ y, float *__restrict__ r,
-                                                      float *__restrict__ z, const float *__restrict__ Pinv, CgScalars *sc) {
+                                                      float *__restrict__ z, const float *__restrict__ Pinv, CgScalars *sc, PeerView pv, int fused) {
     if (sc->status != ST_RUNNING) return;
     const int par = sc->iter & 1;
+    __shared__ double s_sum[2];
+    __shared__ int s_ok;
+    if (fused) { // p.Ap | sum|terms| of all ranks, from the mailboxes the SpMV kernels filled
+        if (threadIdx.x == 0) {
+            s_ok = gather_sum(pv, 0, par, s_sum) ? 1 : 0;
+            if (blockIdx.x == 0) { sc->acc[par][0] = s_sum[0]; sc->acc[par][1] = s_sum[1]; if (!s_ok) sc->status = ST_PEER_TIMEOUT; }
+        }
+        __syncthreads();
+    } else if (threadIdx.x == 0) { s_sum[0] = sc->acc[par][0]; s_sum[1] = sc->acc[par][1]; }
+    if (!fused) __syncthreads();
     int verdict;
     float pAp;
-    const float alpha = cg_alpha(sc, par, verdict, pAp);
+    const float alpha = cg_alpha(s_sum[0], s_sum[1], sc->rzerr[par][0], verdict, pAp);
     float rz = 0.f, err = 0.f;
     // two rows per thread per trip: the vector kernels were latency bound (ncu: long-scoreboard stalls at 55 % of DRAM
     // peak), so both rows' loads are in flight before the first dependent store
@@ -600,25 +679,16 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
         sc->acc[par ^ 1][0] = 0.0; // accumulators of the NEXT iteration (direction kernel + SpMV)
         sc->acc[par ^ 1][1] = 0.0;
     }
+    if (fused && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sc->done_update, 1u) == gridDim.x - 1) {
+            sc->done_update = 0;
+            publish_partial(pv, sc, 1, par ^ 1);
+        }
+    }
 }
 
 // x += alpha p;  p = z + beta p;  y = D p (start value of the next SpMV) with the diagonal's share of p.Ap;  scalar tail
-// Wait until a peer has raised *flag to at least e.  A rank that died or took a different branch must not hang
-// the GPU: after 2 s of wall time the wait gives up and the solve ends with ST_PEER_TIMEOUT on this rank.
-__device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsigned long long e) {
-    unsigned long long t0 = 0;
-    unsigned spins = 0;
-    while (*(volatile const unsigned long long *)flag < e) {
-        if ((++spins & 0xFFFFu) == 0) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (!t0) t0 = now;
-            else if (now - t0 > 2000000000ull) return false;
-        }
-    }
-    return true;
-}
-
 // With peer memory (dist.hpp) a row that other ranks read (push_mask) is also stored straight into their p
 // arrays over NVLink, and the last CTA raises every peer's epoch flag and waits for theirs, so the next SpMV
 // finds its remote rows in place: the exchange costs no extra launch.
@@ -627,13 +697,23 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
                                                          PeerView pv, const unsigned *__restrict__ push_mask) {
     if (sc->status != ST_RUNNING) return;
     const int par = sc->iter & 1;
+    __shared__ double s_rz[2];
+    __shared__ int s_ok;
+    if (push_mask) { // r.z | |r|_1 of all ranks, from the mailboxes k_update filled (fused sums come with the peer path)
+        if (threadIdx.x == 0) {
+            s_ok = gather_sum(pv, 1, par ^ 1, s_rz) ? 1 : 0;
+            if (blockIdx.x == 0) { sc->rzerr[par ^ 1][0] = s_rz[0]; sc->rzerr[par ^ 1][1] = s_rz[1]; }
+        }
+    } else if (threadIdx.x == 0) { s_rz[0] = sc->rzerr[par ^ 1][0]; s_rz[1] = sc->rzerr[par ^ 1][1]; s_ok = 1; }
+    __syncthreads();
     int verdict;
     float pAp;
-    const float alpha = cg_alpha(sc, par, verdict, pAp);
-    const float rz0 = (float)sc->rzerr[par][0], rz1 = (float)sc->rzerr[par ^ 1][0];
+    const float alpha = cg_alpha(sc->acc[par][0], sc->acc[par][1], sc->rzerr[par][0], verdict, pAp);
+    const float rz0 = (float)sc->rzerr[par][0], rz1 = (float)s_rz[0];
     const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
     float dot = 0.f, absdot = 0.f;
     const unsigned stride = gridDim.x * blockDim.x;
+    bool pushed = false;
     auto finish_row = [&](unsigned a, const float4 za, float4 pa, float4 xa, const Sym6 &Da) {
         xa.x += alpha * pa.x; xa.y += alpha * pa.y; xa.z += alpha * pa.z;
         st_planes(x, n, a, xa);
@@ -645,6 +725,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
                 const int q = __ffs(m) - 1;
                 m &= m - 1;
                 pv.p[q][a] = pa;
+                pushed = true;
             }
         }
         const float4 v = sym6_apply(Da, pa);
@@ -667,7 +748,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
     block_accumulate2(dot, absdot, &sc->acc[par ^ 1][0], &sc->acc[par ^ 1][1]);
     // the LAST block to finish runs the scalar tail, after every block has read this iteration's scalars
     __shared__ bool last;
-    if (push_mask) __threadfence_system(); // peer stores of this thread are ordered before the flags raised below
+    if (pushed) __threadfence_system(); // peer stores of this thread are ordered before the flags raised below
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -677,7 +758,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
     if (last && threadIdx.x == 0) {
         sc->done_counter = 0;
         const int it = sc->iter + 1;
-        const double reresid = sc->rzerr[par ^ 1][1] / sc->err0;
+        const double reresid = s_rz[1] / sc->err0;
         sc->last_resid = (float)reresid;
         int st = ST_RUNNING;
         if (reresid < (double)sc->tol) st = ST_CONVERGED;
@@ -686,6 +767,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
         else if (!(rz0 > 0.0f)) st = ST_FATAL_RZ;
         else if (!isfinite(reresid)) st = ST_NONFINITE;
         else if (it >= sc->max_iter) st = ST_CAP;
+        if (!s_ok) st = ST_PEER_TIMEOUT;
         sc->rzerr[par][0] = 0.0; // slots the NEXT iteration's update kernel accumulates into
         sc->rzerr[par][1] = 0.0;
         if (push_mask && st == ST_RUNNING) { // every rank reaches the same verdict, so either all exchange or none does
@@ -696,44 +778,12 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
                 if (q != pv.rank) *(volatile unsigned long long *)&pv.comm[q]->halo_flag[pv.rank] = e;
             for (int q = 0; q < pv.world; ++q)
                 if (q != pv.rank && !spin_until(&mine->halo_flag[q], e)) st = ST_PEER_TIMEOUT;
-            __threadfence_system();
+            // the pushed rows are read by the NEXT kernel (a launch boundary orders them after this wait)
         }
         sc->iter = it;
         __threadfence();
         sc->status = st;
     }
-}
-
-// Sum of a 2-double partial over the ranks through peer mailboxes (dist.hpp): every rank stores its partial
-// into every rank's mailbox, waits for all of them, and adds them in rank order -- the same bits everywhere.
-__global__ void k_allreduce2(PeerView pv, CgScalars *sc, int slot, int parity) {
-    if (sc->status != ST_RUNNING) return; // the verdict is identical on all ranks
-    double *loc = slot == 0 ? sc->acc[parity] : sc->rzerr[parity];
-    CommBuf *mine = pv.comm[pv.rank];
-    const int lane = threadIdx.x;
-    unsigned long long e = 0;
-    if (lane == 0) e = ++mine->red_epoch[slot];
-    e = __shfl_sync(0xffffffffu, e, 0);
-    const double v0 = loc[0], v1 = loc[1];
-    double a = 0.0, b = 0.0;
-    if (lane < pv.world) {
-        Mail *m = &pv.comm[lane]->mail[slot][parity][pv.rank];
-        ((volatile double *)m->v)[0] = v0;
-        ((volatile double *)m->v)[1] = v1;
-        __threadfence_system();
-        *(volatile unsigned long long *)&m->epoch = e;
-        const Mail *in = &mine->mail[slot][parity][lane];
-        if (!spin_until(&in->epoch, e)) sc->status = ST_PEER_TIMEOUT;
-        __threadfence_system();
-        a = ((volatile const double *)in->v)[0];
-        b = ((volatile const double *)in->v)[1];
-    }
-    double sa = 0.0, sb = 0.0;
-    for (int r = 0; r < pv.world; ++r) {
-        sa += __shfl_sync(0xffffffffu, a, r);
-        sb += __shfl_sync(0xffffffffu, b, r);
-    }
-    if (lane == 0) { loc[0] = sa; loc[1] = sb; }
 }
 
 // setup: r = b, x = x0 (seed), p = x0 (SpMV input), y = D x0
@@ -793,6 +843,8 @@ struct Part {
     unsigned kf_first = 0, kf_end = 0;  // own-row blocks of the fixed segment of the list
     unsigned kd_first = 0, kd_end = 0;  // own-row blocks of the dynamic segment (absolute list positions)
     unsigned n_foreign = 0;             // entries of P.foreign
+    unsigned foreign_base = 0;          // list position of the copies of the foreign blocks (chunk aligned)
+    unsigned n_chunks = 0;              // entries of P.chunks: own fixed rows, own dynamic rows, foreign copies
     bool push = false;                  // rows are pushed to peers by k_direction (peer memory) -- else p is all-gathered
 };
 static Part R;
@@ -813,6 +865,18 @@ __global__ void k_dyn_cross(unsigned n, unsigned rpr, unsigned me, const unsigne
             if (slot < cap) foreign[slot] = base + k;
         }
     }
+}
+
+// copies of the foreign blocks to [dst0, dst0 + count) of the packed list, so that the staged kernel streams them too
+__global__ void k_copy_foreign(unsigned count, const unsigned *__restrict__ idx, unsigned *__restrict__ row, unsigned *__restrict__ col,
+                               float *__restrict__ val, size_t plane, unsigned dst0) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const unsigned k = idx[t], d = dst0 + t;
+    row[d] = row[k];
+    col[d] = col[k];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) val[size_t(e) * plane + d] = val[size_t(e) * plane + k];
 }
 
 static void pcg_partition(State &s) {
@@ -848,25 +912,26 @@ static void pcg_partition(State &s) {
         R.kd_first = P.nnz_f + h[1];
         R.kd_end = P.nnz_f + h[2];
     }
+    // copies of the foreign blocks behind the list, then ONE chunk list for the whole SpMV launch
+    R.foreign_base = (unsigned)((size_t(P.nnz_f) + P.nnz_d + SPMV_CHUNK - 1) / SPMV_CHUNK * SPMV_CHUNK);
+    if (size_t(R.foreign_base) + R.n_foreign + SPMV_CHUNK > P.cap) fatal(4, "PCG: block list capacity %zu too small for %u foreign blocks", P.cap, R.n_foreign);
+    if (R.n_foreign)
+        k_copy_foreign<<<div_up(R.n_foreign, 256), 256, 0, q>>>(R.n_foreign, P.foreign.p, P.row.p, P.col.p, P.val.p, P.cap, R.foreign_base);
+    std::vector<ChunkDesc> list;
+    auto add_range = [&](unsigned a, unsigned b) {
+        for (unsigned base = a / SPMV_CHUNK * SPMV_CHUNK; base < b; base += SPMV_CHUNK) list.push_back(ChunkDesc{base, a, b});
+    };
+    add_range(R.kf_first, R.kf_end);
+    add_range(R.kd_first, R.kd_end);
+    add_range(R.foreign_base, R.foreign_base + R.n_foreign);
+    R.n_chunks = (unsigned)list.size();
+    P.chunks.reserve(list.size() + 16);
+    if (!list.empty()) CUDA_OK(cudaMemcpyAsync(P.chunks.p, list.data(), sizeof(ChunkDesc) * list.size(), cudaMemcpyHostToDevice, q));
+    CUDA_OK(cudaStreamSynchronize(q)); // `list` is pageable host memory
     static const bool debug = getenv("PPF_B200_DIST_DEBUG") != nullptr;
     if (debug)
         fprintf(stderr, "[dist %u/%d] rows [%u,%u)  own blocks: fixed [%u,%u) of %u, dyn [%u,%u) of %u;  foreign blocks %u (%u fixed);  push %d\n", rank, g_dist.world,
                 R.lo, R.hi, R.kf_first, R.kf_end, P.nnz_f, R.kd_first - P.nnz_f, R.kd_end - P.nnz_f, P.nnz_d, R.n_foreign, P.n_foreign_fixed, (int)R.push);
-}
-
-// foreign blocks (stored under another rank's row, column owned here): y_col += B^T p_row
-__global__ void __launch_bounds__(256) k_spmv_foreign(unsigned count, const unsigned *__restrict__ idx, const unsigned *__restrict__ row,
-                                                      const unsigned *__restrict__ col, const float *__restrict__ val, size_t plane,
-                                                      const float4 *__restrict__ p, float4 *__restrict__ y, const CgScalars *sc, int with_dots) {
-    if (with_dots && sc->status != ST_RUNNING) return;
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
-        const unsigned k = idx[t];
-        const unsigned a = row[k], b = col[k];
-        const float4 pa = p[a];
-        const float h0 = val[k], h1 = val[plane + k], h2 = val[2 * plane + k], h3 = val[3 * plane + k], h4 = val[4 * plane + k];
-        const float h5 = val[5 * plane + k], h6 = val[6 * plane + k], h7 = val[7 * plane + k], h8 = val[8 * plane + k];
-        red_add_v4(y + b, h0 * pa.x + h1 * pa.y + h2 * pa.z, h3 * pa.x + h4 * pa.y + h5 * pa.z, h6 * pa.x + h7 * pa.y + h8 * pa.z);
-    }
 }
 
 static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const float4 *p, float4 *y, int with_dots) {
@@ -878,7 +943,19 @@ static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const 
     }
     const unsigned k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
     const unsigned grid = std::min(P.spmv_grid, div_up(k_end - k_begin, SPMV_CHUNK));
-    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(k_begin, k_first, k_end, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0u, k_begin, k_first, k_end, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
+                                                         PeerView{}, 0);
+}
+// several ranks: one launch over this rank's chunk list; with peer memory its last CTA publishes the partial p.Ap
+static void launch_spmv_chunks(State &s, const float4 *p, float4 *y, int with_dots, int publish) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(k_spmv_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_SMEM));
+        attr_set = true;
+    }
+    const unsigned grid = std::max(1u, std::min(P.spmv_grid, R.n_chunks));
+    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
+                                                         dist_peers(), publish);
 }
 
 static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
@@ -890,10 +967,8 @@ static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
         k_spmv<<<grid, PCG_BLOCK, 0, s.stream>>>(nnz, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
         return;
     }
+    if (g_dist.on()) { launch_spmv_chunks(s, p, y, with_dots, with_dots && R.push ? 1 : 0); return; }
     launch_spmv_range(s, R.kf_first, R.kf_end, p, y, with_dots);
-    launch_spmv_range(s, R.kd_first, R.kd_end, p, y, with_dots);
-    if (R.n_foreign)
-        k_spmv_foreign<<<std::min(P.grid, div_up(R.n_foreign, 256)), 256, 0, s.stream>>>(R.n_foreign, P.foreign.p, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
 }
 
 // NCCL fallback (no peer mapping): every rank gets every slice of p
@@ -902,20 +977,44 @@ static void exchange_p(State &s) {
     dist_allgather(P.p.p + R.lo, P.p.p, sizeof(float4) * size_t(R.rpr), s.stream);
 }
 
-static void issue_iteration(State &s, int parity) {
+static void issue_iteration(State &s, int parity, cudaEvent_t *ev = nullptr) {
+    auto mark = [&](int k) { if (ev) cudaEventRecord(ev[k], s.stream); };
     const unsigned n = P.n;
     const unsigned rows = R.hi - R.lo;
     const unsigned gv = std::max(1u, std::min(P.grid, div_up(rows, PCG_BLOCK)));
     const PeerView &pv = dist_peers();
     const bool p2p = g_dist.on() && R.push; // reductions through peer mailboxes, rows of p pushed by k_direction
+    mark(0);
     launch_spmv(s, P.p.p, P.y.p, 1);
-    if (p2p) k_allreduce2<<<1, 32, 0, s.stream>>>(pv, P.sc.p, 0, parity);
-    else dist_allreduce_sum_f64(&P.sc.p->acc[parity][0], 2, s.stream);
-    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p);
-    if (p2p) k_allreduce2<<<1, 32, 0, s.stream>>>(pv, P.sc.p, 1, parity ^ 1);
-    else dist_allreduce_sum_f64(&P.sc.p->rzerr[parity ^ 1][0], 2, s.stream);
+    mark(1);
+    if (!p2p) dist_allreduce_sum_f64(&P.sc.p->acc[parity][0], 2, s.stream); // peer path: published by the SpMV, summed by k_update
+    mark(2);
+    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p, pv, p2p ? 1 : 0);
+    mark(3);
+    if (!p2p) dist_allreduce_sum_f64(&P.sc.p->rzerr[parity ^ 1][0], 2, s.stream); // peer path: published by k_update, summed by k_direction
+    mark(4);
     k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, pv, p2p ? P.mask.p : nullptr);
     if (!p2p) exchange_p(s);
+    mark(5);
+}
+
+// PPF_B200_PCG_TUNE=1 with several ranks: 64 real iterations issued outside the graph with an event after every
+// stage, so that the cost of the exchanges (which include waiting for the slowest rank) can be read per stage
+static void pcg_profile_dist(State &s) {
+    const int iters = 64;
+    std::vector<cudaEvent_t> ev(size_t(6) * iters);
+    for (auto &e : ev) cudaEventCreate(&e);
+    for (int k = 0; k < iters; ++k) issue_iteration(s, k & 1, ev.data() + size_t(6) * k);
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 8; k < iters; ++k) {
+        for (int j = 0; j < 5; ++j) { float ms = 0; cudaEventElapsedTime(&ms, ev[size_t(6) * k + j], ev[size_t(6) * k + j + 1]); acc[j] += ms; }
+        if (k + 1 < iters) { float ms = 0; cudaEventElapsedTime(&ms, ev[size_t(6) * k + 5], ev[size_t(6) * (k + 1)]); acc[5] += ms; }
+    }
+    const double d = 1e3 / (iters - 8);
+    fprintf(stderr, "[pcg-dist %d/%d] per iteration: spmv %.1f us | sum(p.Ap) %.1f | update %.1f | sum(r.z) %.1f | direction+push %.1f | gap %.1f  (p2p %d, foreign blocks %u)\n",
+            g_dist.rank, g_dist.world, acc[0] * d, acc[1] * d, acc[2] * d, acc[3] * d, acc[4] * d, acc[5] * d, (int)R.push, R.n_foreign);
+    for (auto &e : ev) cudaEventDestroy(e);
 }
 
 // PPF_B200_PCG_TUNE=1: time the kernels of the iteration in isolation on the first packed system
@@ -951,7 +1050,7 @@ static void pcg_tune(State &s) {
     time_it("spmv register-only (legacy)", 40.0 * nnz + 24.0 * n, [&] {
         k_spmv<<<std::min(P.grid, div_up((unsigned)nnz, PCG_BLOCK)), PCG_BLOCK, 0, q>>>((unsigned)nnz, P.row.p, P.col.p, P.val.p, P.cap, P.p.p, P.y.p, P.sc.p, 1);
     });
-    time_it("update (r,z,dots)", 76.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p); });
+    time_it("update (r,z,dots)", 76.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p, PeerView{}, 0); });
     time_it("direction (x,p,y=Dp,dots)", 108.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, PeerView{}, nullptr); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
     printf("[pcg-tune] n_row=%u n_off=%.0f (fixed %u + dyn %u); SpMV algorithmic bytes (40*n_off + 60*n_row) = %.1f MB\n", n, nnz, P.nnz_f, P.nnz_d,
            (40.0 * nnz + 60.0 * n + 4.0 * (n + 1)) * 1e-6);
@@ -1026,6 +1125,10 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     }
     if (!(h.rzerr[0][0] > 0.0)) fatal(4, "PCG breakdown: r^T M^-1 r = %.6e is not positive at setup; the preconditioner is not SPD", h.rzerr[0][0]);
 
+    {
+        static int profiled = 0;
+        if (g_dist.on() && profiled < 2 && getenv("PPF_B200_PCG_TUNE")) { ++profiled; pcg_profile_dist(s); }
+    }
     // ---- iterate: batches of ITER_PER_GRAPH iterations replayed from a CUDA graph ----
     // iterations per graph launch: the host polls one status word per batch; after convergence the rest of a
     // batch early-exits (~10 us per iteration), so small systems use short batches and large ones long ones
