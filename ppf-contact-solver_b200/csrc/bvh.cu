@@ -8,6 +8,8 @@
 //   * internal boxes are produced by ONE bottom-up kernel (second-arriver-continues with an atomic
 //     flag per node) instead of one launch per tree level plus a D2H copy of the level table;
 //   * no level table / depth pass at all (the reference's compute_depths_kernel is O(n * depth)).
+//   * for the line search the leaves carry the box at x0 plus the interval of their vertices' sweep
+//     displacements (bvh_refit_relative), which the relative-motion traversal of bvh.cuh needs.
 // Only conservativeness of the boxes matters for parity (the narrow phase decides), so the tree
 // shape is free to differ from the reference's.
 #include "bvh.cuh"

@@ -15,6 +15,10 @@
 //      warp scan + one atomic per warp;
 //   3. the dynamic matrix pattern is the sorted unique set of (row, col) keys the accepted pairs
 //      touch outside the fixed pattern (one radix sort), values are accumulated by bisection into it.
+//   4. the line search sweeps with start boxes + displacement intervals (relative-motion test, bvh.cuh)
+//      instead of swept hulls, and the next assembly runs its narrow phase on the sweep's candidate
+//      lists (the evaluation point lies on the swept segment), so there is one traversal per Newton
+//      iteration instead of two.
 // Pair acceptance is independent of the candidate superset, so the accepted sets equal the
 // reference's for the same positions.
 #include "bvh.cuh"

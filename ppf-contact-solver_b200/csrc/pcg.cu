@@ -5,19 +5,24 @@
 //  * Once per Newton iteration the assembled matrices are re-packed into a solver-private
 //    coordinate form: every strictly-upper 3x3 block of B_fixed and A_dyn appears ONCE as
 //    (row, col, nine SoA value planes); diagonals A_ii + B_ii + C_i are merged, symmetrised and kept
-//    as six SoA planes, as is the block-Jacobi inverse.  Every load of the streaming kernels is a
-//    fully coalesced 128-byte line; nothing is 36-byte AoS.
-//  * SpMV is nnz-parallel: one lane per stored block, a persistent grid (SMs x 8 CTAs) striding
-//    over the block list.  H p_col is combined across the lanes of a warp that share a row with a
-//    segmented shuffle scan and leaves as one 16-byte vector reduction (red.global.add.v4.f32,
-//    sm_90+) per row run; H^T p_row leaves as one vector reduction per block.  No lane idles on
-//    short rows (cloth rows hold ~5 blocks), which is what bounded a lanes-per-row CSR kernel.
-//    p.Ap and sum|terms| are fused in.  The diagonal product y = D p is produced by the kernel that
-//    writes p, so y needs no separate zero-fill.
-//  * An iteration is 3 kernels (SpMV+dots; fused x/r/z update + r.z, |r|_1; direction update +
-//    y = D p + scalar tail).  alpha, beta, residual and the breakdown verdicts never leave the
-//    device; each kernel folds its partial sums with ONE double atomic per CTA of a persistent grid.
-//    Iterations are replayed from a CUDA graph in batches; the host polls a pinned status word per batch.
+//    as six SoA planes, as is the block-Jacobi inverse.  Nothing is 36-byte AoS.
+//  * SpMV (k_spmv_staged) is nnz-parallel over a persistent grid (SMs x 4 CTAs).  One elected thread per
+//    CTA streams chunks of 512 blocks -- eleven contiguous 2 KB segments -- into a two-stage shared
+//    memory ring with cp.async.bulk (SASS UBLKCP) + one mbarrier per stage; every thread then takes two
+//    blocks, gathers p_row / p_col from L2 and forms B p_col and B^T p_row.  B p_col is combined
+//    across the lanes of a warp that share a row with a segmented shuffle scan and leaves as one
+//    16-byte vector reduction (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4) per row run; B^T p_row
+//    leaves as one vector reduction per block.  p.Ap and sum|terms| are fused in.  The diagonal
+//    product y = D p is produced by the kernel that writes p, so y needs no separate zero-fill.
+//    (k_spmv is the register-only predecessor, kept behind PPF_B200_SPMV_LEGACY for A/B timing.)
+//  * An iteration is 3 kernels (SpMV+dots; r/z update + r.z, |r|_1; x and direction update +
+//    y = D p + scalar tail).  x, r, z are 12-byte SoA planes, p and y float4 (gathered / reduced
+//    into).  alpha, beta, residual and the breakdown verdicts never leave the device; each kernel
+//    folds its partial sums with ONE double atomic per CTA.  Iterations are replayed from a CUDA
+//    graph in batches (8, or 32 for large systems); the host polls a pinned status word per batch.
+//  * Several GPUs (dist.hpp): rows are sharded; a rank streams its own-row blocks plus copies of its
+//    foreign blocks through ONE chunk-list launch; the two sums and the rows of p other ranks read
+//    travel through NVLink peer memory from inside these same three kernels.
 //  * Semantics kept from the reference: L1 relative residual against the SEEDED initial residual
 //    (solver.cu:1002-1030), curvature-noise verdict 256*eps*sum|terms| (solver.cu:66-114),
 //    truncate-on-noise returns success, negative curvature / r.z <= 0 are fatal, block-Jacobi
