@@ -54,13 +54,17 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self.index = int(os.environ.get("PPF_B200_DEVICE", os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0] or 0))
+        # the device this process computes on, as NVML / nvidia-smi name it: entry PPF_B200_DEVICE (default 0) of
+        # CUDA_VISIBLE_DEVICES when that is set (an index or a GPU-UUID), else the plain index
+        ordinal = int(os.environ.get("PPF_B200_DEVICE", "0") or 0)
+        visible = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        self.device_id = visible[ordinal] if ordinal < len(visible) else str(ordinal)
 
     def _run_nvml(self):
         import pynvml
 
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(self.device_id)) if self.device_id.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(self.device_id.encode())
         self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self.stop_flag:
@@ -77,7 +81,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                out = subprocess.run(["nvidia-smi", "-i", self.device_id, "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 self.samples.append(float(f[0]))
                 self.max_mhz = float(f[1])

@@ -282,4 +282,23 @@ static inline int o_edge_triangle_intersect(const float *a0, const float *a1, co
     return 0;
 }
 
+
+/* ---- lagged Coulomb friction (energy/model/friction.hpp:19-82): gradient and Hessian to ADD to the contact's ---- */
+static inline float o_friction(const float *force_contact, const float *dx, const float *normal, float mu, float min_dx, float *grad, float *hess /* column-major 3x3 */) {
+    const float contact = -o_dot(normal, force_contact), nd = o_dot(normal, dx);
+    float u[3];
+    for (int k = 0; k < 3; ++k) u[k] = dx[k] - normal[k] * nd;
+    const float un = sqrtf(o_dot(u, u));
+    const float lambda = mu > 0.0f ? mu * contact / (min_dx > un ? min_dx : un) : 0.0f;
+    for (int k = 0; k < 3; ++k) grad[k] = lambda * u[k];
+    if (un > min_dx) { /* kinetic: lambda * w w^T with w = n x slip direction */
+        float s[3], w[3];
+        for (int k = 0; k < 3; ++k) s[k] = u[k] / un;
+        o_cross(normal, s, w);
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) hess[c * 3 + r] = lambda * (w[r] * w[c]);
+    } else            /* static: lambda * (I - n n^T) */
+        for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) hess[c * 3 + r] = lambda * ((r == c ? 1.0f : 0.0f) - normal[r] * normal[c]);
+    return lambda;
+}
+
 #endif

@@ -63,3 +63,5 @@ SHIM void orc_svd32(const float *F6 /* row-major 3x2 */, float *U6, float *S2, f
     S2[0] = s.S[0]; S2[1] = s.S[1];
     Vt4[0] = s.Vt[0][0]; Vt4[1] = s.Vt[0][1]; Vt4[2] = s.Vt[1][0]; Vt4[3] = s.Vt[1][1];
 }
+
+SHIM float orc_friction(const float *fc, const float *dx, const float *n, float mu, float min_dx, float *grad, float *hess) { return o_friction(fc, dx, n, mu, min_dx, grad, hess); }

@@ -84,6 +84,18 @@ def main():
         ref.ref_hinge(fp(hx[i]), C.c_float(rest[i]), fp(hf[i]), fp(hH[i]), C.byref(a))
         ha[i] = a.value
     out.update(hinge_x=hx, hinge_rest=rest, hinge_f=hf, hinge_H=hH)
+    # ---- friction (appended last so that the earlier arrays keep their random streams) ----
+    nfr = 1500
+    fc = rng.normal(0, 1.0, size=(nfr, 3)).astype(np.float32)
+    fdx = (rng.normal(0, 1.0, size=(nfr, 3)) * 10.0 ** rng.uniform(-7, -2, size=(nfr, 1))).astype(np.float32)
+    fn = rng.normal(size=(nfr, 3)); fn = (fn / np.linalg.norm(fn, axis=1, keepdims=True)).astype(np.float32)
+    fmu = rng.choice([0.0, 0.1, 0.5], size=nfr).astype(np.float32)
+    fg = np.zeros((nfr, 3), np.float32); fh = np.zeros((nfr, 9), np.float32); fl = np.zeros(nfr, np.float32)
+    for i in range(nfr):
+        lam = C.c_float(0)
+        ref.ref_friction(fp(fc[i]), fp(fdx[i]), fp(fn[i]), C.c_float(fmu[i]), C.c_float(1e-5), fp(fg[i]), fp(fh[i]), C.byref(lam))
+        fl[i] = lam.value
+    out.update(fric_fc=fc, fric_dx=fdx, fric_n=fn, fric_mu=fmu, fric_grad=fg, fric_hess=fh, fric_lambda=fl)
     path = os.path.join(REPO, "tests", "golden", "leaf_math.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -68,3 +68,10 @@ SHIM void orc_svd32(const float *F6, float *U6, float *S2, float *Vt4) {
     S2[0] = s.S[0]; S2[1] = s.S[1];
     Vt4[0] = s.Vt[0][0]; Vt4[1] = s.Vt[0][1]; Vt4[2] = s.Vt[1][0]; Vt4[3] = s.Vt[1][1];
 }
+
+SHIM float orc_friction(const float *fc, const float *dx, const float *n, float mu, float min_dx, float *grad, float *hess) {
+    const FrictionOut o = friction_eval(v(fc), v(dx), v(n), mu, min_dx);
+    grad[0] = o.grad.x; grad[1] = o.grad.y; grad[2] = o.grad.z;
+    for (int e = 0; e < 9; ++e) hess[e] = o.hess.m[e];
+    return o.lambda;
+}

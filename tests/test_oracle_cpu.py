@@ -152,6 +152,21 @@ def test_hinge_matches_reference(orc, gold):
     assert worst_f < 1e-5 and worst_H < 1e-4, (worst_f, worst_H)
 
 
+def test_friction_bit_exact(orc, gold):
+    if "fric_fc" not in gold.files:
+        pytest.skip("leaf_math.npz predates the friction vectors")
+    orc.orc_friction.restype = C.c_float
+    fc, dx, n, mu = gold["fric_fc"], gold["fric_dx"], gold["fric_n"], gold["fric_mu"]
+    g = np.zeros((len(fc), 3), np.float32); h = np.zeros((len(fc), 9), np.float32); lam = np.zeros(len(fc), np.float32)
+    for i in range(len(fc)):
+        lam[i] = orc.orc_friction(fp(fc[i]), fp(dx[i]), fp(n[i]), C.c_float(mu[i]), C.c_float(1e-5), fp(g[i]), fp(h[i]))
+    assert same_bits(lam, gold["fric_lambda"]).all()
+    assert same_bits(g, gold["fric_grad"]).all()
+    assert same_bits(h, gold["fric_hess"]).all()
+    kin = np.linalg.norm(dx - n * (n * dx).sum(axis=1, keepdims=True), axis=1) > 1e-5
+    assert kin.any() and (~kin).any()          # static and kinetic branches are both exercised
+
+
 def _strain_case(rng, stretch):
     """a rest triangle in the plane, deformed by a random rotation times a stretch"""
     rest = np.array([[0.0, 0.0], [1.0, 0.1], [0.2, 0.9]]) * 0.05
