@@ -1055,8 +1055,14 @@ static void pcg_tune(State &s) {
     time_it("spmv register-only (legacy)", 40.0 * nnz + 24.0 * n, [&] {
         k_spmv<<<std::min(P.grid, div_up((unsigned)nnz, PCG_BLOCK)), PCG_BLOCK, 0, q>>>((unsigned)nnz, P.row.p, P.col.p, P.val.p, P.cap, P.p.p, P.y.p, P.sc.p, 1);
     });
-    time_it("update (r,z,dots)", 76.0 * n, [&] { k_update<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p, PeerView{}, 0); });
-    time_it("direction (x,p,y=Dp,dots)", 108.0 * n, [&] { k_direction<<<gv, PCG_BLOCK, 0, q>>>(n, 0u, n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, PeerView{}, nullptr); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
+    for (unsigned gvar : {148u * 4, 148u * 6, 148u * 8, 148u * 16, 148u * 32}) {
+        char nm[64];
+        const unsigned gg = std::min(gvar, div_up(n, PCG_BLOCK));
+        snprintf(nm, sizeof(nm), "update (r,z,dots) grid=%u%s", gg, gg == gv ? " *" : "");
+        time_it(nm, 76.0 * n, [&] { k_update<<<gg, PCG_BLOCK, 0, q>>>(n, 0u, n, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p, PeerView{}, 0); });
+        snprintf(nm, sizeof(nm), "direction (x,p,y=Dp) grid=%u%s", gg, gg == gv ? " *" : "");
+        time_it(nm, 108.0 * n, [&] { k_direction<<<gg, PCG_BLOCK, 0, q>>>(n, 0u, n, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, PeerView{}, nullptr); cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q); });
+    }
     printf("[pcg-tune] n_row=%u n_off=%.0f (fixed %u + dyn %u); SpMV algorithmic bytes (40*n_off + 60*n_row) = %.1f MB\n", n, nnz, P.nnz_f, P.nnz_d,
            (40.0 * nnz + 60.0 * n + 4.0 * (n + 1)) * 1e-6);
     fflush(stdout);
