@@ -448,4 +448,102 @@ static inline int o_strain_face(const float (*xe)[3], const float (*xc)[3], cons
     return 1;
 }
 
+/* ---- rods (yarn): Hookean stretch and interior-vertex bending ---------------------------------------- */
+/* hook::make_diff_table (energy/model/hook.hpp:20-37): gradient per end point and the block K of the
+ * 6x6 Hessian [[K,-K],[-K,K]] = weight (c0 g g^T + c1 dtdx^T dtdx), g = [-n; n], dtdx = [-I, I] */
+static inline void o_rod_hook(const float *x0, const float *x1, float l0, float weight, float f[2][3], float *K /* 3x3 column-major */) {
+    float t[3];
+    o_sub(x1, x0, t);
+    const float l = o_norm3(t);
+    const float n[3] = {t[0] / l, t[1] / l, t[2] / l};
+    const float s = l / l0 - 1.0f;
+    const float r = (l - l0) / l;
+    const float c0 = fmaxf(0.0f, 1.0f - r) / l0;
+    const float c1 = fmaxf(0.0f, r / l0);
+    for (int k = 0; k < 3; ++k) { const float d = s * n[k]; f[0][k] = (-weight) * d; f[1][k] = weight * d; }
+    for (int c = 0; c < 3; ++c)
+        for (int rr = 0; rr < 3; ++rr) K[c * 3 + rr] = weight * ((c0 * n[rr]) * n[c] + (rr == c ? c1 : 0.0f));
+}
+/* dihedral_angle::gradient_theta (energy/model/dihedral_angle.hpp:397-425) */
+static inline void o_strand_gradient_theta(const float *e0, const float *e1, float *g0, float *g1) {
+    float cr[3];
+    o_cross(e0, e1, cr);
+    const float cs = o_dot(cr, cr), a = o_dot(e0, e0), b = o_dot(e1, e1);
+    if (cs <= 1e-12f * a * b) { for (int k = 0; k < 3; ++k) g0[k] = g1[k] = 0.0f; return; }
+    const float sq = sqrtf(cs);
+    const float n[3] = {cr[0] / sq, cr[1] / sq, cr[2] / sq};
+    float p0[3], p1[3];
+    o_cross(e0, n, p0);
+    o_cross(e1, n, p1);
+    for (int k = 0; k < 3; ++k) { g0[k] = p0[k] / a; g1[k] = (-p1[k]) / b; }
+}
+static inline void o_strand_accum(float *H, float lam, const float *qa, const float *qb) {
+    if (lam <= 0.0f) return;
+    const float n2 = o_dot(qa, qa) + o_dot(qb, qb);
+    if (n2 <= 1e-20f) return;
+    float p9[9];
+    for (int c = 0; c < 3; ++c) { p9[c] = qa[c]; p9[3 + c] = -qa[c] - qb[c]; p9[6 + c] = qb[c]; }
+    const float s = lam / n2;
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 9; ++j) H[j * 9 + i] = H[j * 9 + i] + s * p9[i] * p9[j];
+}
+/* dihedral_angle::strand_compute_force_hessian (dihedral_angle.hpp:451-541): E = 1/2 (theta - theta0)^2 over the
+ * polyline (x0, x1, x2); exact gradient, Hessian projected to PSD through the closed-form eigenpairs
+ * (four in-plane, two out-of-plane) of the angle energy in the space of the two segment vectors. H: 9x9 column-major */
+static inline void o_strand(const float *x0, const float *x1, const float *x2, float rest_angle, float f[3][3], float *H) {
+    float e0[3], e1[3], bcr[3], g0[3], g1[3];
+    o_sub(x0, x1, e0);
+    o_sub(x2, x1, e1);
+    o_cross(e0, e1, bcr);
+    const float theta = atan2f(o_norm3(bcr), o_dot(e0, e1));
+    o_strand_gradient_theta(e0, e1, g0, g1);
+    const float w = theta - rest_angle;
+    for (int k = 0; k < 3; ++k) { f[0][k] = w * g0[k]; f[1][k] = w * ((-g0[k]) - g1[k]); f[2][k] = w * g1[k]; }
+    for (int i = 0; i < 81; ++i) H[i] = 0.0f;
+    const float l0 = o_norm3(e0), l1 = o_norm3(e1), lb = o_norm3(bcr);
+    if (lb <= 1e-9f * l0 * l1 || l0 <= 1e-9f || l1 <= 1e-9f) return;
+    const float tb[3] = {bcr[0] / lb, bcr[1] / lb, bcr[2] / lb};
+    float e0p[3], e1p[3];
+    o_cross(e0, tb, e0p);
+    o_cross(e1, tb, e1p);
+    const float cos_t = o_dot(e0, e1) / (l0 * l1);
+    const float sin_t = lb / (l0 * l1);
+    const float gamma = (l1 * l1) / (l0 * l0);
+    const float gm1 = gamma - 1.0f, gp1 = gamma + 1.0f;
+    const float r = sqrtf(4.0f * w * w * (gm1 / gp1) * (gm1 / gp1) + 1.0f);
+    const float Rm = sqrtf(fmaxf(0.0f, 2.0f * (2.0f * w * w + 1.0f - r)));
+    const float Rp = sqrtf(fmaxf(0.0f, 2.0f * (2.0f * w * w + 1.0f + r)));
+    const float Lh = 1.0f / (l0 * l0) + 1.0f / (l1 * l1);
+    const float cc = 4.0f * w / gp1;
+    const int sr[4] = {-1, -1, 1, 1}, sR[4] = {-1, 1, -1, 1};
+    const float RR[4] = {Rm, Rm, Rp, Rp};
+    for (int m = 0; m < 4; ++m) {
+        const float R = RR[m];
+        const float a = w * (gm1 * gm1 / gp1 + sr[m] * gp1 * r + sR[m] * gm1 * R);
+        const float b = -0.5f * gamma * R * R + 2.0f * w * w - sR[m] * 0.5f * (gm1 + sr[m] * gp1 * r) * R;
+        const float d = 1.0f + sr[m] * r + sR[m] * R;
+        const float lam = 0.25f * Lh * d;
+        float qa[3], qb[3];
+        for (int k = 0; k < 3; ++k) { qa[k] = a * e0[k] + b * e0p[k]; qb[k] = cc * e1[k] + d * e1p[k]; }
+        o_strand_accum(H, lam, qa, qb);
+    }
+    const float beta = (l1 / l0 - l0 / l1) * cos_t;
+    const float alpha0 = 0.5f * (-beta + sqrtf(beta * beta + 4.0f));
+    const float ginv = w / sin_t;
+    const float lam4 = ginv * (cos_t / (l1 * l1) - alpha0 / (l0 * l1));
+    const float lam5 = ginv * (cos_t / (l1 * l1) + 1.0f / (alpha0 * l0 * l1));
+    float qa[3], qb[3];
+    for (int k = 0; k < 3; ++k) { qa[k] = alpha0 * tb[k]; qb[k] = tb[k]; }
+    o_strand_accum(H, lam4, qa, qb);
+    for (int k = 0; k < 3; ++k) { qa[k] = tb[k]; qb[k] = (-alpha0) * tb[k]; }
+    o_strand_accum(H, lam5, qa, qb);
+}
+/* coefficient of the rod-bend energy at an interior vertex (energy/energy.cu:572-603) */
+static inline float o_rod_bend_coefficient(float bend0, float bend1, float len0, float len1, float mass) {
+    const float bend = 0.5f * (bend0 + bend1);
+    const float REF_LENGTH = 1e-2f;
+    const float voronoi = 0.5f * (len0 + len1);
+    return voronoi > 0.0f ? bend * mass * (REF_LENGTH * REF_LENGTH) / (voronoi * voronoi) : 0.0f;
+}
+
 #endif

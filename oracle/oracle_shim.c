@@ -65,3 +65,18 @@ SHIM void orc_svd32(const float *F6 /* row-major 3x2 */, float *U6, float *S2, f
 }
 
 SHIM float orc_friction(const float *fc, const float *dx, const float *n, float mu, float min_dx, float *grad, float *hess) { return o_friction(fc, dx, n, mu, min_dx, grad, hess); }
+
+/* rods: gradient 3x2 / Hessian 6x6 (column-major) of one Hookean rod edge; force 3x3 / Hessian 9x9 of one bending vertex */
+SHIM void orc_rod_hook(const float *x6, float l0, float weight, float *grad6, float *hess36) {
+    float f[2][3], K[9];
+    o_rod_hook(x6, x6 + 3, l0, weight, f, K);
+    for (int a = 0; a < 2; ++a) for (int k = 0; k < 3; ++k) grad6[3 * a + k] = f[a][k];
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+        hess36[(3 * b + c) * 6 + 3 * a + r] = (a == b ? 1.0f : -1.0f) * K[c * 3 + r];
+}
+SHIM void orc_strand(const float *x9, float rest_angle, float *force9, float *hess81) {
+    float f[3][3];
+    o_strand(x9, x9 + 3, x9 + 6, rest_angle, f, hess81);
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) force9[3 * a + k] = f[a][k];
+}
+SHIM float orc_rod_bend_coefficient(float b0, float b1, float l0, float l1, float mass) { return o_rod_bend_coefficient(b0, b1, l0, l1, mass); }

@@ -8,7 +8,7 @@
 //
 // Built by oracle/Makefile.ref into oracle/_ref/libref_host.so.  Headers used:
 //   contact/distance.hpp, contact/accd.hpp, contact/intersect_core.hpp, barrier/cubic.hpp,
-//   energy/model/{friction,baraffwitkin,dihedral_angle,momentum}.hpp, linalg/eigsolve.hpp
+//   energy/model/{friction,baraffwitkin,dihedral_angle,hook}.hpp, linalg/eigsolve.hpp
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -23,6 +23,7 @@ using std::isfinite;
 #include "energy/model/friction.hpp"
 #include "energy/model/baraffwitkin.hpp"
 #include "energy/model/dihedral_angle.hpp"
+#include "energy/model/hook.hpp"
 #include "linalg/eigsolve.hpp"
 
 // storage for the device globals accd.hpp declares extern (contact.cu:30-38)
@@ -144,5 +145,21 @@ void ref_symm3x3(const float *A9, float *val3, float *vec9) {
     linalg::eig::symm3x3(A, l, Q);
     for (int k = 0; k < 3; ++k) val3[k] = l[k];
     for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) vec9[c * 3 + r] = Q(r, c);
+}
+// rod stretch (hook.hpp): x6 = the two end points -> gradient (3x2 col-major), hess (6x6 col-major)
+void ref_hook(const float *x6, float l0, float weight, float *grad6, float *hess36) {
+    Mat3x2f g;
+    Mat6x6f H;
+    hook::make_diff_table(v3(x6), v3(x6 + 3), l0, weight, g, H);
+    for (int c = 0; c < 2; ++c) for (int r = 0; r < 3; ++r) grad6[c * 3 + r] = g(r, c);
+    for (int c = 0; c < 6; ++c) for (int r = 0; r < 6; ++r) hess36[c * 6 + r] = H(r, c);
+}
+// rod bending (dihedral_angle.hpp strand_compute_force_hessian): x9 = (x0, x1, x2) -> force (3x3 col-major), hess (9x9 col-major)
+void ref_strand(const float *x9, float rest_angle, float *force9, float *hess81) {
+    Mat3x3f f;
+    Mat9x9f H;
+    dihedral_angle::strand_compute_force_hessian(v3(x9), v3(x9 + 3), v3(x9 + 6), rest_angle, f, H);
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) force9[c * 3 + r] = f(r, c);
+    for (int c = 0; c < 9; ++c) for (int r = 0; r < 9; ++r) hess81[c * 9 + r] = H(r, c);
 }
 }

@@ -2,7 +2,7 @@
 """make_leaf_golden.py -- known-answer vectors for the per-element math of the hot path.
 
 Runs in the build container (needs oracle/_ref/libref_host.so, i.e. the reference's OWN headers
-distance.hpp / accd.hpp / intersect_core.hpp / cubic.hpp / baraffwitkin.hpp / dihedral_angle.hpp
+distance.hpp / accd.hpp / intersect_core.hpp / cubic.hpp / baraffwitkin.hpp / dihedral_angle.hpp / hook.hpp
 compiled for the host by oracle/Makefile.ref with -ffp-contract=off) and writes
 tests/golden/leaf_math.npz: seeded inputs plus the reference's outputs.  The CPU tests check the
 oracle restatement against these vectors bit for bit (float32 payloads compared as uint32).
@@ -96,6 +96,31 @@ def main():
         ref.ref_friction(fp(fc[i]), fp(fdx[i]), fp(fn[i]), C.c_float(fmu[i]), C.c_float(1e-5), fp(fg[i]), fp(fh[i]), C.byref(lam))
         fl[i] = lam.value
     out.update(fric_fc=fc, fric_dx=fdx, fric_n=fn, fric_mu=fmu, fric_grad=fg, fric_hess=fh, fric_lambda=fl)
+    # ---- rods: Hookean stretch (hook.hpp) and interior-vertex bending (dihedral_angle.hpp strand_*) ----
+    nr = 1200
+    rx = rng.uniform(-1, 1, size=(nr, 2, 3)).astype(np.float32)
+    rl0 = (np.linalg.norm(rx[:, 1] - rx[:, 0], axis=1) * rng.uniform(0.6, 1.4, nr)).astype(np.float32)
+    rw = rng.uniform(0.1, 50.0, nr).astype(np.float32)
+    rg = np.zeros((nr, 6), np.float32); rh = np.zeros((nr, 36), np.float32)
+    for i in range(nr):
+        ref.ref_hook(fp(rx[i]), C.c_float(rl0[i]), C.c_float(rw[i]), fp(rg[i]), fp(rh[i]))
+    out.update(rod_x=rx, rod_l0=rl0, rod_weight=rw, rod_grad=rg, rod_hess=rh)
+    ns = 1500
+    sx = rng.uniform(-1, 1, size=(ns, 3, 3)).astype(np.float32)
+    # nearly straight yarn segments (the regime of the woven scenes) and exactly collinear ones (guards)
+    seg = rng.uniform(2e-3, 4e-3, size=(500, 1)).astype(np.float32)
+    dirs = rng.normal(size=(500, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    mid = rng.uniform(-1, 1, size=(500, 3))
+    bend = rng.normal(0, 0.05, size=(500, 3)) * seg
+    near = np.stack([mid - dirs * seg, mid + bend, mid + dirs * seg * rng.uniform(0.7, 1.3, size=(500, 1))], axis=1).astype(np.float32)
+    col = np.stack([mid[:50] - dirs[:50], mid[:50], mid[:50] + 2 * dirs[:50]], axis=1).astype(np.float32)
+    col[:, 1] = (0.5 * (col[:, 0] + col[:, 2])).astype(np.float32)
+    sx = np.concatenate([sx, near, col]).copy()
+    srest = np.concatenate([rng.uniform(0.5, np.pi, ns), np.full(500, np.pi), np.full(50, np.pi)]).astype(np.float32)
+    sf = np.zeros((len(sx), 9), np.float32); sh = np.zeros((len(sx), 81), np.float32)
+    for i in range(len(sx)):
+        ref.ref_strand(fp(sx[i]), C.c_float(srest[i]), fp(sf[i]), fp(sh[i]))
+    out.update(strand_x=sx, strand_rest=srest, strand_f=sf, strand_H=sh)
     path = os.path.join(REPO, "tests", "golden", "leaf_math.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

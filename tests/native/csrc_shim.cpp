@@ -6,6 +6,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_rod.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_strain.cuh"
 using namespace ppf;
 #define SHIM extern "C" __attribute__((visibility("default")))
@@ -75,3 +76,19 @@ SHIM float orc_friction(const float *fc, const float *dx, const float *n, float 
     for (int e = 0; e < 9; ++e) hess[e] = o.hess.m[e];
     return o.lambda;
 }
+
+// rods: same C signatures as the oracle shim (gradient 3x2 / Hessian 6x6 column-major; force 3x3 / Hessian 9x9)
+SHIM void orc_rod_hook(const float *x6, float l0, float weight, float *grad6, float *hess36) {
+    RodElastic re;
+    rod_hook(v(x6), v(x6 + 3), l0, weight, re);
+    for (int a = 0; a < 2; ++a) { grad6[3 * a] = re.f[a].x; grad6[3 * a + 1] = re.f[a].y; grad6[3 * a + 2] = re.f[a].z; }
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+        hess36[(3 * b + c) * 6 + 3 * a + r] = (a == b ? 1.0f : -1.0f) * re.K.m[c * 3 + r];
+}
+SHIM void orc_strand(const float *x9, float rest_angle, float *force9, float *hess81) {
+    StrandElastic se;
+    strand_force_hessian(v(x9), v(x9 + 3), v(x9 + 6), rest_angle, se);
+    for (int a = 0; a < 3; ++a) { force9[3 * a] = se.f[a].x; force9[3 * a + 1] = se.f[a].y; force9[3 * a + 2] = se.f[a].z; }
+    for (int i = 0; i < 81; ++i) hess81[i] = se.H[i];
+}
+SHIM float orc_rod_bend_coefficient(float b0, float b1, float l0, float l1, float mass) { return rod_bend_coefficient(b0, b1, l0, l1, mass); }

@@ -167,6 +167,62 @@ def test_friction_bit_exact(orc, gold):
     assert kin.any() and (~kin).any()          # static and kinetic branches are both exercised
 
 
+def test_rod_hook_bit_exact(orc, gold):
+    """Hookean rod edge (hook.hpp:20-37): gradient and 6x6 Hessian, bit for bit."""
+    rx = gold["rod_x"]
+    g = np.zeros((len(rx), 6), np.float32); h = np.zeros((len(rx), 36), np.float32)
+    for i in range(len(rx)):
+        orc.orc_rod_hook(fp(rx[i]), C.c_float(gold["rod_l0"][i]), C.c_float(gold["rod_weight"][i]), fp(g[i]), fp(h[i]))
+    assert same_bits(g, gold["rod_grad"]).all()
+    assert same_bits(h, gold["rod_hess"]).all()
+    stretched = np.linalg.norm(rx[:, 1] - rx[:, 0], axis=1) > gold["rod_l0"]
+    assert stretched.any() and (~stretched).any()     # both branches of the c0 / c1 clamps
+
+
+def test_rod_bend_bit_exact(orc, gold):
+    """Interior rod vertex bending (dihedral_angle.hpp:451-541): force and PSD-projected 9x9 Hessian, bit for bit,
+    over random triples, nearly straight yarn segments and (near-)collinear ones that hit the guards."""
+    sx = gold["strand_x"]
+    f = np.zeros((len(sx), 9), np.float32); H = np.zeros((len(sx), 81), np.float32)
+    for i in range(len(sx)):
+        orc.orc_strand(fp(sx[i]), C.c_float(gold["strand_rest"][i]), fp(f[i]), fp(H[i]))
+    assert (same_bits(f, gold["strand_f"]) | ((f == 0) & (gold["strand_f"] == 0))).all()
+    assert (same_bits(H, gold["strand_H"]) | ((H == 0) & (gold["strand_H"] == 0))).all()
+    assert (np.abs(gold["strand_H"]).max(axis=1) == 0).any()   # guarded (collinear) cases are present
+    # the projected Hessian is symmetric PSD
+    for i in range(0, len(sx), 37):
+        A = H[i].reshape(9, 9).astype(np.float64)
+        assert np.abs(A - A.T).max() <= 1e-5 * max(np.abs(A).max(), 1e-12)
+        assert np.linalg.eigvalsh(0.5 * (A + A.T)).min() >= -1e-4 * max(np.abs(A).max(), 1e-12)
+
+
+def test_rod_bend_force_is_the_energy_gradient(orc):
+    """finite differences of E = 1/2 (theta - theta0)^2 in float64 against the fp32 force"""
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for _ in range(200):
+        x = rng.uniform(-1, 1, size=(3, 3))
+        rest = rng.uniform(1.0, np.pi)
+
+        def energy(y):
+            e0, e1 = y[0] - y[1], y[2] - y[1]
+            th = np.arctan2(np.linalg.norm(np.cross(e0, e1)), e0 @ e1)
+            return 0.5 * (th - rest) ** 2
+        num = np.zeros((3, 3))
+        for a in range(3):
+            for k in range(3):
+                d = np.zeros((3, 3)); d[a, k] = 1e-6
+                num[a, k] = (energy(x + d) - energy(x - d)) / 2e-6
+        f = np.zeros(9, np.float32); H = np.zeros(81, np.float32)
+        x32 = x.astype(np.float32)
+        orc.orc_strand(fp(x32), C.c_float(rest), fp(f), fp(H))
+        worst = max(worst, np.abs(f.reshape(3, 3) - num).max() / max(np.abs(num).max(), 1e-3))
+    assert worst < 2e-3, worst
+    orc.orc_rod_bend_coefficient.restype = C.c_float
+    k = orc.orc_rod_bend_coefficient(C.c_float(2e-3), C.c_float(4e-3), C.c_float(2e-3), C.c_float(3e-3), C.c_float(5e-4))
+    assert abs(k - 3e-3 * 5e-4 * 1e-4 / (2.5e-3) ** 2) < 1e-9
+
+
 def _strain_case(rng, stretch):
     """a rest triangle in the plane, deformed by a random rotation times a stretch"""
     rest = np.array([[0.0, 0.0], [1.0, 0.1], [0.2, 0.9]]) * 0.05
