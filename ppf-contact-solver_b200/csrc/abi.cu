@@ -5,6 +5,7 @@
 // There is no CPU fallback: without a CUDA device initialize() stamps a fatal code and exits,
 // exactly like the reference (main.cu:1879-1893).
 #include "backend.hpp"
+#include "math_rod.cuh"
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
@@ -114,7 +115,14 @@ void upload_dataset(State &s) {
     s.nsv = d.surface_vert_count;
 
     // ---- scope gate: refuse loudly what this backend does not implement (DESIGN.md "out of scope") ----
-    if (d.rod_count) fatal(4, "B200 backend: rod elements are not implemented (rod_count=%u)", d.rod_count);
+    if (d.rod_count > ne) fatal(4, "rod_count %u exceeds the edge count %u", d.rod_count, ne);
+    for (unsigned i = 0; i < d.rod_count; ++i) {
+        const PpfEdgeParam &ep = d.param_arrays.edge.data[d.prop.edge.data[i].param_index];
+        if (ep.strainlimit > 0.0f || ep.deform_damping > 0.0f || ep.bend_damping > 0.0f || ep.plasticity > 0.0f)
+            fatal(4, "B200 backend: rod strain limiting / Rayleigh damping / bend plasticity are not implemented");
+    }
+    if (d.rod_count && (d.edge_hess_slots.size < 4u * d.rod_count || d.rod_bend_hess_slots.size != 9u * d.surface_vert_count))
+        fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
     if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
     if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
     if (d.constraint.stitch.size || d.constraint.sphere.size || d.constraint.floor.size || d.constraint.mesh.vertex.size ||
@@ -221,6 +229,44 @@ void upload_dataset(State &s) {
         s.fstrain.upload(fs.data(), nf, q);
         s.varea.upload(va.data(), nv, q); s.hinge_stiff.upload(hs.data(), nh, q);
         s.vcollider.upload(vc.data(), nv, q); s.fskip.upload(fsk.data(), nf, q);
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
+    // ---- rods: Hookean edges [0, rod_count) and the bending stencils of interior rod vertices ----
+    s.nrod = d.rod_count;
+    s.nrodbend = 0;
+    if (s.nrod) {
+        std::vector<float2> rp(s.nrod);
+        for (unsigned i = 0; i < s.nrod; ++i) { // energy.cu:272-302
+            const PpfEdgeProp &p = d.prop.edge.data[i];
+            const PpfEdgeParam &ep = d.param_arrays.edge.data[p.param_index];
+            rp[i] = make_float2(p.length, ep.stiffness > 0.0f ? ep.stiffness * p.mass : 0.0f);
+        }
+        s.rod_par.upload(rp.data(), s.nrod, q);
+        s.rod_slots.upload(d.edge_hess_slots.data, size_t(4) * s.nrod, q);
+        CUDA_OK(cudaStreamSynchronize(q));
+        // energy.cu:556-641: a vertex with exactly two incident edges and no incident face bends about its neighbours
+        const PpfVecVecU32 &vedge = d.mesh.neighbor.vertex.edge, &vface = d.mesh.neighbor.vertex.face;
+        std::vector<uint4> el;
+        std::vector<float2> par;
+        std::vector<unsigned> sl;
+        for (unsigned i = 0; i < s.nsv; ++i) {
+            if (i >= vedge.size || vedge.offset[i + 1] - vedge.offset[i] != 2) continue;
+            if (i < vface.size && vface.offset[i + 1] != vface.offset[i]) continue;
+            const unsigned e0 = vedge.data[vedge.offset[i]], e1 = vedge.data[vedge.offset[i] + 1];
+            const PpfEdgeProp &p0 = d.prop.edge.data[e0], &p1 = d.prop.edge.data[e1];
+            const PpfEdgeParam &q0 = d.param_arrays.edge.data[p0.param_index], &q1 = d.param_arrays.edge.data[p1.param_index];
+            const float mass = d.prop.vertex.data[i].mass;
+            const float k = rod_bend_coefficient(q0.bend, q1.bend, p0.length, p1.length, mass);
+            if (!(mass > 0.0f && k > 0.0f)) continue;
+            if (q0.bend_damping > 0.0f || q1.bend_damping > 0.0f) fatal(4, "B200 backend: rod bending damping is not implemented");
+            const PpfVec2u &c0 = d.mesh.mesh.edge.data[e0], &c1 = d.mesh.mesh.edge.data[e1];
+            const unsigned j = c0.v[0] == i ? c0.v[1] : c0.v[0], kk = c1.v[0] == i ? c1.v[1] : c1.v[0];
+            el.push_back(make_uint4(j, i, kk, 0u));
+            par.push_back(make_float2(k, d.prop.vertex.data[i].rest_bend_angle));
+            for (int b = 0; b < 9; ++b) sl.push_back(d.rod_bend_hess_slots.data[size_t(9) * i + b]);
+        }
+        s.nrodbend = (unsigned)el.size();
+        s.rb_elem.upload(el.data(), el.size(), q); s.rb_par.upload(par.data(), par.size(), q); s.rb_slots.upload(sl.data(), sl.size(), q);
         CUDA_OK(cudaStreamSynchronize(q));
     }
     s.fix_index.reserve(nv); s.pull_index.reserve(nv);

@@ -120,6 +120,13 @@ struct State {
     DBuf<float4> inv_rest;                        // per face 2x2
     DBuf<float4> hmat;                            // per hinge (length, area, rest_angle, bend_dir)
     DBuf<float> hinge_stiff;                      // per hinge stiffness (energy.cu:510-517), 0 = skip
+    // rods (yarn): edges [0, nrod) are rod edges; bending vertices are the interior rod vertices (two edges, no face)
+    unsigned nrod = 0, nrodbend = 0;
+    DBuf<float2> rod_par;                         // per rod edge (rest length, stiffness * mass); weight 0 = skip
+    DBuf<unsigned> rod_slots;                     // 4 per rod edge (DataSet.edge_hess_slots)
+    DBuf<uint4> rb_elem;                          // per bending vertex i: (j, i, k, -), its stencil in scatter order
+    DBuf<float2> rb_par;                          // per bending vertex (bending coefficient, rest angle)
+    DBuf<unsigned> rb_slots;                      // 9 per bending vertex (DataSet.rod_bend_hess_slots rows of those vertices)
     DBuf<PpfFixPair> fix;
     DBuf<PpfPullPair> pull;
     // ABI-layout copies kept for fetch_* (plasticity is out of scope, so they never change)

@@ -1005,6 +1005,10 @@ bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm) {
         g_has_offsets = 0;
         for (unsigned i = 0; i < s.host.param_arrays.face.size; ++i)
             if (s.host.param_arrays.face.data[i].offset > 0.0f) g_has_offsets = 1;
+        for (unsigned i = 0; i < s.host.param_arrays.edge.size; ++i)
+            if (s.host.param_arrays.edge.data[i].offset > 0.0f) g_has_offsets = 1;
+        for (unsigned i = 0; i < s.host.param_arrays.vertex.size; ++i)
+            if (s.host.param_arrays.vertex.data[i].offset > 0.0f) g_has_offsets = 1;
     }
     IsectArgs A;
     A.face = view_of(s.bvh_face); A.edge = view_of(s.bvh_edge); A.vert = view_of(s.bvh_vert);

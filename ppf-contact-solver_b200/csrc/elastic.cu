@@ -3,13 +3,14 @@
 //
 // Replaces energy::embed_momentum_force_hessian (crates/ppf-cts-solver/src/cpp/energy/energy.cu:700-716,
 // per-vertex body 182-270) and energy::embed_elastic_force_hessian (energy.cu:718-794; face body
-// 304-364, hinge body 448-553).  One thread per element; the per-element math lives in
+// 304-364, hinge body 448-553, rod stretch 272-302, rod bending 556-641).  One thread per element; the per-element math lives in
 // math_elastic.cuh / math_hinge.cuh; blocks are scattered through the DataSet's precomputed slot
 // tables (builder.rs:1368-1496) with fp32 atomics exactly like the reference's push_at
 // (csrmat.cu:586-594), lower-triangle sentinels skipped.
 #include "backend.hpp"
 #include "math_elastic.cuh"
 #include "math_hinge.cuh"
+#include "math_rod.cuh"
 #include "math_strain.cuh"
 
 namespace ppf {
@@ -139,6 +140,56 @@ __global__ void __launch_bounds__(128) k_hinge(unsigned nh, const uint4 *__restr
         }
 }
 
+// ---- rods (energy.cu:272-302 stretch, 556-641 bending; math_rod.cuh) ----
+__global__ void __launch_bounds__(128) k_rod(unsigned nrod, const uint2 *__restrict__ edge, const float4 *__restrict__ eval_x,
+                                             const float2 *__restrict__ rod_par, const unsigned char *__restrict__ efixed,
+                                             const unsigned *__restrict__ slots, float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrod || efixed[i]) return;
+    const float2 par = rod_par[i]; // (rest length, stiffness * mass)
+    if (!(par.y > 0.0f)) return;
+    const uint2 e = edge[i];
+    RodElastic re;
+    rod_hook(ld3(eval_x, e.x), ld3(eval_x, e.y), par.x, par.y, re);
+    atomic_add3(force + size_t(3) * e.x, re.f[0]);
+    atomic_add3(force + size_t(3) * e.y, re.f[1]);
+    float neg[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) neg[k] = -re.K.m[k];
+    const unsigned *sl = slots + size_t(4) * i;
+    atomic_add_block(val, sl[0], re.K.m);
+    atomic_add_block(val, sl[1], neg);
+    atomic_add_block(val, sl[2], neg);
+    atomic_add_block(val, sl[3], re.K.m);
+}
+
+__global__ void __launch_bounds__(128) k_rod_bend(unsigned n, const uint4 *__restrict__ elem, const float2 *__restrict__ par,
+                                                  const float4 *__restrict__ eval_x, const unsigned *__restrict__ fix_index,
+                                                  const unsigned *__restrict__ slots, float *__restrict__ force, float *__restrict__ val) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4 el = elem[t]; // (j, i, k): i is the bending vertex
+    if (fix_index[el.y] != 0) return;
+    const float2 pr = par[t]; // (coefficient, rest angle)
+    StrandElastic se;
+    strand_force_hessian(ld3(eval_x, el.x), ld3(eval_x, el.y), ld3(eval_x, el.z), pr.y, se);
+    const unsigned vi[3] = {el.x, el.y, el.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], pr.x * se.f[a]);
+    const unsigned *sl = slots + size_t(9) * t;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            const unsigned slot = sl[a * 3 + b];
+            if (slot == 0xFFFFFFFFu) continue;
+            float blk[9];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) blk[c * 3 + r] = pr.x * se.H[(3 * b + c) * 9 + (3 * a + r)];
+            atomic_add_block(val, slot, blk);
+        }
+}
+
 // ---- strain limiting (strainlimiting.cu:46-120, 250-307; math_strain.cuh) ----
 __device__ __forceinline__ unsigned fixed_slot(const unsigned *__restrict__ off, const unsigned *__restrict__ col, unsigned i, unsigned j) { // i <= j
     for (unsigned k = off[i]; k < off[i + 1]; ++k) {
@@ -256,6 +307,11 @@ void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
 
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm) {
     (void)dt; (void)prm;
+    if (s.nrodbend) k_rod_bend<<<div_up(s.nrodbend, 128), 128, 0, s.stream>>>(s.nrodbend, s.rb_elem.p, s.rb_par.p, s.eval_x.p, s.fix_index.p,
+                                                                             s.rb_slots.p, s.force.p, s.fx_val.p);
+    if (s.nrod) k_rod<<<div_up(s.nrod, 128), 128, 0, s.stream>>>(s.nrod, s.edge.p, s.eval_x.p, s.rod_par.p, s.efixed.p, s.rod_slots.p,
+                                                                s.force.p, s.fx_val.p);
+    if (s.nrod) LAUNCH_COUNT(2);
     if (s.nf) k_face<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.fmat.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
                                                              s.face_slots.p, s.force.p, s.fx_val.p);
     if (s.nh) k_hinge<<<div_up(s.nh, 128), 128, 0, s.stream>>>(s.nh, s.hinge.p, s.eval_x.p, s.hmat.p, s.hinge_stiff.p, s.hfixed.p,

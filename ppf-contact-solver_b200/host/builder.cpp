@@ -1,8 +1,8 @@
 // builder.cpp -- topology, props and the repr(C) DataSet / ParamSet.
 // Restates crates/ppf-cts-solver/src/mesh.rs:66-293, scene.rs:1538-1930 (make_props),
 // main.rs:204-258 (non-rod edge props) and builder.rs:339-1681 (build, make_param) for
-// shell scenes (no rods / tets / PDRD / SAND / stitches, which none of the BASELINE
-// twist configs contain).  Edge and hinge numbering: the reference iterates a std HashMap
+// shell and rod scenes (no tets / PDRD / SAND / stitches, which none of the BASELINE
+// configs contain).  Edge and hinge numbering: the reference iterates a std HashMap
 // (random per process, mesh.rs:196-229,257-293); this host uses sorted-key order so a
 // scene is reproducible.  Both backends are always fed the same DataSet.
 #include "ppf_host.hpp"
@@ -49,10 +49,15 @@ static inline Vec3f cross(const Vec3f &a, const Vec3f &b) {
 static inline float dot(const Vec3f &a, const Vec3f &b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 static inline float norm(const Vec3f &a) { return std::sqrt(dot(a, a)); }
 
-template <class P> static unsigned dedup(std::vector<P> &store, const P &p) { // builder.rs:1749-1759
-    for (unsigned i = 0; i < store.size(); ++i)
-        if (std::memcmp(&store[i], &p, sizeof(P)) == 0) return i;
+template <class P> static unsigned dedup(std::vector<P> &store, const P &p) { // builder.rs:1749-1759 (first occurrence keeps its index)
+    static std::map<const void *, std::map<std::string, unsigned>> index_of; // per store: bytes -> index
+    auto &m = index_of[&store];
+    if (store.empty()) m.clear();
+    const std::string key(reinterpret_cast<const char *>(&p), sizeof(P));
+    auto it = m.find(key);
+    if (it != m.end()) return it->second;
     store.push_back(p);
+    m.emplace(key, (unsigned)store.size() - 1);
     return (unsigned)store.size() - 1;
 }
 
@@ -71,6 +76,9 @@ void build_scene(const SceneSpec &spec, Built &b) {
             b.vert_origin.push_back({(unsigned)o, lv});
         }
     };
+    for (size_t o = 0; o < spec.objects.size(); ++o) // rods first (index_map.rs:81-94)
+        for (auto &e : spec.objects[o].rod)
+            for (int k = 0; k < 2; ++k) assign(o, e[k]);
     for (size_t o = 0; o < spec.objects.size(); ++o)
         for (auto &t : spec.objects[o].tri)
             for (int k = 0; k < 3; ++k) assign(o, t[k]);
@@ -108,6 +116,15 @@ void build_scene(const SceneSpec &spec, Built &b) {
             sides.push_back(Side{((unsigned long long)lo << 32) | hi, i, e0, e1, e2});
         }
     std::sort(sides.begin(), sides.end(), [](const Side &x, const Side &y) { return x.key != y.key ? x.key < y.key : x.face < y.face; });
+    // rod edges come first and keep their own vertex order (mesh.rs:216-220)
+    std::vector<unsigned> rod_object;
+    for (size_t o = 0; o < spec.objects.size(); ++o)
+        for (auto &e : spec.objects[o].rod) {
+            b.edge.push_back(PpfVec2u{{(unsigned)l2g[o][e[0]], (unsigned)l2g[o][e[1]]}});
+            b.edge_face.push_back({});
+            rod_object.push_back((unsigned)o);
+        }
+    const unsigned nrod = b.n_rod = (unsigned)rod_object.size();
     for (size_t k = 0; k < sides.size();) {
         size_t m = k;
         while (m < sides.size() && sides[m].key == sides[k].key) ++m;
@@ -126,6 +143,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
     for (unsigned i = 0; i < nf; ++i) for (int k = 0; k < 3; ++k) b.v_face[b.face[i].v[k]].push_back(i);
     for (unsigned i = 0; i < nh; ++i) for (int k = 0; k < 4; ++k) b.v_hinge[b.hinge[i].v[k]].push_back(i);
     for (unsigned i = 0; i < ne; ++i) for (int k = 0; k < 2; ++k) b.v_edge[b.edge[i].v[k]].push_back(i);
+    for (unsigned i = 0; i < nrod; ++i) for (int k = 0; k < 2; ++k) b.v_rod[b.edge[i].v[k]].push_back(i);
 
     // ---- face props / params (scene.rs:1656-1830) ----
     std::vector<float> face_area(nf);
@@ -156,7 +174,29 @@ void build_scene(const SceneSpec &spec, Built &b) {
     }
     // ---- non-rod edge props (main.rs:225-258, builder.rs:1800-1821) ----
     b.eprop.resize(ne);
-    for (unsigned i = 0; i < ne; ++i) {
+    for (unsigned i = 0; i < nrod; ++i) { // rod edges (scene.rs:1542-1648)
+        const auto &pm = spec.objects[rod_object[i]].rod_param;
+        auto get = [&](const char *k) { return float(pm.at(k)); };
+        PpfEdgeParam p;
+        std::memset(&p, 0, sizeof(p));
+        p.stiffness = get("young-mod"); p.bend = get("bend"); p.ghat = get("contact-gap"); p.offset = get("contact-offset");
+        p.friction = get("friction"); p.strainlimit = get("strain-limit");
+        p.plasticity = get("bend-plasticity"); p.plasticity_threshold = get("bend-plasticity-threshold");
+        p.bend_rest_from_geometry = get("bend-rest-from-geometry") != 0.0f;
+        p.deform_damping = get("deformation-damping"); p.bend_damping = get("bending-damping");
+        if (!(get("density") > 0.0f) || !(p.stiffness > 0.0f) || !(p.ghat > 0.0f)) throw std::runtime_error("rod density / young-mod / contact-gap must be positive");
+        PpfEdgeProp ep;
+        std::memset(&ep, 0, sizeof(ep));
+        float length = norm(sub(b.vert[b.edge[i].v[1]], b.vert[b.edge[i].v[0]]));
+        if (!(length > 0.0f)) throw std::runtime_error("degenerate rod edge");
+        ep.initial_length = length;
+        ep.mass = get("density") * length;
+        length *= get("length-factor");
+        ep.length = length;
+        ep.param_index = dedup(b.eparam, p);
+        b.eprop[i] = ep;
+    }
+    for (unsigned i = nrod; i < ne; ++i) {
         float gs = 0, os = 0, fs = 0, as = 0;
         for (unsigned j : b.edge_face[i]) {
             const PpfFaceParam &fp = b.fparam[b.fprop[j].param_index];
@@ -203,12 +243,32 @@ void build_scene(const SceneSpec &spec, Built &b) {
         for (int k = 0; k < 3; ++k) b.vprop[b.face[i].v[k]].area += b.fprop[i].area / 3.0f;
     for (unsigned i = 0; i < nf; ++i)
         for (int k = 0; k < 3; ++k) b.vprop[b.face[i].v[k]].mass += b.fprop[i].mass / 3.0f;
+    for (unsigned i = 0; i < nrod; ++i) // builder.rs:625-643
+        for (int k = 0; k < 2; ++k) b.vprop[b.edge[i].v[k]].mass += b.eprop[i].mass / 2.0f;
+    for (unsigned j = 0; j < nv; ++j) { // builder.rs:521-577: rest bend angle of interior rod vertices from the initial pose
+        if (b.v_rod[j].size() != 2 || !b.v_face[j].empty()) continue;
+        bool from_geometry = false;
+        for (unsigned ei : b.v_rod[j]) from_geometry = from_geometry || b.eparam[b.eprop[ei].param_index].bend_rest_from_geometry;
+        if (!from_geometry) continue;
+        const PpfVec2u &c0 = b.edge[b.v_rod[j][0]], &c1 = b.edge[b.v_rod[j][1]];
+        const unsigned o0 = c0.v[0] == j ? c0.v[1] : c0.v[0], o1 = c1.v[0] == j ? c1.v[1] : c1.v[0];
+        const Vec3f e0 = sub(b.vert[o0], b.vert[j]), e1 = sub(b.vert[o1], b.vert[j]);
+        const float n0 = norm(e0), n1 = norm(e1);
+        if (n0 <= 0.0f || n1 <= 0.0f) continue;
+        b.vprop[j].rest_bend_angle = std::acos(std::min(1.0f, std::max(-1.0f, dot(e0, e1) / (n0 * n1))));
+    }
     for (unsigned j = 0; j < nv; ++j) {
         float gs = 0, os = 0, fs = 0, wsum = 0;
         for (unsigned fi : b.v_face[j]) {
             const PpfFaceParam &fp = b.fparam[b.fprop[fi].param_index];
             const float w = b.fprop[fi].area;
             gs += w * fp.ghat; os += w * fp.offset; fs += w * fp.friction; wsum += w;
+        }
+        for (unsigned ei : b.v_edge[j]) { // rod edges weigh in by their rest length (builder.rs:810-826)
+            if (ei >= nrod) continue;
+            const PpfEdgeParam &ep = b.eparam[b.eprop[ei].param_index];
+            const float w = b.eprop[ei].length;
+            gs += w * ep.ghat; os += w * ep.offset; fs += w * ep.friction; wsum += w;
         }
         if (wsum > 0.0f) {
             PpfVertexParam p{gs / wsum, os / wsum, fs / wsum};
@@ -268,6 +328,12 @@ void build_scene(const SceneSpec &spec, Built &b) {
         for (auto &e : b.edge) for (int p = 0; p < 2; ++p) for (int q = 0; q < 2; ++q) ins(e.v[p], e.v[q]);
         for (auto &f : b.face) for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) ins(f.v[p], f.v[q]);
         for (auto &h : b.hinge) for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) ins(h.v[p], h.v[q]);
+        for (unsigned i = 0; i < nv; ++i) { // rod-bending stencil (j, i, k): the pair (j, k) is no edge (builder.rs:1289-1313)
+            if (b.v_edge[i].size() != 2 || !b.v_face[i].empty()) continue;
+            const PpfVec2u &c0 = b.edge[b.v_edge[i][0]], &c1 = b.edge[b.v_edge[i][1]];
+            const unsigned st[3] = {c0.v[0] == i ? c0.v[1] : c0.v[0], i, c1.v[0] == i ? c1.v[1] : c1.v[0]};
+            for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) ins(st[p], st[q]);
+        }
         for (auto &row : t) { std::sort(row.begin(), row.end()); row.erase(std::unique(row.begin(), row.end()), row.end()); }
     }
     b.transpose_table.assign(nv, {});
@@ -298,6 +364,12 @@ void build_scene(const SceneSpec &spec, Built &b) {
         for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) b.hinge_slots.push_back(slot_of(r[p], r[q]));
     }
     b.rod_bend_slots.assign(size_t(9) * nv, 0xFFFFFFFFu);
+    for (unsigned i = 0; i < nv; ++i) { // builder.rs:1446-1467
+        if (b.v_edge[i].size() != 2 || !b.v_face[i].empty()) continue;
+        const PpfVec2u &c0 = b.edge[b.v_edge[i][0]], &c1 = b.edge[b.v_edge[i][1]];
+        const unsigned st[3] = {c0.v[0] == i ? c0.v[1] : c0.v[0], i, c1.v[0] == i ? c1.v[1] : c1.v[0]};
+        for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) b.rod_bend_slots[size_t(9) * i + p * 3 + q] = slot_of(st[p], st[q]);
+    }
     b.type_face.assign(nf, 0); b.type_vertex.assign(nv, 0); b.type_hinge.assign(nh, 0);
 
     // ---- vertex state (builder.rs:1571-1587) ----
@@ -334,7 +406,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
     set_vec(d.inv_rest2x2, b.inv_rest2x2);
     d.constraint = b.constraint;
     set_vecvec(d.fixed_index_table, b.f_fixed); set_vecvec(d.transpose_table, b.f_transpose);
-    d.rod_count = 0; d.shell_face_count = nf; d.surface_vert_count = nv;
+    d.rod_count = nrod; d.shell_face_count = nf; d.surface_vert_count = nv;
     set_vec(d.grain_omega, b.zero3); set_vec(d.grain_inv_inertia, b.zero1); set_vec(d.grain_torque, b.zero3);
     set_vec(d.grain_ang_stiff, b.zero1); set_vec(d.grain_contact_normal, b.zero3);
     set_vec(d.grain_inv_inertia_center, b.zero1); set_vec(d.grain_omega_prev, b.zero3);

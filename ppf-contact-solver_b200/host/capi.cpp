@@ -131,6 +131,23 @@ void ppfh_topology(Session *s, unsigned *face, unsigned *edge, float *vparam2) {
             vparam2[2 * i] = vp.ghat; vparam2[2 * i + 1] = vp.offset;
         }
 }
+// rod data of the built scene: returns rod_count; per rod edge (rest length, initial length, mass, stiffness, bend),
+// per vertex (mass, rest bend angle), the 9 rod-bend slots per vertex and the fixed index table (offset[n_vert+1], columns)
+unsigned ppfh_rods(Session *s, float *rod5, float *vert2, unsigned *bend_slots9, unsigned *fixed_offset, unsigned *fixed_col) {
+    const Built &b = s->b;
+    if (rod5)
+        for (unsigned i = 0; i < b.n_rod; ++i) {
+            const PpfEdgeProp &p = b.eprop[i];
+            const PpfEdgeParam &q = b.eparam[p.param_index];
+            rod5[5 * i] = p.length; rod5[5 * i + 1] = p.initial_length; rod5[5 * i + 2] = p.mass; rod5[5 * i + 3] = q.stiffness; rod5[5 * i + 4] = q.bend;
+        }
+    if (vert2)
+        for (unsigned i = 0; i < b.n_vert; ++i) { vert2[2 * i] = b.vprop[i].mass; vert2[2 * i + 1] = b.vprop[i].rest_bend_angle; }
+    if (bend_slots9) memcpy(bend_slots9, b.rod_bend_slots.data(), b.rod_bend_slots.size() * sizeof(unsigned));
+    if (fixed_offset) memcpy(fixed_offset, b.f_fixed.offset.data(), b.f_fixed.offset.size() * sizeof(unsigned));
+    if (fixed_col) memcpy(fixed_col, b.f_fixed.data.data(), b.f_fixed.data.size() * sizeof(unsigned));
+    return b.n_rod;
+}
 }
 
 #include <dlfcn.h>

@@ -51,6 +51,10 @@ struct ShellObject {
     std::vector<Vec3d> vert;
     std::vector<std::array<unsigned, 3>> tri;
     std::map<std::string, double> param; // tri params (crates/ppf-cts-core/src/datamodel/params.rs:295-420)
+    // rod (yarn) object: edges between the object's vertices and the rod parameter set (ObjectKind::Rod defaults);
+    // an object is either a shell (tri) or a rod (rod), like app.asset.add.tri / add.rod of the frontend
+    std::vector<std::array<unsigned, 2>> rod;
+    std::map<std::string, double> rod_param;
     std::vector<Pin> pins;
     Vec3d displacement{0, 0, 0};
     Vec3d velocity{0, 0, 0};
@@ -85,6 +89,8 @@ void gen_cylinder(double r, double min_x, double max_x, unsigned n, std::vector<
 void gen_square(unsigned res, double size, Vec3d ex, Vec3d ey, std::vector<Vec3d> &V,
                 std::vector<std::array<unsigned, 3>> &F);
 std::vector<unsigned> grab(const std::vector<Vec3d> &V, Vec3d dir, double eps = 1e-3);
+// make_woven_cylinder of examples/woven.ipynb / large-woven.ipynb: axial strands (open) and woven rings (closed)
+void gen_woven_cylinder(unsigned n, double offset, double scale, std::vector<std::vector<Vec3d>> &strands, std::vector<bool> &closed);
 
 // named scenes of BASELINE.json; `n` overrides the resolution (0 = the config's own)
 SceneSpec make_scene(const std::string &name, unsigned n);
@@ -130,7 +136,7 @@ struct Built {
     PpfDataSet dataset;
     PpfParamSet param;
     PpfConstraint constraint;
-    unsigned n_vert = 0;
+    unsigned n_vert = 0, n_rod = 0;
 };
 
 void build_scene(const SceneSpec &spec, Built &out);            // mesh.rs + scene.rs::make_props + builder.rs::build

@@ -82,6 +82,101 @@ static std::map<std::string, double> tri_defaults() { // params.rs:295-420 (Obje
             {"strain-limit", 0.0}, {"friction", 0.0}, {"pressure", 0.0}};
 }
 
+static std::map<std::string, double> rod_defaults() { // params.rs:295-420 (ObjectKind::Rod)
+    return {{"density", 1.0}, {"young-mod", 1e4}, {"bend", 0.0}, {"contact-gap", 1e-3}, {"contact-offset", 1e-3},
+            {"strain-limit", 0.0}, {"friction", 0.0}, {"length-factor", 1.0}, {"bend-plasticity", 0.0},
+            {"bend-plasticity-threshold", 0.0}, {"bend-rest-from-geometry", 0.0}, {"deformation-damping", 0.0},
+            {"bending-damping", 0.0}};
+}
+
+// make_woven_cylinder(n, offset, scale) of examples/woven.ipynb and examples/large-woven.ipynb (same code in both):
+// v_steps axial strands of n vertices on a cylinder of radius 0.5, and h_steps - 2 closed rings of 3 v_steps
+// vertices whose radius weaves over and under the strands by 1.2 * offset.
+void gen_woven_cylinder(unsigned n, double offset, double scale, std::vector<std::vector<Vec3d>> &strands, std::vector<bool> &closed) {
+    const double dx = 1.0 / double(n - 1), width = 1.25;
+    scale = 2.0 * 1.48 * scale;
+    const unsigned v_steps = (unsigned)(25.0 * scale);
+    const double sep = 0.5;
+    strands.clear();
+    closed.clear();
+    for (unsigned i = 0; i < v_steps; ++i) {
+        const double theta = 2.0 * M_PI * double(i) / double(v_steps);
+        std::vector<Vec3d> xyz(n);
+        for (unsigned k = 0; k < n; ++k) xyz[k] = Vec3d{width * (2.0 * dx * double(k) - 1.0), sep * std::sin(theta), sep * std::cos(theta)};
+        strands.push_back(std::move(xyz));
+        closed.push_back(false);
+    }
+    const unsigned h_steps = (unsigned)(30.0 * scale);
+    const unsigned ring_steps = v_steps * 3;
+    if (ring_steps % 2 != 0) throw std::runtime_error("woven cylinder: ring_steps must be even");
+    const double amp = 1.2 * offset, dx_h = 1.0 / double(h_steps - 1);
+    const unsigned half_v = v_steps / 2;
+    for (unsigned i = 1; i + 1 < h_steps; ++i) {
+        const double sgn = (i % 2 == 0) ? 1.0 : -1.0;
+        std::vector<Vec3d> xyz(ring_steps);
+        for (unsigned j = 0; j < ring_steps; ++j) {
+            const double theta = 2.0 * M_PI * double(j) / double(ring_steps);
+            const double r = sep + sgn * amp * std::cos(double(half_v) * theta);
+            xyz[j] = Vec3d{width * (2.0 * dx_h * double(i) - 1.0), r * std::sin(theta), r * std::cos(theta)};
+        }
+        strands.push_back(std::move(xyz));
+        closed.push_back(true);
+    }
+}
+
+// The woven family (examples/woven.ipynb, examples/large-woven.ipynb): one rod object per strand; the open
+// (axial) strands have both ends pinned with spin [-> scale] -> move_by; the notebooks' random() term of the
+// angular velocity is dropped.
+static SceneSpec woven_scene(const std::string &name, unsigned n, double offset, double scale, double gap, double contact_offset,
+                             double friction, double move_delta, double t_end, double pin_scale, double iso_air, unsigned max_nnz, int frames) {
+    SceneSpec s;
+    s.name = name;
+    std::vector<std::vector<Vec3d>> strands;
+    std::vector<bool> closed;
+    gen_woven_cylinder(n, offset, scale, strands, closed);
+    for (size_t k = 0; k < strands.size(); ++k) {
+        ShellObject o;
+        o.vert = strands[k];
+        const unsigned m = (unsigned)o.vert.size();
+        for (unsigned i = 0; i + 1 < m; ++i) o.rod.push_back({i, i + 1});
+        if (closed[k]) o.rod.push_back({m - 1, 0u});
+        double seg = 0.0; // mean drawn spacing (np.diff: the closing segment of a ring is not counted) times length-factor
+        for (unsigned i = 0; i + 1 < m; ++i) {
+            const Vec3d &a = o.vert[i], &c = o.vert[i + 1];
+            seg += std::sqrt((c[0] - a[0]) * (c[0] - a[0]) + (c[1] - a[1]) * (c[1] - a[1]) + (c[2] - a[2]) * (c[2] - a[2]));
+        }
+        seg = seg / double(m - 1) * 0.8;
+        o.rod_param = rod_defaults();
+        o.rod_param["bend"] = 1e-3 * (seg / 1e-2) * (seg / 1e-2);
+        o.rod_param["young-mod"] = 1e5;
+        o.rod_param["contact-gap"] = gap;
+        o.rod_param["contact-offset"] = contact_offset;
+        o.rod_param["friction"] = friction;
+        o.rod_param["length-factor"] = 0.8;
+        if (!closed[k])
+            for (int side = 0; side < 2; ++side) {
+                const double sg = side == 0 ? -1.0 : 1.0;
+                Pin p;
+                p.index = grab(o.vert, Vec3d{sg, 0, 0});
+                PinOp spin; spin.kind = PinOp::Spin; spin.axis = Vec3d{-sg, 0, 0}; spin.angular_velocity = 360.0;
+                PinOp mv;   mv.kind = PinOp::MoveBy; mv.delta = Vec3d{-sg * move_delta, 0, 0}; mv.t_start = 0; mv.t_end = t_end;
+                if (pin_scale != 1.0) {
+                    PinOp scl; scl.kind = PinOp::Scale; scl.factor = pin_scale; scl.t_start = 0; scl.t_end = t_end;
+                    p.ops = {spin, scl, mv};
+                } else p.ops = {spin, mv};
+                o.pins.push_back(p);
+            }
+        s.objects.push_back(std::move(o));
+    }
+    s.args.dt = 1.0 / 120.0;
+    s.args.frames = frames;
+    s.args.gravity = Vec3d{0, 0, 0};
+    s.args.isotropic_air_friction = iso_air;
+    s.args.friction_mode = "max";
+    s.args.csrmat_max_nnz = max_nnz;
+    return s;
+}
+
 // The twist family (examples/twist.ipynb, examples/large-twist.ipynb): one cylinder, both end
 // rings pinned with spin -> scale -> move_by applied in declaration order.
 static SceneSpec twist_scene(const std::string &name, double r, double half_len, unsigned n, double bend, double gap,
@@ -166,6 +261,18 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.friction_mode = "max";
         s.args.csrmat_max_nnz = 40000000u;
         return s;
+    }
+    if (name == "woven") { // examples/woven.ipynb; an overridden n keeps the vertex spacing along the strands (scale ~ n)
+        const unsigned nn = n ? n : 256;
+        double scale = 2.0 * double(nn) / 256.0;
+        if (n && (unsigned(25.0 * 2.0 * 1.48 * scale) & 1u)) scale = (double(unsigned(25.0 * 2.0 * 1.48 * scale) + 1) + 1e-9) / (25.0 * 2.0 * 1.48); // even strand count
+        return woven_scene(name, nn, 4e-3, scale, 1.5e-3, 2e-3, 0.01, 0.15, 10.0, 1.0, 1e-3, 10000000u, 450);
+    }
+    if (name == "large-woven") { // examples/large-woven.ipynb
+        const unsigned nn = n ? n : 1024;
+        double scale = 10.0 * double(nn) / 1024.0;
+        if (n && (unsigned(25.0 * 2.0 * 1.48 * scale) & 1u)) scale = (double(unsigned(25.0 * 2.0 * 1.48 * scale) + 1) + 1e-9) / (25.0 * 2.0 * 1.48);
+        return woven_scene(name, nn, 0.0015, scale, 0.125e-3, 0.0015 / 2.0, 0.001, 0.3, 20.0, 1.0 - 20.0 * 0.01, 1e-5, 180000000u, 1000);
     }
     if (name == "hang") { // examples/hang.ipynb
         SceneSpec s;

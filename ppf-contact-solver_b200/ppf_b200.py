@@ -22,7 +22,7 @@ LIB_REF = os.path.join(REPO, "oracle", "_ref", "libsimbackend_cuda.so")
 LIB_HOST = os.path.join(ROOT, "lib", "libppf_host.so")
 # the CPU oracle (TEST INFRASTRUCTURE): tests, smoke() and bench.py's cpu_baseline leg only
 LIB_ORACLE = os.path.join(REPO, "oracle", "build", "libppf_oracle.so")
-DEFAULT_RESOLUTION = {"five-twist": 180, "twist": 360, "large-twist": 1410, "fast-twist": 48, "hang": 128, "sheet": 32}  # host/scene.cpp
+DEFAULT_RESOLUTION = {"five-twist": 180, "twist": 360, "large-twist": 1410, "fast-twist": 48, "hang": 128, "sheet": 32, "woven": 256, "large-woven": 1024}  # host/scene.cpp
 HOST_BIN = os.path.join(ROOT, "bin", "ppf_host")
 
 ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"
@@ -238,6 +238,16 @@ class Session:
         face = np.empty((self.n_face, 3), np.uint32); edge = np.empty((self.n_edge, 2), np.uint32); vp = np.empty((self.n_vert, 2), np.float32)
         self.h.ppfh_topology(self.p, face.ctypes.data_as(ctypes.c_void_p), edge.ctypes.data_as(ctypes.c_void_p), vp.ctypes.data_as(ctypes.c_void_p))
         return face, edge, vp
+
+    def rods(self):
+        """rod_count, per-rod (rest length, initial length, mass, stiffness, bend), per-vertex (mass, rest bend angle),
+        rod-bend slots (n_vert, 9), fixed index table (offset, columns)"""
+        n_rod = int(self.h.ppfh_rods(self.p, None, None, None, None, None))
+        rod = np.empty((n_rod, 5), np.float32); vert = np.empty((self.n_vert, 2), np.float32); slots = np.empty((self.n_vert, 9), np.uint32)
+        off = np.empty(self.n_vert + 1, np.uint32); col = np.empty(self.fixed_nnz, np.uint32)
+        vp = ctypes.c_void_p
+        self.h.ppfh_rods(self.p, rod.ctypes.data_as(vp), vert.ctypes.data_as(vp), slots.ctypes.data_as(vp), off.ctypes.data_as(vp), col.ctypes.data_as(vp))
+        return n_rod, rod, vert, slots, off, col
 
     def read_log(self, channel):
         p = os.path.join(self.log_dir, "advance.%s.out" % channel)

@@ -55,3 +55,86 @@ def test_state_round_trip_and_stepping_through_the_abi(ppf, run_job, tmp_path):
     assert bool(r2["ok"].all()) and float(r2["time"][0]) > st["time"]
     assert abs((float(r2["time"][0]) - st["time"]) - 2 * 0.016665) < 1e-4  # dt = min(dt, 0.9999 / fps)
     assert np.isfinite(r2["curr"]).all()
+
+
+def _rods(ppf, scene, n):
+    """built rod scene through the C API (no backend): counts, edges, rod props, vertex props, tables"""
+    import ctypes
+
+    h = ppf.host()
+    h.ppfh_rods.restype = ctypes.c_uint
+    p = ctypes.c_void_p(h.ppfh_create(scene.encode(), ctypes.c_uint(n)))
+    c = (ctypes.c_uint * 6)()
+    h.ppfh_counts(p, c)
+    nv, nf, ne, nh, nfix, nnz = [int(v) for v in c]
+    vp = ctypes.c_void_p
+    n_rod = int(h.ppfh_rods(p, None, None, None, None, None))
+    rod = np.empty((n_rod, 5), np.float32); vert = np.empty((nv, 2), np.float32); slots = np.empty((nv, 9), np.uint32)
+    off = np.empty(nv + 1, np.uint32); col = np.empty(nnz, np.uint32)
+    h.ppfh_rods(p, rod.ctypes.data_as(vp), vert.ctypes.data_as(vp), slots.ctypes.data_as(vp), off.ctypes.data_as(vp), col.ctypes.data_as(vp))
+    edge = np.empty((ne, 2), np.uint32); par = np.empty((nv, 2), np.float32)
+    h.ppfh_topology(p, None, edge.ctypes.data_as(vp), par.ctypes.data_as(vp))
+    h.ppfh_destroy(p)
+    return dict(nv=nv, nf=nf, ne=ne, nh=nh, nfix=nfix, nnz=nnz, n_rod=n_rod, rod=rod, vert=vert, slots=slots, off=off, col=col, edge=edge, vparam=par)
+
+
+def test_woven_scene_sizes_match_the_reference_examples(ppf):
+    """examples/woven.ipynb: 115.6 K vertices / 115.4 K rods (README.md:599); strands 148 x 256, rings 175 x 444"""
+    r = _rods(ppf, "woven", 0)
+    assert (r["nv"], r["n_rod"], r["ne"], r["nf"], r["nh"]) == (148 * 256 + 175 * 444, 148 * 255 + 175 * 444, 148 * 255 + 175 * 444, 0, 0)
+    assert r["nfix"] == 2 * 148                                   # both ends of every axial strand
+    # diagonal + one block per rod edge + one (j, k) block per interior vertex (every vertex but the 2 x 148 strand ends)
+    assert r["nnz"] == r["nv"] + r["n_rod"] + (r["nv"] - 2 * 148)
+
+
+def test_rod_tables_are_consistent(ppf):
+    r = _rods(ppf, "woven", 32)
+    nv, n_rod, edge, rod, vert, slots, off, col = r["nv"], r["n_rod"], r["edge"], r["rod"], r["vert"], r["slots"], r["off"], r["col"]
+    assert n_rod == r["ne"] and n_rod > 0
+    # rest length = drawn length x length-factor 0.8; mass = density x drawn length; mass lumped half / half
+    assert np.allclose(rod[:, 0], 0.8 * rod[:, 1], rtol=1e-6) and np.allclose(rod[:, 2], rod[:, 1], rtol=1e-6)
+    m = np.zeros(nv); np.add.at(m, edge[:, 0], 0.5 * rod[:, 2]); np.add.at(m, edge[:, 1], 0.5 * rod[:, 2])
+    assert np.allclose(vert[:, 0], m, rtol=1e-5)
+    assert (rod[:, 3] == np.float32(1e5)).all()
+    # bend = 1e-3 (seg / 1 cm)^2 with seg = mean drawn spacing x 0.8, per strand
+    assert np.allclose(rod[:, 4], 1e-3 * (rod[:, 0] / 1e-2) ** 2, rtol=2e-2)
+    assert (vert[:, 1] == np.float32(np.pi)).all()                # straight rest shape unless bend-rest-from-geometry
+    # length-weighted average of identical rod parameters: equal up to the rounding of (w0 g + w1 g) / (w0 + w1)
+    assert np.allclose(r["vparam"][:, 0], 1.5e-3, rtol=1e-6) and np.allclose(r["vparam"][:, 1], 2e-3, rtol=1e-6)
+    # fixed index table: sorted rows starting at the diagonal, upper triangle only
+    deg = np.zeros(nv, np.int64); np.add.at(deg, edge[:, 0], 1); np.add.at(deg, edge[:, 1], 1)
+    for i in range(nv):
+        row = col[off[i]:off[i + 1]]
+        assert row[0] == i and (np.diff(row.astype(np.int64)) > 0).all()
+    # bending stencil (j, i, k) of every interior vertex: slot(a, b) addresses column max(a, b)'s entry of row min(a, b)
+    nbr = [[] for _ in range(nv)]
+    for e0, e1 in edge:
+        nbr[e0].append(int(e1)); nbr[e1].append(int(e0))
+    n_interior = 0
+    for i in range(nv):
+        if deg[i] != 2:
+            assert (slots[i] == 0xFFFFFFFF).all()
+            continue
+        n_interior += 1
+        st = [nbr[i][0], i, nbr[i][1]]
+        for a in range(3):
+            for b in range(3):
+                s = slots[i, 3 * a + b]
+                if st[a] > st[b]:
+                    assert s == 0xFFFFFFFF
+                else:
+                    assert off[st[a]] <= s < off[st[a] + 1] and col[s] == st[b]
+    assert n_interior == nv - r["nfix"]
+
+
+def test_oracle_steps_a_woven_rod_scene(run_job):
+    """CPU restatement on a small woven cylinder: contacts from the first step, rods keep their length, pins are exact"""
+    o = run_job({"lib": "oracle", "scene": "woven", "n": 32, "state": None, "steps": 6, "fix_positions": True})
+    assert bool(o["ok"].all()) and np.isfinite(o["curr"]).all()
+    assert o["log_num_contact"].min() > 100 and (o["log_toi"] > 0).all() and (o["log_toi"] <= 1).all()
+    idx = o["fix_index"].astype(np.int64)
+    # a step that the line search cuts short rewinds its kinematic pins by (1 - toi_advanced) of their per-step motion
+    # (main.cu:1418-1440), so the pins sit between the previous and the current targets
+    assert idx.size == 36 and float(np.abs(o["curr"][idx] - o["fix_target"]).max()) < 0.03
+    first = run_job({"lib": "oracle", "scene": "woven", "n": 32, "state": None, "steps": 1, "fix_positions": True})
+    assert (first["log_toi"] == 1.0).all() and np.array_equal(first["curr"][idx], first["fix_target"])   # full step: exact Dirichlet rows
