@@ -284,8 +284,9 @@ def main():
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "%s: cylinder n=%s, V=%d F=%d E=%d hinges=%d, dt=1/60, steps from t=0; %s" % (
-            args.scene, args.n or "config default", s.n_vert, s.n_face, s.n_edge, s.n_hinge,
+        "config": {"workload": "%s: %s n=%s, V=%d F=%d E=%d hinges=%d, dt=%s, steps from t=0; %s" % (
+            args.scene, "woven rod cylinder" if "woven" in args.scene else "cylinder", args.n or "config default", s.n_vert, s.n_face, s.n_edge, s.n_hinge,
+            "1/120" if "woven" in args.scene else ("1e-3" if args.scene == "hang" else "1/60"),
             ("one scene, PCG rows sharded over %d GPUs (rows of p pushed + two 2-double sums per iteration over NVLink peer memory)" % WORLD) if shard is not None
             else ("replicas (one independent scene per GPU)" if WORLD > 1 else "single GPU")),
             "l2": "inputs larger than L2 (packed matrix %.0f MB per SpMV)" % ((40.0 * (st1["spmv_n_off"] if st1 else 0) + 60.0 * s.n_vert) * 1e-6)},

@@ -546,4 +546,59 @@ static inline float o_rod_bend_coefficient(float bend0, float bend1, float len0,
     return voronoi > 0.0f ? bend * mass * (REF_LENGTH * REF_LENGTH) / (voronoi * voronoi) : 0.0f;
 }
 
+/* ---- rod strain limiting (strainlimiting/strainlimiting.cu:100-190, 192-245) ---- */
+static inline void o_mtv3(const float *M, const float *x, float *y) { /* y = M^T x, M column-major */
+    for (int c = 0; c < 3; ++c) y[c] = M[c * 3 + 0] * x[0] + M[c * 3 + 1] * x[1] + M[c * 3 + 2] * x[2];
+}
+/* barrier on the stretch g = l / l0 - 1 beyond the DRAWN length l0, gap = limit; Hessian [[K,-K],[-K,K]];
+ * Hel00 / Hel01 / Hel11: blocks (e0,e0), (e0,e1), (e1,e1) of the elastic-only matrix; c0, c1: start-of-step positions */
+static inline int o_rod_strain(const float *x0, const float *x1, const float *c0, const float *c1, float l0, float limit, float mass,
+                               const float *Hel00, const float *Hel01, const float *Hel11, float f[2][3], float *K) {
+    float d[3];
+    o_sub(x1, x0, d);
+    const float l = o_norm3(d);
+    const float g = l / l0 - 1.0f;
+    if (!(g > 0.0f)) return 0;
+    const float y = limit - g;
+    const float dEdg = -o_cubic_gradient(y, limit, 0.0f);
+    const float d2Edg2 = o_cubic_curvature(y, limit, 0.0f);
+    const float n[3] = {d[0] / l, d[1] / l, d[2] / l};
+    const float inv_ll0 = 1.0f / (l * l0);
+    const float a_psd = fmaxf(0.0f, d2Edg2), b_psd = fmaxf(0.0f, dEdg);
+    float w0[3], w1[3], y0[3], y1[3], t0[3], t1[3];
+    for (int k = 0; k < 3; ++k) { const float ce = 0.5f * c0[k] + 0.5f * c1[k]; w0[k] = c0[k] - ce; w1[k] = c1[k] - ce; }
+    o_mv3(Hel00, w0, t0); o_mv3(Hel01, w1, t1);
+    for (int k = 0; k < 3; ++k) y0[k] = t0[k] + t1[k];
+    o_mtv3(Hel01, w0, t0); o_mv3(Hel11, w1, t1);
+    for (int k = 0; k < 3; ++k) y1[k] = t0[k] + t1[k];
+    const float dd = limit - g;
+    const float stiffness = (o_dot(w0, y0) + o_dot(w1, y1)) + mass / (dd * dd);
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) {
+            const float P = (r == c ? 1.0f : 0.0f) - n[r] * n[c];
+            K[c * 3 + r] = stiffness * (a_psd * ((n[r] / l0) * (n[c] / l0)) + b_psd * (inv_ll0 * P));
+        }
+    for (int k = 0; k < 3; ++k) { const float j1 = n[k] / l0; f[0][k] = stiffness * (dEdg * (-j1)); f[1][k] = stiffness * (dEdg * j1); }
+    return 1;
+}
+static inline float o_rod_strain_toi(const float *d0, const float *d1, float l0, float limit, float max_t) {
+    float t = max_t, dd[3], p[3];
+    o_sub(d1, d0, dd);
+    for (int k = 0; k < 3; ++k) p[k] = d0[k] + t * dd[k];
+    if (o_norm3(p) / l0 - 1.0f >= limit) {
+        float upper_t = t, lower_t = 0.0f, window = upper_t - lower_t;
+        for (;;) {
+            t = 0.5f * (upper_t + lower_t);
+            for (int k = 0; k < 3; ++k) p[k] = d0[k] + t * dd[k];
+            if ((o_norm3(p) / l0 - 1.0f) - limit < 0.0f) lower_t = t;
+            else upper_t = t;
+            const float nw = upper_t - lower_t;
+            if (nw == window) break;
+            window = nw;
+        }
+        t = lower_t;
+    }
+    return t;
+}
+
 #endif

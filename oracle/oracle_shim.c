@@ -80,3 +80,13 @@ SHIM void orc_strand(const float *x9, float rest_angle, float *force9, float *he
     for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) force9[3 * a + k] = f[a][k];
 }
 SHIM float orc_rod_bend_coefficient(float b0, float b1, float l0, float l1, float mass) { return o_rod_bend_coefficient(b0, b1, l0, l1, mass); }
+/* rod strain limiting: Hel27 = blocks (e0,e0), (e0,e1), (e1,e1) column-major; returns 0 when the edge is not stretched */
+SHIM int orc_rod_strain(const float *x6, const float *c6, float l0, float limit, float mass, const float *Hel27, float *grad6, float *hess36) {
+    float f[2][3], K[9];
+    if (!o_rod_strain(x6, x6 + 3, c6, c6 + 3, l0, limit, mass, Hel27, Hel27 + 9, Hel27 + 18, f, K)) return 0;
+    for (int a = 0; a < 2; ++a) for (int k = 0; k < 3; ++k) grad6[3 * a + k] = f[a][k];
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+        hess36[(3 * b + c) * 6 + 3 * a + r] = (a == b ? 1.0f : -1.0f) * K[c * 3 + r];
+    return 1;
+}
+SHIM float orc_rod_strain_toi(const float *d0, const float *d1, float l0, float limit, float max_t) { return o_rod_strain_toi(d0, d1, l0, limit, max_t); }

@@ -118,8 +118,8 @@ void upload_dataset(State &s) {
     if (d.rod_count > ne) fatal(4, "rod_count %u exceeds the edge count %u", d.rod_count, ne);
     for (unsigned i = 0; i < d.rod_count; ++i) {
         const PpfEdgeParam &ep = d.param_arrays.edge.data[d.prop.edge.data[i].param_index];
-        if (ep.strainlimit > 0.0f || ep.deform_damping > 0.0f || ep.bend_damping > 0.0f || ep.plasticity > 0.0f)
-            fatal(4, "B200 backend: rod strain limiting / Rayleigh damping / bend plasticity are not implemented");
+        if (ep.deform_damping > 0.0f || ep.bend_damping > 0.0f || ep.plasticity > 0.0f)
+            fatal(4, "B200 backend: rod Rayleigh damping / bend plasticity are not implemented");
     }
     if (d.rod_count && (d.edge_hess_slots.size < 4u * d.rod_count || d.rod_bend_hess_slots.size != 9u * d.surface_vert_count))
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
@@ -241,6 +241,15 @@ void upload_dataset(State &s) {
             const PpfEdgeParam &ep = d.param_arrays.edge.data[p.param_index];
             rp[i] = make_float2(p.length, ep.stiffness > 0.0f ? ep.stiffness * p.mass : 0.0f);
         }
+        std::vector<float2> rs(s.nrod);
+        s.has_rod_strainlimit = false;
+        for (unsigned i = 0; i < s.nrod; ++i) { // strainlimiting.cu:135-139
+            const PpfEdgeProp &p = d.prop.edge.data[i];
+            const float limit = d.param_arrays.edge.data[p.param_index].strainlimit;
+            rs[i] = make_float2(limit > 0.0f && p.initial_length > 0.0f ? limit : 0.0f, p.initial_length);
+            if (rs[i].x > 0.0f) s.has_rod_strainlimit = true;
+        }
+        s.rod_sl.upload(rs.data(), s.nrod, q);
         s.rod_par.upload(rp.data(), s.nrod, q);
         s.rod_slots.upload(d.edge_hess_slots.data, size_t(4) * s.nrod, q);
         CUDA_OK(cudaStreamSynchronize(q));

@@ -124,6 +124,8 @@ struct State {
     unsigned nrod = 0, nrodbend = 0;
     DBuf<float2> rod_par;                         // per rod edge (rest length, stiffness * mass); weight 0 = skip
     DBuf<unsigned> rod_slots;                     // 4 per rod edge (DataSet.edge_hess_slots)
+    DBuf<float2> rod_sl;                          // per rod edge (strain limit, drawn length); limit 0 = off
+    bool has_rod_strainlimit = false;
     DBuf<uint4> rb_elem;                          // per bending vertex i: (j, i, k, -), its stencil in scatter order
     DBuf<float2> rb_par;                          // per bending vertex (bending coefficient, rest angle)
     DBuf<unsigned> rb_slots;                      // 9 per bending vertex (DataSet.rod_bend_hess_slots rows of those vertices)
@@ -193,6 +195,7 @@ void assemble_momentum(State &s, float dt, const PpfParamSet &prm);
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
 void assemble_strainlimit(State &s, const PpfParamSet &prm);                                  // after the elastic snapshot
 float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // fraction in (0, 1]
+float rod_strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // same for rod edges
 void recompute_fixed_flags(State &s);
 
 // bvh.cu

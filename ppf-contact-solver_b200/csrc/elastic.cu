@@ -266,11 +266,85 @@ __global__ void __launch_bounds__(128) k_strain_toi(unsigned nf, const uint4 *__
     if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
 }
 
+// ---- rod strain limiting (strainlimiting.cu:122-245; math_rod.cuh) ----
+__device__ __forceinline__ M3 ld_block(const float *__restrict__ val, unsigned slot) {
+    M3 m;
+    const float *p = val + size_t(9) * slot;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) m.m[e] = p[e];
+    return m;
+}
+__global__ void __launch_bounds__(128) k_rod_strain(unsigned nrod, const uint2 *__restrict__ edge, const float4 *__restrict__ eval_x,
+                                                    const float4 *__restrict__ curr, const float2 *__restrict__ rod_sl,
+                                                    const float4 *__restrict__ ecp, const unsigned char *__restrict__ efixed,
+                                                    const unsigned *__restrict__ slots, const float *__restrict__ fx_el,
+                                                    float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrod || efixed[i]) return;
+    const float2 sl2 = rod_sl[i]; // (limit, drawn length)
+    if (!(sl2.x > 0.0f)) return;
+    const uint2 e = edge[i];
+    const V3 x0 = ld3(eval_x, e.x), x1 = ld3(eval_x, e.y);
+    if (!(norm(x1 - x0) / sl2.y - 1.0f > 0.0f)) return; // not stretched: skip the block gathers
+    const unsigned *sl = slots + size_t(4) * i;
+    const M3 H00 = ld_block(fx_el, sl[0]), H11 = ld_block(fx_el, sl[3]);
+    const M3 H01 = sl[1] != 0xFFFFFFFFu ? ld_block(fx_el, sl[1]) : transpose(ld_block(fx_el, sl[2]));
+    RodElastic re;
+    if (!rod_strain(x0, x1, ld3(curr, e.x), ld3(curr, e.y), sl2.y, sl2.x, ecp[i].w, H00, H01, H11, re)) return;
+    atomic_add3(force + size_t(3) * e.x, re.f[0]);
+    atomic_add3(force + size_t(3) * e.y, re.f[1]);
+    float neg[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) neg[k] = -re.K.m[k];
+    atomic_add_block(val, sl[0], re.K.m);
+    atomic_add_block(val, sl[1], neg);
+    atomic_add_block(val, sl[2], neg);
+    atomic_add_block(val, sl[3], re.K.m);
+}
+__global__ void __launch_bounds__(128) k_rod_strain_toi(unsigned nrod, const uint2 *__restrict__ edge, const float4 *__restrict__ x0,
+                                                        const float4 *__restrict__ x1, const float2 *__restrict__ rod_sl,
+                                                        const unsigned char *__restrict__ efixed, float max_t, unsigned *toi_bits) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float t = max_t;
+    if (i < nrod && !efixed[i]) {
+        const float2 sl2 = rod_sl[i];
+        if (sl2.x > 0.0f) {
+            const uint2 e = edge[i];
+            t = rod_strain_toi(ld3(x0, e.y) - ld3(x0, e.x), ld3(x1, e.y) - ld3(x1, e.x), sl2.y, sl2.x, max_t);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
+}
+
 void assemble_strainlimit(State &s, const PpfParamSet &prm) {
-    if (!s.has_strainlimit || !s.nf) return;
-    k_strainlimit<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.curr.p, s.fmat.p, s.fstrain.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
-                                                           s.fx_off.p, s.fx_col.p, s.fx_el.p, s.face_slots.p, prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+    if (s.has_strainlimit && s.nf) {
+        k_strainlimit<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.curr.p, s.fmat.p, s.fstrain.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
+                                                               s.fx_off.p, s.fx_col.p, s.fx_el.p, s.face_slots.p, prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
+    if (s.has_rod_strainlimit && s.nrod) {
+        k_rod_strain<<<div_up(s.nrod, 128), 128, 0, s.stream>>>(s.nrod, s.edge.p, s.eval_x.p, s.curr.p, s.rod_sl.p, s.ecp.p, s.efixed.p, s.rod_slots.p,
+                                                                s.fx_el.p, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
+}
+// strainlimiting::rod_line_search: fraction of the step x0 -> x1 that keeps every rod edge below its strain limit
+float rod_strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm) {
+    if (!s.has_rod_strainlimit || !s.nrod) return 1.0f;
+    unsigned *w = s.counters.p + 26;
+    const float max_t = prm.line_search_max_t;
+    unsigned init;
+    memcpy(&init, &max_t, sizeof(float));
+    CUDA_OK(cudaMemcpyAsync(w, &init, sizeof(unsigned), cudaMemcpyHostToDevice, s.stream));
+    k_rod_strain_toi<<<div_up(s.nrod, 128), 128, 0, s.stream>>>(s.nrod, s.edge.p, x0, x1, s.rod_sl.p, s.efixed.p, max_t, w);
     LAUNCH_COUNT(1);
+    unsigned h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, w, sizeof(unsigned), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_OK(cudaStreamSynchronize(s.stream));
+    float t;
+    memcpy(&t, &h, sizeof(float));
+    return t / max_t;
 }
 // strainlimiting::line_search: fraction of the step x0 -> x1 that keeps every face below its strain limit
 float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm) {

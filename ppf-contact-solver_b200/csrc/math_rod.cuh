@@ -7,6 +7,7 @@
 // in the 6-D space of the two segment vectors, mapped to the 9 DOFs by J^T [qa; qb] = [qa; -qa-qb; qb]),
 // plus the rod strain-limit barrier of strainlimiting/strainlimiting.cu:125-190.
 #pragma once
+#include "math_contact.cuh"
 #include "vecmath.cuh"
 
 namespace ppf {
@@ -129,6 +130,65 @@ PPF_HD float rod_bend_coefficient(float bend0, float bend1, float len0, float le
     const float REF_LENGTH = 1e-2f;
     const float voronoi = 0.5f * (len0 + len1);
     return voronoi > 0.0f ? bend * mass * (REF_LENGTH * REF_LENGTH) / (voronoi * voronoi) : 0.0f;
+}
+
+// ---- rod strain limiting (strainlimiting/strainlimiting.cu:100-190) ----
+// Barrier on the stretch g = l / l0 - 1 of a rod edge beyond its DRAWN length l0 (EdgeProp.initial_length), gap = the
+// strain limit.  Same block structure as the Hookean term: Hessian [[K, -K], [-K, K]].  Hel00 / Hel01 / Hel11 are the
+// blocks (e0,e0), (e0,e1), (e1,e1) of the elastic-only matrix (FixedCSRMat::operator(), transposed when stored as (e1,e0));
+// c0, c1 are the start-of-step positions the stiffness is evaluated at.  Returns false when the edge is not stretched.
+PPF_HD bool rod_strain(const V3 &x0, const V3 &x1, const V3 &c0, const V3 &c1, float l0, float limit, float mass, const M3 &Hel00,
+                       const M3 &Hel01, const M3 &Hel11, RodElastic &o) {
+    const V3 d = x1 - x0;
+    const float l = norm(d);
+    const float g = l / l0 - 1.0f;
+    if (!(g > 0.0f)) return false;
+    const float y = limit - g;
+    const float dEdg = -cubic_gradient(y, limit, 0.0f);
+    const float d2Edg2 = cubic_curvature(y, limit, 0.0f);
+    const V3 n = d / l;
+    const float inv_ll0 = 1.0f / (l * l0);
+    const float a_psd = fmaxf(0.0f, d2Edg2);
+    const float b_psd = fmaxf(0.0f, dEdg);
+    // compute_rod_stiffness: w^T H_el w + mass / (limit - g)^2 with w = (c0 - center, c1 - center)
+    const V3 center = 0.5f * c0 + 0.5f * c1;
+    const V3 w0 = c0 - center, w1 = c1 - center;
+    const V3 y0 = mul(Hel00, w0) + mul(Hel01, w1);
+    const V3 y1 = mul_t(Hel01, w0) + mul(Hel11, w1);
+    const float dd = limit - g;
+    const float stiffness = (dot(w0, y0) + dot(w1, y1)) + mass / (dd * dd);
+    const float nv[3] = {n.x, n.y, n.z};
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) {
+            const float P = (r == c ? 1.0f : 0.0f) - nv[r] * nv[c];
+            o.K.m[c * 3 + r] = stiffness * (a_psd * ((nv[r] / l0) * (nv[c] / l0)) + b_psd * (inv_ll0 * P));
+        }
+    const V3 j1 = n / l0;
+    o.f[0] = stiffness * (dEdg * (-j1));
+    o.f[1] = stiffness * (dEdg * j1);
+    return true;
+}
+// strainlimiting::rod_line_search (strainlimiting.cu:192-245): largest t in (0, max_t] keeping the stretch of the
+// segment d0 + t (d1 - d0) below the limit, by bisection until the bracket stops shrinking
+PPF_HD float rod_strain_toi(const V3 &d0, const V3 &d1, float l0, float limit, float max_t) {
+    float t = max_t;
+    const V3 dd = d1 - d0;
+    const float g_t = norm(d0 + t * dd) / l0 - 1.0f;
+    if (g_t >= limit) {
+        float upper_t = t, lower_t = 0.0f;
+        float window = upper_t - lower_t;
+        while (true) {
+            t = 0.5f * (upper_t + lower_t);
+            const float g_here = norm(d0 + t * dd) / l0 - 1.0f;
+            if (g_here - limit < 0.0f) lower_t = t;
+            else upper_t = t;
+            const float new_window = upper_t - lower_t;
+            if (new_window == window) break;
+            window = new_window;
+        }
+        t = lower_t;
+    }
+    return t;
 }
 
 } // namespace ppf

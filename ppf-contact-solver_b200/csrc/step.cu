@@ -311,6 +311,11 @@ void step_advance(State &s, PpfStepResult *out) {
             toi = fminf(toi, sl_toi);
             logging.mark("SL_toi", sl_toi);
         }
+        if (s.has_rod_strainlimit) { // strainlimiting::rod_line_search (main.cu:1336-1343)
+            const float sl_toi = rod_strain_line_search(s, s.x_old.p, s.eval_x.p, prm);
+            toi = fminf(toi, sl_toi);
+            logging.mark("SL_rod_toi", sl_toi);
+        }
         logging.mark("toi", toi);
         last_toi = toi;
         if (toi <= std::numeric_limits<float>::epsilon()) {

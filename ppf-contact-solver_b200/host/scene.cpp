@@ -128,7 +128,8 @@ void gen_woven_cylinder(unsigned n, double offset, double scale, std::vector<std
 // (axial) strands have both ends pinned with spin [-> scale] -> move_by; the notebooks' random() term of the
 // angular velocity is dropped.
 static SceneSpec woven_scene(const std::string &name, unsigned n, double offset, double scale, double gap, double contact_offset,
-                             double friction, double move_delta, double t_end, double pin_scale, double iso_air, unsigned max_nnz, int frames) {
+                             double friction, double move_delta, double t_end, double pin_scale, double iso_air, unsigned max_nnz, int frames,
+                             double strain_limit = 0.0, double ang_vel = 360.0) {
     SceneSpec s;
     s.name = name;
     std::vector<std::vector<Vec3d>> strands;
@@ -153,12 +154,13 @@ static SceneSpec woven_scene(const std::string &name, unsigned n, double offset,
         o.rod_param["contact-offset"] = contact_offset;
         o.rod_param["friction"] = friction;
         o.rod_param["length-factor"] = 0.8;
+        o.rod_param["strain-limit"] = strain_limit;
         if (!closed[k])
             for (int side = 0; side < 2; ++side) {
                 const double sg = side == 0 ? -1.0 : 1.0;
                 Pin p;
                 p.index = grab(o.vert, Vec3d{sg, 0, 0});
-                PinOp spin; spin.kind = PinOp::Spin; spin.axis = Vec3d{-sg, 0, 0}; spin.angular_velocity = 360.0;
+                PinOp spin; spin.kind = PinOp::Spin; spin.axis = Vec3d{-sg, 0, 0}; spin.angular_velocity = ang_vel;
                 PinOp mv;   mv.kind = PinOp::MoveBy; mv.delta = Vec3d{-sg * move_delta, 0, 0}; mv.t_start = 0; mv.t_end = t_end;
                 if (pin_scale != 1.0) {
                     PinOp scl; scl.kind = PinOp::Scale; scl.factor = pin_scale; scl.t_start = 0; scl.t_end = t_end;
@@ -267,6 +269,12 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         double scale = 2.0 * double(nn) / 256.0;
         if (n && (unsigned(25.0 * 2.0 * 1.48 * scale) & 1u)) scale = (double(unsigned(25.0 * 2.0 * 1.48 * scale) + 1) + 1e-9) / (25.0 * 2.0 * 1.48); // even strand count
         return woven_scene(name, nn, 4e-3, scale, 1.5e-3, 2e-3, 0.01, 0.15, 10.0, 1.0, 1e-3, 10000000u, 450);
+    }
+    if (name == "woven-sl") { // test scene: the woven cylinder stretched by 1.6 % along its axis within 0.5 s (slow spin), rods with a 2 % strain limit
+        const unsigned nn = n ? n : 32;
+        double scale = 2.0 * double(nn) / 256.0;
+        if (unsigned(25.0 * 2.0 * 1.48 * scale) & 1u) scale = (double(unsigned(25.0 * 2.0 * 1.48 * scale) + 1) + 1e-9) / (25.0 * 2.0 * 1.48);
+        return woven_scene(name, nn, 4e-3, scale, 1.5e-3, 2e-3, 0.01, -0.015, 0.5, 1.0, 1e-3, 10000000u, 240, 0.02, 0.0);
     }
     if (name == "large-woven") { // examples/large-woven.ipynb
         const unsigned nn = n ? n : 1024;

@@ -16,7 +16,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "ppf-contact-solver_b200"))
 
-CHANNELS = ("num_contact", "iter", "toi", "SL_toi", "newton_steps", "toi_advanced", "max_dx", "reresid")
+CHANNELS = ("num_contact", "iter", "toi", "SL_toi", "SL_rod_toi", "newton_steps", "toi_advanced", "max_dx", "reresid")
 
 
 def run(job):

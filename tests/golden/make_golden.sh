@@ -24,7 +24,7 @@ gen() { # name scene n steps save_every states...
 import json, os, sys
 d = sys.argv[1]
 logs = {}
-for ch in ("num_contact", "iter", "toi", "SL_toi", "newton_steps", "toi_advanced", "final_dt", "max_dx", "reresid", "dyn_consumed"):
+for ch in ("num_contact", "iter", "toi", "SL_toi", "SL_rod_toi", "max_sigma", "newton_steps", "toi_advanced", "final_dt", "max_dx", "reresid", "dyn_consumed"):
     p = os.path.join(d, "data", "advance.%s.out" % ch)
     logs[ch] = [float(l.split()[1]) for l in open(p)] if os.path.exists(p) else []
 json.dump(logs, open(os.path.join(d, "logs.json"), "w"))
@@ -39,10 +39,12 @@ case "$1" in
   five-only) gen five_twist_n24 five-twist 24 100 50 00050 00100 ;;
   hang-only) gen hang_n32 hang 32 300 150 00150 00300 ;;
   woven-only) gen woven_n32 woven 32 120 60 00060 00120 ;;
+  woven-sl-only) gen woven_sl_n32 woven-sl 32 160 80 00080 00160 ;;
   *) gen fast_twist_n16 fast-twist 16 90 30 00030 00060 00090
      gen fast_twist_n24 fast-twist 24 80 40 00040 00080
      gen five_twist_n24 five-twist 24 100 50 00050 00100
      gen hang_n32 hang 32 300 150 00150 00300
-     gen woven_n32 woven 32 120 60 00060 00120 ;;
+     gen woven_n32 woven 32 120 60 00060 00120
+     gen woven_sl_n32 woven-sl 32 160 80 00080 00160 ;;
 esac
 du -sh gpurun_out/golden/*

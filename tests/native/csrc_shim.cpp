@@ -92,3 +92,15 @@ SHIM void orc_strand(const float *x9, float rest_angle, float *force9, float *he
     for (int i = 0; i < 81; ++i) hess81[i] = se.H[i];
 }
 SHIM float orc_rod_bend_coefficient(float b0, float b1, float l0, float l1, float mass) { return rod_bend_coefficient(b0, b1, l0, l1, mass); }
+// rod strain limiting: Hel27 = blocks (e0,e0), (e0,e1), (e1,e1) column-major; outputs like orc_rod_hook; returns 0 when not stretched
+SHIM int orc_rod_strain(const float *x6, const float *c6, float l0, float limit, float mass, const float *Hel27, float *grad6, float *hess36) {
+    M3 h[3];
+    for (int q = 0; q < 3; ++q) for (int e = 0; e < 9; ++e) h[q].m[e] = Hel27[9 * q + e];
+    RodElastic re;
+    if (!rod_strain(v(x6), v(x6 + 3), v(c6), v(c6 + 3), l0, limit, mass, h[0], h[1], h[2], re)) return 0;
+    for (int a = 0; a < 2; ++a) { grad6[3 * a] = re.f[a].x; grad6[3 * a + 1] = re.f[a].y; grad6[3 * a + 2] = re.f[a].z; }
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+        hess36[(3 * b + c) * 6 + 3 * a + r] = (a == b ? 1.0f : -1.0f) * re.K.m[c * 3 + r];
+    return 1;
+}
+SHIM float orc_rod_strain_toi(const float *d0, const float *d1, float l0, float limit, float max_t) { return rod_strain_toi(v(d0), v(d1), l0, limit, max_t); }

@@ -95,3 +95,22 @@ def test_woven_at_full_size_keeps_its_invariants(run_job):
     x = r["curr"].astype(np.float64)
     ln = np.linalg.norm(x[edge[:, 0]] - x[edge[:, 1]], axis=1)
     assert ln.min() > 3e-3 and ln.max() < 2.5e-2
+
+
+def test_rod_strain_limit_matches_the_oracle(run_job):
+    """woven-sl: the woven cylinder stretched along its axis, rods with a 2 % strain limit (strainlimiting.cu:122-245).
+    The strain-limit line search cuts the very first Newton step; compare the cut and the result with the oracle."""
+    job = {"scene": "woven-sl", "n": 32, "state": None, "steps": 3, "dump_linsys": True}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    assert len(g["log_SL_rod_toi"]) == len(o["log_SL_rod_toi"]) > 0 and o["log_SL_rod_toi"].min() < 1.0
+    assert abs(g["log_SL_rod_toi"][0] - o["log_SL_rod_toi"][0]) < 2e-3      # first cut: same positions up to one PCG solve
+    for mine, theirs in zip(g["log_SL_rod_toi"], o["log_SL_rod_toi"]):
+        assert abs(mine - theirs) < 2e-2
+    c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    nb = c["n_blocks"][0]
+    assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
+    assert c["frac_blocks_off"] * nb <= 12 + 0.002 * nb, c
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))

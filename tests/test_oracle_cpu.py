@@ -223,6 +223,66 @@ def test_rod_bend_force_is_the_energy_gradient(orc):
     assert abs(k - 3e-3 * 5e-4 * 1e-4 / (2.5e-3) ** 2) < 1e-9
 
 
+def test_rod_strain_limit_is_the_barrier_gradient_and_hessian(orc):
+    """strainlimiting.cu:122-190: with a zero elastic matrix the stiffness is mass / (limit - g)^2; force / stiffness must
+    be the gradient of the cubic barrier energy E(g) = 2 g^3 / (3 limit) of the stretch g = l / l0 - 1 (cubic.hpp:13-21
+    at the gap limit - g), and the block matrix its Hessian (both PSD clamps are inactive for g > 0)."""
+    rng = np.random.default_rng(11)
+    orc.orc_rod_strain.restype = C.c_int
+    worst_g = worst_h = 0.0
+    n_on = 0
+    for _ in range(300):
+        x = rng.uniform(-1, 1, size=(2, 3))
+        l = np.linalg.norm(x[1] - x[0])
+        l0 = l / rng.uniform(0.97, 1.04)              # stretched by up to 4 % or compressed by up to 3 %
+        limit, mass = 0.05, 0.3
+        x32 = x.astype(np.float32); c32 = (x + rng.normal(0, 0.01, size=(2, 3))).astype(np.float32)
+        g6 = np.zeros(6, np.float32); h36 = np.zeros(36, np.float32); hel = np.zeros(27, np.float32)
+        on = orc.orc_rod_strain(fp(x32), fp(c32), C.c_float(l0), C.c_float(limit), C.c_float(mass), fp(hel), fp(g6), fp(h36))
+        g = np.linalg.norm(x32[1].astype(np.float64) - x32[0]) / np.float32(l0) - 1.0
+        assert bool(on) == (g > 0)
+        if not on:
+            continue
+        n_on += 1
+        kappa = mass / (limit - g) ** 2
+
+        def grad(y):
+            gg = np.linalg.norm(y[1] - y[0]) / np.float64(np.float32(l0)) - 1.0
+            n = (y[1] - y[0]) / np.linalg.norm(y[1] - y[0])
+            dE = 2.0 * gg * gg / limit
+            return np.concatenate([-n, n]) * dE / np.float64(np.float32(l0))
+        ga = grad(x32.astype(np.float64))
+        worst_g = max(worst_g, np.abs(g6 / kappa - ga).max() / max(np.abs(ga).max(), 1e-9))
+        num = np.zeros((6, 6))
+        for k in range(6):
+            d = np.zeros(6); d[k] = 1e-6
+            num[:, k] = (grad(x32.astype(np.float64) + d.reshape(2, 3)) - grad(x32.astype(np.float64) - d.reshape(2, 3))) / 2e-6
+        H = h36.reshape(6, 6).T.astype(np.float64) / kappa
+        worst_h = max(worst_h, np.abs(H - num).max() / max(np.abs(num).max(), 1e-9))
+    assert n_on > 50 and worst_g < 1e-3 and worst_h < 1e-3, (n_on, worst_g, worst_h)
+    # elasticity-inclusive stiffness: w^T H_el w with w = (c0 - centre, c1 - centre) adds to mass / (limit - g)^2
+    x32 = np.array([[0, 0, 0], [1.02, 0, 0]], np.float32); c32 = np.array([[0, 0, 0], [1, 0, 0]], np.float32)
+    hel = np.zeros(27, np.float32); hel[0] = 3.0; hel[18] = 5.0; hel[9] = -1.0     # xx entries of (e0,e0), (e1,e1), (e0,e1)
+    g0 = np.zeros(6, np.float32); g1 = np.zeros(6, np.float32); h = np.zeros(36, np.float32)
+    orc.orc_rod_strain(fp(x32), fp(c32), C.c_float(1.0), C.c_float(0.05), C.c_float(0.3), fp(np.zeros(27, np.float32)), fp(g0), fp(h))
+    orc.orc_rod_strain(fp(x32), fp(c32), C.c_float(1.0), C.c_float(0.05), C.c_float(0.3), fp(hel), fp(g1), fp(h))
+    k0 = 0.3 / (0.05 - 0.02) ** 2
+    wHw = 0.25 * 3.0 + 0.25 * 5.0 + 2 * (-0.5) * 0.5 * (-1.0)
+    assert abs(g1[3] / g0[3] - (k0 + wHw) / k0) < 1e-4
+
+
+def test_rod_strain_line_search(orc):
+    orc.orc_rod_strain_toi.restype = C.c_float
+    d0 = np.array([1.0, 0, 0], np.float32)
+    for grow, limit in ((1.01, 0.02), (1.03, 0.02), (1.10, 0.02), (0.9, 0.02)):
+        d1 = (d0 * grow).astype(np.float32)
+        t = orc.orc_rod_strain_toi(fp(d0), fp(d1), C.c_float(1.0), C.c_float(limit), C.c_float(1.25))
+        if 1.25 * (grow - 1.0) < limit * 0.999:
+            assert t == np.float32(1.25)
+        else:
+            assert abs(t * (grow - 1.0) - limit) < 1e-5 and t * (grow - 1.0) <= limit * (1 + 1e-5)   # fp32 bisection
+
+
 def _strain_case(rng, stretch):
     """a rest triangle in the plane, deformed by a random rotation times a stretch"""
     rest = np.array([[0.0, 0.0], [1.0, 0.1], [0.2, 0.9]]) * 0.05
