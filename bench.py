@@ -318,8 +318,10 @@ def main():
         achieved = bytes_per_launch / (us * 1e-6) * 1e-9
         traffic = None
         tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        if os.path.exists(tp):  # one ncu --set full capture; only meaningful for the scene (matrix size) it was taken on
+            prof = json.load(open(tp))
+            if prof.get("scene", "large-twist") == args.scene and abs(prof.get("n_off", n_off) - n_off) <= 0.02 * n_off:
+                traffic = prof.get("dram_bytes_per_launch")
         line["roofline"] = {"bound": "hbm", "kernel": "ppf::k_spmv_staged" + (" (rank 0's share of the rows)" if shard is not None else ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "peak_source": how, "us_per_launch": us, "n_row": n_row, "n_off": n_off,
                             "bytes_per_launch": bytes_per_launch}
