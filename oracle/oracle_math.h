@@ -301,4 +301,128 @@ static inline float o_friction(const float *force_contact, const float *dx, cons
     return lambda;
 }
 
+/* ---- analytic colliders: invisible spheres / bowls and walls (TEST INFRASTRUCTURE restatement) ------------------
+ * push barrier energy/model/push.hpp:15-50; embed_vertex_constraint_force_hessian contact/contact.cu:1154-1383;
+ * vertex_constraint_line_search contact/contact.cu:2318-2470.  Sphere / floor records are passed as plain floats:
+ *   sphere: center[3], ghat, friction, radius, thickness, bowl, reverse, kinematic   (10 floats)
+ *   floor : ground[3], ghat, friction, thickness, up[3], kinematic                     (10 floats) */
+static inline void o_push(const float *e, const float *n, float eps, float scale, float *f, float *H) { /* f += scale grad, H += scale hess */
+    const float d = o_dot(e, n);
+    if (!(d < 0.0f)) return;
+    const float g = -(d * d) / eps, c = -2.0f * d / eps;
+    for (int k = 0; k < 3; ++k) f[k] += scale * (g * n[k]);
+    for (int cc = 0; cc < 3; ++cc) for (int r = 0; r < 3; ++r) H[cc * 3 + r] += scale * ((c * n[r]) * n[cc]);
+}
+static inline float o_combine_friction(float a, float b, int mode) { return mode == 1 ? (a > b ? a : b) : (mode == 2 ? 0.5f * (a + b) : (a < b ? a : b)); }
+static inline float o_nHn(const float *H, const float *n) {
+    float y[3];
+    for (int r = 0; r < 3; ++r) y[r] = H[r] * n[0] + H[3 + r] * n[1] + H[6 + r] * n[2];
+    return o_dot(n, y);
+}
+static inline unsigned o_collider_vertex(const float *x, const float *dx, float mass, float vfriction, const float *Hii, const float *spheres, unsigned n_sphere,
+                                         const float *floors, unsigned n_floor, int friction_mode, float friction_eps, float constraint_tol, float *f, float *H) {
+    unsigned count = 0;
+    for (int k = 0; k < 3; ++k) f[k] = 0.0f;
+    for (int k = 0; k < 9; ++k) H[k] = 0.0f;
+    for (unsigned j = 0; j < n_sphere; ++j) {
+        const float *s = spheres + 10 * j;
+        const float ghat = s[3], friction = o_combine_friction(s[4], vfriction, friction_mode), sr = s[5], thickness = s[6];
+        const int bowl = s[7] != 0.0f, kinematic = s[9] != 0.0f;
+        int reverse = s[8] != 0.0f;
+        float radius = sr;
+        float center[3] = {s[0], s[1], s[2]}, ov[3];
+        if (bowl && x[1] > center[1]) center[1] = x[1];
+        o_sub(x, center, ov);
+        const float d2 = o_dot(ov, ov);
+        if (kinematic) {
+            if (!d2) continue;
+            const float dist = sqrtf(d2);
+            float normal[3] = {ov[0] / dist, ov[1] / dist, ov[2] / dist}, e[3];
+            const float eff = reverse ? (radius - ghat) : (radius + ghat);
+            for (int k = 0; k < 3; ++k) e[k] = ov[k] - eff * normal[k];
+            if (bowl) reverse = 1;
+            const float stiff_k = mass / (ghat * ghat), r2 = eff * eff;
+            const float depth = reverse ? (dist - sr) : (sr - dist);
+            if (thickness > 0.0f && depth > thickness) continue;
+            if (reverse && d2 > r2) { float nn[3] = {-normal[0], -normal[1], -normal[2]}; ++count; o_push(e, nn, ghat, stiff_k, f, H); }
+            else if (!reverse && d2 < r2) { ++count; o_push(e, normal, ghat, stiff_k, f, H); }
+        } else {
+            if (reverse) radius -= ghat; else radius += ghat;
+            const float r2 = radius * radius;
+            if (!(reverse ? d2 > r2 : d2 < r2)) continue;
+            const float dist = sqrtf(d2);
+            const float depth = reverse ? (dist - sr) : (sr - dist);
+            if (thickness > 0.0f && depth > thickness) continue;
+            ++count;
+            float normal[3] = {ov[0] / dist, ov[1] / dist, ov[2] / dist}, e[3];
+            for (int k = 0; k < 3; ++k) e[k] = ov[k] - radius * normal[k];
+            if (reverse) for (int k = 0; k < 3; ++k) normal[k] = -normal[k];
+            const float gap = reverse ? sr - dist : dist - sr;
+            const float stiff_k = o_nHn(Hii, normal) + mass / (gap * gap);
+            float fp[3] = {0, 0, 0}, g[3], h[9];
+            o_push(e, normal, ghat, stiff_k, fp, H);
+            for (int k = 0; k < 3; ++k) f[k] += fp[k];
+            o_friction(fp, dx, normal, friction, friction_eps, g, h);
+            for (int k = 0; k < 3; ++k) f[k] += g[k];
+            for (int k = 0; k < 9; ++k) H[k] += h[k];
+        }
+    }
+    for (unsigned j = 0; j < n_floor; ++j) {
+        const float *fl = floors + 10 * j;
+        const float ghat = fl[3], friction = o_combine_friction(fl[4], vfriction, friction_mode), thickness = fl[5];
+        const float *up = fl + 6;
+        float e[3], p[3], q[3];
+        for (int k = 0; k < 3; ++k) e[k] = x[k] - (fl[k] + ghat * up[k]);
+        const float eu = o_dot(e, up);
+        if (!(eu < 0.0f)) continue;
+        if (thickness > 0.0f && -eu > thickness) continue;
+        ++count;
+        for (int k = 0; k < 3; ++k) { p[k] = -((-eu) * up[k]); q[k] = x[k] - fl[k]; }
+        float gap = o_dot(q, up);
+        if (fl[9] != 0.0f) gap = fmaxf(gap, constraint_tol * ghat);
+        const float stiff_k = o_nHn(Hii, up) + mass / (gap * gap);
+        float fp[3] = {0, 0, 0}, g[3], h[9];
+        o_push(p, up, ghat, stiff_k, fp, H);
+        for (int k = 0; k < 3; ++k) f[k] += fp[k];
+        o_friction(fp, dx, up, friction, friction_eps, g, h);
+        for (int k = 0; k < 3; ++k) f[k] += g[k];
+        for (int k = 0; k < 9; ++k) H[k] += h[k];
+    }
+    return count;
+}
+static inline float o_collider_toi(const float *y0, const float *y1, int pinned, const float *spheres, unsigned n_sphere, const float *floors, unsigned n_floor,
+                                   float max_t, int *infeasible) {
+    float x1[3], toi = max_t;
+    for (int k = 0; k < 3; ++k) x1[k] = max_t * (y1[k] - y0[k]) + y0[k];
+    for (unsigned j = 0; j < n_sphere; ++j) {
+        const float *s = spheres + 10 * j;
+        if (s[9] != 0.0f) continue;
+        const int bowl = s[7] != 0.0f, reverse = s[8] != 0.0f;
+        float c0[3] = {s[0], s[1], s[2]}, c1[3] = {s[0], s[1], s[2]}, a[3], b[3];
+        if (bowl && y0[1] > s[1]) c0[1] = y0[1];
+        if (bowl && x1[1] > s[1]) c1[1] = x1[1];
+        o_sub(y0, c0, a); o_sub(x1, c1, b);
+        const float r = s[5], r0 = sqrtf(o_dot(a, a)), r1 = sqrtf(o_dot(b, b));
+        if (pinned) {
+            const float d0 = reverse ? (r - r0) : (r0 - r), d1 = reverse ? (r - r1) : (r1 - r);
+            if (d0 >= 0.0f && d1 < 0.0f) *infeasible = 1;
+            continue;
+        }
+        const float depth0 = reverse ? (r0 - r) : (r - r0);
+        if (s[6] > 0.0f && depth0 > s[6]) continue;
+        if ((r0 - r) * (r1 - r) <= 0.0f) toi = fminf(toi, max_t * ((r - r0) / (r1 - r0)));
+    }
+    for (unsigned j = 0; j < n_floor; ++j) {
+        const float *fl = floors + 10 * j;
+        if (fl[9] != 0.0f) continue;
+        float a[3], b[3];
+        o_sub(y0, fl, a); o_sub(x1, fl, b);
+        const float h0 = o_dot(fl + 6, a), h1 = o_dot(fl + 6, b);
+        if (pinned) { if (h0 >= 0.0f && h1 < 0.0f) *infeasible = 1; continue; }
+        if (fl[5] > 0.0f && -h0 > fl[5]) continue;
+        if (h1 < 0.0f) toi = fminf(toi, max_t * (-h0 / (h1 - h0)));
+    }
+    return toi;
+}
+
 #endif

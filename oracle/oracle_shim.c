@@ -90,3 +90,13 @@ SHIM int orc_rod_strain(const float *x6, const float *c6, float l0, float limit,
     return 1;
 }
 SHIM float orc_rod_strain_toi(const float *d0, const float *d1, float l0, float limit, float max_t) { return o_rod_strain_toi(d0, d1, l0, limit, max_t); }
+
+/* analytic colliders (10 floats per sphere / floor record, see oracle_math.h) */
+SHIM unsigned orc_collider_vertex(const float *x, const float *dx, float mass, float vfriction, const float *Hii, const float *spheres, unsigned ns,
+                                  const float *floors, unsigned nf, int friction_mode, float friction_eps, float constraint_tol, float *f, float *H) {
+    return o_collider_vertex(x, dx, mass, vfriction, Hii, spheres, ns, floors, nf, friction_mode, friction_eps, constraint_tol, f, H);
+}
+SHIM float orc_collider_toi(const float *y0, const float *y1, int pinned, const float *spheres, unsigned ns, const float *floors, unsigned nf, float max_t, int *infeasible) {
+    *infeasible = 0;
+    return o_collider_toi(y0, y1, pinned, spheres, ns, floors, nf, max_t, infeasible);
+}

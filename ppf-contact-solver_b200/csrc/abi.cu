@@ -80,6 +80,10 @@ void apply_constraint(State &s, const PpfConstraint *c) {
     s.npull = c->pull.size;
     s.fix.upload(c->fix.data, c->fix.size, q);
     s.pull.upload(c->pull.data, c->pull.size, q);
+    s.nsphere = c->sphere.size;
+    s.nfloor = c->floor.size;
+    s.spheres.upload(c->sphere.data, c->sphere.size, q);
+    s.floors.upload(c->floor.data, c->floor.size, q);
     k_clear_pin_index<<<div_up(s.nv, 256), 256, 0, q>>>(s.fix_index.p, s.pull_index.p, s.nv);
     if (s.nfix) k_set_fix_index<<<div_up(s.nfix, 256), 256, 0, q>>>(s.fix.p, s.nfix, s.fix_index.p);
     if (s.npull) k_set_pull_index<<<div_up(s.npull, 256), 256, 0, q>>>(s.pull.p, s.npull, s.pull_index.p);
@@ -125,9 +129,9 @@ void upload_dataset(State &s) {
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
     if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
     if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
-    if (d.constraint.stitch.size || d.constraint.sphere.size || d.constraint.floor.size || d.constraint.mesh.vertex.size ||
-        d.constraint.torque_vertices.size)
-        fatal(4, "B200 backend: stitches / analytic colliders / static collision meshes / torque pins are not implemented");
+    if (d.constraint.stitch.size || d.constraint.mesh.vertex.size || d.constraint.torque_vertices.size)
+        fatal(4, "B200 backend: stitches / static collision meshes / torque pins are not implemented");
+    if (prm.disable_pin_dof_removal) fatal(4, "B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
     if (d.translation_lock.size) fatal(4, "B200 backend: translation/rotation locks are not implemented");
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
         if (d.grain_inv_inertia.data[i] > 0.0f) fatal(4, "B200 backend: SAND grains are not implemented");
@@ -429,9 +433,8 @@ PPF_EXPORT void update_dyn(unsigned *index, unsigned *offset) {
 }
 
 PPF_EXPORT void update_constraint(const PpfConstraint *constraint) {
-    if (constraint->stitch.size || constraint->sphere.size || constraint->floor.size || constraint->mesh.vertex.size ||
-        constraint->torque_vertices.size)
-        fatal(4, "B200 backend: stitches / analytic colliders / static collision meshes / torque pins are not implemented");
+    if (constraint->stitch.size || constraint->mesh.vertex.size || constraint->torque_vertices.size)
+        fatal(4, "B200 backend: stitches / static collision meshes / torque pins are not implemented");
     apply_constraint(g, constraint);
 }
 PPF_EXPORT void update_rest_shape(const PpfRestShapeUpdate *update) {

@@ -131,6 +131,9 @@ struct State {
     DBuf<unsigned> rb_slots;                      // 9 per bending vertex (DataSet.rod_bend_hess_slots rows of those vertices)
     DBuf<PpfFixPair> fix;
     DBuf<PpfPullPair> pull;
+    DBuf<PpfSphere> spheres;                      // analytic colliders of the last update_constraint
+    DBuf<PpfFloor> floors;
+    unsigned nsphere = 0, nfloor = 0;
     // ABI-layout copies kept for fetch_* (plasticity is out of scope, so they never change)
     // fixed (topology) matrix: upper-triangle block CSR, AoS 3x3 column-major blocks
     DBuf<unsigned> fx_off, fx_col;
@@ -208,6 +211,9 @@ void bvh_refit_relative(State &s, Bvh &b, int kind, const float4 *x0, const floa
 unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed);
 float contact_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap);
 bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm);
+unsigned assemble_colliders(State &s, const PpfParamSet &prm);   // analytic spheres / walls; returns the contact count
+// collider part of the line search: step fraction in (0, 1]; bad_vertex != 0xFFFFFFFF: a pinned vertex is driven through a collider
+float collider_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, unsigned &bad_vertex);
 void build_fetch_pattern(State &s, std::vector<unsigned> &index, std::vector<unsigned> &offset);
 
 // pcg.cu

@@ -23,6 +23,7 @@
 // reference's for the same positions.
 #include "bvh.cuh"
 #include "math_accd.cuh"
+#include "math_collider.cuh"
 #include "math_contact.cuh"
 #include "math_distance.cuh"
 #include <algorithm>
@@ -852,6 +853,97 @@ float contact_line_search(State &s, const float4 *x0, const float4 *x1, const Pp
     memcpy(&toi, &h[0], sizeof(float));
     overlap = h[1] != 0u;
     return toi / prm.line_search_max_t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// analytic colliders: invisible spheres / bowls and walls (contact.cu:1154-1383, 2318-2470; math_collider.cuh)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_collider(unsigned nsv, const float4 *__restrict__ eval_x, const float4 *__restrict__ curr,
+                                                  const float4 *__restrict__ vcp, const unsigned *__restrict__ fix_index,
+                                                  const float *__restrict__ fx_el, const unsigned *__restrict__ diag_slot,
+                                                  const PpfSphere *__restrict__ spheres, unsigned n_sphere, const PpfFloor *__restrict__ floors,
+                                                  unsigned n_floor, int friction_mode, float friction_eps, float constraint_tol,
+                                                  float *__restrict__ force, float *__restrict__ fx_val, unsigned *counter) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned count = 0;
+    if (i < nsv && fix_index[i] == 0) {
+        const float4 cp = vcp[i]; // (ghat, offset, friction, mass)
+        if (cp.w > 0.0f) {       // zero-mass vertices are static solids
+            const V3 x = ld3c(eval_x, i);
+            const unsigned slot = diag_slot[i];
+            M3 Hii;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) Hii.m[e] = fx_el[size_t(9) * slot + e];
+            ColliderOut o;
+            collider_vertex(x, x - ld3c(curr, i), cp.w, cp.z, Hii, spheres, n_sphere, floors, n_floor, friction_mode, friction_eps, constraint_tol, o);
+            count = o.count;
+            if (count) { // one thread owns vertex i in this kernel, but the contact kernels may still be adding to it
+                float *fo = force + size_t(3) * i;
+                if (o.f.x) atomicAdd(fo + 0, o.f.x);
+                if (o.f.y) atomicAdd(fo + 1, o.f.y);
+                if (o.f.z) atomicAdd(fo + 2, o.f.z);
+                float *dst = fx_val + size_t(9) * slot;
+#pragma unroll
+                for (int e = 0; e < 9; ++e)
+                    if (o.H.m[e]) atomicAdd(dst + e, o.H.m[e]);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if ((threadIdx.x & 31) == 0 && count) atomicAdd(counter, count);
+}
+
+__global__ void __launch_bounds__(128) k_collider_toi(unsigned nsv, const float4 *__restrict__ x0, const float4 *__restrict__ x1,
+                                                      const float4 *__restrict__ vcp, const unsigned *__restrict__ fix_index,
+                                                      const PpfSphere *__restrict__ spheres, unsigned n_sphere, const PpfFloor *__restrict__ floors,
+                                                      unsigned n_floor, float max_t, unsigned *toi_bits, unsigned *bad_vertex) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float t = max_t;
+    if (i < nsv) {
+        const bool pinned = fix_index[i] != 0;
+        if (pinned || vcp[i].w > 0.0f) {
+            bool infeasible = false;
+            t = collider_toi(ld3c(x0, i), ld3c(x1, i), pinned, spheres, n_sphere, floors, n_floor, max_t, &infeasible);
+            if (infeasible) atomicMin(bad_vertex, i);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
+}
+
+unsigned assemble_colliders(State &s, const PpfParamSet &prm) {
+    if (!(s.nsphere || s.nfloor) || !s.nsv) return 0;
+    cudaStream_t q = s.stream;
+    unsigned *cnt = s.counters.p + 30;
+    CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), q));
+    k_collider<<<div_up(s.nsv, 128), 128, 0, q>>>(s.nsv, s.eval_x.p, s.curr.p, s.vcp.p, s.fix_index.p, s.fx_el.p, s.fx_diag_slot.p, s.spheres.p, s.nsphere,
+                                                  s.floors.p, s.nfloor, (int)prm.friction_mode, prm.friction_eps, prm.constraint_tol, s.force.p, s.fx_val.p, cnt);
+    LAUNCH_COUNT(1);
+    unsigned h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    return h;
+}
+
+float collider_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, unsigned &bad_vertex) {
+    bad_vertex = 0xFFFFFFFFu;
+    if (!(s.nsphere || s.nfloor) || !s.nsv) return 1.0f;
+    cudaStream_t q = s.stream;
+    unsigned *w = s.counters.p + 32; // [32] toi bits, [33] smallest infeasible pinned vertex
+    const float max_t = prm.line_search_max_t;
+    unsigned init[2];
+    memcpy(&init[0], &max_t, sizeof(float));
+    init[1] = 0xFFFFFFFFu;
+    CUDA_OK(cudaMemcpyAsync(w, init, sizeof(init), cudaMemcpyHostToDevice, q));
+    k_collider_toi<<<div_up(s.nsv, 128), 128, 0, q>>>(s.nsv, x0, x1, s.vcp.p, s.fix_index.p, s.spheres.p, s.nsphere, s.floors.p, s.nfloor, max_t, w, w + 1);
+    LAUNCH_COUNT(1);
+    unsigned h[2];
+    CUDA_OK(cudaMemcpyAsync(h, w, sizeof(h), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    float t;
+    memcpy(&t, &h[0], sizeof(float));
+    bad_vertex = h[1];
+    return t / max_t;
 }
 
 // ---------------------------------------------------------------------------------------------

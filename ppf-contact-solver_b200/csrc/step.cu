@@ -242,6 +242,7 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.pop();
         logging.mark("dyn_consumed", dyn_consumed);
         logging.mark("max_nnz_row", max_nnz_row);
+        num_contact += assemble_colliders(s, prm); // embed_constraint_force_hessian (main.cu:873): spheres / walls, contact on or off
         logging.mark("num_contact", num_contact);
         s.tm.ms_assembly += t_ph.stop();
         logging.pop();
@@ -305,6 +306,17 @@ void step_advance(State &s, PpfStepResult *out) {
                 return;
             }
             logging.pop();
+        }
+        if (s.nsphere || s.nfloor) { // vertex_constraint_line_search (contact.cu:2318-2470), inside contact::line_search in the reference
+            unsigned bad_vert = 0xFFFFFFFFu;
+            toi = fminf(toi, collider_line_search(s, s.x_old.p, s.eval_x.p, prm, bad_vert));
+            if (bad_vert != 0xFFFFFFFFu) {
+                logging.message("### infeasible pin: prescribed vertex %u is driven through an analytic collider (floor/sphere) it cannot yield to", bad_vert);
+                logging.message("### re-author the pin's path so it stays outside the collider, or make it a soft pull pin so it can yield.");
+                result.pin_feasible = false;
+                finish(false);
+                return;
+            }
         }
         if (s.has_strainlimit) { // strainlimiting::line_search (main.cu:1321-1335)
             const float sl_toi = strain_line_search(s, s.x_old.p, s.eval_x.p, prm);

@@ -77,9 +77,15 @@ struct SimArgs { // crates/ppf-cts-solver/src/args.rs:22-94 (defaults params.rs:
     // time-varying gravity keyframes (scene.rs dyn_param; used by `hang`): (time, gravity-y)
     std::vector<std::pair<double, double>> gravity_y_keys;
 };
+// invisible analytic colliders (frontend scene.add.invisible.wall / .sphere; scene.rs InvisibleWall / InvisibleSphere).
+// Static ones only (a single keyframe): make_constraint emits them with kinematic = false (scene.rs:2041-2049).
+struct WallCollider { Vec3d position{0, 0, 0}, normal{0, 1, 0}; double contact_gap = 1e-3, friction = 0.0, thickness = 1.0; };
+struct SphereCollider { Vec3d center{0, 0, 0}; double radius = 1.0; bool inverted = false, hemisphere = false; double contact_gap = 1e-3, friction = 0.0, thickness = 1.0; };
 struct SceneSpec {
     std::string name;
     std::vector<ShellObject> objects;
+    std::vector<WallCollider> walls;
+    std::vector<SphereCollider> spheres;
     SimArgs args;
 };
 
@@ -133,6 +139,7 @@ struct Built {
     std::vector<GPin> pins;
     // constraint storage (rebuilt every step)
     std::vector<PpfFixPair> fix; std::vector<PpfPullPair> pull;
+    std::vector<PpfSphere> sphere; std::vector<PpfFloor> floor;
     PpfDataSet dataset;
     PpfParamSet param;
     PpfConstraint constraint;

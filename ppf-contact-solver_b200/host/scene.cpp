@@ -302,6 +302,25 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.gravity_y_keys = {{0.0, -9.8}, {1.0, -9.8}, {1.0 + jitter, 9.8}, {2.0, -9.8}};
         return s;
     }
+    if (name == "drape") { // test scene: a sheet thrown onto an invisible sphere standing on an invisible floor (analytic colliders with friction)
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_square(n ? n : 32, 1.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+        o.param = tri_defaults();
+        o.param["friction"] = 0.3;
+        o.displacement = Vec3d{0.03, 0.45, 0.02};
+        o.velocity = Vec3d{0, -3.0, 0};
+        s.objects.push_back(o);
+        SphereCollider sp; sp.center = Vec3d{0, 0, 0}; sp.radius = 0.4; sp.friction = 0.3;
+        WallCollider fl; fl.position = Vec3d{0, -0.08, 0}; fl.normal = Vec3d{0, 1, 0}; fl.friction = 0.3;
+        s.spheres.push_back(sp);
+        s.walls.push_back(fl);
+        s.args.frames = 120;
+        s.args.dt = 1e-2;
+        s.args.friction_mode = "min";
+        return s;
+    }
     if (name == "sheet") { // free-hanging sheet without strain limit: elastic-only smoke scene
         SceneSpec s;
         s.name = name;
@@ -410,8 +429,29 @@ void make_constraint(Built &b, double time, double prev_time) {
             }
         }
     }
+    // invisible walls and spheres (scene.rs:2213-2254); world scaling applies to positions, radii and thickness
+    const float ws = float(b.spec.args.world_scaling);
+    b.floor.clear();
+    b.sphere.clear();
+    for (auto &w : b.spec.walls) {
+        PpfFloor f{};
+        for (int k = 0; k < 3; ++k) { f.ground.v[k] = float(w.position[k]) * ws; f.up.v[k] = float(w.normal[k]); }
+        f.ghat = float(w.contact_gap); f.friction = float(w.friction); f.thickness = float(w.thickness) * ws; f.kinematic = false;
+        b.floor.push_back(f);
+    }
+    for (auto &sp : b.spec.spheres) {
+        PpfSphere q{};
+        for (int k = 0; k < 3; ++k) q.center.v[k] = float(sp.center[k]) * ws;
+        q.ghat = float(sp.contact_gap); q.friction = float(sp.friction); q.radius = float(sp.radius) * ws; q.thickness = float(sp.thickness) * ws;
+        q.bowl = sp.hemisphere; q.reverse = sp.inverted; q.kinematic = false;
+        b.sphere.push_back(q);
+    }
     PpfConstraint &c = b.constraint;
     c = PpfConstraint{};
+    c.floor.data = b.floor.data();
+    c.floor.size = c.floor.allocated = (unsigned)b.floor.size();
+    c.sphere.data = b.sphere.data();
+    c.sphere.size = c.sphere.allocated = (unsigned)b.sphere.size();
     c.fix.data = b.fix.data();
     c.fix.size = c.fix.allocated = (unsigned)b.fix.size();
     c.pull.data = b.pull.data();

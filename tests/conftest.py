@@ -75,7 +75,7 @@ def golden_cases():
     import json
 
     out = []
-    for name in ("fast_twist_n16", "fast_twist_n24", "five_twist_n24", "hang_n32", "woven_n32", "woven_sl_n32"):
+    for name in ("fast_twist_n16", "fast_twist_n24", "five_twist_n24", "hang_n32", "woven_n32", "woven_sl_n32", "drape_n32"):
         if not os.path.exists(os.path.join(GOLDEN, name, "meta.json")):
             continue
         d = os.path.join(GOLDEN, name)

@@ -40,11 +40,13 @@ case "$1" in
   hang-only) gen hang_n32 hang 32 300 150 00150 00300 ;;
   woven-only) gen woven_n32 woven 32 120 60 00060 00120 ;;
   woven-sl-only) gen woven_sl_n32 woven-sl 32 160 80 00080 00160 ;;
+  drape-only) gen drape_n32 drape 32 140 70 00070 00140 ;;
   *) gen fast_twist_n16 fast-twist 16 90 30 00030 00060 00090
      gen fast_twist_n24 fast-twist 24 80 40 00040 00080
      gen five_twist_n24 five-twist 24 100 50 00050 00100
      gen hang_n32 hang 32 300 150 00150 00300
      gen woven_n32 woven 32 120 60 00060 00120
-     gen woven_sl_n32 woven-sl 32 160 80 00080 00160 ;;
+     gen woven_sl_n32 woven-sl 32 160 80 00080 00160
+     gen drape_n32 drape 32 140 70 00070 00140 ;;
 esac
 du -sh gpurun_out/golden/*

@@ -2,6 +2,7 @@
 // compiled for the host in the tests only, -ffp-contract=off) under the same C signatures as
 // oracle/oracle_shim.c, so tests/test_oracle_cpu.py runs one set of known-answer checks over both.
 #include "../../ppf-contact-solver_b200/csrc/math_accd.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_collider.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_contact.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
@@ -104,3 +105,41 @@ SHIM int orc_rod_strain(const float *x6, const float *c6, float l0, float limit,
     return 1;
 }
 SHIM float orc_rod_strain_toi(const float *d0, const float *d1, float l0, float limit, float max_t) { return rod_strain_toi(v(d0), v(d1), l0, limit, max_t); }
+
+// analytic colliders: sphere / floor records as 10 floats each (layout documented in oracle/oracle_math.h)
+static void unpack_colliders(const float *sp, unsigned ns, const float *fl, unsigned nf, PpfSphere *S, PpfFloor *F) {
+    for (unsigned j = 0; j < ns; ++j) {
+        const float *s = sp + 10 * j;
+        PpfSphere q{};
+        q.center.v[0] = s[0]; q.center.v[1] = s[1]; q.center.v[2] = s[2];
+        q.ghat = s[3]; q.friction = s[4]; q.radius = s[5]; q.thickness = s[6]; q.bowl = s[7] != 0.0f; q.reverse = s[8] != 0.0f; q.kinematic = s[9] != 0.0f;
+        S[j] = q;
+    }
+    for (unsigned j = 0; j < nf; ++j) {
+        const float *s = fl + 10 * j;
+        PpfFloor q{};
+        q.ground.v[0] = s[0]; q.ground.v[1] = s[1]; q.ground.v[2] = s[2];
+        q.ghat = s[3]; q.friction = s[4]; q.thickness = s[5]; q.up.v[0] = s[6]; q.up.v[1] = s[7]; q.up.v[2] = s[8]; q.kinematic = s[9] != 0.0f;
+        F[j] = q;
+    }
+}
+SHIM unsigned orc_collider_vertex(const float *x, const float *dx, float mass, float vfriction, const float *Hii, const float *spheres, unsigned ns,
+                                  const float *floors, unsigned nf, int friction_mode, float friction_eps, float constraint_tol, float *f, float *H) {
+    PpfSphere S[16]; PpfFloor F[16];
+    unpack_colliders(spheres, ns, floors, nf, S, F);
+    M3 h;
+    for (int e = 0; e < 9; ++e) h.m[e] = Hii[e];
+    ColliderOut o;
+    collider_vertex(v(x), v(dx), mass, vfriction, h, S, ns, F, nf, friction_mode, friction_eps, constraint_tol, o);
+    f[0] = o.f.x; f[1] = o.f.y; f[2] = o.f.z;
+    for (int e = 0; e < 9; ++e) H[e] = o.H.m[e];
+    return o.count;
+}
+SHIM float orc_collider_toi(const float *y0, const float *y1, int pinned, const float *spheres, unsigned ns, const float *floors, unsigned nf, float max_t, int *infeasible) {
+    PpfSphere S[16]; PpfFloor F[16];
+    unpack_colliders(spheres, ns, floors, nf, S, F);
+    bool bad = false;
+    const float t = collider_toi(v(y0), v(y1), pinned != 0, S, ns, F, nf, max_t, &bad);
+    *infeasible = bad ? 1 : 0;
+    return t;
+}

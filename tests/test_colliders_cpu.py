@@ -1,0 +1,167 @@
+"""Analytic colliders (invisible spheres / bowls / walls): the oracle's plain-C restatement and the CUDA backend's
+header (csrc/math_collider.cuh compiled for the host) against each other and against first principles.
+
+The reference keeps this code inside contact.cu (embed_vertex_constraint_force_hessian 1154-1383,
+vertex_constraint_line_search 2318-2470), not in a header, so it cannot be compiled for the host: leaf parity with
+the reference is pinned through the whole-step golden fixtures of tests/golden/drape_n32 instead (produced by the
+reference on a B200).  Here: (1) oracle == backend header, bit for bit, over random configurations of every branch;
+(2) the push force is stiffness x the gradient of the cubic push energy -d^3 / (3 ghat) (push.hpp:15-50);
+(3) the line search returns the first crossing and flags prescribed vertices driven through a collider.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle_cpu import _build_csrc_shim, fp, same_bits
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libs(built):
+    o = C.CDLL(os.path.join(REPO, "oracle", "build", "liboracle_math.so"))
+    b = C.CDLL(_build_csrc_shim())
+    for l in (o, b):
+        l.orc_collider_vertex.restype = C.c_uint
+        l.orc_collider_toi.restype = C.c_float
+    return o, b
+
+
+def _scene(rng):
+    """two spheres (one random flavour each) and two floors, 10 floats per record"""
+    sp = np.zeros((2, 10), np.float32); fl = np.zeros((2, 10), np.float32)
+    for j in range(2):
+        sp[j, :3] = rng.uniform(-0.2, 0.2, 3); sp[j, 3] = rng.choice([1e-3, 5e-3]); sp[j, 4] = rng.choice([0.0, 0.3])
+        sp[j, 5] = rng.uniform(0.3, 0.6); sp[j, 6] = rng.choice([1.0, 0.05]); sp[j, 7] = rng.integers(0, 2); sp[j, 8] = rng.integers(0, 2); sp[j, 9] = rng.integers(0, 2)
+        up = rng.normal(size=3); up /= np.linalg.norm(up)
+        fl[j, :3] = rng.uniform(-0.5, 0.5, 3); fl[j, 3] = rng.choice([1e-3, 5e-3]); fl[j, 4] = rng.choice([0.0, 0.5]); fl[j, 5] = rng.choice([1.0, 0.02])
+        fl[j, 6:9] = up; fl[j, 9] = rng.integers(0, 2)
+    return sp, fl
+
+
+def _call_vertex(l, x, dx, mass, vf, H, sp, fl, mode):
+    f = np.zeros(3, np.float32); Hh = np.zeros(9, np.float32)
+    n = l.orc_collider_vertex(fp(x), fp(dx), C.c_float(mass), C.c_float(vf), fp(H), fp(sp), C.c_uint(len(sp)), fp(fl), C.c_uint(len(fl)), C.c_int(mode),
+                              C.c_float(1e-5), C.c_float(0.01), fp(f), fp(Hh))
+    return int(n), f, Hh
+
+
+def test_oracle_and_backend_header_agree_bit_for_bit(libs):
+    o, b = libs
+    rng = np.random.default_rng(3)
+    hits = 0
+    for _ in range(1500):
+        sp, fl = _scene(rng)
+        x = rng.uniform(-0.7, 0.7, 3).astype(np.float32)
+        if rng.random() < 0.5:                                      # near a sphere surface (inside the gap)
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            x = (sp[0, :3] + d * (sp[0, 5] + rng.uniform(-2, 2) * sp[0, 3])).astype(np.float32)
+        dx = (rng.normal(size=3) * 1e-3).astype(np.float32)
+        A = rng.normal(size=(3, 3)); H = (A @ A.T).astype(np.float32).reshape(9)
+        mode = int(rng.integers(0, 3))
+        n0, f0, H0 = _call_vertex(o, x, dx, 0.01, 0.4, H, sp, fl, mode)
+        n1, f1, H1 = _call_vertex(b, x, dx, 0.01, 0.4, H, sp, fl, mode)
+        assert n0 == n1 and same_bits(f0, f1).all() and same_bits(H0, H1).all()
+        hits += n0
+        y1 = (x + rng.normal(size=3) * 0.2).astype(np.float32)
+        for pinned in (0, 1):
+            i0 = C.c_int(0); i1 = C.c_int(0)
+            t0 = o.orc_collider_toi(fp(x), fp(y1), pinned, fp(sp), 2, fp(fl), 2, C.c_float(1.25), C.byref(i0))
+            t1 = b.orc_collider_toi(fp(x), fp(y1), pinned, fp(sp), 2, fp(fl), 2, C.c_float(1.25), C.byref(i1))
+            assert same_bits(np.float32(t0), np.float32(t1)) and i0.value == i1.value
+    assert hits > 300
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_push_force_is_stiffness_times_the_energy_gradient(libs, which):
+    l = libs[which]
+    rng = np.random.default_rng(9)
+    none = np.zeros((0, 10), np.float32)
+    worst = 0.0
+    for case in range(200):
+        ghat, mass = 2e-3, 0.02
+        A = rng.normal(size=(3, 3)); Hm = A @ A.T
+        H = Hm.astype(np.float32).T.reshape(9)
+        if case % 2 == 0:   # static floor without friction: E = -d^3 / (3 ghat), d = (x - ground - ghat up) . up < 0
+            up = rng.normal(size=3); up /= np.linalg.norm(up)
+            ground = rng.uniform(-0.3, 0.3, 3)
+            gap = rng.uniform(0.1, 0.9) * ghat
+            x = (ground + up * gap + np.cross(up, rng.normal(size=3)) * 0.1)
+            fl = np.array([[*ground, ghat, 0.0, 1.0, *up, 0]], np.float32)
+            n, f, Hh = _call_vertex(l, x.astype(np.float32), np.zeros(3, np.float32), mass, 0.0, H, none, fl, 0)
+            x32 = x.astype(np.float32).astype(np.float64); g32 = fl[0, :3].astype(np.float64); u32 = fl[0, 6:9].astype(np.float64)
+            d = (x32 - g32 - np.float64(np.float32(ghat)) * u32) @ u32
+            gap_now = (x32 - g32) @ u32
+            k = u32 @ (Hm.astype(np.float32).astype(np.float64) @ u32) + mass / gap_now ** 2
+            want = k * (-(d * d) / ghat) * u32
+            curv = k * (-2.0 * d / ghat)
+            want_H = curv * np.outer(u32, u32)
+        else:               # static solid sphere without friction
+            c = rng.uniform(-0.2, 0.2, 3); r = 0.4
+            nrm = rng.normal(size=3); nrm /= np.linalg.norm(nrm)
+            gap = rng.uniform(0.1, 0.9) * ghat
+            x = c + nrm * (r + gap)
+            sp = np.array([[*c, ghat, 0.0, r, 1.0, 0, 0, 0]], np.float32)
+            n, f, Hh = _call_vertex(l, x.astype(np.float32), np.zeros(3, np.float32), mass, 0.0, H, sp, none, 0)
+            x32 = x.astype(np.float32).astype(np.float64); c32 = sp[0, :3].astype(np.float64)
+            dist = np.linalg.norm(x32 - c32); n32 = (x32 - c32) / dist
+            d = dist - (np.float64(np.float32(r)) + np.float64(np.float32(ghat)))
+            k = n32 @ (Hm.astype(np.float32).astype(np.float64) @ n32) + mass / (dist - np.float64(np.float32(r))) ** 2
+            want = k * (-(d * d) / ghat) * n32
+            want_H = k * (-2.0 * d / ghat) * np.outer(n32, n32)
+        assert n == 1
+        worst = max(worst, np.abs(f - want).max() / np.abs(want).max(), np.abs(Hh.reshape(3, 3).T - want_H).max() / np.abs(want_H).max())
+    assert worst < 2e-3, worst
+    # friction only adds a tangential force opposing nothing when the vertex has not moved, and never changes the count
+    fl = np.array([[0, 0, 0, ghat, 0.5, 1.0, 0, 1, 0, 0]], np.float32)
+    x = np.array([0.1, 0.5 * ghat, 0.2], np.float32)
+    n0, f0, _ = _call_vertex(l, x, np.zeros(3, np.float32), 0.02, 0.5, np.zeros(9, np.float32), none, fl, 0)
+    n1, f1, _ = _call_vertex(l, x, np.array([1e-3, 0, 0], np.float32), 0.02, 0.5, np.zeros(9, np.float32), none, fl, 0)
+    assert n0 == n1 == 1 and f0[0] == 0 and f1[0] != 0 and f0[1] == f1[1]
+    # the gradient points against the wall normal (sign convention: "force" arrays hold dE/dx) and friction along the slip
+    assert f0[1] < 0 and f1[0] > 0
+    # zero thickness cutoff: a vertex deeper than `thickness` below the wall passes through
+    fl[0, 5] = 1e-4
+    n2, f2, _ = _call_vertex(l, np.array([0.1, -5e-4, 0.2], np.float32), np.zeros(3, np.float32), 0.02, 0.5, np.zeros(9, np.float32), none, fl, 0)
+    assert n2 == 0 and not f2.any()
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_collider_line_search(libs, which):
+    l = libs[which]
+    none = np.zeros((0, 10), np.float32)
+    fl = np.array([[0, 0, 0, 1e-3, 0, 1.0, 0, 1, 0, 0]], np.float32)
+    inf = C.c_int(0)
+    y0 = np.array([0, 0.1, 0], np.float32)
+    # free vertex heading through the wall: stops exactly at the wall (t = h0 / (h0 - h1), in units of the 1.25 x extrapolated step)
+    t = l.orc_collider_toi(fp(y0), fp(np.array([0, -0.1, 0], np.float32)), 0, fp(none), 0, fp(fl), 1, C.c_float(1.25), C.byref(inf))
+    assert abs(t - 1.25 * (0.1 / (0.1 + 0.15))) < 1e-6 and inf.value == 0
+    # staying above: no cut
+    t = l.orc_collider_toi(fp(y0), fp(np.array([0.3, 0.05, 0], np.float32)), 0, fp(none), 0, fp(fl), 1, C.c_float(1.25), C.byref(inf))
+    assert t == np.float32(1.25)
+    # a pinned vertex crossing from outside to inside is flagged, not clamped
+    t = l.orc_collider_toi(fp(y0), fp(np.array([0, -0.1, 0], np.float32)), 1, fp(none), 0, fp(fl), 1, C.c_float(1.25), C.byref(inf))
+    assert t == np.float32(1.25) and inf.value == 1
+    # sphere: radial crossing at r = radius; inverted sphere (container) keeps the vertex inside
+    sp = np.array([[0, 0, 0, 1e-3, 0, 0.5, 1.0, 0, 0, 0]], np.float32)
+    t = l.orc_collider_toi(fp(np.array([0.8, 0, 0], np.float32)), fp(np.array([0.4, 0, 0], np.float32)), 0, fp(sp), 1, fp(none), 0, C.c_float(1.25), C.byref(inf))
+    assert abs(t - 1.25 * (0.3 / 0.5)) < 1e-6
+    sp[0, 8] = 1
+    t = l.orc_collider_toi(fp(np.array([0.2, 0, 0], np.float32)), fp(np.array([0.6, 0, 0], np.float32)), 0, fp(sp), 1, fp(none), 0, C.c_float(1.25), C.byref(inf))
+    assert abs(t - 1.25 * (0.3 / 0.5)) < 1e-6
+    # kinematic colliders take no part in the line search
+    sp[0, 9] = 1
+    t = l.orc_collider_toi(fp(np.array([0.2, 0, 0], np.float32)), fp(np.array([0.6, 0, 0], np.float32)), 0, fp(sp), 1, fp(none), 0, C.c_float(1.25), C.byref(inf))
+    assert t == np.float32(1.25)
+
+
+def test_oracle_drapes_a_sheet_over_sphere_and_floor(run_job):
+    """whole steps on the CPU: the sheet lands on the invisible sphere, its corners on the invisible floor; nothing tunnels"""
+    o = run_job({"lib": "oracle", "scene": "drape", "n": 24, "state": None, "steps": 140})
+    assert bool(o["ok"].all()) and np.isfinite(o["curr"]).all()
+    x = o["curr"].astype(np.float64)
+    assert np.linalg.norm(x, axis=1).min() > 0.4 and x[:, 1].min() > -0.08      # outside the sphere (r = 0.4), above the floor (y = -0.08)
+    assert o["log_num_contact"].max() > 100
+    assert np.linalg.norm(x, axis=1).min() < 0.4 + 1.01e-3                       # resting inside the contact gap
