@@ -94,6 +94,7 @@ void gen_cylinder(double r, double min_x, double max_x, unsigned n, std::vector<
                   std::vector<std::array<unsigned, 3>> &F);
 void gen_square(unsigned res, double size, Vec3d ex, Vec3d ey, std::vector<Vec3d> &V,
                 std::vector<std::array<unsigned, 3>> &F);
+void gen_icosphere(double r, unsigned subdiv_count, std::vector<Vec3d> &V, std::vector<std::array<unsigned, 3>> &F);
 std::vector<unsigned> grab(const std::vector<Vec3d> &V, Vec3d dir, double eps = 1e-3);
 // make_woven_cylinder of examples/woven.ipynb / large-woven.ipynb: axial strands (open) and woven rings (closed)
 void gen_woven_cylinder(unsigned n, double offset, double scale, std::vector<std::vector<Vec3d>> &strands, std::vector<bool> &closed);

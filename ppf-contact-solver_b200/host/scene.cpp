@@ -66,6 +66,46 @@ void gen_square(unsigned res, double size, Vec3d ex, Vec3d ey, std::vector<Vec3d
         }
 }
 
+// crates/ppf-cts-core/src/datamodel/mesh.rs:359-438: icosahedron refined `subdiv_count` times, edge midpoints pushed to the sphere
+void gen_icosphere(double r, unsigned subdiv_count, std::vector<Vec3d> &V, std::vector<std::array<unsigned, 3>> &F) {
+    const double phi = (1.0 + std::sqrt(5.0)) / 2.0, nrm = std::sqrt(1.0 + phi * phi);
+    const double raw[12][3] = {{-1, phi, 0}, {1, phi, 0}, {-1, -phi, 0}, {1, -phi, 0}, {0, -1, phi}, {0, 1, phi},
+                               {0, -1, -phi}, {0, 1, -phi}, {phi, 0, -1}, {phi, 0, 1}, {-phi, 0, -1}, {-phi, 0, 1}};
+    static const unsigned base[20][3] = {{0, 11, 5}, {0, 5, 1}, {0, 1, 7}, {0, 7, 10}, {0, 10, 11}, {1, 5, 9}, {5, 11, 4}, {11, 10, 2}, {10, 7, 6}, {7, 1, 8},
+                                         {3, 9, 4}, {3, 4, 2}, {3, 2, 6}, {3, 6, 8}, {3, 8, 9}, {4, 9, 5}, {2, 4, 11}, {6, 2, 10}, {8, 6, 7}, {9, 8, 1}};
+    V.clear();
+    F.clear();
+    for (auto &v : raw) V.push_back(Vec3d{v[0] / nrm, v[1] / nrm, v[2] / nrm});
+    for (auto &f : base) F.push_back({f[0], f[1], f[2]});
+    for (unsigned it = 0; it < subdiv_count; ++it) {
+        std::map<std::pair<unsigned, unsigned>, unsigned> mid;
+        std::vector<std::array<unsigned, 3>> nf;
+        nf.reserve(F.size() * 4);
+        auto get_mid = [&](unsigned i, unsigned j) {
+            const auto key = i < j ? std::make_pair(i, j) : std::make_pair(j, i);
+            auto f = mid.find(key);
+            if (f != mid.end()) return f->second;
+            const Vec3d &p0 = V[i], &p1 = V[j];
+            const Vec3d m{0.5 * (p0[0] + p1[0]), 0.5 * (p0[1] + p1[1]), 0.5 * (p0[2] + p1[2])};
+            const double len = std::sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+            const unsigned idx = (unsigned)V.size();
+            V.push_back(Vec3d{m[0] / len, m[1] / len, m[2] / len});
+            mid.emplace(key, idx);
+            return idx;
+        };
+        for (auto &t : F) {
+            const unsigned a = t[0], b = t[1], c = t[2];
+            const unsigned m0 = get_mid(a, b), m1 = get_mid(b, c), m2 = get_mid(c, a);
+            nf.push_back({a, m0, m2});
+            nf.push_back({m0, b, m1});
+            nf.push_back({m2, m1, c});
+            nf.push_back({m0, m1, m2});
+        }
+        F.swap(nf);
+    }
+    for (auto &v : V) v = Vec3d{v[0] * r, v[1] * r, v[2] * r};
+}
+
 // crates/ppf-cts-core/src/kernels/scene_build/transform.rs:97-120
 std::vector<unsigned> grab(const std::vector<Vec3d> &V, Vec3d dir, double eps) {
     std::vector<unsigned> out;
@@ -300,6 +340,38 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.frames = 200;
         const double jitter = 0.35;
         s.args.gravity_y_keys = {{0.0, -9.8}, {1.0, -9.8}, {1.0 + jitter, 9.8}, {2.0, -9.8}};
+        return s;
+    }
+    if (name == "headless") { // examples/headless.py (the CI smoke scene): five curtains pinned along their top edge, a fully pinned
+        // sphere mesh pushed through them (.jitter() left out; UV-less rest frames, like `hang`)
+        SceneSpec s;
+        s.name = name;
+        const unsigned res = n ? n : 64;
+        const unsigned subdiv = (n == 0 || n >= 64) ? 4u : (n >= 32 ? 3u : 2u);
+        for (int i = 0; i < 5; ++i) {
+            ShellObject o;
+            gen_square(res, 2.0, Vec3d{0, 0, 1}, Vec3d{0, 1, 0}, o.vert, o.tri);
+            o.param = tri_defaults();
+            o.param["strain-limit"] = 0.05;
+            o.displacement = Vec3d{i * 0.25, 0, 0};
+            Pin p;
+            p.index = grab(o.vert, Vec3d{0, 1, 0});
+            o.pins.push_back(p);
+            s.objects.push_back(std::move(o));
+        }
+        ShellObject sp;
+        gen_icosphere(0.5, subdiv, sp.vert, sp.tri);
+        sp.param = tri_defaults();
+        sp.displacement = Vec3d{-1, 0, 0};
+        Pin p;
+        for (unsigned k = 0; k < sp.vert.size(); ++k) p.index.push_back(k);
+        PinOp mv; mv.kind = PinOp::MoveBy; mv.delta = Vec3d{8, 0, 0}; mv.t_start = 0.0; mv.t_end = 5.0;
+        p.ops = {mv};
+        sp.pins.push_back(p);
+        s.objects.push_back(std::move(sp));
+        s.args.dt = 0.01;
+        s.args.min_newton_steps = 8;
+        s.args.frames = 60;
         return s;
     }
     if (name == "drape") { // test scene: a sheet thrown onto an invisible sphere standing on an invisible floor (analytic colliders with friction)

@@ -1,7 +1,7 @@
 """Runs one backend job (a backend library keeps global state, so one Session per library per process).
 
 job = {"lib": "ours"|"reference"|"oracle", "scene": ..., "n": ..., "state": path|None, "steps": k,
-       "dump_linsys": bool, "detect": "state"|"final"|None, "detect_twice": bool, "out": directory}
+       "dump_linsys": bool, "detect": "state"|"final"|None, "detect_twice": bool, "save_state": path|None, "out": directory}
 Writes out/result.npz (+ out/linsys_0.bin) and returns the dict of arrays.  Used in-process by the
 tests for the first job on a library (so the CUDA .so is loaded by the pytest process itself) and as
 `python tests/_worker.py job.json` in a subprocess for every further job.
@@ -46,6 +46,8 @@ def run(job):
         oks.append(ok); walls.append(ms)
         if not ok:
             break
+    if job.get("save_state"):
+        assert s.save_state(job["save_state"])
     curr, prev = s.fetch()
     res["ok"] = np.array(oks); res["wall_ms"] = np.array(walls)
     res["curr"] = curr; res["prev"] = prev; res["time"] = np.array([s.time])

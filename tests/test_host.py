@@ -138,3 +138,38 @@ def test_oracle_steps_a_woven_rod_scene(run_job):
     assert idx.size == 36 and float(np.abs(o["curr"][idx] - o["fix_target"]).max()) < 0.03
     first = run_job({"lib": "oracle", "scene": "woven", "n": 32, "state": None, "steps": 1, "fix_positions": True})
     assert (first["log_toi"] == 1.0).all() and np.array_equal(first["curr"][idx], first["fix_target"])   # full step: exact Dirichlet rows
+
+
+def test_headless_scene_matches_the_reference_example(ppf):
+    """examples/headless.py: five 64 x 64 curtains + a fully pinned icosphere(r = 0.5, subdiv 4): 23 042 vertices"""
+    import ctypes
+
+    h = ppf.host()
+    p = ctypes.c_void_p(h.ppfh_create(b"headless", ctypes.c_uint(0)))
+    c = (ctypes.c_uint * 6)()
+    h.ppfh_counts(p, c)
+    nv, nf, ne, nh, nfix = [int(v) for v in c[:5]]
+    assert nv == 5 * 64 * 64 + 2562 and nf == 5 * 2 * 63 * 63 + 5120
+    assert nfix == 5 * 64 + 2562                      # top edge of every curtain + the whole sphere
+    face = np.empty((nf, 3), np.uint32)
+    h.ppfh_topology(p, face.ctypes.data_as(ctypes.c_void_p), None, None)
+    h.ppfh_destroy(p)
+    # the sphere is the last object: a closed surface (V - E + F = 2 with E = 3F / 2)
+    sph = face[5 * 2 * 63 * 63:]
+    vs = np.unique(sph)
+    assert vs.size == 2562 and vs.size - 3 * len(sph) // 2 + len(sph) == 2
+
+
+def test_oracle_steps_headless_from_a_contact_state(run_job):
+    """the pinned sphere pushing into the curtains (state made by tests/golden/make_headless_state.py): moving fully pinned
+    object vs free cloth, strain limiting and min-newton-steps 8 in one step"""
+    state = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "headless_n24", "state_00068.bin")
+    o = run_job({"lib": "oracle", "scene": "headless", "n": 24, "state": state, "steps": 1, "fix_positions": True})
+    assert bool(o["ok"].all()) and len(o["log_iter"]) >= 9          # min-newton-steps 8 + the error-reduction iteration
+    assert o["log_num_contact"].min() > 100
+    idx = o["fix_index"].astype(np.int64)
+    assert idx.size == 5 * 24 + 162
+    # the sphere (last 162 vertices) stays rigid: it is fully prescribed
+    x = o["curr"].astype(np.float64)[-162:]
+    r = np.linalg.norm(x - x.mean(axis=0), axis=1)
+    assert np.allclose(r, 0.5, atol=1e-5)
