@@ -78,9 +78,23 @@ struct SimArgs { // crates/ppf-cts-solver/src/args.rs:22-94 (defaults params.rs:
     std::vector<std::pair<double, double>> gravity_y_keys;
 };
 // invisible analytic colliders (frontend scene.add.invisible.wall / .sphere; scene.rs InvisibleWall / InvisibleSphere).
-// Static ones only (a single keyframe): make_constraint emits them with kinematic = false (scene.rs:2041-2049).
-struct WallCollider { Vec3d position{0, 0, 0}, normal{0, 1, 0}; double contact_gap = 1e-3, friction = 0.0, thickness = 1.0; };
-struct SphereCollider { Vec3d center{0, 0, 0}; double radius = 1.0; bool inverted = false, hemisphere = false; double contact_gap = 1e-3, friction = 0.0, thickness = 1.0; };
+// `keys` = further keyframes (time, position[, radius]) after the one at t = 0 (frontend .move_to / .move_by / .radius): a
+// collider with keyframes is kinematic for the whole run and blended linearly (or smoothstep) between them (scene.rs:2014-2049).
+struct WallCollider {
+    Vec3d position{0, 0, 0}, normal{0, 1, 0};
+    double contact_gap = 1e-3, friction = 0.0, thickness = 1.0;
+    std::vector<std::pair<double, Vec3d>> keys;
+    bool smooth = false;
+};
+struct SphereCollider {
+    Vec3d center{0, 0, 0};
+    double radius = 1.0;
+    bool inverted = false, hemisphere = false;
+    double contact_gap = 1e-3, friction = 0.0, thickness = 1.0;
+    struct Key { double time; Vec3d center; double radius; };
+    std::vector<Key> keys;
+    bool smooth = false;
+};
 struct SceneSpec {
     std::string name;
     std::vector<ShellObject> objects;

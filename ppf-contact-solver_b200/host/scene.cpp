@@ -393,6 +393,27 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.friction_mode = "min";
         return s;
     }
+    if (name == "lift") { // test scene: a sheet pinned at two corners, lifted by an invisible sphere that rises from below (kinematic collider)
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_square(n ? n : 32, 2.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+        o.param = tri_defaults();
+        Pin p;
+        auto a = grab(o.vert, Vec3d{-1, 0, -1}), c = grab(o.vert, Vec3d{1, 0, -1});
+        p.index = a;
+        p.index.insert(p.index.end(), c.begin(), c.end());
+        o.pins.push_back(p);
+        s.objects.push_back(o);
+        SphereCollider sp;
+        sp.center = Vec3d{0.1, -0.9, 0.2};
+        sp.radius = 0.5;
+        sp.keys.push_back({0.6, Vec3d{0.1, -0.2, 0.2}, 0.5});
+        s.spheres.push_back(sp);
+        s.args.frames = 90;
+        s.args.dt = 1e-2;
+        return s;
+    }
     if (name == "sheet") { // free-hanging sheet without strain limit: elastic-only smoke scene
         SceneSpec s;
         s.name = name;
@@ -505,17 +526,50 @@ void make_constraint(Built &b, double time, double prev_time) {
     const float ws = float(b.spec.args.world_scaling);
     b.floor.clear();
     b.sphere.clear();
+    // calc_coefficient (scene.rs:2014-2038): keyframe pair (j, k) and blend weight at `time`; timings[0] = 0
+    auto blend = [&](const std::vector<double> &timings, bool smooth, size_t &j, size_t &k, float &w) {
+        const size_t n = timings.size();
+        if (time >= timings[n - 1]) { j = k = n - 1; w = 1.0f; return; }
+        for (size_t i = 0; i + 1 < n; ++i)
+            if (time >= timings[i] && time < timings[i + 1]) {
+                double ww = (time - timings[i]) / (timings[i + 1] - timings[i]);
+                if (smooth) ww = ww * ww * (3.0 - 2.0 * ww);
+                j = i; k = i + 1; w = float(ww);
+                return;
+            }
+        j = k = 0; w = 0.0f;
+    };
     for (auto &w : b.spec.walls) {
         PpfFloor f{};
-        for (int k = 0; k < 3; ++k) { f.ground.v[k] = float(w.position[k]) * ws; f.up.v[k] = float(w.normal[k]); }
-        f.ghat = float(w.contact_gap); f.friction = float(w.friction); f.thickness = float(w.thickness) * ws; f.kinematic = false;
+        std::vector<double> timings{0.0};
+        std::vector<Vec3f> pos{Vec3f{float(w.position[0]) * ws, float(w.position[1]) * ws, float(w.position[2]) * ws}};
+        for (auto &kf : w.keys) { timings.push_back(kf.first); pos.push_back(Vec3f{float(kf.second[0]) * ws, float(kf.second[1]) * ws, float(kf.second[2]) * ws}); }
+        size_t j = 0, k = 0;
+        float wt = 0.0f;
+        const bool kinematic = timings.size() > 1;
+        if (kinematic) blend(timings, w.smooth, j, k, wt);
+        for (int c = 0; c < 3; ++c) { f.ground.v[c] = pos[j][c] * (1.0f - wt) + pos[k][c] * wt; f.up.v[c] = float(w.normal[c]); }
+        f.ghat = float(w.contact_gap); f.friction = float(w.friction); f.thickness = float(w.thickness) * ws; f.kinematic = kinematic;
         b.floor.push_back(f);
     }
     for (auto &sp : b.spec.spheres) {
         PpfSphere q{};
-        for (int k = 0; k < 3; ++k) q.center.v[k] = float(sp.center[k]) * ws;
-        q.ghat = float(sp.contact_gap); q.friction = float(sp.friction); q.radius = float(sp.radius) * ws; q.thickness = float(sp.thickness) * ws;
-        q.bowl = sp.hemisphere; q.reverse = sp.inverted; q.kinematic = false;
+        std::vector<double> timings{0.0};
+        std::vector<Vec3f> pos{Vec3f{float(sp.center[0]) * ws, float(sp.center[1]) * ws, float(sp.center[2]) * ws}};
+        std::vector<float> rad{float(sp.radius) * ws};
+        for (auto &kf : sp.keys) {
+            timings.push_back(kf.time);
+            pos.push_back(Vec3f{float(kf.center[0]) * ws, float(kf.center[1]) * ws, float(kf.center[2]) * ws});
+            rad.push_back(float(kf.radius) * ws);
+        }
+        size_t j = 0, k = 0;
+        float wt = 0.0f;
+        const bool kinematic = timings.size() > 1;
+        if (kinematic) blend(timings, sp.smooth, j, k, wt);
+        for (int c = 0; c < 3; ++c) q.center.v[c] = pos[j][c] * (1.0f - wt) + pos[k][c] * wt;
+        q.radius = rad[j] * (1.0f - wt) + rad[k] * wt;
+        q.ghat = float(sp.contact_gap); q.friction = float(sp.friction); q.thickness = float(sp.thickness) * ws;
+        q.bowl = sp.hemisphere; q.reverse = sp.inverted; q.kinematic = kinematic;
         b.sphere.push_back(q);
     }
     PpfConstraint &c = b.constraint;

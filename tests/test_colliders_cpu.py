@@ -165,3 +165,15 @@ def test_oracle_drapes_a_sheet_over_sphere_and_floor(run_job):
     assert np.linalg.norm(x, axis=1).min() > 0.4 and x[:, 1].min() > -0.08      # outside the sphere (r = 0.4), above the floor (y = -0.08)
     assert o["log_num_contact"].max() > 100
     assert np.linalg.norm(x, axis=1).min() < 0.4 + 1.01e-3                       # resting inside the contact gap
+
+
+def test_oracle_lifts_a_sheet_with_a_kinematic_sphere(run_job):
+    """keyframed (kinematic) collider: penalty with the stiffness m / ghat^2 and no line search (contact.cu:1230-1263)"""
+    o = run_job({"lib": "oracle", "scene": "lift", "n": 24, "state": None, "steps": 70})
+    assert bool(o["ok"].all()) and np.isfinite(o["curr"]).all()
+    assert o["log_num_contact"].max() > 100
+    x = o["curr"].astype(np.float64)
+    t = min(float(o["time"][0]), 0.6) / 0.6
+    c = np.array([0.1, -0.9 + 0.7 * t, 0.2])
+    assert np.linalg.norm(x - c, axis=1).min() > 0.5 - 2e-3           # a penalty, not a hard constraint: at most a fraction of the gap inside
+    assert x[:, 1].max() > 0.2                                          # the sheet has been lifted above its pinned corners

@@ -43,3 +43,22 @@ def test_headless_step_matches_the_oracle(run_job):
     # the prescribed sphere (last 162 vertices) is where the oracle has it: Dirichlet rows copy the pin targets (a step whose
     # accumulated line-search fraction stays below 1 rewinds them by that fraction of the 1.6 cm the sphere moves per step)
     assert float(np.abs(g["curr"][-162:] - o["curr"][-162:]).max()) < 1e-4
+
+
+def test_kinematic_collider_lift_matches_the_oracle(run_job):
+    """`lift`: a sheet pinned at two corners lifted by a keyframed invisible sphere (kinematic collider branch of
+    contact.cu:1230-1263).  Chained steps through the first contacts, compared in aggregate like the drape test."""
+    job = {"scene": "lift", "n": 24, "state": None, "steps": 30}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    assert o["log_num_contact"].max() > 30
+    assert abs(len(g["log_num_contact"]) - len(o["log_num_contact"])) <= 4
+    assert abs(g["log_num_contact"].max() - o["log_num_contact"].max()) <= 5 + 0.25 * o["log_num_contact"].max()
+    assert abs(float(g["time"][0]) - float(o["time"][0])) < 0.1 * float(o["time"][0])
+    x = g["curr"].astype(np.float64)
+    t = min(float(g["time"][0]), 0.6) / 0.6
+    c = np.array([0.1, -0.9 + 0.7 * t, 0.2])
+    assert np.isfinite(x).all() and np.linalg.norm(x - c, axis=1).min() > 0.5 - 2e-3
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 1e-3, float(np.median(d))
