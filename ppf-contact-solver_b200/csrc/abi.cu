@@ -235,6 +235,10 @@ void upload_dataset(State &s) {
         s.vcollider.upload(vc.data(), nv, q); s.fskip.upload(fsk.data(), nf, q);
         CUDA_OK(cudaStreamSynchronize(q));
     }
+    s.has_offsets = false;
+    for (unsigned i = 0; i < d.param_arrays.face.size; ++i) s.has_offsets = s.has_offsets || d.param_arrays.face.data[i].offset > 0.0f;
+    for (unsigned i = 0; i < d.param_arrays.edge.size; ++i) s.has_offsets = s.has_offsets || d.param_arrays.edge.data[i].offset > 0.0f;
+    for (unsigned i = 0; i < d.param_arrays.vertex.size; ++i) s.has_offsets = s.has_offsets || d.param_arrays.vertex.data[i].offset > 0.0f;
     // ---- rods: Hookean edges [0, rod_count) and the bending stencils of interior rod vertices ----
     s.nrod = d.rod_count;
     s.nrodbend = 0;

@@ -117,6 +117,7 @@ struct State {
     DBuf<float4> fmat;                            // per face (mu, lambda, mass, deform_damping)
     DBuf<float2> fstrain;                         // per face (strain-limit parameter, shrink-adjusted limit); 0 = off
     bool has_strainlimit = false;
+    bool has_offsets = false;                     // some vertex / edge / face parameter set carries a contact offset
     DBuf<float4> inv_rest;                        // per face 2x2
     DBuf<float4> hmat;                            // per hinge (length, area, rest_angle, bend_dir)
     DBuf<float> hinge_stiff;                      // per hinge stiffness (energy.cu:510-517), 0 = skip

@@ -1088,30 +1088,19 @@ __global__ void __launch_bounds__(128) k_isect_vertex(IsectArgs A, unsigned nq) 
     if (!ok) atomicExch(A.counter + 1, 1u);
 }
 
-static int g_has_offsets = -1;
-
 bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm) {
     (void)prm;
     cudaStream_t q = s.stream;
-    if (g_has_offsets < 0) {
-        g_has_offsets = 0;
-        for (unsigned i = 0; i < s.host.param_arrays.face.size; ++i)
-            if (s.host.param_arrays.face.data[i].offset > 0.0f) g_has_offsets = 1;
-        for (unsigned i = 0; i < s.host.param_arrays.edge.size; ++i)
-            if (s.host.param_arrays.edge.data[i].offset > 0.0f) g_has_offsets = 1;
-        for (unsigned i = 0; i < s.host.param_arrays.vertex.size; ++i)
-            if (s.host.param_arrays.vertex.data[i].offset > 0.0f) g_has_offsets = 1;
-    }
     IsectArgs A;
     A.face = view_of(s.bvh_face); A.edge = view_of(s.bvh_edge); A.vert = view_of(s.bvh_vert);
     A.x = x; A.faces = s.face.p; A.edges = s.edge.p; A.vcp = s.vcp.p; A.ecp = s.ecp.p; A.fcp = s.fcp.p;
     A.vfixed = s.vfixed.p; A.efixed = s.efixed.p; A.ffixed = s.ffixed.p; A.vcollider = s.vcollider.p;
     A.records = s.isect_records.p;
     A.counter = s.counters.p + 26;
-    A.check_offsets = g_has_offsets;
+    A.check_offsets = s.has_offsets ? 1 : 0; // no contact offset anywhere: the "closer than the offsets" tests cannot fire
     CUDA_OK(cudaMemsetAsync(A.counter, 0, 2 * sizeof(unsigned), q));
     if (s.ne) k_isect_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);
-    if (g_has_offsets && s.nsv) k_isect_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(A, s.nsv);
+    if (s.has_offsets && s.nsv) k_isect_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(A, s.nsv);
     LAUNCH_COUNT(2);
     unsigned h[2];
     CUDA_OK(cudaMemcpyAsync(h, A.counter, sizeof(h), cudaMemcpyDeviceToHost, q));
