@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="large-twist")
     ap.add_argument("--n", type=int, default=0, help="resolution override (0 = the config's own: n=1410 for large-twist)")
+    ap.add_argument("--state", default=None, help="start from a saved state (ppf_host --save-every / Session.save_state) instead of t=0, e.g. a contact-rich window")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent scenes (weak scaling) instead of sharding ONE scene's PCG rows over the GPUs")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--full-v", type=int, default=0, help=argparse.SUPPRESS)
@@ -211,7 +212,7 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(devnull, 1)  # the backends narrate on stdout; keep ours for the JSON line
     try:
-        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK, shard=shard)
+        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK, shard=shard, state=args.state)
         if shard is not None:  # all ranks or none: a rank that could not join the communicator turns the run into replicas
             oks = [None] * WORLD
             ranks.dist.all_gather_object(oks, bool(s.sharded))
@@ -284,9 +285,9 @@ def main():
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "%s: %s n=%s, V=%d F=%d E=%d hinges=%d, dt=%s, steps from t=0; %s" % (
+        "config": {"workload": "%s: %s n=%s, V=%d F=%d E=%d hinges=%d, dt=%s; %s" % (
             args.scene, "woven rod cylinder" if "woven" in args.scene else "cylinder", args.n or "config default", s.n_vert, s.n_face, s.n_edge, s.n_hinge,
-            "1/120" if "woven" in args.scene else ("1e-3" if args.scene == "hang" else "1/60"),
+            ("1/120" if "woven" in args.scene else ("1e-3" if args.scene == "hang" else "1/60")) + (", steps from the saved state %s" % os.path.basename(args.state) if args.state else ", steps from t=0"),
             ("one scene, PCG rows sharded over %d GPUs (rows of p pushed + two 2-double sums per iteration over NVLink peer memory)" % WORLD) if shard is not None
             else ("replicas (one independent scene per GPU)" if WORLD > 1 else "single GPU")),
             "l2": "inputs larger than L2 (packed matrix %.0f MB per SpMV)" % ((40.0 * (st1["spmv_n_off"] if st1 else 0) + 60.0 * s.n_vert) * 1e-6)},
