@@ -304,6 +304,186 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.csrmat_max_nnz = 40000000u;
         return s;
     }
+    if (name == "large-five-twist") { // examples/large-five-twist.ipynb (8.2 M vertices at its own resolution; README.md:616)
+        SceneSpec s;
+        s.name = name;
+        const double half_length = 2.0 / 0.75, rad = 1.75;
+        const unsigned nn = n ? n : 1181;
+        for (int i = 0; i < 5; ++i) {
+            const double t = 2.0 * i / 5.0 * M_PI;
+            const double x = 0.0, y = rad * std::cos(t), z = rad * std::sin(t); // .at(0, x, y) of the notebook
+            ShellObject o;
+            gen_cylinder(1.0, -half_length, half_length, nn, o.vert, o.tri);
+            o.param = tri_defaults();
+            o.param["bend"] = 500.0 / 3.5;
+            o.param["contact-gap"] = n ? 2.0 * half_length / nn * 0.3875 : 1.75e-3; // the notebook's 1.75e-3 at n=1181 (0.39 edge lengths), scaled with n
+            o.param["young-mod"] = 1e4;
+            o.param["poiss-rat"] = 0.25;
+            o.param["density"] = 3.5;
+            o.displacement = Vec3d{x, y, z};
+            const double ang = 180.0, move_delta = 1.0, scale = 0.25, t_end = 34.0, t_wait = 500.0 / 60.0, s_wait = 16.0;
+            for (int side = 0; side < 2; ++side) {
+                const double sg = side == 0 ? -1.0 : 1.0; // left pin first
+                Pin p;
+                p.index = grab(o.vert, Vec3d{sg, 0, 0});
+                PinOp spin; spin.kind = PinOp::Spin; spin.axis = Vec3d{-sg, 0, 0}; spin.angular_velocity = ang; spin.t_start = 0; spin.t_end = t_wait;
+                PinOp scl; scl.kind = PinOp::Scale; scl.factor = scale; scl.t_start = 0; scl.t_end = s_wait; scl.center = Vec3d{-x + sg * half_length, -y, -z};
+                PinOp mv; mv.kind = PinOp::MoveBy; mv.delta = Vec3d{-sg * move_delta, 0, 0}; mv.t_start = 0; mv.t_end = t_end;
+                PinOp orbit; orbit.kind = PinOp::Spin; orbit.center = Vec3d{-x, -y, -z}; orbit.axis = Vec3d{-sg, 0, 0}; orbit.angular_velocity = 180.0;
+                orbit.t_start = t_wait; orbit.t_end = 150.0;
+                p.ops = {spin, scl, mv, orbit};
+                o.pins.push_back(p);
+            }
+            s.objects.push_back(std::move(o));
+        }
+        s.args.dt = 1.0 / 60.0;
+        s.args.frames = 2400;
+        s.args.gravity = Vec3d{0, 0, 0};
+        s.args.friction_mode = "max";
+        s.args.csrmat_max_nnz = 90000000u;
+        return s;
+    }
+    if (name == "curtain" || name == "drape-sheets") {
+        // examples/curtain.ipynb: fifteen curtains pinned along their top edge, a fully pinned sphere mesh pushed through them;
+        // examples/drape.ipynb: five sheets pinned at two corners settling onto a fully pinned sphere mesh (.jitter() left out)
+        const bool curtain = name == "curtain";
+        SceneSpec s;
+        s.name = name;
+        const unsigned res = n ? n : (curtain ? 64 : 128);
+        const unsigned subdiv = (n == 0 || n >= 64) ? 4u : (n >= 32 ? 3u : 2u);
+        for (int i = 0; i < (curtain ? 15 : 5); ++i) {
+            ShellObject o;
+            if (curtain) gen_square(res, 2.0, Vec3d{0, 0, 1}, Vec3d{0, 1, 0}, o.vert, o.tri);
+            else gen_square(res, 2.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+            o.param = tri_defaults();
+            o.param["strain-limit"] = 0.05;
+            o.displacement = curtain ? Vec3d{i * 0.25, 0, 0} : Vec3d{0, 0.05 * i, 0};
+            Pin p;
+            if (curtain) p.index = grab(o.vert, Vec3d{0, 1, 0});
+            else {
+                p.index = grab(o.vert, Vec3d{1, 0, -1});
+                auto c = grab(o.vert, Vec3d{-1, 0, -1});
+                p.index.insert(p.index.end(), c.begin(), c.end());
+            }
+            o.pins.push_back(p);
+            s.objects.push_back(std::move(o));
+        }
+        ShellObject sp;
+        gen_icosphere(0.5, subdiv, sp.vert, sp.tri);
+        sp.param = tri_defaults();
+        sp.displacement = curtain ? Vec3d{-1, 0, 0} : Vec3d{0, -0.5 - 0.05, 0};
+        Pin p;
+        for (unsigned k = 0; k < sp.vert.size(); ++k) p.index.push_back(k);
+        if (curtain) {
+            PinOp mv; mv.kind = PinOp::MoveBy; mv.delta = Vec3d{8, 0, 0}; mv.t_start = 0.0; mv.t_end = 5.0;
+            p.ops = {mv};
+        }
+        sp.pins.push_back(p);
+        s.objects.push_back(std::move(sp));
+        if (!curtain) { s.args.dt = 0.01; s.args.frames = 100; }
+        return s;
+    }
+    if (name == "belt") { // examples/belt.ipynb: three pinned rollers move outward and spin, tensioning three strain-limited belts (friction 0.5)
+        SceneSpec s;
+        s.name = name;
+        auto rotate_y90 = [](std::vector<Vec3d> &V) { for (auto &v : V) v = Vec3d{v[2], v[1], -v[0]}; }; // .rotate(90, "y")
+        const unsigned nroll = 21; // the scene exists at the notebook's resolution only (the 2 mm spacing of the nested belts needs it)
+        (void)n;
+        for (int i = 0; i < 3; ++i) {
+            const double t = 2.0 * i * M_PI / 3.0, x = 0.65 * std::sin(t), y = 0.65 * std::cos(t);
+            ShellObject o;
+            gen_cylinder(0.5, -0.5, 0.5, nroll, o.vert, o.tri);
+            rotate_y90(o.vert);
+            o.param = tri_defaults();
+            o.param["friction"] = 0.5;
+            o.displacement = Vec3d{x, y, 3e-3 * i}; // the notebook's 1e-2 * random() jitter, fixed
+            Pin p;
+            for (unsigned k = 0; k < o.vert.size(); ++k) p.index.push_back(k);
+            PinOp spin; spin.kind = PinOp::Spin; spin.axis = Vec3d{0, 0, 1}; spin.angular_velocity = 60.0; spin.t_start = 1.5; spin.t_end = 3.0;
+            PinOp mv; mv.kind = PinOp::MoveBy; mv.delta = Vec3d{0.511 * x, 0.511 * y, 0}; mv.t_start = 0.0; mv.t_end = 1.0;
+            p.ops = {spin, mv};
+            o.pins.push_back(p);
+            s.objects.push_back(std::move(o));
+        }
+        for (int k = 0; k < 3; ++k) {
+            const double r = 1.25 + 2e-3 * k, hw = 0.4 - 0.05 * k;
+            const unsigned nb = (unsigned)(44 * hw);
+            ShellObject o;
+            gen_cylinder(r, -hw, hw, nb, o.vert, o.tri);
+            rotate_y90(o.vert);
+            o.param = tri_defaults();
+            o.param["strain-limit"] = 0.06;
+            s.objects.push_back(std::move(o));
+        }
+        s.args.dt = 0.01;
+        s.args.frames = 200;
+        s.args.gravity = Vec3d{0, 0, 0};
+        s.args.min_newton_steps = 32;
+        s.args.friction_mode = "max";
+        return s;
+    }
+    if (name == "yarn") { // examples/yarn.ipynb: make_strands(4e-3, 0.5, res): interlaced yarns pulled apart at both ends, closed loops along the edges
+        SceneSpec s;
+        s.name = name;
+        const double res = 1.0, width = 0.5; // the notebook's make_strands(4e-3, 0.5, 1.0); the weave does not scale with a resolution override
+        (void)n;
+        const double offset = 1.3 * 4e-3;
+        const unsigned n_vertical = (unsigned)(res * 0.28 / offset), n_per_seg = (unsigned)(res * 20), n_segs = (unsigned)(width * n_vertical);
+        const unsigned n_points = n_segs * n_per_seg;
+        const double dx = 1.0 / double(n_points - 1);
+        auto add_rod = [&](std::vector<Vec3d> V, bool closed) {
+            ShellObject o;
+            o.vert = std::move(V);
+            const unsigned m = (unsigned)o.vert.size();
+            for (unsigned i = 0; i + 1 < m; ++i) o.rod.push_back({i, i + 1});
+            if (closed) o.rod.push_back({m - 1, 0u});
+            o.rod_param = rod_defaults();
+            o.rod_param["bend"] = 0.0;
+            o.rod_param["young-mod"] = 1e5;
+            o.rod_param["contact-gap"] = 1e-3;
+            o.rod_param["contact-offset"] = 2.3e-3;
+            o.rod_param["length-factor"] = 0.85;
+            if (!closed)
+                for (int side = 0; side < 2; ++side) {
+                    const double sg = side == 0 ? -1.0 : 1.0;
+                    Pin p;
+                    p.index = grab(o.vert, Vec3d{sg, 0, 0});
+                    PinOp mv; mv.kind = PinOp::MoveBy; mv.delta = Vec3d{sg * 5.0, 0, 0}; mv.t_start = 0; mv.t_end = 10.0;
+                    p.ops = {mv};
+                    o.pins.push_back(p);
+                }
+            s.objects.push_back(std::move(o));
+        };
+        for (unsigned k = 0; k < n_vertical; ++k) {
+            const double y_base = n_vertical > 1 ? double(k) / double(n_vertical - 1) - 0.5 : 0.0;
+            std::vector<Vec3d> xyz(n_points);
+            for (unsigned j = 0; j < n_points; ++j) {
+                const double x_mod = double(j % n_per_seg) / double(n_per_seg), t = 2.0 * M_PI * x_mod;
+                xyz[j] = Vec3d{width * (2.0 * dx * j - 1.0) - width * (0.5 / n_segs) * std::sin(2.0 * t), y_base + (0.85 / n_vertical) * std::sin(t),
+                               0.75 * offset * std::cos(2.0 * t)};
+            }
+            add_rod(std::move(xyz), false);
+        }
+        for (int pos = 0; pos < 2; ++pos)
+            for (unsigned k = 0; k + 1 < n_segs; ++k) {
+                const double dxl = 2.0 * width / n_segs;
+                const double y_base = pos == 0 ? 0.5 + 0.25 * dxl : -0.5 - 0.25 * dxl, z_base = 0.15 * dxl;
+                double x_center = dxl * (k + 0.77) - width;
+                if (pos == 1) x_center += 0.5 * dxl;
+                const double r = 0.78 * width / n_segs, theta = 0.25 * M_PI;
+                std::vector<Vec3d> xyz(n_per_seg);
+                for (unsigned j = 0; j < n_per_seg; ++j) {
+                    const double t = 2.0 * M_PI * j / double(n_per_seg), zv = r * std::cos(t);
+                    xyz[j] = Vec3d{x_center + r * std::sin(t), pos == 0 ? y_base + zv * std::sin(theta) : y_base - zv * std::sin(theta), z_base + zv * std::cos(theta)};
+                }
+                add_rod(std::move(xyz), true);
+            }
+        s.args.dt = 1e-2;
+        s.args.frames = 120;
+        s.args.gravity = Vec3d{0, 0, 0};
+        s.args.friction_mode = "max";
+        return s;
+    }
     if (name == "woven") { // examples/woven.ipynb; an overridden n keeps the vertex spacing along the strands (scale ~ n)
         const unsigned nn = n ? n : 256;
         double scale = 2.0 * double(nn) / 256.0;

@@ -173,3 +173,29 @@ def test_oracle_steps_headless_from_a_contact_state(run_job):
     x = o["curr"].astype(np.float64)[-162:]
     r = np.linalg.norm(x - x.mean(axis=0), axis=1)
     assert np.allclose(r, 0.5, atol=1e-5)
+
+
+def test_example_scene_sizes(ppf):
+    """further reference examples the host restates; vertex counts at the notebooks' own resolutions"""
+    import ctypes
+
+    h = ppf.host()
+    want = {"curtain": 15 * 64 * 64 + 2562, "drape-sheets": 5 * 128 * 128 + 2562, "yarn": 53 * 520 + 2 * 25 * 20, "belt": None}
+    for scene, nv_want in want.items():
+        p = ctypes.c_void_p(h.ppfh_create(scene.encode(), ctypes.c_uint(0)))
+        assert p
+        c = (ctypes.c_uint * 6)()
+        h.ppfh_counts(p, c)
+        if nv_want is not None:
+            assert int(c[0]) == nv_want, (scene, int(c[0]))
+        assert int(c[4]) > 0                                  # every one of them has pins
+        h.ppfh_destroy(p)
+
+
+def test_oracle_steps_reduced_example_scenes(run_job):
+    """reduced-resolution variants step on the CPU oracle: sheets settling on a fully pinned sphere mesh (contacts between free
+    cloth and prescribed faces), and the five-cylinder twist with orbiting pins"""
+    o = run_job({"lib": "oracle", "scene": "drape-sheets", "n": 24, "state": None, "steps": 25})
+    assert bool(o["ok"].all()) and o["log_num_contact"].max() > 50
+    o = run_job({"lib": "oracle", "scene": "large-five-twist", "n": 24, "state": None, "steps": 8})
+    assert bool(o["ok"].all()) and o["log_num_contact"].max() > 500
