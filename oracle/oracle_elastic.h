@@ -601,4 +601,80 @@ static inline float o_rod_strain_toi(const float *d0, const float *d1, float l0,
     return t;
 }
 
+/* ---- isotropic shell models ARAP / StVK / SNHk (energy.cu:337-352; arap.hpp:36-49, stvk.hpp:38-72 + detsqr.hpp:22-33,
+ * snhk.hpp:45-56; eigenanalysis.cu:14-85).  model: 0 ARAP, 1 StVK, 3 SNHk.  d2 = (d00, d01, d11). ---- */
+static inline void o_iso_table2(int model, const float *a, float mu, float lmd, float *deda, float *d2) {
+    if (model == 0) {
+        const float tr = (a[0] - 1.0f) + (a[1] - 1.0f);
+        deda[0] = 2.0f * mu * (a[0] - 1.0f) + lmd * tr * 1.0f;
+        deda[1] = 2.0f * mu * (a[1] - 1.0f) + lmd * tr * 1.0f;
+        d2[0] = 2.0f * mu * 1.0f + lmd; d2[2] = 2.0f * mu * 1.0f + lmd; d2[1] = 2.0f * mu * 0.0f + lmd;
+    } else if (model == 1) {
+        const float a0 = a[0] - 1.0f, a1 = a[1] - 1.0f, J = a[0] * a[1];
+        deda[0] = mu * (a0 * a0 * a0) + lmd * a[1] * (J - 1.0f);
+        deda[1] = mu * (a1 * a1 * a1) + lmd * a[0] * (J - 1.0f);
+        d2[0] = mu * (3.0f * a0 * a0) + lmd * (a[1] * a[1]);
+        d2[2] = mu * (3.0f * a1 * a1) + lmd * (a[0] * a[0]);
+        d2[1] = mu * 0.0f + lmd * (2.0f * a[0] * a[1] - 1.0f);
+    } else {
+        const float x = a[0], y = a[1];
+        deda[0] = lmd * y * (x * y - 1.0f) + mu * (x - y);
+        deda[1] = lmd * x * (x * y - 1.0f) + mu * (y - x);
+        d2[0] = lmd * y * y + mu; d2[2] = lmd * x * x + mu; d2[1] = 2.0f * lmd * x * y - lmd - mu;
+    }
+}
+static inline void o_iso_face(const float *x0, const float *x1, const float *x2, const float *ir, int model, float mu, float lmd, float mass,
+                              float eig_eps, float f[3][3], float H[3][3][9]) {
+    float F[3][2], deda[2], d2[3], dedF[3][2], ev[2], evec[2][2];
+    o_svd32 svd;
+    o_defgrad32(x0, x1, x2, ir, F);
+    o_jacobi_svd32(F, &svd);
+    o_iso_table2(model, svd.S, mu, lmd, deda, d2);
+    for (int r = 0; r < 3; ++r)
+        for (int j = 0; j < 2; ++j) dedF[r][j] = (svd.U[r][0] * deda[0]) * svd.Vt[0][j] + (svd.U[r][1] * deda[1]) * svd.Vt[1][j];
+    o_symm2x2(d2[0], d2[1], d2[2], ev, evec);
+    const float is2 = 0.7071067811865475f;
+    float U3[3][3], Q[6][3][2];
+    for (int r = 0; r < 3; ++r) { U3[r][0] = svd.U[r][0]; U3[r][1] = svd.U[r][1]; }
+    U3[0][2] = svd.U[1][0] * svd.U[2][1] - svd.U[2][0] * svd.U[1][1];
+    U3[1][2] = svd.U[2][0] * svd.U[0][1] - svd.U[0][0] * svd.U[2][1];
+    U3[2][2] = svd.U[0][0] * svd.U[1][1] - svd.U[1][0] * svd.U[0][1];
+    memset(Q, 0, sizeof(Q));
+    Q[0][0][1] = is2; Q[0][1][0] = -is2; Q[1][0][1] = is2; Q[1][1][0] = is2; Q[2][2][0] = 1.0f; Q[3][2][1] = 1.0f;
+    for (int i = 0; i < 2; ++i) { Q[4][i][i] = evec[i][0]; Q[5][i][i] = evec[i][1]; }
+    const float a0 = svd.S[0], a1 = svd.S[1], den = a0 - a1;
+    float lam[6];
+    lam[0] = fmaxf(0.0f, (deda[0] + deda[1]) / (a0 + a1));
+    lam[1] = fmaxf(0.0f, fabsf(den) > eig_eps ? (deda[0] - deda[1]) / den : 0.5f * (d2[0] + d2[2]) - 0.5f * (d2[1] + d2[1]));
+    lam[2] = fmaxf(0.0f, deda[0] / a0);
+    lam[3] = fmaxf(0.0f, deda[1] / a1);
+    lam[4] = fmaxf(0.0f, ev[0]);
+    lam[5] = fmaxf(0.0f, ev[1]);
+    float d2F[6][6];
+    memset(d2F, 0, sizeof(d2F));
+    for (int i = 0; i < 6; ++i) {
+        if (!lam[i]) continue;
+        float T[3][2], M[3][2], q[6];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 2; ++j) T[r][j] = U3[r][0] * Q[i][0][j] + U3[r][1] * Q[i][1][j] + U3[r][2] * Q[i][2][j];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 2; ++j) M[r][j] = T[r][0] * svd.Vt[0][j] + T[r][1] * svd.Vt[1][j];
+        for (int j = 0; j < 2; ++j) for (int r = 0; r < 3; ++r) q[3 * j + r] = M[r][j];
+        for (int x = 0; x < 6; ++x) for (int y = 0; y < 6; ++y) d2F[x][y] += lam[i] * q[x] * q[y];
+    }
+    const float g[3][2] = {{-ir[0] - ir[1], -ir[2] - ir[3]}, {ir[0], ir[2]}, {ir[1], ir[3]}};
+    for (int a = 0; a < 3; ++a)
+        for (int dim = 0; dim < 3; ++dim) f[a][dim] = mass * (g[a][0] * dedF[dim][0] + g[a][1] * dedF[dim][1]);
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            float blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int dd = 0; dd < 2; ++dd)
+                for (int ee = 0; ee < 2; ++ee) {
+                    const float sc = g[a][dd] * g[b][ee];
+                    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) blk[c * 3 + r] += sc * d2F[3 * dd + r][3 * ee + c];
+                }
+            for (int e = 0; e < 9; ++e) H[a][b][e] = mass * blk[e];
+        }
+}
+
 #endif

@@ -100,3 +100,16 @@ SHIM float orc_collider_toi(const float *y0, const float *y1, int pinned, const 
     *infeasible = 0;
     return o_collider_toi(y0, y1, pinned, spheres, ns, floors, nf, max_t, infeasible);
 }
+
+/* isotropic shell models (ARAP 0 / StVK 1 / SNHk 3) */
+SHIM void orc_iso_table2(int model, const float *a2, float mu, float lmd, float *out5) {
+    float deda[2], d2[3];
+    o_iso_table2(model, a2, mu, lmd, deda, d2);
+    out5[0] = deda[0]; out5[1] = deda[1]; out5[2] = d2[0]; out5[3] = d2[1]; out5[4] = d2[2];
+}
+SHIM void orc_iso_face(const float *x9, const float *ir4, int model, float mu, float lmd, float mass, float eig_eps, float *g9, float *H81) {
+    float f[3][3], H[3][3][9];
+    o_iso_face(x9, x9 + 3, x9 + 6, ir4, model, mu, lmd, mass, eig_eps, f, H);
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) g9[3 * a + k] = f[a][k];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) H81[(3 * b + c) * 9 + 3 * a + r] = H[a][b][c * 3 + r];
+}

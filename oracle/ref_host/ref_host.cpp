@@ -24,6 +24,9 @@ using std::isfinite;
 #include "energy/model/baraffwitkin.hpp"
 #include "energy/model/dihedral_angle.hpp"
 #include "energy/model/hook.hpp"
+#include "energy/model/arap.hpp"
+#include "energy/model/stvk.hpp"
+#include "energy/model/snhk.hpp"
 #include "linalg/eigsolve.hpp"
 
 // storage for the device globals accd.hpp declares extern (contact.cu:30-38)
@@ -161,5 +164,12 @@ void ref_strand(const float *x9, float rest_angle, float *force9, float *hess81)
     dihedral_angle::strand_compute_force_hessian(v3(x9), v3(x9 + 3), v3(x9 + 6), rest_angle, f, H);
     for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) force9[c * 3 + r] = f(r, c);
     for (int c = 0; c < 9; ++c) for (int r = 0; r < 9; ++r) hess81[c * 9 + r] = H(r, c);
+}
+// isotropic shell models: table of derivatives w.r.t. the two singular values; model 0 ARAP, 1 StVK, 3 SNHk
+// out5 = deda[0], deda[1], d2(0,0), d2(0,1), d2(1,1)
+void ref_iso_table2(int model, const float *a2, float mu, float lmd, float *out5) {
+    Vec2f a(a2[0], a2[1]);
+    DiffTable2 t = model == 0 ? ARAP::make_diff_table2(a, mu, lmd) : (model == 1 ? StVK::make_diff_table2(a, mu, lmd) : SNHk::make_diff_table2(a, mu, lmd));
+    out5[0] = t.deda[0]; out5[1] = t.deda[1]; out5[2] = t.d2ed2a(0, 0); out5[3] = t.d2ed2a(0, 1); out5[4] = t.d2ed2a(1, 1);
 }
 }

@@ -140,7 +140,8 @@ void upload_dataset(State &s) {
     if (prm.fix_xz != 0.0f) fatal(4, "B200 backend: fix-xz is not implemented");
     for (unsigned i = 0; i < d.param_arrays.face.size; ++i) {
         const PpfFaceParam &fp = d.param_arrays.face.data[i];
-        if (fp.model != PPF_MODEL_BARAFFWITKIN) fatal(4, "B200 backend: only the Baraff-Witkin shell model is implemented");
+        if (fp.model != PPF_MODEL_BARAFFWITKIN && fp.model != PPF_MODEL_ARAP && fp.model != PPF_MODEL_STVK && fp.model != PPF_MODEL_SNHK)
+            fatal(4, "B200 backend: shell model %d is not implemented (Baraff-Witkin, ARAP, StVK and SNHk are)", (int)fp.model);
         if (fp.pressure > 0.0f || fp.deform_damping > 0.0f || fp.bend_damping > 0.0f)
             fatal(4, "B200 backend: inflation pressure / Rayleigh damping are not implemented");
     }
@@ -182,6 +183,7 @@ void upload_dataset(State &s) {
         std::vector<float4> v(nv), e(ne), f(nf), fm(nf), ir(nf), hm(nh);
         std::vector<float2> fs(nf);
         s.has_strainlimit = false;
+        s.has_iso_faces = false;
         std::vector<float> va(nv), hs(nh);
         std::vector<unsigned char> vc(nv), fsk(nf);
         for (unsigned i = 0; i < nv; ++i) {
@@ -201,7 +203,8 @@ void upload_dataset(State &s) {
             const PpfFaceProp &p = d.prop.face.data[i];
             const PpfFaceParam &fp = d.param_arrays.face.data[p.param_index];
             f[i] = make_float4(fp.ghat, fp.offset, fp.friction, p.mass);
-            fm[i] = make_float4(fp.mu, fp.lambda, p.mass, 0.0f);
+            fm[i] = make_float4(fp.mu, fp.lambda, p.mass, (float)(int)fp.model);
+            if (fp.model != PPF_MODEL_BARAFFWITKIN) s.has_iso_faces = true;
             // strainlimiting.cu:63-64: the limit is relaxed by the smallest shrink factor
             fs[i] = make_float2(fp.strainlimit, fp.strainlimit > 0.0f ? (fp.strainlimit + 1.0f) / fminf(fp.shrink_x, fp.shrink_y) - 1.0f : 0.0f);
             if (fp.strainlimit > 0.0f && !(p.rest_excluded || p.collider)) s.has_strainlimit = true;

@@ -114,7 +114,8 @@ struct State {
     DBuf<float> varea;                            // vertex area
     DBuf<unsigned> fix_index, pull_index;         // per vertex (1-based, 0 = none)
     DBuf<unsigned char> vfixed, efixed, ffixed, hfixed, vcollider, fskip;
-    DBuf<float4> fmat;                            // per face (mu, lambda, mass, deform_damping)
+    DBuf<float4> fmat;                            // per face (mu, lambda, mass, model as a float: the ABI's Model enum)
+    bool has_iso_faces = false;                   // some face uses an SVD-based model (ARAP / StVK / SNHk)
     DBuf<float2> fstrain;                         // per face (strain-limit parameter, shrink-adjusted limit); 0 = off
     bool has_strainlimit = false;
     bool has_offsets = false;                     // some vertex / edge / face parameter set carries a contact offset

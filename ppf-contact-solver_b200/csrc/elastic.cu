@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) k_face(unsigned nf, const uint4 *__restri
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nf || ffixed[i] || fskip[i]) return;
     const float4 m = fmat[i];
-    if (!(m.x > 0.0f)) return;
+    if (!(m.x > 0.0f) || (int)m.w != (int)PPF_MODEL_BARAFFWITKIN) return; // the SVD-based models run in k_face_iso
     const uint4 f = face[i];
     const float4 ir = inv_rest[i];
     const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
@@ -107,6 +107,28 @@ __global__ void __launch_bounds__(128) k_face(unsigned nf, const uint4 *__restri
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) atomic_add_block(val, sl[a * 3 + b], fe.H[a][b].m);
+}
+
+// shell faces with an SVD-based model: ARAP / StVK / SNHk (energy.cu:337-352; math_strain.cuh iso_face)
+__global__ void __launch_bounds__(128) k_face_iso(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ eval_x,
+                                                  const float4 *__restrict__ fmat, const float4 *__restrict__ inv_rest,
+                                                  const unsigned char *__restrict__ ffixed, const unsigned char *__restrict__ fskip,
+                                                  const unsigned *__restrict__ slots, float eig_eps, float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || ffixed[i] || fskip[i]) return;
+    const float4 m = fmat[i];
+    const int model = (int)m.w;
+    if (!(m.x > 0.0f) || model == (int)PPF_MODEL_BARAFFWITKIN) return;
+    const uint4 f = face[i];
+    const float4 ir = inv_rest[i];
+    const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+    StrainFace sf;
+    iso_face(ld3(eval_x, f.x), ld3(eval_x, f.y), ld3(eval_x, f.z), irv, model, m.x, m.y, m.z, eig_eps, sf);
+    const unsigned vi[3] = {f.x, f.y, f.z};
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], sf.f[a]);
+    const unsigned *sl = slots + size_t(9) * i;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) atomic_add_block(val, sl[a * 3 + b], sf.H[a][b].m);
 }
 
 __global__ void __launch_bounds__(128) k_hinge(unsigned nh, const uint4 *__restrict__ hinge, const float4 *__restrict__ eval_x,
@@ -380,7 +402,7 @@ void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
 }
 
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm) {
-    (void)dt; (void)prm;
+    (void)dt;
     if (s.nrodbend) k_rod_bend<<<div_up(s.nrodbend, 128), 128, 0, s.stream>>>(s.nrodbend, s.rb_elem.p, s.rb_par.p, s.eval_x.p, s.fix_index.p,
                                                                              s.rb_slots.p, s.force.p, s.fx_val.p);
     if (s.nrod) k_rod<<<div_up(s.nrod, 128), 128, 0, s.stream>>>(s.nrod, s.edge.p, s.eval_x.p, s.rod_par.p, s.efixed.p, s.rod_slots.p,
@@ -388,6 +410,11 @@ void assemble_elastic(State &s, float dt, const PpfParamSet &prm) {
     if (s.nrod) LAUNCH_COUNT(2);
     if (s.nf) k_face<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.fmat.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
                                                              s.face_slots.p, s.force.p, s.fx_val.p);
+    if (s.nf && s.has_iso_faces) {
+        k_face_iso<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.fmat.p, s.inv_rest.p, s.ffixed.p, s.fskip.p, s.face_slots.p,
+                                                            prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
     if (s.nh) k_hinge<<<div_up(s.nh, 128), 128, 0, s.stream>>>(s.nh, s.hinge.p, s.eval_x.p, s.hmat.p, s.hinge_stiff.p, s.hfixed.p,
                                                               s.hinge_slots.p, s.force.p, s.fx_val.p);
     LAUNCH_COUNT(2);

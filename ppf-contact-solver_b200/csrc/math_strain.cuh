@@ -231,4 +231,101 @@ PPF_HD bool strain_face(const V3 *xe, const V3 *xc, const float *ir, float strai
     return true;
 }
 
+// ---- isotropic shell models (energy.cu:337-352): ARAP / StVK / SNHk as functions of the two singular values ----
+// table of first / second derivatives w.r.t. the singular values: energy/model/arap.hpp:36-49, stvk.hpp:38-72 with
+// detsqr.hpp:22-33, snhk.hpp:45-56.  model: the ABI's Model enum (0 ARAP, 1 StVK, 3 SNHk).  d2 = (d00, d01, d11).
+PPF_HD void iso_table2(int model, const float a[2], float mu, float lmd, float deda[2], float d2[3]) {
+    if (model == 0) { // ARAP
+        const float trace_strain = (a[0] - 1.0f) + (a[1] - 1.0f);
+        deda[0] = 2.0f * mu * (a[0] - 1.0f) + lmd * trace_strain * 1.0f;
+        deda[1] = 2.0f * mu * (a[1] - 1.0f) + lmd * trace_strain * 1.0f;
+        d2[0] = 2.0f * mu * 1.0f + lmd;
+        d2[2] = 2.0f * mu * 1.0f + lmd;
+        d2[1] = 2.0f * mu * 0.0f + lmd;
+    } else if (model == 1) { // StVK: mu/4 sum (a_i - 1)^4 + lmd/2 (a0 a1 - 1)^2
+        const float a0 = a[0] - 1.0f, a1 = a[1] - 1.0f;
+        const float J = a[0] * a[1];
+        deda[0] = mu * (a0 * a0 * a0) + lmd * a[1] * (J - 1.0f);
+        deda[1] = mu * (a1 * a1 * a1) + lmd * a[0] * (J - 1.0f);
+        d2[0] = mu * (3.0f * a0 * a0) + lmd * (a[1] * a[1]);
+        d2[2] = mu * (3.0f * a1 * a1) + lmd * (a[0] * a[0]);
+        d2[1] = mu * 0.0f + lmd * (2.0f * a[0] * a[1] - 1.0f);
+    } else { // SNHk
+        const float x = a[0], y = a[1];
+        deda[0] = lmd * y * (x * y - 1.0f) + mu * (x - y);
+        deda[1] = lmd * x * (x * y - 1.0f) + mu * (y - x);
+        d2[0] = lmd * y * y + mu;
+        d2[2] = lmd * x * x + mu;
+        d2[1] = 2.0f * lmd * x * y - lmd - mu;
+    }
+}
+// One face of embed_face_force_hessian for the SVD-based models: force U diag(deda) V^T and the eigen-projected Hessian
+// (eigenanalysis.cu:14-85) chained to the vertices and scaled by the face mass.
+PPF_HD void iso_face(const V3 &x0, const V3 &x1, const V3 &x2, const float *ir, int model, float mu, float lmd, float mass, float eig_eps,
+                     StrainFace &out) {
+    float F[3][2];
+    deformation_grad32(x0, x1, x2, ir, F);
+    Svd32 svd;
+    jacobi_svd32(F, svd);
+    float deda[2], d2[3];
+    iso_table2(model, svd.S, mu, lmd, deda, d2);
+    float dedF[3][2];
+    for (int r = 0; r < 3; ++r)
+        for (int j = 0; j < 2; ++j) dedF[r][j] = (svd.U[r][0] * deda[0]) * svd.Vt[0][j] + (svd.U[r][1] * deda[1]) * svd.Vt[1][j];
+    float ev[2], evec[2][2];
+    symm2x2(d2[0], d2[1], d2[2], ev, evec);
+    const float inv_sqrt2 = 0.7071067811865475f;
+    float U3[3][3];
+    for (int r = 0; r < 3; ++r) { U3[r][0] = svd.U[r][0]; U3[r][1] = svd.U[r][1]; }
+    U3[0][2] = svd.U[1][0] * svd.U[2][1] - svd.U[2][0] * svd.U[1][1];
+    U3[1][2] = svd.U[2][0] * svd.U[0][1] - svd.U[0][0] * svd.U[2][1];
+    U3[2][2] = svd.U[0][0] * svd.U[1][1] - svd.U[1][0] * svd.U[0][1];
+    float Q[6][3][2];
+    for (int i = 0; i < 6; ++i) for (int r = 0; r < 3; ++r) Q[i][r][0] = Q[i][r][1] = 0.0f;
+    Q[0][0][1] = inv_sqrt2; Q[0][1][0] = -inv_sqrt2;
+    Q[1][0][1] = inv_sqrt2; Q[1][1][0] = inv_sqrt2;
+    Q[2][2][0] = 1.0f;
+    Q[3][2][1] = 1.0f;
+    for (int i = 0; i < 2; ++i) { Q[4][i][i] = evec[i][0]; Q[5][i][i] = evec[i][1]; }
+    const float a0 = svd.S[0], a1 = svd.S[1], denom = a0 - a1;
+    float lambda[6];
+    lambda[0] = fmaxf(0.0f, (deda[0] + deda[1]) / (a0 + a1));
+    lambda[1] = fmaxf(0.0f, fabsf(denom) > eig_eps ? (deda[0] - deda[1]) / denom : 0.5f * (d2[0] + d2[2]) - 0.5f * (d2[1] + d2[1]));
+    lambda[2] = fmaxf(0.0f, deda[0] / a0);
+    lambda[3] = fmaxf(0.0f, deda[1] / a1);
+    lambda[4] = fmaxf(0.0f, ev[0]);
+    lambda[5] = fmaxf(0.0f, ev[1]);
+    float d2F[6][6];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) d2F[i][j] = 0.0f;
+    for (int i = 0; i < 6; ++i) {
+        if (!lambda[i]) continue;
+        float T[3][2], M[3][2];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 2; ++j) T[r][j] = U3[r][0] * Q[i][0][j] + U3[r][1] * Q[i][1][j] + U3[r][2] * Q[i][2][j];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 2; ++j) M[r][j] = T[r][0] * svd.Vt[0][j] + T[r][1] * svd.Vt[1][j];
+        float q[6];
+        for (int j = 0; j < 2; ++j) for (int r = 0; r < 3; ++r) q[3 * j + r] = M[r][j];
+        for (int x = 0; x < 6; ++x) for (int y = 0; y < 6; ++y) d2F[x][y] += lambda[i] * q[x] * q[y];
+    }
+    const float irr[2][2] = {{ir[0], ir[2]}, {ir[1], ir[3]}};
+    const float g[3][2] = {{-irr[0][0] - irr[1][0], -irr[0][1] - irr[1][1]}, {irr[0][0], irr[0][1]}, {irr[1][0], irr[1][1]}};
+    for (int a = 0; a < 3; ++a) {
+        float v[3];
+        for (int dim = 0; dim < 3; ++dim) v[dim] = g[a][0] * dedF[dim][0] + g[a][1] * dedF[dim][1];
+        out.f[a] = mass * mk(v[0], v[1], v[2]);
+    }
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            M3 blk = m3_zero();
+            for (int dd = 0; dd < 2; ++dd)
+                for (int ee = 0; ee < 2; ++ee) {
+                    const float sc = g[a][dd] * g[b][ee];
+                    for (int c = 0; c < 3; ++c)
+                        for (int r = 0; r < 3; ++r) blk.m[c * 3 + r] += sc * d2F[3 * dd + r][3 * ee + c];
+                }
+            for (int e = 0; e < 9; ++e) out.H[a][b].m[e] = mass * blk.m[e];
+        }
+}
+
 } // namespace ppf

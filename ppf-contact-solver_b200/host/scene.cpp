@@ -594,12 +594,15 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.dt = 1e-2;
         return s;
     }
-    if (name == "sheet") { // free-hanging sheet without strain limit: elastic-only smoke scene
+    if (name == "sheet" || name == "sheet-arap" || name == "sheet-stvk" || name == "sheet-snhk") { // free-hanging sheet without strain limit: elastic-only smoke scene (the suffix selects the shell model)
         SceneSpec s;
         s.name = name;
         ShellObject o;
         gen_square(n ? n : 32, 2.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
         o.param = tri_defaults();
+        if (name == "sheet-arap") o.param["model"] = 0.0;
+        if (name == "sheet-stvk") o.param["model"] = 1.0;
+        if (name == "sheet-snhk") o.param["model"] = 3.0;
         Pin p;
         auto a = grab(o.vert, Vec3d{-1, 0, -1}), b = grab(o.vert, Vec3d{1, 0, -1});
         p.index = a;

@@ -121,6 +121,15 @@ def main():
     for i in range(len(sx)):
         ref.ref_strand(fp(sx[i]), C.c_float(srest[i]), fp(sf[i]), fp(sh[i]))
     out.update(strand_x=sx, strand_rest=srest, strand_f=sf, strand_H=sh)
+    # ---- isotropic shell models ARAP / StVK / SNHk: derivative tables w.r.t. the singular values (arap.hpp, stvk.hpp, snhk.hpp) ----
+    nt = 600
+    ta = rng.uniform(0.5, 1.6, size=(nt, 2)).astype(np.float32)
+    tmodel = rng.choice([0, 1, 3], size=nt).astype(np.int32)
+    tmu = rng.uniform(0.5, 500.0, nt).astype(np.float32); tl = rng.uniform(0.5, 800.0, nt).astype(np.float32)
+    tt = np.zeros((nt, 5), np.float32)
+    for i in range(nt):
+        ref.ref_iso_table2(C.c_int(int(tmodel[i])), fp(ta[i]), C.c_float(tmu[i]), C.c_float(tl[i]), fp(tt[i]))
+    out.update(iso_a=ta, iso_model=tmodel, iso_mu=tmu, iso_lmd=tl, iso_table=tt)
     path = os.path.join(REPO, "tests", "golden", "leaf_math.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

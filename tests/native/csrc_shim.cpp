@@ -143,3 +143,16 @@ SHIM float orc_collider_toi(const float *y0, const float *y1, int pinned, const 
     *infeasible = bad ? 1 : 0;
     return t;
 }
+
+// isotropic shell models (ARAP 0 / StVK 1 / SNHk 3): derivative table and one face (force 3x3, Hessian 9x9 column-major)
+SHIM void orc_iso_table2(int model, const float *a2, float mu, float lmd, float *out5) {
+    float deda[2], d2[3];
+    iso_table2(model, a2, mu, lmd, deda, d2);
+    out5[0] = deda[0]; out5[1] = deda[1]; out5[2] = d2[0]; out5[3] = d2[1]; out5[4] = d2[2];
+}
+SHIM void orc_iso_face(const float *x9, const float *ir4, int model, float mu, float lmd, float mass, float eig_eps, float *g9, float *H81) {
+    StrainFace sf;
+    iso_face(v(x9), v(x9 + 3), v(x9 + 6), ir4, model, mu, lmd, mass, eig_eps, sf);
+    for (int a = 0; a < 3; ++a) { g9[3 * a] = sf.f[a].x; g9[3 * a + 1] = sf.f[a].y; g9[3 * a + 2] = sf.f[a].z; }
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) H81[(3 * b + c) * 9 + 3 * a + r] = sf.H[a][b].m[c * 3 + r];
+}

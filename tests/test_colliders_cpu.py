@@ -177,3 +177,24 @@ def test_oracle_lifts_a_sheet_with_a_kinematic_sphere(run_job):
     c = np.array([0.1, -0.9 + 0.7 * t, 0.2])
     assert np.linalg.norm(x - c, axis=1).min() > 0.5 - 2e-3           # a penalty, not a hard constraint: at most a fraction of the gap inside
     assert x[:, 1].max() > 0.2                                          # the sheet has been lifted above its pinned corners
+
+
+def test_isotropic_shell_face_oracle_equals_backend_header(libs):
+    """ARAP / StVK / SNHk shell faces: the oracle's plain C and the backend's header perform the same fp32 operations"""
+    o, b = libs
+    rng = np.random.default_rng(17)
+    for _ in range(300):
+        rest = rng.uniform(-1, 1, size=(3, 2)) * 0.05
+        Dm = np.stack([rest[1] - rest[0], rest[2] - rest[0]], axis=1)
+        if abs(np.linalg.det(Dm)) < 1e-5:
+            continue
+        ir = np.linalg.inv(Dm)
+        ir32 = np.array([ir[0, 0], ir[1, 0], ir[0, 1], ir[1, 1]], np.float32)
+        x = (rng.uniform(-1, 1, size=(3, 3)) * 0.05).astype(np.float32)
+        model = int(rng.choice([0, 1, 3]))
+        out = []
+        for l in (o, b):
+            g9 = np.zeros(9, np.float32); H81 = np.zeros(81, np.float32)
+            l.orc_iso_face(fp(x), fp(ir32), C.c_int(model), C.c_float(30.0), C.c_float(20.0), C.c_float(0.01), C.c_float(1e-2), fp(g9), fp(H81))
+            out.append((g9, H81))
+        assert same_bits(out[0][0], out[1][0]).all() and same_bits(out[0][1], out[1][1]).all()

@@ -199,3 +199,17 @@ def test_oracle_steps_reduced_example_scenes(run_job):
     assert bool(o["ok"].all()) and o["log_num_contact"].max() > 50
     o = run_job({"lib": "oracle", "scene": "large-five-twist", "n": 24, "state": None, "steps": 8})
     assert bool(o["ok"].all()) and o["log_num_contact"].max() > 500
+
+
+def test_oracle_steps_sheets_with_the_svd_based_shell_models(run_job):
+    """ARAP / StVK / SNHk shells (energy.cu:337-352) on a sheet hanging from two corners: each model steps and sags differently"""
+    res = {}
+    for m in ("sheet", "sheet-arap", "sheet-stvk", "sheet-snhk"):
+        o = run_job({"lib": "oracle", "scene": m, "n": 16, "state": None, "steps": 20})
+        assert bool(o["ok"].all()) and np.isfinite(o["curr"]).all()
+        res[m] = o["curr"]
+        assert o["curr"][:, 1].min() < -0.05                       # gravity pulled the free part down
+    for a in res:
+        for b in res:
+            if a < b:
+                assert float(np.abs(res[a] - res[b]).max()) > 1e-5  # four different constitutive models

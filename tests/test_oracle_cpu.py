@@ -296,6 +296,66 @@ def _strain_case(rng, stretch):
     return x, ir32
 
 
+def test_isotropic_shell_model_tables_bit_exact(orc, gold):
+    """ARAP / StVK / SNHk derivative tables w.r.t. the two singular values (arap.hpp:36-49, stvk.hpp:66-72 + detsqr.hpp:22-33,
+    snhk.hpp:45-56), bit for bit against the reference's headers"""
+    a, model = gold["iso_a"], gold["iso_model"]
+    t = np.zeros((len(a), 5), np.float32)
+    for i in range(len(a)):
+        orc.orc_iso_table2(C.c_int(int(model[i])), fp(a[i]), C.c_float(gold["iso_mu"][i]), C.c_float(gold["iso_lmd"][i]), fp(t[i]))
+    assert same_bits(t, gold["iso_table"]).all()
+    assert set(model.tolist()) == {0, 1, 3}
+
+
+def _iso_energy(model, S, mu, lmd):
+    a, b = S
+    if model == 0:
+        return mu * ((a - 1) ** 2 + (b - 1) ** 2) + 0.5 * lmd * (a + b - 2) ** 2
+    if model == 1:
+        return mu * ((a - 1) ** 4 + (b - 1) ** 4) / 4.0 + 0.5 * lmd * (a * b - 1) ** 2
+    return 0.5 * mu * (a * a + b * b - 2.0) - mu * (a * b - 1.0) + 0.5 * lmd * (a * b - 1.0) ** 2
+
+
+@pytest.mark.parametrize("model", [0, 1, 3])
+def test_isotropic_shell_face_is_the_energy_gradient_and_hessian(orc, model):
+    """embed_face_force_hessian for the SVD-based models (energy.cu:337-352): force = mass x dE/dx of the model's energy of
+    the singular values; where every eigen-mode is convex (a stretched face) the projected Hessian is the exact one."""
+    rng = np.random.default_rng(21 + model)
+    mu, lmd, mass = 3.0, 2.0, 0.7
+    worst_g = worst_h = 0.0
+    for _ in range(60):
+        x, ir32 = _strain_case(rng, (rng.uniform(1.05, 1.3), rng.uniform(1.05, 1.3)))
+        ir = np.array([[ir32[0], ir32[2]], [ir32[1], ir32[3]]], np.float64)
+
+        def energy(y):
+            Ds = np.stack([y[1] - y[0], y[2] - y[0]], axis=1)
+            S = np.linalg.svd(Ds @ ir, compute_uv=False)
+            return mass * _iso_energy(model, S, mu, lmd)
+        x64 = x.astype(np.float64)
+        num = np.zeros(9); numH = np.zeros((9, 9))
+        h = 1e-5
+
+        def grad(y):
+            g = np.zeros(9)
+            for k in range(9):
+                d = np.zeros(9); d[k] = h
+                g[k] = (energy(y + d.reshape(3, 3)) - energy(y - d.reshape(3, 3))) / (2 * h)
+            return g
+        num = grad(x64)
+        for k in range(9):
+            d = np.zeros(9); d[k] = 1e-4
+            numH[:, k] = (grad(x64 + d.reshape(3, 3)) - grad(x64 - d.reshape(3, 3))) / 2e-4
+        g9 = np.zeros(9, np.float32); H81 = np.zeros(81, np.float32)
+        orc.orc_iso_face(fp(x), fp(ir32), C.c_int(model), C.c_float(mu), C.c_float(lmd), C.c_float(mass), C.c_float(1e-2), fp(g9), fp(H81))
+        worst_g = max(worst_g, np.abs(g9 - num).max() / max(np.abs(num).max(), 1e-9))
+        H = H81.reshape(9, 9).T.astype(np.float64)
+        assert np.linalg.eigvalsh(0.5 * (H + H.T)).min() > -1e-3 * np.abs(H).max()       # PSD by construction
+        if np.linalg.eigvalsh(0.5 * (numH + numH.T)).min() > -1e-6 * np.abs(numH).max():     # exact Hessian already PSD: nothing was projected away
+            worst_h = max(worst_h, np.abs(H - numH).max() / np.abs(numH).max())
+    assert worst_g < 2e-3, worst_g
+    assert worst_h < 2e-2, worst_h
+
+
 def test_strain_limit_svd_and_gradient(orc):
     """Jacobi SVD reconstructs F; the strain-limit force is the gradient of the barrier energy on the
     singular values (checked against float64 finite differences of numpy's SVD); the Hessian is symmetric PSD."""
