@@ -41,6 +41,12 @@ case "$1" in
   woven-only) gen woven_n32 woven 32 120 60 00060 00120 ;;
   woven-sl-only) gen woven_sl_n32 woven-sl 32 160 80 00080 00160 ;;
   drape-only) gen drape_n32 drape 32 140 70 00070 00140 ;;
+  next-round) # cases that have no reference golden yet (features added after the GPU budget of round 1 was spent)
+     gen headless_ref_n24 headless 24 68 68 00068
+     gen lift_n24 lift 24 40 40 00040
+     gen sheet_arap_n24 sheet-arap 24 20 20 00020
+     gen sheet_stvk_n24 sheet-stvk 24 20 20 00020
+     gen sheet_snhk_n24 sheet-snhk 24 20 20 00020 ;;
   *) gen fast_twist_n16 fast-twist 16 90 30 00030 00060 00090
      gen fast_twist_n24 fast-twist 24 80 40 00040 00080
      gen five_twist_n24 five-twist 24 100 50 00050 00100
