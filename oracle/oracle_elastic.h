@@ -677,4 +677,32 @@ static inline void o_iso_face(const float *x0, const float *x1, const float *x2,
         }
 }
 
+/* ---- stiffness-proportional (Rayleigh) damping of one element: energy.cu:88-180 ----
+ * K: dense (3n)x(3n) column-major element Hessian, u: x - x^n per vertex, f: element gradient.  s = beta / dt.
+ * plain form: f += s K u, K *= (1 + s);  lagged form (bending): f += s K_lag u, K += s K_lag */
+static inline void o_damping_gradient(int n, const float *K, const float (*u)[3], float s, float (*f)[3]) {
+    for (int a = 0; a < n; ++a) {
+        float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+        for (int b = 0; b < 3 * n; ++b) {
+            const float ub = u[b / 3][b % 3];
+            f0 += K[b * 3 * n + 3 * a + 0] * ub;
+            f1 += K[b * 3 * n + 3 * a + 1] * ub;
+            f2 += K[b * 3 * n + 3 * a + 2] * ub;
+        }
+        f[a][0] += s * f0; f[a][1] += s * f1; f[a][2] += s * f2;
+    }
+}
+static inline void o_stiffness_damping(int n, float *K, const float (*u)[3], float beta, float dt, float (*f)[3]) {
+    if (beta <= 0.0f || dt <= 0.0f) return;
+    const float s = beta / dt;
+    o_damping_gradient(n, K, u, s, f);
+    for (int i = 0; i < 9 * n * n; ++i) K[i] *= (1.0f + s);
+}
+static inline void o_stiffness_damping_lagged(int n, float *K, const float *K_lag, const float (*u)[3], float beta, float dt, float (*f)[3]) {
+    if (beta <= 0.0f || dt <= 0.0f) return;
+    const float s = beta / dt;
+    o_damping_gradient(n, K_lag, u, s, f);
+    for (int i = 0; i < 9 * n * n; ++i) K[i] += s * K_lag[i];
+}
+
 #endif

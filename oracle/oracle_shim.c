@@ -113,3 +113,12 @@ SHIM void orc_iso_face(const float *x9, const float *ir4, int model, float mu, f
     for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) g9[3 * a + k] = f[a][k];
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) H81[(3 * b + c) * 9 + 3 * a + r] = H[a][b][c * 3 + r];
 }
+
+/* Rayleigh damping of one element (n = 2, 3 or 4 vertices) */
+SHIM void orc_damping(int n, float *K, const float *K_lag, const float *u, float beta, float dt, float *f, int lagged) {
+    float uu[4][3], ff[4][3];
+    for (int a = 0; a < n; ++a) for (int k = 0; k < 3; ++k) { uu[a][k] = u[3 * a + k]; ff[a][k] = f[3 * a + k]; }
+    if (lagged) o_stiffness_damping_lagged(n, K, K_lag, uu, beta, dt, ff);
+    else o_stiffness_damping(n, K, uu, beta, dt, ff);
+    for (int a = 0; a < n; ++a) for (int k = 0; k < 3; ++k) f[3 * a + k] = ff[a][k];
+}

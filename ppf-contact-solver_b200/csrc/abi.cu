@@ -122,8 +122,7 @@ void upload_dataset(State &s) {
     if (d.rod_count > ne) fatal(4, "rod_count %u exceeds the edge count %u", d.rod_count, ne);
     for (unsigned i = 0; i < d.rod_count; ++i) {
         const PpfEdgeParam &ep = d.param_arrays.edge.data[d.prop.edge.data[i].param_index];
-        if (ep.deform_damping > 0.0f || ep.bend_damping > 0.0f || ep.plasticity > 0.0f)
-            fatal(4, "B200 backend: rod Rayleigh damping / bend plasticity are not implemented");
+        if (ep.plasticity > 0.0f) fatal(4, "B200 backend: rod bend plasticity is not implemented");
     }
     if (d.rod_count && (d.edge_hess_slots.size < 4u * d.rod_count || d.rod_bend_hess_slots.size != 9u * d.surface_vert_count))
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
@@ -142,8 +141,8 @@ void upload_dataset(State &s) {
         const PpfFaceParam &fp = d.param_arrays.face.data[i];
         if (fp.model != PPF_MODEL_BARAFFWITKIN && fp.model != PPF_MODEL_ARAP && fp.model != PPF_MODEL_STVK && fp.model != PPF_MODEL_SNHK)
             fatal(4, "B200 backend: shell model %d is not implemented (Baraff-Witkin, ARAP, StVK and SNHk are)", (int)fp.model);
-        if (fp.pressure > 0.0f || fp.deform_damping > 0.0f || fp.bend_damping > 0.0f)
-            fatal(4, "B200 backend: inflation pressure / Rayleigh damping are not implemented");
+        if (fp.pressure > 0.0f) fatal(4, "B200 backend: inflation pressure is not implemented");
+        if (fp.plasticity > 0.0f || fp.bend_plasticity > 0.0f) fatal(4, "B200 backend: shell plasticity is not implemented");
     }
     if (d.face_hess_slots.size != 9u * nf || d.hinge_hess_slots.size != 16u * nh)
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
@@ -231,6 +230,14 @@ void upload_dataset(State &s) {
             hs[i] = k;
             hm[i] = make_float4(p.length, p.area, p.rest_angle, bend_dir);
         }
+        {
+            std::vector<float> fd(nf), hd(nh);
+            s.has_fdamp = s.has_hdamp = false;
+            for (unsigned i = 0; i < nf; ++i) { fd[i] = d.param_arrays.face.data[d.prop.face.data[i].param_index].deform_damping; s.has_fdamp = s.has_fdamp || fd[i] > 0.0f; }
+            for (unsigned i = 0; i < nh; ++i) { hd[i] = d.param_arrays.hinge.data[d.prop.hinge.data[i].param_index].bend_damping; s.has_hdamp = s.has_hdamp || hd[i] > 0.0f; }
+            s.fdamp.upload(fd.data(), nf, q); s.hdamp.upload(hd.data(), nh, q);
+            CUDA_OK(cudaStreamSynchronize(q));
+        }
         s.vcp.upload(v.data(), nv, q); s.ecp.upload(e.data(), ne, q); s.fcp.upload(f.data(), nf, q);
         s.fmat.upload(fm.data(), nf, q); s.inv_rest.upload(ir.data(), nf, q); s.hmat.upload(hm.data(), nh, q);
         s.fstrain.upload(fs.data(), nf, q);
@@ -269,6 +276,7 @@ void upload_dataset(State &s) {
         std::vector<uint4> el;
         std::vector<float2> par;
         std::vector<unsigned> sl;
+        std::vector<float> rbd;
         for (unsigned i = 0; i < s.nsv; ++i) {
             if (i >= vedge.size || vedge.offset[i + 1] - vedge.offset[i] != 2) continue;
             if (i < vface.size && vface.offset[i + 1] != vface.offset[i]) continue;
@@ -278,15 +286,25 @@ void upload_dataset(State &s) {
             const float mass = d.prop.vertex.data[i].mass;
             const float k = rod_bend_coefficient(q0.bend, q1.bend, p0.length, p1.length, mass);
             if (!(mass > 0.0f && k > 0.0f)) continue;
-            if (q0.bend_damping > 0.0f || q1.bend_damping > 0.0f) fatal(4, "B200 backend: rod bending damping is not implemented");
             const PpfVec2u &c0 = d.mesh.mesh.edge.data[e0], &c1 = d.mesh.mesh.edge.data[e1];
             const unsigned j = c0.v[0] == i ? c0.v[1] : c0.v[0], kk = c1.v[0] == i ? c1.v[1] : c1.v[0];
             el.push_back(make_uint4(j, i, kk, 0u));
             par.push_back(make_float2(k, d.prop.vertex.data[i].rest_bend_angle));
+            rbd.push_back(0.5f * (q0.bend_damping + q1.bend_damping)); // energy.cu:570-571
             for (int b = 0; b < 9; ++b) sl.push_back(d.rod_bend_hess_slots.data[size_t(9) * i + b]);
         }
         s.nrodbend = (unsigned)el.size();
         s.rb_elem.upload(el.data(), el.size(), q); s.rb_par.upload(par.data(), par.size(), q); s.rb_slots.upload(sl.data(), sl.size(), q);
+        s.rb_damp.upload(rbd.data(), rbd.size(), q);
+        s.has_rb_damp = false;
+        for (float v : rbd) s.has_rb_damp = s.has_rb_damp || v > 0.0f;
+        std::vector<float> rdm(s.nrod);
+        s.has_rod_damp = false;
+        for (unsigned i = 0; i < s.nrod; ++i) {
+            rdm[i] = d.param_arrays.edge.data[d.prop.edge.data[i].param_index].deform_damping;
+            s.has_rod_damp = s.has_rod_damp || rdm[i] > 0.0f;
+        }
+        s.rod_damp.upload(rdm.data(), s.nrod, q);
         CUDA_OK(cudaStreamSynchronize(q));
     }
     s.fix_index.reserve(nv); s.pull_index.reserve(nv);

@@ -116,6 +116,9 @@ struct State {
     DBuf<unsigned char> vfixed, efixed, ffixed, hfixed, vcollider, fskip;
     DBuf<float4> fmat;                            // per face (mu, lambda, mass, model as a float: the ABI's Model enum)
     bool has_iso_faces = false;                   // some face uses an SVD-based model (ARAP / StVK / SNHk)
+    // Rayleigh damping coefficients (seconds), 0 = none: faces / rods use deform_damping, hinges / rod bending bend_damping
+    DBuf<float> fdamp, hdamp, rod_damp, rb_damp;
+    bool has_fdamp = false, has_hdamp = false, has_rod_damp = false, has_rb_damp = false;
     DBuf<float2> fstrain;                         // per face (strain-limit parameter, shrink-adjusted limit); 0 = off
     bool has_strainlimit = false;
     bool has_offsets = false;                     // some vertex / edge / face parameter set carries a contact offset
@@ -198,6 +201,7 @@ void step_advance(State &s, PpfStepResult *result);          // step.cu
 // elastic.cu
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm);
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
+void assemble_damping(State &s, float dt, const PpfParamSet &prm);                             // Rayleigh damping, part of "asm elastic"
 void assemble_strainlimit(State &s, const PpfParamSet &prm);                                  // after the elastic snapshot
 float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // fraction in (0, 1]
 float rod_strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // same for rod edges

@@ -9,6 +9,7 @@
 // (csrmat.cu:586-594), lower-triangle sentinels skipped.
 #include "backend.hpp"
 #include "math_elastic.cuh"
+#include "math_damping.cuh"
 #include "math_hinge.cuh"
 #include "math_rod.cuh"
 #include "math_strain.cuh"
@@ -286,6 +287,159 @@ __global__ void __launch_bounds__(128) k_strain_toi(unsigned nf, const uint4 *__
     }
     for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
     if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
+}
+
+// ---- Rayleigh damping (energy.cu:88-180; math_damping.cuh) ----
+// The element kernels above stay as they are; these kernels add only the damping DELTA of the damped elements:
+//   membrane / rod stretch:  gradient += s K u,      Hessian += s K       (the reference scales K by (1 + s) in place)
+//   hinge / rod bending:     gradient += s K_lag u,  Hessian += s K_lag   (K_lag = element Hessian at the start-of-step positions)
+// with s = beta / dt and u = eval_x - curr.
+__global__ void __launch_bounds__(128) k_damp_face(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ eval_x,
+                                                   const float4 *__restrict__ curr, const float4 *__restrict__ fmat,
+                                                   const float4 *__restrict__ inv_rest, const float *__restrict__ fdamp,
+                                                   const unsigned char *__restrict__ ffixed, const unsigned char *__restrict__ fskip,
+                                                   const unsigned *__restrict__ slots, float dt, float eig_eps, float *__restrict__ force,
+                                                   float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || ffixed[i] || fskip[i]) return;
+    const float beta = fdamp[i];
+    const float4 m = fmat[i];
+    if (!(beta > 0.0f) || !(m.x > 0.0f)) return;
+    const uint4 f = face[i];
+    const unsigned vi[3] = {f.x, f.y, f.z};
+    const float4 ir = inv_rest[i];
+    const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+    float K[81];
+    if ((int)m.w == (int)PPF_MODEL_BARAFFWITKIN) {
+        FaceElastic fe;
+        bw_face(ld3(eval_x, f.x), ld3(eval_x, f.y), ld3(eval_x, f.z), irv, m.x, m.y, m.z, fe);
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) K[(3 * b + c) * 9 + 3 * a + r] = fe.H[a][b].m[c * 3 + r];
+    } else {
+        StrainFace sf;
+        iso_face(ld3(eval_x, f.x), ld3(eval_x, f.y), ld3(eval_x, f.z), irv, (int)m.w, m.x, m.y, m.z, eig_eps, sf);
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) K[(3 * b + c) * 9 + 3 * a + r] = sf.H[a][b].m[c * 3 + r];
+    }
+    V3 u[3], df[3];
+    for (int a = 0; a < 3; ++a) { u[a] = ld3(eval_x, vi[a]) - ld3(curr, vi[a]); df[a] = mk(0.f, 0.f, 0.f); }
+    const float s = beta / dt;
+    damping_gradient<3>(K, u, s, df);
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], df[a]);
+    const unsigned *sl = slots + size_t(9) * i;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            if (sl[a * 3 + b] == 0xFFFFFFFFu) continue;
+            float blk[9];
+            for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) blk[c * 3 + r] = s * K[(3 * b + c) * 9 + 3 * a + r];
+            atomic_add_block(val, sl[a * 3 + b], blk);
+        }
+}
+__global__ void __launch_bounds__(128) k_damp_rod(unsigned nrod, const uint2 *__restrict__ edge, const float4 *__restrict__ eval_x,
+                                                  const float4 *__restrict__ curr, const float2 *__restrict__ rod_par,
+                                                  const float *__restrict__ rod_damp, const unsigned char *__restrict__ efixed,
+                                                  const unsigned *__restrict__ slots, float dt, float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrod || efixed[i]) return;
+    const float beta = rod_damp[i];
+    const float2 par = rod_par[i];
+    if (!(beta > 0.0f) || !(par.y > 0.0f)) return;
+    const uint2 e = edge[i];
+    RodElastic re;
+    rod_hook(ld3(eval_x, e.x), ld3(eval_x, e.y), par.x, par.y, re);
+    float K[36];
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r)
+        K[(3 * b + c) * 6 + 3 * a + r] = (a == b ? 1.0f : -1.0f) * re.K.m[c * 3 + r];
+    const V3 u[2] = {ld3(eval_x, e.x) - ld3(curr, e.x), ld3(eval_x, e.y) - ld3(curr, e.y)};
+    V3 df[2] = {mk(0.f, 0.f, 0.f), mk(0.f, 0.f, 0.f)};
+    const float s = beta / dt;
+    damping_gradient<2>(K, u, s, df);
+    atomic_add3(force + size_t(3) * e.x, df[0]);
+    atomic_add3(force + size_t(3) * e.y, df[1]);
+    float pos[9], neg[9];
+    for (int k = 0; k < 9; ++k) { pos[k] = s * re.K.m[k]; neg[k] = -pos[k]; }
+    const unsigned *sl = slots + size_t(4) * i;
+    atomic_add_block(val, sl[0], pos);
+    atomic_add_block(val, sl[1], neg);
+    atomic_add_block(val, sl[2], neg);
+    atomic_add_block(val, sl[3], pos);
+}
+__global__ void __launch_bounds__(128) k_damp_hinge(unsigned nh, const uint4 *__restrict__ hinge, const float4 *__restrict__ eval_x,
+                                                    const float4 *__restrict__ curr, const float4 *__restrict__ hmat,
+                                                    const float *__restrict__ stiff, const float *__restrict__ hdamp,
+                                                    const unsigned char *__restrict__ hfixed, const unsigned *__restrict__ slots, float dt,
+                                                    float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nh || hfixed[i]) return;
+    const float beta = hdamp[i], k = stiff[i];
+    if (!(beta > 0.0f) || !(k > 0.0f)) return;
+    const uint4 h = hinge[i];
+    const unsigned vi[4] = {h.z, h.y, h.x, h.w};
+    V3 X[4], u[4], df[4];
+    for (int a = 0; a < 4; ++a) { X[a] = ld3(curr, vi[a]); u[a] = ld3(eval_x, vi[a]) - X[a]; df[a] = mk(0.f, 0.f, 0.f); }
+    HingeElastic he; // at the START-OF-STEP positions: K_lag
+    hinge_force_hessian(X, hmat[i].z, he);
+    const float s = beta / dt;
+    damping_gradient<4>(he.H, u, s * k, df); // K_lag = k * H
+    for (int a = 0; a < 4; ++a) atomic_add3(force + size_t(3) * vi[a], df[a]);
+    const unsigned *sl = slots + size_t(16) * i;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) {
+            if (sl[a * 4 + b] == 0xFFFFFFFFu) continue;
+            float blk[9];
+            for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) blk[c * 3 + r] = s * (k * he.H[(3 * b + c) * 12 + (3 * a + r)]);
+            atomic_add_block(val, sl[a * 4 + b], blk);
+        }
+}
+__global__ void __launch_bounds__(128) k_damp_rod_bend(unsigned n, const uint4 *__restrict__ elem, const float2 *__restrict__ par,
+                                                       const float *__restrict__ rb_damp, const float4 *__restrict__ eval_x,
+                                                       const float4 *__restrict__ curr, const unsigned *__restrict__ fix_index,
+                                                       const unsigned *__restrict__ slots, float dt, float *__restrict__ force,
+                                                       float *__restrict__ val) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4 el = elem[t];
+    const float beta = rb_damp[t];
+    if (fix_index[el.y] != 0 || !(beta > 0.0f)) return;
+    const float2 pr = par[t];
+    const unsigned vi[3] = {el.x, el.y, el.z};
+    V3 X[3], u[3], df[3];
+    for (int a = 0; a < 3; ++a) { X[a] = ld3(curr, vi[a]); u[a] = ld3(eval_x, vi[a]) - X[a]; df[a] = mk(0.f, 0.f, 0.f); }
+    StrandElastic se; // K_lag
+    strand_force_hessian(X[0], X[1], X[2], pr.y, se);
+    const float s = beta / dt;
+    damping_gradient<3>(se.H, u, s * pr.x, df);
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], df[a]);
+    const unsigned *sl = slots + size_t(9) * t;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            if (sl[a * 3 + b] == 0xFFFFFFFFu) continue;
+            float blk[9];
+            for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) blk[c * 3 + r] = s * (pr.x * se.H[(3 * b + c) * 9 + (3 * a + r)]);
+            atomic_add_block(val, sl[a * 3 + b], blk);
+        }
+}
+
+void assemble_damping(State &s, float dt, const PpfParamSet &prm) {
+    if (!(dt > 0.0f)) return;
+    cudaStream_t q = s.stream;
+    if (s.has_fdamp && s.nf) {
+        k_damp_face<<<div_up(s.nf, 128), 128, 0, q>>>(s.nf, s.face.p, s.eval_x.p, s.curr.p, s.fmat.p, s.inv_rest.p, s.fdamp.p, s.ffixed.p, s.fskip.p, s.face_slots.p,
+                                                      dt, prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
+    if (s.has_rod_damp && s.nrod) {
+        k_damp_rod<<<div_up(s.nrod, 128), 128, 0, q>>>(s.nrod, s.edge.p, s.eval_x.p, s.curr.p, s.rod_par.p, s.rod_damp.p, s.efixed.p, s.rod_slots.p, dt, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
+    if (s.has_hdamp && s.nh) {
+        k_damp_hinge<<<div_up(s.nh, 128), 128, 0, q>>>(s.nh, s.hinge.p, s.eval_x.p, s.curr.p, s.hmat.p, s.hinge_stiff.p, s.hdamp.p, s.hfixed.p, s.hinge_slots.p, dt,
+                                                       s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
+    if (s.has_rb_damp && s.nrodbend) {
+        k_damp_rod_bend<<<div_up(s.nrodbend, 128), 128, 0, q>>>(s.nrodbend, s.rb_elem.p, s.rb_par.p, s.rb_damp.p, s.eval_x.p, s.curr.p, s.fix_index.p, s.rb_slots.p,
+                                                                dt, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
 }
 
 // ---- rod strain limiting (strainlimiting.cu:122-245; math_rod.cuh) ----

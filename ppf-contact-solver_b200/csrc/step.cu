@@ -223,6 +223,7 @@ void step_advance(State &s, PpfStepResult *out) {
         assemble_momentum(s, dt, prm);
         logging.push("asm elastic");
         assemble_elastic(s, dt, prm);
+        assemble_damping(s, dt, prm);
         logging.pop();
         logging.push("asm copy");
         CUDA_OK(cudaMemcpyAsync(s.fx_el.p, s.fx_val.p, sizeof(float) * 9 * size_t(s.fixed_nnz), cudaMemcpyDeviceToDevice, q));

@@ -165,6 +165,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
         p.friction = get("friction"); p.ghat = get("contact-gap"); p.offset = get("contact-offset");
         p.bend = get("bend"); p.strainlimit = get("strain-limit");
         p.shrink_x = get("shrink-x"); p.shrink_y = get("shrink-y"); p.pressure = get("pressure");
+        p.deform_damping = get("deformation-damping"); p.bend_damping = get("bending-damping");
         PpfFaceProp fp;
         std::memset(&fp, 0, sizeof(fp));
         fp.area = face_area[i];
@@ -279,17 +280,18 @@ void build_scene(const SceneSpec &spec, Built &b) {
     b.hprop.resize(nh);
     for (unsigned i = 0; i < nh; ++i) {
         const PpfVec4u &h = b.hinge[i];
-        float os = 0, gs = 0, bs = 0, as = 0;
+        float os = 0, gs = 0, bs = 0, as = 0, ds = 0;
         bool all_fixed = true;
         for (unsigned j : b.hinge_face[i]) {
             const PpfFaceParam &fp = b.fparam[b.fprop[j].param_index];
             const float ar = b.fprop[j].area;
             all_fixed = all_fixed && b.fprop[j].fixed;
-            os += ar * fp.offset; gs += ar * fp.ghat; bs += ar * fp.bend; as += ar;
+            os += ar * fp.offset; gs += ar * fp.ghat; bs += ar * fp.bend; as += ar; ds += ar * fp.bend_damping;
         }
         PpfHingeParam p;
         std::memset(&p, 0, sizeof(p));
         p.bend = all_fixed ? 0.0f : bs / as;
+        p.bend_damping = all_fixed ? 0.0f : ds / as; // builder.rs:881-920
         p.ghat = gs / as; p.offset = os / as;
         PpfHingeProp hp;
         std::memset(&hp, 0, sizeof(hp));

@@ -4,6 +4,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_accd.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_collider.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_contact.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_damping.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
@@ -155,4 +156,14 @@ SHIM void orc_iso_face(const float *x9, const float *ir4, int model, float mu, f
     iso_face(v(x9), v(x9 + 3), v(x9 + 6), ir4, model, mu, lmd, mass, eig_eps, sf);
     for (int a = 0; a < 3; ++a) { g9[3 * a] = sf.f[a].x; g9[3 * a + 1] = sf.f[a].y; g9[3 * a + 2] = sf.f[a].z; }
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) H81[(3 * b + c) * 9 + 3 * a + r] = sf.H[a][b].m[c * 3 + r];
+}
+
+// Rayleigh damping of one element (n = 2, 3 or 4 vertices): K (3n)^2 column-major in/out, f 3n in/out; lagged != 0 uses K_lag
+SHIM void orc_damping(int n, float *K, const float *K_lag, const float *u, float beta, float dt, float *f, int lagged) {
+    V3 uu[4], ff[4];
+    for (int a = 0; a < n; ++a) { uu[a] = v(u + 3 * a); ff[a] = v(f + 3 * a); }
+    if (n == 2) { if (lagged) stiffness_damping_lagged<2>(K, K_lag, uu, beta, dt, ff); else stiffness_damping<2>(K, uu, beta, dt, ff); }
+    else if (n == 3) { if (lagged) stiffness_damping_lagged<3>(K, K_lag, uu, beta, dt, ff); else stiffness_damping<3>(K, uu, beta, dt, ff); }
+    else { if (lagged) stiffness_damping_lagged<4>(K, K_lag, uu, beta, dt, ff); else stiffness_damping<4>(K, uu, beta, dt, ff); }
+    for (int a = 0; a < n; ++a) { f[3 * a] = ff[a].x; f[3 * a + 1] = ff[a].y; f[3 * a + 2] = ff[a].z; }
 }

@@ -198,3 +198,35 @@ def test_isotropic_shell_face_oracle_equals_backend_header(libs):
             l.orc_iso_face(fp(x), fp(ir32), C.c_int(model), C.c_float(30.0), C.c_float(20.0), C.c_float(0.01), C.c_float(1e-2), fp(g9), fp(H81))
             out.append((g9, H81))
         assert same_bits(out[0][0], out[1][0]).all() and same_bits(out[0][1], out[1][1]).all()
+
+
+def test_rayleigh_damping_oracle_equals_backend_header_and_the_definition(libs):
+    """add_stiffness_damping / add_stiffness_damping_lagged (energy.cu:88-180): gradient += (beta/dt) K u, Hessian *= 1 + beta/dt
+    (lagged: gradient += (beta/dt) K_lag u, Hessian += (beta/dt) K_lag); oracle and backend header bit for bit, both against numpy"""
+    o, b = libs
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 4):
+        for lagged in (0, 1):
+            for _ in range(40):
+                A = rng.normal(size=(3 * n, 3 * n)); K = (A @ A.T).astype(np.float32)
+                B = rng.normal(size=(3 * n, 3 * n)); Kl = (B @ B.T).astype(np.float32)
+                u = (rng.normal(size=3 * n) * 1e-2).astype(np.float32); f = rng.normal(size=3 * n).astype(np.float32)
+                beta, dt = 0.03, 0.01
+                outs = []
+                for l in (o, b):
+                    Kc = np.ascontiguousarray(K.T).reshape(-1).copy(); Klc = np.ascontiguousarray(Kl.T).reshape(-1).copy(); fc = f.copy()
+                    l.orc_damping(C.c_int(n), fp(Kc), fp(Klc), fp(u), C.c_float(beta), C.c_float(dt), fp(fc), C.c_int(lagged))
+                    outs.append((Kc, fc))
+                assert same_bits(outs[0][0], outs[1][0]).all() and same_bits(outs[0][1], outs[1][1]).all()
+                s = np.float64(np.float32(beta)) / np.float64(np.float32(dt))
+                Kout = outs[0][0].reshape(3 * n, 3 * n).T
+                op = Kl if lagged else K
+                assert np.allclose(outs[0][1], f + s * (op.astype(np.float64) @ u), rtol=2e-5, atol=1e-5)
+                want = K + s * Kl if lagged else K * (1 + s)
+                assert np.allclose(Kout, want, rtol=2e-6, atol=2e-5 * float(np.abs(want).max()))
+    # beta = 0 or dt = 0: nothing changes
+    K = np.eye(6, dtype=np.float32).reshape(-1); f = np.ones(6, np.float32); u = np.ones(6, np.float32)
+    for beta, dt in ((0.0, 0.01), (0.1, 0.0)):
+        Kc, fc = K.copy(), f.copy()
+        o.orc_damping(C.c_int(2), fp(Kc), fp(K), fp(u), C.c_float(beta), C.c_float(dt), fp(fc), C.c_int(0))
+        assert np.array_equal(Kc, K) and np.array_equal(fc, f)

@@ -213,3 +213,19 @@ def test_oracle_steps_sheets_with_the_svd_based_shell_models(run_job):
         for b in res:
             if a < b:
                 assert float(np.abs(res[a] - res[b]).max()) > 1e-5  # four different constitutive models
+
+
+def test_oracle_rayleigh_damping_dissipates(run_job):
+    """deformation / bending damping (energy.cu:88-180) on a sheet hanging from two corners and on woven rods: the damped run
+    steps, differs from the undamped one, and carries less internal (non-rigid) motion"""
+    a = run_job({"lib": "oracle", "scene": "sheet", "n": 16, "state": None, "steps": 40})
+    d = run_job({"lib": "oracle", "scene": "sheet-damped", "n": 16, "state": None, "steps": 40})
+    assert bool(a["ok"].all()) and bool(d["ok"].all())
+    assert float(np.abs(a["curr"] - d["curr"]).max()) > 1e-4
+
+    def wobble(r):            # velocity field minus its mean: what membrane / bending damping acts on
+        v = (r["curr"] - r["prev"]).astype(np.float64)
+        return float(np.linalg.norm(v - v.mean(axis=0)))
+    assert wobble(d) < wobble(a)
+    w = run_job({"lib": "oracle", "scene": "woven-damped", "n": 32, "state": None, "steps": 6})
+    assert bool(w["ok"].all()) and w["log_num_contact"].min() > 100

@@ -81,3 +81,28 @@ def test_svd_based_shell_models_match_the_oracle(run_job, scene):
         assert abs(mine - theirs) <= 2 + 0.05 * theirs
     d = np.abs(g["curr"] - o["curr"]).max(axis=1)
     assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))
+
+
+@pytest.mark.parametrize("scene,n", [("sheet-damped", 24), ("sheet-arap-damped", 24), ("woven-damped", 32)])
+def test_rayleigh_damping_matches_the_oracle(run_job, scene, n):
+    """Rayleigh damping of membranes / hinges / rods (k_damp_*: the damped elements' delta on top of the undamped kernels)
+    against the CPU oracle, which applies it in place like the reference (energy.cu:88-180).  The first assembled system
+    already carries the damping: u = x - x^n is still zero there, but every damped element Hessian is scaled by 1 + beta/dt
+    (= 3 for the membranes, 6 for the bending terms of these scenes), which the undamped system does not show."""
+    job = {"scene": scene, "n": n, "state": None, "steps": 3, "dump_linsys": True}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    nb = c["n_blocks"][0]
+    assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
+    assert c["frac_blocks_off"] * nb <= 12 + 0.002 * nb, c
+    base = {"sheet-damped": "sheet", "sheet-arap-damped": "sheet-arap", "woven-damped": "woven"}[scene]
+    u = run_job({"lib": "oracle", "scene": base, "n": n, "state": None, "steps": 1, "dump_linsys": True}, force_subprocess=True)
+    cu = compare(os.path.join(u["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    assert cu["frac_blocks_off"] > 0.5, cu                      # ... and the damping is really on: the undamped matrix is a different one
+    assert len(g["log_iter"]) == len(o["log_iter"])
+    for mine, theirs in zip(g["log_iter"], o["log_iter"]):
+        assert abs(mine - theirs) <= 2 + 0.05 * theirs
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))
