@@ -705,4 +705,36 @@ static inline void o_stiffness_damping_lagged(int n, float *K, const float *K_la
     for (int i = 0; i < 9 * n * n; ++i) K[i] += s * K_lag[i];
 }
 
+/* ---- stitches: seam springs between two barycentric points (energy.cu:796-886) ----
+ * x[6][3]: the six slots (source 0..2, target 3..5), ghat / offset: their vertices' contact gap and offset, w: weights.
+ * f[6][3] gradient, H 18x18 column-major, both scaled by the stitch stiffness. */
+static inline void o_stitch(const float (*x)[3], const float *ghat, const float *offset, const float *w, float stiffness, float length_factor,
+                            float f[6][3], float *H) {
+    const float l0 = (w[0] * ghat[0] + w[1] * ghat[1] + w[2] * ghat[2] + w[3] * ghat[3] + w[4] * ghat[4] + w[5] * ghat[5]) / 2.0f;
+    const float so = fmaxf(fmaxf(offset[0], offset[1]), offset[2]), to = fmaxf(fmaxf(offset[3], offset[4]), offset[5]);
+    const float l_cap = length_factor * l0 + so + to;
+    const float s = 1.0f / 6.0f;
+    float cog[3], z0[3], z1[3], t[3], n[3];
+    for (int k = 0; k < 3; ++k) {
+        cog[k] = s * x[0][k] + s * x[1][k] + s * x[2][k] + s * x[3][k] + s * x[4][k] + s * x[5][k];
+        z0[k] = w[0] * (x[0][k] - cog[k]) + w[1] * (x[1][k] - cog[k]) + w[2] * (x[2][k] - cog[k]);
+        z1[k] = w[3] * (x[3][k] - cog[k]) + w[4] * (x[4][k] - cog[k]) + w[5] * (x[5][k] - cog[k]);
+        t[k] = z0[k] - z1[k];
+    }
+    const float l = fminf(l_cap, o_norm3(t));
+    for (int k = 0; k < 3; ++k) n[k] = t[k] / l;
+    const float sw[6] = {w[0], w[1], w[2], -w[3], -w[4], -w[5]};
+    const float e = l / l0 - 1.0f;
+    float g[18];
+    for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) g[3 * a + k] = sw[a] * n[k];
+    const float r = (l - l0) / l;
+    const float c0 = fmaxf(0.0f, 1.0f - r) / l0, c1 = fmaxf(0.0f, r / l0);
+    for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) f[a][k] = stiffness * (sw[a] * (e * n[k]));
+    for (int j = 0; j < 18; ++j)
+        for (int i = 0; i < 18; ++i) {
+            const float dd = (i % 3 == j % 3) ? (c1 * sw[i / 3]) * sw[j / 3] : 0.0f; /* (c1 dtdx^T) dtdx */
+            H[j * 18 + i] = stiffness * ((c0 * g[i]) * g[j] + dd);
+        }
+}
+
 #endif

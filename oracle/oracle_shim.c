@@ -122,3 +122,11 @@ SHIM void orc_damping(int n, float *K, const float *K_lag, const float *u, float
     else o_stiffness_damping(n, K, uu, beta, dt, ff);
     for (int a = 0; a < n; ++a) for (int k = 0; k < 3; ++k) f[3 * a + k] = ff[a][k];
 }
+
+/* one stitch (six slots) */
+SHIM void orc_stitch(const float *x18, const float *ghat6, const float *offset6, const float *w6, float stiffness, float length_factor, float *f18, float *H324) {
+    float x[6][3], f[6][3];
+    for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) x[a][k] = x18[3 * a + k];
+    o_stitch(x, ghat6, offset6, w6, stiffness, length_factor, f, H324);
+    for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) f18[3 * a + k] = f[a][k];
+}

@@ -80,6 +80,8 @@ void apply_constraint(State &s, const PpfConstraint *c) {
     s.npull = c->pull.size;
     s.fix.upload(c->fix.data, c->fix.size, q);
     s.pull.upload(c->pull.data, c->pull.size, q);
+    s.nstitch = c->stitch.size;
+    s.stitches.upload(c->stitch.data, c->stitch.size, q);
     s.nsphere = c->sphere.size;
     s.nfloor = c->floor.size;
     s.spheres.upload(c->sphere.data, c->sphere.size, q);
@@ -128,8 +130,10 @@ void upload_dataset(State &s) {
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
     if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
     if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
-    if (d.constraint.stitch.size || d.constraint.mesh.vertex.size || d.constraint.torque_vertices.size)
-        fatal(4, "B200 backend: stitches / static collision meshes / torque pins are not implemented");
+    if (d.constraint.mesh.vertex.size || d.constraint.torque_vertices.size)
+        fatal(4, "B200 backend: static collision meshes / torque pins are not implemented");
+    if (d.constraint.stitch.size && d.stitch_hess_slots.size != 36u * d.constraint.stitch.size)
+        fatal(4, "B200 backend: slot-replay tables are required (stitch_hess_slots)");
     if (prm.disable_pin_dof_removal) fatal(4, "B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
     if (d.translation_lock.size) fatal(4, "B200 backend: translation/rotation locks are not implemented");
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
@@ -319,6 +323,8 @@ void upload_dataset(State &s) {
         s.fx_col.upload(t.data, s.fixed_nnz, q);
         s.fx_val.reserve(size_t(9) * s.fixed_nnz); s.fx_el.reserve(size_t(9) * s.fixed_nnz);
         s.face_slots.upload(d.face_hess_slots.data, d.face_hess_slots.size, q);
+        s.nstitch_slots = d.stitch_hess_slots.size;
+        s.stitch_slots.upload(d.stitch_hess_slots.data, d.stitch_hess_slots.size, q);
         s.hinge_slots.upload(d.hinge_hess_slots.data, d.hinge_hess_slots.size, q);
         std::vector<unsigned> ds(nv);
         for (unsigned i = 0; i < nv; ++i) {
@@ -458,8 +464,9 @@ PPF_EXPORT void update_dyn(unsigned *index, unsigned *offset) {
 }
 
 PPF_EXPORT void update_constraint(const PpfConstraint *constraint) {
-    if (constraint->stitch.size || constraint->mesh.vertex.size || constraint->torque_vertices.size)
-        fatal(4, "B200 backend: stitches / static collision meshes / torque pins are not implemented");
+    if (constraint->mesh.vertex.size || constraint->torque_vertices.size)
+        fatal(4, "B200 backend: static collision meshes / torque pins are not implemented");
+    if (36u * constraint->stitch.size > g.nstitch_slots) fatal(4, "update_constraint: %u stitches but slots for %u only", constraint->stitch.size, g.nstitch_slots / 36u);
     apply_constraint(g, constraint);
 }
 PPF_EXPORT void update_rest_shape(const PpfRestShapeUpdate *update) {

@@ -136,6 +136,9 @@ struct State {
     DBuf<unsigned> rb_slots;                      // 9 per bending vertex (DataSet.rod_bend_hess_slots rows of those vertices)
     DBuf<PpfFixPair> fix;
     DBuf<PpfPullPair> pull;
+    DBuf<PpfStitch> stitches;                     // seams of the last update_constraint
+    DBuf<unsigned> stitch_slots;                  // 36 per seam (DataSet.stitch_hess_slots)
+    unsigned nstitch = 0, nstitch_slots = 0;
     DBuf<PpfSphere> spheres;                      // analytic colliders of the last update_constraint
     DBuf<PpfFloor> floors;
     unsigned nsphere = 0, nfloor = 0;
@@ -201,6 +204,7 @@ void step_advance(State &s, PpfStepResult *result);          // step.cu
 // elastic.cu
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm);
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
+void assemble_stitches(State &s, const PpfParamSet &prm);                                     // seam springs, before the elastic snapshot
 void assemble_damping(State &s, float dt, const PpfParamSet &prm);                             // Rayleigh damping, part of "asm elastic"
 void assemble_strainlimit(State &s, const PpfParamSet &prm);                                  // after the elastic snapshot
 float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // fraction in (0, 1]

@@ -12,6 +12,7 @@
 #include "math_damping.cuh"
 #include "math_hinge.cuh"
 #include "math_rod.cuh"
+#include "math_stitch.cuh"
 #include "math_strain.cuh"
 
 namespace ppf {
@@ -287,6 +288,40 @@ __global__ void __launch_bounds__(128) k_strain_toi(unsigned nf, const uint4 *__
     }
     for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
     if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
+}
+
+// ---- stitches (energy.cu:796-886; math_stitch.cuh) ----
+__global__ void __launch_bounds__(64) k_stitch(unsigned n, const PpfStitch *__restrict__ st, const float4 *__restrict__ eval_x,
+                                               const float4 *__restrict__ vcp, const unsigned *__restrict__ slots, float length_factor,
+                                               float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PpfStitch q = st[i];
+    V3 x[6];
+    float ghat[6], offset[6], w[6];
+    for (int a = 0; a < 6; ++a) {
+        const unsigned v = q.index.v[a];
+        x[a] = ld3(eval_x, v);
+        const float4 cp = vcp[v];
+        ghat[a] = cp.x; offset[a] = cp.y; w[a] = q.weight.v[a];
+    }
+    StitchOut o;
+    stitch_force_hessian(x, ghat, offset, w, q.stiffness, length_factor, o);
+    for (int a = 0; a < 6; ++a) atomic_add3(force + size_t(3) * q.index.v[a], o.f[a]);
+    const unsigned *sl = slots + size_t(36) * i;
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) {
+            const unsigned slot = sl[a * 6 + b];
+            if (slot == 0xFFFFFFFFu) continue;
+            float blk[9];
+            for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) blk[c * 3 + r] = o.H[(3 * b + c) * 18 + (3 * a + r)];
+            atomic_add_block(val, slot, blk);
+        }
+}
+void assemble_stitches(State &s, const PpfParamSet &prm) {
+    if (!s.nstitch) return;
+    k_stitch<<<div_up(s.nstitch, 64), 64, 0, s.stream>>>(s.nstitch, s.stitches.p, s.eval_x.p, s.vcp.p, s.stitch_slots.p, prm.stitch_length_factor, s.force.p, s.fx_val.p);
+    LAUNCH_COUNT(1);
 }
 
 // ---- Rayleigh damping (energy.cu:88-180; math_damping.cuh) ----

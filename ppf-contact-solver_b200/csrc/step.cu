@@ -225,6 +225,7 @@ void step_advance(State &s, PpfStepResult *out) {
         assemble_elastic(s, dt, prm);
         assemble_damping(s, dt, prm);
         logging.pop();
+        assemble_stitches(s, prm); // main.cu:793-796: after "asm elastic", before the snapshot
         logging.push("asm copy");
         CUDA_OK(cudaMemcpyAsync(s.fx_el.p, s.fx_val.p, sizeof(float) * 9 * size_t(s.fixed_nnz), cudaMemcpyDeviceToDevice, q));
         logging.pop();

@@ -226,6 +226,16 @@ void build_scene(const SceneSpec &spec, Built &b) {
             }
             b.pins.push_back(std::move(g));
         }
+    for (auto &st : spec.stitches) { // seams in global indices (scene.rs:2200-2212)
+        PpfStitch q;
+        std::memset(&q, 0, sizeof(q));
+        for (int k = 0; k < 3; ++k) {
+            q.index.v[k] = (unsigned)l2g[st.src][st.src_index[k]]; q.weight.v[k] = float(st.src_weight[k]);
+            q.index.v[3 + k] = (unsigned)l2g[st.dst][st.dst_index[k]]; q.weight.v[3 + k] = float(st.dst_weight[k]);
+        }
+        q.stiffness = float(st.stiffness);
+        b.stitch.push_back(q);
+    }
     make_constraint(b, 0.0, 0.0);
 
     // ---- builder.rs:388-432 fixed flags ----
@@ -330,6 +340,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
         for (auto &e : b.edge) for (int p = 0; p < 2; ++p) for (int q = 0; q < 2; ++q) ins(e.v[p], e.v[q]);
         for (auto &f : b.face) for (int p = 0; p < 3; ++p) for (int q = 0; q < 3; ++q) ins(f.v[p], f.v[q]);
         for (auto &h : b.hinge) for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) ins(h.v[p], h.v[q]);
+        for (auto &q : b.stitch) for (int p = 0; p < 6; ++p) for (int r = 0; r < 6; ++r) ins(q.index.v[p], q.index.v[r]); // builder.rs:1315-1321
         for (unsigned i = 0; i < nv; ++i) { // rod-bending stencil (j, i, k): the pair (j, k) is no edge (builder.rs:1289-1313)
             if (b.v_edge[i].size() != 2 || !b.v_face[i].empty()) continue;
             const PpfVec2u &c0 = b.edge[b.v_edge[i][0]], &c1 = b.edge[b.v_edge[i][1]];
@@ -365,6 +376,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
         const unsigned r[4] = {h.v[2], h.v[1], h.v[0], h.v[3]};
         for (int p = 0; p < 4; ++p) for (int q = 0; q < 4; ++q) b.hinge_slots.push_back(slot_of(r[p], r[q]));
     }
+    for (auto &q : b.stitch) for (int p = 0; p < 6; ++p) for (int r = 0; r < 6; ++r) b.stitch_slots.push_back(slot_of(q.index.v[p], q.index.v[r])); // builder.rs:1468-1478
     b.rod_bend_slots.assign(size_t(9) * nv, 0xFFFFFFFFu);
     for (unsigned i = 0; i < nv; ++i) { // builder.rs:1446-1467
         if (b.v_edge[i].size() != 2 || !b.v_face[i].empty()) continue;
@@ -415,6 +427,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
     set_vec(d.grain_A, b.zero9); set_vec(d.grain_B, b.zero9); set_vec(d.grain_grot, b.zero3);
     set_vec(d.face_hess_slots, b.face_slots); set_vec(d.edge_hess_slots, b.edge_slots);
     set_vec(d.hinge_hess_slots, b.hinge_slots); set_vec(d.rod_bend_hess_slots, b.rod_bend_slots);
+    set_vec(d.stitch_hess_slots, b.stitch_slots);
     set_vec(d.translation_lock_index, b.lock_index);
 
     // ---- make_param (builder.rs:1629-1681) ----

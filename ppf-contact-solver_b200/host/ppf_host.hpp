@@ -95,9 +95,18 @@ struct SphereCollider {
     std::vector<Key> keys;
     bool smooth = false;
 };
+// one seam spring between a barycentric point of object `src` and one of object `dst` (local vertex indices; a plain
+// vertex is {v, v, v} with weights {1, 0, 0}); scene.rs stitch_ind / stitch_w / stitch_stiffness
+struct StitchSpec {
+    unsigned src = 0, dst = 0;
+    std::array<unsigned, 3> src_index{0, 0, 0}, dst_index{0, 0, 0};
+    std::array<double, 3> src_weight{1, 0, 0}, dst_weight{1, 0, 0};
+    double stiffness = 1.0; // "stitch-stiffness"
+};
 struct SceneSpec {
     std::string name;
     std::vector<ShellObject> objects;
+    std::vector<StitchSpec> stitches;
     std::vector<WallCollider> walls;
     std::vector<SphereCollider> spheres;
     SimArgs args;
@@ -155,6 +164,7 @@ struct Built {
     // constraint storage (rebuilt every step)
     std::vector<PpfFixPair> fix; std::vector<PpfPullPair> pull;
     std::vector<PpfSphere> sphere; std::vector<PpfFloor> floor;
+    std::vector<PpfStitch> stitch; std::vector<unsigned> stitch_slots;
     PpfDataSet dataset;
     PpfParamSet param;
     PpfConstraint constraint;

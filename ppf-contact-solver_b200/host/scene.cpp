@@ -581,6 +581,37 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.friction_mode = "min";
         return s;
     }
+    if (name == "seam") { // test scene: two sheets side by side joined by a row of stitches; the first hangs from two corners, the second from the seam
+        SceneSpec s;
+        s.name = name;
+        const unsigned res = n ? n : 16;
+        for (int k = 0; k < 2; ++k) {
+            ShellObject o;
+            gen_square(res, 1.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+            o.param = tri_defaults();
+            o.displacement = Vec3d{k == 0 ? -0.51 : 0.51, 0, 0};
+            if (k == 0) {
+                Pin p;
+                auto a = grab(o.vert, Vec3d{-1, 0, -1}), c = grab(o.vert, Vec3d{-1, 0, 1});
+                p.index = a;
+                p.index.insert(p.index.end(), c.begin(), c.end());
+                o.pins.push_back(p);
+            }
+            s.objects.push_back(std::move(o));
+        }
+        for (unsigned j = 0; j < res; ++j) { // gen_square: vertex (i, j) has index i * res + j, x grows with i
+            StitchSpec st;
+            st.src = 0; st.dst = 1;
+            const unsigned a = (res - 1) * res + j, c = j;
+            st.src_index = {a, a, a};
+            if (j + 1 < res && (j % 2)) { st.dst_index = {c, c + 1, c + 1}; st.dst_weight = {0.5, 0.5, 0.0}; } // every other stitch lands on an edge midpoint
+            else st.dst_index = {c, c, c};
+            s.stitches.push_back(st);
+        }
+        s.args.frames = 60;
+        s.args.dt = 1e-2;
+        return s;
+    }
     if (name == "lift") { // test scene: a sheet pinned at two corners, lifted by an invisible sphere that rises from below (kinematic collider)
         SceneSpec s;
         s.name = name;
@@ -766,6 +797,8 @@ void make_constraint(Built &b, double time, double prev_time) {
     }
     PpfConstraint &c = b.constraint;
     c = PpfConstraint{};
+    c.stitch.data = b.stitch.data();
+    c.stitch.size = c.stitch.allocated = (unsigned)b.stitch.size();
     c.floor.data = b.floor.data();
     c.floor.size = c.floor.allocated = (unsigned)b.floor.size();
     c.sphere.data = b.sphere.data();

@@ -9,6 +9,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_rod.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_stitch.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_strain.cuh"
 using namespace ppf;
 #define SHIM extern "C" __attribute__((visibility("default")))
@@ -166,4 +167,14 @@ SHIM void orc_damping(int n, float *K, const float *K_lag, const float *u, float
     else if (n == 3) { if (lagged) stiffness_damping_lagged<3>(K, K_lag, uu, beta, dt, ff); else stiffness_damping<3>(K, uu, beta, dt, ff); }
     else { if (lagged) stiffness_damping_lagged<4>(K, K_lag, uu, beta, dt, ff); else stiffness_damping<4>(K, uu, beta, dt, ff); }
     for (int a = 0; a < n; ++a) { f[3 * a] = ff[a].x; f[3 * a + 1] = ff[a].y; f[3 * a + 2] = ff[a].z; }
+}
+
+// one stitch: x18 = six slot positions, ghat6 / offset6 / w6; outputs gradient 18, Hessian 18x18 column-major
+SHIM void orc_stitch(const float *x18, const float *ghat6, const float *offset6, const float *w6, float stiffness, float length_factor, float *f18, float *H324) {
+    V3 x[6];
+    for (int a = 0; a < 6; ++a) x[a] = v(x18 + 3 * a);
+    StitchOut o;
+    stitch_force_hessian(x, ghat6, offset6, w6, stiffness, length_factor, o);
+    for (int a = 0; a < 6; ++a) { f18[3 * a] = o.f[a].x; f18[3 * a + 1] = o.f[a].y; f18[3 * a + 2] = o.f[a].z; }
+    for (int i = 0; i < 324; ++i) H324[i] = o.H[i];
 }

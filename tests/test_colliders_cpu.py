@@ -230,3 +230,44 @@ def test_rayleigh_damping_oracle_equals_backend_header_and_the_definition(libs):
         Kc, fc = K.copy(), f.copy()
         o.orc_damping(C.c_int(2), fp(Kc), fp(K), fp(u), C.c_float(beta), C.c_float(dt), fp(fc), C.c_int(0))
         assert np.array_equal(Kc, K) and np.array_equal(fc, f)
+
+
+def test_stitch_oracle_equals_backend_header_and_the_spring_energy(libs):
+    """embed_stitch_force_hessian (energy.cu:796-886): oracle and backend header bit for bit; below the length cap the
+    gradient is that of the spring energy (l0 / 2)(l / l0 - 1)^2 of the distance between the two barycentric points; the
+    slot gradients sum to zero (source and target weights both sum to one); the Hessian is symmetric PSD."""
+    o, b = libs
+    rng = np.random.default_rng(12)
+    worst = 0.0
+    for case in range(200):
+        x = rng.uniform(-0.05, 0.05, size=(6, 3)).astype(np.float32)
+        ws = rng.dirichlet([1, 1, 1]); wd = rng.dirichlet([1, 1, 1])
+        if case % 3 == 0:
+            ws = np.array([1.0, 0, 0]); x[1] = x[0]; x[2] = x[0]         # plain vertex as the source: {s, s, s}, {1, 0, 0}
+        w = np.concatenate([ws, wd]).astype(np.float32)
+        ghat = rng.choice([1e-3, 4e-3], size=6).astype(np.float32); off = rng.choice([0.0, 1e-3], size=6).astype(np.float32)
+        lf = 10.0 if case % 2 else 1e6                                    # capped / uncapped
+        outs = []
+        for l in (o, b):
+            f = np.zeros(18, np.float32); H = np.zeros(324, np.float32)
+            l.orc_stitch(fp(x), fp(ghat), fp(off), fp(w), C.c_float(2.5), C.c_float(lf), fp(f), fp(H))
+            outs.append((f, H))
+        assert same_bits(outs[0][0], outs[1][0]).all() and same_bits(outs[0][1], outs[1][1]).all()
+        f, H = outs[0]
+        assert np.abs(f.reshape(6, 3).sum(axis=0)).max() <= 2e-5 * max(np.abs(f).max(), 1e-9)
+        Hm = H.reshape(18, 18).T.astype(np.float64)
+        assert np.abs(Hm - Hm.T).max() <= 1e-6 * max(np.abs(Hm).max(), 1e-12)
+        assert np.linalg.eigvalsh(0.5 * (Hm + Hm.T)).min() >= -1e-5 * np.abs(Hm).max()
+        if lf > 1e5:
+            l0 = float((w.astype(np.float64) * ghat).sum() / 2.0)
+
+            def energy(y):
+                t = (w[:3, None] * y[:3]).sum(axis=0) - (w[3:, None] * y[3:]).sum(axis=0)
+                return 2.5 * 0.5 * l0 * (np.linalg.norm(t) / l0 - 1.0) ** 2
+            x64 = x.astype(np.float64)
+            num = np.zeros(18)
+            for k in range(18):
+                d = np.zeros(18); d[k] = 1e-7
+                num[k] = (energy(x64 + d.reshape(6, 3)) - energy(x64 - d.reshape(6, 3))) / 2e-7
+            worst = max(worst, np.abs(f - num).max() / max(np.abs(num).max(), 1e-9))
+    assert worst < 2e-3, worst

@@ -229,3 +229,15 @@ def test_oracle_rayleigh_damping_dissipates(run_job):
     assert wobble(d) < wobble(a)
     w = run_job({"lib": "oracle", "scene": "woven-damped", "n": 32, "state": None, "steps": 6})
     assert bool(w["ok"].all()) and w["log_num_contact"].min() > 100
+
+
+def test_oracle_sews_two_sheets_with_stitches(run_job):
+    """`seam`: a sheet hanging from two corners carries a second sheet through a row of stitches (energy.cu:796-886), every
+    other stitch landing on an edge midpoint of the second sheet (barycentric target)"""
+    o = run_job({"lib": "oracle", "scene": "seam", "n": 12, "state": None, "steps": 50})
+    assert bool(o["ok"].all()) and np.isfinite(o["curr"]).all()
+    x = o["curr"].astype(np.float64)
+    A, B = x[:144], x[144:]
+    near = np.sort(np.linalg.norm(A[:, None, :] - B[None, :, :], axis=2).min(axis=0))[:12]
+    assert near.max() < 0.05                      # the twelve seam vertices of the second sheet stay sewn to the first
+    assert B[:, 1].min() < A[:, 1].min() - 0.2    # and it hangs below
