@@ -50,9 +50,17 @@ static inline float dot(const Vec3f &a, const Vec3f &b) { return a[0] * b[0] + a
 static inline float norm(const Vec3f &a) { return std::sqrt(dot(a, a)); }
 
 template <class P> static unsigned dedup(std::vector<P> &store, const P &p) { // builder.rs:1749-1759 (first occurrence keeps its index)
-    static std::map<const void *, std::map<std::string, unsigned>> index_of; // per store: bytes -> index
+    if (store.size() <= 16) { // the common case (a handful of distinct parameter sets): linear scan, no allocation
+        for (unsigned i = 0; i < store.size(); ++i)
+            if (std::memcmp(&store[i], &p, sizeof(P)) == 0) return i;
+    } else if (std::memcmp(&store.back(), &p, sizeof(P)) == 0)
+        return (unsigned)store.size() - 1;
+    static std::map<const void *, std::map<std::string, unsigned>> index_of; // per store: bytes -> index (large stores)
     auto &m = index_of[&store];
-    if (store.empty()) m.clear();
+    if (m.size() != store.size()) { // first use on this store, or the store was filled through the linear path / reset
+        m.clear();
+        for (unsigned i = 0; i < store.size(); ++i) m.emplace(std::string(reinterpret_cast<const char *>(&store[i]), sizeof(P)), i);
+    }
     const std::string key(reinterpret_cast<const char *>(&p), sizeof(P));
     auto it = m.find(key);
     if (it != m.end()) return it->second;
@@ -153,8 +161,12 @@ void build_scene(const SceneSpec &spec, Built &b) {
         if (!(face_area[i] > 0.0f)) throw std::runtime_error("degenerate face");
     }
     b.fprop.resize(nf);
-    for (unsigned i = 0; i < nf; ++i) {
-        const auto &pm = spec.objects[face_object[i]].param;
+    // the parameter set is per object: resolve the string-keyed map once per object, not once per face
+    std::vector<PpfFaceParam> obj_fparam(spec.objects.size());
+    std::vector<float> obj_density(spec.objects.size(), 0.0f);
+    for (size_t o = 0; o < spec.objects.size(); ++o) {
+        if (spec.objects[o].tri.empty()) continue;
+        const auto &pm = spec.objects[o].param;
         auto get = [&](const char *k) { return float(pm.at(k)); };
         PpfFaceParam p;
         std::memset(&p, 0, sizeof(p));
@@ -166,17 +178,24 @@ void build_scene(const SceneSpec &spec, Built &b) {
         p.bend = get("bend"); p.strainlimit = get("strain-limit");
         p.shrink_x = get("shrink-x"); p.shrink_y = get("shrink-y"); p.pressure = get("pressure");
         p.deform_damping = get("deformation-damping"); p.bend_damping = get("bending-damping");
+        obj_fparam[o] = p;
+        obj_density[o] = get("density");
+    }
+    for (unsigned i = 0; i < nf; ++i) {
         PpfFaceProp fp;
         std::memset(&fp, 0, sizeof(fp));
         fp.area = face_area[i];
-        fp.mass = get("density") * face_area[i];
-        fp.param_index = dedup(b.fparam, p);
+        fp.mass = obj_density[face_object[i]] * face_area[i];
+        fp.param_index = dedup(b.fparam, obj_fparam[face_object[i]]);
         b.fprop[i] = fp;
     }
     // ---- non-rod edge props (main.rs:225-258, builder.rs:1800-1821) ----
     b.eprop.resize(ne);
-    for (unsigned i = 0; i < nrod; ++i) { // rod edges (scene.rs:1542-1648)
-        const auto &pm = spec.objects[rod_object[i]].rod_param;
+    std::vector<PpfEdgeParam> obj_eparam(spec.objects.size());
+    std::vector<float> obj_rod_density(spec.objects.size(), 0.0f), obj_length_factor(spec.objects.size(), 1.0f);
+    for (size_t o = 0; o < spec.objects.size(); ++o) { // rod parameters, once per object (scene.rs:1542-1648)
+        if (spec.objects[o].rod.empty()) continue;
+        const auto &pm = spec.objects[o].rod_param;
         auto get = [&](const char *k) { return float(pm.at(k)); };
         PpfEdgeParam p;
         std::memset(&p, 0, sizeof(p));
@@ -186,13 +205,19 @@ void build_scene(const SceneSpec &spec, Built &b) {
         p.bend_rest_from_geometry = get("bend-rest-from-geometry") != 0.0f;
         p.deform_damping = get("deformation-damping"); p.bend_damping = get("bending-damping");
         if (!(get("density") > 0.0f) || !(p.stiffness > 0.0f) || !(p.ghat > 0.0f)) throw std::runtime_error("rod density / young-mod / contact-gap must be positive");
+        obj_eparam[o] = p;
+        obj_rod_density[o] = get("density");
+        obj_length_factor[o] = get("length-factor");
+    }
+    for (unsigned i = 0; i < nrod; ++i) { // rod edges
+        const PpfEdgeParam &p = obj_eparam[rod_object[i]];
         PpfEdgeProp ep;
         std::memset(&ep, 0, sizeof(ep));
         float length = norm(sub(b.vert[b.edge[i].v[1]], b.vert[b.edge[i].v[0]]));
         if (!(length > 0.0f)) throw std::runtime_error("degenerate rod edge");
         ep.initial_length = length;
-        ep.mass = get("density") * length;
-        length *= get("length-factor");
+        ep.mass = obj_rod_density[rod_object[i]] * length;
+        length *= obj_length_factor[rod_object[i]];
         ep.length = length;
         ep.param_index = dedup(b.eparam, p);
         b.eprop[i] = ep;
