@@ -13,6 +13,7 @@
 namespace ppf {
 State g;
 unsigned long long g_launches = 0;
+unsigned long long g_dev_alloc = 0, g_dev_free = 0;
 }
 using namespace ppf;
 
@@ -240,6 +241,9 @@ void upload_dataset(State &s) {
             for (unsigned i = 0; i < nf; ++i) { fd[i] = d.param_arrays.face.data[d.prop.face.data[i].param_index].deform_damping; s.has_fdamp = s.has_fdamp || fd[i] > 0.0f; }
             for (unsigned i = 0; i < nh; ++i) { hd[i] = d.param_arrays.hinge.data[d.prop.hinge.data[i].param_index].bend_damping; s.has_hdamp = s.has_hdamp || hd[i] > 0.0f; }
             s.fdamp.upload(fd.data(), nf, q); s.hdamp.upload(hd.data(), nh, q);
+            std::vector<float> fsh(nf);
+            for (unsigned i = 0; i < nf; ++i) { const PpfFaceParam &fp = d.param_arrays.face.data[d.prop.face.data[i].param_index]; fsh[i] = d.prop.face.data[i].collider ? 0.0f : fminf(fp.shrink_x, fp.shrink_y); }
+            s.fshrink.upload(fsh.data(), nf, q);
             CUDA_OK(cudaStreamSynchronize(q));
         }
         s.vcp.upload(v.data(), nv, q); s.ecp.upload(e.data(), ne, q); s.fcp.upload(f.data(), nf, q);

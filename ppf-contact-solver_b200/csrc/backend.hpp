@@ -33,6 +33,7 @@ void log_info(const char *fmt, ...);
     } while (0)
 
 extern unsigned long long g_launches; // kernels launched by this backend (PpfB200Stats.n_kernel_launches)
+extern unsigned long long g_dev_alloc, g_dev_free; // cudaMalloc / cudaFree calls of the grow-only buffers ("device-alloc" / "device-free" channels)
 #define LAUNCH_COUNT(n) (::ppf::g_launches += (n))
 
 inline unsigned div_up(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
@@ -43,9 +44,10 @@ template <class T> struct DBuf {
     size_t cap = 0;
     void reserve(size_t n) {
         if (n > cap) {
-            if (p) CUDA_OK(cudaFree(p));
+            if (p) { CUDA_OK(cudaFree(p)); ++g_dev_free; }
             size_t want = n + n / 4 + 16;
             CUDA_OK(cudaMalloc(&p, want * sizeof(T)));
+            ++g_dev_alloc;
             cap = want;
         }
     }
@@ -54,10 +56,12 @@ template <class T> struct DBuf {
             size_t want = n + n / 2 + 16;
             T *q = nullptr;
             CUDA_OK(cudaMalloc(&q, want * sizeof(T)));
+            ++g_dev_alloc;
             if (p) {
                 CUDA_OK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
                 CUDA_OK(cudaStreamSynchronize(s));
                 CUDA_OK(cudaFree(p));
+                ++g_dev_free;
             }
             p = q;
             cap = want;
@@ -120,6 +124,7 @@ struct State {
     DBuf<float> fdamp, hdamp, rod_damp, rb_damp;
     bool has_fdamp = false, has_hdamp = false, has_rod_damp = false, has_rb_damp = false;
     DBuf<float2> fstrain;                         // per face (strain-limit parameter, shrink-adjusted limit); 0 = off
+    DBuf<float> fshrink;                          // per face min(shrink_x, shrink_y) (max_sigma diagnostic)
     bool has_strainlimit = false;
     bool has_offsets = false;                     // some vertex / edge / face parameter set carries a contact offset
     DBuf<float4> inv_rest;                        // per face 2x2
@@ -207,6 +212,7 @@ void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
 void assemble_stitches(State &s, const PpfParamSet &prm);                                     // seam springs, before the elastic snapshot
 void assemble_damping(State &s, float dt, const PpfParamSet &prm);                             // Rayleigh damping, part of "asm elastic"
 void assemble_strainlimit(State &s, const PpfParamSet &prm);                                  // after the elastic snapshot
+float max_stretch_ratio(State &s);                                                            // "max_sigma" channel (main.cu:424-488)
 float strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // fraction in (0, 1]
 float rod_strain_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm); // same for rod edges
 void recompute_fixed_flags(State &s);

@@ -575,6 +575,55 @@ float strain_line_search(State &s, const float4 *x0, const float4 *x1, const Ppf
     return t / max_t;
 }
 
+// ---- "max_sigma": largest stretch ratio at the start of the step (main.cu:424-488) ----
+// shells: largest singular value of the deformation gradient x min(shrink_x, shrink_y); rods: length / drawn length
+__global__ void __launch_bounds__(128) k_face_sigma(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ curr,
+                                                    const float4 *__restrict__ inv_rest, const float *__restrict__ fshrink,
+                                                    const unsigned char *__restrict__ ffixed, float *__restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    float v = 0.0f;
+    const float shrink = fshrink[i]; // 0 for collider faces: they carry no elastic energy (main.cu:446-449)
+    if (!ffixed[i] && shrink > 0.0f) {
+        const uint4 f = face[i];
+        const float4 ir = inv_rest[i];
+        const float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+        float F[3][2];
+        deformation_grad32(ld3(curr, f.x), ld3(curr, f.y), ld3(curr, f.z), irv, F);
+        Svd32 svd;
+        jacobi_svd32(F, svd);
+        v = fmaxf(svd.S[0], svd.S[1]) * shrink;
+    }
+    out[i] = v;
+}
+__global__ void __launch_bounds__(128) k_rod_sigma(unsigned nrod, const uint2 *__restrict__ edge, const float4 *__restrict__ curr,
+                                                   const float2 *__restrict__ rod_sl, const unsigned char *__restrict__ efixed, float *__restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrod) return;
+    float v = 0.0f;
+    const float l0 = rod_sl[i].y; // drawn length
+    if (!efixed[i] && l0 > 0.0f) {
+        const uint2 e = edge[i];
+        v = norm(ld3(curr, e.y) - ld3(curr, e.x)) / l0;
+    }
+    out[i] = v;
+}
+float max_stretch_ratio(State &s) {
+    float *tmp = reinterpret_cast<float *>(s.velocity.p); // 4 floats per vertex of scratch
+    float m = 0.0f;
+    if (s.nf && size_t(s.nf) <= size_t(4) * s.nv) {
+        k_face_sigma<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.curr.p, s.inv_rest.p, s.fshrink.p, s.ffixed.p, tmp);
+        LAUNCH_COUNT(1);
+        m = fmaxf(m, reduce_max_f(s, tmp, s.nf, 0.0f));
+    }
+    if (s.nrod && size_t(s.nrod) <= size_t(4) * s.nv) {
+        k_rod_sigma<<<div_up(s.nrod, 128), 128, 0, s.stream>>>(s.nrod, s.edge.p, s.curr.p, s.rod_sl.p, s.efixed.p, tmp);
+        LAUNCH_COUNT(1);
+        m = fmaxf(m, reduce_max_f(s, tmp, s.nrod, 0.0f));
+    }
+    return m;
+}
+
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
     MomentumArgs a;
     a.dt = dt; a.air_density = prm.air_density; a.air_friction = prm.air_friction; a.iso_air = prm.isotropic_air_friction;

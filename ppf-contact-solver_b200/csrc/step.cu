@@ -177,6 +177,8 @@ void step_advance(State &s, PpfStepResult *out) {
     float dt = s.param->dt * s.param->playback;
     logging.mark("dt", dt);
     logging.mark("playback", s.param->playback);
+    if (s.nf || s.nrod) logging.mark("max_sigma", max_stretch_ratio(s)); // main.cu:424-488
+    const unsigned long long alloc0 = g_dev_alloc, free0 = g_dev_free;
 
     const float3 gravity = make_float3(prm.gravity.v[0], prm.gravity.v[1], prm.gravity.v[2]);
     auto compute_target = [&](float dtt) {
@@ -263,6 +265,9 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.pop();
         logging.mark("iter", sr.iter);
         logging.mark("reresid", sr.resid);
+        // this backend always solves with block-Jacobi: a request for the Schwarz preconditioner is reported the way the
+        // reference reports its own fallback to block-Jacobi (main.cu:1124, solver.cu:2317)
+        logging.mark("schwarz_fallback", prm.precond == PPF_PRECOND_SCHWARZ ? 1 : 0);
         if (!sr.ok) {
             logging.message("### cg failed");
             result.pcg_success = false;
@@ -320,13 +325,13 @@ void step_advance(State &s, PpfStepResult *out) {
                 return;
             }
         }
-        if (s.has_strainlimit) { // strainlimiting::line_search (main.cu:1321-1335)
-            const float sl_toi = strain_line_search(s, s.x_old.p, s.eval_x.p, prm);
+        if (s.nf) { // strainlimiting::line_search (main.cu:1321-1335); the channel exists for every shell scene
+            const float sl_toi = s.has_strainlimit ? strain_line_search(s, s.x_old.p, s.eval_x.p, prm) : 1.0f;
             toi = fminf(toi, sl_toi);
             logging.mark("SL_toi", sl_toi);
         }
-        if (s.has_rod_strainlimit) { // strainlimiting::rod_line_search (main.cu:1336-1343)
-            const float sl_toi = rod_strain_line_search(s, s.x_old.p, s.eval_x.p, prm);
+        if (s.nrod) { // strainlimiting::rod_line_search (main.cu:1336-1343)
+            const float sl_toi = s.has_rod_strainlimit ? rod_strain_line_search(s, s.x_old.p, s.eval_x.p, prm) : 1.0f;
             toi = fminf(toi, sl_toi);
             logging.mark("SL_rod_toi", sl_toi);
         }
@@ -364,6 +369,9 @@ void step_advance(State &s, PpfStepResult *out) {
     logging.mark("toi_advanced", toi_advanced);
     logging.mark("newton_steps", step);
     logging.mark("final_dt", dt);
+    logging.mark("device-alloc", static_cast<double>(g_dev_alloc - alloc0)); // main.cu:1636-1645
+    logging.mark("device-free", static_cast<double>(g_dev_free - free0));
+    logging.message("* device alloc/free this step: %llu / %llu", g_dev_alloc - alloc0, g_dev_free - free0);
     s.param->prev_dt = dt;
     s.param->time += static_cast<double>(s.param->prev_dt / s.param->playback);
     // prev <- curr, curr <- eval_x
