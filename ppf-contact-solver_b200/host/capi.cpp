@@ -131,6 +131,21 @@ void ppfh_topology(Session *s, unsigned *face, unsigned *edge, float *vparam2) {
             vparam2[2 * i] = vp.ghat; vparam2[2 * i + 1] = vp.offset;
         }
 }
+// pins evaluated at (time, prev_time) like the per-step make_constraint: returns the number of fix pins and fills, per pin,
+// vertex index, target position, the displacement since prev_time (FixPair.step_delta) and the kinematic flag; initial
+// positions of the scene's vertices come with ppfh_initial_positions
+unsigned ppfh_constraint_at(Session *s, double time, double prev_time, unsigned *index, float *pos, float *delta, unsigned char *kinematic) {
+    make_constraint(s->b, time, prev_time);
+    const unsigned n = (unsigned)s->b.fix.size();
+    for (unsigned i = 0; i < n && index; ++i) {
+        index[i] = s->b.fix[i].index;
+        memcpy(pos + 3 * i, s->b.fix[i].position.v, 12);
+        memcpy(delta + 3 * i, s->b.fix[i].step_delta.v, 12);
+        kinematic[i] = s->b.fix[i].kinematic ? 1 : 0;
+    }
+    return n;
+}
+void ppfh_initial_positions(Session *s, float *out) { memcpy(out, s->b.vert.data(), s->b.vert.size() * sizeof(Vec3f)); }
 // rod data of the built scene: returns rod_count; per rod edge (rest length, initial length, mass, stiffness, bend),
 // per vertex (mass, rest bend angle), the 9 rod-bend slots per vertex and the fixed index table (offset[n_vert+1], columns)
 unsigned ppfh_rods(Session *s, float *rod5, float *vert2, unsigned *bend_slots9, unsigned *fixed_offset, unsigned *fixed_col) {

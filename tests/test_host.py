@@ -241,3 +241,87 @@ def test_oracle_sews_two_sheets_with_stitches(run_job):
     near = np.sort(np.linalg.norm(A[:, None, :] - B[None, :, :], axis=2).min(axis=0))[:12]
     assert near.max() < 0.05                      # the twelve seam vertices of the second sheet stay sewn to the first
     assert B[:, 1].min() < A[:, 1].min() - 0.2    # and it hangs below
+
+
+def _pins_at(ppf, scene, n, time, prev_time):
+    import ctypes
+
+    h = ppf.host()
+    h.ppfh_constraint_at.restype = ctypes.c_uint
+    p = ctypes.c_void_p(h.ppfh_create(scene.encode(), ctypes.c_uint(n)))
+    c = (ctypes.c_uint * 6)()
+    h.ppfh_counts(p, c)
+    nv = int(c[0])
+    x0 = np.empty((nv, 3), np.float32)
+    h.ppfh_initial_positions(p, x0.ctypes.data_as(ctypes.c_void_p))
+    vp = ctypes.c_void_p
+    k = int(h.ppfh_constraint_at(p, ctypes.c_double(time), ctypes.c_double(prev_time), None, None, None, None))
+    idx = np.empty(k, np.uint32); pos = np.empty((k, 3), np.float32); dlt = np.empty((k, 3), np.float32); kin = np.empty(k, np.uint8)
+    h.ppfh_constraint_at(p, ctypes.c_double(time), ctypes.c_double(prev_time), idx.ctypes.data_as(vp), pos.ctypes.data_as(vp), dlt.ctypes.data_as(vp), kin.ctypes.data_as(vp))
+    h.ppfh_destroy(p)
+    return x0.astype(np.float64), idx.astype(np.int64), pos.astype(np.float64), dlt.astype(np.float64), kin
+
+
+def test_twist_pin_operations_follow_the_notebook(ppf):
+    """examples/twist.ipynb: each end ring spins about +-x at 360 deg/s, scales to 0.9 over 10 s (about the origin) and moves
+    +-0.2 along x over 10 s, applied in that order (scene.rs:2747-2870, pin_apply.rs:27-160); FixPair.step_delta is the
+    displacement since the previous step's time; a pin that moves is kinematic"""
+    for t, tp in ((0.25, 0.25 - 1 / 60), (3.0, 3.0 - 1 / 60), (12.0, 12.0 - 1 / 60)):
+        x0, idx, pos, dlt, kin = _pins_at(ppf, "twist", 24, t, tp)
+        assert idx.size > 0 and kin.all()
+
+        def where(tt):
+            out = np.empty((idx.size, 3))
+            for k, v in enumerate(idx):
+                p = x0[v]
+                sg = -1.0 if p[0] < 0 else 1.0
+                ang = np.deg2rad(360.0) * tt * (-sg)                  # left ring: axis +x, right ring: axis -x
+                c, s = np.cos(ang), np.sin(ang)
+                q = np.array([p[0], c * p[1] - s * p[2], s * p[1] + c * p[2]])       # rotation about the x axis
+                q = q * (1.0 + (0.9 - 1.0) * min(tt, 10.0) / 10.0)                   # scale about the origin
+                q = q + np.array([-sg * 0.2 * min(tt, 10.0) / 10.0, 0, 0])           # move_by
+                out[k] = q
+            return out
+        want, want_prev = where(t), where(tp)
+        assert np.abs(pos - want).max() < 2e-6, np.abs(pos - want).max()
+        assert np.abs(dlt - (want - want_prev)).max() < 2e-6
+    # at t = 0 nothing has moved yet: targets are the rest positions, and the ring is static for the solver
+    x0, idx, pos, dlt, kin = _pins_at(ppf, "twist", 24, 0.0, 0.0)
+    assert np.abs(pos - x0[idx]).max() < 1e-7 and not dlt.any()
+
+
+def test_static_pins_are_not_kinematic(ppf):
+    x0, idx, pos, dlt, kin = _pins_at(ppf, "hang", 16, 0.7, 0.699)
+    assert idx.size > 0 and not kin.any() and not dlt.any() and np.abs(pos - x0[idx]).max() < 1e-7
+
+
+def test_five_twist_pin_operations_follow_the_notebook(ppf):
+    """examples/five-twist.ipynb: spin (5 s) -> move_by (25 s) -> scale about the ring's own centre (5 s) -> orbit about the common
+    axis (5..15 s), all in the object's local frame, then the object's displacement"""
+    half = 2.6
+    for t in (2.0, 7.0, 20.0):
+        x0, idx, pos, dlt, kin = _pins_at(ppf, "five-twist", 16, t, t - 1 / 60)
+        assert idx.size > 0 and kin.all()
+        # the object of a pinned vertex: recover its displacement from the cylinder axis (rings sit at radius 1 about x)
+        worst = 0.0
+        for k, v in enumerate(idx):
+            g = x0[v]                                                # rest position incl. the object's displacement
+            cands = [np.array([0.0, np.cos(2 * i / 5 * np.pi), np.sin(2 * i / 5 * np.pi)]) for i in range(5)]
+            d = min(cands, key=lambda c: abs(np.linalg.norm(g[1:] - c[1:]) - 0.55))
+            p = g - d                                                # local rest position
+            sg = -1.0 if p[0] < 0 else 1.0
+
+            def rot_x(q, deg, sign, centre):
+                a = np.deg2rad(deg) * sign
+                c, s = np.cos(a), np.sin(a)
+                r = q - centre
+                return np.array([r[0], c * r[1] - s * r[2], s * r[1] + c * r[2]]) + centre
+            q = rot_x(p, 360.0 * min(t, 5.0), -sg, np.zeros(3))
+            q = q + np.array([-sg * 1.0 * min(t, 25.0) / 25.0, 0, 0])
+            f = 1.0 + (0.75 - 1.0) * min(t, 5.0) / 5.0
+            centre = np.array([-d[0] + sg * half, -d[1], -d[2]])
+            q = (q - centre) * f + centre
+            if t > 5.0:
+                q = rot_x(q, 180.0 * (min(t, 15.0) - 5.0), -sg, -d)
+            worst = max(worst, float(np.abs(pos[k] - (q + d)).max()))
+        assert worst < 5e-6, worst
