@@ -146,6 +146,19 @@ unsigned ppfh_constraint_at(Session *s, double time, double prev_time, unsigned 
     return n;
 }
 void ppfh_initial_positions(Session *s, float *out) { memcpy(out, s->b.vert.data(), s->b.vert.size() * sizeof(Vec3f)); }
+// slot-replay tables of the shell elements (builder.rs:1368-1496): 9 per face, 16 per hinge (remapped order h2, h1, h0, h3),
+// plus the hinge quadruples, the fixed index table and, per off-diagonal block, its (row, slot) in the transpose table
+void ppfh_slot_tables(Session *s, unsigned *face_slots, unsigned *hinge_slots, unsigned *hinge4, unsigned *fixed_offset, unsigned *fixed_col,
+                      unsigned *transpose_offset, unsigned *transpose_rowslot) {
+    const Built &b = s->b;
+    if (face_slots) memcpy(face_slots, b.face_slots.data(), b.face_slots.size() * sizeof(unsigned));
+    if (hinge_slots) memcpy(hinge_slots, b.hinge_slots.data(), b.hinge_slots.size() * sizeof(unsigned));
+    if (hinge4) memcpy(hinge4, b.hinge.data(), b.hinge.size() * sizeof(PpfVec4u));
+    if (fixed_offset) memcpy(fixed_offset, b.f_fixed.offset.data(), b.f_fixed.offset.size() * sizeof(unsigned));
+    if (fixed_col) memcpy(fixed_col, b.f_fixed.data.data(), b.f_fixed.data.size() * sizeof(unsigned));
+    if (transpose_offset) memcpy(transpose_offset, b.f_transpose.offset.data(), b.f_transpose.offset.size() * sizeof(unsigned));
+    if (transpose_rowslot) memcpy(transpose_rowslot, b.f_transpose.data.data(), b.f_transpose.data.size() * sizeof(PpfVec2u));
+}
 // rod data of the built scene: returns rod_count; per rod edge (rest length, initial length, mass, stiffness, bend),
 // per vertex (mass, rest bend angle), the 9 rod-bend slots per vertex and the fixed index table (offset[n_vert+1], columns)
 unsigned ppfh_rods(Session *s, float *rod5, float *vert2, unsigned *bend_slots9, unsigned *fixed_offset, unsigned *fixed_col) {

@@ -325,3 +325,58 @@ def test_five_twist_pin_operations_follow_the_notebook(ppf):
                 q = rot_x(q, 180.0 * (min(t, 15.0) - 5.0), -sg, -d)
             worst = max(worst, float(np.abs(pos[k] - (q + d)).max()))
         assert worst < 5e-6, worst
+
+
+def test_shell_slot_and_transpose_tables_address_the_right_blocks(ppf):
+    """builder.rs:1244-1496 for a shell scene: the fixed index table holds the upper triangle of (edges + hinge stencils + diagonal);
+    face / hinge slot tables address block (row min, col max) or carry the lower-triangle sentinel; the transpose table lists,
+    for every column, the (row, slot) of each strictly-upper block in it"""
+    import ctypes
+
+    h = ppf.host()
+    p = ctypes.c_void_p(h.ppfh_create(b"fast-twist", ctypes.c_uint(12)))
+    c = (ctypes.c_uint * 6)()
+    h.ppfh_counts(p, c)
+    nv, nf, ne, nh, nfix, nnz = [int(v) for v in c]
+    vp = ctypes.c_void_p
+    face = np.empty((nf, 3), np.uint32); edge = np.empty((ne, 2), np.uint32)
+    h.ppfh_topology(p, face.ctypes.data_as(vp), edge.ctypes.data_as(vp), None)
+    fs = np.empty((nf, 9), np.uint32); hs = np.empty((nh, 16), np.uint32); hg = np.empty((nh, 4), np.uint32)
+    off = np.empty(nv + 1, np.uint32); col = np.empty(nnz, np.uint32); toff = np.empty(nv + 1, np.uint32); trs = np.empty((nnz - nv, 2), np.uint32)
+    h.ppfh_slot_tables(p, fs.ctypes.data_as(vp), hs.ctypes.data_as(vp), hg.ctypes.data_as(vp), off.ctypes.data_as(vp), col.ctypes.data_as(vp),
+                       toff.ctypes.data_as(vp), trs.ctypes.data_as(vp))
+    h.ppfh_destroy(p)
+    # the pattern: diagonal + edges + the two opposite vertices of every hinge, upper triangle
+    want = {(i, i) for i in range(nv)}
+    for a, b in edge:
+        want.add((min(a, b), max(a, b)))
+    for q in hg:
+        for a in q:
+            for b in q:
+                want.add((min(a, b), max(a, b)))
+    got = {(i, int(col[k])) for i in range(nv) for k in range(off[i], off[i + 1])}
+    assert got == {(int(a), int(b)) for a, b in want}
+    assert off[nv] == nnz and all((np.diff(col[off[i]:off[i + 1]].astype(np.int64)) > 0).all() for i in range(nv))
+
+    def check(slot, a, b):
+        if a > b:
+            assert slot == 0xFFFFFFFF
+        else:
+            assert off[a] <= slot < off[a + 1] and col[slot] == b
+    for i in range(nf):
+        for a in range(3):
+            for b in range(3):
+                check(fs[i, 3 * a + b], face[i, a], face[i, b])
+    for i in range(nh):
+        r = [hg[i, 2], hg[i, 1], hg[i, 0], hg[i, 3]]
+        for a in range(4):
+            for b in range(4):
+                check(hs[i, 4 * a + b], r[a], r[b])
+    # transpose table: column j lists (row i, slot of (i, j)) for every strictly-upper block (i, j)
+    n_t = 0
+    for j in range(nv):
+        for k in range(toff[j], toff[j + 1]):
+            i, slot = int(trs[k, 0]), int(trs[k, 1])
+            assert i < j and off[i] <= slot < off[i + 1] and col[slot] == j
+            n_t += 1
+    assert n_t == nnz - nv
