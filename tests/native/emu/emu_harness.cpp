@@ -1,0 +1,61 @@
+// emu_harness.cpp -- TEST INFRASTRUCTURE: drives the backend's own upload + assembly code (csrc/abi.cu, csrc/elastic.cu,
+// rewritten for the host by tests/test_kernel_emulation.py, see cuda_runtime.h next to this file) on a scene built by the C++
+// host, and hands the assembled gradient / fixed-matrix blocks / diagonal blocks back for comparison with the oracle.
+#include "backend.hpp"
+#include "../../../ppf-contact-solver_b200/host/ppf_host.hpp"
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+PpfEmuDim blockIdx, blockDim, threadIdx;
+
+// ---- pieces of the backend that the two emulated files reference but that are not part of this check ----
+namespace ppf {
+void step_advance(State &, PpfStepResult *) {}
+void bvh_build(State &, Bvh &, int, const float4 *) {}
+void bvh_refit(State &, Bvh &, int, const float4 *, const float4 *, float) {}
+bool check_intersection(State &, const float4 *, const PpfParamSet &) { return true; }
+void build_fetch_pattern(State &, std::vector<unsigned> &, std::vector<unsigned> &) {}
+float reduce_max_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] > m ? d[i] : m; return m; }
+struct ScopeLog::Impl {};
+ScopeLog::ScopeLog(const char *) : impl(nullptr) {}
+ScopeLog::~ScopeLog() {}
+void ScopeLog::push(const char *) {}
+void ScopeLog::pop() {}
+void ScopeLog::mark(const char *, double) {}
+void ScopeLog::message(const char *, ...) {}
+void simplelog_set_path(const char *) {}
+void simplelog_set_time(double) {}
+} // namespace ppf
+extern "C" void print_rust(const char *) {}
+
+extern "C" __attribute__((visibility("default")))
+int emu_assemble(const char *scene, unsigned n, const float *eval_x, float dt, float *force, float *fx_val, float *diag, unsigned *counts) {
+    using namespace ppf;
+    static ppfh::Built b; // keeps the host arrays alive
+    ppfh::build_scene(ppfh::make_scene(scene, n), b);
+    State &s = g;
+    s.host = b.dataset;
+    s.param = &b.param;
+    s.stream = nullptr;
+    upload_dataset(s);
+    const unsigned nv = s.nv;
+    counts[0] = nv; counts[1] = s.fixed_nnz; counts[2] = s.nrod; counts[3] = s.nrodbend; counts[4] = s.nstitch;
+    if (!eval_x) return 0;
+    for (unsigned i = 0; i < nv; ++i) s.eval_x.p[i] = make_float4(eval_x[3 * i], eval_x[3 * i + 1], eval_x[3 * i + 2], 0.f);
+    std::memcpy(s.target.p, s.curr.p, sizeof(float4) * nv);
+    std::memset(s.diag.p, 0, sizeof(float) * 9 * size_t(nv));
+    std::memset(s.fx_val.p, 0, sizeof(float) * 9 * size_t(s.fixed_nnz));
+    std::memset(s.force.p, 0, sizeof(float) * 3 * size_t(nv));
+    const PpfParamSet prm = *s.param;
+    assemble_momentum(s, dt, prm);
+    assemble_elastic(s, dt, prm);
+    assemble_damping(s, dt, prm);
+    assemble_stitches(s, prm);
+    std::memcpy(s.fx_el.p, s.fx_val.p, sizeof(float) * 9 * size_t(s.fixed_nnz));
+    assemble_strainlimit(s, prm);
+    std::memcpy(force, s.force.p, sizeof(float) * 3 * size_t(nv));
+    std::memcpy(fx_val, s.fx_val.p, sizeof(float) * 9 * size_t(s.fixed_nnz));
+    std::memcpy(diag, s.diag.p, sizeof(float) * 9 * size_t(nv));
+    return 1;
+}

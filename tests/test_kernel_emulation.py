@@ -1,0 +1,121 @@
+"""Wiring check of the CUDA assembly kernels WITHOUT a GPU.
+
+The backend's own sources csrc/abi.cu (upload_dataset, the constraint kernels) and csrc/elastic.cu (k_momentum, k_face,
+k_face_iso, k_hinge, k_rod, k_rod_bend, k_rod_strain, k_damp_*, k_stitch, k_strainlimit) are rewritten for the host --
+every `kernel<<<grid, block, shmem, stream>>>(args)` becomes a serial loop over the threads, device memory becomes host
+memory (tests/native/emu/cuda_runtime.h) -- compiled by g++ and run on scenes built by the C++ host.  The assembled
+gradient, fixed-matrix blocks and diagonal blocks are compared with the oracle's assembly of the same positions.
+The per-element math of both sides is pinned elsewhere (tests/test_oracle_cpu.py); what this test adds is the part no
+other CPU test sees: argument order, packed parameter arrays, slot tables, gating flags and scatter of every kernel.
+Agreement is to fp32 summation-order noise (the oracle accumulates in a different element order)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(REPO, "ppf-contact-solver_b200", "csrc")
+HOST = os.path.join(REPO, "ppf-contact-solver_b200", "host")
+EMU = os.path.join(REPO, "tests", "native", "emu")
+OUT = os.path.join(REPO, "tests", "native", "build", "emu")
+
+
+def _rewrite_launches(src):
+    """kernel<<<grid, block, shmem, stream>>>(args)  ->  PPF_EMU_LAUNCH(kernel, grid, block, args)"""
+    out, pos = [], 0
+    while True:
+        k = src.find("<<<", pos)
+        if k < 0:
+            out.append(src[pos:])
+            return "".join(out)
+        m = re.search(r"[A-Za-z_][A-Za-z_0-9]*(?:<[^<>;]*>)?$", src[:k])
+        name_start = m.start()
+        e = src.index(">>>", k)
+        cfg = src[k + 3:e]
+        depth, parts, cur = 0, [], ""
+        for ch in cfg:                        # split the launch configuration at top-level commas
+            if ch == "(":
+                depth += 1
+            if ch == ")":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur); cur = ""
+            else:
+                cur += ch
+        parts.append(cur)
+        a = src.index("(", e)
+        depth, j = 0, a
+        while True:                           # the balanced argument list
+            if src[j] == "(":
+                depth += 1
+            elif src[j] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        args = src[a + 1:j]
+        out.append(src[pos:name_start])
+        out.append("PPF_EMU_LAUNCH(%s, %s, %s, %s)" % (src[name_start:k], parts[0].strip(), parts[1].strip(), args))
+        pos = j + 1
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    os.makedirs(OUT, exist_ok=True)
+    srcs = []
+    for f in ("abi.cu", "elastic.cu"):
+        text = _rewrite_launches(open(os.path.join(CSRC, f)).read())
+        assert "<<<" not in text
+        p = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
+        open(p, "w").write(text)
+        srcs.append(p)
+    lib = os.path.join(OUT, "libemu.so")
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off", "-w", "-I", EMU, "-I", CSRC, "-I", os.path.join(REPO, "include"),
+           os.path.join(EMU, "emu_harness.cpp"), os.path.join(HOST, "scene.cpp"), os.path.join(HOST, "builder.cpp")] + srcs + ["-o", lib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    l = C.CDLL(lib)
+    l.emu_assemble.restype = C.c_int
+    return l
+
+
+def _assemble_both(emu, ppf, scene, n, seed, amplitude, dt):
+    cnt = (C.c_uint * 5)()
+    emu.emu_assemble(scene.encode(), C.c_uint(n), None, C.c_float(dt), None, None, None, cnt)
+    nv, nnz = int(cnt[0]), int(cnt[1])
+    s = ppf.Session(scene, n=n, lib=ppf.LIB_ORACLE)
+    x0, _ = s.fetch()
+    rng = np.random.default_rng(seed)
+    x = (x0 + rng.normal(0, amplitude, size=x0.shape)).astype(np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    f1 = np.zeros(3 * nv, np.float32); v1 = np.zeros(9 * nnz, np.float32); d1 = np.zeros(9 * nv, np.float32)
+    assert emu.emu_assemble(scene.encode(), C.c_uint(n), fp(x), C.c_float(dt), fp(f1), fp(v1), fp(d1), cnt) == 1
+    ora = C.CDLL(ppf.LIB_ORACLE)
+    f0 = np.zeros(3 * nv, np.float32); v0 = np.zeros(9 * nnz, np.float32); d0 = np.zeros(9 * nv, np.float32)
+    ora.oracle_assemble(fp(x), C.c_float(dt), fp(f0), fp(v0), fp(d0))
+    return (f0, v0, d0), (f1, v1, d1), [int(c) for c in cnt]
+
+
+CASES = [("fast-twist", 12, 2e-3), ("hang", 12, 2e-3), ("sheet-arap", 10, 2e-3), ("sheet-stvk", 10, 2e-3), ("sheet-snhk", 10, 2e-3),
+         ("sheet-damped", 10, 2e-3), ("sheet-arap-damped", 10, 2e-3), ("woven", 32, 2e-4), ("woven-sl", 32, 3e-4), ("woven-damped", 32, 2e-4),
+         ("seam", 10, 2e-3), ("headless", 10, 2e-3)]
+
+
+@pytest.mark.parametrize("scene,n,amp", CASES, ids=[c[0] for c in CASES])
+def test_emulated_assembly_kernels_match_the_oracle(emu, ppf, scene, n, amp):
+    (f0, v0, d0), (f1, v1, d1), cnt = _assemble_both(emu, ppf, scene, n, seed=5, amplitude=amp, dt=0.01)
+    assert np.isfinite(f1).all() and np.isfinite(v1).all() and np.isfinite(d1).all()
+    assert np.abs(v0).max() > 0 and np.abs(f0).max() > 0
+    # blocks: every entry within 2e-4 of its block's scale (fp32 sums of up to ~12 element contributions in different orders)
+    b0, b1 = v0.reshape(-1, 9), v1.reshape(-1, 9)
+    scale = np.maximum(np.abs(b0).max(axis=1, keepdims=True), 1e-3 * np.abs(b0).max())
+    assert float((np.abs(b0 - b1) / scale).max()) < 2e-4
+    assert float(np.abs(d0 - d1).max()) <= 2e-5 * max(float(np.abs(d0).max()), 1e-12)
+    assert float(np.abs(f0 - f1).max()) <= 2e-4 * float(np.abs(f0).max())
+    if scene.startswith("woven"):
+        assert cnt[2] > 0 and cnt[3] > 0          # rod edges and bending stencils were assembled
+    if scene == "seam":
+        assert cnt[4] == 10
