@@ -59,3 +59,18 @@ int emu_assemble(const char *scene, unsigned n, const float *eval_x, float dt, f
     std::memcpy(diag, s.diag.p, sizeof(float) * 9 * size_t(nv));
     return 1;
 }
+
+// "max_sigma" diagnostic (k_face_sigma / k_rod_sigma) at caller-provided start-of-step positions
+extern "C" __attribute__((visibility("default")))
+float emu_max_sigma(const char *scene, unsigned n, const float *x) {
+    using namespace ppf;
+    static ppfh::Built b;
+    ppfh::build_scene(ppfh::make_scene(scene, n), b);
+    State &s = g;
+    s.host = b.dataset;
+    s.param = &b.param;
+    s.stream = nullptr;
+    upload_dataset(s);
+    if (x) for (unsigned i = 0; i < s.nv; ++i) s.curr.p[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.f);
+    return max_stretch_ratio(s);
+}

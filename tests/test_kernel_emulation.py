@@ -119,3 +119,26 @@ def test_emulated_assembly_kernels_match_the_oracle(emu, ppf, scene, n, amp):
         assert cnt[2] > 0 and cnt[3] > 0          # rod edges and bending stencils were assembled
     if scene == "seam":
         assert cnt[4] == 10
+
+
+def test_emulated_max_sigma_diagnostic(emu, ppf):
+    """the `max_sigma` channel (main.cu:424-488): 1 at rest; for rods the largest length / drawn length; for shells the largest
+    singular value of the deformation gradient (a uniform 3 % stretch of the whole sheet reads 1.03)"""
+    emu.emu_max_sigma.restype = C.c_float
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    assert abs(emu.emu_max_sigma(b"fast-twist", C.c_uint(12), None) - 1.0) < 2e-5
+    assert abs(emu.emu_max_sigma(b"woven", C.c_uint(32), None) - 1.0) < 2e-6
+    s = ppf.Session("sheet", n=10, lib=ppf.LIB_ORACLE)
+    x0, _ = s.fetch()
+    x = x0.copy(); x[:, 0] *= np.float32(1.03)                      # stretch along x only
+    assert abs(emu.emu_max_sigma(b"sheet", C.c_uint(10), fp(np.ascontiguousarray(x))) - 1.03) < 1e-4
+    w = ppf.Session("woven", n=32, lib=ppf.LIB_ORACLE)
+    y0, _ = w.fetch()
+    _, edge, _ = w.topology()
+    rng = np.random.default_rng(2)
+    y = (y0 + rng.normal(0, 2e-3, size=y0.shape)).astype(np.float32)
+    drawn = np.linalg.norm(y0[edge[:, 0]].astype(np.float64) - y0[edge[:, 1]], axis=1)
+    now = np.linalg.norm(y[edge[:, 0]].astype(np.float64) - y[edge[:, 1]], axis=1)
+    fixed = np.zeros(len(y0), bool); fixed[w.fix_targets()[0]] = True
+    free = ~(fixed[edge[:, 0]] & fixed[edge[:, 1]])
+    assert abs(emu.emu_max_sigma(b"woven", C.c_uint(32), fp(y)) - float((now / drawn)[free].max())) < 1e-5
