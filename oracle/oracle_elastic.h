@@ -737,4 +737,63 @@ static inline void o_stitch(const float (*x)[3], const float *ghat, const float 
         }
 }
 
+/* ---- plastic creep of the rest shape after a step (plasticity/plasticity.cu:12-86, 147-245) ---- */
+static inline float o_plastic_alpha(float rate, float dt) { return 1.0f - expf(-rate * dt); }
+static inline float o_dead_zone_creep(float delta, float threshold, float alpha) { return alpha * (delta - ((delta > 0.0f) ? threshold : -threshold)); }
+static inline float o_hinge_angle(const float (*X)[3]) { /* dihedral_angle.hpp:81-96 with (v0,v1,v2,v3) = the remapped vertices */
+    float a[3], b[3], n1[3], n2[3], ee[3], t[3];
+    o_sub(X[1], X[0], a); o_sub(X[2], X[0], b); o_cross(a, b, n1);
+    o_sub(X[2], X[3], a); o_sub(X[1], X[3], b); o_cross(a, b, n2);
+    o_sub(X[1], X[2], ee);
+    const float en = o_norm3(ee);
+    if (!(en > 0.0f)) return 0.0f;
+    o_cross(n2, n1, t);
+    return atan2f(o_dot(t, ee) / en, o_dot(n1, n2));
+}
+/* ir: inverse rest 2x2 (column-major), updated in place; returns 1 when it changed */
+static inline int o_face_plasticity(const float *x0, const float *x1, const float *x2, float *ir, float threshold, float alpha) {
+    float F[3][2], Sn[2], Fn[3][2], d0[3], d1[3], c[3], n[3], t[3], b[3];
+    o_svd32 svd;
+    o_defgrad32(x0, x1, x2, ir, F);
+    o_jacobi_svd32(F, &svd);
+    int changed = 0;
+    for (int k = 0; k < 2; ++k) {
+        Sn[k] = svd.S[k];
+        if (fabsf(svd.S[k] - 1.0f) > threshold) {
+            const float target = (svd.S[k] < 1.0f) ? (1.0f - threshold) : (1.0f + threshold);
+            Sn[k] = svd.S[k] + alpha * (target - svd.S[k]);
+            changed = 1;
+        }
+    }
+    if (!changed) return 0;
+    for (int r = 0; r < 3; ++r)
+        for (int j = 0; j < 2; ++j) Fn[r][j] = (svd.U[r][0] * Sn[0]) * svd.Vt[0][j] + (svd.U[r][1] * Sn[1]) * svd.Vt[1][j];
+    o_sub(x1, x0, d0); o_sub(x2, x0, d1);
+    o_cross(d0, d1, c);
+    float l = o_norm3(c); for (int k = 0; k < 3; ++k) n[k] = l > 0.0f ? c[k] / l : c[k];
+    l = o_norm3(d0); for (int k = 0; k < 3; ++k) t[k] = l > 0.0f ? d0[k] / l : d0[k];
+    o_cross(n, t, c);
+    l = o_norm3(c); for (int k = 0; k < 3; ++k) b[k] = l > 0.0f ? c[k] / l : c[k];
+    const float m00 = o_dot(t, d0), m01 = o_dot(t, d1), m10 = o_dot(b, d0), m11 = o_dot(b, d1);
+    const float det = m00 * m11 - m01 * m10;
+    const float i00 = m11 / det, i01 = -m01 / det, i10 = -m10 / det, i11 = m00 / det;
+    float PF[2][2];
+    for (int j = 0; j < 2; ++j) { const float col[3] = {Fn[0][j], Fn[1][j], Fn[2][j]}; PF[0][j] = o_dot(t, col); PF[1][j] = o_dot(b, col); }
+    ir[0] = i00 * PF[0][0] + i01 * PF[1][0]; ir[2] = i00 * PF[0][1] + i01 * PF[1][1];
+    ir[1] = i10 * PF[0][0] + i11 * PF[1][0]; ir[3] = i10 * PF[0][1] + i11 * PF[1][1];
+    return 1;
+}
+static inline float o_hinge_plasticity(const float (*X)[3], float rest_angle, float threshold, float alpha) {
+    const float delta = o_hinge_angle(X) - rest_angle;
+    return fabsf(delta) > threshold ? rest_angle + o_dead_zone_creep(delta, threshold, alpha) : rest_angle;
+}
+static inline float o_rod_bend_plasticity(const float *xj, const float *xi, const float *xk, float rest_angle, float threshold, float alpha) {
+    float e0[3], e1[3];
+    o_sub(xj, xi, e0); o_sub(xk, xi, e1);
+    const float n0 = o_norm3(e0), n1 = o_norm3(e1);
+    if (n0 <= 0.0f || n1 <= 0.0f) return rest_angle;
+    const float delta = acosf(fmaxf(-1.0f, fminf(1.0f, o_dot(e0, e1) / (n0 * n1)))) - rest_angle;
+    return fabsf(delta) > threshold ? rest_angle + o_dead_zone_creep(delta, threshold, alpha) : rest_angle;
+}
+
 #endif

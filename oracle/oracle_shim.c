@@ -130,3 +130,17 @@ SHIM void orc_stitch(const float *x18, const float *ghat6, const float *offset6,
     o_stitch(x, ghat6, offset6, w6, stiffness, length_factor, f, H324);
     for (int a = 0; a < 6; ++a) for (int k = 0; k < 3; ++k) f18[3 * a + k] = f[a][k];
 }
+
+/* plastic creep */
+SHIM int orc_face_plasticity(const float *x9, float *ir4, float threshold, float rate, float dt) {
+    return o_face_plasticity(x9, x9 + 3, x9 + 6, ir4, threshold, o_plastic_alpha(rate, dt));
+}
+SHIM float orc_hinge_plasticity(const float *x12, float rest, float threshold, float rate, float dt) {
+    static const int map[4] = {2, 1, 0, 3};
+    float X[4][3];
+    for (int a = 0; a < 4; ++a) for (int k = 0; k < 3; ++k) X[a][k] = x12[3 * map[a] + k];
+    return o_hinge_plasticity(X, rest, threshold, o_plastic_alpha(rate, dt));
+}
+SHIM float orc_rod_bend_plasticity(const float *x9, float rest, float threshold, float rate, float dt) {
+    return o_rod_bend_plasticity(x9, x9 + 3, x9 + 6, rest, threshold, o_plastic_alpha(rate, dt));
+}

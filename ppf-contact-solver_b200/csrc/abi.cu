@@ -125,7 +125,7 @@ void upload_dataset(State &s) {
     if (d.rod_count > ne) fatal(4, "rod_count %u exceeds the edge count %u", d.rod_count, ne);
     for (unsigned i = 0; i < d.rod_count; ++i) {
         const PpfEdgeParam &ep = d.param_arrays.edge.data[d.prop.edge.data[i].param_index];
-        if (ep.plasticity > 0.0f) fatal(4, "B200 backend: rod bend plasticity is not implemented");
+        (void)ep;
     }
     if (d.rod_count && (d.edge_hess_slots.size < 4u * d.rod_count || d.rod_bend_hess_slots.size != 9u * d.surface_vert_count))
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
@@ -147,7 +147,6 @@ void upload_dataset(State &s) {
         if (fp.model != PPF_MODEL_BARAFFWITKIN && fp.model != PPF_MODEL_ARAP && fp.model != PPF_MODEL_STVK && fp.model != PPF_MODEL_SNHK)
             fatal(4, "B200 backend: shell model %d is not implemented (Baraff-Witkin, ARAP, StVK and SNHk are)", (int)fp.model);
         if (fp.pressure > 0.0f) fatal(4, "B200 backend: inflation pressure is not implemented");
-        if (fp.plasticity > 0.0f || fp.bend_plasticity > 0.0f) fatal(4, "B200 backend: shell plasticity is not implemented");
     }
     if (d.face_hess_slots.size != 9u * nf || d.hinge_hess_slots.size != 16u * nh)
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
@@ -241,6 +240,19 @@ void upload_dataset(State &s) {
             for (unsigned i = 0; i < nf; ++i) { fd[i] = d.param_arrays.face.data[d.prop.face.data[i].param_index].deform_damping; s.has_fdamp = s.has_fdamp || fd[i] > 0.0f; }
             for (unsigned i = 0; i < nh; ++i) { hd[i] = d.param_arrays.hinge.data[d.prop.hinge.data[i].param_index].bend_damping; s.has_hdamp = s.has_hdamp || hd[i] > 0.0f; }
             s.fdamp.upload(fd.data(), nf, q); s.hdamp.upload(hd.data(), nh, q);
+            std::vector<float2> fpl(nf), hpl(nh);
+            s.has_fplast = s.has_hplast = false;
+            for (unsigned i = 0; i < nf; ++i) {
+                const PpfFaceParam &fp = d.param_arrays.face.data[d.prop.face.data[i].param_index];
+                fpl[i] = make_float2(i < d.shell_face_count ? fp.plasticity : 0.0f, fp.plasticity_threshold);
+                s.has_fplast = s.has_fplast || fpl[i].x > 0.0f;
+            }
+            for (unsigned i = 0; i < nh; ++i) {
+                const PpfHingeParam &hp = d.param_arrays.hinge.data[d.prop.hinge.data[i].param_index];
+                hpl[i] = make_float2(hp.plasticity, hp.plasticity_threshold);
+                s.has_hplast = s.has_hplast || hpl[i].x > 0.0f;
+            }
+            s.fplast.upload(fpl.data(), nf, q); s.hplast.upload(hpl.data(), nh, q);
             std::vector<float> fsh(nf);
             for (unsigned i = 0; i < nf; ++i) { const PpfFaceParam &fp = d.param_arrays.face.data[d.prop.face.data[i].param_index]; fsh[i] = d.prop.face.data[i].collider ? 0.0f : fminf(fp.shrink_x, fp.shrink_y); }
             s.fshrink.upload(fsh.data(), nf, q);
@@ -285,6 +297,7 @@ void upload_dataset(State &s) {
         std::vector<float2> par;
         std::vector<unsigned> sl;
         std::vector<float> rbd;
+        std::vector<float2> rbp;
         for (unsigned i = 0; i < s.nsv; ++i) {
             if (i >= vedge.size || vedge.offset[i + 1] - vedge.offset[i] != 2) continue;
             if (i < vface.size && vface.offset[i + 1] != vface.offset[i]) continue;
@@ -299,11 +312,15 @@ void upload_dataset(State &s) {
             el.push_back(make_uint4(j, i, kk, 0u));
             par.push_back(make_float2(k, d.prop.vertex.data[i].rest_bend_angle));
             rbd.push_back(0.5f * (q0.bend_damping + q1.bend_damping)); // energy.cu:570-571
+            rbp.push_back(make_float2(0.5f * (q0.plasticity + q1.plasticity), 0.5f * (q0.plasticity_threshold + q1.plasticity_threshold))); // plasticity.cu:218-224
             for (int b = 0; b < 9; ++b) sl.push_back(d.rod_bend_hess_slots.data[size_t(9) * i + b]);
         }
         s.nrodbend = (unsigned)el.size();
         s.rb_elem.upload(el.data(), el.size(), q); s.rb_par.upload(par.data(), par.size(), q); s.rb_slots.upload(sl.data(), sl.size(), q);
         s.rb_damp.upload(rbd.data(), rbd.size(), q);
+        s.rb_plast.upload(rbp.data(), rbp.size(), q);
+        s.has_rb_plast = false;
+        for (const float2 &v : rbp) s.has_rb_plast = s.has_rb_plast || v.x > 0.0f;
         s.has_rb_damp = false;
         for (float v : rbd) s.has_rb_damp = s.has_rb_damp || v > 0.0f;
         std::vector<float> rdm(s.nrod);
@@ -439,10 +456,33 @@ PPF_EXPORT void fetch(void) {
     CUDA_OK(cudaStreamSynchronize(q));
     LAUNCH_COUNT(2);
 }
-// plasticity is out of scope, so the device never changes inv_rest or the rest angles: the host
-// arrays already hold what the reference would copy back (main.cu:1939-1968)
-PPF_EXPORT void fetch_inv_rest(void) {}
-PPF_EXPORT void fetch_rest_angles(void) {}
+// plastic creep changes inv_rest and the rest angles on the device: copy them back into the caller's host arrays so that
+// a saved state carries them (main.cu:1939-1968)
+PPF_EXPORT void fetch_inv_rest(void) {
+    State &s = g;
+    if (!s.nf || !s.has_fplast) return;
+    std::vector<float4> h(s.nf);
+    CUDA_OK(cudaMemcpy(h.data(), s.inv_rest.p, sizeof(float4) * s.nf, cudaMemcpyDeviceToHost));
+    for (unsigned i = 0; i < s.nf && i < s.host.inv_rest2x2.size; ++i) {
+        PpfMat2x2f &m = s.host.inv_rest2x2.data[i];
+        m.m[0] = h[i].x; m.m[1] = h[i].y; m.m[2] = h[i].z; m.m[3] = h[i].w;
+    }
+}
+PPF_EXPORT void fetch_rest_angles(void) {
+    State &s = g;
+    if (s.nh && s.has_hplast) {
+        std::vector<float4> h(s.nh);
+        CUDA_OK(cudaMemcpy(h.data(), s.hmat.p, sizeof(float4) * s.nh, cudaMemcpyDeviceToHost));
+        for (unsigned i = 0; i < s.nh; ++i) s.host.prop.hinge.data[i].rest_angle = h[i].z;
+    }
+    if (s.nrodbend && s.has_rb_plast) {
+        std::vector<uint4> el(s.nrodbend);
+        std::vector<float2> par(s.nrodbend);
+        CUDA_OK(cudaMemcpy(el.data(), s.rb_elem.p, sizeof(uint4) * s.nrodbend, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(par.data(), s.rb_par.p, sizeof(float2) * s.nrodbend, cudaMemcpyDeviceToHost));
+        for (unsigned t = 0; t < s.nrodbend; ++t) s.host.prop.vertex.data[el[t].y].rest_bend_angle = par[t].y;
+    }
+}
 
 PPF_EXPORT void fetch_dyn_counts(unsigned *n_value, unsigned *n_offset) {
     State &s = g;

@@ -121,6 +121,8 @@ struct State {
     DBuf<float4> fmat;                            // per face (mu, lambda, mass, model as a float: the ABI's Model enum)
     bool has_iso_faces = false;                   // some face uses an SVD-based model (ARAP / StVK / SNHk)
     // Rayleigh damping coefficients (seconds), 0 = none: faces / rods use deform_damping, hinges / rod bending bend_damping
+    DBuf<float2> fplast, hplast, rb_plast;        // plastic creep (rate per second, dead-zone threshold) per face / hinge / bending vertex
+    bool has_fplast = false, has_hplast = false, has_rb_plast = false;
     DBuf<float> fdamp, hdamp, rod_damp, rb_damp;
     bool has_fdamp = false, has_hdamp = false, has_rod_damp = false, has_rb_damp = false;
     DBuf<float2> fstrain;                         // per face (strain-limit parameter, shrink-adjusted limit); 0 = off
@@ -209,6 +211,7 @@ void step_advance(State &s, PpfStepResult *result);          // step.cu
 // elastic.cu
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm);
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm);
+void apply_plasticity(State &s, const PpfParamSet &prm);                                      // after the step: rest shapes creep (plasticity.cu)
 void assemble_stitches(State &s, const PpfParamSet &prm);                                     // seam springs, before the elastic snapshot
 void assemble_damping(State &s, float dt, const PpfParamSet &prm);                             // Rayleigh damping, part of "asm elastic"
 void assemble_strainlimit(State &s, const PpfParamSet &prm);                                  // after the elastic snapshot

@@ -11,6 +11,7 @@
 #include "math_elastic.cuh"
 #include "math_damping.cuh"
 #include "math_hinge.cuh"
+#include "math_plasticity.cuh"
 #include "math_rod.cuh"
 #include "math_stitch.cuh"
 #include "math_strain.cuh"
@@ -288,6 +289,50 @@ __global__ void __launch_bounds__(128) k_strain_toi(unsigned nf, const uint4 *__
     }
     for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
     if ((threadIdx.x & 31) == 0 && t < max_t) atomicMin(toi_bits, __float_as_uint(fmaxf(t, 0.0f)));
+}
+
+// ---- plastic creep of the rest shape after a step (plasticity.cu; math_plasticity.cuh) ----
+__global__ void __launch_bounds__(128) k_plastic_face(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ curr,
+                                                      const float2 *__restrict__ fplast, float dt, float4 *__restrict__ inv_rest) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const float2 pl = fplast[i]; // (rate, threshold)
+    if (!(pl.x > 0.0f)) return;
+    const uint4 f = face[i];
+    const float4 ir = inv_rest[i];
+    float irv[4] = {ir.x, ir.y, ir.z, ir.w};
+    if (face_plasticity(ld3(curr, f.x), ld3(curr, f.y), ld3(curr, f.z), irv, pl.y, plastic_alpha(pl.x, dt)))
+        inv_rest[i] = make_float4(irv[0], irv[1], irv[2], irv[3]);
+}
+__global__ void __launch_bounds__(128) k_plastic_hinge(unsigned nh, const uint4 *__restrict__ hinge, const float4 *__restrict__ curr,
+                                                       const float2 *__restrict__ hplast, const unsigned char *__restrict__ hfixed, float dt,
+                                                       float4 *__restrict__ hmat) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nh || hfixed[i]) return;
+    const float2 pl = hplast[i];
+    if (!(pl.x > 0.0f)) return;
+    const uint4 h = hinge[i];
+    const V3 X[4] = {ld3(curr, h.z), ld3(curr, h.y), ld3(curr, h.x), ld3(curr, h.w)}; // remapped (dihedral_angle.hpp:15-17)
+    float4 m = hmat[i]; // (length, area, rest angle, bend)
+    m.z = hinge_plasticity(X, m.z, pl.y, plastic_alpha(pl.x, dt));
+    hmat[i] = m;
+}
+__global__ void __launch_bounds__(128) k_plastic_rod_bend(unsigned n, const uint4 *__restrict__ elem, const float4 *__restrict__ curr,
+                                                          const float2 *__restrict__ rb_plast, float dt, float2 *__restrict__ par) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float2 pl = rb_plast[t];
+    if (!(pl.x > 0.0f)) return;
+    const uint4 el = elem[t]; // (j, i, k)
+    float2 pr = par[t];       // (coefficient, rest angle)
+    pr.y = rod_bend_plasticity(ld3(curr, el.x), ld3(curr, el.y), ld3(curr, el.z), pr.y, pl.y, plastic_alpha(pl.x, dt));
+    par[t] = pr;
+}
+void apply_plasticity(State &s, const PpfParamSet &prm) {
+    cudaStream_t q = s.stream;
+    if (s.has_fplast && s.nf) { k_plastic_face<<<div_up(s.nf, 128), 128, 0, q>>>(s.nf, s.face.p, s.curr.p, s.fplast.p, prm.dt, s.inv_rest.p); LAUNCH_COUNT(1); }
+    if (s.has_hplast && s.nh) { k_plastic_hinge<<<div_up(s.nh, 128), 128, 0, q>>>(s.nh, s.hinge.p, s.curr.p, s.hplast.p, s.hfixed.p, prm.dt, s.hmat.p); LAUNCH_COUNT(1); }
+    if (s.has_rb_plast && s.nrodbend) { k_plastic_rod_bend<<<div_up(s.nrodbend, 128), 128, 0, q>>>(s.nrodbend, s.rb_elem.p, s.curr.p, s.rb_plast.p, prm.dt, s.rb_par.p); LAUNCH_COUNT(1); }
 }
 
 // ---- stitches (energy.cu:796-886; math_stitch.cuh) ----

@@ -378,6 +378,7 @@ void step_advance(State &s, PpfStepResult *out) {
     std::swap(s.prev.p, s.curr.p);
     std::swap(s.prev.cap, s.curr.cap);
     CUDA_OK(cudaMemcpyAsync(s.curr.p, s.eval_x.p, sizeof(float4) * nv, cudaMemcpyDeviceToDevice, q));
+    apply_plasticity(s, *s.param); // main.cu:1613-1626: on the new positions, with the session's dt
     CUDA_OK(cudaStreamSynchronize(q));
     result.time = s.param->time;
     finish(true);

@@ -178,6 +178,8 @@ void build_scene(const SceneSpec &spec, Built &b) {
         p.bend = get("bend"); p.strainlimit = get("strain-limit");
         p.shrink_x = get("shrink-x"); p.shrink_y = get("shrink-y"); p.pressure = get("pressure");
         p.deform_damping = get("deformation-damping"); p.bend_damping = get("bending-damping");
+        p.plasticity = get("plasticity"); p.plasticity_threshold = get("plasticity-threshold");
+        p.bend_plasticity = get("bend-plasticity"); p.bend_plasticity_threshold = get("bend-plasticity-threshold");
         obj_fparam[o] = p;
         obj_density[o] = get("density");
     }
@@ -315,18 +317,20 @@ void build_scene(const SceneSpec &spec, Built &b) {
     b.hprop.resize(nh);
     for (unsigned i = 0; i < nh; ++i) {
         const PpfVec4u &h = b.hinge[i];
-        float os = 0, gs = 0, bs = 0, as = 0, ds = 0;
+        float os = 0, gs = 0, bs = 0, as = 0, ds = 0, ps = 0, pts = 0;
         bool all_fixed = true;
         for (unsigned j : b.hinge_face[i]) {
             const PpfFaceParam &fp = b.fparam[b.fprop[j].param_index];
             const float ar = b.fprop[j].area;
             all_fixed = all_fixed && b.fprop[j].fixed;
             os += ar * fp.offset; gs += ar * fp.ghat; bs += ar * fp.bend; as += ar; ds += ar * fp.bend_damping;
+            ps += ar * fp.bend_plasticity; pts += ar * fp.bend_plasticity_threshold;
         }
         PpfHingeParam p;
         std::memset(&p, 0, sizeof(p));
         p.bend = all_fixed ? 0.0f : bs / as;
         p.bend_damping = all_fixed ? 0.0f : ds / as; // builder.rs:881-920
+        p.plasticity = ps / as; p.plasticity_threshold = pts / as;
         p.ghat = gs / as; p.offset = os / as;
         PpfHingeProp hp;
         std::memset(&hp, 0, sizeof(hp));

@@ -119,7 +119,8 @@ std::vector<unsigned> grab(const std::vector<Vec3d> &V, Vec3d dir, double eps) {
 static std::map<std::string, double> tri_defaults() { // params.rs:295-420 (ObjectKind::Tri)
     return {{"model", 2.0 /* baraff-witkin */}, {"density", 1.0}, {"young-mod", 1000.0}, {"poiss-rat", 0.35},
             {"bend", 10.0}, {"shrink-x", 1.0}, {"shrink-y", 1.0}, {"contact-gap", 1e-3}, {"contact-offset", 0.0},
-            {"strain-limit", 0.0}, {"friction", 0.0}, {"pressure", 0.0}, {"deformation-damping", 0.0}, {"bending-damping", 0.0}};
+            {"strain-limit", 0.0}, {"friction", 0.0}, {"pressure", 0.0}, {"deformation-damping", 0.0}, {"bending-damping", 0.0},
+            {"plasticity", 0.0}, {"plasticity-threshold", 0.0}, {"bend-plasticity", 0.0}, {"bend-plasticity-threshold", 0.0}};
 }
 
 static std::map<std::string, double> rod_defaults() { // params.rs:295-420 (ObjectKind::Rod)
@@ -490,6 +491,14 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         if (n && (unsigned(25.0 * 2.0 * 1.48 * scale) & 1u)) scale = (double(unsigned(25.0 * 2.0 * 1.48 * scale) + 1) + 1e-9) / (25.0 * 2.0 * 1.48); // even strand count
         return woven_scene(name, nn, 4e-3, scale, 1.5e-3, 2e-3, 0.01, 0.15, 10.0, 1.0, 1e-3, 10000000u, 450);
     }
+    if (name == "woven-plastic") { // test scene: the woven cylinder with bend plasticity on the rods
+        const unsigned nn = n ? n : 32;
+        double scale = 2.0 * double(nn) / 256.0;
+        if (unsigned(25.0 * 2.0 * 1.48 * scale) & 1u) scale = (double(unsigned(25.0 * 2.0 * 1.48 * scale) + 1) + 1e-9) / (25.0 * 2.0 * 1.48);
+        SceneSpec s = woven_scene(name, nn, 4e-3, scale, 1.5e-3, 2e-3, 0.01, 0.15, 10.0, 1.0, 1e-3, 10000000u, 240);
+        for (auto &o : s.objects) { o.rod_param["bend-plasticity"] = 30.0; o.rod_param["bend-plasticity-threshold"] = 1e-3; }
+        return s;
+    }
     if (name == "woven-damped") { // test scene: the woven cylinder with Rayleigh damping on the rod stretch and bending
         const unsigned nn = n ? n : 32;
         double scale = 2.0 * double(nn) / 256.0;
@@ -633,13 +642,18 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.dt = 1e-2;
         return s;
     }
-    if (name == "sheet" || name == "sheet-arap" || name == "sheet-stvk" || name == "sheet-snhk" || name == "sheet-damped" || name == "sheet-arap-damped") { // free-hanging sheet without strain limit: elastic-only smoke scene (the suffix selects the shell model)
+    if (name == "sheet" || name == "sheet-arap" || name == "sheet-stvk" || name == "sheet-snhk" || name == "sheet-damped" || name == "sheet-arap-damped" ||
+        name == "sheet-plastic") { // free-hanging sheet without strain limit: elastic-only smoke scene (the suffix selects the shell model)
         SceneSpec s;
         s.name = name;
         ShellObject o;
         gen_square(n ? n : 32, 2.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
         o.param = tri_defaults();
         if (name == "sheet-arap" || name == "sheet-arap-damped") o.param["model"] = 0.0;
+        if (name == "sheet-plastic") { // membrane and bending rest shapes creep toward the deformed shape
+            o.param["plasticity"] = 20.0; o.param["plasticity-threshold"] = 1e-3;
+            o.param["bend-plasticity"] = 20.0; o.param["bend-plasticity-threshold"] = 1e-2;
+        }
         if (name == "sheet-damped" || name == "sheet-arap-damped") { o.param["deformation-damping"] = 0.02; o.param["bending-damping"] = 0.05; } // Rayleigh damping (seconds)
         if (name == "sheet-stvk") o.param["model"] = 1.0;
         if (name == "sheet-snhk") o.param["model"] = 3.0;

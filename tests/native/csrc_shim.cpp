@@ -8,6 +8,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_plasticity.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_rod.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_stitch.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_strain.cuh"
@@ -177,4 +178,18 @@ SHIM void orc_stitch(const float *x18, const float *ghat6, const float *offset6,
     stitch_force_hessian(x, ghat6, offset6, w6, stiffness, length_factor, o);
     for (int a = 0; a < 6; ++a) { f18[3 * a] = o.f[a].x; f18[3 * a + 1] = o.f[a].y; f18[3 * a + 2] = o.f[a].z; }
     for (int i = 0; i < 324; ++i) H324[i] = o.H[i];
+}
+
+// plastic creep: face (ir4 in/out, returns changed), hinge (x12 in the ORIGINAL hinge order h0..h3), rod bend (x9 = j, i, k)
+SHIM int orc_face_plasticity(const float *x9, float *ir4, float threshold, float rate, float dt) {
+    return face_plasticity(v(x9), v(x9 + 3), v(x9 + 6), ir4, threshold, plastic_alpha(rate, dt)) ? 1 : 0;
+}
+SHIM float orc_hinge_plasticity(const float *x12, float rest, float threshold, float rate, float dt) {
+    static const int map[4] = {2, 1, 0, 3};
+    V3 X[4];
+    for (int a = 0; a < 4; ++a) X[a] = v(x12 + 3 * map[a]);
+    return hinge_plasticity(X, rest, threshold, plastic_alpha(rate, dt));
+}
+SHIM float orc_rod_bend_plasticity(const float *x9, float rest, float threshold, float rate, float dt) {
+    return rod_bend_plasticity(v(x9), v(x9 + 3), v(x9 + 6), rest, threshold, plastic_alpha(rate, dt));
 }

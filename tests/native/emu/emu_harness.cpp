@@ -74,3 +74,26 @@ float emu_max_sigma(const char *scene, unsigned n, const float *x) {
     if (x) for (unsigned i = 0; i < s.nv; ++i) s.curr.p[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.f);
     return max_stretch_ratio(s);
 }
+
+// plastic creep kernels (k_plastic_*) at caller-provided new positions, then the ABI's fetch_inv_rest / fetch_rest_angles:
+// returns what a host would read back (inverse rest matrices, hinge rest angles, per-vertex rest bend angles)
+extern "C" void fetch_inv_rest(void);
+extern "C" void fetch_rest_angles(void);
+extern "C" __attribute__((visibility("default")))
+void emu_plasticity(const char *scene, unsigned n, const float *x, float *inv_rest, float *hinge_rest, float *vertex_rest) {
+    using namespace ppf;
+    static ppfh::Built b;
+    ppfh::build_scene(ppfh::make_scene(scene, n), b);
+    State &s = g;
+    s.host = b.dataset;
+    s.param = &b.param;
+    s.stream = nullptr;
+    upload_dataset(s);
+    for (unsigned i = 0; i < s.nv; ++i) s.curr.p[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], 0.f);
+    apply_plasticity(s, *s.param);
+    fetch_inv_rest();
+    fetch_rest_angles();
+    for (unsigned i = 0; i < s.nf; ++i) std::memcpy(inv_rest + 4 * size_t(i), b.inv_rest2x2[i].m, 16);
+    for (unsigned i = 0; i < s.nh; ++i) hinge_rest[i] = b.hprop[i].rest_angle;
+    for (unsigned i = 0; i < s.nv; ++i) vertex_rest[i] = b.vprop[i].rest_bend_angle;
+}

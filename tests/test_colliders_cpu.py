@@ -271,3 +271,62 @@ def test_stitch_oracle_equals_backend_header_and_the_spring_energy(libs):
                 num[k] = (energy(x64 + d.reshape(6, 3)) - energy(x64 - d.reshape(6, 3))) / 2e-7
             worst = max(worst, np.abs(f - num).max() / max(np.abs(num).max(), 1e-9))
     assert worst < 2e-3, worst
+
+
+def test_plastic_creep_oracle_equals_backend_header_and_relaxes_toward_the_dead_zone(libs):
+    """plasticity.cu:21-86, 147-245: oracle and backend header bit for bit; with alpha -> 1 (a huge rate) the rebuilt inverse rest
+    matrix puts the singular values of the same deformed face on the dead-zone edge 1 +- threshold; rest angles move toward the
+    current angle by alpha x (deviation - threshold) and stay put inside the dead zone"""
+    o, b = libs
+    for l in libs:
+        l.orc_face_plasticity.restype = C.c_int
+        l.orc_hinge_plasticity.restype = C.c_float
+        l.orc_rod_bend_plasticity.restype = C.c_float
+    rng = np.random.default_rng(31)
+    n_changed = 0
+    for case in range(200):
+        rest = np.array([[0.0, 0.0], [1.0, 0.1], [0.2, 0.9]]) * 0.05
+        Dm = np.stack([rest[1] - rest[0], rest[2] - rest[0]], axis=1)
+        ir = np.linalg.inv(Dm)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        s1, s2 = rng.uniform(0.9, 1.2), rng.uniform(0.9, 1.2)
+        Fm = q[:, :2] @ np.diag([s1, s2])
+        x0 = rng.uniform(-1, 1, 3)
+        x = np.stack([x0, x0 + Fm @ Dm[:, 0], x0 + Fm @ Dm[:, 1]]).astype(np.float32)
+        ir32 = np.array([ir[0, 0], ir[1, 0], ir[0, 1], ir[1, 1]], np.float32)
+        thr = 0.05
+        outs = []
+        for l in (o, b):
+            irc = ir32.copy()
+            ch = l.orc_face_plasticity(fp(x), fp(irc), C.c_float(thr), C.c_float(1e4 if case % 2 else 3.0), C.c_float(0.01))
+            outs.append((ch, irc))
+        assert outs[0][0] == outs[1][0] and same_bits(outs[0][1], outs[1][1]).all()
+        expect_change = abs(s1 - 1) > thr * 1.001 or abs(s2 - 1) > thr * 1.001
+        if abs(abs(s1 - 1) - thr) > 1e-3 and abs(abs(s2 - 1) - thr) > 1e-3:
+            assert bool(outs[0][0]) == expect_change
+        if outs[0][0] and case % 2:          # alpha = 1: singular values of the new F sit on the dead-zone edge (or were inside it)
+            n_changed += 1
+            irn = outs[0][1].astype(np.float64)
+            irm = np.array([[irn[0], irn[2]], [irn[1], irn[3]]])
+            Ds = np.stack([x[1] - x[0], x[2] - x[0]], axis=1).astype(np.float64)
+            S = np.linalg.svd(Ds @ irm, compute_uv=False)
+            for sv, s_old in zip(sorted(S), sorted([s1, s2])):
+                want = s_old if abs(s_old - 1) <= thr else (1 - thr if s_old < 1 else 1 + thr)
+                assert abs(sv - want) < 2e-3, (S, s1, s2)
+    assert n_changed > 30
+    for _ in range(200):                      # rest angles
+        hx = rng.uniform(-1, 1, size=(4, 3)).astype(np.float32)
+        rest = float(rng.uniform(-0.5, 0.5))
+        a = o.orc_hinge_plasticity(fp(hx), C.c_float(rest), C.c_float(0.05), C.c_float(2.0), C.c_float(0.01))
+        c = b.orc_hinge_plasticity(fp(hx), C.c_float(rest), C.c_float(0.05), C.c_float(2.0), C.c_float(0.01))
+        assert same_bits(np.float32(a), np.float32(c))
+        sx = rng.uniform(-1, 1, size=(3, 3)).astype(np.float32)
+        a = o.orc_rod_bend_plasticity(fp(sx), C.c_float(np.pi), C.c_float(0.05), C.c_float(2.0), C.c_float(0.01))
+        c = b.orc_rod_bend_plasticity(fp(sx), C.c_float(np.pi), C.c_float(0.05), C.c_float(2.0), C.c_float(0.01))
+        assert same_bits(np.float32(a), np.float32(c))
+        e0, e1 = sx[0].astype(np.float64) - sx[1], sx[2].astype(np.float64) - sx[1]
+        theta = np.arccos(np.clip(e0 @ e1 / np.linalg.norm(e0) / np.linalg.norm(e1), -1, 1))
+        delta = theta - np.float32(np.pi)
+        alpha = 1 - np.exp(-2.0 * 0.01)
+        want = np.pi + (alpha * (delta - np.sign(delta) * 0.05) if abs(delta) > 0.05 else 0.0)
+        assert abs(a - want) < 1e-5

@@ -380,3 +380,13 @@ def test_shell_slot_and_transpose_tables_address_the_right_blocks(ppf):
             assert i < j and off[i] <= slot < off[i + 1] and col[slot] == j
             n_t += 1
     assert n_t == nnz - nv
+
+
+def test_oracle_plastic_sheet_keeps_its_deformation(run_job):
+    """membrane + bend plasticity (plasticity.cu): the run steps, and ends elsewhere than the elastic sheet"""
+    a = run_job({"lib": "oracle", "scene": "sheet", "n": 16, "state": None, "steps": 30})
+    p = run_job({"lib": "oracle", "scene": "sheet-plastic", "n": 16, "state": None, "steps": 30})
+    assert bool(a["ok"].all()) and bool(p["ok"].all()) and np.isfinite(p["curr"]).all()
+    assert float(np.abs(a["curr"] - p["curr"]).max()) > 1e-3
+    w = run_job({"lib": "oracle", "scene": "woven-plastic", "n": 32, "state": None, "steps": 6})
+    assert bool(w["ok"].all())

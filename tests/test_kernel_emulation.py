@@ -142,3 +142,33 @@ def test_emulated_max_sigma_diagnostic(emu, ppf):
     fixed = np.zeros(len(y0), bool); fixed[w.fix_targets()[0]] = True
     free = ~(fixed[edge[:, 0]] & fixed[edge[:, 1]])
     assert abs(emu.emu_max_sigma(b"woven", C.c_uint(32), fp(y)) - float((now / drawn)[free].max())) < 1e-5
+
+
+@pytest.mark.parametrize("scene,n,amp", [("sheet-plastic", 10, 2e-2), ("woven-plastic", 32, 5e-4)], ids=["sheet-plastic", "woven-plastic"])
+def test_emulated_plasticity_kernels_and_fetch_match_the_oracle(emu, ppf, scene, n, amp):
+    """k_plastic_face / k_plastic_hinge / k_plastic_rod_bend followed by the ABI's fetch_inv_rest / fetch_rest_angles
+    (plasticity.cu, main.cu:1939-1968) against the oracle's creep of the same deformed positions"""
+    s = ppf.Session(scene, n=n, lib=ppf.LIB_ORACLE)
+    x0, _ = s.fetch()
+    rng = np.random.default_rng(8)
+    x = (x0 + rng.normal(0, amp, size=x0.shape)).astype(np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    nv, nf, nh = s.n_vert, s.n_face, s.n_hinge
+    out = []
+    ora = C.CDLL(ppf.LIB_ORACLE)
+    for which in ("oracle", "emu"):
+        ir = np.zeros(4 * max(nf, 1), np.float32); hr = np.zeros(max(nh, 1), np.float32); vr = np.zeros(nv, np.float32)
+        if which == "oracle":
+            ora.oracle_plasticity(fp(x), fp(ir), fp(hr), fp(vr))
+        else:
+            emu.emu_plasticity(scene.encode(), C.c_uint(n), fp(x), fp(ir), fp(hr), fp(vr))
+        out.append((ir, hr, vr))
+    (ir0, hr0, vr0), (ir1, hr1, vr1) = out
+    assert np.allclose(ir0, ir1, rtol=1e-5, atol=1e-4) and np.allclose(hr0, hr1, atol=1e-6) and np.allclose(vr0, vr1, atol=1e-6)
+    if nf:
+        ir_rest = np.zeros_like(ir0); hr_r = np.zeros_like(hr0); vr_r = np.zeros_like(vr0)
+        emu.emu_plasticity(scene.encode(), C.c_uint(n), fp(np.ascontiguousarray(x0)), fp(ir_rest), fp(hr_r), fp(vr_r))   # undeformed: inside every dead zone
+        assert not hr_r.any()
+        assert float(np.abs(ir1 - ir_rest).max()) > 1e-3 * float(np.abs(ir_rest).max()) and (np.abs(hr0) > 1e-4).any()   # membranes and hinges really crept
+    else:
+        assert (np.abs(vr0 - np.float32(np.pi)) > 1e-5).any()                     # rod rest bend angles really crept
