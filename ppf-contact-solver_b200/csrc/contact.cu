@@ -38,6 +38,9 @@ __device__ __forceinline__ float sqr(float x) { return x * x; }
 
 // warp-cooperative slot allocation: every lane of a full warp calls this with its own k
 __device__ __forceinline__ unsigned warp_alloc(unsigned *counter, unsigned k) {
+#ifdef PPF_EMULATE // tests/native/emu runs the kernels one thread at a time on the host: there is no warp to cooperate with
+    return k ? atomicAdd(counter, k) : 0u;
+#endif
     const unsigned lane = threadIdx.x & 31;
     unsigned incl = k;
 #pragma unroll

@@ -22,7 +22,8 @@ CHANNELS = ("num_contact", "iter", "toi", "SL_toi", "SL_rod_toi", "newton_steps"
 def run(job):
     import ppf_b200
 
-    lib = {"ours": ppf_b200.LIB_OURS, "reference": ppf_b200.LIB_REF, "oracle": ppf_b200.LIB_ORACLE}[job["lib"]]
+    lib = {"ours": ppf_b200.LIB_OURS, "reference": ppf_b200.LIB_REF, "oracle": ppf_b200.LIB_ORACLE,
+           "emu": os.path.join(REPO, "tests", "native", "build", "emu", "libemu.so")}[job["lib"]]   # the backend's kernels run on the host (tests/test_kernel_emulation.py)
     out = job["out"]
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out, exist_ok=True)

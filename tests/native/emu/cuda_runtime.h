@@ -49,6 +49,21 @@ static inline unsigned atomicExch(unsigned *p, unsigned v) { const unsigned o = 
 static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }
 static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int) { return v; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned atomicMax(unsigned *p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
+static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { const unsigned o = *p; if (o == cmp) *p = v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline double atomicAdd(double *p, double v) { const double o = *p; *p = o + v; return o; }
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+static inline int __clz(int x) { return __clz((unsigned)x); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
+static inline void __threadfence() {}
+template <class T> static inline T __ldcg(const T *p) { return *p; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;

@@ -9,14 +9,13 @@
 
 PpfEmuDim blockIdx, blockDim, threadIdx;
 
-// ---- pieces of the backend that the two emulated files reference but that are not part of this check ----
+// ---- pieces of the backend that the emulated files reference but that are not part of this check ----
+// (csrc/step.cu and csrc/pcg.cu are not emulated: the PCG kernels stream the matrix with cp.async.bulk PTX)
 namespace ppf {
 void step_advance(State &, PpfStepResult *) {}
-void bvh_build(State &, Bvh &, int, const float4 *) {}
-void bvh_refit(State &, Bvh &, int, const float4 *, const float4 *, float) {}
-bool check_intersection(State &, const float4 *, const PpfParamSet &) { return true; }
-void build_fetch_pattern(State &, std::vector<unsigned> &, std::vector<unsigned> &) {}
 float reduce_max_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] > m ? d[i] : m; return m; }
+float reduce_min_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] < m ? d[i] : m; return m; }
+unsigned reduce_sum_u(State &, const unsigned *d, size_t n) { unsigned a = 0; for (size_t i = 0; i < n; ++i) a += d[i]; return a; }
 struct ScopeLog::Impl {};
 ScopeLog::ScopeLog(const char *) : impl(nullptr) {}
 ScopeLog::~ScopeLog() {}

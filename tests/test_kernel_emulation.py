@@ -1,7 +1,9 @@
 """Wiring check of the CUDA assembly kernels WITHOUT a GPU.
 
-The backend's own sources csrc/abi.cu (upload_dataset, the constraint kernels) and csrc/elastic.cu (k_momentum, k_face,
-k_face_iso, k_hinge, k_rod, k_rod_bend, k_rod_strain, k_damp_*, k_stitch, k_strainlimit) are rewritten for the host --
+The backend's own sources csrc/abi.cu (upload_dataset, the constraint kernels, the ABI entry points), csrc/elastic.cu
+(k_momentum, k_face, k_face_iso, k_hinge, k_rod, k_rod_bend, k_rod_strain, k_damp_*, k_stitch, k_strainlimit, k_plastic_*),
+csrc/bvh.cu (Morton LBVH build + refit) and csrc/contact.cu (broad / narrow phase, dynamic pattern, barrier fill, ACCD line
+search, colliders, intersection check) are rewritten for the host --
 every `kernel<<<grid, block, shmem, stream>>>(args)` becomes a serial loop over the threads, device memory becomes host
 memory (tests/native/emu/cuda_runtime.h) -- compiled by g++ and run on scenes built by the C++ host.  The assembled
 gradient, fixed-matrix blocks and diagonal blocks are compared with the oracle's assembly of the same positions.
@@ -66,14 +68,14 @@ def _rewrite_launches(src):
 def emu(built):
     os.makedirs(OUT, exist_ok=True)
     srcs = []
-    for f in ("abi.cu", "elastic.cu"):
+    for f in ("abi.cu", "elastic.cu", "bvh.cu", "contact.cu"):
         text = _rewrite_launches(open(os.path.join(CSRC, f)).read())
         assert "<<<" not in text
         p = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
         open(p, "w").write(text)
         srcs.append(p)
     lib = os.path.join(OUT, "libemu.so")
-    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off", "-w", "-I", EMU, "-I", CSRC, "-I", os.path.join(REPO, "include"),
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off", "-w", "-DPPF_EMULATE", "-I", EMU, "-I", CSRC, "-I", os.path.join(REPO, "include"),
            os.path.join(EMU, "emu_harness.cpp"), os.path.join(HOST, "scene.cpp"), os.path.join(HOST, "builder.cpp")] + srcs + ["-o", lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
@@ -172,3 +174,40 @@ def test_emulated_plasticity_kernels_and_fetch_match_the_oracle(emu, ppf, scene,
         assert float(np.abs(ir1 - ir_rest).max()) > 1e-3 * float(np.abs(ir_rest).max()) and (np.abs(hr0) > 1e-4).any()   # membranes and hinges really crept
     else:
         assert (np.abs(vr0 - np.float32(np.pi)) > 1e-5).any()                     # rod rest bend angles really crept
+
+
+from conftest import golden_cases  # noqa: E402
+
+_G = golden_cases()
+_PAIR_CASES = [c for c in _G if c[0] in ("fast_twist_n16", "five_twist_n24", "woven_n32", "drape_n32")][::2]   # hang has no self contact
+
+
+@pytest.mark.parametrize("case", _PAIR_CASES, ids=["%s-%s" % (c[0], os.path.basename(c[3])[6:11]) for c in _PAIR_CASES])
+def test_emulated_contact_detection_matches_the_oracle(emu, run_job, case):
+    """The emulated library is a complete ABI backend up to advance(): loaded by the C++ host like any other, it builds the
+    LBVHs (csrc/bvh.cu), runs the broad + narrow phase (csrc/contact.cu) at a contact-rich golden state and returns its sorted
+    pair lists.  Both sides compute without FMA contraction here, so every pair the oracle accepts robustly must be present
+    and nothing the oracle robustly rejects may appear; the reference's own count of that state is met up to the tie-decided pairs."""
+    import json
+
+    name, scene, n, state, refdir = case
+    g = run_job({"lib": "emu", "scene": scene, "n": n, "state": state, "steps": 0, "detect": "state", "detect_twice": True}, force_subprocess=True)
+    o = run_job({"lib": "oracle", "scene": scene, "n": n, "state": state, "steps": 0, "detect": "state"}, force_subprocess=True)
+    assert bool(g["state_repeat_equal"][0])
+    n_pairs = n_tie = 0
+    for k in range(4):
+        key = lambda p: (p[:, 0].astype(np.int64) << 32 | p[:, 1].astype(np.int64))
+        gk, ok, fk = key(g["state_pairs%d" % k]), key(o["state_pairs%d" % k]), key(o["state_fragile%d" % k])
+        assert (np.diff(gk) > 0).all()
+        missing = np.setdiff1d(np.setdiff1d(ok, fk), gk)
+        extra = np.setdiff1d(np.setdiff1d(gk, ok), fk)
+        assert missing.size == 0 and extra.size == 0, (k, missing[:4], extra[:4])
+        n_pairs += ok.size; n_tie += fk.size
+    assert n_pairs > (100 if scene != "drape" else 3)      # the draped sheet touches itself in a few places only
+    logs = json.load(open(os.path.join(refdir, "logs.json")))
+    analytic = 0
+    if scene == "drape":     # the reference's num_contact also counts sphere / floor contacts, which are no pairs
+        analytic = int(logs["num_contact"][0]) - int(g["state_total"][0])
+        assert 100 < analytic < 1000
+    # the reference ran on a GPU, where a*b+c contracts into FMAs: the handful of tie-decided pairs may fall the other way there
+    assert abs(int(g["state_total"][0]) + analytic - int(logs["num_contact"][0])) <= n_tie
