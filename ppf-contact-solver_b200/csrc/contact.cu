@@ -892,6 +892,10 @@ __global__ void __launch_bounds__(128) k_collider(unsigned nsv, const float4 *__
             }
         }
     }
+#ifdef PPF_EMULATE // tests/native/emu: one thread at a time, a shuffle returns the caller's own value (fine for min / max, not for sums)
+    if (count) atomicAdd(counter, count);
+    return;
+#endif
     for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
     if ((threadIdx.x & 31) == 0 && count) atomicAdd(counter, count);
 }

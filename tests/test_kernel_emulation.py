@@ -68,7 +68,7 @@ def _rewrite_launches(src):
 def emu(built):
     os.makedirs(OUT, exist_ok=True)
     srcs = []
-    for f in ("abi.cu", "elastic.cu", "bvh.cu", "contact.cu"):
+    for f in ("abi.cu", "elastic.cu", "bvh.cu", "contact.cu", "step.cu"):
         text = _rewrite_launches(open(os.path.join(CSRC, f)).read())
         assert "<<<" not in text
         p = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
@@ -76,7 +76,7 @@ def emu(built):
         srcs.append(p)
     lib = os.path.join(OUT, "libemu.so")
     cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-fvisibility=hidden", "-ffp-contract=off", "-w", "-DPPF_EMULATE", "-I", EMU, "-I", CSRC, "-I", os.path.join(REPO, "include"),
-           os.path.join(EMU, "emu_harness.cpp"), os.path.join(HOST, "scene.cpp"), os.path.join(HOST, "builder.cpp")] + srcs + ["-o", lib]
+           os.path.join(EMU, "emu_harness.cpp"), os.path.join(CSRC, "simplelog.cpp"), os.path.join(HOST, "scene.cpp"), os.path.join(HOST, "builder.cpp")] + srcs + ["-o", lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     l = C.CDLL(lib)
@@ -211,3 +211,69 @@ def test_emulated_contact_detection_matches_the_oracle(emu, run_job, case):
         assert 100 < analytic < 1000
     # the reference ran on a GPU, where a*b+c contracts into FMAs: the handful of tie-decided pairs may fall the other way there
     assert abs(int(g["state_total"][0]) + analytic - int(logs["num_contact"][0])) <= n_tie
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole steps: csrc/step.cu driving the emulated assembly / contact / line-search code, with a serial stand-in for the PCG
+# kernels (tests/native/emu/emu_harness.cpp), loaded through the ABI by the same C++ host as every other backend
+# ---------------------------------------------------------------------------------------------------------------------
+_STEP_CASES = _G[::2]
+
+
+@pytest.mark.parametrize("case", _STEP_CASES, ids=["%s-%s" % (c[0], os.path.basename(c[3])[6:11]) for c in _STEP_CASES])
+def test_emulated_step_reproduces_the_reference_golden(emu, run_job, case):
+    """One advance() from a golden state on the CPU: the backend's own step logic (Newton loop, assembly, contact detection,
+    dynamic pattern, ACCD + strain-limit + collider line searches, intersection check) against the output of the REFERENCE
+    (positions, per-iteration contact counts, line-search fractions, assembled first system).  Same bars as the gpu test of the
+    same name, except that tie-decided pairs follow the no-FMA resolution here."""
+    import json
+    import sys
+
+    sys.path.insert(0, os.path.join(REPO, "scripts"))
+    from compare_linsys import compare
+
+    name, scene, n, state, refdir = case
+    r = run_job({"lib": "emu", "scene": scene, "n": n, "state": state, "steps": 1, "dump_linsys": True}, force_subprocess=True)
+    assert bool(r["ok"].all())
+    logs = json.load(open(os.path.join(refdir, "logs.json")))
+    c = compare(os.path.join(refdir, "linsys_0.bin"), os.path.join(r["out_dir"], "linsys_0.bin"), verbose=False)
+    nb = c["n_blocks"][0]
+    assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
+    assert c["frac_blocks_off"] * nb <= 12 + 0.002 * nb, c
+    assert abs(r["log_num_contact"][0] - logs["num_contact"][0]) <= 2
+    assert len(r["log_num_contact"]) == len(logs["num_contact"])
+    for mine, theirs in zip(r["log_num_contact"], logs["num_contact"]):
+        assert abs(mine - theirs) <= 3 + 2e-3 * theirs
+    for mine, theirs in zip(r["log_toi"], logs["toi"]):
+        assert abs(mine - theirs) < 1e-2
+    for mine, theirs in zip(r["log_iter"], logs["iter"]):
+        assert abs(mine - theirs) <= 3 + 0.1 * theirs          # a different (double precision, serial) PCG: same rule, similar counts
+    ref = np.fromfile(os.path.join(refdir, "final_curr.bin"), dtype=np.float32).reshape(-1, 3)
+    d = np.abs(r["curr"] - ref).max(axis=1)
+    assert float(np.percentile(d, 90)) < 5e-5 and float(d.max()) < 5e-4, (float(np.percentile(d, 90)), float(d.max()))
+
+
+_LATE = [("headless", 24, os.path.join(REPO, "tests", "golden", "headless_n24", "state_00068.bin"), 1),
+         ("lift", 24, None, 30), ("sheet-arap", 24, None, 5), ("sheet-stvk", 24, None, 5), ("sheet-snhk", 24, None, 5),
+         ("sheet-damped", 24, None, 3), ("woven-damped", 32, None, 3), ("seam", 16, None, 4), ("sheet-plastic", 24, None, 6),
+         ("woven-plastic", 32, None, 2)]      # chained woven steps separate by their line-search cuts after ~3 steps, plastic or not
+
+
+@pytest.mark.parametrize("scene,n,state,steps", _LATE, ids=[c[0] for c in _LATE])
+def test_emulated_steps_of_the_late_features_match_the_oracle(emu, run_job, scene, n, state, steps):
+    """The features written after the GPU budget of round 1 was spent (fully pinned moving mesh, kinematic colliders, ARAP /
+    StVK / SNHk shells, Rayleigh damping, stitches, plasticity): whole steps of the backend's own code on the CPU against the
+    oracle -- the comparison tests/test_zz_gpu_headless.py makes on a GPU."""
+    job = {"scene": scene, "n": n, "state": state, "steps": steps}
+    g = run_job(dict(job, lib="emu"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    assert abs(len(g["log_iter"]) - len(o["log_iter"])) <= 1
+    assert abs(float(g["time"][0]) - float(o["time"][0])) <= 1e-3 * float(o["time"][0])
+    if len(o["log_num_contact"]) and o["log_num_contact"].max() > 0:
+        assert abs(g["log_num_contact"][0] - o["log_num_contact"][0]) <= 1
+        assert abs(g["log_num_contact"].max() - o["log_num_contact"].max()) <= 3 + 0.05 * o["log_num_contact"].max()
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    # the stitched sheet swings on stiff, length-capped seam springs: the 1e-3 stopping residual of two different PCGs shows more
+    med_bar, max_bar = (1e-4, 5e-3) if scene == "seam" else (2e-5, 2e-3)
+    assert float(np.median(d)) < med_bar and float(d.max()) < max_bar, (float(np.median(d)), float(d.max()))
