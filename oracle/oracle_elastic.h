@@ -369,6 +369,7 @@ static inline void o_symm2x2(float a00, float a01, float a11, float *val, float 
 }
 /* One face.  xe: evaluation positions, xc: start-of-step positions, Hel[a][b][9]: elastic-only blocks (column-major).
  * Outputs are already scaled by the stiffness; returns 0 when the face is not stretched. */
+static int o_barrier_kind = 0; /* ParamSet.barrier of the running scene (set by the oracle at initialize; 0 = cubic) */
 static inline int o_strain_face(const float (*xe)[3], const float (*xc)[3], const float *ir, float strainlimit, float limit, float mass,
                                 const float Hel[3][3][9], float eig_eps, float f[3][3], float H[3][3][9]) {
     float F[3][2];
@@ -382,8 +383,8 @@ static inline int o_strain_face(const float (*xe)[3], const float (*xc)[3], cons
     for (int i = 0; i < 2; ++i)
         if (S[i] > 0.0f) {
             const float y = strainlimit - S[i];
-            deda[i] = -o_cubic_gradient(y, strainlimit, 0.0f);
-            d2[i] = o_cubic_curvature(y, strainlimit, 0.0f);
+            deda[i] = -o_barrier_gradient(y, strainlimit, 0.0f, o_barrier_kind);
+            d2[i] = o_barrier_curvature(y, strainlimit, 0.0f, o_barrier_kind);
         }
     const float third = 1.0f / 3.0f;
     float w[3][3], wHw = 0.0f;
@@ -560,8 +561,8 @@ static inline int o_rod_strain(const float *x0, const float *x1, const float *c0
     const float g = l / l0 - 1.0f;
     if (!(g > 0.0f)) return 0;
     const float y = limit - g;
-    const float dEdg = -o_cubic_gradient(y, limit, 0.0f);
-    const float d2Edg2 = o_cubic_curvature(y, limit, 0.0f);
+    const float dEdg = -o_barrier_gradient(y, limit, 0.0f, o_barrier_kind);
+    const float d2Edg2 = o_barrier_curvature(y, limit, 0.0f, o_barrier_kind);
     const float n[3] = {d[0] / l, d[1] / l, d[2] / l};
     const float inv_ll0 = 1.0f / (l * l0);
     const float a_psd = fmaxf(0.0f, d2Edg2), b_psd = fmaxf(0.0f, dEdg);

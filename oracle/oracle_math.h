@@ -283,6 +283,24 @@ static inline int o_edge_triangle_intersect(const float *a0, const float *a1, co
 }
 
 
+/* the other two barriers of ParamSet.barrier (barrier/quadratic.hpp:13-41, barrier/logarithm.hpp:14-44); kind 0 cubic, 1 quad, 2 log */
+static inline float o_barrier_gradient(float g, float ghat, float offset, int kind) {
+    if (kind == 0) return o_cubic_gradient(g, ghat, offset);
+    g -= offset;
+    if (kind == 1) { const float y = ghat - g; return y > 0.0f ? -2.0f * y : 0.0f; }
+    if (g <= 0.0f) return -INFINITY;
+    if (g >= ghat) return 0.0f;
+    return (ghat - g) * (2.0f * g * logf(g / ghat) + g - ghat) / g;
+}
+static inline float o_barrier_curvature(float g, float ghat, float offset, int kind) {
+    if (kind == 0) return o_cubic_curvature(g, ghat, offset);
+    g -= offset;
+    if (kind == 1) return (ghat - g > 0.0f) ? 2.0f : 0.0f;
+    if (g <= 0.0f) return INFINITY;
+    if (g >= ghat) return 0.0f;
+    return -2.0f * logf(g / ghat) + ghat * (ghat + 2.0f * g) / (g * g) - 3.0f;
+}
+
 /* ---- lagged Coulomb friction (energy/model/friction.hpp:19-82): gradient and Hessian to ADD to the contact's ---- */
 static inline float o_friction(const float *force_contact, const float *dx, const float *normal, float mu, float min_dx, float *grad, float *hess /* column-major 3x3 */) {
     const float contact = -o_dot(normal, force_contact), nd = o_dot(normal, dx);

@@ -144,3 +144,6 @@ SHIM float orc_hinge_plasticity(const float *x12, float rest, float threshold, f
 SHIM float orc_rod_bend_plasticity(const float *x9, float rest, float threshold, float rate, float dt) {
     return o_rod_bend_plasticity(x9, x9 + 3, x9 + 6, rest, threshold, o_plastic_alpha(rate, dt));
 }
+
+/* barrier gradient / curvature of ParamSet.barrier (0 cubic, 1 quad, 2 log) */
+SHIM void orc_barrier(int kind, float g, float ghat, float offset, float *out2) { out2[0] = o_barrier_gradient(g, ghat, offset, kind); out2[1] = o_barrier_curvature(g, ghat, offset, kind); }

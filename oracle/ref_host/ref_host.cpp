@@ -20,6 +20,8 @@ using std::isfinite;
 #include "contact/accd.hpp"
 #include "contact/intersect_core.hpp"
 #include "barrier/cubic.hpp"
+#include "barrier/quadratic.hpp"
+#include "barrier/logarithm.hpp"
 #include "energy/model/friction.hpp"
 #include "energy/model/baraffwitkin.hpp"
 #include "energy/model/dihedral_angle.hpp"
@@ -171,5 +173,11 @@ void ref_iso_table2(int model, const float *a2, float mu, float lmd, float *out5
     Vec2f a(a2[0], a2[1]);
     DiffTable2 t = model == 0 ? ARAP::make_diff_table2(a, mu, lmd) : (model == 1 ? StVK::make_diff_table2(a, mu, lmd) : SNHk::make_diff_table2(a, mu, lmd));
     out5[0] = t.deda[0]; out5[1] = t.deda[1]; out5[2] = t.d2ed2a(0, 0); out5[3] = t.d2ed2a(0, 1); out5[4] = t.d2ed2a(1, 1);
+}
+// the three barriers of ParamSet.barrier: kind 0 cubic, 1 quad, 2 log -> gradient, curvature
+void ref_barrier(int kind, float g, float ghat, float offset, float *out2) {
+    if (kind == 0) { out2[0] = cubic::gradient(g, ghat, offset); out2[1] = cubic::curvature(g, ghat, offset); }
+    else if (kind == 1) { out2[0] = quadratic::gradient(g, ghat, offset); out2[1] = quadratic::curvature(g, ghat, offset); }
+    else { out2[0] = logarithm::gradient(g, ghat, offset); out2[1] = logarithm::curvature(g, ghat, offset); }
 }
 }

@@ -139,7 +139,6 @@ void upload_dataset(State &s) {
     if (d.translation_lock.size) fatal(4, "B200 backend: translation/rotation locks are not implemented");
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
         if (d.grain_inv_inertia.data[i] > 0.0f) fatal(4, "B200 backend: SAND grains are not implemented");
-    if (prm.barrier != PPF_BARRIER_CUBIC) fatal(4, "B200 backend: only the cubic barrier is implemented");
     if (nf != d.shell_face_count || s.nsv != nv) fatal(4, "B200 backend: solid (tet) surfaces and interior vertices are not implemented (shell faces and rods only)");
     if (prm.fix_xz != 0.0f) fatal(4, "B200 backend: fix-xz is not implemented");
     for (unsigned i = 0; i < d.param_arrays.face.size; ++i) {

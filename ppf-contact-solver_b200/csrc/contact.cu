@@ -226,6 +226,7 @@ struct Ctx {
     const unsigned *vf_off, *vf_idx, *ve_off, *ve_idx, *ef_off, *ef_idx;
     int friction_mode;
     float friction_eps;
+    int barrier; // ParamSet.barrier: 0 cubic, 1 quad, 2 log
     // matrices
     const unsigned *fx_off, *fx_col;
     const float *fx_el; // elastic-only snapshot
@@ -504,8 +505,8 @@ template <int N> __device__ __forceinline__ void embed_contact(const Ctx &c, con
             kappa += (ii == jj) ? t : 2.0f * t;
         }
     }
-    V3 f = kappa * barrier_edge_gradient(ex, pr.ghat, pr.offset);
-    M3 H = kappa * barrier_edge_hessian(ex, pr.ghat, pr.offset);
+    V3 f = kappa * barrier_edge_gradient(ex, pr.ghat, pr.offset, c.barrier);
+    M3 H = kappa * barrier_edge_hessian(ex, pr.ghat, pr.offset, c.barrier);
     if (pr.include_friction) {
         const FrictionOut fr = friction_eval(f, dxs, normal, pr.friction, c.friction_eps);
         f += fr.grad;
@@ -556,7 +557,7 @@ static Ctx make_ctx(State &s, const PpfParamSet &prm) {
     c.face = s.face.p; c.edge = s.edge.p;
     c.vfixed = s.vfixed.p; c.efixed = s.efixed.p; c.ffixed = s.ffixed.p; c.vcollider = s.vcollider.p;
     c.vf_off = s.vf_off.p; c.vf_idx = s.vf_idx.p; c.ve_off = s.ve_off.p; c.ve_idx = s.ve_idx.p; c.ef_off = s.ef_off.p; c.ef_idx = s.ef_idx.p;
-    c.friction_mode = (int)prm.friction_mode; c.friction_eps = prm.friction_eps;
+    c.friction_mode = (int)prm.friction_mode; c.friction_eps = prm.friction_eps; c.barrier = (int)prm.barrier;
     c.fx_off = s.fx_off.p; c.fx_col = s.fx_col.p; c.fx_el = s.fx_el.p; c.fx_val = s.fx_val.p;
     c.dyn_off = s.dyn_off.p; c.dyn_col = s.dyn_col.p; c.dyn_val = s.dyn_val.p;
     c.force = s.force.p;

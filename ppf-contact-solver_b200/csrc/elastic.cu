@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(128) k_strainlimit(unsigned nf, const uint4 *_
                                                      const float2 *__restrict__ fstrain, const float4 *__restrict__ inv_rest,
                                                      const unsigned char *__restrict__ ffixed, const unsigned char *__restrict__ fskip,
                                                      const unsigned *__restrict__ fx_off, const unsigned *__restrict__ fx_col,
-                                                     const float *__restrict__ fx_el, const unsigned *__restrict__ slots, float eig_eps,
+                                                     const float *__restrict__ fx_el, const unsigned *__restrict__ slots, float eig_eps, int barrier,
                                                      float *__restrict__ force, float *__restrict__ val) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nf || ffixed[i] || fskip[i]) return;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128) k_strainlimit(unsigned nf, const uint4 *_
             Hel[a][b] = m;
         }
     StrainFace sf;
-    if (!strain_face(xe, xc, irv, sl2.x, sl2.y, fmat[i].z, Hel, eig_eps, sf)) return;
+    if (!strain_face(xe, xc, irv, sl2.x, sl2.y, fmat[i].z, Hel, eig_eps, sf, barrier)) return;
     for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], sf.f[a]);
     const unsigned *sl = slots + size_t(9) * i;
     for (int a = 0; a < 3; ++a)
@@ -533,7 +533,7 @@ __device__ __forceinline__ M3 ld_block(const float *__restrict__ val, unsigned s
 __global__ void __launch_bounds__(128) k_rod_strain(unsigned nrod, const uint2 *__restrict__ edge, const float4 *__restrict__ eval_x,
                                                     const float4 *__restrict__ curr, const float2 *__restrict__ rod_sl,
                                                     const float4 *__restrict__ ecp, const unsigned char *__restrict__ efixed,
-                                                    const unsigned *__restrict__ slots, const float *__restrict__ fx_el,
+                                                    const unsigned *__restrict__ slots, const float *__restrict__ fx_el, int barrier,
                                                     float *__restrict__ force, float *__restrict__ val) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrod || efixed[i]) return;
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(128) k_rod_strain(unsigned nrod, const uint2 *
     const M3 H00 = ld_block(fx_el, sl[0]), H11 = ld_block(fx_el, sl[3]);
     const M3 H01 = sl[1] != 0xFFFFFFFFu ? ld_block(fx_el, sl[1]) : transpose(ld_block(fx_el, sl[2]));
     RodElastic re;
-    if (!rod_strain(x0, x1, ld3(curr, e.x), ld3(curr, e.y), sl2.y, sl2.x, ecp[i].w, H00, H01, H11, re)) return;
+    if (!rod_strain(x0, x1, ld3(curr, e.x), ld3(curr, e.y), sl2.y, sl2.x, ecp[i].w, H00, H01, H11, re, barrier)) return;
     atomic_add3(force + size_t(3) * e.x, re.f[0]);
     atomic_add3(force + size_t(3) * e.y, re.f[1]);
     float neg[9];
@@ -576,12 +576,12 @@ __global__ void __launch_bounds__(128) k_rod_strain_toi(unsigned nrod, const uin
 void assemble_strainlimit(State &s, const PpfParamSet &prm) {
     if (s.has_strainlimit && s.nf) {
         k_strainlimit<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.curr.p, s.fmat.p, s.fstrain.p, s.inv_rest.p, s.ffixed.p, s.fskip.p,
-                                                               s.fx_off.p, s.fx_col.p, s.fx_el.p, s.face_slots.p, prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+                                                               s.fx_off.p, s.fx_col.p, s.fx_el.p, s.face_slots.p, prm.eiganalysis_eps, (int)prm.barrier, s.force.p, s.fx_val.p);
         LAUNCH_COUNT(1);
     }
     if (s.has_rod_strainlimit && s.nrod) {
         k_rod_strain<<<div_up(s.nrod, 128), 128, 0, s.stream>>>(s.nrod, s.edge.p, s.eval_x.p, s.curr.p, s.rod_sl.p, s.ecp.p, s.efixed.p, s.rod_slots.p,
-                                                                s.fx_el.p, s.force.p, s.fx_val.p);
+                                                                s.fx_el.p, (int)prm.barrier, s.force.p, s.fx_val.p);
         LAUNCH_COUNT(1);
     }
 }

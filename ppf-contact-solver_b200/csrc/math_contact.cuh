@@ -21,13 +21,41 @@ PPF_HD float cubic_curvature(float g, float ghat, float offset) {
     g -= offset;
     return (g - ghat < 0.0f) ? 4.0f * (1.0f - g / ghat) : 0.0f;
 }
-PPF_HD V3 barrier_edge_gradient(const V3 &e, float ghat, float offset) {
+// the other two barriers of ParamSet.barrier (barrier/quadratic.hpp:13-41, barrier/logarithm.hpp:14-44); kind = the ABI's
+// Barrier enum (0 cubic, 1 quad, 2 log).  The log barrier uses the fast intrinsic on the device like the reference's fmath::log.
+PPF_HD float fast_log(float x) {
+#if defined(__CUDA_ARCH__)
+    return __logf(x);
+#else
+    return logf(x);
+#endif
+}
+PPF_HD float barrier_gradient(float g, float ghat, float offset, int kind) {
+    if (kind == 0) return cubic_gradient(g, ghat, offset);
+    g -= offset;
+    if (kind == 1) {
+        const float y = ghat - g;
+        return y > 0.0f ? -2.0f * y : 0.0f;
+    }
+    if (g <= 0.0f) return -INFINITY;
+    if (g >= ghat) return 0.0f;
+    return (ghat - g) * (2.0f * g * fast_log(g / ghat) + g - ghat) / g;
+}
+PPF_HD float barrier_curvature(float g, float ghat, float offset, int kind) {
+    if (kind == 0) return cubic_curvature(g, ghat, offset);
+    g -= offset;
+    if (kind == 1) return (ghat - g > 0.0f) ? 2.0f : 0.0f;
+    if (g <= 0.0f) return INFINITY;
+    if (g >= ghat) return 0.0f;
+    return -2.0f * fast_log(g / ghat) + ghat * (ghat + 2.0f * g) / (g * g) - 3.0f;
+}
+PPF_HD V3 barrier_edge_gradient(const V3 &e, float ghat, float offset, int kind = 0) {
     const float g = norm(e);
     const V3 n = e / g;
-    return n * cubic_gradient(g, ghat, offset);
+    return n * barrier_gradient(g, ghat, offset, kind);
 }
-PPF_HD M3 barrier_edge_hessian(const V3 &e, float ghat, float offset) {
-    const float c = cubic_curvature(norm(e), ghat, offset);
+PPF_HD M3 barrier_edge_hessian(const V3 &e, float ghat, float offset, int kind = 0) {
+    const float c = barrier_curvature(norm(e), ghat, offset, kind);
     // c * e * e^T / |e|^2  evaluated left to right: ((c*e) e^T) / sq
     const V3 ce = c * e;
     const float sq = sqnorm(e);

@@ -138,14 +138,14 @@ PPF_HD float rod_bend_coefficient(float bend0, float bend1, float len0, float le
 // blocks (e0,e0), (e0,e1), (e1,e1) of the elastic-only matrix (FixedCSRMat::operator(), transposed when stored as (e1,e0));
 // c0, c1 are the start-of-step positions the stiffness is evaluated at.  Returns false when the edge is not stretched.
 PPF_HD bool rod_strain(const V3 &x0, const V3 &x1, const V3 &c0, const V3 &c1, float l0, float limit, float mass, const M3 &Hel00,
-                       const M3 &Hel01, const M3 &Hel11, RodElastic &o) {
+                       const M3 &Hel01, const M3 &Hel11, RodElastic &o, int barrier = 0) {
     const V3 d = x1 - x0;
     const float l = norm(d);
     const float g = l / l0 - 1.0f;
     if (!(g > 0.0f)) return false;
     const float y = limit - g;
-    const float dEdg = -cubic_gradient(y, limit, 0.0f);
-    const float d2Edg2 = cubic_curvature(y, limit, 0.0f);
+    const float dEdg = -barrier_gradient(y, limit, 0.0f, barrier);
+    const float d2Edg2 = barrier_curvature(y, limit, 0.0f, barrier);
     const V3 n = d / l;
     const float inv_ll0 = 1.0f / (l * l0);
     const float a_psd = fmaxf(0.0f, d2Edg2);

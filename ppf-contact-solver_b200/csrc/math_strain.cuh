@@ -136,7 +136,7 @@ struct StrainFace {
 //   Hel[a][b]: block (a, b) of the elastic-only fixed matrix for the face's vertices.
 // Returns false when the face is not stretched (largest strain <= 0): nothing to add.
 PPF_HD bool strain_face(const V3 *xe, const V3 *xc, const float *ir, float strainlimit, float limit, float mass, const M3 Hel[3][3],
-                        float eig_eps, StrainFace &out) {
+                        float eig_eps, StrainFace &out, int barrier = 0) {
     float F[3][2];
     deformation_grad32(xe[0], xe[1], xe[2], ir, F);
     Svd32 svd;
@@ -150,8 +150,8 @@ PPF_HD bool strain_face(const V3 *xe, const V3 *xc, const float *ir, float strai
         const float g = S[i];
         if (g > 0.0f) {
             const float y = strainlimit - g;
-            deda[i] = -cubic_gradient(y, strainlimit, 0.0f);
-            d2[i] = cubic_curvature(y, strainlimit, 0.0f);
+            deda[i] = -barrier_gradient(y, strainlimit, 0.0f, barrier);
+            d2[i] = barrier_curvature(y, strainlimit, 0.0f, barrier);
         }
     }
     // stiffness (strainlimiting.cu:22-44): w = start-of-step positions relative to their centroid

@@ -256,6 +256,16 @@ static SceneSpec twist_scene(const std::string &name, double r, double half_len,
 }
 
 SceneSpec make_scene(const std::string &name, unsigned n) {
+    // "<scene>@quad" / "<scene>@log": the same scene with the quadratic / logarithmic barrier (param.rs Barrier, ParamSet.barrier)
+    for (const char *suffix : {"@quad", "@log", "@cubic"}) {
+        const std::string sfx = suffix;
+        if (name.size() > sfx.size() && name.compare(name.size() - sfx.size(), sfx.size(), sfx) == 0) {
+            SceneSpec s = make_scene(name.substr(0, name.size() - sfx.size()), n);
+            s.name = name;
+            s.args.barrier = sfx.substr(1);
+            return s;
+        }
+    }
     if (name == "twist") // examples/twist.ipynb
         return twist_scene(name, 0.5, 1.0, n ? n : 360, 500.0, 4e-3, 1e4, 0.35, 1.0, 360.0, 0.2, 10.0, 0.01, 35000000u, "min", 430);
     if (name == "large-twist") // examples/large-twist.ipynb (headline)

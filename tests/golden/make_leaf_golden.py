@@ -130,6 +130,13 @@ def main():
     for i in range(nt):
         ref.ref_iso_table2(C.c_int(int(tmodel[i])), fp(ta[i]), C.c_float(tmu[i]), C.c_float(tl[i]), fp(tt[i]))
     out.update(iso_a=ta, iso_model=tmodel, iso_mu=tmu, iso_lmd=tl, iso_table=tt)
+    # ---- quadratic and logarithmic barriers (barrier/quadratic.hpp, barrier/logarithm.hpp) ----
+    bg = np.concatenate([rng.uniform(1e-5, 2.4e-3, 1500), [2e-4, 1.2e-3, 1.3e-3]]).astype(np.float32)
+    bk = rng.integers(1, 3, size=len(bg)).astype(np.int32)
+    bo = np.zeros((len(bg), 2), np.float32)
+    for i in range(len(bg)):
+        ref.ref_barrier(C.c_int(int(bk[i])), C.c_float(bg[i]), C.c_float(1e-3), C.c_float(2e-4), fp(bo[i]))
+    out.update(barrier_g=bg, barrier_kind=bk, barrier_out=bo)
     path = os.path.join(REPO, "tests", "golden", "leaf_math.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -193,3 +193,5 @@ SHIM float orc_hinge_plasticity(const float *x12, float rest, float threshold, f
 SHIM float orc_rod_bend_plasticity(const float *x9, float rest, float threshold, float rate, float dt) {
     return rod_bend_plasticity(v(x9), v(x9 + 3), v(x9 + 6), rest, threshold, plastic_alpha(rate, dt));
 }
+
+SHIM void orc_barrier(int kind, float g, float ghat, float offset, float *out2) { out2[0] = barrier_gradient(g, ghat, offset, kind); out2[1] = barrier_curvature(g, ghat, offset, kind); }

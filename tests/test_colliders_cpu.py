@@ -330,3 +330,42 @@ def test_plastic_creep_oracle_equals_backend_header_and_relaxes_toward_the_dead_
         alpha = 1 - np.exp(-2.0 * 0.01)
         want = np.pi + (alpha * (delta - np.sign(delta) * 0.05) if abs(delta) > 0.05 else 0.0)
         assert abs(a - want) < 1e-5
+
+
+def test_quadratic_and_logarithmic_barriers_bit_exact(libs, built):
+    """ParamSet.barrier = quad / log (barrier/quadratic.hpp:13-41, barrier/logarithm.hpp:14-44): gradient and curvature of
+    the oracle and of the backend header against vectors produced by the reference's own headers (tests/golden/leaf_math.npz),
+    bit for bit (the host build of the reference takes std::log, as do both restatements when compiled for the host)."""
+    o, b = libs
+    gold = np.load(os.path.join(REPO, "tests", "golden", "leaf_math.npz"))
+    g, kind, want = gold["barrier_g"], gold["barrier_kind"], gold["barrier_out"]
+    assert set(kind.tolist()) == {1, 2} and np.isinf(want).any() and (want == 0).any()
+    for l in (o, b):
+        got = np.zeros_like(want)
+        for i in range(len(g)):
+            l.orc_barrier(C.c_int(int(kind[i])), C.c_float(g[i]), C.c_float(1e-3), C.c_float(2e-4), fp(got[i]))
+        assert same_bits(got, want).all()
+    # kind 0 is the cubic barrier of the existing vectors
+    out = np.zeros(2, np.float32)
+    o.orc_barrier(C.c_int(0), C.c_float(5e-4), C.c_float(1e-3), C.c_float(0.0), fp(out))
+    ref = np.zeros(2, np.float32)
+    b.orc_barrier(C.c_int(0), C.c_float(5e-4), C.c_float(1e-3), C.c_float(0.0), fp(ref))
+    assert same_bits(out, ref).all() and out[0] < 0 < out[1]
+    # the gradient is the derivative of the energy: quad (ghat - g)^2, log -(g - ghat)^2 log(g / ghat)
+    for k, energy in ((1, lambda x: (1e-3 - x) ** 2), (2, lambda x: -(x - 1e-3) ** 2 * np.log(x / 1e-3))):
+        for x in (2e-4, 5e-4, 9e-4):
+            o.orc_barrier(C.c_int(k), C.c_float(x), C.c_float(1e-3), C.c_float(0.0), fp(out))
+            h = 1e-7
+            assert abs(out[0] - (energy(x + h) - energy(x - h)) / (2 * h)) < 2e-3 * abs(out[0]) + 1e-9
+            assert abs(out[1] - (energy(x + h) - 2 * energy(x) + energy(x - h)) / h ** 2) < 2e-2 * abs(out[1]) + 1e-6
+
+
+@pytest.mark.parametrize("kind", ["quad", "log"])
+def test_oracle_runs_the_twist_with_the_other_barriers(run_job, kind):
+    """the contact-rich fast twist with ParamSet.barrier = quad / log: the step converges, contacts are found and the
+    result stays free of intersections (the step's own final check) while differing from the cubic-barrier run"""
+    r = run_job({"lib": "oracle", "scene": "fast-twist@" + kind, "n": 12, "state": None, "steps": 30}, force_subprocess=True)
+    c = run_job({"lib": "oracle", "scene": "fast-twist", "n": 12, "state": None, "steps": 30}, force_subprocess=True)
+    assert r["ok"].all() and np.asarray(r["log_num_contact"]).max() > 0
+    assert np.isfinite(r["curr"]).all()
+    assert not np.array_equal(r["curr"], c["curr"])

@@ -277,3 +277,38 @@ def test_emulated_steps_of_the_late_features_match_the_oracle(emu, run_job, scen
     # the stitched sheet swings on stiff, length-capped seam springs: the 1e-3 stopping residual of two different PCGs shows more
     med_bar, max_bar = (1e-4, 5e-3) if scene == "seam" else (2e-5, 2e-3)
     assert float(np.median(d)) < med_bar and float(d.max()) < max_bar, (float(np.median(d)), float(d.max()))
+
+
+_BARRIER = [("fast-twist", 16, os.path.join(REPO, "tests", "golden", "fast_twist_n16", "state_00060.bin")),
+            ("woven-sl", 32, os.path.join(REPO, "tests", "golden", "woven_sl_n32", "state_00080.bin"))]
+
+
+@pytest.mark.parametrize("kind", ["quad", "log"])
+@pytest.mark.parametrize("scene,n,state", _BARRIER, ids=[c[0] for c in _BARRIER])
+def test_emulated_steps_with_the_quadratic_and_logarithmic_barriers(emu, run_job, scene, n, state, kind):
+    """ParamSet.barrier = quad / log (barrier/barrier.cu dispatch): one step from a contact-rich (twist) / strain-limited
+    (woven-sl) saved state; the first assembled system and the per-iteration contact counts against the oracle, positions
+    within the bar of two different PCGs on the (stiffer, for quad) system."""
+    import sys
+
+    sys.path.insert(0, os.path.join(REPO, "scripts"))
+    from compare_linsys import compare
+
+    job = {"scene": "%s@%s" % (scene, kind), "n": n, "state": state, "steps": 1, "dump_linsys": True}
+    g = run_job(dict(job, lib="emu"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    base = run_job(dict(job, scene=scene, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    nb = c["n_blocks"][0]
+    assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
+    assert c["frac_blocks_off"] * nb <= 12 + 0.002 * nb, c
+    # the barrier really is a different one: the first system differs from the cubic run's
+    cb = compare(os.path.join(base["out_dir"], "linsys_0.bin"), os.path.join(o["out_dir"], "linsys_0.bin"), verbose=False)
+    assert cb["frac_blocks_off"] * nb > 50, cb
+    assert len(g["log_iter"]) == len(o["log_iter"])
+    assert g["log_num_contact"][0] == o["log_num_contact"][0]
+    for mine, theirs in zip(g["log_num_contact"], o["log_num_contact"]):
+        assert abs(mine - theirs) <= 3 + 2e-3 * theirs
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 1e-4 and float(d.max()) < 3e-3, (float(np.median(d)), float(d.max()))

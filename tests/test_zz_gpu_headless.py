@@ -140,3 +140,27 @@ def test_plasticity_matches_the_oracle(run_job, scene, n):
     u = run_job({"lib": "oracle", "scene": base, "n": n, "state": None, "steps": steps}, force_subprocess=True)
     if abs(float(u["time"][0]) - float(o["time"][0])) < 1e-9:           # same clock: the plastic run must be the closer one
         assert float(np.median(np.abs(g["curr"] - u["curr"]).max(axis=1))) > float(np.median(d))
+
+
+_BARRIER = [("fast-twist", 16, os.path.join(REPO, "tests", "golden", "fast_twist_n16", "state_00060.bin")),
+            ("woven-sl", 32, os.path.join(REPO, "tests", "golden", "woven_sl_n32", "state_00080.bin"))]
+
+
+@pytest.mark.parametrize("kind", ["quad", "log"])
+@pytest.mark.parametrize("scene,n,state", _BARRIER, ids=[c[0] for c in _BARRIER])
+def test_quadratic_and_logarithmic_barriers_match_the_oracle(run_job, scene, n, state, kind):
+    """ParamSet.barrier = quad / log (barrier/quadratic.hpp, barrier/logarithm.hpp; dispatch barrier/barrier.cu): one step
+    from a contact-rich (twist) / strain-limited (woven-sl) saved state against the CPU oracle -- first assembled system,
+    contact counts, positions (the device takes __logf where the host takes logf: inside the 2e-4 block bar)."""
+    job = {"scene": "%s@%s" % (scene, kind), "n": n, "state": state, "steps": 1, "dump_linsys": True}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    nb = c["n_blocks"][0]
+    assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
+    assert c["frac_blocks_off"] * nb <= 12 + 0.002 * nb, c
+    assert abs(len(g["log_iter"]) - len(o["log_iter"])) <= 1
+    assert abs(g["log_num_contact"][0] - o["log_num_contact"][0]) <= 2
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 1e-4 and float(d.max()) < 3e-3, (float(np.median(d)), float(d.max()))
