@@ -140,7 +140,6 @@ void upload_dataset(State &s) {
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
         if (d.grain_inv_inertia.data[i] > 0.0f) fatal(4, "B200 backend: SAND grains are not implemented");
     if (nf != d.shell_face_count || s.nsv != nv) fatal(4, "B200 backend: solid (tet) surfaces and interior vertices are not implemented (shell faces and rods only)");
-    if (prm.fix_xz != 0.0f) fatal(4, "B200 backend: fix-xz is not implemented");
     for (unsigned i = 0; i < d.param_arrays.face.size; ++i) {
         const PpfFaceParam &fp = d.param_arrays.face.data[i];
         if (fp.model != PPF_MODEL_BARAFFWITKIN && fp.model != PPF_MODEL_ARAP && fp.model != PPF_MODEL_STVK && fp.model != PPF_MODEL_SNHK)

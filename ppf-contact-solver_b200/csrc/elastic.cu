@@ -33,7 +33,7 @@ __device__ __forceinline__ void atomic_add_block(float *val, unsigned slot, cons
 }
 
 struct MomentumArgs {
-    float dt, air_density, air_friction, iso_air, wind_w;
+    float dt, air_density, air_friction, iso_air, wind_w, fix_xz;
     float3 wind;
     int inactive_momentum;
 };
@@ -81,6 +81,13 @@ __global__ void k_momentum(unsigned nv, const float4 *__restrict__ curr, const f
     if (a.iso_air) {
         f += (a.iso_air * idt2) * (y - x);
         H += (a.iso_air * idt2) * m3_identity();
+    }
+    if (a.fix_xz && y.y > a.fix_xz) { // ParamSet.fix_xz: drag on the horizontal motion above the height fix_xz (energy.cu:260-266)
+        const float tm = fminf(1.0f, y.y - a.fix_xz) * mass;
+        f.x += (tm * (y.x - x.x)) / (a.dt * a.dt);
+        f.z += (tm * (y.z - x.z)) / (a.dt * a.dt);
+        H.m[0] += tm * (a.dt * a.dt);
+        H.m[8] += tm * (a.dt * a.dt);
     }
     float *fo = force + size_t(3) * i; // one thread owns vertex i in this kernel
     fo[0] += f.x; fo[1] += f.y; fo[2] += f.z;
@@ -671,7 +678,7 @@ float max_stretch_ratio(State &s) {
 
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
     MomentumArgs a;
-    a.dt = dt; a.air_density = prm.air_density; a.air_friction = prm.air_friction; a.iso_air = prm.isotropic_air_friction;
+    a.dt = dt; a.air_density = prm.air_density; a.air_friction = prm.air_friction; a.iso_air = prm.isotropic_air_friction; a.fix_xz = prm.fix_xz;
     a.wind = make_float3(prm.wind.v[0], prm.wind.v[1], prm.wind.v[2]);
     a.inactive_momentum = prm.inactive_momentum;
     { // utility.cu get_wind_weight (float time)

@@ -74,6 +74,21 @@ __global__ void k_apply_dx(unsigned n, float4 *eval_x, float4 *x_old, const floa
     eval_x[i] = make_float4(e.x - (toi_recale * dx[3 * size_t(i)]), e.y - (toi_recale * dx[3 * size_t(i) + 1]), e.z - (toi_recale * dx[3 * size_t(i) + 2]), 0.f);
 }
 
+// ParamSet.fix_xz: above the height fix_xz the horizontal part of the Newton update is pulled back toward the start-of-step
+// position, fully from one unit above (main.cu:1190-1208); prescribed (DOF-removed) vertices keep their keyframe
+__global__ void k_fix_xz(unsigned n, float4 *eval_x, const float4 *curr, const unsigned *fix_index, float fix_xz) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || fix_index[i] != 0) return;
+    float4 e = eval_x[i];
+    if (e.y > fix_xz) {
+        const float y = fminf(1.0f, e.y - fix_xz);
+        const float4 z = curr[i];
+        e.x -= y * (e.x - z.x);
+        e.z -= y * (e.z - z.z);
+        eval_x[i] = e;
+    }
+}
+
 __global__ void k_lerp(unsigned n, float4 *eval_x, const float4 *x_old, float toi) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -287,6 +302,10 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.mark("toi_recale", toi_recale);
         k_apply_dx<<<gv, 256, 0, q>>>(nv, s.eval_x.p, s.x_old.p, s.dx.p, toi_recale);
         LAUNCH_COUNT(1);
+        if (prm.fix_xz) {
+            k_fix_xz<<<gv, 256, 0, q>>>(nv, s.eval_x.p, s.curr.p, s.fix_index.p, prm.fix_xz);
+            LAUNCH_COUNT(1);
+        }
 
         float toi = 1.0f;
         if (!prm.disable_contact) {

@@ -653,7 +653,7 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         return s;
     }
     if (name == "sheet" || name == "sheet-arap" || name == "sheet-stvk" || name == "sheet-snhk" || name == "sheet-damped" || name == "sheet-arap-damped" ||
-        name == "sheet-plastic") { // free-hanging sheet without strain limit: elastic-only smoke scene (the suffix selects the shell model)
+        name == "sheet-plastic" || name == "sheet-fixxz") { // free-hanging sheet without strain limit: elastic-only smoke scene (the suffix selects the shell model)
         SceneSpec s;
         s.name = name;
         ShellObject o;
@@ -675,6 +675,7 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.objects.push_back(o);
         s.args.frames = 60;
         s.args.dt = 1e-2;
+        if (name == "sheet-fixxz") s.args.fix_xz = -0.4; // horizontal drag on everything higher than y = -0.4 (ParamSet.fix_xz)
         return s;
     }
     throw std::runtime_error("unknown scene: " + name);

@@ -390,3 +390,18 @@ def test_oracle_plastic_sheet_keeps_its_deformation(run_job):
     assert float(np.abs(a["curr"] - p["curr"]).max()) > 1e-3
     w = run_job({"lib": "oracle", "scene": "woven-plastic", "n": 32, "state": None, "steps": 6})
     assert bool(w["ok"].all())
+
+
+def test_fix_xz_drags_the_horizontal_motion_above_the_threshold(run_job):
+    """ParamSet.fix_xz (energy.cu:260-266, main.cu:1190-1208): the swinging sheet with a horizontal drag above y = -0.4 --
+    vertices that stay above the threshold move less in x/z than in the free run, the ones far below are not held"""
+    f = run_job({"lib": "oracle", "scene": "sheet-fixxz", "n": 16, "state": None, "steps": 25}, force_subprocess=True)
+    u = run_job({"lib": "oracle", "scene": "sheet", "n": 16, "state": None, "steps": 25}, force_subprocess=True)
+    assert bool(f["ok"].all()) and bool(u["ok"].all())
+    s0 = run_job({"lib": "oracle", "scene": "sheet", "n": 16, "state": None, "steps": 0}, force_subprocess=True)["curr"]
+    hf = np.hypot(f["curr"][:, 0] - s0[:, 0], f["curr"][:, 2] - s0[:, 2])
+    hu = np.hypot(u["curr"][:, 0] - s0[:, 0], u["curr"][:, 2] - s0[:, 2])
+    assert hu.max() > 0.02                                       # the free sheet swings
+    high = (f["curr"][:, 1] > -0.2) & (u["curr"][:, 1] > -0.2) & (hu > 1e-3)
+    assert high.sum() > 10 and float(np.median(hf[high] / hu[high])) < 0.7
+    assert not np.array_equal(f["curr"], u["curr"])

@@ -164,3 +164,17 @@ def test_quadratic_and_logarithmic_barriers_match_the_oracle(run_job, scene, n, 
     assert abs(g["log_num_contact"][0] - o["log_num_contact"][0]) <= 2
     d = np.abs(g["curr"] - o["curr"]).max(axis=1)
     assert float(np.median(d)) < 1e-4 and float(d.max()) < 3e-3, (float(np.median(d)), float(d.max()))
+
+
+def test_fix_xz_matches_the_oracle(run_job):
+    """ParamSet.fix_xz (horizontal drag above a height; k_momentum + k_fix_xz) on the swinging sheet against the CPU oracle"""
+    job = {"scene": "sheet-fixxz", "n": 24, "state": None, "steps": 8, "dump_linsys": True}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    assert c["only_ref"] == 0 and c["only_ours"] == 0, c
+    assert c["offdiag_max_rel_block_diff"] < 1e-3 and c["diag_max_rel_diff"] < 1e-3 and c["rhs_max_abs_diff_over_scale"] < 1e-3, c
+    assert len(g["log_iter"]) == len(o["log_iter"])
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))
