@@ -575,13 +575,43 @@ PPF_EXPORT void override_angular_velocity(const unsigned *indices, unsigned coun
     CUDA_OK(cudaStreamSynchronize(s.stream));
     d.free();
 }
+// collision windows (main.cu:2230-2330): vertex -> object map, up to 8 [start, end) windows per object.  The tables are kept on
+// the host until the first refresh (the reference's host calls this right after initialize; either order works here).
+__global__ void k_cw_refresh(unsigned n, const unsigned *__restrict__ dmap, const float *__restrict__ windows,
+                             const unsigned *__restrict__ counts, float time, unsigned char *__restrict__ active) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned dm = dmap[i], cnt = counts[dm];
+    bool a = cnt == 0;
+    for (unsigned w = 0; w < cnt && !a; ++w) a = time >= windows[dm * 16 + 2 * w] && time < windows[dm * 16 + 2 * w + 1];
+    active[i] = a ? 1 : 0;
+}
 PPF_EXPORT void init_collision_windows(const unsigned *vert_dmap, unsigned vert_count, const float *windows,
                                        const unsigned *window_counts, unsigned n_groups) {
-    (void)vert_dmap; (void)vert_count; (void)windows;
-    for (unsigned i = 0; i < n_groups; ++i)
-        if (window_counts[i]) fatal(4, "B200 backend: collision windows are not implemented");
+    State &s = g;
+    s.h_cw_dmap.assign(vert_dmap, vert_dmap + vert_count);
+    s.h_cw_windows.assign(windows, windows + size_t(n_groups) * 16); // MAX_COLLISION_WINDOWS = 8 pairs per object
+    s.h_cw_counts.assign(window_counts, window_counts + n_groups);
+    for (unsigned i = 0; i < vert_count; ++i)
+        if (vert_dmap[i] >= n_groups) fatal(4, "init_collision_windows: vertex %u maps to object %u of %u", i, vert_dmap[i], n_groups);
+    s.has_cw = false;
+    for (unsigned i = 0; i < n_groups; ++i) s.has_cw |= window_counts[i] != 0;
+    s.cw_uploaded = false;
 }
-PPF_EXPORT void refresh_collision_active(float time) { (void)time; }
+PPF_EXPORT void refresh_collision_active(float time) {
+    State &s = g;
+    if (!s.has_cw) return;
+    if (!s.nv || s.h_cw_dmap.size() != s.nv) fatal(4, "refresh_collision_active: %zu window vertices for a scene of %u", s.h_cw_dmap.size(), s.nv);
+    if (!s.cw_uploaded) {
+        s.cw_dmap.upload(s.h_cw_dmap.data(), s.h_cw_dmap.size(), s.stream);
+        s.cw_windows.upload(s.h_cw_windows.data(), s.h_cw_windows.size(), s.stream);
+        s.cw_counts.upload(s.h_cw_counts.data(), s.h_cw_counts.size(), s.stream);
+        s.cw_active.reserve(s.nv);
+        s.cw_uploaded = true;
+    }
+    k_cw_refresh<<<div_up(s.nv, 256), 256, 0, s.stream>>>(s.nv, s.cw_dmap.p, s.cw_windows.p, s.cw_counts.p, time, s.cw_active.p);
+    LAUNCH_COUNT(1);
+}
 
 PPF_EXPORT unsigned fetch_intersection_records(PpfIntersectionRecord *out, unsigned max_count) {
     State &s = g;

@@ -179,6 +179,14 @@ struct State {
 
     // intersection records (fetch_intersection_records)
     DBuf<PpfIntersectionRecord> isect_records;
+    // collision windows (init_collision_windows / refresh_collision_active): per-vertex "takes part in contact now" flags;
+    // has_cw stays false for scenes without windows and the contact kernels then see a null pointer
+    DBuf<unsigned> cw_dmap, cw_counts;
+    DBuf<float> cw_windows;
+    DBuf<unsigned char> cw_active;
+    std::vector<unsigned> h_cw_dmap, h_cw_counts;
+    std::vector<float> h_cw_windows;
+    bool has_cw = false, cw_uploaded = false;
     std::vector<PpfIntersectionRecord> h_isect;
     unsigned h_isect_count = 0;
 

@@ -89,12 +89,18 @@ struct BpArgs {
     unsigned *cnt; // 4 counters
     unsigned cap[4];
     unsigned *error;
+    const unsigned char *active; // collision windows: per-vertex flags, or null (everything takes part)
 };
+// collision windows (main.cu:48-110, 2266-2330): an edge / face takes part when any of its vertices does
+__device__ __forceinline__ bool cw_vertex(const unsigned char *a, unsigned v) { return !a || a[v]; }
+__device__ __forceinline__ bool cw_edge(const unsigned char *a, const uint2 e) { return !a || a[e.x] || a[e.y]; }
+__device__ __forceinline__ bool cw_face(const unsigned char *a, const uint4 f) { return !a || a[f.x] || a[f.y] || a[f.z]; }
 
 __global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq) return;
     const unsigned v = A.vert.prim[t];
+    if (!cw_vertex(A.active, v)) return;
     const float4 cp = A.vcp[v];
     const float ext = 0.5f * cp.x + cp.y;
     const float4 p0 = A.x0[v];
@@ -118,6 +124,7 @@ __global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
         Emit em; em.out = A.out[0]; em.counter = A.cnt + 0; em.cap = A.cap[0];
         auto emit = [&](unsigned f) {
             if (!sweep) { const uint4 fv = A.faces[f]; if (fv.x == v || fv.y == v || fv.z == v) return; }
+            if (A.active && !cw_face(A.active, A.faces[f])) return;
             em.push(v, f);
         };
         ok &= rel ? bvh_query_relative(A.face, q, u, emit) : bvh_query(A.face, q, emit);
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
         Emit em; em.out = A.out[1]; em.counter = A.cnt + 1; em.cap = A.cap[1];
         auto emit = [&](unsigned e) {
             const uint2 ev = A.edges[e];
-            if (ev.x == v || ev.y == v) return;
+            if (ev.x == v || ev.y == v || !cw_edge(A.active, ev)) return;
             em.push(v, e);
         };
         ok &= rel ? bvh_query_relative(A.edge, q, u, emit) : bvh_query(A.edge, q, emit);
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
     }
     {
         Emit em; em.out = A.out[2]; em.counter = A.cnt + 2; em.cap = A.cap[2];
-        auto emit = [&](unsigned w) { if (w < v) em.push(v, w); };
+        auto emit = [&](unsigned w) { if (w < v && cw_vertex(A.active, w)) em.push(v, w); };
         ok &= rel ? bvh_query_relative(A.vert, q, u, emit) : bvh_query(A.vert, q, emit);
         em.flush();
     }
@@ -148,6 +155,7 @@ __global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned nq) {
     if (t >= nq) return;
     const unsigned e = A.edge.prim[t];
     const uint2 ev = A.edges[e];
+    if (!cw_edge(A.active, ev)) return;
     const float4 cp = A.ecp[e];
     const float ext = 0.5f * cp.x + cp.y;
     const float4 a0 = A.x0[ev.x], b0 = A.x0[ev.y];
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned nq) {
     auto emit = [&](unsigned f) {
         if (!(e < f)) return;
         if (!sweep) { const uint2 fv = A.edges[f]; if (fv.x == ev.x || fv.x == ev.y || fv.y == ev.x || fv.y == ev.y) return; }
+        if (A.active && !cw_edge(A.active, A.edges[f])) return;
         em.push(e, f);
     };
     const bool ok = rel ? bvh_query_relative(A.edge, q, u, emit) : bvh_query(A.edge, q, emit);
@@ -196,6 +205,7 @@ static void broad_phase(State &s, const float4 *x0, const float4 *x1, bool sweep
         A.vcp = s.vcp.p; A.ecp = s.ecp.p; A.faces = s.face.p; A.edges = s.edge.p;
         for (int k = 0; k < 4; ++k) { A.out[k] = s.cand[k].pairs.p; A.cap[k] = (unsigned)std::min<size_t>(s.cand[k].pairs.cap, 0xFFFFFFF0u); }
         A.cnt = cnt; A.error = cnt + 4;
+        A.active = s.has_cw ? s.cw_active.p : nullptr;
         if (s.nsv) k_bp_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(A, s.nsv);
         if (s.ne) k_bp_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);
         LAUNCH_COUNT(2);
@@ -1000,6 +1010,7 @@ struct IsectArgs {
     PpfIntersectionRecord *records;
     unsigned *counter; // [0] record counter, [1] error
     int check_offsets;
+    const unsigned char *active; // collision windows (see BpArgs)
 };
 
 __device__ void record_isect(const IsectArgs &A, unsigned type, unsigned e0, unsigned e1, const V3 *v0, unsigned n0, const V3 *v1, unsigned n1) {
@@ -1018,6 +1029,7 @@ __global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
     if (t >= nq) return;
     const unsigned e = A.edge.prim[t];
     const uint2 ev = A.edges[e];
+    if (!cw_edge(A.active, ev)) return;
     const V3 y0 = ld3c(A.x, ev.x), y1 = ld3c(A.x, ev.y);
     Box q;
     q.lx = fminf(y0.x, y1.x); q.ly = fminf(y0.y, y1.y); q.lz = fminf(y0.z, y1.z);
@@ -1028,7 +1040,7 @@ __global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
         const bool either_nonzero = A.fcp[fi].w > 0.0f || emass > 0.0f;
         const uint4 f = A.faces[fi];
         const bool both_collider = A.vcollider[ev.x] && A.vcollider[f.x];
-        if (!either_dyn || !either_nonzero || both_collider) return;
+        if (!either_dyn || !either_nonzero || both_collider || !cw_face(A.active, f)) return;
         if (ev.x == f.x || ev.x == f.y || ev.x == f.z || ev.y == f.x || ev.y == f.y || ev.y == f.z) return;
         const V3 x0 = ld3c(A.x, f.x), x1 = ld3c(A.x, f.y), x2 = ld3c(A.x, f.z);
         if (edge_triangle_intersect(y0, y1, x0, x1, x2)) {
@@ -1044,7 +1056,7 @@ __global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
             const bool either_dyn = !A.efixed[e] || !A.efixed[e2];
             const bool either_nonzero = emass > 0.0f || A.ecp[e2].w > 0.0f;
             const bool both_collider = A.vcollider[ev.x] && A.vcollider[fv.x];
-            if (!either_dyn || !either_nonzero || both_collider) return;
+            if (!either_dyn || !either_nonzero || both_collider || !cw_edge(A.active, fv)) return;
             const float offset = ep.y + A.ecp[e2].y;
             const bool shared = fv.x == ev.x || fv.x == ev.y || fv.y == ev.x || fv.y == ev.y;
             bool hit = false;
@@ -1077,6 +1089,7 @@ __global__ void __launch_bounds__(128) k_isect_vertex(IsectArgs A, unsigned nq) 
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq) return;
     const unsigned v = A.vert.prim[t];
+    if (!cw_vertex(A.active, v)) return;
     const float4 vp = A.vcp[v];
     const V3 p = ld3c(A.x, v);
     Box q;
@@ -1087,7 +1100,7 @@ __global__ void __launch_bounds__(128) k_isect_vertex(IsectArgs A, unsigned nq) 
         const bool either_dyn = !A.vfixed[v] || !A.vfixed[w];
         const bool either_nonzero = vp.w > 0.0f || wp.w > 0.0f;
         const bool both_collider = A.vcollider[v] && A.vcollider[w];
-        if (!either_dyn || !either_nonzero || both_collider) return;
+        if (!either_dyn || !either_nonzero || both_collider || !cw_vertex(A.active, w)) return;
         const float offset = vp.y + wp.y;
         const V3 qv = ld3c(A.x, w);
         const V3 e = p - qv;
@@ -1105,6 +1118,7 @@ bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm) {
     A.vfixed = s.vfixed.p; A.efixed = s.efixed.p; A.ffixed = s.ffixed.p; A.vcollider = s.vcollider.p;
     A.records = s.isect_records.p;
     A.counter = s.counters.p + 26;
+    A.active = s.has_cw ? s.cw_active.p : nullptr;
     A.check_offsets = s.has_offsets ? 1 : 0; // no contact offset anywhere: the "closer than the offsets" tests cannot fire
     CUDA_OK(cudaMemsetAsync(A.counter, 0, 2 * sizeof(unsigned), q));
     if (s.ne) k_isect_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <stdexcept>
 
 namespace ppfh {
 
@@ -41,7 +42,21 @@ bool Runner::init(const std::string &log_dir) {
     be->set_log_path(log_dir.c_str()); // main.rs:44
     time = b->param.time;
     curr_frame = int(std::floor(time * b->spec.args.fps));
-    return be->initialize(&b->dataset, &b->param); // backend.rs:653
+    if (!be->initialize(&b->dataset, &b->param)) return false; // backend.rs:653
+    // backend.rs:654-672 + scene.rs:2471-2542: one group per object, up to 8 windows each
+    const unsigned n_groups = (unsigned)b->spec.objects.size();
+    std::vector<float> windows(size_t(n_groups) * 16, 0.0f);
+    std::vector<unsigned> counts(n_groups, 0u);
+    bool any = false;
+    for (unsigned o = 0; o < n_groups; ++o) {
+        const auto &w = b->spec.objects[o].collision_windows;
+        if (w.size() > 8) throw std::runtime_error("an object has more than 8 collision windows");
+        counts[o] = (unsigned)w.size();
+        for (size_t k = 0; k < w.size(); ++k) { windows[size_t(o) * 16 + 2 * k] = float(w[k].first); windows[size_t(o) * 16 + 2 * k + 1] = float(w[k].second); }
+        any |= !w.empty();
+    }
+    if (any) be->init_collision_windows(b->vert_dmap.data(), (unsigned)b->vert_dmap.size(), windows.data(), counts.data(), n_groups);
+    return true;
 }
 
 bool Runner::step() {

@@ -58,6 +58,9 @@ struct ShellObject {
     std::vector<Pin> pins;
     Vec3d displacement{0, 0, 0};
     Vec3d velocity{0, 0, 0};
+    // collision windows: [start, end) intervals of simulated time during which the object takes part in contact; none = always
+    // (scene.rs:2471-2542 build_collision_window_table, at most 8 per object)
+    std::vector<std::pair<double, double>> collision_windows;
 };
 struct SimArgs { // crates/ppf-cts-solver/src/args.rs:22-94 (defaults params.rs:207-290)
     bool disable_contact = false, inactive_momentum = false, include_face_mass = false;

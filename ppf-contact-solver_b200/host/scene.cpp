@@ -549,6 +549,13 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.gravity_y_keys = {{0.0, -9.8}, {1.0, -9.8}, {1.0 + jitter, 9.8}, {2.0, -9.8}};
         return s;
     }
+    if (name == "headless-cw-open" || name == "headless-cw-closed") { // `headless` with a collision window on the moving sphere:
+        // open = [0, 100) (the same run as `headless`), closed = [0, 0.3): from t = 0.3 on the sphere passes through the curtains
+        SceneSpec s = make_scene("headless", n);
+        s.name = name;
+        s.objects.back().collision_windows = {{0.0, name == "headless-cw-open" ? 100.0 : 0.3}};
+        return s;
+    }
     if (name == "headless") { // examples/headless.py (the CI smoke scene): five curtains pinned along their top edge, a fully pinned
         // sphere mesh pushed through them (.jitter() left out; UV-less rest frames, like `hang`)
         SceneSpec s;

@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 
-from conftest import golden_cases
+from conftest import REPO, golden_cases
 
 
 def test_scene_counts_follow_euler(ppf):
@@ -405,3 +405,20 @@ def test_fix_xz_drags_the_horizontal_motion_above_the_threshold(run_job):
     high = (f["curr"][:, 1] > -0.2) & (u["curr"][:, 1] > -0.2) & (hu > 1e-3)
     assert high.sum() > 10 and float(np.median(hf[high] / hu[high])) < 0.7
     assert not np.array_equal(f["curr"], u["curr"])
+
+
+def test_collision_windows_switch_an_object_out_of_contact(run_job):
+    """init_collision_windows / refresh_collision_active (main.cu:48-110, 2230-2330; scene.rs:2471-2542): `headless` from a
+    saved state at t = 0.68 where the moving sphere presses into the curtains.  A window that is open ([0, 100)) changes
+    nothing, bit for bit; with the sphere's window closed ([0, 0.3)) its contacts are gone (the curtain-curtain ones stay),
+    the step still passes its intersection check (the sphere is ignored there too) and the curtains are released."""
+    state = os.path.join(REPO, "tests", "golden", "headless_n24", "state_00068.bin")
+    job = {"lib": "oracle", "n": 24, "state": state, "steps": 2}
+    plain = run_job(dict(job, scene="headless"), force_subprocess=True)
+    opened = run_job(dict(job, scene="headless-cw-open"), force_subprocess=True)
+    closed = run_job(dict(job, scene="headless-cw-closed"), force_subprocess=True)
+    assert bool(plain["ok"].all()) and bool(opened["ok"].all()) and bool(closed["ok"].all())
+    assert np.array_equal(plain["curr"], opened["curr"]) and np.array_equal(plain["log_num_contact"], opened["log_num_contact"])
+    assert closed["log_num_contact"][0] < plain["log_num_contact"][0] - 20
+    assert closed["log_num_contact"][-1] < 0.6 * plain["log_num_contact"][-1]
+    assert float(np.abs(closed["curr"] - plain["curr"]).max()) > 1e-3

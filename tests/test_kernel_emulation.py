@@ -256,6 +256,7 @@ def test_emulated_step_reproduces_the_reference_golden(emu, run_job, case):
 _LATE = [("headless", 24, os.path.join(REPO, "tests", "golden", "headless_n24", "state_00068.bin"), 1),
          ("lift", 24, None, 30), ("sheet-arap", 24, None, 5), ("sheet-stvk", 24, None, 5), ("sheet-snhk", 24, None, 5),
          ("sheet-damped", 24, None, 3), ("woven-damped", 32, None, 3), ("seam", 16, None, 4), ("sheet-plastic", 24, None, 6), ("sheet-fixxz", 24, None, 8),
+         ("headless-cw-closed", 24, os.path.join(REPO, "tests", "golden", "headless_n24", "state_00068.bin"), 2),   # collision windows
          ("woven-plastic", 32, None, 2)]      # chained woven steps separate by their line-search cuts after ~3 steps, plastic or not
 
 

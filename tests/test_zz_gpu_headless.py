@@ -178,3 +178,22 @@ def test_fix_xz_matches_the_oracle(run_job):
     assert len(g["log_iter"]) == len(o["log_iter"])
     d = np.abs(g["curr"] - o["curr"]).max(axis=1)
     assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))
+
+
+def test_collision_windows_match_the_oracle(run_job):
+    """collision windows (k_cw_refresh + the per-vertex flags in the broad phase and the intersection check): `headless` with
+    the sphere's window closed, from the saved contact-rich state, against the CPU oracle; and the open window is a no-op"""
+    job = {"scene": "headless-cw-closed", "n": 24, "state": STATE, "steps": 2}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    assert len(g["log_num_contact"]) == len(o["log_num_contact"])
+    assert abs(g["log_num_contact"][0] - o["log_num_contact"][0]) <= 1
+    for mine, theirs in zip(g["log_num_contact"], o["log_num_contact"]):
+        assert abs(mine - theirs) <= 3 + 0.05 * theirs
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))
+    p = run_job(dict(job, scene="headless", lib="ours"), force_subprocess=True)
+    q = run_job(dict(job, scene="headless-cw-open", lib="ours"), force_subprocess=True)
+    assert p["log_num_contact"][0] == q["log_num_contact"][0] > g["log_num_contact"][0] + 20
+    assert float(np.abs(p["curr"] - q["curr"]).max()) < 2e-4      # atomics order only
