@@ -159,7 +159,8 @@ def test_quadratic_and_logarithmic_barriers_match_the_oracle(run_job, scene, n, 
     c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
     nb = c["n_blocks"][0]
     assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
-    assert c["frac_blocks_off"] * nb <= 12 + 0.002 * nb, c
+    # __logf's absolute error (2^-21.4 near 1) shows in blocks made of nothing but a contact at the very edge of the gap
+    assert c["frac_blocks_off"] * nb <= 12 + (0.01 if kind == "log" else 0.002) * nb, c
     assert abs(len(g["log_iter"]) - len(o["log_iter"])) <= 1
     assert abs(g["log_num_contact"][0] - o["log_num_contact"][0]) <= 2
     d = np.abs(g["curr"] - o["curr"]).max(axis=1)
@@ -197,3 +198,26 @@ def test_collision_windows_match_the_oracle(run_job):
     q = run_job(dict(job, scene="headless-cw-open", lib="ours"), force_subprocess=True)
     assert p["log_num_contact"][0] == q["log_num_contact"][0] > g["log_num_contact"][0] + 20
     assert float(np.abs(p["curr"] - q["curr"]).max()) < 2e-4      # atomics order only
+
+
+def test_drape_first_contacts_match_the_oracle(run_job):
+    """Five chained steps from rest: free fall, first touch of the sphere, then ~15 Newton iterations that the collider
+    line search cuts to a few percent each.  Whether a vertex sits inside the 1e-3 contact gap at the first touch is an
+    fp32 tie between the two builds (observed on a B200: 1 vs 2 vertices, after which this backend needs 21 Newton
+    iterations and the oracle 20), so the iteration-by-iteration logs are compared in aggregate; exact agreement with the
+    reference is the job of the golden cases drape_n32 in test_gpu_parity.py."""
+    job = {"scene": "drape", "n": 32, "state": None, "steps": 5}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    assert json.loads(str(g["stats_json"]))["n_kernel_launches"] > 0
+    assert abs(len(g["log_num_contact"]) - len(o["log_num_contact"])) <= 4 and o["log_num_contact"].max() > 20
+    first_g, first_o = int(np.argmax(g["log_num_contact"] > 0)), int(np.argmax(o["log_num_contact"] > 0))
+    assert abs(first_g - first_o) <= 1 and first_o > 0            # the same free fall before the first touch
+    assert abs(g["log_num_contact"][-1] - o["log_num_contact"][-1]) <= 3 + 0.25 * o["log_num_contact"][-1]
+    assert (g["log_toi"] > 0).all() and (g["log_toi"] <= 1).all() and g["log_toi"].min() < 0.5   # the collider line search cuts steps
+    # a cut step advances time by dt * toi_advanced, so the two runs are at slightly different times (and the falling sheet at
+    # slightly different heights): compare the clocks, and the positions only against the colliders
+    assert abs(float(g["time"][0]) - float(o["time"][0])) < 0.3 * float(o["time"][0])
+    x = g["curr"].astype(np.float64)
+    assert np.isfinite(x).all() and np.linalg.norm(x, axis=1).min() > 0.4 and x[:, 1].min() > -0.08   # outside the sphere, above the floor
