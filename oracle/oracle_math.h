@@ -443,4 +443,93 @@ static inline float o_collider_toi(const float *y0, const float *y1, int pinned,
     return toi;
 }
 
+
+/* ---- static collision mesh (TEST INFRASTRUCTURE restatement of contact/contact.cu:899-1151) -----------------------
+ * One dynamic vertex / face / edge against one static face / vertex / edge: the push penalty of the analytic colliders
+ * with the elasticity-inclusive stiffness of the dynamic element.  Outputs: f[3] (force on the contact point), H[9]
+ * (column-major), c[] (weights of the element's vertices: vertex k receives c[k] f, block (j,k) receives c[j] c[k] H). */
+static inline float o_cmesh_stiffness(int n, const float *B /* [n][n][9] column-major blocks */, const float *vmass, float gap_squared, const float *c,
+                                      const float *normal) {
+    float v[9], Av[9];
+    for (int j = 0; j < 3 * n; ++j) v[j] = c[j / 3] * normal[j % 3];
+    for (int r = 0; r < 3 * n; ++r) {
+        float acc = 0.0f;
+        for (int k = 0; k < 3 * n; ++k) {
+            float a = B[((r / 3) * n + (k / 3)) * 9 + (k % 3) * 3 + (r % 3)];
+            if (r == k) a += vmass[r / 3] / gap_squared;
+            acc += a * v[k];
+        }
+        Av[r] = acc;
+    }
+    float num = 0.0f, den = 0.0f;
+    for (int r = 0; r < 3 * n; ++r) { num += Av[r] * v[r]; den += v[r] * v[r]; }
+    return num / den;
+}
+static inline void o_cmesh_force(const float *a, const float *normal, const float *dx, float ghat, float mu, float stiff_k, float friction_eps, float *f,
+                                 float *H) {
+    float fg[3], fh[9];
+    for (int k = 0; k < 3; ++k) f[k] = 0.0f;
+    for (int k = 0; k < 9; ++k) H[k] = 0.0f;
+    o_push(a, normal, ghat, stiff_k, f, H);
+    o_friction(f, dx, normal, mu, friction_eps, fg, fh);
+    for (int k = 0; k < 3; ++k) f[k] += fg[k];
+    for (int k = 0; k < 9; ++k) H[k] = H[k] + fh[k];
+}
+static inline void o_normalize(const float *e, float *n) {
+    const float l = sqrtf(o_dot(e, e));
+    for (int k = 0; k < 3; ++k) n[k] = l > 0.0f ? e[k] / l : e[k];
+}
+static inline int o_cmesh_vertex_face(const float *p, const float *p_start, const float *T0, const float *T1, const float *T2, float offset, float ghat,
+                                      float mu, float mass, const float *Hii, float friction_eps, float *f, float *H, float *c3) {
+    const float zero[3] = {0.0f, 0.0f, 0.0f};
+    float t0[3], t1[3], t2[3], c[3], y[3], e[3], mq[3], normal[3], a[3];
+    o_sub(T0, p, t0); o_sub(T1, p, t1); o_sub(T2, p, t2);
+    o_point_triangle_coeff_unclassified(zero, t0, t1, t2, c);
+    for (int k = 0; k < 3; ++k) { y[k] = c[0] * t0[k] + c[1] * t1[k] + c[2] * t2[k]; e[k] = -y[k]; mq[k] = -(p_start[k] - p[k]); }
+    const float s = offset + ghat;
+    if (!(o_dot(e, e) < s * s)) return 0;
+    o_normalize(e, normal);
+    for (int k = 0; k < 3; ++k) a[k] = -(y[k] + normal[k] * s);
+    const float gap = sqrtf(o_dot(e, e)) - offset;
+    const float stiff_k = o_nHn(Hii, normal) + mass / (gap * gap);
+    o_cmesh_force(a, normal, mq, ghat, mu, stiff_k, friction_eps, f, H);
+    c3[0] = 1.0f; c3[1] = c3[2] = 0.0f;
+    return 1;
+}
+static inline int o_cmesh_face_vertex(const float *y, const float (*X)[3], const float (*Xs)[3], float offset, float ghat, float mu, const float *vmass,
+                                      const float *B /* [3][3][9] */, float friction_eps, float *f, float *H, float *c3) {
+    const float zero[3] = {0.0f, 0.0f, 0.0f};
+    float t[3][3], sv[3][3], c[3], p[3], q[3], normal[3], a[3], dx[3];
+    for (int j = 0; j < 3; ++j) { o_sub(X[j], y, t[j]); o_sub(Xs[j], y, sv[j]); }
+    o_point_triangle_coeff_unclassified(zero, t[0], t[1], t[2], c);
+    for (int k = 0; k < 3; ++k) { p[k] = c[0] * t[0][k] + c[1] * t[1][k] + c[2] * t[2][k]; q[k] = c[0] * sv[0][k] + c[1] * sv[1][k] + c[2] * sv[2][k]; }
+    const float s = offset + ghat;
+    if (!(o_dot(p, p) < s * s)) return 0;
+    o_normalize(p, normal);
+    const float gap = sqrtf(o_dot(p, p)) - offset;
+    for (int k = 0; k < 3; ++k) c3[k] = c[k];
+    const float stiff_k = o_cmesh_stiffness(3, B, vmass, gap * gap, c3, normal);
+    for (int k = 0; k < 3; ++k) { a[k] = p[k] - normal[k] * s; dx[k] = p[k] - q[k]; }
+    o_cmesh_force(a, normal, dx, ghat, mu, stiff_k, friction_eps, f, H);
+    return 1;
+}
+static inline int o_cmesh_edge_edge(const float (*P)[3], const float (*Ps)[3], const float *Q0, const float *Q1, float offset, float ghat, float mu,
+                                    const float *vmass, const float *B /* [2][2][9] */, float friction_eps, float *f, float *H, float *c3) {
+    float c[4], x[3], y[3], z[3], e[3], normal[3], a[3], dx[3];
+    o_edge_edge_coeff(P[0], P[1], Q0, Q1, c);
+    for (int k = 0; k < 3; ++k) {
+        x[k] = c[0] * P[0][k] + c[1] * P[1][k]; y[k] = c[2] * Q0[k] + c[3] * Q1[k]; z[k] = c[0] * Ps[0][k] + c[1] * Ps[1][k];
+        e[k] = x[k] - y[k];
+    }
+    const float s = offset + ghat;
+    if (!(o_dot(e, e) < s * s)) return 0;
+    o_normalize(e, normal);
+    const float gap = sqrtf(o_dot(e, e)) - offset;
+    c3[0] = c[0]; c3[1] = c[1]; c3[2] = 0.0f;
+    const float stiff_k = o_cmesh_stiffness(2, B, vmass, gap * gap, c3, normal);
+    for (int k = 0; k < 3; ++k) { a[k] = e[k] - s * normal[k]; dx[k] = x[k] - z[k]; }
+    o_cmesh_force(a, normal, dx, ghat, mu, stiff_k, friction_eps, f, H);
+    return 1;
+}
+
 #endif

@@ -147,3 +147,18 @@ SHIM float orc_rod_bend_plasticity(const float *x9, float rest, float threshold,
 
 /* barrier gradient / curvature of ParamSet.barrier (0 cubic, 1 quad, 2 log) */
 SHIM void orc_barrier(int kind, float g, float ghat, float offset, float *out2) { out2[0] = o_barrier_gradient(g, ghat, offset, kind); out2[1] = o_barrier_curvature(g, ghat, offset, kind); }
+
+/* static collision mesh: kind 0 dynamic vertex / static face, 1 dynamic face / static vertex, 2 dynamic edge / static edge.
+ * dyn = the dynamic element's vertices (evaluation positions, then start-of-step positions), sta = the static element's,
+ * par = offset, ghat, mu, friction_eps, then the vertex masses; B = the element's elastic blocks [n][n][9].
+ * out = hit flag, f[3], H[9], c[3] */
+SHIM void orc_cmesh(int kind, const float *dyn, const float *sta, const float *par, const float *B, float *out16) {
+    float f[3] = {0, 0, 0}, H[9] = {0}, c[3] = {0, 0, 0};
+    int hit;
+    if (kind == 0) hit = o_cmesh_vertex_face(dyn, dyn + 3, sta, sta + 3, sta + 6, par[0], par[1], par[2], par[4], B, par[3], f, H, c);
+    else if (kind == 1) hit = o_cmesh_face_vertex(sta, (const float(*)[3])dyn, (const float(*)[3])(dyn + 9), par[0], par[1], par[2], par + 4, B, par[3], f, H, c);
+    else hit = o_cmesh_edge_edge((const float(*)[3])dyn, (const float(*)[3])(dyn + 6), sta, sta + 3, par[0], par[1], par[2], par + 4, B, par[3], f, H, c);
+    out16[0] = (float)hit;
+    for (int k = 0; k < 3; ++k) { out16[1 + k] = f[k]; out16[13 + k] = c[k]; }
+    for (int k = 0; k < 9; ++k) out16[4 + k] = H[k];
+}

@@ -131,8 +131,7 @@ void upload_dataset(State &s) {
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
     if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
     if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
-    if (d.constraint.mesh.vertex.size || d.constraint.torque_vertices.size)
-        fatal(4, "B200 backend: static collision meshes / torque pins are not implemented");
+    if (d.constraint.torque_vertices.size) fatal(4, "B200 backend: torque pins are not implemented");
     if (d.constraint.stitch.size && d.stitch_hess_slots.size != 36u * d.constraint.stitch.size)
         fatal(4, "B200 backend: slot-replay tables are required (stitch_hess_slots)");
     if (prm.disable_pin_dof_removal) fatal(4, "B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
@@ -257,6 +256,33 @@ void upload_dataset(State &s) {
             CUDA_OK(cudaStreamSynchronize(q));
         }
         s.vcp.upload(v.data(), nv, q); s.ecp.upload(e.data(), ne, q); s.fcp.upload(f.data(), nf, q);
+        // the static collision mesh (Constraint.mesh; main.cu:1725-1770 copies it once, lbvh.cu:1099-1115 builds its trees once)
+        const PpfCollisionMesh &cm = d.constraint.mesh;
+        s.cm_nv = cm.vertex.size; s.cm_nf = cm.face.size; s.cm_ne = cm.edge.size;
+        if (s.cm_nv) {
+            std::vector<float4> cx(s.cm_nv), cv(s.cm_nv), ce(std::max(s.cm_ne, 1u)), cf(std::max(s.cm_nf, 1u));
+            std::vector<uint4> f4(std::max(s.cm_nf, 1u));
+            std::vector<uint2> e2(std::max(s.cm_ne, 1u));
+            for (unsigned i = 0; i < s.cm_nv; ++i) {
+                cx[i] = make_float4(cm.vertex.data[i].v[0], cm.vertex.data[i].v[1], cm.vertex.data[i].v[2], 0.f);
+                const PpfVertexParam &pa = cm.param_arrays.vertex.data[cm.prop.vertex.data[i].param_index];
+                cv[i] = make_float4(pa.ghat, pa.offset, pa.friction, 0.f);
+            }
+            for (unsigned i = 0; i < s.cm_ne; ++i) {
+                e2[i] = make_uint2(cm.edge.data[i].v[0], cm.edge.data[i].v[1]);
+                const PpfEdgeParam &pa = cm.param_arrays.edge.data[cm.prop.edge.data[i].param_index];
+                ce[i] = make_float4(pa.ghat, pa.offset, pa.friction, 0.f);
+            }
+            for (unsigned i = 0; i < s.cm_nf; ++i) {
+                f4[i] = make_uint4(cm.face.data[i].v[0], cm.face.data[i].v[1], cm.face.data[i].v[2], 0);
+                const PpfFaceParam &pa = cm.param_arrays.face.data[cm.prop.face.data[i].param_index];
+                cf[i] = make_float4(pa.ghat, pa.offset, pa.friction, 0.f);
+            }
+            s.cm_x.upload(cx.data(), s.cm_nv, q); s.cm_vcp.upload(cv.data(), s.cm_nv, q);
+            s.cm_ecp.upload(ce.data(), ce.size(), q); s.cm_fcp.upload(cf.data(), cf.size(), q);
+            s.cm_face.upload(f4.data(), f4.size(), q); s.cm_edge.upload(e2.data(), e2.size(), q);
+            CUDA_OK(cudaStreamSynchronize(q));
+        }
         s.fmat.upload(fm.data(), nf, q); s.inv_rest.upload(ir.data(), nf, q); s.hmat.upload(hm.data(), nh, q);
         s.fstrain.upload(fs.data(), nf, q);
         s.varea.upload(va.data(), nv, q); s.hinge_stiff.upload(hs.data(), nh, q);
@@ -356,6 +382,12 @@ void upload_dataset(State &s) {
     s.diag.reserve(size_t(9) * nv); s.force.reserve(size_t(3) * nv); s.dx.reserve(size_t(3) * nv);
     s.counters.reserve(64); s.scalars.reserve(64);
     s.counters.zero(64, q); s.scalars.zero(64, q);
+    if (s.cm_nv) { // trees of the static collision mesh, built once (they use the bounds words of `counters`)
+        bvh_build_static(s, s.cm_bvh_face, 0, s.cm_nf, s.cm_x.p, s.cm_face.p, s.cm_edge.p, s.cm_fcp.p);
+        bvh_build_static(s, s.cm_bvh_edge, 1, s.cm_ne, s.cm_x.p, s.cm_face.p, s.cm_edge.p, s.cm_ecp.p);
+        bvh_build_static(s, s.cm_bvh_vert, 2, s.cm_nv, s.cm_x.p, s.cm_face.p, s.cm_edge.p, s.cm_vcp.p);
+        CUDA_OK(cudaStreamSynchronize(q));
+    }
     CUDA_OK(cudaMallocHost(&s.h_pinned, 256 * sizeof(float)));
     s.isect_records.reserve(PPF_MAX_INTERSECTION_RECORDS);
     s.h_isect.resize(PPF_MAX_INTERSECTION_RECORDS);
@@ -506,8 +538,10 @@ PPF_EXPORT void update_dyn(unsigned *index, unsigned *offset) {
 }
 
 PPF_EXPORT void update_constraint(const PpfConstraint *constraint) {
-    if (constraint->mesh.vertex.size || constraint->torque_vertices.size)
-        fatal(4, "B200 backend: static collision meshes / torque pins are not implemented");
+    if (constraint->torque_vertices.size) fatal(4, "B200 backend: torque pins are not implemented");
+    // the static collision mesh is taken at initialize, where its trees are built once (the reference never rebuilds them either)
+    if (constraint->mesh.vertex.size != g.cm_nv || constraint->mesh.face.size != g.cm_nf)
+        fatal(4, "update_constraint: the static collision mesh changed size (%u vertices, %u at initialize)", constraint->mesh.vertex.size, g.cm_nv);
     if (36u * constraint->stitch.size > g.nstitch_slots) fatal(4, "update_constraint: %u stitches but slots for %u only", constraint->stitch.size, g.nstitch_slots / 36u);
     apply_constraint(g, constraint);
 }

@@ -179,6 +179,13 @@ struct State {
 
     // intersection records (fetch_intersection_records)
     DBuf<PpfIntersectionRecord> isect_records;
+    // static collision mesh (Constraint.mesh at initialize): positions, elements, (ghat, offset, friction, 0) per vertex /
+    // edge / face and one tree per element kind, built once
+    unsigned cm_nv = 0, cm_nf = 0, cm_ne = 0;
+    DBuf<float4> cm_x, cm_vcp, cm_ecp, cm_fcp;
+    DBuf<uint4> cm_face;
+    DBuf<uint2> cm_edge;
+    Bvh cm_bvh_face, cm_bvh_edge, cm_bvh_vert;
     // collision windows (init_collision_windows / refresh_collision_active): per-vertex "takes part in contact now" flags;
     // has_cw stays false for scenes without windows and the contact kernels then see a null pointer
     DBuf<unsigned> cw_dmap, cw_counts;
@@ -230,6 +237,7 @@ void recompute_fixed_flags(State &s);
 
 // bvh.cu
 void bvh_build(State &s, Bvh &b, int kind, const float4 *x);      // kind: 0 face, 1 edge, 2 vertex
+void bvh_build_static(State &s, Bvh &b, int kind, unsigned n, const float4 *x, const uint4 *face, const uint2 *edge, const float4 *cp);
 void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate);
 // boxes at x0 plus per-node displacement intervals t_max*(x1-x0) for relative-motion sweep queries
 void bvh_refit_relative(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float t_max);
@@ -238,6 +246,8 @@ void bvh_refit_relative(State &s, Bvh &b, int kind, const float4 *x0, const floa
 unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &max_nnz_row, float &dyn_consumed);
 float contact_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap);
 bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm);
+unsigned assemble_collision_mesh(State &s, const PpfParamSet &prm); // static collision mesh; returns the contact count
+float collision_mesh_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap);
 unsigned assemble_colliders(State &s, const PpfParamSet &prm);   // analytic spheres / walls; returns the contact count
 // collider part of the line search: step fraction in (0, 1]; bad_vertex != 0xFFFFFFFF: a pinned vertex is driven through a collider
 float collider_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, unsigned &bad_vertex);

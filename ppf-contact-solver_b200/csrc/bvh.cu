@@ -191,18 +191,22 @@ __global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_s
     }
 }
 
-static void fit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate, bool relative = false) {
+static void fit_leaves(State &s, Bvh &b, int kind, const LeafParams &P, bool relative) {
     if (b.n == 0) return;
     if (relative) { b.ulo.reserve(2 * size_t(b.n)); b.uhi.reserve(2 * size_t(b.n)); }
-    LeafParams P{x0, x1, extrapolate, s.face.p, s.edge.p, kind == 0 ? s.fcp.p : (kind == 1 ? s.ecp.p : s.vcp.p)};
     if (b.n > 1) CUDA_OK(cudaMemsetAsync(b.flag.p, 0, sizeof(unsigned) * (b.n - 1), s.stream));
     k_fit<<<div_up(b.n, 256), 256, 0, s.stream>>>(kind, b.n, P, b.prim_sorted.p, b.child.p, b.parent.p, b.lo.p, b.hi.p, b.flag.p,
                                                    relative ? b.ulo.p : nullptr, relative ? b.uhi.p : nullptr);
     LAUNCH_COUNT(1);
 }
+static void fit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate, bool relative = false) {
+    LeafParams P{x0, x1, extrapolate, s.face.p, s.edge.p, kind == 0 ? s.fcp.p : (kind == 1 ? s.ecp.p : s.vcp.p)};
+    fit_leaves(s, b, kind, P, relative);
+}
 
-void bvh_build(State &s, Bvh &b, int kind, const float4 *x) {
-    const unsigned n = kind == 0 ? s.nf : (kind == 1 ? s.ne : s.nsv);
+// Morton codes, sort, Karras tree and the leaf / node boxes of n primitives of any mesh (the simulated one or the static
+// collision mesh): kind 0 faces, 1 edges, 2 vertices; cp = (ghat, offset, ., .) per primitive
+static void build_tree(State &s, Bvh &b, int kind, unsigned n, const float4 *x, const uint4 *face, const uint2 *edge, const float4 *cp) {
     b.n = n;
     if (n == 0) return;
     cudaStream_t q = s.stream;
@@ -211,17 +215,29 @@ void bvh_build(State &s, Bvh &b, int kind, const float4 *x) {
     unsigned *bounds = s.counters.p + 40; // 6 words
     const unsigned init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
     CUDA_OK(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, q));
-    k_bounds<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, s.face.p, s.edge.p, bounds);
-    k_morton<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, s.face.p, s.edge.p, bounds, b.morton.p, b.prim.p);
+    k_bounds<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, face, edge, bounds);
+    k_morton<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, face, edge, bounds, b.morton.p, b.prim.p);
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, (int)n, 0, 30, q);
     if (need > b.sort_tmp_bytes) { b.sort_tmp.reserve(need); b.sort_tmp_bytes = need; }
     cub::DeviceRadixSort::SortPairs(b.sort_tmp.p, need, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, (int)n, 0, 30, q);
     if (n > 1) k_radix_tree<<<div_up(n - 1, 256), 256, 0, q>>>((int)n, b.morton_sorted.p, b.child.p, b.parent.p);
     LAUNCH_COUNT(4);
-    fit(s, b, kind, x, x, 1.0f);
+    LeafParams P{x, x, 1.0f, face, edge, cp};
+    fit_leaves(s, b, kind, P, false);
+}
+
+void bvh_build(State &s, Bvh &b, int kind, const float4 *x) {
+    const unsigned n = kind == 0 ? s.nf : (kind == 1 ? s.ne : s.nsv);
+    build_tree(s, b, kind, n, x, s.face.p, s.edge.p, kind == 0 ? s.fcp.p : (kind == 1 ? s.ecp.p : s.vcp.p));
+    if (n == 0) return;
     s.bvh_cover_eval = true;
     s.bvh_relative = false;
+}
+// the static collision mesh (lbvh.cu:1099-1115 build_collision_mesh_bvh, plus a vertex tree so that every query of this
+// backend runs from a dynamic element against a static tree): built once at initialize
+void bvh_build_static(State &s, Bvh &b, int kind, unsigned n, const float4 *x, const uint4 *face, const uint2 *edge, const float4 *cp) {
+    build_tree(s, b, kind, n, x, face, edge, cp);
 }
 
 void bvh_refit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate) {

@@ -24,6 +24,7 @@
 #include "bvh.cuh"
 #include "math_accd.cuh"
 #include "math_collider.cuh"
+#include "math_cmesh.cuh"
 #include "math_contact.cuh"
 #include "math_distance.cuh"
 #include <algorithm>
@@ -965,6 +966,274 @@ float collider_line_search(State &s, const float4 *x0, const float4 *x1, const P
 }
 
 // ---------------------------------------------------------------------------------------------
+// static collision mesh (Constraint.mesh; contact.cu:899-1151 embeds, 1826-1955 assembly driver, 1956-2093 + 2596-2728 line
+// search; math_cmesh.cuh).  Every query runs from a dynamic element against a tree of the static mesh built once at
+// initialize: dynamic vertex -> static faces, dynamic edge -> static edges, dynamic face -> static vertices (the reference
+// runs the last one from the static vertex against the dynamic face tree; box overlap is symmetric, so the pairs are the same).
+// ---------------------------------------------------------------------------------------------
+struct CmArgs {
+    BvhView sface, sedge, svert;
+    const float4 *sx, *svcp, *secp, *sfcp;
+    const uint4 *sfaces;
+    const uint2 *sedges;
+    const unsigned *fix_index;
+    const unsigned char *active; // collision windows (see BpArgs)
+    unsigned *counter;           // [0] contact count, [1] traversal error
+};
+static CmArgs make_cm_args(State &s, unsigned *counter) {
+    CmArgs A;
+    A.sface = view_of(s.cm_bvh_face); A.sedge = view_of(s.cm_bvh_edge); A.svert = view_of(s.cm_bvh_vert);
+    A.sx = s.cm_x.p; A.svcp = s.cm_vcp.p; A.secp = s.cm_ecp.p; A.sfcp = s.cm_fcp.p; A.sfaces = s.cm_face.p; A.sedges = s.cm_edge.p;
+    A.fix_index = s.fix_index.p;
+    A.active = s.has_cw ? s.cw_active.p : nullptr;
+    A.counter = counter;
+    return A;
+}
+// block (i, j) of the elastic-only matrix, transposed when it is stored as (j, i); zero when the pattern lacks it
+__device__ __forceinline__ M3 elastic_block(const Ctx &c, unsigned i, unsigned j) {
+    const bool swap = i > j;
+    const unsigned slot = fixed_find(c, swap ? j : i, swap ? i : j);
+    if (slot == 0xFFFFFFFFu) return m3_zero();
+    const M3 B = load_block(c.fx_el, slot);
+    return swap ? transpose(B) : B;
+}
+template <int N> __device__ __forceinline__ void cm_scatter(const Ctx &c, const unsigned *idx, const CmeshOut &o) {
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        const V3 fa = o.c[a] * o.f;
+        float *dst = c.force + size_t(3) * idx[a];
+        if (fa.x) atomicAdd(dst + 0, fa.x);
+        if (fa.y) atomicAdd(dst + 1, fa.y);
+        if (fa.z) atomicAdd(dst + 2, fa.z);
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = 0; b < N; ++b) {
+            const unsigned i = idx[a], j = idx[b];
+            if (!(i <= j)) continue;
+            const unsigned slot = fixed_find(c, i, j);
+            if (slot == 0xFFFFFFFFu) continue; // cannot happen: the blocks of one element are in the fixed pattern
+            const float sc = o.c[a] * o.c[b];
+            float *dst = c.fx_val + size_t(9) * slot;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                const float v = sc * o.H.m[e];
+                if (v) atomicAdd(dst + e, v);
+            }
+        }
+}
+__device__ __forceinline__ void cm_count(const CmArgs &A, unsigned count, bool ok) {
+    if (count) atomicAdd(A.counter, count);
+    if (!ok) atomicExch(A.counter + 1, 1u);
+}
+
+__global__ void __launch_bounds__(128) k_cm_vertex(Ctx c, CmArgs A, unsigned nsv) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsv || A.fix_index[i] != 0 || !cw_vertex(A.active, i)) return;
+    const float4 cp = c.vcp[i];
+    if (!(cp.w > 0.0f)) return;
+    const V3 p = ld3c(c.x, i), ps = ld3c(c.x0, i);
+    const float ext = 0.5f * cp.x + cp.y;
+    Box q;
+    q.lx = p.x - ext; q.ly = p.y - ext; q.lz = p.z - ext; q.hx = p.x + ext; q.hy = p.y + ext; q.hz = p.z + ext;
+    const M3 Hii = elastic_block(c, i, i);
+    unsigned count = 0;
+    const bool ok = bvh_query(A.sface, q, [&](unsigned fi) {
+        const uint4 f = A.sfaces[fi];
+        const float4 sp = A.sfcp[fi];
+        CmeshOut o;
+        if (!cmesh_vertex_face(p, ps, ld3c(A.sx, f.x), ld3c(A.sx, f.y), ld3c(A.sx, f.z), cp.y + sp.y, 0.5f * (cp.x + sp.x),
+                               combine_friction(cp.z, sp.z, c.friction_mode), cp.w, Hii, c.friction_eps, o)) return;
+        const unsigned idx[1] = {i};
+        cm_scatter<1>(c, idx, o);
+        ++count;
+    });
+    cm_count(A, count, ok);
+}
+
+__global__ void __launch_bounds__(128) k_cm_edge(Ctx c, CmArgs A, unsigned ne) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne || c.efixed[i]) return;
+    const float4 cp = c.ecp[i];
+    const uint2 ev = c.edge[i];
+    if (!(cp.w > 0.0f) || !cw_edge(A.active, ev)) return;
+    const V3 P[2] = {ld3c(c.x, ev.x), ld3c(c.x, ev.y)}, Ps[2] = {ld3c(c.x0, ev.x), ld3c(c.x0, ev.y)};
+    const float ext = 0.5f * cp.x + cp.y;
+    Box q;
+    q.lx = fminf(P[0].x, P[1].x) - ext; q.ly = fminf(P[0].y, P[1].y) - ext; q.lz = fminf(P[0].z, P[1].z) - ext;
+    q.hx = fmaxf(P[0].x, P[1].x) + ext; q.hy = fmaxf(P[0].y, P[1].y) + ext; q.hz = fmaxf(P[0].z, P[1].z) + ext;
+    const unsigned idx[2] = {ev.x, ev.y};
+    const float vmass[2] = {c.vcp[ev.x].w, c.vcp[ev.y].w};
+    M3 B[2][2];
+    bool have = false;
+    unsigned count = 0;
+    const bool ok = bvh_query(A.sedge, q, [&](unsigned ei) {
+        if (!have) {
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) B[a][b] = elastic_block(c, idx[a], idx[b]);
+            have = true;
+        }
+        const uint2 se = A.sedges[ei];
+        const float4 sp = A.secp[ei];
+        CmeshOut o;
+        if (!cmesh_edge_edge(P, Ps, ld3c(A.sx, se.x), ld3c(A.sx, se.y), cp.y + sp.y, 0.5f * (cp.x + sp.x), combine_friction(cp.z, sp.z, c.friction_mode),
+                             vmass, B, c.friction_eps, o)) return;
+        cm_scatter<2>(c, idx, o);
+        ++count;
+    });
+    cm_count(A, count, ok);
+}
+
+__global__ void __launch_bounds__(128) k_cm_face(Ctx c, CmArgs A, unsigned nf) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || c.ffixed[i]) return;
+    const float4 cp = c.fcp[i];
+    const uint4 fv = c.face[i];
+    if (!(cp.w > 0.0f) || !cw_face(A.active, fv)) return;
+    const V3 X[3] = {ld3c(c.x, fv.x), ld3c(c.x, fv.y), ld3c(c.x, fv.z)}, Xs[3] = {ld3c(c.x0, fv.x), ld3c(c.x0, fv.y), ld3c(c.x0, fv.z)};
+    const float ext = 0.5f * cp.x + cp.y;
+    Box q;
+    q.lx = fminf(X[0].x, fminf(X[1].x, X[2].x)) - ext; q.ly = fminf(X[0].y, fminf(X[1].y, X[2].y)) - ext; q.lz = fminf(X[0].z, fminf(X[1].z, X[2].z)) - ext;
+    q.hx = fmaxf(X[0].x, fmaxf(X[1].x, X[2].x)) + ext; q.hy = fmaxf(X[0].y, fmaxf(X[1].y, X[2].y)) + ext; q.hz = fmaxf(X[0].z, fmaxf(X[1].z, X[2].z)) + ext;
+    const unsigned idx[3] = {fv.x, fv.y, fv.z};
+    const float vmass[3] = {c.vcp[fv.x].w, c.vcp[fv.y].w, c.vcp[fv.z].w};
+    M3 B[3][3];
+    bool have = false;
+    unsigned count = 0;
+    const bool ok = bvh_query(A.svert, q, [&](unsigned vi) {
+        if (!have) {
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) B[a][b] = elastic_block(c, idx[a], idx[b]);
+            have = true;
+        }
+        const float4 sp = A.svcp[vi];
+        CmeshOut o;
+        if (!cmesh_face_vertex(ld3c(A.sx, vi), X, Xs, cp.y + sp.y, 0.5f * (cp.x + sp.x), combine_friction(cp.z, sp.z, c.friction_mode), vmass, B,
+                               c.friction_eps, o)) return;
+        cm_scatter<3>(c, idx, o);
+        ++count;
+    });
+    cm_count(A, count, ok);
+}
+
+unsigned assemble_collision_mesh(State &s, const PpfParamSet &prm) {
+    if (!s.cm_nv || prm.disable_contact) return 0;
+    cudaStream_t q = s.stream;
+    unsigned *cnt = s.counters.p + 34; // [34] count, [35] traversal error
+    CUDA_OK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned), q));
+    Ctx c = make_ctx(s, prm);
+    const CmArgs A = make_cm_args(s, cnt);
+    if (s.cm_nf && s.nsv) k_cm_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(c, A, s.nsv);
+    if (s.cm_ne && s.ne) k_cm_edge<<<div_up(s.ne, 128), 128, 0, q>>>(c, A, s.ne);
+    if (s.nf) k_cm_face<<<div_up(s.nf, 128), 128, 0, q>>>(c, A, s.nf);
+    LAUNCH_COUNT(3);
+    unsigned h[2];
+    CUDA_OK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    if (h[1]) fatal(4, "BVH traversal stack overflow against the static collision mesh");
+    return h[0];
+}
+
+// swept box of a dynamic element over x0 -> x0 + max_t (x1 - x0), grown by ext
+__device__ __forceinline__ void cm_sweep(Box &q, const V3 &a0, const V3 &a1, float max_t, float ext, bool first) {
+    const V3 z = max_t * (a1 - a0) + a0;
+    const float lx = fminf(a0.x, z.x) - ext, ly = fminf(a0.y, z.y) - ext, lz = fminf(a0.z, z.z) - ext;
+    const float hx = fmaxf(a0.x, z.x) + ext, hy = fmaxf(a0.y, z.y) + ext, hz = fmaxf(a0.z, z.z) + ext;
+    if (first) { q.lx = lx; q.ly = ly; q.lz = lz; q.hx = hx; q.hy = hy; q.hz = hz; }
+    else { q.lx = fminf(q.lx, lx); q.ly = fminf(q.ly, ly); q.lz = fminf(q.lz, lz); q.hx = fmaxf(q.hx, hx); q.hy = fmaxf(q.hy, hy); q.hz = fmaxf(q.hz, hz); }
+}
+__global__ void __launch_bounds__(128) k_cm_ccd_vertex(CcdCtx c, CmArgs A, unsigned nsv) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsv || A.fix_index[i] != 0 || !cw_vertex(A.active, i)) return;
+    const float4 cp = c.vcp[i];
+    if (cp.w == 0.0f) return;
+    const V3 p0 = ld3c(c.x0, i), p1 = ld3c(c.x1, i);
+    Box q;
+    cm_sweep(q, p0, p1, c.max_t, 0.5f * cp.x + cp.y, true);
+    const bool ok = bvh_query(A.sface, q, [&](unsigned fi) {
+        const uint4 f = A.sfaces[fi];
+        const float4 sp = A.sfcp[fi];
+        const V3 t0 = ld3c(A.sx, f.x), t1 = ld3c(A.sx, f.y), t2 = ld3c(A.sx, f.z);
+        CcdOverlap ov{0u, -1.0f, -1.0f};
+        const float result = point_triangle_ccd(p0, p1, t0, t1, t2, t0, t1, t2, cp.y + sp.y, 0.5f * (cp.x + sp.x), c.max_t, c.ccd_eps, ov);
+        ccd_commit(c, result, ov, i, f.x, 3u);
+    });
+    if (!ok) atomicExch(A.counter + 1, 1u);
+}
+__global__ void __launch_bounds__(128) k_cm_ccd_edge(CcdCtx c, CmArgs A, unsigned ne) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne || c.efixed[i]) return;
+    const float4 cp = c.ecp[i];
+    const uint2 ev = c.edge[i];
+    if (!(cp.w > 0.0f) || !cw_edge(A.active, ev)) return;
+    const V3 a0 = ld3c(c.x0, ev.x), b0 = ld3c(c.x0, ev.y), a1 = ld3c(c.x1, ev.x), b1 = ld3c(c.x1, ev.y);
+    const float ext = 0.5f * cp.x + cp.y;
+    Box q;
+    cm_sweep(q, a0, a1, c.max_t, ext, true);
+    cm_sweep(q, b0, b1, c.max_t, ext, false);
+    const bool ok = bvh_query(A.sedge, q, [&](unsigned ei) {
+        const uint2 se = A.sedges[ei];
+        const float4 sp = A.secp[ei];
+        const V3 q0 = ld3c(A.sx, se.x), q1 = ld3c(A.sx, se.y);
+        CcdOverlap ov{0u, -1.0f, -1.0f};
+        const float result = edge_edge_ccd(a0, b0, q0, q1, a1, b1, q0, q1, cp.y + sp.y, 0.5f * (cp.x + sp.x), c.max_t, c.ccd_eps, ov);
+        ccd_commit(c, result, ov, ev.x, se.x, 5u);
+    });
+    if (!ok) atomicExch(A.counter + 1, 1u);
+}
+__global__ void __launch_bounds__(128) k_cm_ccd_face(CcdCtx c, CmArgs A, unsigned nf) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || c.ffixed[i]) return;
+    const float4 cp = c.fcp[i];
+    const uint4 fv = c.face[i];
+    if (!(cp.w > 0.0f) || !cw_face(A.active, fv)) return;
+    const V3 t00 = ld3c(c.x0, fv.x), t01 = ld3c(c.x0, fv.y), t02 = ld3c(c.x0, fv.z), t10 = ld3c(c.x1, fv.x), t11 = ld3c(c.x1, fv.y), t12 = ld3c(c.x1, fv.z);
+    const float ext = 0.5f * cp.x + cp.y;
+    Box q;
+    cm_sweep(q, t00, t10, c.max_t, ext, true);
+    cm_sweep(q, t01, t11, c.max_t, ext, false);
+    cm_sweep(q, t02, t12, c.max_t, ext, false);
+    const bool ok = bvh_query(A.svert, q, [&](unsigned vi) {
+        const float4 sp = A.svcp[vi];
+        const V3 p = ld3c(A.sx, vi);
+        CcdOverlap ov{0u, -1.0f, -1.0f};
+        const float result = point_triangle_ccd(p, p, t00, t01, t02, t10, t11, t12, cp.y + sp.y, 0.5f * (cp.x + sp.x), c.max_t, c.ccd_eps, ov);
+        ccd_commit(c, result, ov, fv.x, vi, 4u);
+    });
+    if (!ok) atomicExch(A.counter + 1, 1u);
+}
+
+// fraction of the step x0 -> x1 that stays clear of the static collision mesh (1 = the whole step)
+float collision_mesh_line_search(State &s, const float4 *x0, const float4 *x1, const PpfParamSet &prm, bool &overlap) {
+    overlap = false;
+    if (!s.cm_nv || prm.disable_contact) return 1.0f;
+    cudaStream_t q = s.stream;
+    CcdCtx c;
+    c.x0 = x0; c.x1 = x1; c.vcp = s.vcp.p; c.ecp = s.ecp.p; c.fcp = s.fcp.p; c.face = s.face.p; c.edge = s.edge.p;
+    c.vfixed = s.vfixed.p; c.efixed = s.efixed.p; c.ffixed = s.ffixed.p; c.vcollider = s.vcollider.p;
+    c.max_t = prm.line_search_max_t; c.ccd_eps = prm.ccd_eps;
+    unsigned *w = s.counters.p + 48; // [48] toi bits, [49..52] overlap info, [53] unused, [54] traversal error
+    const float max_t = prm.line_search_max_t;
+    unsigned init[7];
+    memcpy(&init[0], &max_t, sizeof(float));
+    init[1] = 0u; init[2] = 0xFFFFFFFFu; init[3] = 0xFFFFFFFFu; init[4] = 0xFFFFFFFFu; init[5] = 0u; init[6] = 0u;
+    CUDA_OK(cudaMemcpyAsync(w, init, sizeof(init), cudaMemcpyHostToDevice, q));
+    c.toi_bits = w; c.overlap = w + 1;
+    const CmArgs A = make_cm_args(s, w + 5);
+    if (s.cm_nf && s.nsv) k_cm_ccd_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(c, A, s.nsv);
+    if (s.cm_ne && s.ne) k_cm_ccd_edge<<<div_up(s.ne, 128), 128, 0, q>>>(c, A, s.ne);
+    if (s.nf) k_cm_ccd_face<<<div_up(s.nf, 128), 128, 0, q>>>(c, A, s.nf);
+    LAUNCH_COUNT(3);
+    unsigned h[7];
+    CUDA_OK(cudaMemcpyAsync(h, w, sizeof(h), cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    if (h[6]) fatal(4, "BVH traversal stack overflow against the static collision mesh");
+    float toi;
+    memcpy(&toi, &h[0], sizeof(float));
+    overlap = h[1] != 0u;
+    return toi / prm.line_search_max_t;
+}
+
+// ---------------------------------------------------------------------------------------------
 // intersection check (contact.cu:3056-3175, intersect_core.hpp:21-79)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool point_triangle_inside(const float *p, const float *d1, const float *d2) {
@@ -1011,6 +1280,9 @@ struct IsectArgs {
     unsigned *counter; // [0] record counter, [1] error
     int check_offsets;
     const unsigned char *active; // collision windows (see BpArgs)
+    BvhView sface;               // static collision mesh (n = 0 when the scene has none)
+    const float4 *sx;
+    const uint4 *sfaces;
 };
 
 __device__ void record_isect(const IsectArgs &A, unsigned type, unsigned e0, unsigned e1, const V3 *v0, unsigned n0, const V3 *v1, unsigned n1) {
@@ -1048,6 +1320,15 @@ __global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
             record_isect(A, 0, fi, e, fv, 3, evv, 2);
         }
     });
+    if (A.sface.n && emass > 0.0f) // zero-mass edges are static solids themselves (contact.cu:3114-3126)
+        ok &= bvh_query(A.sface, q, [&](unsigned fi) {
+            const uint4 f = A.sfaces[fi];
+            const V3 x0 = ld3c(A.sx, f.x), x1 = ld3c(A.sx, f.y), x2 = ld3c(A.sx, f.z);
+            if (edge_triangle_intersect(y0, y1, x0, x1, x2)) {
+                const V3 fv[3] = {x0, x1, x2}, evv[2] = {y0, y1};
+                record_isect(A, 2, fi, e, fv, 3, evv, 2);
+            }
+        });
     if (A.check_offsets) {
         const float4 ep = A.ecp[e];
         ok &= bvh_query(A.edge, q, [&](unsigned e2) {
@@ -1119,6 +1400,8 @@ bool check_intersection(State &s, const float4 *x, const PpfParamSet &prm) {
     A.records = s.isect_records.p;
     A.counter = s.counters.p + 26;
     A.active = s.has_cw ? s.cw_active.p : nullptr;
+    A.sface = view_of(s.cm_bvh_face); A.sx = s.cm_x.p; A.sfaces = s.cm_face.p;
+    if (!s.cm_nf) A.sface.n = 0;
     A.check_offsets = s.has_offsets ? 1 : 0; // no contact offset anywhere: the "closer than the offsets" tests cannot fire
     CUDA_OK(cudaMemsetAsync(A.counter, 0, 2 * sizeof(unsigned), q));
     if (s.ne) k_isect_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);

@@ -261,6 +261,7 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.pop();
         logging.mark("dyn_consumed", dyn_consumed);
         logging.mark("max_nnz_row", max_nnz_row);
+        num_contact += assemble_collision_mesh(s, prm); // static collision mesh (contact.cu:1834-1947)
         num_contact += assemble_colliders(s, prm); // embed_constraint_force_hessian (main.cu:873): spheres / walls, contact on or off
         logging.mark("num_contact", num_contact);
         s.tm.ms_assembly += t_ph.stop();
@@ -322,6 +323,7 @@ void step_advance(State &s, PpfStepResult *out) {
             t_ph.start();
             bool overlap = false;
             toi = fminf(toi, contact_line_search(s, s.x_old.p, s.eval_x.p, prm, overlap));
+            if (s.cm_nv && !overlap) toi = fminf(toi, collision_mesh_line_search(s, s.x_old.p, s.eval_x.p, prm, overlap));
             s.tm.ms_line_search += t_ph.stop();
             if (overlap) {
                 logging.message("### contact starts overlapping: two surfaces begin the step already touching or overlapping "

@@ -69,6 +69,82 @@ template <class P> static unsigned dedup(std::vector<P> &store, const P &p) { //
     return (unsigned)store.size() - 1;
 }
 
+// scene.rs:1945-2013 + builder.rs:1823-1935 (make_collision_mesh): the static objects merged into one contact-only mesh; face
+// parameters per object (deduplicated), edge / vertex parameters = the area-weighted average of the incident faces
+static void build_static_mesh(Built &b) {
+    const SceneSpec &spec = b.spec;
+    const float ws = float(spec.args.world_scaling);
+    b.cm_vert.clear(); b.cm_face.clear(); b.cm_edge.clear(); b.cm_vprop.clear(); b.cm_eprop.clear(); b.cm_fprop.clear();
+    b.cm_vparam.clear(); b.cm_eparam.clear(); b.cm_fparam.clear();
+    b.cmesh = PpfCollisionMesh{};
+    if (spec.statics.empty()) return;
+    for (const StaticObject &o : spec.statics) {
+        const unsigned base = (unsigned)b.cm_vert.size();
+        for (const Vec3d &p : o.vert) {
+            PpfVec3f q;
+            for (int k = 0; k < 3; ++k) q.v[k] = (float(p[k]) + float(o.displacement[k])) * ws;
+            b.cm_vert.push_back(q);
+        }
+        PpfFaceParam pa{};
+        pa.model = PPF_MODEL_BARAFFWITKIN; // Model::default()
+        pa.friction = float(o.friction); pa.ghat = float(o.contact_gap) * ws; pa.offset = float(o.contact_offset) * ws;
+        pa.shrink_x = pa.shrink_y = 1.0f;
+        const unsigned pi = dedup(b.cm_fparam, pa);
+        for (const auto &t : o.tri) {
+            PpfVec3u f; for (int k = 0; k < 3; ++k) f.v[k] = base + t[k];
+            const Vec3f x0{b.cm_vert[f.v[0]].v[0], b.cm_vert[f.v[0]].v[1], b.cm_vert[f.v[0]].v[2]}, x1{b.cm_vert[f.v[1]].v[0], b.cm_vert[f.v[1]].v[1], b.cm_vert[f.v[1]].v[2]},
+                x2{b.cm_vert[f.v[2]].v[0], b.cm_vert[f.v[2]].v[1], b.cm_vert[f.v[2]].v[2]};
+            PpfFaceProp fp{};
+            fp.area = 0.5f * norm(cross(sub(x1, x0), sub(x2, x0)));
+            if (!(fp.area > 0.0f)) throw std::runtime_error("degenerate static face");
+            fp.param_index = pi;
+            b.cm_face.push_back(f); b.cm_fprop.push_back(fp);
+        }
+    }
+    const unsigned nv = (unsigned)b.cm_vert.size(), nf = (unsigned)b.cm_face.size();
+    // unique undirected edges in order of first appearance over the face rows (mesh.rs:66-123)
+    std::map<std::pair<unsigned, unsigned>, unsigned> edge_of;
+    std::vector<std::vector<unsigned>> edge_faces, vert_faces(nv);
+    for (unsigned i = 0; i < nf; ++i)
+        for (int k = 0; k < 3; ++k) {
+            vert_faces[b.cm_face[i].v[k]].push_back(i);
+            unsigned a = b.cm_face[i].v[k], c = b.cm_face[i].v[(k + 1) % 3];
+            if (a > c) std::swap(a, c);
+            auto it = edge_of.find({a, c});
+            if (it == edge_of.end()) { it = edge_of.emplace(std::make_pair(a, c), (unsigned)b.cm_edge.size()).first; b.cm_edge.push_back(PpfVec2u{{a, c}}); edge_faces.push_back({}); }
+            edge_faces[it->second].push_back(i);
+        }
+    auto weighted = [&](const std::vector<unsigned> &faces, float &ghat, float &offset, float &friction) { // builder.rs:1770-1795
+        float gs = 0.0f, os = 0.0f, fs = 0.0f, as = 0.0f;
+        for (unsigned j : faces) {
+            const PpfFaceParam &pa = b.cm_fparam[b.cm_fprop[j].param_index];
+            const float area = b.cm_fprop[j].area;
+            gs += area * pa.ghat; os += area * pa.offset; fs += area * pa.friction; as += area;
+        }
+        ghat = gs / as; offset = os / as; friction = fs / as;
+    };
+    for (unsigned i = 0; i < b.cm_edge.size(); ++i) {
+        PpfEdgeParam pa{};
+        weighted(edge_faces[i], pa.ghat, pa.offset, pa.friction);
+        PpfEdgeProp ep{};
+        ep.param_index = dedup(b.cm_eparam, pa);
+        b.cm_eprop.push_back(ep);
+    }
+    for (unsigned i = 0; i < nv; ++i) {
+        if (vert_faces[i].empty()) throw std::runtime_error("static vertex without a face");
+        PpfVertexParam pa{};
+        weighted(vert_faces[i], pa.ghat, pa.offset, pa.friction);
+        PpfVertexProp vp{};
+        vp.rest_bend_angle = 3.14159265358979323846f;
+        vp.param_index = dedup(b.cm_vparam, pa);
+        b.cm_vprop.push_back(vp);
+    }
+    PpfCollisionMesh &m = b.cmesh;
+    set_vec(m.vertex, b.cm_vert); set_vec(m.face, b.cm_face); set_vec(m.edge, b.cm_edge);
+    set_vec(m.prop.vertex, b.cm_vprop); set_vec(m.prop.edge, b.cm_eprop); set_vec(m.prop.face, b.cm_fprop);
+    set_vec(m.param_arrays.vertex, b.cm_vparam); set_vec(m.param_arrays.edge, b.cm_eparam); set_vec(m.param_arrays.face, b.cm_fparam);
+}
+
 void build_scene(const SceneSpec &spec, Built &b) {
     b = Built{};
     b.spec = spec;
@@ -263,6 +339,7 @@ void build_scene(const SceneSpec &spec, Built &b) {
         q.stiffness = float(st.stiffness);
         b.stitch.push_back(q);
     }
+    build_static_mesh(b);
     make_constraint(b, 0.0, 0.0);
 
     // ---- builder.rs:388-432 fixed flags ----

@@ -106,9 +106,17 @@ struct StitchSpec {
     std::array<double, 3> src_weight{1, 0, 0}, dst_weight{1, 0, 0};
     double stiffness = 1.0; // "stitch-stiffness"
 };
+// a static triangle mesh the simulated objects collide with (scene.rs:1945-2013 static_vert / static_tri -> Constraint.mesh)
+struct StaticObject {
+    std::vector<Vec3d> vert;
+    std::vector<std::array<unsigned, 3>> tri;
+    Vec3d displacement{0, 0, 0};
+    double contact_gap = 1e-3, contact_offset = 0.0, friction = 0.0;
+};
 struct SceneSpec {
     std::string name;
     std::vector<ShellObject> objects;
+    std::vector<StaticObject> statics;
     std::vector<StitchSpec> stitches;
     std::vector<WallCollider> walls;
     std::vector<SphereCollider> spheres;
@@ -167,6 +175,11 @@ struct Built {
     // constraint storage (rebuilt every step)
     std::vector<PpfFixPair> fix; std::vector<PpfPullPair> pull;
     std::vector<PpfSphere> sphere; std::vector<PpfFloor> floor;
+    // static collision mesh (builder.rs:1823-1935 make_collision_mesh): all static objects merged
+    std::vector<PpfVec3f> cm_vert; std::vector<PpfVec3u> cm_face; std::vector<PpfVec2u> cm_edge;
+    std::vector<PpfVertexProp> cm_vprop; std::vector<PpfEdgeProp> cm_eprop; std::vector<PpfFaceProp> cm_fprop;
+    std::vector<PpfVertexParam> cm_vparam; std::vector<PpfEdgeParam> cm_eparam; std::vector<PpfFaceParam> cm_fparam;
+    PpfCollisionMesh cmesh{};
     std::vector<PpfStitch> stitch; std::vector<unsigned> stitch_slots;
     PpfDataSet dataset;
     PpfParamSet param;

@@ -607,6 +607,31 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.friction_mode = "min";
         return s;
     }
+    if (name == "drape-mesh") { // test scene: `drape` with the colliders as STATIC TRIANGLE MESHES (Constraint.mesh): an icosphere
+        // standing on a ground square, both with friction; the sheet is thrown onto them
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_square(n ? n : 32, 1.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+        o.param = tri_defaults();
+        o.param["friction"] = 0.3;
+        o.displacement = Vec3d{0.03, 0.45, 0.02};
+        o.velocity = Vec3d{0, -3.0, 0};
+        s.objects.push_back(o);
+        StaticObject ball;
+        gen_icosphere(0.4, (n == 0 || n >= 32) ? 3u : 2u, ball.vert, ball.tri);
+        ball.friction = 0.3;
+        s.statics.push_back(ball);
+        StaticObject ground;
+        gen_square(8, 3.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, ground.vert, ground.tri);
+        ground.displacement = Vec3d{0, -0.42, 0};
+        ground.friction = 0.3;
+        s.statics.push_back(ground);
+        s.args.frames = 120;
+        s.args.dt = 1e-2;
+        s.args.friction_mode = "min";
+        return s;
+    }
     if (name == "seam") { // test scene: two sheets side by side joined by a row of stitches; the first hangs from two corners, the second from the seam
         SceneSpec s;
         s.name = name;
@@ -829,6 +854,7 @@ void make_constraint(Built &b, double time, double prev_time) {
     }
     PpfConstraint &c = b.constraint;
     c = PpfConstraint{};
+    c.mesh = b.cmesh;
     c.stitch.data = b.stitch.data();
     c.stitch.size = c.stitch.allocated = (unsigned)b.stitch.size();
     c.floor.data = b.floor.data();

@@ -2,6 +2,7 @@
 // compiled for the host in the tests only, -ffp-contract=off) under the same C signatures as
 // oracle/oracle_shim.c, so tests/test_oracle_cpu.py runs one set of known-answer checks over both.
 #include "../../ppf-contact-solver_b200/csrc/math_accd.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_cmesh.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_collider.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_contact.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_damping.cuh"
@@ -195,3 +196,26 @@ SHIM float orc_rod_bend_plasticity(const float *x9, float rest, float threshold,
 }
 
 SHIM void orc_barrier(int kind, float g, float ghat, float offset, float *out2) { out2[0] = barrier_gradient(g, ghat, offset, kind); out2[1] = barrier_curvature(g, ghat, offset, kind); }
+
+// static collision mesh (math_cmesh.cuh); same argument layout as the oracle's shim
+SHIM void orc_cmesh(int kind, const float *dyn, const float *sta, const float *par, const float *B, float *out16) {
+    CmeshOut o;
+    o.f = mk(0.f, 0.f, 0.f); o.H = m3_zero(); o.c[0] = o.c[1] = o.c[2] = 0.0f;
+    bool hit;
+    if (kind == 0) {
+        M3 Hii; for (int e = 0; e < 9; ++e) Hii.m[e] = B[e];
+        hit = cmesh_vertex_face(v(dyn), v(dyn + 3), v(sta), v(sta + 3), v(sta + 6), par[0], par[1], par[2], par[4], Hii, par[3], o);
+    } else if (kind == 1) {
+        V3 X[3], Xs[3]; M3 Bl[3][3];
+        for (int a = 0; a < 3; ++a) { X[a] = v(dyn + 3 * a); Xs[a] = v(dyn + 9 + 3 * a); for (int b = 0; b < 3; ++b) for (int e = 0; e < 9; ++e) Bl[a][b].m[e] = B[(a * 3 + b) * 9 + e]; }
+        hit = cmesh_face_vertex(v(sta), X, Xs, par[0], par[1], par[2], par + 4, Bl, par[3], o);
+    } else {
+        V3 P[2], Ps[2]; M3 Bl[2][2];
+        for (int a = 0; a < 2; ++a) { P[a] = v(dyn + 3 * a); Ps[a] = v(dyn + 6 + 3 * a); for (int b = 0; b < 2; ++b) for (int e = 0; e < 9; ++e) Bl[a][b].m[e] = B[(a * 2 + b) * 9 + e]; }
+        hit = cmesh_edge_edge(P, Ps, v(sta), v(sta + 3), par[0], par[1], par[2], par + 4, Bl, par[3], o);
+    }
+    out16[0] = hit ? 1.0f : 0.0f;
+    out16[1] = o.f.x; out16[2] = o.f.y; out16[3] = o.f.z;
+    for (int k = 0; k < 9; ++k) out16[4 + k] = o.H.m[k];
+    for (int k = 0; k < 3; ++k) out16[13 + k] = o.c[k];
+}

@@ -369,3 +369,68 @@ def test_oracle_runs_the_twist_with_the_other_barriers(run_job, kind):
     assert r["ok"].all() and np.asarray(r["log_num_contact"]).max() > 0
     assert np.isfinite(r["curr"]).all()
     assert not np.array_equal(r["curr"], c["curr"])
+
+
+def test_static_collision_mesh_math_oracle_equals_backend_header(libs):
+    """Constraint.mesh contacts (contact.cu:899-1151): dynamic vertex / face / edge against a static face / vertex / edge --
+    the oracle's plain C and the backend's math_cmesh.cuh compiled for the host, bit for bit, on random close configurations;
+    plus first principles: the force pushes the dynamic element away from the static one and vanishes beyond offset + ghat."""
+    o, b = libs
+    rng = np.random.default_rng(11)
+    hits = [0, 0, 0]
+    for trial in range(600):
+        kind = trial % 3
+        n = (1, 3, 2)[kind]
+        ghat, offset = np.float32(2e-3), np.float32(rng.choice([0.0, 5e-4]))
+        sta_n = (3, 1, 2)[kind]
+        sta = rng.uniform(-0.05, 0.05, size=(sta_n, 3)).astype(np.float32)
+        sta[:, 1] = rng.uniform(-2e-4, 2e-4, size=sta_n)                       # static element near the plane y = 0
+        height = rng.uniform(float(offset) + 2e-4, float(offset + ghat) * 1.3)  # inside the gap most of the time
+        dyn_eval = rng.uniform(-0.03, 0.03, size=(n, 3)).astype(np.float32)
+        dyn_eval[:, 1] = height + rng.uniform(0, 2e-4, size=n)
+        if kind == 2:                                                           # crossing edges
+            sta[:, 0] = [-0.05, 0.05]; sta[:, 2] = 0.0
+            dyn_eval[:, 2] = [-0.04, 0.04]; dyn_eval[:, 0] = rng.uniform(-0.01, 0.01, size=2)
+        if kind == 1:                                                           # the static vertex under the dynamic face
+            dyn_eval[:, 0] = [-0.03, 0.03, 0.0]; dyn_eval[:, 2] = [-0.02, -0.02, 0.03]; sta[0, 0] = sta[0, 2] = 0.0
+        if kind == 0:
+            sta[:, 0] = [-0.05, 0.05, 0.0]; sta[:, 2] = [-0.04, -0.04, 0.05]; dyn_eval[0, 0] = dyn_eval[0, 2] = 0.0
+        dyn_start = (dyn_eval + rng.normal(0, 3e-4, size=dyn_eval.shape)).astype(np.float32)
+        dyn = np.concatenate([dyn_eval.ravel(), dyn_start.ravel()]).astype(np.float32)
+        mass = rng.uniform(1e-4, 1e-3, size=3).astype(np.float32)
+        par = np.concatenate([[offset, ghat, rng.choice([0.0, 0.4]), 1e-5], mass]).astype(np.float32)
+        A = rng.normal(size=(3 * n, 3 * n)); A = (A @ A.T * 10.0)
+        B = np.zeros((n, n, 9), np.float32)
+        for i in range(n):
+            for j in range(n):
+                B[i, j] = A[3 * i:3 * i + 3, 3 * j:3 * j + 3].T.ravel()          # column-major blocks
+        outs = []
+        for l in (o, b):
+            out = np.full(16, np.nan, np.float32)
+            l.orc_cmesh(C.c_int(kind), fp(dyn), fp(np.ascontiguousarray(sta.ravel())), fp(par), fp(np.ascontiguousarray(B.ravel())), fp(out))
+            outs.append(out)
+        assert same_bits(outs[0], outs[1]).all(), (kind, outs)
+        out = outs[0]
+        if out[0]:
+            hits[kind] += 1
+            assert out[2] < 0 or abs(out[2]) > 0                                # a force exists ...
+            assert -out[2] > 0                                                  # ... and f = dE/dx points down: the element is pushed up (-f)
+            assert abs(out[13:13 + n].sum() - 1.0) < 1e-5
+            H = out[4:13].reshape(3, 3)
+            assert np.allclose(H, H.T, atol=1e-6 * np.abs(H).max()) and np.linalg.eigvalsh(H.astype(np.float64)).min() > -1e-5 * np.abs(H).max()
+        else:
+            assert height + 2e-4 >= float(offset + ghat) - 4e-4                 # misses only near / beyond the gap
+    assert min(hits) > 50
+
+
+def test_oracle_drapes_a_sheet_over_static_meshes(run_job):
+    """`drape-mesh`: the sheet thrown onto a static icosphere standing on a static ground square (Constraint.mesh): contacts
+    appear, the line search cuts the steps, nothing passes through the meshes (the step's own intersection check covers the
+    dynamic edges against the static faces) and the sheet ends up lying on the ball."""
+    r = run_job({"lib": "oracle", "scene": "drape-mesh", "n": 16, "state": None, "steps": 14}, force_subprocess=True)
+    assert bool(r["ok"].all())
+    assert r["log_num_contact"].max() > 15 and r["log_toi"].min() < 0.5
+    x = r["curr"].astype(np.float64)
+    assert np.isfinite(x).all()
+    assert np.linalg.norm(x, axis=1).min() > 0.37          # the icosphere's faces lie up to 4 % inside the radius 0.4
+    assert x[:, 1].min() > -0.42

@@ -221,3 +221,23 @@ def test_drape_first_contacts_match_the_oracle(run_job):
     assert abs(float(g["time"][0]) - float(o["time"][0])) < 0.3 * float(o["time"][0])
     x = g["curr"].astype(np.float64)
     assert np.isfinite(x).all() and np.linalg.norm(x, axis=1).min() > 0.4 and x[:, 1].min() > -0.08   # outside the sphere, above the floor
+
+
+def test_static_collision_mesh_matches_the_oracle(run_job):
+    """`drape-mesh`: contacts with the static collision mesh (k_cm_vertex / k_cm_edge / k_cm_face, their line-search kernels
+    and the static part of the intersection check) against the CPU oracle: same contact counts and line-search cuts through
+    the first touch, same positions"""
+    job = {"scene": "drape-mesh", "n": 24, "state": None, "steps": 7, "dump_linsys": True}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    assert abs(len(g["log_num_contact"]) - len(o["log_num_contact"])) <= 2 and o["log_num_contact"].max() > 15
+    first_g, first_o = int(np.argmax(g["log_num_contact"] > 0)), int(np.argmax(o["log_num_contact"] > 0))
+    assert abs(first_g - first_o) <= 1 and first_o > 0
+    assert abs(g["log_num_contact"][-1] - o["log_num_contact"][-1]) <= 3 + 0.25 * o["log_num_contact"][-1]
+    assert abs(float(g["time"][0]) - float(o["time"][0])) < 0.1 * float(o["time"][0])
+    x = g["curr"].astype(np.float64)
+    assert np.isfinite(x).all() and np.linalg.norm(x, axis=1).min() > 0.37 and x[:, 1].min() > -0.42
+    if len(g["log_num_contact"]) == len(o["log_num_contact"]) and abs(float(g["time"][0]) - float(o["time"][0])) < 1e-5:
+        d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+        assert float(np.median(d)) < 1e-4 and float(d.max()) < 3e-3, (float(np.median(d)), float(d.max()))
