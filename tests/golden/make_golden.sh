@@ -50,7 +50,12 @@ case "$1" in
      gen sheet_damped_n24 sheet-damped 24 20 20 00020
      gen woven_damped_n32 woven-damped 32 60 60 00060
      gen seam_n16 seam 16 40 40 00040
-     gen sheet_plastic_n24 sheet-plastic 24 20 20 00020 ;;
+     gen sheet_plastic_n24 sheet-plastic 24 20 20 00020
+     gen sheet_fixxz_n24 sheet-fixxz 24 20 20 00020
+     gen drape_mesh_n24 drape-mesh 24 40 20 00020 00040
+     gen headless_cw_closed_n24 headless-cw-closed 24 68 68 00068
+     gen fast_twist_quad_n16 fast-twist@quad 16 60 30 00030 00060
+     gen fast_twist_log_n16 fast-twist@log 16 60 30 00030 00060 ;;
   *) gen fast_twist_n16 fast-twist 16 90 30 00030 00060 00090
      gen fast_twist_n24 fast-twist 24 80 40 00040 00080
      gen five_twist_n24 five-twist 24 100 50 00050 00100
