@@ -532,4 +532,93 @@ static inline int o_cmesh_edge_edge(const float (*P)[3], const float (*Ps)[3], c
     return 1;
 }
 
+
+/* ---- torque pins (TEST INFRASTRUCTURE restatement of energy/energy.cu:20-86, 643-701, 221-246) ------------------- */
+static inline void o_eigen_sym3x3(float a00, float a01, float a02, float a11, float a12, float a22, float evecs[3][3] /* [column][component] */) {
+    const float q = (a00 + a11 + a22) / 3.0f;
+    const float p2 = (a00 - q) * (a00 - q) + (a11 - q) * (a11 - q) + (a22 - q) * (a22 - q) + 2.0f * (a01 * a01 + a02 * a02 + a12 * a12);
+    const float p = sqrtf(fmaxf(p2 / 6.0f, 0.0f));
+    float lam0, lam1, lam2;
+    if (p < 1e-12f) { lam0 = a00; lam1 = a11; lam2 = a22; }
+    else {
+        const float inv_p = 1.0f / p;
+        const float b00 = (a00 - q) * inv_p, b01 = a01 * inv_p, b02 = a02 * inv_p, b11 = (a11 - q) * inv_p, b12 = a12 * inv_p, b22 = (a22 - q) * inv_p;
+        const float det_b = b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02);
+        const float r = fminf(1.0f, fmaxf(-1.0f, det_b * 0.5f));
+        const float phi = acosf(r) / 3.0f;
+        lam0 = q + 2.0f * p * cosf(phi);
+        lam2 = q + 2.0f * p * cosf(phi + 2.0943951f);
+        lam1 = 3.0f * q - lam0 - lam2;
+    }
+    float t;
+    if (lam1 > lam0) { t = lam0; lam0 = lam1; lam1 = t; }
+    if (lam2 > lam0) { t = lam0; lam0 = lam2; lam2 = t; }
+    if (lam2 > lam1) { t = lam1; lam1 = lam2; lam2 = t; }
+    const float vals[3] = {lam0, lam1, lam2};
+    for (int c = 0; c < 3; ++c) {
+        const float l = vals[c];
+        const float r0[3] = {a00 - l, a01, a02}, r1[3] = {a01, a11 - l, a12}, r2[3] = {a02, a12, a22 - l};
+        float v[3];
+        o_cross(r0, r1, v);
+        float vn = sqrtf(o_dot(v, v));
+        if (vn < 1e-8f) { o_cross(r0, r2, v); vn = sqrtf(o_dot(v, v)); }
+        if (vn < 1e-8f) { o_cross(r1, r2, v); vn = sqrtf(o_dot(v, v)); }
+        for (int k = 0; k < 3; ++k) evecs[c][k] = vn > 1e-8f ? v[k] / vn : (k == c ? 1.0f : 0.0f);
+    }
+    float e0[3], e1[3], e2[3];
+    o_normalize(evecs[0], e0);
+    const float d = o_dot(e0, evecs[1]);
+    for (int k = 0; k < 3; ++k) e1[k] = evecs[1][k] - e0[k] * d;
+    o_normalize(e1, e1);
+    o_cross(e0, e1, e2);
+    for (int k = 0; k < 3; ++k) { evecs[0][k] = e0[k]; evecs[1][k] = e1[k]; evecs[2][k] = e2[k]; }
+}
+/* group g: vertices tv_index[vs .. vs+vn); x = 3 floats per vertex, mass per vertex; out7 = centre, axis, 1 / sum |r_perp|^2 */
+static inline void o_torque_group(unsigned axis_component, unsigned vs, unsigned vn, unsigned hint_vertex, const unsigned *tv_index, const float *x,
+                                  const float *mass, float *out7) {
+    float center[3] = {0.0f, 0.0f, 0.0f}, total_mass = 0.0f;
+    for (unsigned k = vs; k < vs + vn; ++k) {
+        const unsigned idx = tv_index[k];
+        const float m = mass[idx];
+        for (int q = 0; q < 3; ++q) center[q] = center[q] + x[3 * (size_t)idx + q] * m;
+        total_mass += m;
+    }
+    if (total_mass > 1e-12f) { const float s = 1.0f / total_mass; for (int q = 0; q < 3; ++q) center[q] = center[q] * s; }
+    float c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+    for (unsigned k = vs; k < vs + vn; ++k) {
+        float d[3];
+        o_sub(x + 3 * (size_t)tv_index[k], center, d);
+        c00 += d[0] * d[0]; c01 += d[0] * d[1]; c02 += d[0] * d[2]; c11 += d[1] * d[1]; c12 += d[1] * d[2]; c22 += d[2] * d[2];
+    }
+    const float inv_n = 1.0f / (float)vn;
+    c00 *= inv_n; c01 *= inv_n; c02 *= inv_n; c11 *= inv_n; c12 *= inv_n; c22 *= inv_n;
+    float evecs[3][3], ax[3], hint[3];
+    o_eigen_sym3x3(c00, c01, c02, c11, c12, c22, evecs);
+    o_normalize(evecs[axis_component < 3 ? axis_component : 0], ax);
+    o_sub(x + 3 * (size_t)hint_vertex, center, hint);
+    if (o_dot(ax, hint) < 0.0f) for (int q = 0; q < 3; ++q) ax[q] = -ax[q];
+    float sum = 0.0f;
+    for (unsigned k = vs; k < vs + vn; ++k) {
+        float r[3], rp[3];
+        o_sub(x + 3 * (size_t)tv_index[k], center, r);
+        const float d = o_dot(ax, r);
+        for (int q = 0; q < 3; ++q) rp[q] = r[q] - ax[q] * d;
+        sum += o_dot(rp, rp);
+    }
+    for (int q = 0; q < 3; ++q) { out7[q] = center[q]; out7[3 + q] = ax[q]; }
+    out7[6] = sum > 1e-12f ? 1.0f / sum : 0.0f;
+}
+static inline void o_torque_vertex(const float *y, float magnitude, const float *grp7, float *f, float *H) {
+    const float *center = grp7, *axis = grp7 + 3;
+    float r[3], rp[3], cr[3];
+    o_sub(y, center, r);
+    const float d = o_dot(axis, r);
+    for (int q = 0; q < 3; ++q) rp[q] = r[q] - axis[q] * d;
+    const float scale = magnitude * grp7[6];
+    o_cross(axis, rp, cr);
+    for (int q = 0; q < 3; ++q) f[q] = -(cr[q] * scale);
+    const float sp = fmaxf(0.0f, scale);
+    for (int c = 0; c < 3; ++c) for (int rr = 0; rr < 3; ++rr) H[c * 3 + rr] = sp * ((rr == c ? 1.0f : 0.0f) - axis[rr] * axis[c]);
+}
+
 #endif

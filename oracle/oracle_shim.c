@@ -162,3 +162,11 @@ SHIM void orc_cmesh(int kind, const float *dyn, const float *sta, const float *p
     for (int k = 0; k < 3; ++k) { out16[1 + k] = f[k]; out16[13 + k] = c[k]; }
     for (int k = 0; k < 9; ++k) out16[4 + k] = H[k];
 }
+
+/* torque pins: one group over all n vertices; out = group result (7), then per vertex f[3], H[9] */
+SHIM void orc_torque(const float *x, const float *mass, unsigned n, unsigned axis_component, unsigned hint, float magnitude, float *out) {
+    unsigned idx[256];
+    for (unsigned k = 0; k < n; ++k) idx[k] = k;
+    o_torque_group(axis_component, 0, n, hint, idx, x, mass, out);
+    for (unsigned k = 0; k < n; ++k) o_torque_vertex(x + 3 * k, magnitude, out, out + 7 + 12 * k, out + 7 + 12 * k + 3);
+}

@@ -83,6 +83,17 @@ void apply_constraint(State &s, const PpfConstraint *c) {
     s.pull.upload(c->pull.data, c->pull.size, q);
     s.nstitch = c->stitch.size;
     s.stitches.upload(c->stitch.data, c->stitch.size, q);
+    s.ntgroup = c->torque_groups.size; s.ntvert = c->torque_vertices.size;
+    s.tgroups.upload(c->torque_groups.data, s.ntgroup, q);
+    s.tverts.upload(c->torque_vertices.data, s.ntvert, q);
+    if (s.ntgroup) s.tresult.reserve(size_t(7) * s.ntgroup);
+    for (unsigned k = 0; k < s.ntgroup; ++k) {
+        const PpfTorqueGroup &tg = c->torque_groups.data[k];
+        if (tg.vertex_count == 0 || tg.vertex_start + tg.vertex_count > s.ntvert || tg.hint_vertex >= s.nv || tg.axis_component > 2)
+            fatal(4, "update_constraint: torque group %u is malformed", k);
+    }
+    for (unsigned k = 0; k < s.ntvert; ++k)
+        if (c->torque_vertices.data[k].index >= s.nv || c->torque_vertices.data[k].group_id >= s.ntgroup) fatal(4, "update_constraint: torque vertex %u is malformed", k);
     s.nsphere = c->sphere.size;
     s.nfloor = c->floor.size;
     s.spheres.upload(c->sphere.data, c->sphere.size, q);
@@ -131,7 +142,6 @@ void upload_dataset(State &s) {
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
     if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
     if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
-    if (d.constraint.torque_vertices.size) fatal(4, "B200 backend: torque pins are not implemented");
     if (d.constraint.stitch.size && d.stitch_hess_slots.size != 36u * d.constraint.stitch.size)
         fatal(4, "B200 backend: slot-replay tables are required (stitch_hess_slots)");
     if (prm.disable_pin_dof_removal) fatal(4, "B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
@@ -538,7 +548,6 @@ PPF_EXPORT void update_dyn(unsigned *index, unsigned *offset) {
 }
 
 PPF_EXPORT void update_constraint(const PpfConstraint *constraint) {
-    if (constraint->torque_vertices.size) fatal(4, "B200 backend: torque pins are not implemented");
     // the static collision mesh is taken at initialize, where its trees are built once (the reference never rebuilds them either)
     if (constraint->mesh.vertex.size != g.cm_nv || constraint->mesh.face.size != g.cm_nf)
         fatal(4, "update_constraint: the static collision mesh changed size (%u vertices, %u at initialize)", constraint->mesh.vertex.size, g.cm_nv);

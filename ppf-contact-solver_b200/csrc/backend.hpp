@@ -143,6 +143,11 @@ struct State {
     DBuf<unsigned> rb_slots;                      // 9 per bending vertex (DataSet.rod_bend_hess_slots rows of those vertices)
     DBuf<PpfFixPair> fix;
     DBuf<PpfPullPair> pull;
+    // torque pins (Constraint.torque_groups / torque_vertices, re-sent with every update_constraint)
+    DBuf<PpfTorqueGroup> tgroups;
+    DBuf<PpfTorqueVertex> tverts;
+    DBuf<float> tresult; // 7 floats per group: centre, axis, 1 / sum |r_perp|^2
+    unsigned ntgroup = 0, ntvert = 0;
     DBuf<PpfStitch> stitches;                     // seams of the last update_constraint
     DBuf<unsigned> stitch_slots;                  // 36 per seam (DataSet.stitch_hess_slots)
     unsigned nstitch = 0, nstitch_slots = 0;

@@ -15,6 +15,7 @@
 #include "math_rod.cuh"
 #include "math_stitch.cuh"
 #include "math_strain.cuh"
+#include "math_torque.cuh"
 
 namespace ppf {
 
@@ -676,6 +677,36 @@ float max_stretch_ratio(State &s) {
     return m;
 }
 
+// torque pins (energy.cu:643-701 pre-pass, 221-246 per-vertex force): one thread per group walks its vertices (groups are few
+// and small: a pinned handle), then one thread per torque vertex adds its force and the PSD part of its Hessian
+__global__ void k_torque_groups(unsigned ng, const PpfTorqueGroup *__restrict__ groups, const PpfTorqueVertex *__restrict__ tv,
+                                const float4 *__restrict__ eval_x, const float4 *__restrict__ vcp, float *__restrict__ result) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ng) return;
+    const TorqueGroupResult r = torque_group(groups[g], tv, [&](unsigned v) { return ld3(eval_x, v); }, [&](unsigned v) { return vcp[v].w; });
+    float *o = result + size_t(7) * g;
+    o[0] = r.center.x; o[1] = r.center.y; o[2] = r.center.z; o[3] = r.axis.x; o[4] = r.axis.y; o[5] = r.axis.z; o[6] = r.inv_r_perp_sq_sum;
+}
+__global__ void k_torque_vertices(unsigned n, const PpfTorqueVertex *__restrict__ tv, const float *__restrict__ result,
+                                  const float4 *__restrict__ eval_x, const unsigned *__restrict__ fix_index, float *__restrict__ force,
+                                  float *__restrict__ diag) {
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const PpfTorqueVertex t = tv[j];
+    if (fix_index[t.index] != 0) return; // the momentum term skips prescribed vertices altogether (energy.cu:709-714)
+    const float *o = result + size_t(7) * t.group_id;
+    TorqueGroupResult r;
+    r.center = mk(o[0], o[1], o[2]); r.axis = mk(o[3], o[4], o[5]); r.inv_r_perp_sq_sum = o[6];
+    V3 f;
+    M3 H;
+    torque_vertex(ld3(eval_x, t.index), t.magnitude, r, f, H);
+    float *fo = force + size_t(3) * t.index;
+    atomicAdd(fo + 0, f.x); atomicAdd(fo + 1, f.y); atomicAdd(fo + 2, f.z);
+    float *dg = diag + size_t(9) * t.index;
+    for (int k = 0; k < 9; ++k)
+        if (H.m[k]) atomicAdd(dg + k, H.m[k]);
+}
+
 void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
     MomentumArgs a;
     a.dt = dt; a.air_density = prm.air_density; a.air_friction = prm.air_friction; a.iso_air = prm.isotropic_air_friction; a.fix_xz = prm.fix_xz;
@@ -689,6 +720,11 @@ void assemble_momentum(State &s, float dt, const PpfParamSet &prm) {
     k_momentum<<<div_up(s.nv, 128), 128, 0, s.stream>>>(s.nv, s.curr.p, s.eval_x.p, s.target.p, s.vcp.p, s.varea.p, s.fix_index.p,
                                                         s.pull_index.p, s.pull.p, s.vf_off.p, s.vf_idx.p, s.face.p, a, s.force.p, s.diag.p);
     LAUNCH_COUNT(1);
+    if (s.ntvert) {
+        k_torque_groups<<<div_up(s.ntgroup, 64), 64, 0, s.stream>>>(s.ntgroup, s.tgroups.p, s.tverts.p, s.eval_x.p, s.vcp.p, s.tresult.p);
+        k_torque_vertices<<<div_up(s.ntvert, 128), 128, 0, s.stream>>>(s.ntvert, s.tverts.p, s.tresult.p, s.eval_x.p, s.fix_index.p, s.force.p, s.diag.p);
+        LAUNCH_COUNT(2);
+    }
 }
 
 void assemble_elastic(State &s, float dt, const PpfParamSet &prm) {

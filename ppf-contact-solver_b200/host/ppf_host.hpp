@@ -32,7 +32,11 @@ using Vec3f = std::array<float, 3>;
 
 // ---- scene description (what the frontend would write into a session dir) ----
 struct PinOp {
-    enum Kind { MoveBy, Spin, Scale } kind;
+    enum Kind { MoveBy, Spin, Scale, Torque } kind;
+    // Torque (pin.rs:131-140): a force, not a motion -- the pinned vertices stay free and are driven about a principal axis
+    // of the group (0 = largest spread), oriented toward the hint vertex (local index), at full power inside [t_start, t_end]
+    unsigned axis_component = 0, hint_vertex = 0;
+    double magnitude = 0.0;
     Vec3d delta{0, 0, 0};      // MoveBy
     Vec3d center{0, 0, 0};     // Spin / Scale
     Vec3d axis{0, 1, 0};       // Spin
@@ -175,6 +179,7 @@ struct Built {
     // constraint storage (rebuilt every step)
     std::vector<PpfFixPair> fix; std::vector<PpfPullPair> pull;
     std::vector<PpfSphere> sphere; std::vector<PpfFloor> floor;
+    std::vector<PpfTorqueGroup> torque_groups; std::vector<PpfTorqueVertex> torque_vertices;
     // static collision mesh (builder.rs:1823-1935 make_collision_mesh): all static objects merged
     std::vector<PpfVec3f> cm_vert; std::vector<PpfVec3u> cm_face; std::vector<PpfVec2u> cm_edge;
     std::vector<PpfVertexProp> cm_vprop; std::vector<PpfEdgeProp> cm_eprop; std::vector<PpfFaceProp> cm_fprop;

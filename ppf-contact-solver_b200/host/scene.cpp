@@ -607,6 +607,24 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.friction_mode = "min";
         return s;
     }
+    if (name == "sheet-torque") { // test scene: a free sheet in zero gravity spun up by a torque pin on its middle strip
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_square(n ? n : 24, 1.0, Vec3d{1, 0, 0}, Vec3d{0, 0, 1}, o.vert, o.tri);
+        o.param = tri_defaults();
+        Pin p;
+        for (unsigned k = 0; k < o.vert.size(); ++k)
+            if (std::fabs(o.vert[k][0]) < 0.3) p.index.push_back(k); // the strip |x| < 0.3: its longest spread is along z
+        PinOp t; t.kind = PinOp::Torque; t.axis_component = 0; t.magnitude = 0.05; t.hint_vertex = 0; t.t_start = 0.0; t.t_end = 0.2;
+        p.ops = {t};
+        o.pins.push_back(p);
+        s.objects.push_back(o);
+        s.args.gravity = Vec3d{0, 0, 0};
+        s.args.frames = 60;
+        s.args.dt = 1e-2;
+        return s;
+    }
     if (name == "drape-mesh") { // test scene: `drape` with the colliders as STATIC TRIANGLE MESHES (Constraint.mesh): an icosphere
         // standing on a ground square, both with friction; the sheet is thrown onto them
         SceneSpec s;
@@ -748,6 +766,7 @@ static bool apply_pin_op(const PinOp &op, Vec3f &pos, double time) {
         r[2] = pz * ct + cz * st + ax[2] * dp * omc + c[2];
         break;
     }
+    case PinOp::Torque: return false; // a force, not a motion (pin.rs:131-134)
     case PinOp::Scale: {
         if (time < op.t_start) return false;
         double cur;
@@ -769,8 +788,27 @@ static bool apply_pin_op(const PinOp &op, Vec3f &pos, double time) {
 void make_constraint(Built &b, double time, double prev_time) {
     b.fix.clear();
     b.pull.clear();
+    b.torque_groups.clear();
+    b.torque_vertices.clear();
+    for (auto &pin : b.pins) { // torque operations: one group per pin (scene.rs:2132-2198), full power inside the window
+        if (pin.unpin_time >= 0.0 && time >= pin.unpin_time) continue;
+        for (auto &op : pin.ops) {
+            if (op.kind != PinOp::Torque || time < op.t_start || time > op.t_end) continue;
+            PpfTorqueGroup g{};
+            g.axis_component = op.axis_component;
+            g.vertex_start = (unsigned)b.torque_vertices.size();
+            g.vertex_count = (unsigned)pin.index.size();
+            g.hint_vertex = pin.index.at(op.hint_vertex);
+            for (unsigned ind : pin.index) b.torque_vertices.push_back(PpfTorqueVertex{float(op.magnitude), ind, (unsigned)b.torque_groups.size()});
+            b.torque_groups.push_back(g);
+            break; // one torque per pin group
+        }
+    }
     for (auto &pin : b.pins) {
         if (pin.unpin_time >= 0.0 && time >= pin.unpin_time) continue;
+        bool torque_only = !pin.ops.empty(); // scene.rs:2061-2070: such vertices stay free
+        for (auto &op : pin.ops) torque_only = torque_only && op.kind == PinOp::Torque;
+        if (torque_only) continue;
         const Vec3d &d = b.spec.objects[pin.object].displacement;
         const Vec3f dx{float(d[0]), float(d[1]), float(d[2])};
         for (size_t i = 0; i < pin.index.size(); ++i) {
@@ -865,6 +903,10 @@ void make_constraint(Built &b, double time, double prev_time) {
     c.fix.size = c.fix.allocated = (unsigned)b.fix.size();
     c.pull.data = b.pull.data();
     c.pull.size = c.pull.allocated = (unsigned)b.pull.size();
+    c.torque_groups.data = b.torque_groups.data();
+    c.torque_groups.size = c.torque_groups.allocated = (unsigned)b.torque_groups.size();
+    c.torque_vertices.data = b.torque_vertices.data();
+    c.torque_vertices.size = c.torque_vertices.allocated = (unsigned)b.torque_vertices.size();
 }
 
 // scene.rs update_param: time-varying session params (only gravity keyframes are needed here)

@@ -13,6 +13,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_rod.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_stitch.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_strain.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_torque.cuh"
 using namespace ppf;
 #define SHIM extern "C" __attribute__((visibility("default")))
 static V3 v(const float *p) { return mk(p[0], p[1], p[2]); }
@@ -218,4 +219,20 @@ SHIM void orc_cmesh(int kind, const float *dyn, const float *sta, const float *p
     out16[1] = o.f.x; out16[2] = o.f.y; out16[3] = o.f.z;
     for (int k = 0; k < 9; ++k) out16[4 + k] = o.H.m[k];
     for (int k = 0; k < 3; ++k) out16[13 + k] = o.c[k];
+}
+
+// torque pins (math_torque.cuh); same layout as the oracle's shim
+SHIM void orc_torque(const float *x, const float *mass, unsigned n, unsigned axis_component, unsigned hint, float magnitude, float *out) {
+    PpfTorqueVertex tv[256];
+    for (unsigned k = 0; k < n; ++k) { tv[k].index = k; tv[k].group_id = 0; tv[k].magnitude = magnitude; }
+    PpfTorqueGroup g{axis_component, 0u, n, hint};
+    const TorqueGroupResult r = torque_group(g, tv, [&](unsigned i) { return v(x + 3 * i); }, [&](unsigned i) { return mass[i]; });
+    out[0] = r.center.x; out[1] = r.center.y; out[2] = r.center.z; out[3] = r.axis.x; out[4] = r.axis.y; out[5] = r.axis.z; out[6] = r.inv_r_perp_sq_sum;
+    for (unsigned k = 0; k < n; ++k) {
+        V3 f; M3 H;
+        torque_vertex(v(x + 3 * k), magnitude, r, f, H);
+        float *o = out + 7 + 12 * k;
+        o[0] = f.x; o[1] = f.y; o[2] = f.z;
+        for (int e = 0; e < 9; ++e) o[3 + e] = H.m[e];
+    }
 }

@@ -434,3 +434,40 @@ def test_oracle_drapes_a_sheet_over_static_meshes(run_job):
     assert np.isfinite(x).all()
     assert np.linalg.norm(x, axis=1).min() > 0.37          # the icosphere's faces lie up to 4 % inside the radius 0.4
     assert x[:, 1].min() > -0.42
+
+
+def test_torque_pin_math_oracle_equals_backend_header_and_first_principles(libs):
+    """Torque pins (energy.cu:20-86 eigen_sym3x3, 643-701 group pre-pass, 221-246 per-vertex force): oracle's plain C and the
+    backend's math_torque.cuh bit for bit; the axis is the requested principal direction of the group oriented toward the hint
+    vertex; the forces carry no net force and exactly the requested torque about that axis."""
+    o, b = libs
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        n = int(rng.integers(6, 40))
+        scale = np.array([1.0, 0.35, 0.08]) * rng.uniform(0.05, 0.5)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        x = ((rng.normal(size=(n, 3)) * scale) @ q.T + rng.uniform(-1, 1, 3)).astype(np.float32)
+        uniform = trial % 2 == 0
+        mass = (np.full(n, 5e-4) if uniform else rng.uniform(1e-4, 1e-3, n)).astype(np.float32)
+        comp, hint, mag = trial % 3, int(rng.integers(0, n)), np.float32(rng.choice([-0.3, 0.7]))
+        outs = []
+        for l in (o, b):
+            out = np.zeros(7 + 12 * n, np.float32)
+            l.orc_torque(fp(np.ascontiguousarray(x.ravel())), fp(mass), C.c_uint(n), C.c_uint(comp), C.c_uint(hint), C.c_float(mag), fp(out))
+            outs.append(out)
+        assert same_bits(outs[0], outs[1]).all()
+        out = outs[0].astype(np.float64)
+        center, axis = out[0:3], out[3:6]
+        assert np.allclose(center, (x * mass[:, None]).sum(0) / mass.sum(), atol=1e-5)
+        cov = np.cov((x - center).T.astype(np.float64), bias=True)
+        w, V = np.linalg.eigh(cov)
+        want = V[:, ::-1][:, comp]
+        assert abs(abs(axis @ want) - 1.0) < 2e-3 and abs(np.linalg.norm(axis) - 1.0) < 1e-5
+        assert axis @ (x[hint] - center) >= -1e-6
+        f = -out[7:].reshape(n, 12)[:, :3]                          # the shim returns the gradient; the force is its negative
+        if uniform:                                                 # the centre is the MASS-weighted centroid: no net force for equal masses
+            assert np.abs(f.sum(0)).max() < 2e-3 * np.abs(f).max() * n
+        torque = np.cross(x - center, f).sum(0)
+        assert abs(torque @ axis - float(mag)) < 2e-3 * abs(float(mag))
+        H = out[7:].reshape(n, 12)[0, 3:].reshape(3, 3)
+        assert np.allclose(H, H.T) and np.linalg.eigvalsh(H).min() > -1e-6 * max(np.abs(H).max(), 1e-12)

@@ -422,3 +422,16 @@ def test_collision_windows_switch_an_object_out_of_contact(run_job):
     assert closed["log_num_contact"][0] < plain["log_num_contact"][0] - 20
     assert closed["log_num_contact"][-1] < 0.6 * plain["log_num_contact"][-1]
     assert float(np.abs(closed["curr"] - plain["curr"]).max()) > 1e-3
+
+
+def test_torque_pin_spins_a_free_sheet_without_moving_its_centre(run_job):
+    """PinOperation::Torque (scene.rs:2061-2198): the pinned strip stays free (no fix / pull pairs), the sheet gains angular
+    momentum about the strip's longest principal axis while the torque is on (t <= 0.2 s) and keeps it afterwards; no net force"""
+    r0 = run_job({"lib": "oracle", "scene": "sheet-torque", "n": 16, "state": None, "steps": 0}, force_subprocess=True)
+    r = run_job({"lib": "oracle", "scene": "sheet-torque", "n": 16, "state": None, "steps": 30}, force_subprocess=True)
+    assert bool(r["ok"].all()) and "fix_index" not in r or len(r.get("fix_index", [])) == 0
+    x0, x, v = r0["curr"].astype(np.float64), r["curr"].astype(np.float64), (r["curr"] - r["prev"]).astype(np.float64)
+    assert np.abs(x.mean(0) - x0.mean(0)).max() < 1e-5
+    L = np.cross(x - x.mean(0), v).sum(0)
+    assert abs(L[2]) > 0.99 * np.linalg.norm(L) and np.linalg.norm(L) > 1e-3
+    assert np.abs(x - x0).max() > 5e-3
