@@ -315,3 +315,14 @@ def test_emulated_steps_with_the_quadratic_and_logarithmic_barriers(emu, run_job
         assert abs(mine - theirs) <= 3 + 2e-3 * theirs
     d = np.abs(g["curr"] - o["curr"]).max(axis=1)
     assert float(np.median(d)) < 1e-4 and float(d.max()) < 3e-3, (float(np.median(d)), float(d.max()))
+
+
+def test_emulated_sheet_comes_to_rest_on_the_static_mesh(emu, run_job):
+    """`drape-mesh` for a whole simulated second through the backend's own kernels: every step passes (line search, intersection
+    check against the static faces), the sheet ends up draped over the icosphere without passing through it or the ground"""
+    g = run_job({"lib": "emu", "scene": "drape-mesh", "n": 16, "state": None, "steps": 150}, force_subprocess=True)
+    assert bool(g["ok"].all()) and float(g["time"][0]) > 0.9
+    x = g["curr"].astype(np.float64)
+    assert np.isfinite(x).all() and np.linalg.norm(x, axis=1).min() > 0.37 and x[:, 1].min() > -0.42
+    assert g["log_num_contact"].max() > 40
+    assert x[:, 1].max() > 0.35                      # the middle of the sheet lies on top of the ball
