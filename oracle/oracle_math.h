@@ -621,4 +621,106 @@ static inline void o_torque_vertex(const float *y, float magnitude, const float 
     for (int c = 0; c < 3; ++c) for (int rr = 0; rr < 3; ++rr) H[c * 3 + rr] = sp * ((rr == c ? 1.0f : 0.0f) - axis[rr] * axis[c]);
 }
 
+
+/* ---- inflation pressure (TEST INFRASTRUCTURE restatement of energy/model/inflate.hpp:16-150, utility/utility.cu:60-183) ---- */
+static inline void o_jacobi_svd3(const float *F /* column-major */, float *U, float *S, float *V) {
+    float A[3][3], Vv[3][3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { A[r][c] = F[c * 3 + r]; Vv[r][c] = r == c ? 1.0f : 0.0f; }
+    for (int sweep = 0; sweep < 5; ++sweep)
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                float a = 0.0f, b = 0.0f, g = 0.0f;
+                for (int r = 0; r < 3; ++r) { a += A[r][p] * A[r][p]; b += A[r][q] * A[r][q]; g += A[r][p] * A[r][q]; }
+                const float zeta = (b - a) / (2.0f * g);
+                const float t = (g == 0.0f) ? 0.0f : (zeta >= 0.0f ? 1.0f : -1.0f) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+                const float c = 1.0f / sqrtf(1.0f + t * t), s = c * t;
+                for (int r = 0; r < 3; ++r) {
+                    const float ap = A[r][p], aq = A[r][q];
+                    A[r][p] = c * ap - s * aq; A[r][q] = s * ap + c * aq;
+                    const float vp = Vv[r][p], vq = Vv[r][q];
+                    Vv[r][p] = c * vp - s * vq; Vv[r][q] = s * vp + c * vq;
+                }
+            }
+    float s_[3], u_[3][3];
+    for (int c = 0; c < 3; ++c) {
+        float n2 = 0.0f;
+        for (int r = 0; r < 3; ++r) n2 += A[r][c] * A[r][c];
+        const float n = sqrtf(n2);
+        s_[c] = n;
+        const float inv = n > 0.0f ? 1.0f / n : 0.0f;
+        for (int r = 0; r < 3; ++r) u_[r][c] = A[r][c] * inv;
+    }
+    int idx[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i) for (int j = i + 1; j < 3; ++j) if (s_[idx[j]] < s_[idx[i]]) { const int tmp = idx[i]; idx[i] = idx[j]; idx[j] = tmp; }
+    for (int c = 0; c < 3; ++c) { S[c] = s_[idx[c]]; for (int r = 0; r < 3; ++r) { U[c * 3 + r] = u_[r][idx[c]]; V[c * 3 + r] = Vv[r][idx[c]]; } }
+}
+static inline float o_det3(const float *m) { return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[3] * (m[1] * m[8] - m[7] * m[2]) + m[6] * (m[1] * m[5] - m[4] * m[2]); }
+static inline void o_svd3_rv(const float *F, float *U, float *S, float *V) {
+    o_jacobi_svd3(F, U, S, V);
+    const float du = o_det3(U), dv = o_det3(V);
+    int mi = 0;
+    for (int i = 1; i < 3; ++i) if (S[i] < S[mi]) mi = i;
+    if (du < 0.0f && dv > 0.0f) { for (int r = 0; r < 3; ++r) U[mi * 3 + r] = -U[mi * 3 + r]; S[mi] = -S[mi]; }
+    else if (du > 0.0f && dv < 0.0f) { for (int r = 0; r < 3; ++r) V[mi * 3 + r] = -V[mi * 3 + r]; S[mi] = -S[mi]; }
+}
+static inline void o_jacobi_eig3(float A[3][3], float *val, float vec[3][3]) {
+    float Q[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    for (int sweep = 0; sweep < 8; ++sweep)
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const float apq = A[p][q];
+                if (apq == 0.0f) continue;
+                const float theta = (A[q][q] - A[p][p]) / (2.0f * apq);
+                const float t = (theta >= 0.0f ? 1.0f : -1.0f) / (fabsf(theta) + sqrtf(1.0f + theta * theta));
+                const float c = 1.0f / sqrtf(1.0f + t * t), s = c * t;
+                for (int k = 0; k < 3; ++k) { const float akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { const float apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { const float qkp = Q[k][p], qkq = Q[k][q]; Q[k][p] = c * qkp - s * qkq; Q[k][q] = s * qkp + c * qkq; }
+            }
+    for (int k = 0; k < 3; ++k) { val[k] = A[k][k]; for (int r = 0; r < 3; ++r) vec[k][r] = Q[r][k]; }
+}
+static inline void o_inflate_gradient(float pressure, const float *x0, const float *x1, const float *x2, float g[3][3]) {
+    const float coeff = -pressure / 6.0f;
+    float e1[3], e2[3], d[3], a[3], b[3];
+    o_sub(x1, x0, e1); o_sub(x2, x0, e2); o_sub(e1, e2, d);
+    o_cross(e1, e2, a); o_cross(d, x0, b);
+    for (int k = 0; k < 3; ++k) g[0][k] = coeff * (a[k] + b[k]);
+    o_cross(e2, x0, a); for (int k = 0; k < 3; ++k) g[1][k] = coeff * a[k];
+    o_cross(x0, e1, a); for (int k = 0; k < 3; ++k) g[2][k] = coeff * a[k];
+}
+static inline void o_inflate_hessian(float pressure, const float *x0, const float *x1, const float *x2, float *H /* 9x9 column-major */) {
+    float X[9], U[9], V[9], s[3];
+    for (int k = 0; k < 3; ++k) { X[k] = x0[k]; X[3 + k] = x1[k]; X[6 + k] = x2[k]; }
+    o_svd3_rv(X, U, s, V);
+    float A[3][3] = {{0.f, s[2], s[1]}, {s[2], 0.f, s[0]}, {s[1], s[0], 0.f}};
+    float ev[3], evec[3][3];
+    o_jacobi_eig3(A, ev, evec);
+    const float c = pressure / 6.0f, inv_sqrt2 = 0.7071067811865475f;
+    float weights[5], Q[5][3][3];
+    int kept = 0;
+    const int swap_ij[3][2] = {{1, 0}, {2, 0}, {2, 1}};
+    const float swap_s[3] = {s[2], s[1], s[0]};
+    for (int p = 0; p < 3; ++p) {
+        const float w = c * swap_s[p];
+        if (!(w > 0.0f)) continue;
+        const int i = swap_ij[p][0], j = swap_ij[p][1];
+        weights[kept] = w;
+        for (int k = 0; k < 3; ++k) for (int r = 0; r < 3; ++r) Q[kept][k][r] = inv_sqrt2 * (V[j * 3 + k] * U[i * 3 + r] + V[i * 3 + k] * U[j * 3 + r]);
+        ++kept;
+    }
+    for (int d = 0; d < 3 && kept < 5; ++d) {
+        if (!(ev[d] < -1e-12f)) continue;
+        const float w = c * fabsf(ev[d]);
+        if (!(w > 0.0f)) continue;
+        weights[kept] = w;
+        for (int k = 0; k < 3; ++k) for (int r = 0; r < 3; ++r)
+            Q[kept][k][r] = ((evec[d][0] * V[0 * 3 + k]) * U[0 * 3 + r] + (evec[d][1] * V[1 * 3 + k]) * U[1 * 3 + r]) + (evec[d][2] * V[2 * 3 + k]) * U[2 * 3 + r];
+        ++kept;
+    }
+    for (int i = 0; i < 81; ++i) H[i] = 0.0f;
+    for (int m = 0; m < kept; ++m)
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int cc = 0; cc < 3; ++cc) for (int r = 0; r < 3; ++r)
+            H[(3 * b + cc) * 9 + 3 * a + r] += weights[m] * Q[m][a][r] * Q[m][b][cc];
+}
+
 #endif

@@ -170,3 +170,11 @@ SHIM void orc_torque(const float *x, const float *mass, unsigned n, unsigned axi
     o_torque_group(axis_component, 0, n, hint, idx, x, mass, out);
     for (unsigned k = 0; k < n; ++k) o_torque_vertex(x + 3 * k, magnitude, out, out + 7 + 12 * k, out + 7 + 12 * k + 3);
 }
+
+/* inflation pressure of one face: gradient (9) and PSD-projected Hessian (81, column-major) */
+SHIM void orc_inflate(float pressure, const float *x9, float *g9, float *H81) {
+    float g[3][3];
+    o_inflate_gradient(pressure, x9, x9 + 3, x9 + 6, g);
+    for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) g9[3 * a + k] = g[a][k];
+    o_inflate_hessian(pressure, x9, x9 + 3, x9 + 6, H81);
+}

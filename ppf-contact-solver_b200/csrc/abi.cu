@@ -153,7 +153,6 @@ void upload_dataset(State &s) {
         const PpfFaceParam &fp = d.param_arrays.face.data[i];
         if (fp.model != PPF_MODEL_BARAFFWITKIN && fp.model != PPF_MODEL_ARAP && fp.model != PPF_MODEL_STVK && fp.model != PPF_MODEL_SNHK)
             fatal(4, "B200 backend: shell model %d is not implemented (Baraff-Witkin, ARAP, StVK and SNHk are)", (int)fp.model);
-        if (fp.pressure > 0.0f) fatal(4, "B200 backend: inflation pressure is not implemented");
     }
     if (d.face_hess_slots.size != 9u * nf || d.hinge_hess_slots.size != 16u * nh)
         fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
@@ -291,6 +290,16 @@ void upload_dataset(State &s) {
             s.cm_x.upload(cx.data(), s.cm_nv, q); s.cm_vcp.upload(cv.data(), s.cm_nv, q);
             s.cm_ecp.upload(ce.data(), ce.size(), q); s.cm_fcp.upload(cf.data(), cf.size(), q);
             s.cm_face.upload(f4.data(), f4.size(), q); s.cm_edge.upload(e2.data(), e2.size(), q);
+            CUDA_OK(cudaStreamSynchronize(q));
+        }
+        {
+            std::vector<float> pr(std::max(nf, 1u), 0.0f);
+            s.has_pressure = false;
+            for (unsigned i = 0; i < nf; ++i) {
+                pr[i] = d.param_arrays.face.data[d.prop.face.data[i].param_index].pressure;
+                s.has_pressure = s.has_pressure || pr[i] > 0.0f;
+            }
+            s.fpressure.upload(pr.data(), pr.size(), q);
             CUDA_OK(cudaStreamSynchronize(q));
         }
         s.fmat.upload(fm.data(), nf, q); s.inv_rest.upload(ir.data(), nf, q); s.hmat.upload(hm.data(), nh, q);

@@ -118,6 +118,8 @@ struct State {
     DBuf<float> varea;                            // vertex area
     DBuf<unsigned> fix_index, pull_index;         // per vertex (1-based, 0 = none)
     DBuf<unsigned char> vfixed, efixed, ffixed, hfixed, vcollider, fskip;
+    DBuf<float> fpressure;                        // per face inflation pressure (FaceParam.pressure); has_pressure when any is set
+    bool has_pressure = false;
     DBuf<float4> fmat;                            // per face (mu, lambda, mass, model as a float: the ABI's Model enum)
     bool has_iso_faces = false;                   // some face uses an SVD-based model (ARAP / StVK / SNHk)
     // Rayleigh damping coefficients (seconds), 0 = none: faces / rods use deform_damping, hinges / rod bending bend_damping

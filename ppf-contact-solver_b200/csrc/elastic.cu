@@ -11,6 +11,7 @@
 #include "math_elastic.cuh"
 #include "math_damping.cuh"
 #include "math_hinge.cuh"
+#include "math_inflate.cuh"
 #include "math_plasticity.cuh"
 #include "math_rod.cuh"
 #include "math_stitch.cuh"
@@ -118,6 +119,33 @@ __global__ void __launch_bounds__(128) k_face(unsigned nf, const uint4 *__restri
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) atomic_add_block(val, sl[a * 3 + b], fe.H[a][b].m);
+}
+
+// inflation pressure on shell faces (energy.cu:366-392; math_inflate.cuh), same face gate as the membrane term
+__global__ void __launch_bounds__(128) k_face_pressure(unsigned nf, const uint4 *__restrict__ face, const float4 *__restrict__ eval_x,
+                                                       const float *__restrict__ pressure, const unsigned char *__restrict__ ffixed,
+                                                       const unsigned char *__restrict__ fskip, const unsigned *__restrict__ slots,
+                                                       float *__restrict__ force, float *__restrict__ val) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf || ffixed[i] || fskip[i]) return;
+    const float P = pressure[i];
+    if (!(P > 0.0f)) return;
+    const uint4 f = face[i];
+    const V3 x0 = ld3(eval_x, f.x), x1 = ld3(eval_x, f.y), x2 = ld3(eval_x, f.z);
+    V3 g[3];
+    inflate_gradient(P, x0, x1 - x0, x2 - x0, g);
+    float H[81];
+    inflate_hessian(P, x0, x1, x2, H);
+    const unsigned vi[3] = {f.x, f.y, f.z};
+    for (int a = 0; a < 3; ++a) atomic_add3(force + size_t(3) * vi[a], g[a]);
+    const unsigned *sl = slots + size_t(9) * i;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            float B[9];
+            for (int cc = 0; cc < 3; ++cc)
+                for (int r = 0; r < 3; ++r) B[cc * 3 + r] = H[(3 * b + cc) * 9 + 3 * a + r];
+            atomic_add_block(val, sl[a * 3 + b], B);
+        }
 }
 
 // shell faces with an SVD-based model: ARAP / StVK / SNHk (energy.cu:337-352; math_strain.cuh iso_face)
@@ -739,6 +767,11 @@ void assemble_elastic(State &s, float dt, const PpfParamSet &prm) {
     if (s.nf && s.has_iso_faces) {
         k_face_iso<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.fmat.p, s.inv_rest.p, s.ffixed.p, s.fskip.p, s.face_slots.p,
                                                             prm.eiganalysis_eps, s.force.p, s.fx_val.p);
+        LAUNCH_COUNT(1);
+    }
+    if (s.nf && s.has_pressure) {
+        k_face_pressure<<<div_up(s.nf, 128), 128, 0, s.stream>>>(s.nf, s.face.p, s.eval_x.p, s.fpressure.p, s.ffixed.p, s.fskip.p, s.face_slots.p, s.force.p,
+                                                                 s.fx_val.p);
         LAUNCH_COUNT(1);
     }
     if (s.nh) k_hinge<<<div_up(s.nh, 128), 128, 0, s.stream>>>(s.nh, s.hinge.p, s.eval_x.p, s.hmat.p, s.hinge_stiff.p, s.hfixed.p,

@@ -607,6 +607,20 @@ SceneSpec make_scene(const std::string &name, unsigned n) {
         s.args.friction_mode = "min";
         return s;
     }
+    if (name == "balloon") { // test scene: a closed icosphere shell in zero gravity inflated by FaceParam.pressure
+        SceneSpec s;
+        s.name = name;
+        ShellObject o;
+        gen_icosphere(0.3, (n == 0 || n >= 24) ? 3u : 2u, o.vert, o.tri);
+        o.param = tri_defaults();
+        o.param["pressure"] = 100.0;
+        o.displacement = Vec3d{0.4, 0.5, 0.3}; // away from the origin: the per-face terms are translation-variant, their sum is not
+        s.objects.push_back(o);
+        s.args.gravity = Vec3d{0, 0, 0};
+        s.args.frames = 60;
+        s.args.dt = 1e-2;
+        return s;
+    }
     if (name == "sheet-torque") { // test scene: a free sheet in zero gravity spun up by a torque pin on its middle strip
         SceneSpec s;
         s.name = name;

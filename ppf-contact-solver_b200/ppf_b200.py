@@ -22,7 +22,7 @@ LIB_REF = os.path.join(REPO, "oracle", "_ref", "libsimbackend_cuda.so")
 LIB_HOST = os.path.join(ROOT, "lib", "libppf_host.so")
 # the CPU oracle (TEST INFRASTRUCTURE): tests, smoke() and bench.py's cpu_baseline leg only
 LIB_ORACLE = os.path.join(REPO, "oracle", "build", "libppf_oracle.so")
-DEFAULT_RESOLUTION = {"five-twist": 180, "twist": 360, "large-twist": 1410, "fast-twist": 48, "hang": 128, "sheet": 32, "woven": 256, "large-woven": 1024, "woven-sl": 32, "drape": 32, "headless": 64, "lift": 32, "curtain": 64, "drape-sheets": 128, "large-five-twist": 1181, "sheet-arap": 32, "sheet-stvk": 32, "sheet-snhk": 32, "sheet-damped": 32, "sheet-arap-damped": 32, "woven-damped": 32, "seam": 16, "sheet-plastic": 32, "sheet-fixxz": 32, "drape-mesh": 32, "sheet-torque": 24, "woven-plastic": 32}  # host/scene.cpp
+DEFAULT_RESOLUTION = {"five-twist": 180, "twist": 360, "large-twist": 1410, "fast-twist": 48, "hang": 128, "sheet": 32, "woven": 256, "large-woven": 1024, "woven-sl": 32, "drape": 32, "headless": 64, "lift": 32, "curtain": 64, "drape-sheets": 128, "large-five-twist": 1181, "sheet-arap": 32, "sheet-stvk": 32, "sheet-snhk": 32, "sheet-damped": 32, "sheet-arap-damped": 32, "woven-damped": 32, "seam": 16, "sheet-plastic": 32, "sheet-fixxz": 32, "drape-mesh": 32, "sheet-torque": 24, "balloon": 24, "woven-plastic": 32}  # host/scene.cpp
 HOST_BIN = os.path.join(ROOT, "bin", "ppf_host")
 
 ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"

@@ -54,6 +54,7 @@ case "$1" in
      gen sheet_fixxz_n24 sheet-fixxz 24 20 20 00020
      gen drape_mesh_n24 drape-mesh 24 40 20 00020 00040
      gen sheet_torque_n24 sheet-torque 24 30 15 00015 00030
+     gen balloon_n24 balloon 24 20 10 00010 00020
      gen headless_cw_closed_n24 headless-cw-closed 24 68 68 00068
      gen fast_twist_quad_n16 fast-twist@quad 16 60 30 00030 00060
      gen fast_twist_log_n16 fast-twist@log 16 60 30 00030 00060 ;;

@@ -9,6 +9,7 @@
 #include "../../ppf-contact-solver_b200/csrc/math_distance.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_elastic.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_hinge.cuh"
+#include "../../ppf-contact-solver_b200/csrc/math_inflate.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_plasticity.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_rod.cuh"
 #include "../../ppf-contact-solver_b200/csrc/math_stitch.cuh"
@@ -235,4 +236,13 @@ SHIM void orc_torque(const float *x, const float *mass, unsigned n, unsigned axi
         o[0] = f.x; o[1] = f.y; o[2] = f.z;
         for (int e = 0; e < 9; ++e) o[3 + e] = H.m[e];
     }
+}
+
+// inflation pressure (math_inflate.cuh)
+SHIM void orc_inflate(float pressure, const float *x9, float *g9, float *H81) {
+    const V3 v0 = v(x9), v1 = v(x9 + 3), v2 = v(x9 + 6);
+    V3 g[3];
+    inflate_gradient(pressure, v0, v1 - v0, v2 - v0, g);
+    for (int a = 0; a < 3; ++a) { g9[3 * a] = g[a].x; g9[3 * a + 1] = g[a].y; g9[3 * a + 2] = g[a].z; }
+    inflate_hessian(pressure, v0, v1, v2, H81);
 }

@@ -471,3 +471,40 @@ def test_torque_pin_math_oracle_equals_backend_header_and_first_principles(libs)
         assert abs(torque @ axis - float(mag)) < 2e-3 * abs(float(mag))
         H = out[7:].reshape(n, 12)[0, 3:].reshape(3, 3)
         assert np.allclose(H, H.T) and np.linalg.eigvalsh(H).min() > -1e-6 * max(np.abs(H).max(), 1e-12)
+
+
+def test_inflation_pressure_oracle_equals_backend_header_and_the_volume_energy(libs):
+    """FaceParam.pressure (inflate.hpp:16-150): E = -(P/6) x0 . (x1 x x2) per face.  Oracle and backend header bit for bit; the
+    gradient is the derivative of E; the Hessian is positive semi-definite, never exceeds the positive part of the exact
+    Hessian and equals its exact PSD projection when the face's tetrahedron with the origin is positively oriented."""
+    o, b = libs
+    rng = np.random.default_rng(31)
+    exact = 0
+    for trial in range(80):
+        x = rng.uniform(-1, 1, 9).astype(np.float32)
+        P = np.float32(rng.uniform(0.5, 4.0))
+        res = []
+        for l in (o, b):
+            g = np.zeros(9, np.float32); H = np.zeros(81, np.float32)
+            l.orc_inflate(C.c_float(P), fp(x), fp(g), fp(H))
+            res.append((g, H))
+        assert same_bits(res[0][0], res[1][0]).all() and same_bits(res[0][1], res[1][1]).all()
+        g, H = res[0][0].astype(np.float64), res[0][1].reshape(9, 9).T.astype(np.float64)
+        xd = x.astype(np.float64)
+        E = lambda y: -(float(P) / 6.0) * np.linalg.det(y.reshape(3, 3).T)
+        h = 1e-4
+        gfd = np.array([(E(xd + h * np.eye(9)[i]) - E(xd - h * np.eye(9)[i])) / (2 * h) for i in range(9)])
+        assert np.abs(g - gfd).max() < 1e-5
+        He = np.zeros((9, 9))
+        I = np.eye(9) * h
+        for i in range(9):
+            for j in range(9):
+                He[i, j] = (E(xd + I[i] + I[j]) - E(xd + I[i] - I[j]) - E(xd - I[i] + I[j]) + E(xd - I[i] - I[j])) / (4 * h * h)
+        w, V = np.linalg.eigh(He)
+        Hp = (V * np.maximum(w, 0)) @ V.T
+        assert np.allclose(H, H.T, atol=1e-6) and np.linalg.eigvalsh(H).min() > -1e-5
+        assert np.linalg.eigvalsh(Hp - H).min() > -2e-4 * np.abs(Hp).max()          # a sub-sum of the positive modes
+        if np.linalg.det(xd.reshape(3, 3).T) > 0.05:
+            assert np.abs(H - Hp).max() < 2e-4 * np.abs(Hp).max()
+            exact += 1
+    assert exact > 15

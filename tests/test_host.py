@@ -435,3 +435,17 @@ def test_torque_pin_spins_a_free_sheet_without_moving_its_centre(run_job):
     L = np.cross(x - x.mean(0), v).sum(0)
     assert abs(L[2]) > 0.99 * np.linalg.norm(L) and np.linalg.norm(L) > 1e-3
     assert np.abs(x - x0).max() > 5e-3
+
+
+def test_inflation_pressure_blows_up_a_closed_shell_without_moving_it(run_job):
+    """FaceParam.pressure on the `balloon` scene (a closed icosphere away from the origin, no gravity): the shell grows
+    (mean radius +2..8 % after 0.2 s), stays round and its centre stays where it was -- the per-face pressure terms depend
+    on the distance from the origin, their sum over the closed surface does not."""
+    r0 = run_job({"lib": "oracle", "scene": "balloon", "n": 16, "state": None, "steps": 0}, force_subprocess=True)
+    r = run_job({"lib": "oracle", "scene": "balloon", "n": 16, "state": None, "steps": 20}, force_subprocess=True)
+    assert bool(r["ok"].all())
+    x0, x = r0["curr"].astype(np.float64), r["curr"].astype(np.float64)
+    rad0, rad = np.linalg.norm(x0 - x0.mean(0), axis=1), np.linalg.norm(x - x.mean(0), axis=1)
+    assert 1.02 < rad.mean() / rad0.mean() < 1.08
+    assert rad.std() < 0.01 * rad.mean()
+    assert np.abs(x.mean(0) - x0.mean(0)).max() < 5e-4

@@ -103,7 +103,7 @@ def _assemble_both(emu, ppf, scene, n, seed, amplitude, dt):
 
 CASES = [("fast-twist", 12, 2e-3), ("hang", 12, 2e-3), ("sheet-arap", 10, 2e-3), ("sheet-stvk", 10, 2e-3), ("sheet-snhk", 10, 2e-3),
          ("sheet-damped", 10, 2e-3), ("sheet-arap-damped", 10, 2e-3), ("sheet-fixxz", 10, 2e-3), ("woven", 32, 2e-4), ("woven-sl", 32, 3e-4), ("woven-damped", 32, 2e-4),
-         ("seam", 10, 2e-3), ("headless", 10, 2e-3), ("drape-mesh", 10, 2e-3), ("sheet-torque", 10, 2e-3)]
+         ("seam", 10, 2e-3), ("headless", 10, 2e-3), ("drape-mesh", 10, 2e-3), ("sheet-torque", 10, 2e-3), ("balloon", 10, 1e-3)]
 
 
 @pytest.mark.parametrize("scene,n,amp", CASES, ids=[c[0] for c in CASES])
@@ -257,6 +257,7 @@ _LATE = [("headless", 24, os.path.join(REPO, "tests", "golden", "headless_n24", 
          ("lift", 24, None, 30), ("sheet-arap", 24, None, 5), ("sheet-stvk", 24, None, 5), ("sheet-snhk", 24, None, 5),
          ("sheet-damped", 24, None, 3), ("woven-damped", 32, None, 3), ("seam", 16, None, 4), ("sheet-plastic", 24, None, 6), ("sheet-fixxz", 24, None, 8),
          ("headless-cw-closed", 24, os.path.join(REPO, "tests", "golden", "headless_n24", "state_00068.bin"), 2),   # collision windows
+         ("balloon", 24, None, 6),            # inflation pressure on a closed shell
          ("sheet-torque", 24, None, 5),       # torque pin on a strip of a free sheet
          ("drape-mesh", 24, None, 7),         # static collision mesh (Constraint.mesh): icosphere + ground square
          ("woven-plastic", 32, None, 2)]      # chained woven steps separate by their line-search cuts after ~3 steps, plastic or not

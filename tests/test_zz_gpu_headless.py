@@ -258,3 +258,17 @@ def test_torque_pins_match_the_oracle(run_job):
     x, v = g["curr"].astype(np.float64), (g["curr"] - g["prev"]).astype(np.float64)
     L = np.cross(x - x.mean(0), v).sum(0)
     assert abs(L[2]) > 0.9 * np.linalg.norm(L) > 0                 # spun about the strip's long axis (z)
+
+
+def test_inflation_pressure_matches_the_oracle(run_job):
+    """`balloon`: FaceParam.pressure (k_face_pressure: conditioned gradient + SVD-projected Hessian) against the CPU oracle"""
+    job = {"scene": "balloon", "n": 24, "state": None, "steps": 6, "dump_linsys": True}
+    g = run_job(dict(job, lib="ours"), force_subprocess=True)
+    o = run_job(dict(job, lib="oracle"), force_subprocess=True)
+    assert bool(g["ok"].all()) and bool(o["ok"].all())
+    c = compare(os.path.join(o["out_dir"], "linsys_0.bin"), os.path.join(g["out_dir"], "linsys_0.bin"), verbose=False)
+    assert c["only_ref"] == 0 and c["only_ours"] == 0, c
+    assert c["offdiag_max_rel_block_diff"] < 1e-3 and c["diag_max_rel_diff"] < 1e-3 and c["rhs_max_abs_diff_over_scale"] < 1e-3, c
+    assert len(g["log_iter"]) == len(o["log_iter"])
+    d = np.abs(g["curr"] - o["curr"]).max(axis=1)
+    assert float(np.median(d)) < 2e-5 and float(d.max()) < 2e-3, (float(np.median(d)), float(d.max()))
