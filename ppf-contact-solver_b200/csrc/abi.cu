@@ -146,6 +146,7 @@ void upload_dataset(State &s) {
         fatal(4, "B200 backend: slot-replay tables are required (stitch_hess_slots)");
     if (prm.disable_pin_dof_removal) fatal(4, "B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
     if (d.translation_lock.size) fatal(4, "B200 backend: translation/rotation locks are not implemented");
+    if (d.statistics_contact_count.size) fatal(4, "B200 backend: per-object contact statistics (statistics_contact_count) are not implemented");
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
         if (d.grain_inv_inertia.data[i] > 0.0f) fatal(4, "B200 backend: SAND grains are not implemented");
     if (nf != d.shell_face_count || s.nsv != nv) fatal(4, "B200 backend: solid (tet) surfaces and interior vertices are not implemented (shell faces and rods only)");
