@@ -159,6 +159,18 @@ void ppfh_slot_tables(Session *s, unsigned *face_slots, unsigned *hinge_slots, u
     if (transpose_offset) memcpy(transpose_offset, b.f_transpose.offset.data(), b.f_transpose.offset.size() * sizeof(unsigned));
     if (transpose_rowslot) memcpy(transpose_rowslot, b.f_transpose.data.data(), b.f_transpose.data.size() * sizeof(PpfVec2u));
 }
+// the static collision mesh of the built scene (Constraint.mesh): counts[3] = vertices, faces, edges; optional copies of the
+// positions (3 per vertex), faces (3), edges (2) and per-vertex / per-edge / per-face (ghat, offset, friction)
+void ppfh_static_mesh(Session *s, unsigned *counts, float *vert, unsigned *face, unsigned *edge, float *vpar, float *epar, float *fpar) {
+    const Built &b = s->b;
+    counts[0] = (unsigned)b.cm_vert.size(); counts[1] = (unsigned)b.cm_face.size(); counts[2] = (unsigned)b.cm_edge.size();
+    if (vert) memcpy(vert, b.cm_vert.data(), b.cm_vert.size() * sizeof(PpfVec3f));
+    if (face) memcpy(face, b.cm_face.data(), b.cm_face.size() * sizeof(PpfVec3u));
+    if (edge) memcpy(edge, b.cm_edge.data(), b.cm_edge.size() * sizeof(PpfVec2u));
+    if (vpar) for (size_t i = 0; i < b.cm_vert.size(); ++i) { const PpfVertexParam &q = b.cm_vparam[b.cm_vprop[i].param_index]; vpar[3 * i] = q.ghat; vpar[3 * i + 1] = q.offset; vpar[3 * i + 2] = q.friction; }
+    if (epar) for (size_t i = 0; i < b.cm_edge.size(); ++i) { const PpfEdgeParam &q = b.cm_eparam[b.cm_eprop[i].param_index]; epar[3 * i] = q.ghat; epar[3 * i + 1] = q.offset; epar[3 * i + 2] = q.friction; }
+    if (fpar) for (size_t i = 0; i < b.cm_face.size(); ++i) { const PpfFaceParam &q = b.cm_fparam[b.cm_fprop[i].param_index]; fpar[3 * i] = q.ghat; fpar[3 * i + 1] = q.offset; fpar[3 * i + 2] = q.friction; }
+}
 // rod data of the built scene: returns rod_count; per rod edge (rest length, initial length, mass, stiffness, bend),
 // per vertex (mass, rest bend angle), the 9 rod-bend slots per vertex and the fixed index table (offset[n_vert+1], columns)
 unsigned ppfh_rods(Session *s, float *rod5, float *vert2, unsigned *bend_slots9, unsigned *fixed_offset, unsigned *fixed_col) {

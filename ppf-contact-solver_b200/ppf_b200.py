@@ -249,6 +249,18 @@ class Session:
         self.h.ppfh_rods(self.p, rod.ctypes.data_as(vp), vert.ctypes.data_as(vp), slots.ctypes.data_as(vp), off.ctypes.data_as(vp), col.ctypes.data_as(vp))
         return n_rod, rod, vert, slots, off, col
 
+    def static_mesh(self):
+        """the static collision mesh (Constraint.mesh): positions, faces, edges and per-vertex / edge / face (ghat, offset, friction)"""
+        cnt = (ctypes.c_uint * 3)()
+        self.h.ppfh_static_mesh(self.p, cnt, None, None, None, None, None, None)
+        nv, nf, ne = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        vert = np.empty((nv, 3), np.float32); face = np.empty((nf, 3), np.uint32); edge = np.empty((ne, 2), np.uint32)
+        vpar = np.empty((nv, 3), np.float32); epar = np.empty((ne, 3), np.float32); fpar = np.empty((nf, 3), np.float32)
+        vp = ctypes.c_void_p
+        self.h.ppfh_static_mesh(self.p, cnt, vert.ctypes.data_as(vp), face.ctypes.data_as(vp), edge.ctypes.data_as(vp), vpar.ctypes.data_as(vp),
+                                epar.ctypes.data_as(vp), fpar.ctypes.data_as(vp))
+        return vert, face, edge, vpar, epar, fpar
+
     def read_log(self, channel):
         p = os.path.join(self.log_dir, "advance.%s.out" % channel)
         if not os.path.exists(p):

@@ -449,3 +449,22 @@ def test_inflation_pressure_blows_up_a_closed_shell_without_moving_it(run_job):
     assert 1.02 < rad.mean() / rad0.mean() < 1.08
     assert rad.std() < 0.01 * rad.mean()
     assert np.abs(x.mean(0) - x0.mean(0)).max() < 5e-4
+
+
+def test_static_mesh_tables_of_the_drape_mesh_scene(ppf):
+    """builder.rs:1823-1935 make_collision_mesh restated in host/builder.cpp: the two static objects merged, every undirected edge
+    once (closed icosphere: E = 3F/2; open ground square: more), the scene's contact parameters on every element"""
+    s = ppf.Session("drape-mesh", n=16, lib=ppf.LIB_ORACLE)
+    vert, face, edge, vpar, epar, fpar = s.static_mesh()
+    n_ball_f = 20 * 4 ** 2                                         # icosphere, two subdivisions at n = 16
+    n_ground_f = 2 * 7 * 7                                        # gen_square(8, ...): 8 vertices per side
+    assert len(face) == n_ball_f + n_ground_f and face.max() == len(vert) - 1
+    assert len(vert) == (10 * 4 ** 2 + 2) + 8 * 8
+    und = {tuple(sorted(e)) for e in edge.tolist()}
+    assert len(und) == len(edge)                                   # unique
+    want = {tuple(sorted((int(f[k]), int(f[(k + 1) % 3])))) for f in face for k in range(3)}
+    assert und == want and len(edge) == 3 * n_ball_f // 2 + (3 * n_ground_f + 4 * 7) // 2
+    for par in (vpar, epar, fpar):
+        assert np.allclose(par[:, 0], 1e-3, rtol=1e-6) and np.allclose(par[:, 1], 0.0) and np.allclose(par[:, 2], 0.3, rtol=1e-6)
+    ball = vert[:10 * 4 ** 2 + 2]
+    assert np.allclose(np.linalg.norm(ball, axis=1), 0.4, atol=1e-5) and np.allclose(vert[len(ball):, 1], -0.42, atol=1e-6)
