@@ -452,6 +452,15 @@ PPF_EXPORT bool initialize(PpfDataSet *dataset, PpfParamSet *param) {
     if (!s.stream) CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     s.host = *dataset;
     s.param = param;
+    // a second initialize() in the same process starts a new session: nothing of the previous scene may leak into its first step
+    s.cand_cover_eval = s.bvh_cover_eval = s.bvh_relative = false;
+    for (int k = 0; k < 4; ++k) { s.cand[k].count = 0; s.pairs[k].count = 0; s.last_num_contact[k] = 0; }
+    s.dyn_valid = false;
+    s.dyn_nnz = 0;
+    s.carried_index.clear();
+    s.carried_offset.clear();
+    s.has_cw = s.cw_uploaded = false;
+    s.h_isect_count = 0;
     ScopeLog logging("initialize");
     upload_dataset(s);
     s.initialized = true;
@@ -650,6 +659,12 @@ PPF_EXPORT void init_collision_windows(const unsigned *vert_dmap, unsigned vert_
     s.has_cw = false;
     for (unsigned i = 0; i < n_groups; ++i) s.has_cw |= window_counts[i] != 0;
     s.cw_uploaded = false;
+    // until the next refresh_collision_active every vertex takes part in contact (main.cu:2230-2264 memsets the flags to active)
+    if (s.has_cw && vert_count) {
+        s.cw_active.reserve(vert_count);
+        CUDA_OK(cudaMemsetAsync(s.cw_active.p, 1, vert_count, s.stream));
+    }
+    s.cand_cover_eval = false;
 }
 PPF_EXPORT void refresh_collision_active(float time) {
     State &s = g;

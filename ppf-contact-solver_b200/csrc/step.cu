@@ -74,15 +74,15 @@ __global__ void k_apply_dx(unsigned n, float4 *eval_x, float4 *x_old, const floa
     eval_x[i] = make_float4(e.x - (toi_recale * dx[3 * size_t(i)]), e.y - (toi_recale * dx[3 * size_t(i) + 1]), e.z - (toi_recale * dx[3 * size_t(i) + 2]), 0.f);
 }
 
-// ParamSet.fix_xz: above the height fix_xz the horizontal part of the Newton update is pulled back toward the start-of-step
-// position, fully from one unit above (main.cu:1190-1208); prescribed (DOF-removed) vertices keep their keyframe
-__global__ void k_fix_xz(unsigned n, float4 *eval_x, const float4 *curr, const unsigned *fix_index, float fix_xz) {
+// ParamSet.fix_xz: above the height fix_xz the horizontal part of the Newton update is pulled back toward the PREVIOUS step's
+// position (data.vertex.prev, main.cu:361,1190-1208), fully from one unit above; prescribed (DOF-removed) vertices keep their keyframe
+__global__ void k_fix_xz(unsigned n, float4 *eval_x, const float4 *prev, const unsigned *fix_index, float fix_xz) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || fix_index[i] != 0) return;
     float4 e = eval_x[i];
     if (e.y > fix_xz) {
         const float y = fminf(1.0f, e.y - fix_xz);
-        const float4 z = curr[i];
+        const float4 z = prev[i];
         e.x -= y * (e.x - z.x);
         e.z -= y * (e.z - z.z);
         eval_x[i] = e;
@@ -167,7 +167,11 @@ void step_advance(State &s, PpfStepResult *out) {
     simplelog_set_time(prm.time);
     EvTimer t_all(q), t_ph(q);
     t_all.start();
-    auto finish = [&](bool) {
+    // The sweep's candidate lists were filtered with the collision-window flags of the step that produced them: when windows
+    // exist (refresh_collision_active runs before every advance) the first assembly of a step traverses afresh.
+    if (s.has_cw) s.cand_cover_eval = false;
+    auto finish = [&](bool ok) {
+        if (!ok) s.cand_cover_eval = false; // a failed advance leaves eval_x to be reset: its sweep candidates cover nothing
         s.tm.ms_advance += t_all.stop();
         s.tm.n_advance += 1;
         *out = result;
@@ -304,7 +308,7 @@ void step_advance(State &s, PpfStepResult *out) {
         k_apply_dx<<<gv, 256, 0, q>>>(nv, s.eval_x.p, s.x_old.p, s.dx.p, toi_recale);
         LAUNCH_COUNT(1);
         if (prm.fix_xz) {
-            k_fix_xz<<<gv, 256, 0, q>>>(nv, s.eval_x.p, s.curr.p, s.fix_index.p, prm.fix_xz);
+            k_fix_xz<<<gv, 256, 0, q>>>(nv, s.eval_x.p, s.prev.p, s.fix_index.p, prm.fix_xz);
             LAUNCH_COUNT(1);
         }
 

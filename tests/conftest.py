@@ -75,7 +75,11 @@ def golden_cases():
     import json
 
     out = []
-    for name in ("fast_twist_n16", "fast_twist_n24", "five_twist_n24", "hang_n32", "woven_n32", "woven_sl_n32", "drape_n32"):
+    # second line: reference golden for the features written late in round 1 (make_golden.sh next-round, run on a B200 in round 2)
+    for name in ("fast_twist_n16", "fast_twist_n24", "five_twist_n24", "hang_n32", "woven_n32", "woven_sl_n32", "drape_n32",
+                 "headless_ref_n24", "lift_n24", "sheet_arap_n24", "sheet_stvk_n24", "sheet_snhk_n24", "sheet_damped_n24", "woven_damped_n32",
+                 "seam_n16", "sheet_plastic_n24", "sheet_fixxz_n24", "drape_mesh_n24", "sheet_torque_n24", "balloon_n24",
+                 "fast_twist_quad_n16", "fast_twist_log_n16"):
         if not os.path.exists(os.path.join(GOLDEN, name, "meta.json")):
             continue
         d = os.path.join(GOLDEN, name)

