@@ -78,7 +78,7 @@ def host():
 class Session:
     """One scene + one backend library (one per process: the backends keep global state)."""
 
-    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None):
+    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None, allow_init_failure=False):
         """shard = (rank, world, nccl_id_bytes[, allgather]): row-shard the PCG solve of this scene over `world`
         GPUs (every rank builds the same scene; see csrc/dist.hpp).  `allgather(bytes) -> [bytes per rank]` is
         the launcher's object all-gather; with it the ranks also exchange CUDA IPC handles and the per-iteration
@@ -100,7 +100,8 @@ class Session:
             raise RuntimeError("cannot open backend: %s" % self.h.ppfh_error(self.p).decode())
         self.log_dir = log_dir or "/tmp/ppf_b200_logs_%d" % os.getpid()
         os.makedirs(self.log_dir, exist_ok=True)
-        if not self.h.ppfh_init(self.p, self.log_dir.encode()):
+        self.init_ok = bool(self.h.ppfh_init(self.p, self.log_dir.encode()))
+        if not self.init_ok and not allow_init_failure:
             raise RuntimeError("backend initialize() failed")
         self.is_b200 = bool(self.h.ppfh_has_b200_ext(self.p))
         self.sharded = False
@@ -227,6 +228,25 @@ class Session:
         frag = self._sym("oracle_fetch_fragile", *fetch_t)
         return total, [self._pair_list(fetch, k) for k in range(4)], [self._pair_list(frag, k) for k in range(4)]
 
+    def intersection_records(self):
+        """fetch_intersection_records (main.cu:2341) of the last intersection check: list of
+        (type, elem0, elem1, positions[(n0 + n1) x 3]) sorted by (type, elem0, elem1) -- the slot order is atomics order."""
+        class Rec(ctypes.Structure):  # PpfIntersectionRecord, 80 bytes
+            _fields_ = [("type", ctypes.c_uint), ("elem0", ctypes.c_uint), ("elem1", ctypes.c_uint), ("num_verts0", ctypes.c_uint),
+                        ("num_verts1", ctypes.c_uint), ("positions", ctypes.c_float * 15)]
+        fn = self._sym("fetch_intersection_records", ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint)
+        buf = (Rec * 256)()
+        n = int(fn(ctypes.cast(buf, ctypes.c_void_p), 256))
+        out = []
+        for r in buf[:n]:
+            k = 3 * (r.num_verts0 + r.num_verts1)
+            out.append((int(r.type), int(r.elem0), int(r.elem1), tuple(float(v) for v in r.positions[:k])))
+        return sorted(out)
+
+    def fatal_code(self):
+        fn = self._sym("ppf_fatal_code", ctypes.c_ubyte)
+        return int(fn())
+
     def fix_targets(self):
         n = int(self.h.ppfh_fix_targets(self.p, None, None))
         idx = np.empty(n, np.uint32); pos = np.empty((n, 3), np.float32)
@@ -287,6 +307,17 @@ def exported_symbols(lib):
 def pattern_keys(index, offset):
     rows = np.repeat(np.arange(offset.size - 1, dtype=np.uint64), np.diff(offset.astype(np.int64)))
     return rows << np.uint64(32) | index.astype(np.uint64)
+
+
+def write_state_file(path, curr, prev, time=0.0, prev_dt=1e-3, dyn_index=None, dyn_offset=None):
+    """host/backend.cpp save_state: magic 'PPST', n_vert, n_index, n_offset, time f64, prev_dt f32, curr, prev, dyn pattern"""
+    curr = np.ascontiguousarray(curr, np.float32); prev = np.ascontiguousarray(prev, np.float32)
+    di = np.zeros(0, np.uint32) if dyn_index is None else np.ascontiguousarray(dyn_index, np.uint32)
+    do = np.zeros(0, np.uint32) if dyn_offset is None else np.ascontiguousarray(dyn_offset, np.uint32)
+    with open(path, "wb") as f:
+        f.write(np.array([0x54535050, curr.shape[0], di.size, do.size], np.uint32).tobytes())
+        f.write(np.array([time], np.float64).tobytes()); f.write(np.array([prev_dt], np.float32).tobytes())
+        f.write(curr.tobytes()); f.write(prev.tobytes()); f.write(di.tobytes()); f.write(do.tobytes())
 
 
 def load_state_file(path):

@@ -23,6 +23,8 @@ def run(job):
     import ppf_b200
 
     lib = {"ours": ppf_b200.LIB_OURS, "reference": ppf_b200.LIB_REF, "oracle": ppf_b200.LIB_ORACLE,
+           # the reference with ONE hook that writes its four contact-pair caches to a file (oracle/ref_pair_dump.hpp)
+           "reference_pairs": os.path.join(REPO, "oracle", "_ref", "libsimbackend_cuda_pairs.so"),
            "emu": os.path.join(REPO, "tests", "native", "build", "emu", "libemu.so")}[job["lib"]]   # the backend's kernels run on the host (tests/test_kernel_emulation.py)
     out = job["out"]
     shutil.rmtree(out, ignore_errors=True)
@@ -36,8 +38,20 @@ def run(job):
         os.environ["PPF_DUMP_DIR"] = out
     else:
         os.environ.pop("PPF_DUMP_LINSYS", None)
-    s = ppf_b200.Session(job["scene"], n=job.get("n", 0), lib=lib, log_dir=os.path.join(out, "logs"), state=job.get("state"))
+    if job.get("dump_pairs"):
+        os.environ["PPF_DUMP_PAIRS_DIR"] = out
+    else:
+        os.environ.pop("PPF_DUMP_PAIRS_DIR", None)
+    s = ppf_b200.Session(job["scene"], n=job.get("n", 0), lib=lib, log_dir=os.path.join(out, "logs"), state=job.get("state"),
+                         allow_init_failure=bool(job.get("allow_init_failure")))
     res = {"counts": np.array([s.n_vert, s.n_face, s.n_edge, s.n_hinge, s.n_fix], np.int64)}
+    if job.get("allow_init_failure"):   # positive path of the intersection check: initialize() may refuse the start state
+        rec = s.intersection_records()
+        res["init_ok"] = np.array([s.init_ok]); res["fatal_code"] = np.array([s.fatal_code()])
+        res["isect"] = np.array([[t, a, b] + list(pos) + [0.0] * (15 - len(pos)) for t, a, b, pos in rec], np.float64).reshape(len(rec), 18)
+        if not s.init_ok:
+            np.savez(os.path.join(out, "result.npz"), **res)
+            return res
     if job.get("detect") == "state":
         x0, _ = s.fetch()
         _pairs(s, x0, res, "state", job.get("detect_twice"))
@@ -61,10 +75,26 @@ def run(job):
         res["stats_json"] = np.array(json.dumps(st))
     if job.get("detect") == "final":
         _pairs(s, curr, res, "final", job.get("detect_twice"))
+    if job.get("dump_pairs"):
+        for k, p in enumerate(read_pair_dump(os.path.join(out, "pairs_0.bin"))):
+            res["ref_pairs%d" % k] = p
     if job.get("fix_positions"):
         res["fix_index"], res["fix_target"] = s.fix_targets()
     np.savez(os.path.join(out, "result.npz"), **res)
     return res
+
+
+def read_pair_dump(path):
+    """oracle/ref_pair_dump.hpp: magic, overflow, four counts, four (count x 2) u32 lists in discovery order -> sorted by (a, b)"""
+    raw = np.fromfile(path, dtype=np.uint32)
+    assert raw[0] == 0x52494150 and raw[1] == 0, "pair dump missing or a cache overflowed"
+    out, at = [], 6
+    for k in range(4):
+        n = int(raw[2 + k])
+        p = raw[at:at + 2 * n].reshape(n, 2)
+        at += 2 * n
+        out.append(p[np.lexsort((p[:, 1], p[:, 0]))])
+    return out
 
 
 def _pairs(s, x, res, tag, twice):
