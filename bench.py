@@ -18,9 +18,9 @@ by oracle/Makefile.ref) through the same host on the same scene.  The reference 
 path, so its "own implementation of the path" is that CUDA build on this B200.
 
 N > 1 (torchrun): every rank holds the same scene and the rows of the PCG solve (>90 % of the step)
-are sharded over the GPUs inside the backend -- NCCL halo exchange of the search direction plus two
-2-double all-reduces per iteration, captured in the iteration graph (csrc/dist.hpp).  "scaling" is
-"strong": `value` = frames of the ONE scene / max-over-ranks device time.  --replicas instead runs N
+are sharded over the GPUs inside the backend -- rows of the search direction pushed over NVLink peer
+memory plus two 2-double sums per iteration (csrc/dist.hpp).  "scaling" is "strong" at every N:
+`value` = frames of the ONE scene / max-over-ranks device time.  --replicas instead runs N
 independent scenes (weak scaling).
 """
 import argparse
@@ -233,6 +233,7 @@ def main():
         barrier()
         clocks = ClockSampler()
         clocks.start()
+        log0 = {ch: len(s.read_log(ch)) for ch in ("iter", "newton_steps", "num_contact")}   # both arms write these channels
         st0 = s.stats() if s.is_b200 else None
         t_sim0 = s.time
         wall_e2e = 0.0
@@ -249,6 +250,7 @@ def main():
         clocks.join(timeout=2)
         st1 = s.stats() if s.is_b200 else None
         frames = (s.time - t_sim0) * fps
+        logs = {ch: s.read_log(ch)[log0[ch]:] for ch in log0}
         spmv = s.measure_spmv(20) if s.is_b200 else None
         h2d, d2h = s.io_bytes()
     finally:
@@ -281,7 +283,8 @@ def main():
         "warmup": W,
         "ms_per_step": 1e3 * t_dev / K,
         "higher_is_better": True,
-        "scaling": "strong" if shard is not None else "weak",
+        # one scene whatever N is: its rows are sharded over the GPUs (strong scaling); --replicas runs N independent scenes
+        "scaling": "weak" if (args.replicas and WORLD > 1) else "strong",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
@@ -290,11 +293,20 @@ def main():
             ("1/120" if "woven" in args.scene else ("1e-3" if args.scene == "hang" else "1/60")) + (", steps from the saved state %s" % os.path.basename(args.state) if args.state else ", steps from t=0"),
             ("one scene, PCG rows sharded over %d GPUs (rows of p pushed + two 2-double sums per iteration over NVLink peer memory)" % WORLD) if shard is not None
             else ("replicas (one independent scene per GPU)" if WORLD > 1 else "single GPU")),
-            "l2": "inputs larger than L2 (packed matrix %.0f MB per SpMV)" % ((40.0 * (st1["spmv_n_off"] if st1 else 0) + 60.0 * s.n_vert) * 1e-6)},
+            # the same text on both arms: from the topology-fixed block count the host knows (contact blocks come on top)
+            "l2": "inputs larger than L2 (fixed part of the matrix alone: %.0f MB per SpMV, 40 B per strictly-upper block + 60 B per row)"
+                  % ((40.0 * (s.fixed_nnz - s.n_vert) + 60.0 * s.n_vert) * 1e-6)},
         "e2e": {"value": tot_frames / t_e2e, "unit": "frames/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks.result(),
     }
+    # work done in the timed region, read from the log channels both libraries write (advance.iter / newton_steps / num_contact):
+    # lets a reader check that the two arms solved the same problem, and gives the time-per-unit-of-work figures next to frames/sec
+    n_solves = len(logs["iter"])
+    line["work"] = {"frames_per_step": tot_frames / K, "newton_solves": n_solves, "pcg_iters": int(sum(logs["iter"])),
+                    "pcg_iters_per_solve": (sum(logs["iter"]) / n_solves) if n_solves else None,
+                    "num_contact_first": int(logs["num_contact"][0]) if logs["num_contact"] else None,
+                    "num_contact_last": int(logs["num_contact"][-1]) if logs["num_contact"] else None}
     if n_newton:
         line["ms_per_newton_step"] = 1e3 * dev_s / n_newton
         line["newton_steps_per_step"] = n_newton / K
@@ -305,6 +317,9 @@ def main():
         line["impl"] = "reference"
         line["value"] = tot_frames / wall_adv
         line["ms_per_step"] = 1e3 * wall_adv / K
+        if n_solves:
+            line["ms_per_newton_step"] = 1e3 * wall_adv / n_solves
+            line["us_per_pcg_iter_incl_everything"] = 1e6 * wall_adv / max(1, sum(logs["iter"]))
         line["gpu_launches"] = None
         line["e2e"] = {"value": line["value"], "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         line["cpu_baseline"] = {"value": line["value"], "unit": "frames/sec", "cores": os.cpu_count(), "kind": "reference",

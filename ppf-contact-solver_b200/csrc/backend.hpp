@@ -168,6 +168,7 @@ struct State {
     DBuf<unsigned long long> dyn_keys, dyn_keys_sorted;
     DBuf<unsigned> dyn_off, dyn_col;
     DBuf<float> dyn_val;
+    DBuf<unsigned char> dyn_keep;                 // per block: non-zero when freshly assembled, i.e. before the Dirichlet elimination (fetch_dyn)
     unsigned dyn_nnz = 0;
     unsigned long long dyn_cap = 0;
     // carried pattern handed through fetch_dyn / update_dyn

@@ -27,6 +27,7 @@
 #include "math_cmesh.cuh"
 #include "math_contact.cuh"
 #include "math_distance.cuh"
+#include "warp_prims.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cub/device/device_radix_sort.cuh>
@@ -36,25 +37,6 @@ namespace ppf {
 
 __device__ __forceinline__ V3 ld3c(const float4 *p, unsigned i) { const float4 v = p[i]; return mk(v.x, v.y, v.z); }
 __device__ __forceinline__ float sqr(float x) { return x * x; }
-
-// warp-cooperative slot allocation: every lane of a full warp calls this with its own k
-__device__ __forceinline__ unsigned warp_alloc(unsigned *counter, unsigned k) {
-#ifdef PPF_EMULATE // tests/native/emu runs the kernels one thread at a time on the host: there is no warp to cooperate with
-    return k ? atomicAdd(counter, k) : 0u;
-#endif
-    const unsigned lane = threadIdx.x & 31;
-    unsigned incl = k;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += t;
-    }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned base = 0;
-    if (lane == 31 && total) base = atomicAdd(counter, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    return base + incl - k;
-}
 
 // ---------------------------------------------------------------------------------------------
 // broad phase
@@ -444,6 +426,16 @@ template <int KIND> __global__ void __launch_bounds__(256) k_keys(Ctx c, const u
     for (unsigned q = 0; q < k; ++q) out[base + q] = keys[q];
 }
 
+__global__ void k_dyn_keep(unsigned nnz, const float *__restrict__ val, unsigned char *__restrict__ keep) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    bool zero = true;
+#pragma unroll
+    for (int e = 0; e < 9; ++e)
+        if (!(fabsf(val[size_t(9) * k + e]) <= 1e-5f)) zero = false;
+    keep[k] = zero ? 0 : 1;
+}
+
 __global__ void k_dyn_structure(unsigned nv, unsigned nnz, const unsigned long long *keys, unsigned shift, unsigned *off, unsigned *col) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nnz) col[t] = (unsigned)(keys[t] & ((1ull << shift) - 1ull));
@@ -707,6 +699,14 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
     if (hc[2]) k_fill<2><<<div_up(hc[2], 128), 128, 0, q>>>(c, s.pairs[2].pairs.p, hc[2]);
     if (hc[3]) k_fill<3><<<div_up(hc[3], 128), 128, 0, q>>>(c, s.pairs[3].pairs.p, hc[3]);
     LAUNCH_COUNT(4);
+    // which blocks the reference's finalize() would keep (row_dedupe.hpp:96-150 drops blocks that are zero in SMat::isZero's
+    // sense) -- decided HERE, on the freshly accumulated values: the Dirichlet elimination zeroes the blocks of pinned rows and
+    // columns afterwards (main.cu:954-1049), and the reference's carried pattern (fetch_dyn) still lists those
+    s.dyn_keep.reserve(std::max<size_t>(nnz, 16));
+    if (nnz) {
+        k_dyn_keep<<<div_up(nnz, 256), 256, 0, q>>>(nnz, s.dyn_val.p, s.dyn_keep.p);
+        LAUNCH_COUNT(1);
+    }
     s.dyn_valid = true;
     if (prof) {
         const auto t3 = now();
@@ -718,25 +718,21 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
 }
 
 // pattern handed out by fetch_dyn: per row, the sorted columns whose accumulated block is not
-// "zero" in the reference's sense (SMat::isZero, |m| <= 1e-5 for all entries; row_dedupe.hpp:96-150)
+// "zero" in the reference's sense (SMat::isZero, |m| <= 1e-5 for all entries; row_dedupe.hpp:96-150), see k_dyn_keep
 void build_fetch_pattern(State &s, std::vector<unsigned> &index, std::vector<unsigned> &offset) {
     const unsigned nv = s.nv, nnz = s.dyn_nnz;
     offset.assign(nv + 1, 0);
     index.clear();
     if (!nnz) return;
     std::vector<unsigned> off(nv + 1), col(nnz);
-    std::vector<float> val(size_t(9) * nnz);
+    std::vector<unsigned char> keep(nnz);
     CUDA_OK(cudaMemcpy(off.data(), s.dyn_off.p, sizeof(unsigned) * (nv + 1), cudaMemcpyDeviceToHost));
     CUDA_OK(cudaMemcpy(col.data(), s.dyn_col.p, sizeof(unsigned) * nnz, cudaMemcpyDeviceToHost));
-    CUDA_OK(cudaMemcpy(val.data(), s.dyn_val.p, sizeof(float) * 9 * size_t(nnz), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(keep.data(), s.dyn_keep.p, nnz, cudaMemcpyDeviceToHost));
     for (unsigned i = 0; i < nv; ++i) {
         offset[i] = (unsigned)index.size();
-        for (unsigned k = off[i]; k < off[i + 1]; ++k) {
-            bool zero = true;
-            for (int e = 0; e < 9; ++e)
-                if (!(fabsf(val[size_t(9) * k + e]) <= 1e-5f)) { zero = false; break; }
-            if (!zero) index.push_back(col[k]);
-        }
+        for (unsigned k = off[i]; k < off[i + 1]; ++k)
+            if (keep[k]) index.push_back(col[k]);
     }
     offset[nv] = (unsigned)index.size();
 }
@@ -904,12 +900,7 @@ __global__ void __launch_bounds__(128) k_collider(unsigned nsv, const float4 *__
             }
         }
     }
-#ifdef PPF_EMULATE // tests/native/emu: one thread at a time, a shuffle returns the caller's own value (fine for min / max, not for sums)
-    if (count) atomicAdd(counter, count);
-    return;
-#endif
-    for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
-    if ((threadIdx.x & 31) == 0 && count) atomicAdd(counter, count);
+    warp_sum_add(counter, count);
 }
 
 __global__ void __launch_bounds__(128) k_collider_toi(unsigned nsv, const float4 *__restrict__ x0, const float4 *__restrict__ x1,

@@ -31,6 +31,8 @@
 #include "dist.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <vector>
 
 namespace ppf {
 
@@ -66,8 +68,12 @@ struct PackedMatrix {
     DBuf<unsigned> fx_pos;           // per ORIGINAL fixed slot: position in the block list, 0xFFFFFFFF for diagonals
     DBuf<float> D, Pinv;             // 6 planes x n: (00, 11, 22, 01, 02, 12)
     DBuf<float> x, r, z;             // three SoA planes of n floats each
-    DBuf<float4> p, y;
+    DBuf<float4> py;                 // [p | y], see pcg_init
+    DBuf<float4> p, y;               // views into py
     DBuf<CgScalars> sc;
+    cudaAccessPolicyWindow l2win = {}; // persisting-L2 window over y (and p), also stamped on the graph's kernel nodes
+    bool l2win_on = false;
+    int evict_first = 1;             // matrix stream loaded with L2::evict_first (PPF_B200_L2_STREAM=0: evict_normal, for A/B timing)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     unsigned graph_nnz = ~0u;
@@ -98,6 +104,39 @@ static constexpr int SPMV_ARRAYS = 11;                   // row, col, nine value
 static constexpr unsigned SPMV_STAGE_BYTES = SPMV_ARRAYS * SPMV_CHUNK * 4;
 static constexpr size_t SPMV_SMEM = size_t(SPMV_STAGES) * SPMV_STAGE_BYTES + 128;
 static size_t round_cap(size_t n) { return (n + SPMV_CHUNK - 1) / SPMV_CHUNK * SPMV_CHUNK + SPMV_CHUNK; }
+
+// B200's 126 MB L2 against the vectors that several kernels of ONE iteration touch: y (16 B x N rows; 51 MB at large-twist) is
+// written by k_direction (y = D p), read-modify-written by the SpMV's vector reductions and read by k_update -- four passes
+// over DRAM per iteration (~200 MB of ~1450 MB) if the 707 MB matrix stream flushes it in between.  A persisting access-policy
+// window keeps y in an L2 set-aside; the matrix stream itself is loaded with an L2 evict_first hint (bulk_g2s) so that it
+// does not push out p (gathered by the SpMV right after k_direction wrote it) either.
+//   PPF_B200_L2_PERSIST = y (default) | yp (window over p and y, hit ratio = set-aside / window) | 0 (off, for A/B timing)
+static void pcg_l2_policy(State &s) {
+    if (const char *e = getenv("PPF_B200_L2_STREAM")) P.evict_first = e[0] != '0';
+    const char *mode = getenv("PPF_B200_L2_PERSIST");
+    if (mode && mode[0] == '0') return;
+    const bool both = mode && strcmp(mode, "yp") == 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    const size_t bytes_one = sizeof(float4) * P.n_pad;
+    size_t window = both ? 2 * bytes_one : bytes_one;
+    window = std::min(window, (size_t)prop.accessPolicyMaxWindowSize);
+    const size_t setaside = std::min((size_t)prop.persistingL2CacheMaxSize, window);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) != cudaSuccess) { cudaGetLastError(); return; }
+    P.l2win.base_ptr = both ? (void *)P.p.p : (void *)P.y.p;
+    P.l2win.num_bytes = window;
+    P.l2win.hitRatio = (float)std::min(1.0, double(setaside) / double(window));
+    P.l2win.hitProp = cudaAccessPropertyPersisting;
+    P.l2win.missProp = cudaAccessPropertyStreaming;
+    cudaStreamAttrValue v = {};
+    v.accessPolicyWindow = P.l2win;
+    if (cudaStreamSetAttribute(s.stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) { cudaGetLastError(); return; }
+    P.l2win_on = true;
+    log_info("pcg: persisting L2 window over %s: %.1f MB (set-aside %.1f MB of %.1f MB max, hit ratio %.2f)", both ? "p|y" : "y", window * 1e-6,
+             setaside * 1e-6, prop.persistingL2CacheMaxSize * 1e-6, P.l2win.hitRatio);
+}
 
 static void pcg_init(State &s) {
     const unsigned n = s.nv;
@@ -149,7 +188,13 @@ static void pcg_init(State &s) {
     P.fx_pos.upload(pos.data(), nnz, q);
     CUDA_OK(cudaStreamSynchronize(q));
     P.D.reserve(size_t(6) * n); P.Pinv.reserve(size_t(6) * n);
-    P.x.reserve(size_t(3) * n); P.r.reserve(size_t(3) * n); P.z.reserve(size_t(3) * n); P.p.reserve(P.n_pad); P.y.reserve(P.n_pad);
+    P.x.reserve(size_t(3) * n); P.r.reserve(size_t(3) * n); P.z.reserve(size_t(3) * n);
+    // p and y share ONE allocation (p first: its IPC handle is exported to the peers, dist.cu) so that one L2 access-policy
+    // window can cover them; P.p / P.y are non-owning views of it
+    P.py.reserve(2 * P.n_pad);
+    P.p.p = P.py.p; P.p.cap = P.n_pad;
+    P.y.p = P.py.p + P.n_pad; P.y.cap = P.n_pad;
+    pcg_l2_policy(s);
     if (world > 1) s.dx.reserve_keep(size_t(3) * P.n_pad, q); // the solved step is all-gathered in place, in equal slices
     P.sc.reserve(1);
     CUDA_OK(cudaMallocHost(&P.h_status, 64));
@@ -431,9 +476,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     while (!done)
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
+// the block list is read once per launch: its lines are the first to go when L2 needs room (L2::evict_first), so that the
+// vectors the kernels of one iteration share (p, y) stay resident
+__device__ __forceinline__ unsigned long long l2_stream_policy(int evict_first) {
+    unsigned long long pol;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
 }
 
@@ -498,7 +551,7 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
                                                           unsigned nnz, unsigned row_lo, unsigned row_hi, const unsigned *__restrict__ row,
                                                           const unsigned *__restrict__ col, const float *__restrict__ val, size_t plane,
                                                           const float4 *__restrict__ p, float4 *__restrict__ y, CgScalars *sc, int with_dots,
-                                                          PeerView pv, int publish) {
+                                                          PeerView pv, int publish, int evict_first) {
     if (with_dots && sc->status != ST_RUNNING) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
@@ -512,14 +565,15 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const unsigned long long pol = l2_stream_policy(evict_first);
     auto fill = [&](int st, unsigned ci) {
         unsigned *dst = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
         const size_t base = desc(ci).base;
         mbar_expect_tx(&full[st], SPMV_STAGE_BYTES);
-        bulk_g2s(dst, row + base, SPMV_CHUNK * 4, &full[st]);
-        bulk_g2s(dst + SPMV_CHUNK, col + base, SPMV_CHUNK * 4, &full[st]);
+        bulk_g2s(dst, row + base, SPMV_CHUNK * 4, &full[st], pol);
+        bulk_g2s(dst + SPMV_CHUNK, col + base, SPMV_CHUNK * 4, &full[st], pol);
 #pragma unroll
-        for (int e = 0; e < 9; ++e) bulk_g2s(dst + (2 + e) * SPMV_CHUNK, val + size_t(e) * plane + base, SPMV_CHUNK * 4, &full[st]);
+        for (int e = 0; e < 9; ++e) bulk_g2s(dst + (2 + e) * SPMV_CHUNK, val + size_t(e) * plane + base, SPMV_CHUNK * 4, &full[st], pol);
     };
     if (tid == 0)
         for (int st = 0; st < SPMV_STAGES; ++st) {
@@ -949,7 +1003,7 @@ static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const 
     const unsigned k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
     const unsigned grid = std::min(P.spmv_grid, div_up(k_end - k_begin, SPMV_CHUNK));
     k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0u, k_begin, k_first, k_end, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
-                                                         PeerView{}, 0);
+                                                         PeerView{}, 0, P.evict_first);
 }
 // several ranks: one launch over this rank's chunk list; with peer memory its last CTA publishes the partial p.Ap
 static void launch_spmv_chunks(State &s, const float4 *p, float4 *y, int with_dots, int publish) {
@@ -960,7 +1014,7 @@ static void launch_spmv_chunks(State &s, const float4 *p, float4 *y, int with_do
     }
     const unsigned grid = std::max(1u, std::min(P.spmv_grid, R.n_chunks));
     k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
-                                                         dist_peers(), publish);
+                                                         dist_peers(), publish, P.evict_first);
 }
 
 static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
@@ -1155,6 +1209,19 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
         CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < ITER_PER_GRAPH; ++k) issue_iteration(s, k & 1);
         CUDA_OK(cudaStreamEndCapture(q, &P.graph));
+        if (P.l2win_on) { // the window is a stream attribute; make sure every captured kernel node carries it
+            size_t nn = 0;
+            CUDA_OK(cudaGraphGetNodes(P.graph, nullptr, &nn));
+            std::vector<cudaGraphNode_t> nodes(nn);
+            CUDA_OK(cudaGraphGetNodes(P.graph, nodes.data(), &nn));
+            cudaKernelNodeAttrValue av = {};
+            av.accessPolicyWindow = P.l2win;
+            for (cudaGraphNode_t nd : nodes) {
+                cudaGraphNodeType ty;
+                if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel)
+                    if (cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+            }
+        }
         CUDA_OK(cudaGraphInstantiate(&P.exec, P.graph, 0ull));
         P.graph_nnz = nnz;
         P.graph_val = (const void *)P.val.p;

@@ -41,6 +41,12 @@ def test_oracle_reproduces_reference_step(run_job, name, scene, n, state, refdir
         assert abs(mine - theirs) <= 2 + 0.05 * theirs
     for mine, theirs in zip(r["log_toi"], logs["toi"]):
         assert abs(mine - theirs) < 1e-2
+    # carried contact pattern (fetch_dyn) of the last assembly: tie-decided pairs aside, the reference's
+    import ppf_b200
+    ri = np.fromfile(os.path.join(refdir, "dyn_index.bin"), dtype=np.uint32)
+    ro = np.fromfile(os.path.join(refdir, "dyn_offset.bin"), dtype=np.uint32)
+    a = set(ppf_b200.pattern_keys(ri, ro).tolist()); b = set(ppf_b200.pattern_keys(r["dyn_index"], r["dyn_offset"]).tolist())
+    assert len(a ^ b) <= 12 + 0.01 * len(a), (len(a), len(b), len(a ^ b))
     c = compare(os.path.join(refdir, "linsys_0.bin"), os.path.join(r["out_dir"], "linsys_0.bin"), verbose=False)
     nb = c["n_blocks"][0]
     assert c["only_ref"] + c["only_ours"] <= max(2, 0.002 * nb), c
