@@ -299,6 +299,9 @@ int ppf_b200_dist_init(int rank, int world, const unsigned char *id_bytes, unsig
  * per-iteration collectives now run over NVLink peer memory, 0/negative when NCCL stays in use. */
 int ppf_b200_dist_export(unsigned char *out, unsigned cap);
 int ppf_b200_dist_connect(const unsigned char *all, unsigned len);
+/* Self-test of the backend's own radix sort / unique kernels (csrc/prims.cu) on n pseudo-random keys against the host's
+ * std::stable_sort / std::unique; 0 = every check passed.  Needs no initialize(). */
+int ppf_b200_selftest_sort(unsigned n, int bits, unsigned seed);
 /* Average microseconds of the SpMV kernel alone on the last packed system (CUDA events, `reps` launches). */
 double ppf_b200_measure_spmv(unsigned reps, unsigned long long *n_row, unsigned long long *n_off);
 

@@ -42,7 +42,7 @@ __global__ void k_distance(const float *in, unsigned n, float *out_ref, float *o
         r[3] = e.squaredNorm();
         ppf::C3 d = ppf::point_triangle_coeff(mv(p), mv(p + 3), mv(p + 6), mv(p + 9));
         m[0] = d.a; m[1] = d.b; m[2] = d.c;
-        ppf::V3 f = d.a * (mv(p) - mv(p + 3)) + d.b * (mv(p) - mv(p + 6)) + d.c * (mv(p) - mv(p + 9));
+        ppf::V3 f = ppf::lin3(d.a, mv(p) - mv(p + 3), d.b, mv(p) - mv(p + 6), d.c, mv(p) - mv(p + 9));
         m[3] = ppf::sqnorm(f);
     }
     {
@@ -52,7 +52,7 @@ __global__ void k_distance(const float *in, unsigned n, float *out_ref, float *o
         r[6] = e.squaredNorm();
         ppf::C2 d = ppf::point_edge_coeff(mv(p), mv(p + 3), mv(p + 6));
         m[4] = d.a; m[5] = d.b;
-        ppf::V3 f = d.a * (mv(p) - mv(p + 3)) + d.b * (mv(p) - mv(p + 6));
+        ppf::V3 f = ppf::lin2(d.a, mv(p) - mv(p + 3), d.b, mv(p) - mv(p + 6));
         m[6] = ppf::sqnorm(f);
     }
     {
@@ -64,7 +64,7 @@ __global__ void k_distance(const float *in, unsigned n, float *out_ref, float *o
         r[11] = e.squaredNorm();
         ppf::C4 d = ppf::edge_edge_coeff(mv(p), mv(p + 3), mv(p + 6), mv(p + 9));
         m[7] = d.a; m[8] = d.b; m[9] = d.c; m[10] = d.d;
-        ppf::V3 a = d.a * mv(p) + d.b * mv(p + 3), b = d.c * mv(p + 6) + d.d * mv(p + 9);
+        ppf::V3 a = ppf::lin2(d.a, mv(p), d.b, mv(p + 3)), b = ppf::lin2(d.c, mv(p + 6), d.d, mv(p + 9));
         ppf::V3 f = a - b;
         m[11] = ppf::sqnorm(f);
     }

@@ -83,8 +83,6 @@ struct Bvh {
     DBuf<float4> lo, hi;        // per node AABB (xyz)
     DBuf<float4> ulo, uhi;      // per node interval of sweep displacements t_max*(x1-x0) (relative-motion sweeps only)
     DBuf<unsigned> flag;        // bottom-up arrival counters
-    DBuf<unsigned char> sort_tmp;
-    size_t sort_tmp_bytes = 0;
     int root = 0;
 };
 
@@ -270,5 +268,10 @@ void apply_dirichlet(State &s);
 float reduce_max_f(State &s, const float *d, size_t n, float init);
 float reduce_min_f(State &s, const float *d, size_t n, float init);
 unsigned reduce_sum_u(State &s, const unsigned *d, size_t n);
+// prims.cu -- LSD radix sort of the low `bits` bits (stable; the first buffers are scratch afterwards, the result is in *_sorted)
+void radix_sort_pairs_u32(State &s, unsigned *keys, unsigned *keys_sorted, unsigned *vals, unsigned *vals_sorted, unsigned n, int bits);
+void radix_sort_keys_u64(State &s, unsigned long long *keys, unsigned long long *keys_sorted, unsigned n, int bits);
+// first key of every run of a sorted list -> out (may not alias), number of runs -> *d_count (device)
+void unique_sorted_u64(State &s, const unsigned long long *keys_sorted, unsigned long long *out, unsigned n, unsigned *d_count);
 
 } // namespace ppf

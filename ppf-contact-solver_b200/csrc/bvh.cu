@@ -13,7 +13,6 @@
 // Only conservativeness of the boxes matters for parity (the narrow phase decides), so the tree
 // shape is free to differ from the reference's.
 #include "bvh.cuh"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace ppf {
 
@@ -217,10 +216,7 @@ static void build_tree(State &s, Bvh &b, int kind, unsigned n, const float4 *x, 
     CUDA_OK(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, q));
     k_bounds<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, face, edge, bounds);
     k_morton<<<div_up(n, 256), 256, 0, q>>>(kind, n, x, face, edge, bounds, b.morton.p, b.prim.p);
-    size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, (int)n, 0, 30, q);
-    if (need > b.sort_tmp_bytes) { b.sort_tmp.reserve(need); b.sort_tmp_bytes = need; }
-    cub::DeviceRadixSort::SortPairs(b.sort_tmp.p, need, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, (int)n, 0, 30, q);
+    radix_sort_pairs_u32(s, b.morton.p, b.morton_sorted.p, b.prim.p, b.prim_sorted.p, n, 30); // prims.cu (4 passes of 8 bits)
     if (n > 1) k_radix_tree<<<div_up(n - 1, 256), 256, 0, q>>>((int)n, b.morton_sorted.p, b.child.p, b.parent.p);
     LAUNCH_COUNT(4);
     LeafParams P{x, x, 1.0f, face, edge, cp};

@@ -30,8 +30,6 @@
 #include "warp_prims.cuh"
 #include <algorithm>
 #include <chrono>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
 
 namespace ppf {
 
@@ -246,7 +244,7 @@ __device__ __forceinline__ bool eval_pf(const Ctx &c, unsigned v, unsigned fi, P
     const V3 p = ld3c(c.x, v), t0 = ld3c(c.x, f.x), t1 = ld3c(c.x, f.y), t2 = ld3c(c.x, f.z);
     const C3 cf = point_triangle_coeff(p, t0, t1, t2);
     if (!strictly_interior(cf)) return false;
-    const V3 e = cf.a * (p - t0) + cf.b * (p - t1) + cf.c * (p - t2);
+    const V3 e = lin3(cf.a, p - t0, cf.b, p - t1, cf.c, p - t2);
     const float4 vp = c.vcp[v], fp = c.fcp[fi];
     const float offset = vp.y + fp.y;
     const float ghat = 0.5f * (vp.x + fp.x);
@@ -267,7 +265,7 @@ __device__ __forceinline__ bool eval_pe(const Ctx &c, unsigned v, unsigned ei, P
     const V3 p = ld3c(c.x, v), t0 = ld3c(c.x, f.x), t1 = ld3c(c.x, f.y);
     const C2 cf = point_edge_coeff(p, t0, t1);
     if (!strictly_interior(cf)) return false;
-    const V3 e = cf.a * (p - t0) + cf.b * (p - t1);
+    const V3 e = lin2(cf.a, p - t0, cf.b, p - t1);
     const float4 vp = c.vcp[v], ep = c.ecp[ei];
     const float offset = vp.y + ep.y;
     const float ghat = 0.5f * (vp.x + ep.x);
@@ -347,8 +345,8 @@ __device__ __forceinline__ bool eval_ee(const Ctx &c, unsigned ea, unsigned eb, 
     const V3 p0 = ld3c(c.x, e0.x), p1 = ld3c(c.x, e0.y), q0 = ld3c(c.x, e1.x), q1 = ld3c(c.x, e1.y);
     const C4 cf = edge_edge_coeff(p0, p1, q0, q1);
     if (!strictly_interior(cf)) return false;
-    const V3 xa = cf.a * p0 + cf.b * p1;
-    const V3 xb = cf.c * q0 + cf.d * q1;
+    const V3 xa = lin2(cf.a, p0, cf.b, p1);
+    const V3 xb = lin2(cf.c, q0, cf.d, q1);
     const V3 e = xa - xb;
     const float4 ap = c.ecp[ea], bp = c.ecp[eb];
     const float offset = ap.y + bp.y;
@@ -567,7 +565,6 @@ static Ctx make_ctx(State &s, const PpfParamSet &prm) {
     return c;
 }
 
-static DBuf<unsigned char> g_cub_tmp;
 
 // broad + narrow phase at eval_x: fills s.pairs[0..3] (unsorted) and returns the four counts
 static std::vector<uint2> sorted_pairs_host(State &s, int k) {
@@ -673,13 +670,8 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
     CUDA_OK(cudaStreamSynchronize(q));
     unsigned nnz = 0;
     if (nkeys) {
-        size_t need = 0, need2 = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, need, s.dyn_keys.p, s.dyn_keys_sorted.p, (int)nkeys, 0, (int)(2 * shift), q);
-        cub::DeviceSelect::Unique(nullptr, need2, s.dyn_keys_sorted.p, s.dyn_keys.p, key_cnt + 1, (int)nkeys, q);
-        g_cub_tmp.reserve(std::max(need, need2));
-        cub::DeviceRadixSort::SortKeys(g_cub_tmp.p, need, s.dyn_keys.p, s.dyn_keys_sorted.p, (int)nkeys, 0, (int)(2 * shift), q);
-        cub::DeviceSelect::Unique(g_cub_tmp.p, need2, s.dyn_keys_sorted.p, s.dyn_keys.p, key_cnt + 1, (int)nkeys, q);
-        LAUNCH_COUNT(8);
+        radix_sort_keys_u64(s, s.dyn_keys.p, s.dyn_keys_sorted.p, nkeys, (int)(2 * shift));   // prims.cu
+        unique_sorted_u64(s, s.dyn_keys_sorted.p, s.dyn_keys.p, nkeys, key_cnt + 1);
         CUDA_OK(cudaMemcpyAsync(&nnz, key_cnt + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
         CUDA_OK(cudaStreamSynchronize(q));
     }
@@ -1335,7 +1327,7 @@ __global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
             const V3 q0 = ld3c(A.x, fv.x), q1 = ld3c(A.x, fv.y);
             if (!shared) {
                 const C4 c = edge_edge_coeff(y0, y1, q0, q1);
-                const V3 d = (c.a * y0 + c.b * y1) - (c.c * q0 + c.d * q1);
+                const V3 d = lin2(c.a, y0, c.b, y1) - lin2(c.c, q0, c.d, q1);
                 hit = dot(d, d) < offset * offset;
             } else {
                 const unsigned a[2] = {ev.x, ev.y}, b[2] = {fv.x, fv.y};
@@ -1344,7 +1336,7 @@ __global__ void __launch_bounds__(128) k_isect_edge(IsectArgs A, unsigned nq) {
                         if (a[i] == b[j]) {
                             const V3 p0 = ld3c(A.x, a[i]), p1 = ld3c(A.x, a[1 - i]), p2 = ld3c(A.x, b[1 - j]);
                             const C2 c0 = point_edge_coeff_unclassified(p1, p0, p2), c1 = point_edge_coeff_unclassified(p2, p0, p1);
-                            const V3 d0 = (c0.a * p0 + c0.b * p2) - p1, d1 = (c1.a * p0 + c1.b * p1) - p2;
+                            const V3 d0 = lin2(c0.a, p0, c0.b, p2) - p1, d1 = lin2(c1.a, p0, c1.b, p1) - p2;
                             hit = fminf(dot(d0, d0), dot(d1, d1)) < offset * offset;
                         }
             }

@@ -73,6 +73,7 @@ struct PackedMatrix {
     DBuf<CgScalars> sc;
     cudaAccessPolicyWindow l2win = {}; // persisting-L2 window over y (and p), also stamped on the graph's kernel nodes
     bool l2win_on = false;
+    int spmv_variant = 0;            // 0 staged (bulk copies through shared memory), 1 / 2 register-pipelined with 1 / 2 blocks per thread
     int evict_first = 1;             // matrix stream loaded with L2::evict_first (PPF_B200_L2_STREAM=0: evict_normal, for A/B timing)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -113,6 +114,7 @@ static size_t round_cap(size_t n) { return (n + SPMV_CHUNK - 1) / SPMV_CHUNK * S
 //   PPF_B200_L2_PERSIST = y (default) | yp (window over p and y, hit ratio = set-aside / window) | 0 (off, for A/B timing)
 static void pcg_l2_policy(State &s) {
     if (const char *e = getenv("PPF_B200_L2_STREAM")) P.evict_first = e[0] != '0';
+    if (const char *e = getenv("PPF_B200_SPMV")) P.spmv_variant = strcmp(e, "direct1") == 0 ? 1 : (strcmp(e, "direct2") == 0 ? 2 : 0);
     const char *mode = getenv("PPF_B200_L2_PERSIST");
     if (mode && mode[0] == '0') return;
     const bool both = mode && strcmp(mode, "yp") == 0;
@@ -201,7 +203,7 @@ static void pcg_init(State &s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    P.grid = (unsigned)sms * 8u;
+    P.grid = (unsigned)sms * 4u; // vector kernels: 4 CTAs of 256 threads per SM (pcg-tune on large-twist: update 39.5 us / direction 59.0 us at 592 CTAs, 42.9 / 60.9 at 1184)
     if (const char *e = getenv("PPF_B200_PCG_GRID")) P.grid = (unsigned)atoi(e);
     P.spmv_grid = (unsigned)sms * 4u;
     if (const char *e = getenv("PPF_B200_SPMV_GRID")) P.spmv_grid = (unsigned)atoi(e);
@@ -449,6 +451,89 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_spmv(unsigned nnz, const unsigned
         }
         const unsigned next = __shfl_down_sync(0xffffffffu, a, 1);
         if (on && (lane == 31 || next != a)) red_add_v4(y + a, s0, s1, s2);
+    }
+    if (!with_dots) return;
+    const int par = sc->iter & 1;
+    block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
+}
+
+// ---- the same product with the block list read straight into registers, software-pipelined ----
+// ncu on the staged kernel (profiles/r01_pcg_ncu_full_summary.json): the L1 data pipe runs at 80 % of its wavefront peak
+// (DRAM at 65 %) -- per 32 blocks ~22 wavefronts are the bulk copies WRITING shared memory, ~11 the LDS reads, ~16 the two
+// p gathers and ~26 the vector reductions.  Reading the eleven arrays with coalesced 128-byte loads instead costs 11
+// wavefronts per 32 blocks and no shared memory; the latency the staging hid is hidden here by issuing the loads of the
+// NEXT trip before the dependent gathers of the current one (U blocks per thread per trip, one trip ahead in registers).
+struct BlkRegs { unsigned a, b; float h[9]; };
+template <int U> __device__ __forceinline__ void spmv_load(BlkRegs (&r)[U], unsigned k0, unsigned lane, unsigned k_first, unsigned nnz,
+                                                           const unsigned *__restrict__ row, const unsigned *__restrict__ col,
+                                                           const float *__restrict__ val, size_t plane) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned k = k0 + u * 32 + lane;
+        if (k < nnz && k >= k_first) {
+            r[u].a = __ldcs(row + k);
+            r[u].b = __ldcs(col + k);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) r[u].h[e] = __ldcs(val + size_t(e) * plane + k);
+        } else {
+            r[u].a = 0xFFFFFFFFu;
+            r[u].b = 0;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) r[u].h[e] = 0.f;
+        }
+    }
+}
+template <int U, int MINB>
+__global__ void __launch_bounds__(PCG_BLOCK, MINB) k_spmv_direct(unsigned k_first, unsigned nnz, const unsigned *__restrict__ row, const unsigned *__restrict__ col,
+                                                                 const float *__restrict__ val, size_t plane, const float4 *__restrict__ p,
+                                                                 float4 *__restrict__ y, CgScalars *sc, int with_dots) {
+    if (with_dots && sc->status != ST_RUNNING) return;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warps_total = gridDim.x * (PCG_BLOCK / 32), wid = blockIdx.x * (PCG_BLOCK / 32) + (threadIdx.x >> 5);
+    const unsigned k_begin = k_first & ~31u;
+    const unsigned ntrips = (nnz - k_begin + 32 * U - 1) / (32 * U);
+    float dot = 0.f, absdot = 0.f;
+    BlkRegs cur[U], nxt[U];
+    unsigned t = wid; // warp-uniform
+    if (t < ntrips) spmv_load<U>(cur, k_begin + t * (32 * U), lane, k_first, nnz, row, col, val, plane);
+    while (t < ntrips) {
+        const unsigned tn = t + warps_total;
+        if (tn < ntrips) spmv_load<U>(nxt, k_begin + tn * (32 * U), lane, k_first, nnz, row, col, val, plane);
+        float4 pa[U], pb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool on = cur[u].a != 0xFFFFFFFFu;
+            pa[u] = on ? p[cur[u].a] : make_float4(0.f, 0.f, 0.f, 0.f);
+            pb[u] = on ? p[cur[u].b] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float *hh = cur[u].h;
+            const unsigned a = cur[u].a;
+            const bool on = a != 0xFFFFFFFFu;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            if (on) {
+                red_add_v4(y + cur[u].b, hh[0] * pa[u].x + hh[1] * pa[u].y + hh[2] * pa[u].z, hh[3] * pa[u].x + hh[4] * pa[u].y + hh[5] * pa[u].z,
+                           hh[6] * pa[u].x + hh[7] * pa[u].y + hh[8] * pa[u].z);
+                s0 = hh[0] * pb[u].x + hh[3] * pb[u].y + hh[6] * pb[u].z;
+                s1 = hh[1] * pb[u].x + hh[4] * pb[u].y + hh[7] * pb[u].z;
+                s2 = hh[2] * pb[u].x + hh[5] * pb[u].y + hh[8] * pb[u].z;
+                const float term = 2.0f * (pa[u].x * s0 + pa[u].y * s1 + pa[u].z * s2);
+                dot += term;
+                absdot += fabsf(term);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned ra = __shfl_up_sync(0xffffffffu, a, o);
+                const float t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+                if (lane >= (unsigned)o && ra == a) { s0 += t0; s1 += t1; s2 += t2; }
+            }
+            const unsigned next = __shfl_down_sync(0xffffffffu, a, 1);
+            if (on && (lane == 31 || next != a)) red_add_v4(y + a, s0, s1, s2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        t = tn;
     }
     if (!with_dots) return;
     const int par = sc->iter & 1;
@@ -1027,6 +1112,19 @@ static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
         return;
     }
     if (g_dist.on()) { launch_spmv_chunks(s, p, y, with_dots, with_dots && R.push ? 1 : 0); return; }
+    if (P.spmv_variant) { // one rank: the register-pipelined kernel (PPF_B200_SPMV=direct1|direct2|staged)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (P.spmv_variant == 1) {
+            const unsigned grid = std::min((unsigned)sms * 4u, div_up(R.kf_end - (R.kf_first & ~31u), PCG_BLOCK));
+            k_spmv_direct<1, 4><<<grid, PCG_BLOCK, 0, s.stream>>>(R.kf_first, R.kf_end, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+        } else {
+            const unsigned grid = std::min((unsigned)sms * 3u, div_up(R.kf_end - (R.kf_first & ~31u), 2 * PCG_BLOCK));
+            k_spmv_direct<2, 3><<<grid, PCG_BLOCK, 0, s.stream>>>(R.kf_first, R.kf_end, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots);
+        }
+        return;
+    }
     launch_spmv_range(s, R.kf_first, R.kf_end, p, y, with_dots);
 }
 
@@ -1106,6 +1204,16 @@ static void pcg_tune(State &s) {
         time_it(nm, 40.0 * nnz + 24.0 * n, [&] { launch_spmv(s, P.p.p, P.y.p, 1); });
     }
     P.spmv_grid = grid_save;
+    {
+        const int keep = P.spmv_variant;
+        for (int v : {1, 2}) {
+            P.spmv_variant = v;
+            char nm[64];
+            snprintf(nm, sizeof(nm), "spmv register-pipelined U=%d", v);
+            time_it(nm, 40.0 * nnz + 24.0 * n, [&] { launch_spmv(s, P.p.p, P.y.p, 1); });
+        }
+        P.spmv_variant = keep;
+    }
     time_it("spmv register-only (legacy)", 40.0 * nnz + 24.0 * n, [&] {
         k_spmv<<<std::min(P.grid, div_up((unsigned)nnz, PCG_BLOCK)), PCG_BLOCK, 0, q>>>((unsigned)nnz, P.row.p, P.col.p, P.val.p, P.cap, P.p.p, P.y.p, P.sc.p, 1);
     });

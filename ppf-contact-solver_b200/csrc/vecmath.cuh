@@ -38,22 +38,44 @@ PPF_HD V3 &operator-=(V3 &a, const V3 &b) { a.x = a.x - b.x; a.y = a.y - b.y; a.
 // NOTE: the accumulator starts from an explicit 0.0f exactly like SMat::dot (smat.hpp:330-335): with FMA
 // contraction the first product is then ROUNDED (fma(a0,b0,0)) and the later ones are fused, which is a
 // different rounding from `a0*b0 + a1*b1 + ...` (where the compiler fuses the first product instead).
+// On the device the contraction is PINNED with explicit intrinsics: nvcc emits mul.f32 / add.f32 without a rounding
+// modifier and ptxas decides per call site what to fuse, so the same source line can round differently in two kernels
+// (round 2: one edge-edge pair in 380 000 of the twist scene flipped on exactly that).  The pinned shapes are the ones
+// the reference's expressions get by default (checked bit for bit on a B200 by oracle/ref_device_check.cu).
 PPF_HD float dot(const V3 &a, const V3 &b) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x)));
+#else
     float acc = 0.0f;
     acc = acc + a.x * b.x;
     acc = acc + a.y * b.y;
     acc = acc + a.z * b.z;
     return acc;
+#endif
+}
+// a x + b y: the first product fused into the sum, the second one rounded (LHS-first contraction of fadd(fmul, fmul))
+PPF_HD float lin2(float a, float x, float b, float y) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, x, __fmul_rn(b, y));
+#else
+    return a * x + b * y;
+#endif
+}
+// (a x + b y) + c z
+PPF_HD float lin3(float a, float x, float b, float y, float c, float z) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(c, z, __fmaf_rn(a, x, __fmul_rn(b, y)));
+#else
+    return a * x + b * y + c * z;
+#endif
 }
 PPF_HD V3 cross(const V3 &a, const V3 &b) {
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-PPF_HD float sqnorm(const V3 &a) {
-    float acc = 0.0f;
-    acc = acc + a.x * a.x;
-    acc = acc + a.y * a.y;
-    acc = acc + a.z * a.z;
-    return acc;
+PPF_HD float sqnorm(const V3 &a) { return dot(a, a); }
+PPF_HD V3 lin2(float a, const V3 &x, float b, const V3 &y) { return mk(lin2(a, x.x, b, y.x), lin2(a, x.y, b, y.y), lin2(a, x.z, b, y.z)); }
+PPF_HD V3 lin3(float a, const V3 &x, float b, const V3 &y, float c, const V3 &z) {
+    return mk(lin3(a, x.x, b, y.x, c, z.x), lin3(a, x.y, b, y.y, c, z.y), lin3(a, x.z, b, y.z, c, z.z));
 }
 PPF_HD float norm(const V3 &a) { return sqrtf(sqnorm(a)); }
 PPF_HD V3 normalized(const V3 &a) {

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [  # include/ppf_abi.h "exported entry points"
     "override_angular_velocity", "init_collision_windows", "refresh_collision_active", "fetch_intersection_records",
     "set_log_path", "ppf_fatal_code", "ppf_fatal_detail", "g_ppf_fatal_code", "g_ppf_fatal_detail", "print_rust",
 ]
-EXT_SYMBOLS = ["ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_detect_pairs", "ppf_b200_measure_spmv",
+EXT_SYMBOLS = ["ppf_b200_selftest_sort", "ppf_b200_get_stats", "ppf_b200_reset_stats", "ppf_b200_fetch_pairs", "ppf_b200_detect_pairs", "ppf_b200_measure_spmv",
                "ppf_b200_dist_unique_id", "ppf_b200_dist_init", "ppf_b200_dist_export", "ppf_b200_dist_connect"]
 
 

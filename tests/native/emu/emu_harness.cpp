@@ -1,6 +1,8 @@
 // emu_harness.cpp -- TEST INFRASTRUCTURE: drives the backend's own upload + assembly code (csrc/abi.cu, csrc/elastic.cu,
 // rewritten for the host by tests/test_kernel_emulation.py, see cuda_runtime.h next to this file) on a scene built by the C++
 // host, and hands the assembled gradient / fixed-matrix blocks / diagonal blocks back for comparison with the oracle.
+#include <algorithm>
+#include <vector>
 #include "backend.hpp"
 #include "../../../ppf-contact-solver_b200/host/ppf_host.hpp"
 #include <cmath>
@@ -128,6 +130,25 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *) {
 float reduce_max_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] > m ? d[i] : m; return m; }
 float reduce_min_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] < m ? d[i] : m; return m; }
 unsigned reduce_sum_u(State &, const unsigned *d, size_t n) { unsigned a = 0; for (size_t i = 0; i < n; ++i) a += d[i]; return a; }
+// prims.cu's sort / unique (device kernels there): the same contracts on the host
+void radix_sort_pairs_u32(State &, unsigned *keys, unsigned *keys_sorted, unsigned *vals, unsigned *vals_sorted, unsigned n, int bits) {
+    std::vector<unsigned> order(n);
+    for (unsigned i = 0; i < n; ++i) order[i] = i;
+    const unsigned mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    std::stable_sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return (keys[a] & mask) < (keys[b] & mask); });
+    for (unsigned i = 0; i < n; ++i) { keys_sorted[i] = keys[order[i]]; vals_sorted[i] = vals[order[i]]; }
+}
+void radix_sort_keys_u64(State &, unsigned long long *keys, unsigned long long *keys_sorted, unsigned n, int bits) {
+    const unsigned long long mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
+    std::vector<unsigned long long> v(keys, keys + n);
+    std::stable_sort(v.begin(), v.end(), [&](unsigned long long a, unsigned long long b) { return (a & mask) < (b & mask); });
+    for (unsigned i = 0; i < n; ++i) keys_sorted[i] = v[i];
+}
+void unique_sorted_u64(State &, const unsigned long long *keys_sorted, unsigned long long *out, unsigned n, unsigned *d_count) {
+    unsigned m = 0;
+    for (unsigned i = 0; i < n; ++i) if (i == 0 || keys_sorted[i] != keys_sorted[i - 1]) out[m++] = keys_sorted[i];
+    *d_count = m;
+}
 } // namespace ppf
 extern "C" __attribute__((weak)) void print_rust(const char *) {}
 
