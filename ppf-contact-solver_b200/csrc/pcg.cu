@@ -73,6 +73,8 @@ struct PackedMatrix {
     DBuf<CgScalars> sc;
     cudaAccessPolicyWindow l2win = {}; // persisting-L2 window over y (and p), also stamped on the graph's kernel nodes
     bool l2win_on = false;
+    unsigned loop_grid = 0;          // k_pcg_loop: co-resident grid (pcg_loop_ready)
+    DBuf<unsigned> loop_bar;         // its grid barrier: [0] arrivals, [1] generation
     int spmv_variant = 0;            // 0 staged (bulk copies through shared memory), 1 / 2 register-pipelined with 1 / 2 blocks per thread
     int evict_first = 1;             // matrix stream loaded with L2::evict_first (PPF_B200_L2_STREAM=0: evict_normal, for A/B timing)
     cudaGraph_t graph = nullptr;
@@ -930,6 +932,307 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The whole iteration loop in ONE cooperative kernel (default; PPF_B200_PCG_GRAPH=1 keeps the three-kernel CUDA graph)
+// ---------------------------------------------------------------------------------------------
+// The three phases of an iteration -- SpMV + dots, r/z update, x/p/y update -- are separated by grid-wide barriers instead
+// of kernel boundaries: no launch ramp and drain per phase (three per iteration, ~270 us each on one GPU, ~75 us on
+// eight), and the host is only asked every LOOP_ITERS iterations.  The LAST CTA to arrive at a barrier runs a leader action
+// before it releases the others: with several GPUs that is where the cross-GPU exchange happens -- the 2-double sums go
+// through the peers' mailboxes (st.release.sys / ld.acquire.sys; one polling thread per GPU instead of one per CTA), and
+// after the direction phase the epoch flags of the pushed rows of p are raised and awaited -- so every rank crosses each
+// barrier of an iteration together with its peers.
+struct LoopArgs {
+    const ChunkDesc *chunks;                 // this rank's chunk list (several ranks) or null: the range [k_first, nnz)
+    unsigned n_desc, k_begin, k_first, nnz, row_lo, row_hi;
+    const unsigned *row, *col;
+    const float *val;
+    size_t plane;
+    float4 *p, *y;                           // written and re-read across phases by different SMs: never through the read-only path
+    float *x, *r, *z;
+    const float *Pinv, *D;
+    unsigned n;
+    CgScalars *sc;
+    unsigned *bar;                           // [0] arrivals, [1] generation
+    int max_iters, evict_first, dist;
+    PeerView pv;
+    const unsigned *push_mask;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until *flag >= e: relaxed polling, then one acquire load that orders the reads that follow; false after 2 s
+__device__ __forceinline__ bool wait_flag_sys(const unsigned long long *flag, unsigned long long e) {
+    if (!spin_until(flag, e)) return false;
+    return ld_acquire_sys_u64(flag) >= e;
+}
+
+// leader action of a barrier: all-reduce of the two doubles at loc over the ranks (peer mailboxes; same bits on every rank)
+__device__ __forceinline__ bool leader_allreduce2(const PeerView &pv, int slot, int parity, volatile double *loc) {
+    const double v0 = loc[0], v1 = loc[1];
+    CommBuf *mine = pv.comm[pv.rank];
+    const unsigned long long e = ++mine->red_epoch[slot];
+    for (int q = 0; q < pv.world; ++q) {
+        Mail *m = &pv.comm[q]->mail[slot][parity][pv.rank];
+        m->v[0] = v0;
+        m->v[1] = v1;
+        st_release_sys_u64(&m->epoch, e); // orders the two stores above before the flag, system scope
+    }
+    bool ok = true;
+    for (int q = 0; q < pv.world; ++q) ok = wait_flag_sys(&mine->mail[slot][parity][q].epoch, e) && ok;
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < pv.world; ++q) {
+        a += ((volatile const double *)mine->mail[slot][parity][q].v)[0];
+        b += ((volatile const double *)mine->mail[slot][parity][q].v)[1];
+    }
+    loc[0] = a; loc[1] = b;
+    return ok;
+}
+
+template <class F> __device__ __forceinline__ void grid_barrier(unsigned *bar, bool sys, F &&leader) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned *gen = bar + 1;
+        const unsigned g = *gen;           // cannot advance before this CTA has arrived
+        if (sys) __threadfence_system(); else __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            if (sys) __threadfence_system(); else __threadfence();
+            leader();
+            *(volatile unsigned *)bar = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) {}
+        }
+        __threadfence();                   // acquire side: also drops this SM's stale L1 lines
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SPMV_T, 4) k_pcg_loop(const LoopArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + size_t(SPMV_STAGES) * SPMV_STAGE_BYTES);
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    CgScalars *sc = A.sc;
+    volatile CgScalars *vsc = A.sc;
+    const unsigned n = A.n;
+    const unsigned c_begin = A.k_begin / SPMV_CHUNK;
+    const unsigned n_list = A.chunks ? A.n_desc : (A.nnz + SPMV_CHUNK - 1) / SPMV_CHUNK - c_begin;
+    auto desc = [&](unsigned ci) { return A.chunks ? A.chunks[ci] : ChunkDesc{(c_begin + ci) * SPMV_CHUNK, A.k_first, A.nnz}; };
+    if (tid == 0) {
+        for (int st = 0; st < SPMV_STAGES; ++st) mbar_init(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned long long pol = l2_stream_policy(A.evict_first);
+    auto fill = [&](int st, unsigned ci) {
+        unsigned *dst = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
+        const size_t base = desc(ci).base;
+        mbar_expect_tx(&full[st], SPMV_STAGE_BYTES);
+        bulk_g2s(dst, A.row + base, SPMV_CHUNK * 4, &full[st], pol);
+        bulk_g2s(dst + SPMV_CHUNK, A.col + base, SPMV_CHUNK * 4, &full[st], pol);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) bulk_g2s(dst + (2 + e) * SPMV_CHUNK, A.val + size_t(e) * A.plane + base, SPMV_CHUNK * 4, &full[st], pol);
+    };
+    float4 *const p = A.p;
+    float4 *const y = A.y;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const bool dist = A.dist != 0;
+    unsigned fills = 0; // stage fills this CTA has consumed so far (mbarrier phase parity), carried across iterations
+
+    for (int it_local = 0; it_local < A.max_iters; ++it_local) {
+        if (vsc->status != ST_RUNNING) break; // uniform over the grid: written before the last barrier
+        const int par = vsc->iter & 1;
+
+        // ================= phase A: y += (L + L^T) p, partial p.Ap and sum|terms| =================
+        if (tid == 0)
+            for (int st = 0; st < SPMV_STAGES; ++st) {
+                const unsigned c = blockIdx.x + unsigned(st) * gridDim.x;
+                if (c < n_list) fill(int((fills + st) % SPMV_STAGES), c);
+            }
+        {
+            float dot = 0.f, absdot = 0.f;
+            for (unsigned chunk = blockIdx.x; chunk < n_list; chunk += gridDim.x, ++fills) {
+                const ChunkDesc cd = desc(chunk);
+                const int st = int(fills % SPMV_STAGES);
+                mbar_wait(&full[st], (fills / SPMV_STAGES) & 1u);
+                const unsigned *sm = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
+                unsigned a[SPMV_U], b[SPMV_U];
+                float h[SPMV_U][9];
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) {
+                    const unsigned j = u * SPMV_T + tid;
+                    a[u] = sm[j];
+                    b[u] = sm[SPMV_CHUNK + j];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) h[u][e] = __uint_as_float(sm[(2 + e) * SPMV_CHUNK + j]);
+                }
+                __syncthreads(); // every thread holds its blocks in registers: the stage can be refilled
+                if (tid == 0) {
+                    const unsigned nc = chunk + unsigned(SPMV_STAGES) * gridDim.x;
+                    if (nc < n_list) fill(st, nc);
+                }
+                const size_t k0 = cd.base;
+                bool on[SPMV_U];
+                float4 pa[SPMV_U], pb[SPMV_U];
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) {
+                    on[u] = k0 + u * SPMV_T + tid < cd.end && k0 + u * SPMV_T + tid >= cd.first;
+                    if (!on[u]) { a[u] = 0xFFFFFFFFu; b[u] = 0; }
+                    pa[u] = on[u] ? p[a[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pb[u] = on[u] ? p[b[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < SPMV_U; ++u) {
+                    const float *hh = h[u];
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+                    const bool own_a = on[u] && a[u] >= A.row_lo && a[u] < A.row_hi;
+                    if (on[u]) {
+                        if (b[u] >= A.row_lo && b[u] < A.row_hi)
+                            red_add_v4(y + b[u], hh[0] * pa[u].x + hh[1] * pa[u].y + hh[2] * pa[u].z, hh[3] * pa[u].x + hh[4] * pa[u].y + hh[5] * pa[u].z,
+                                       hh[6] * pa[u].x + hh[7] * pa[u].y + hh[8] * pa[u].z);
+                        if (own_a) {
+                            s0 = hh[0] * pb[u].x + hh[3] * pb[u].y + hh[6] * pb[u].z;
+                            s1 = hh[1] * pb[u].x + hh[4] * pb[u].y + hh[7] * pb[u].z;
+                            s2 = hh[2] * pb[u].x + hh[5] * pb[u].y + hh[8] * pb[u].z;
+                            const float term = 2.0f * (pa[u].x * s0 + pa[u].y * s1 + pa[u].z * s2);
+                            dot += term;
+                            absdot += fabsf(term);
+                        }
+                    }
+                    const unsigned ra_self = a[u];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned ra = __shfl_up_sync(0xffffffffu, ra_self, o);
+                        const float t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+                        if (lane >= (unsigned)o && ra == ra_self) { s0 += t0; s1 += t1; s2 += t2; }
+                    }
+                    const unsigned next = __shfl_down_sync(0xffffffffu, ra_self, 1);
+                    if (own_a && (lane == 31 || next != ra_self)) red_add_v4(y + ra_self, s0, s1, s2);
+                }
+            }
+            block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
+        }
+        grid_barrier(A.bar, dist, [&] {
+            if (dist && !leader_allreduce2(A.pv, 0, par, vsc->acc[par])) vsc->status = ST_PEER_TIMEOUT;
+        });
+
+        // ================= phase B: r -= alpha y, z = Pinv r, partial r.z and |r|_1 =================
+        int verdict;
+        float pAp;
+        const double rz0_d = vsc->rzerr[par][0];
+        const float alpha = cg_alpha(vsc->acc[par][0], vsc->acc[par][1], rz0_d, verdict, pAp);
+        {
+            float rz = 0.f, err = 0.f;
+            for (unsigned a = A.row_lo + blockIdx.x * blockDim.x + tid; a < A.row_hi; a += 2 * stride) {
+                const unsigned b = a + stride;
+                const bool two = b < A.row_hi;
+                const float4 ya = y[a];
+                float4 ra = ld_planes(A.r, n, a);
+                const Sym6 Ma = ld_sym6(A.Pinv, n, a);
+                float4 yb = make_float4(0.f, 0.f, 0.f, 0.f), rb = yb;
+                Sym6 Mb = {};
+                if (two) { yb = y[b]; rb = ld_planes(A.r, n, b); Mb = ld_sym6(A.Pinv, n, b); }
+                ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
+                st_planes(A.r, n, a, ra);
+                const float4 za = sym6_apply(Ma, ra);
+                st_planes(A.z, n, a, za);
+                rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
+                err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+                if (two) {
+                    rb.x -= alpha * yb.x; rb.y -= alpha * yb.y; rb.z -= alpha * yb.z;
+                    st_planes(A.r, n, b, rb);
+                    const float4 zb = sym6_apply(Mb, rb);
+                    st_planes(A.z, n, b, zb);
+                    rz += rb.x * zb.x + rb.y * zb.y + rb.z * zb.z;
+                    err += fabsf(rb.x) + fabsf(rb.y) + fabsf(rb.z);
+                }
+            }
+            __syncthreads(); // block_accumulate2's shared scratch was used by phase A
+            block_accumulate2(rz, err, &sc->rzerr[par ^ 1][0], &sc->rzerr[par ^ 1][1]);
+        }
+        grid_barrier(A.bar, dist, [&] {
+            if (verdict) { vsc->breakdown = verdict; vsc->break_val = pAp; }
+            vsc->acc[par ^ 1][0] = 0.0; // accumulators of the NEXT iteration (direction phase + SpMV)
+            vsc->acc[par ^ 1][1] = 0.0;
+            if (dist && !leader_allreduce2(A.pv, 1, par ^ 1, vsc->rzerr[par ^ 1])) vsc->status = ST_PEER_TIMEOUT;
+        });
+
+        // ================= phase C: x += alpha p, p = z + beta p, y = D p, diagonal share of the next p.Ap =================
+        const float rz0 = (float)rz0_d, rz1 = (float)vsc->rzerr[par ^ 1][0];
+        const double err1 = vsc->rzerr[par ^ 1][1];
+        const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
+        {
+            float dot = 0.f, absdot = 0.f;
+            auto finish_row = [&](unsigned a, const float4 za, float4 pa, float4 xa, const Sym6 &Da) {
+                xa.x += alpha * pa.x; xa.y += alpha * pa.y; xa.z += alpha * pa.z;
+                st_planes(A.x, n, a, xa);
+                pa.x = za.x + beta * pa.x; pa.y = za.y + beta * pa.y; pa.z = za.z + beta * pa.z;
+                p[a] = pa;
+                if (A.push_mask) { // ranks that own a block partner of row a read p[a]: store it into their arrays over NVLink
+                    unsigned m = A.push_mask[a];
+                    while (m) {
+                        const int q = __ffs(m) - 1;
+                        m &= m - 1;
+                        A.pv.p[q][a] = pa;
+                    }
+                }
+                const float4 v = sym6_apply(Da, pa);
+                y[a] = v;
+                const float term = pa.x * v.x + pa.y * v.y + pa.z * v.z;
+                dot += term;
+                absdot += fabsf(term);
+            };
+            for (unsigned a = A.row_lo + blockIdx.x * blockDim.x + tid; a < A.row_hi; a += 2 * stride) {
+                const unsigned b = a + stride;
+                const bool two = b < A.row_hi;
+                const float4 za = ld_planes(A.z, n, a), pa = p[a], xa = ld_planes(A.x, n, a);
+                const Sym6 Da = ld_sym6(A.D, n, a);
+                float4 zb = make_float4(0.f, 0.f, 0.f, 0.f), pb = zb, xb = zb;
+                Sym6 Db = {};
+                if (two) { zb = ld_planes(A.z, n, b); pb = p[b]; xb = ld_planes(A.x, n, b); Db = ld_sym6(A.D, n, b); }
+                finish_row(a, za, pa, xa, Da);
+                if (two) finish_row(b, zb, pb, xb, Db);
+            }
+            __syncthreads();
+            block_accumulate2(dot, absdot, &sc->acc[par ^ 1][0], &sc->acc[par ^ 1][1]);
+        }
+        grid_barrier(A.bar, dist, [&] { // scalar tail of the iteration, then (several ranks) the flags of the pushed rows
+            const int it = vsc->iter + 1;
+            const double reresid = err1 / vsc->err0;
+            vsc->last_resid = (float)reresid;
+            int st = vsc->status; // ST_RUNNING unless a peer timed out above
+            if (st == ST_RUNNING) {
+                if (reresid < (double)vsc->tol) st = ST_CONVERGED;
+                else if (vsc->breakdown == 1) st = ST_TRUNCATED;
+                else if (vsc->breakdown == 2) st = ST_FATAL_PAP;
+                else if (!(rz0 > 0.0f)) st = ST_FATAL_RZ;
+                else if (!isfinite(reresid)) st = ST_NONFINITE;
+                else if (it >= vsc->max_iter) st = ST_CAP;
+            }
+            vsc->rzerr[par][0] = 0.0; // slots the NEXT iteration's update phase accumulates into
+            vsc->rzerr[par][1] = 0.0;
+            if (dist && A.push_mask && st == ST_RUNNING) { // every rank reaches the same verdict: all exchange or none does
+                CommBuf *mine = A.pv.comm[A.pv.rank];
+                const unsigned long long e = ++mine->halo_epoch;
+                for (int q = 0; q < A.pv.world; ++q)
+                    if (q != A.pv.rank) st_release_sys_u64(&A.pv.comm[q]->halo_flag[A.pv.rank], e);
+                for (int q = 0; q < A.pv.world; ++q)
+                    if (q != A.pv.rank && !wait_flag_sys(&mine->halo_flag[q], e)) st = ST_PEER_TIMEOUT;
+            }
+            vsc->iter = it;
+            vsc->status = st;
+        });
+    }
+}
+
 // setup: r = b, x = x0 (seed), p = x0 (SpMV input), y = D x0
 __global__ void k_load(unsigned n, const float *__restrict__ force, const float *__restrict__ dx, float *__restrict__ r, float *__restrict__ x,
                        float4 *__restrict__ p, float4 *__restrict__ y, const float *__restrict__ D) {
@@ -1231,6 +1534,28 @@ static void pcg_tune(State &s) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
+// k_pcg_loop needs every CTA of its grid resident at once: size the grid from the occupancy the driver reports
+static bool pcg_loop_ready() {
+    static int state = -1;
+    if (state >= 0) return state == 1;
+    state = 0;
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!coop) return false;
+    if (cudaFuncSetAttribute(k_pcg_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_SMEM) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_loop, SPMV_T, SPMV_SMEM) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
+    per_sm = std::min(per_sm, 4);
+    if (const char *e = getenv("PPF_B200_LOOP_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+    P.loop_grid = (unsigned)(sms * per_sm);
+    P.loop_bar.reserve(4);
+    CUDA_OK(cudaMemset(P.loop_bar.p, 0, 4 * sizeof(unsigned)));
+    log_info("pcg: iteration loop in one cooperative kernel, %u CTAs (%d per SM)", P.loop_grid, per_sm);
+    state = 1;
+    return true;
+}
+
 float4 *pcg_search_direction_buffer(State &s) {
     if (!P.ready) pcg_init(s);
     return P.p.p;
@@ -1309,11 +1634,30 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     const unsigned nnz = P.nnz_f + P.nnz_d;
     const unsigned long long part_sig = (unsigned long long)R.kd_first ^ ((unsigned long long)R.kd_end << 20) ^ ((unsigned long long)R.n_foreign << 40) ^
                                         (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7);
+    // ---- default: the whole loop in one cooperative kernel (k_pcg_loop); the graph of three kernels per iteration is kept
+    //      for the NCCL fallback of several ranks and behind PPF_B200_PCG_GRAPH=1 for A/B timing ----
+    static const bool force_graph = getenv("PPF_B200_PCG_GRAPH") != nullptr;
+    const bool p2p_now = g_dist.on() && R.push;
+    const bool use_loop = !force_graph && pcg_loop_ready() && (!g_dist.on() || p2p_now) && nnz > 0;
+    LoopArgs loop_args = {};
+    if (use_loop) {
+        LoopArgs &A = loop_args;
+        if (g_dist.on()) { A.chunks = P.chunks.p; A.n_desc = R.n_chunks; }
+        else { A.chunks = nullptr; A.k_first = R.kf_first; A.k_begin = R.kf_first / SPMV_CHUNK * SPMV_CHUNK; A.nnz = R.kf_end; }
+        A.row_lo = R.lo; A.row_hi = R.hi;
+        A.row = P.row.p; A.col = P.col.p; A.val = P.val.p; A.plane = P.cap;
+        A.p = P.p.p; A.y = P.y.p; A.x = P.x.p; A.r = P.r.p; A.z = P.z.p; A.Pinv = P.Pinv.p; A.D = P.D.p; A.n = n;
+        A.sc = P.sc.p; A.bar = P.loop_bar.p;
+        A.max_iters = n >= 500000u ? 64 : 32;
+        A.evict_first = P.evict_first; A.dist = p2p_now ? 1 : 0;
+        A.pv = dist_peers(); A.push_mask = p2p_now ? P.mask.p : nullptr;
+    }
+    if (!use_loop)
     if (P.exec && (P.graph_iters != ITER_PER_GRAPH || P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p || P.graph_part != part_sig)) { // kernel parameters changed: re-capture
         cudaGraphExecDestroy(P.exec); cudaGraphDestroy(P.graph);
         P.exec = nullptr; P.graph = nullptr;
     }
-    if (!P.exec) {
+    if (!use_loop && !P.exec) {
         CUDA_OK(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal));
         for (int k = 0; k < ITER_PER_GRAPH; ++k) issue_iteration(s, k & 1);
         CUDA_OK(cudaStreamEndCapture(q, &P.graph));
@@ -1342,8 +1686,15 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     int status = ST_RUNNING, iter = 0;
     float resid = 0.f;
     while (status == ST_RUNNING) {
+        if (use_loop) {
+            LoopArgs A = loop_args;
+            void *params[] = {&A};
+            CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_pcg_loop, dim3(P.loop_grid), dim3(SPMV_T), params, SPMV_SMEM, q));
+            LAUNCH_COUNT(1);
+        } else {
         CUDA_OK(cudaGraphLaunch(P.exec, q));
         LAUNCH_COUNT(3 * ITER_PER_GRAPH);
+        }
         CUDA_OK(cudaMemcpyAsync(P.h_status, &P.sc.p->iter, 2 * sizeof(int), cudaMemcpyDeviceToHost, q));
         CUDA_OK(cudaMemcpyAsync(P.h_status + 2, &P.sc.p->last_resid, sizeof(float), cudaMemcpyDeviceToHost, q));
         CUDA_OK(cudaStreamSynchronize(q));
