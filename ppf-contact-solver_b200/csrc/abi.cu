@@ -400,8 +400,8 @@ void upload_dataset(State &s) {
         CUDA_OK(cudaStreamSynchronize(q));
     }
     s.diag.reserve(size_t(9) * nv); s.force.reserve(size_t(3) * nv); s.dx.reserve(size_t(3) * nv);
-    s.counters.reserve(64); s.scalars.reserve(64);
-    s.counters.zero(64, q); s.scalars.zero(64, q);
+    s.counters.reserve(160); s.scalars.reserve(64);
+    s.counters.zero(160, q); s.scalars.zero(64, q);
     if (s.cm_nv) { // trees of the static collision mesh, built once (they use the bounds words of `counters`)
         bvh_build_static(s, s.cm_bvh_face, 0, s.cm_nf, s.cm_x.p, s.cm_face.p, s.cm_edge.p, s.cm_fcp.p);
         bvh_build_static(s, s.cm_bvh_edge, 1, s.cm_ne, s.cm_x.p, s.cm_face.p, s.cm_edge.p, s.cm_ecp.p);

@@ -22,6 +22,7 @@
 // Pair acceptance is independent of the candidate superset, so the accepted sets equal the
 // reference's for the same positions.
 #include "bvh.cuh"
+#include "dist.hpp"
 #include "math_accd.cuh"
 #include "math_collider.cuh"
 #include "math_cmesh.cuh"
@@ -77,8 +78,8 @@ __device__ __forceinline__ bool cw_vertex(const unsigned char *a, unsigned v) { 
 __device__ __forceinline__ bool cw_edge(const unsigned char *a, const uint2 e) { return !a || a[e.x] || a[e.y]; }
 __device__ __forceinline__ bool cw_face(const unsigned char *a, const uint4 f) { return !a || a[f.x] || a[f.y] || a[f.z]; }
 
-__global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned q_lo, unsigned nq) { // Morton-ordered queries [q_lo, nq)
+    const unsigned t = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq) return;
     const unsigned v = A.vert.prim[t];
     if (!cw_vertex(A.active, v)) return;
@@ -131,8 +132,8 @@ __global__ void __launch_bounds__(128) k_bp_vertex(BpArgs A, unsigned nq) {
     if (!ok) atomicExch(A.error, 1u);
 }
 
-__global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned nq) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned q_lo, unsigned nq) {
+    const unsigned t = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq) return;
     const unsigned e = A.edge.prim[t];
     const uint2 ev = A.edges[e];
@@ -171,6 +172,12 @@ __global__ void __launch_bounds__(128) k_bp_edge(BpArgs A, unsigned nq) {
     if (!ok) atomicExch(A.error, 1u);
 }
 
+// several ranks: are contact detection and the line search sharded (default) or replicated (PPF_B200_DIST_CONTACT=0)?
+static bool contact_sharded() {
+    static const bool off = getenv("PPF_B200_DIST_CONTACT") && getenv("PPF_B200_DIST_CONTACT")[0] == '0';
+    return g_dist.on() && !off;
+}
+
 // runs the broad phase; grows candidate buffers and retries on overflow
 static void broad_phase(State &s, const float4 *x0, const float4 *x1, bool sweep, float sweep_t) {
     cudaStream_t q = s.stream;
@@ -187,8 +194,15 @@ static void broad_phase(State &s, const float4 *x0, const float4 *x1, bool sweep
         for (int k = 0; k < 4; ++k) { A.out[k] = s.cand[k].pairs.p; A.cap[k] = (unsigned)std::min<size_t>(s.cand[k].pairs.cap, 0xFFFFFFF0u); }
         A.cnt = cnt; A.error = cnt + 4;
         A.active = s.has_cw ? s.cw_active.p : nullptr;
-        if (s.nsv) k_bp_vertex<<<div_up(s.nsv, 128), 128, 0, q>>>(A, s.nsv);
-        if (s.ne) k_bp_edge<<<div_up(s.ne, 128), 128, 0, q>>>(A, s.ne);
+        // several ranks: this rank's slice of the query elements (dist.hpp); the candidate lists are then this rank's share
+        unsigned v_lo = 0, v_hi = s.nsv, e_lo = 0, e_hi = s.ne;
+        if (contact_sharded()) {
+            const unsigned long long r = (unsigned long long)g_dist.rank, w = (unsigned long long)g_dist.world;
+            v_lo = (unsigned)(s.nsv * r / w); v_hi = (unsigned)(s.nsv * (r + 1) / w);
+            e_lo = (unsigned)(s.ne * r / w); e_hi = (unsigned)(s.ne * (r + 1) / w);
+        }
+        if (v_hi > v_lo) k_bp_vertex<<<div_up(v_hi - v_lo, 128), 128, 0, q>>>(A, v_lo, v_hi);
+        if (e_hi > e_lo) k_bp_edge<<<div_up(e_hi - e_lo, 128), 128, 0, q>>>(A, e_lo, e_hi);
         LAUNCH_COUNT(2);
         unsigned h[5];
         CUDA_OK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, q));
@@ -600,6 +614,38 @@ static unsigned detect_contacts(State &s, const PpfParamSet &prm, unsigned hc[4]
     return total;
 }
 
+// Several ranks: every rank accepted the pairs of its own query slice; all-gather the four lists so that every rank assembles
+// the whole contact set (the union over the ranks IS the single-GPU set: each pair has exactly one query side).  hc: in = this
+// rank's counts, out = the totals.  Rank-major order; the lists are unordered anyway (slots are handed out by atomics).
+static DBuf<uint2> g_pair_stage;
+static void gather_pair_lists(State &s, unsigned hc[4]) {
+    cudaStream_t q = s.stream;
+    const unsigned W = (unsigned)g_dist.world;
+    unsigned *d_cnt = s.counters.p + 64; // [64 .. 64 + 4 W): counts of every rank
+    CUDA_OK(cudaMemcpyAsync(d_cnt + 4 * g_dist.rank, hc, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, q));
+    dist_allgather(d_cnt + 4 * g_dist.rank, d_cnt, 4 * sizeof(unsigned), q);
+    std::vector<unsigned> all(4 * W);
+    CUDA_OK(cudaMemcpyAsync(all.data(), d_cnt, sizeof(unsigned) * 4 * W, cudaMemcpyDeviceToHost, q));
+    CUDA_OK(cudaStreamSynchronize(q));
+    for (int k = 0; k < 4; ++k) {
+        unsigned mx = 0;
+        unsigned long long tot = 0;
+        for (unsigned r = 0; r < W; ++r) { mx = std::max(mx, all[4 * r + k]); tot += all[4 * r + k]; }
+        if (tot > 0xFFFFFFF0ull) fatal(4, "contact pair list of kind %d exceeds 2^32 entries over the ranks", k);
+        hc[k] = (unsigned)tot;
+        if (!mx) continue;
+        s.pairs[k].pairs.reserve_keep(std::max<size_t>(mx, tot), q); // send buffer: at least the largest share (the tail is never read as pairs)
+        g_pair_stage.reserve(size_t(mx) * W);
+        dist_allgather(s.pairs[k].pairs.p, g_pair_stage.p, sizeof(uint2) * size_t(mx), q);
+        size_t at = 0;
+        for (unsigned r = 0; r < W; ++r) {
+            const unsigned c = all[4 * r + k];
+            if (c) CUDA_OK(cudaMemcpyAsync(s.pairs[k].pairs.p + at, g_pair_stage.p + size_t(mx) * r, sizeof(uint2) * c, cudaMemcpyDeviceToDevice, q));
+            at += c;
+        }
+    }
+}
+
 static unsigned detect_contacts_impl(State &s, const PpfParamSet &prm, unsigned hc[4], bool allow_reuse) {
     cudaStream_t q = s.stream;
     // The candidate lists of the last line-search sweep x_old -> x_old + t_max*(x_new - x_old) cover every
@@ -630,6 +676,7 @@ static unsigned detect_contacts_impl(State &s, const PpfParamSet &prm, unsigned 
     }
     CUDA_OK(cudaMemcpyAsync(hc, acc_cnt, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, q));
     CUDA_OK(cudaStreamSynchronize(q));
+    if (contact_sharded()) gather_pair_lists(s, hc);
     unsigned total = 0;
     for (int k = 0; k < 4; ++k) { s.pairs[k].count = hc[k]; s.last_num_contact[k] = hc[k]; total += hc[k]; }
     return total;
@@ -849,6 +896,10 @@ float contact_line_search(State &s, const float4 *x0, const float4 *x1, const Pp
     if (s.cand[2].count) k_ccd_pp<<<div_up(s.cand[2].count, 128), 128, 0, q>>>(c, s.cand[2].pairs.p, s.cand[2].count);
     if (s.cand[3].count) k_ccd_ee<<<div_up(s.cand[3].count, 128), 128, 0, q>>>(c, s.cand[3].pairs.p, s.cand[3].count);
     LAUNCH_COUNT(3);
+    if (contact_sharded()) { // every rank swept its own slice of the queries: the step fraction is the minimum over the ranks
+        dist_allreduce_u32(w, 1, false, q);     // positive floats order like unsigned ints
+        dist_allreduce_u32(w + 1, 1, true, q);  // "starts overlapping" flag
+    }
     unsigned h[5];
     CUDA_OK(cudaMemcpyAsync(h, w, sizeof(h), cudaMemcpyDeviceToHost, q));
     CUDA_OK(cudaStreamSynchronize(q));

@@ -51,6 +51,10 @@ void dist_allreduce_sum_f64(double *buf, size_t count, cudaStream_t q) {
     if (!g_dist.on()) return;
     check(N.AllReduce(buf, buf, count, ncclDouble, ncclSum, N.comm, q), "all-reduce");
 }
+void dist_allreduce_u32(unsigned *buf, size_t count, bool take_max, cudaStream_t q) {
+    if (!g_dist.on()) return;
+    check(N.AllReduce(buf, buf, count, ncclUint32, take_max ? ncclMax : ncclMin, N.comm, q), "all-reduce (u32)");
+}
 void dist_allgather(const void *send, void *recv, size_t bytes_per_rank, cudaStream_t q) {
     if (!g_dist.on()) return;
     check(N.AllGather(send, recv, bytes_per_rank, ncclChar, N.comm, q), "all-gather");

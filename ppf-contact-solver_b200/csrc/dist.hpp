@@ -1,10 +1,12 @@
 // dist.hpp -- multi-GPU plumbing of the backend: one process per GPU, NCCL over NVLink/NVSwitch.
 //
-// The reference is single-GPU; this is new.  Only the PCG solve is sharded (it is >90 %
-// of the headline step): every rank keeps the full scene and runs the cheap phases redundantly --
-// their only inputs are the positions, which stay bitwise identical on all ranks because the solved
-// step dx is all-gathered -- while the rows of the linear system are split into contiguous ranges
-// (pcg.cu).  Exchanges per PCG iteration: the rows of the search direction p that other ranks read
+// The reference is single-GPU; this is new.  Every rank keeps the full scene; positions stay bitwise
+// identical on all ranks because the solved step dx is all-gathered.  Sharded: (1) the PCG solve -- the rows of the linear
+// system are split into contiguous ranges (pcg.cu); (2) contact detection and the CCD line search -- every rank issues the
+// broad-phase queries of ITS slice of the Morton-ordered query elements only (each pair has exactly one query side:
+// vertex for point-face / point-edge / point-point, the lower edge for edge-edge), runs narrow phase / ACCD on its own
+// candidates, then the accepted pair lists are all-gathered (their union is the single-GPU set) and the step fraction is
+// min-reduced (contact.cu).  The remaining phases (BVH build / refit, elastic assembly, contact fill) run redundantly.  Exchanges per PCG iteration: the rows of the search direction p that other ranks read
 // (known from the block pattern) and two 2-double sums (p.Ap | sum|terms|,  r.z | |r|_1).  All of them
 // run on the backend stream inside the iteration CUDA graph.
 //
@@ -36,6 +38,7 @@ struct CommBuf {
     unsigned long long halo_flag[PPF_MAX_RANKS]; // [q]: epoch of the last push of p rows received from rank q
     unsigned long long red_epoch[2];     // local counters (never reset, identical on all ranks by construction)
     unsigned long long halo_epoch;
+    unsigned long long sum_ready[2];     // local: epoch of the last all-rank sum that CTA 0 of the consuming kernel has formed (pcg.cu)
 };
 struct PeerView {
     CommBuf *comm[PPF_MAX_RANKS];        // comm[r]: rank r's mailbox buffer mapped into this process (own buffer at [rank])
@@ -46,5 +49,6 @@ const PeerView &dist_peers();
 
 void dist_allreduce_sum_f64(double *buf, size_t count, cudaStream_t q);                          // in place
 void dist_allgather(const void *send, void *recv, size_t bytes_per_rank, cudaStream_t q);        // recv = world * bytes_per_rank
+void dist_allreduce_u32(unsigned *buf, size_t count, bool take_max, cudaStream_t q);             // in place, min or max
 
 } // namespace ppf

@@ -600,6 +600,28 @@ __device__ __forceinline__ bool spin_until(const unsigned long long *flag, unsig
 // The LAST CTA of the producing kernel publishes this rank's partial to every rank's mailbox; every CTA of the
 // consuming kernel waits for all mailboxes and adds them in rank order -- the same bits on every rank, no extra
 // launch.  Mailboxes are double-buffered by iteration parity; a rank can be at most one reduction ahead of another.
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until *flag >= e: relaxed polling, then one acquire load that orders the reads that follow; false after 2 s
+__device__ __forceinline__ bool wait_flag_sys(const unsigned long long *flag, unsigned long long e) {
+    if (!spin_until(flag, e)) return false;
+    return ld_acquire_sys_u64(flag) >= e;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void publish_partial(const PeerView &pv, CgScalars *sc, int slot, int parity) {
     volatile double *loc = slot == 0 ? sc->acc[parity] : sc->rzerr[parity];
     const double v0 = loc[0], v1 = loc[1];
@@ -607,27 +629,45 @@ __device__ __forceinline__ void publish_partial(const PeerView &pv, CgScalars *s
     const unsigned long long e = ++mine->red_epoch[slot];
     for (int q = 0; q < pv.world; ++q) {
         Mail *m = &pv.comm[q]->mail[slot][parity][pv.rank];
-        ((volatile double *)m->v)[0] = v0;
-        ((volatile double *)m->v)[1] = v1;
+        m->v[0] = v0;
+        m->v[1] = v1;
+        st_release_sys_u64(&m->epoch, e); // release at system scope: the two stores above are visible before the flag
     }
-    __threadfence_system();
-    for (int q = 0; q < pv.world; ++q) *(volatile unsigned long long *)&pv.comm[q]->mail[slot][parity][pv.rank].epoch = e;
 }
+// Sum of all ranks' partials, the same bits on every rank.  CTA 0 alone talks to the mailboxes (relaxed polling, then one
+// ld.acquire.sys per mailbox -- the acquire side of the peers' st.release.sys), adds them in rank order, stores the sum at dst
+// and releases it to the other CTAs of this kernel through a device-scope flag; those only ever issue device-scope acquires.
+// (Every CTA of the grid is resident -- the vector kernels run 4 CTAs per SM -- so waiting for CTA 0 cannot deadlock.)
 // one thread per CTA; false = a peer did not answer (ST_PEER_TIMEOUT)
-__device__ __forceinline__ bool gather_sum(const PeerView &pv, int slot, int parity, double out[2]) {
-    const CommBuf *mine = pv.comm[pv.rank];
+__device__ __forceinline__ bool gather_sum(const PeerView &pv, int slot, int parity, double out[2], volatile double *dst) {
+    CommBuf *mine = pv.comm[pv.rank];
     const unsigned long long e = *(volatile const unsigned long long *)&mine->red_epoch[slot];
     bool ok = true;
-    for (int q = 0; q < pv.world; ++q) ok = spin_until(&mine->mail[slot][parity][q].epoch, e) && ok;
-    // no fence here: the writer ordered data before flag with a system fence, the mailbox lives in THIS device's
-    // memory and is read with volatile (L1-bypassing) loads.  A system fence per CTA cost ~40 us per kernel.
-    double a = 0.0, b = 0.0;
-    for (int q = 0; q < pv.world; ++q) {
-        a += ((volatile const double *)mine->mail[slot][parity][q].v)[0];
-        b += ((volatile const double *)mine->mail[slot][parity][q].v)[1];
+    if (blockIdx.x == 0) {
+        for (int q = 0; q < pv.world; ++q) ok = wait_flag_sys(&mine->mail[slot][parity][q].epoch, e) && ok;
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < pv.world; ++q) {
+            a += ((volatile const double *)mine->mail[slot][parity][q].v)[0];
+            b += ((volatile const double *)mine->mail[slot][parity][q].v)[1];
+        }
+        dst[0] = a; dst[1] = b;
+        st_release_gpu_u64(&mine->sum_ready[slot], ok ? e : ~0ull);
+        out[0] = a; out[1] = b;
+        return ok;
     }
-    out[0] = a; out[1] = b;
-    return ok;
+    unsigned long long seen;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while ((seen = ld_acquire_gpu_u64(&mine->sum_ready[slot])) < e) {
+        if ((++spins & 0xFFFFu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            else if (now - t0 > 4000000000ull) return false;
+        }
+    }
+    out[0] = dst[0]; out[1] = dst[1];
+    return seen != ~0ull;
 }
 
 // With a chunk list (several ranks) the launch walks the listed chunks instead of one contiguous range: this rank's
@@ -782,8 +822,8 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
     __shared__ int s_ok;
     if (fused) { // p.Ap | sum|terms| of all ranks, from the mailboxes the SpMV kernels filled
         if (threadIdx.x == 0) {
-            s_ok = gather_sum(pv, 0, par, s_sum) ? 1 : 0;
-            if (blockIdx.x == 0) { sc->acc[par][0] = s_sum[0]; sc->acc[par][1] = s_sum[1]; if (!s_ok) sc->status = ST_PEER_TIMEOUT; }
+            s_ok = gather_sum(pv, 0, par, s_sum, sc->acc[par]) ? 1 : 0;
+            if (blockIdx.x == 0 && !s_ok) sc->status = ST_PEER_TIMEOUT;
         }
         __syncthreads();
     } else if (threadIdx.x == 0) { s_sum[0] = sc->acc[par][0]; s_sum[1] = sc->acc[par][1]; }
@@ -847,8 +887,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
     __shared__ int s_ok;
     if (push_mask) { // r.z | |r|_1 of all ranks, from the mailboxes k_update filled (fused sums come with the peer path)
         if (threadIdx.x == 0) {
-            s_ok = gather_sum(pv, 1, par ^ 1, s_rz) ? 1 : 0;
-            if (blockIdx.x == 0) { sc->rzerr[par ^ 1][0] = s_rz[0]; sc->rzerr[par ^ 1][1] = s_rz[1]; }
+            s_ok = gather_sum(pv, 1, par ^ 1, s_rz, sc->rzerr[par ^ 1]) ? 1 : 0;
         }
     } else if (threadIdx.x == 0) { s_rz[0] = sc->rzerr[par ^ 1][0]; s_rz[1] = sc->rzerr[par ^ 1][1]; s_ok = 1; }
     __syncthreads();
@@ -919,11 +958,11 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
         if (push_mask && st == ST_RUNNING) { // every rank reaches the same verdict, so either all exchange or none does
             CommBuf *mine = pv.comm[pv.rank];
             const unsigned long long e = ++mine->halo_epoch;
-            __threadfence_system();
+            __threadfence_system(); // the pushing threads fenced their peer stores and arrived at done_counter before this point
             for (int q = 0; q < pv.world; ++q)
-                if (q != pv.rank) *(volatile unsigned long long *)&pv.comm[q]->halo_flag[pv.rank] = e;
+                if (q != pv.rank) st_release_sys_u64(&pv.comm[q]->halo_flag[pv.rank], e);
             for (int q = 0; q < pv.world; ++q)
-                if (q != pv.rank && !spin_until(&mine->halo_flag[q], e)) st = ST_PEER_TIMEOUT;
+                if (q != pv.rank && !wait_flag_sys(&mine->halo_flag[q], e)) st = ST_PEER_TIMEOUT;
             // the pushed rows are read by the NEXT kernel (a launch boundary orders them after this wait)
         }
         sc->iter = it;
@@ -933,7 +972,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// The whole iteration loop in ONE cooperative kernel (default; PPF_B200_PCG_GRAPH=1 keeps the three-kernel CUDA graph)
+// The whole iteration loop in ONE cooperative kernel (opt-in: PPF_B200_PCG_LOOP=1; the three-kernel CUDA graph is the default)
 // ---------------------------------------------------------------------------------------------
 // The three phases of an iteration -- SpMV + dots, r/z update, x/p/y update -- are separated by grid-wide barriers instead
 // of kernel boundaries: no launch ramp and drain per phase (three per iteration, ~270 us each on one GPU, ~75 us on
@@ -958,20 +997,6 @@ struct LoopArgs {
     PeerView pv;
     const unsigned *push_mask;
 };
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// wait until *flag >= e: relaxed polling, then one acquire load that orders the reads that follow; false after 2 s
-__device__ __forceinline__ bool wait_flag_sys(const unsigned long long *flag, unsigned long long e) {
-    if (!spin_until(flag, e)) return false;
-    return ld_acquire_sys_u64(flag) >= e;
-}
 
 // leader action of a barrier: all-reduce of the two doubles at loc over the ranks (peer mailboxes; same bits on every rank)
 __device__ __forceinline__ bool leader_allreduce2(const PeerView &pv, int slot, int parity, volatile double *loc) {
@@ -1634,11 +1659,13 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     const unsigned nnz = P.nnz_f + P.nnz_d;
     const unsigned long long part_sig = (unsigned long long)R.kd_first ^ ((unsigned long long)R.kd_end << 20) ^ ((unsigned long long)R.n_foreign << 40) ^
                                         (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7);
-    // ---- default: the whole loop in one cooperative kernel (k_pcg_loop); the graph of three kernels per iteration is kept
-    //      for the NCCL fallback of several ranks and behind PPF_B200_PCG_GRAPH=1 for A/B timing ----
-    static const bool force_graph = getenv("PPF_B200_PCG_GRAPH") != nullptr;
+    // ---- PPF_B200_PCG_LOOP=1: the whole loop in one cooperative kernel (k_pcg_loop) instead of the graph of three kernels per
+    //      iteration.  Measured on a B200 (profiles/r02_pcg_loop_vs_graph.json): correct, but SLOWER -- a software barrier over
+    //      592 CTAs costs more than a kernel boundary inside a CUDA graph (large-twist 274.8 vs 264.9 us per iteration, twist
+    //      42.4 vs 29.6 us) -- so the graph stays the default and the kernel is kept as a measured negative result ----
+    static const bool want_loop = getenv("PPF_B200_PCG_LOOP") != nullptr;
     const bool p2p_now = g_dist.on() && R.push;
-    const bool use_loop = !force_graph && pcg_loop_ready() && (!g_dist.on() || p2p_now) && nnz > 0;
+    const bool use_loop = want_loop && pcg_loop_ready() && (!g_dist.on() || p2p_now) && nnz > 0;
     LoopArgs loop_args = {};
     if (use_loop) {
         LoopArgs &A = loop_args;

@@ -264,7 +264,7 @@ extern "C" __attribute__((visibility("default"))) int ppf_b200_selftest_sort(uns
     using namespace ppf;
     State &s = g;
     if (!s.stream) CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    if (!s.counters.p) s.counters.reserve(64);
+    if (!s.counters.p) s.counters.reserve(160);
     unsigned long long x = 0x9E3779B97F4A7C15ull ^ seed;
     auto next = [&] { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
     const unsigned mask32 = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);

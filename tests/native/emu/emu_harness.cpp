@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <vector>
 #include "backend.hpp"
+#include "dist.hpp"
 #include "../../../ppf-contact-solver_b200/host/ppf_host.hpp"
 #include <cmath>
 #include <cstdarg>
@@ -130,6 +131,10 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *) {
 float reduce_max_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] > m ? d[i] : m; return m; }
 float reduce_min_f(State &, const float *d, size_t n, float init) { float m = init; for (size_t i = 0; i < n; ++i) m = d[i] < m ? d[i] : m; return m; }
 unsigned reduce_sum_u(State &, const unsigned *d, size_t n) { unsigned a = 0; for (size_t i = 0; i < n; ++i) a += d[i]; return a; }
+// dist.cu (NCCL plumbing) is not part of the emulated build: one rank, the collectives are never reached
+Dist g_dist;
+void dist_allgather(const void *, void *, size_t, cudaStream_t) {}
+void dist_allreduce_u32(unsigned *, size_t, bool, cudaStream_t) {}
 // prims.cu's sort / unique (device kernels there): the same contracts on the host
 void radix_sort_pairs_u32(State &, unsigned *keys, unsigned *keys_sorted, unsigned *vals, unsigned *vals_sorted, unsigned n, int bits) {
     std::vector<unsigned> order(n);
