@@ -14,9 +14,9 @@ from conftest import REPO
 pytestmark = pytest.mark.gpu
 
 
-def _launch(world, scene, n, steps, env=None):
+def _launch(world, scene, n, steps, env=None, state=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(REPO, "scripts", "dist_check.py"), scene, str(n), str(steps)]
+           "--master-port", "29517", os.path.join(REPO, "scripts", "dist_check.py"), scene, str(n), str(steps)] + ([state] if state else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
@@ -38,3 +38,25 @@ def test_two_gpu_sharded_pcg_matches_single_gpu(built):
         # run is asserted inside scripts/dist_check.py
         d = np.abs(x1 - x2).max(axis=1)
         assert float(np.median(d)) < 5e-4 and float(d.max()) < 1e-2
+
+
+def test_two_gpu_sharded_contact_detection_gives_the_single_gpu_pair_sets(built):
+    """Contact detection and the line search are sharded by query slice (csrc/contact.cu): at a contact-rich golden state the
+    all-gathered sorted pair lists of the 2-GPU run are, bit for bit, the single-GPU lists (dist_check.py also asserts that both
+    ranks hold the same lists), and the step that follows takes the same number of Newton iterations with the same line-search
+    cuts up to the usual tie noise."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    state = os.path.join(REPO, "tests", "golden", "fast_twist_n24", "state_00080.bin")
+    one, x1 = _launch(1, "fast-twist", 24, 2, state=state)
+    p1 = dict(np.load("/tmp/dist_check_pairs_w1.npz"))
+    two, x2 = _launch(2, "fast-twist", 24, 2, state=state)
+    p2 = dict(np.load("/tmp/dist_check_pairs_w2.npz"))
+    assert int(p1["total"][0]) == int(p2["total"][0]) > 1000
+    for k in range(4):
+        assert np.array_equal(p1["k%d" % k], p2["k%d" % k]), "pair lists of kind %d differ" % k
+    assert one["num_contact_tail"][-1] > 0 and abs(two["n_newton"] - one["n_newton"]) <= 1
+    d = np.abs(x1 - x2).max(axis=1)
+    assert float(np.median(d)) < 5e-4 and float(d.max()) < 1e-2
