@@ -46,6 +46,21 @@ void log_info(const char *fmt, ...) {
     exit(1); // never abort(): the host's atexit hook reads the code (main/fatal.hpp:17-24)
 }
 
+// Scope gate: a dataset that holds something this backend does not implement is REFUSED -- initialize() returns false with
+// g_ppf_fatal_code = 4 and the reason in g_ppf_fatal_detail, the way the reference reports an initial intersection
+// (main.cu:247-263) -- instead of taking the process down: an in-process host (ctypes / PyO3) keeps running and can tell why.
+struct ScopeRefusal {};
+[[noreturn]] static void refuse(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_ppf_fatal_detail, sizeof(g_ppf_fatal_detail), fmt, ap);
+    va_end(ap);
+    g_ppf_fatal_code = 4;
+    fprintf(stderr, "PPF REFUSED (4): %s\n", g_ppf_fatal_detail);
+    fflush(stderr);
+    throw ScopeRefusal{};
+}
+
 // ---------------------------------------------------------------------------------------------
 // device-side maintenance kernels
 // ---------------------------------------------------------------------------------------------
@@ -134,29 +149,25 @@ void upload_dataset(State &s) {
 
     // ---- scope gate: refuse loudly what this backend does not implement (DESIGN.md "out of scope") ----
     if (d.rod_count > ne) fatal(4, "rod_count %u exceeds the edge count %u", d.rod_count, ne);
-    for (unsigned i = 0; i < d.rod_count; ++i) {
-        const PpfEdgeParam &ep = d.param_arrays.edge.data[d.prop.edge.data[i].param_index];
-        (void)ep;
-    }
     if (d.rod_count && (d.edge_hess_slots.size < 4u * d.rod_count || d.rod_bend_hess_slots.size != 9u * d.surface_vert_count))
-        fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
-    if (d.mesh.mesh.tet.size) fatal(4, "B200 backend: tetrahedral solids are not implemented");
-    if (d.prop.pdrd_body.size) fatal(4, "B200 backend: PDRD rigid bodies are not implemented");
+        refuse("B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
+    if (d.mesh.mesh.tet.size) refuse("B200 backend: tetrahedral solids are not implemented");
+    if (d.prop.pdrd_body.size) refuse("B200 backend: PDRD rigid bodies are not implemented");
     if (d.constraint.stitch.size && d.stitch_hess_slots.size != 36u * d.constraint.stitch.size)
-        fatal(4, "B200 backend: slot-replay tables are required (stitch_hess_slots)");
-    if (prm.disable_pin_dof_removal) fatal(4, "B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
-    if (d.translation_lock.size) fatal(4, "B200 backend: translation/rotation locks are not implemented");
-    if (d.statistics_contact_count.size) fatal(4, "B200 backend: per-object contact statistics (statistics_contact_count) are not implemented");
+        refuse("B200 backend: slot-replay tables are required (stitch_hess_slots)");
+    if (prm.disable_pin_dof_removal) refuse("B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
+    if (d.translation_lock.size) refuse("B200 backend: translation/rotation locks are not implemented");
+    if (d.statistics_contact_count.size) refuse("B200 backend: per-object contact statistics (statistics_contact_count) are not implemented");
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
-        if (d.grain_inv_inertia.data[i] > 0.0f) fatal(4, "B200 backend: SAND grains are not implemented");
-    if (nf != d.shell_face_count || s.nsv != nv) fatal(4, "B200 backend: solid (tet) surfaces and interior vertices are not implemented (shell faces and rods only)");
+        if (d.grain_inv_inertia.data[i] > 0.0f) refuse("B200 backend: SAND grains are not implemented");
+    if (nf != d.shell_face_count || s.nsv != nv) refuse("B200 backend: solid (tet) surfaces and interior vertices are not implemented (shell faces and rods only)");
     for (unsigned i = 0; i < d.param_arrays.face.size; ++i) {
         const PpfFaceParam &fp = d.param_arrays.face.data[i];
         if (fp.model != PPF_MODEL_BARAFFWITKIN && fp.model != PPF_MODEL_ARAP && fp.model != PPF_MODEL_STVK && fp.model != PPF_MODEL_SNHK)
-            fatal(4, "B200 backend: shell model %d is not implemented (Baraff-Witkin, ARAP, StVK and SNHk are)", (int)fp.model);
+            refuse("B200 backend: shell model %d is not implemented (Baraff-Witkin, ARAP, StVK and SNHk are)", (int)fp.model);
     }
     if (d.face_hess_slots.size != 9u * nf || d.hinge_hess_slots.size != 16u * nh)
-        fatal(4, "B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
+        refuse("B200 backend: slot-replay tables are required (PPF_SLOT_REPLAY=0 is not supported)");
 
     // ---- positions ----
     std::vector<float4> tmp4(nv);
@@ -462,7 +473,13 @@ PPF_EXPORT bool initialize(PpfDataSet *dataset, PpfParamSet *param) {
     s.has_cw = s.cw_uploaded = false;
     s.h_isect_count = 0;
     ScopeLog logging("initialize");
-    upload_dataset(s);
+    try {
+        upload_dataset(s);
+    } catch (const ScopeRefusal &) {
+        logging.message("### refused: %s", g_ppf_fatal_detail);
+        s.initialized = false;
+        return false;
+    }
     s.initialized = true;
     bool result = true;
     if (!param->disable_contact) {
@@ -575,7 +592,7 @@ PPF_EXPORT void update_constraint(const PpfConstraint *constraint) {
 }
 PPF_EXPORT void update_rest_shape(const PpfRestShapeUpdate *update) {
     State &s = g;
-    if (update->inv_rest3x3.size || update->exclude_tet.size) fatal(4, "B200 backend: tetrahedral rest shapes are not implemented");
+    if (update->inv_rest3x3.size || update->exclude_tet.size) refuse("B200 backend: tetrahedral rest shapes are not implemented");
     if (update->inv_rest2x2.size) {
         std::vector<float4> ir(update->inv_rest2x2.size);
         for (unsigned i = 0; i < update->inv_rest2x2.size; ++i) {

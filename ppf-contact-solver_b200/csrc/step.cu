@@ -97,13 +97,32 @@ __global__ void k_lerp(unsigned n, float4 *eval_x, const float4 *x_old, float to
     eval_x[i] = make_float4(t.x + dx, t.y + dy, t.z + dz, 0.f);
 }
 
-struct EvTimer { // accumulates device time of a phase with CUDA events on the backend stream
-    cudaEvent_t a = nullptr, b = nullptr;
+// Device time of the phases, with CUDA events on the backend stream.  Events are only RECORDED while the step is being issued
+// (no host wait per phase: round 1 synchronised on every stop()); the elapsed times are read once, when the step has ended.
+struct PhaseClock {
     cudaStream_t q;
-    explicit EvTimer(cudaStream_t s) : q(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
-    ~EvTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
-    void start() { cudaEventRecord(a, q); }
-    double stop() { cudaEventRecord(b, q); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Span { size_t a, b; double *dst; };
+    std::vector<Span> spans;
+    explicit PhaseClock(cudaStream_t s) : q(s) {}
+    size_t mark() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        cudaEventRecord(pool[used], q);
+        return used++;
+    }
+    void collect() { // after the stream has been drained
+        for (const Span &sp : spans) { float ms = 0.f; if (cudaEventElapsedTime(&ms, pool[sp.a], pool[sp.b]) == cudaSuccess) *sp.dst += ms; }
+        spans.clear();
+        used = 0;
+    }
+};
+static PhaseClock *g_clock = nullptr;
+struct EvTimer { // one phase: start() ... stop(&accumulator)
+    size_t a = 0;
+    explicit EvTimer(cudaStream_t) {}
+    void start() { a = g_clock->mark(); }
+    void stop(double *dst) { g_clock->spans.push_back({a, g_clock->mark(), dst}); }
 };
 
 // PPF_DUMP_LINSYS=<k> / PPF_DUMP_DIR: one-shot dump of the k-th assembled Newton system in the
@@ -165,6 +184,7 @@ void step_advance(State &s, PpfStepResult *out) {
     const unsigned nv = s.nv;
     const unsigned gv = div_up(nv, 256);
     simplelog_set_time(prm.time);
+    if (!g_clock) g_clock = new PhaseClock(q);
     EvTimer t_all(q), t_ph(q);
     t_all.start();
     // The sweep's candidate lists were filtered with the collision-window flags of the step that produced them: when windows
@@ -172,7 +192,9 @@ void step_advance(State &s, PpfStepResult *out) {
     if (s.has_cw) s.cand_cover_eval = false;
     auto finish = [&](bool ok) {
         if (!ok) s.cand_cover_eval = false; // a failed advance leaves eval_x to be reset: its sweep candidates cover nothing
-        s.tm.ms_advance += t_all.stop();
+        t_all.stop(&s.tm.ms_advance);
+        CUDA_OK(cudaStreamSynchronize(q));
+        g_clock->collect();
         s.tm.n_advance += 1;
         *out = result;
     };
@@ -183,7 +205,7 @@ void step_advance(State &s, PpfStepResult *out) {
         bvh_build(s, s.bvh_face, 0, s.curr.p);
         bvh_build(s, s.bvh_edge, 1, s.curr.p);
         bvh_build(s, s.bvh_vert, 2, s.curr.p);
-        s.tm.ms_lbvh_build += t_ph.stop();
+        t_ph.stop(&s.tm.ms_lbvh_build);
         logging.pop();
     }
     const float prev_dt = prm.prev_dt;
@@ -260,7 +282,7 @@ void step_advance(State &s, PpfStepResult *out) {
             EvTimer tc(q);
             tc.start();
             num_contact += assemble_contact(s, dt, prm, max_nnz_row, dyn_consumed);
-            s.tm.ms_contact += tc.stop();
+            tc.stop(&s.tm.ms_contact);
         }
         logging.pop();
         logging.mark("dyn_consumed", dyn_consumed);
@@ -268,7 +290,7 @@ void step_advance(State &s, PpfStepResult *out) {
         num_contact += assemble_collision_mesh(s, prm); // static collision mesh (contact.cu:1834-1947)
         num_contact += assemble_colliders(s, prm); // embed_constraint_force_hessian (main.cu:873): spheres / walls, contact on or off
         logging.mark("num_contact", num_contact);
-        s.tm.ms_assembly += t_ph.stop();
+        t_ph.stop(&s.tm.ms_assembly);
         logging.pop();
 
         if (n_dof_removed > 0) {
@@ -281,7 +303,7 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.push("linsolve");
         t_ph.start();
         const SolveResult sr = pcg_solve(s, prm, s.vfixed.p);
-        s.tm.ms_linsolve += t_ph.stop();
+        t_ph.stop(&s.tm.ms_linsolve);
         logging.pop();
         logging.mark("iter", sr.iter);
         logging.mark("reresid", sr.resid);
@@ -321,14 +343,14 @@ void step_advance(State &s, PpfStepResult *out) {
             refit(s, s.bvh_face, 0, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
             refit(s, s.bvh_edge, 1, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
             refit(s, s.bvh_vert, 2, s.x_old.p, s.eval_x.p, prm.line_search_max_t);
-            s.tm.ms_aabb_update += t_ph.stop();
+            t_ph.stop(&s.tm.ms_aabb_update);
             logging.pop();
             logging.push("line search");
             t_ph.start();
             bool overlap = false;
             toi = fminf(toi, contact_line_search(s, s.x_old.p, s.eval_x.p, prm, overlap));
             if (s.cm_nv && !overlap) toi = fminf(toi, collision_mesh_line_search(s, s.x_old.p, s.eval_x.p, prm, overlap));
-            s.tm.ms_line_search += t_ph.stop();
+            t_ph.stop(&s.tm.ms_line_search);
             if (overlap) {
                 logging.message("### contact starts overlapping: two surfaces begin the step already touching or overlapping "
                                 "(a contact pair is inside the contact offset at the start of the step).");

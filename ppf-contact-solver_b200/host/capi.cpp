@@ -47,6 +47,11 @@ void ppfh_set_args(Session *s, unsigned cg_max_iter, float cg_tol, int disable_c
     if (cg_tol > 0) s->b.param.cg_tol = cg_tol;
     if (disable_contact >= 0) s->b.param.disable_contact = disable_contact != 0;
 }
+// ParamSet switches a test needs to flip before initialize(): "disable_pin_dof_removal" (barrier-held fix pins, scene.rs make_param)
+int ppfh_set_param_flag(Session *s, const char *name, int value) {
+    if (std::string(name) == "disable_pin_dof_removal") { s->b.param.disable_pin_dof_removal = value != 0; return 1; }
+    return 0;
+}
 int ppfh_load_state(Session *s, const char *path) {
     double t; float prev_dt;
     std::vector<float> c, p;

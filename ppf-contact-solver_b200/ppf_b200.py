@@ -78,7 +78,7 @@ def host():
 class Session:
     """One scene + one backend library (one per process: the backends keep global state)."""
 
-    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None, allow_init_failure=False):
+    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None, allow_init_failure=False, param_flags=None):
         """shard = (rank, world, nccl_id_bytes[, allgather]): row-shard the PCG solve of this scene over `world`
         GPUs (every rank builds the same scene; see csrc/dist.hpp).  `allgather(bytes) -> [bytes per rank]` is
         the launcher's object all-gather; with it the ranks also exchange CUDA IPC handles and the per-iteration
@@ -94,6 +94,9 @@ class Session:
         self.n_vert, self.n_face, self.n_edge, self.n_hinge, self.n_fix, self.fixed_nnz = [int(v) for v in c]
         if cg_tol or cg_max_iter:
             self.h.ppfh_set_args(self.p, ctypes.c_uint(cg_max_iter), ctypes.c_float(cg_tol), ctypes.c_int(-1))
+        for name, value in (param_flags or {}).items():
+            if not self.h.ppfh_set_param_flag(self.p, name.encode(), ctypes.c_int(int(value))):
+                raise RuntimeError("unknown ParamSet flag %s" % name)
         if state is not None and not self.h.ppfh_load_state(self.p, state.encode()):
             raise RuntimeError("cannot load state %s" % state)
         if not self.h.ppfh_open(self.p, lib.encode()):
@@ -246,6 +249,10 @@ class Session:
     def fatal_code(self):
         fn = self._sym("ppf_fatal_code", ctypes.c_ubyte)
         return int(fn())
+
+    def fatal_detail(self):
+        fn = self._sym("ppf_fatal_detail", ctypes.c_char_p)
+        return (fn() or b"").decode(errors="replace")
 
     def fix_targets(self):
         n = int(self.h.ppfh_fix_targets(self.p, None, None))

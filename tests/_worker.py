@@ -43,11 +43,11 @@ def run(job):
     else:
         os.environ.pop("PPF_DUMP_PAIRS_DIR", None)
     s = ppf_b200.Session(job["scene"], n=job.get("n", 0), lib=lib, log_dir=os.path.join(out, "logs"), state=job.get("state"),
-                         allow_init_failure=bool(job.get("allow_init_failure")))
+                         allow_init_failure=bool(job.get("allow_init_failure")), param_flags=job.get("param_flags"))
     res = {"counts": np.array([s.n_vert, s.n_face, s.n_edge, s.n_hinge, s.n_fix], np.int64)}
     if job.get("allow_init_failure"):   # positive path of the intersection check: initialize() may refuse the start state
         rec = s.intersection_records()
-        res["init_ok"] = np.array([s.init_ok]); res["fatal_code"] = np.array([s.fatal_code()])
+        res["init_ok"] = np.array([s.init_ok]); res["fatal_code"] = np.array([s.fatal_code()]); res["fatal_detail"] = np.array(s.fatal_detail())
         res["isect"] = np.array([[t, a, b] + list(pos) + [0.0] * (15 - len(pos)) for t, a, b, pos in rec], np.float64).reshape(len(rec), 18)
         if not s.init_ok:
             np.savez(os.path.join(out, "result.npz"), **res)

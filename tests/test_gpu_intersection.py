@@ -43,3 +43,13 @@ def test_intersecting_start_state_is_refused_with_the_same_records(run_job, ppf,
     # ... and the untouched start state is accepted
     r = run_job({"lib": "ours", "scene": scene, "n": n, "state": None, "steps": 0, "allow_init_failure": True}, force_subprocess=True)
     assert bool(r["init_ok"][0]) and len(r["isect"]) == 0
+
+
+def test_scope_gate_refuses_without_killing_the_process(run_job):
+    """A dataset with something this backend does not implement (here: barrier-held fix pins, ParamSet.disable_pin_dof_removal)
+    is refused: initialize() returns false with fatal code 4 and the reason in ppf_fatal_detail -- the worker process lives on
+    to report it (round 1 called exit(1) here)."""
+    r = run_job({"lib": "ours", "scene": "fast-twist", "n": 16, "state": None, "steps": 0, "allow_init_failure": True,
+                 "param_flags": {"disable_pin_dof_removal": 1}}, force_subprocess=True)
+    assert not bool(r["init_ok"][0]) and int(r["fatal_code"][0]) == 4
+    assert "disable_pin_dof_removal" in str(r["fatal_detail"])
