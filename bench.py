@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--scene", default="large-twist")
     ap.add_argument("--n", type=int, default=0, help="resolution override (0 = the config's own: n=1410 for large-twist)")
     ap.add_argument("--state", default=None, help="start from a saved state (ppf_host --save-every / Session.save_state) instead of t=0, e.g. a contact-rich window")
+    ap.add_argument("--precond", type=int, default=0, help="ParamSet.precond: 0 block-Jacobi (the reference's default and the parity configuration), 1 Schwarz")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent scenes (weak scaling) instead of sharding ONE scene's PCG rows over the GPUs")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--full-v", type=int, default=0, help=argparse.SUPPRESS)
@@ -212,7 +213,8 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(devnull, 1)  # the backends narrate on stdout; keep ours for the JSON line
     try:
-        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK, shard=shard, state=args.state)
+        s = ppf_b200.Session(args.scene, n=args.n, lib=lib, log_dir="/tmp/ppf_bench_logs_%d" % RANK, shard=shard, state=args.state,
+                             param_flags={"precond": args.precond} if args.precond else None)
         if shard is not None:  # all ranks or none: a rank that could not join the communicator turns the run into replicas
             oks = [None] * WORLD
             ranks.dist.all_gather_object(oks, bool(s.sharded))

@@ -263,6 +263,7 @@ void build_fetch_pattern(State &s, std::vector<unsigned> &index, std::vector<uns
 struct SolveResult { bool ok; unsigned iter; float resid; };
 SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof_mask);
 void apply_dirichlet(State &s);
+bool pcg_schwarz_served();   // ParamSet.precond == Schwarz was honoured by the last solve (multilevel additive preconditioner, pcg.cu)
 
 // prims.cu -- reductions on the backend stream, result returned to the host
 float reduce_max_f(State &s, const float *d, size_t n, float init);

@@ -307,9 +307,9 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.pop();
         logging.mark("iter", sr.iter);
         logging.mark("reresid", sr.resid);
-        // this backend always solves with block-Jacobi: a request for the Schwarz preconditioner is reported the way the
-        // reference reports its own fallback to block-Jacobi (main.cu:1124, solver.cu:2317)
-        logging.mark("schwarz_fallback", prm.precond == PPF_PRECOND_SCHWARZ ? 1 : 0);
+        // a request for the Schwarz preconditioner that could not be served (several ranks) is reported the way the reference
+        // reports its own fallback to block-Jacobi (main.cu:1124, solver.cu:2317)
+        logging.mark("schwarz_fallback", prm.precond == PPF_PRECOND_SCHWARZ && !pcg_schwarz_served() ? 1 : 0);
         if (!sr.ok) {
             logging.message("### cg failed");
             result.pcg_success = false;

@@ -50,6 +50,7 @@ void ppfh_set_args(Session *s, unsigned cg_max_iter, float cg_tol, int disable_c
 // ParamSet switches a test needs to flip before initialize(): "disable_pin_dof_removal" (barrier-held fix pins, scene.rs make_param)
 int ppfh_set_param_flag(Session *s, const char *name, int value) {
     if (std::string(name) == "disable_pin_dof_removal") { s->b.param.disable_pin_dof_removal = value != 0; return 1; }
+    if (std::string(name) == "precond") { s->b.param.precond = value ? PPF_PRECOND_SCHWARZ : PPF_PRECOND_BLOCKJACOBI; return 1; } // 0 block-Jacobi, 1 Schwarz (data.hpp:83)
     return 0;
 }
 int ppfh_load_state(Session *s, const char *path) {

@@ -1,9 +1,13 @@
-"""Multi-GPU plumbing of the hot path: one process per GPU, "replicas only".
+"""Launcher-side plumbing for N > 1 (one process per GPU): rank bookkeeping, the barrier around the timed region and the
+max-over-ranks / sum-over-ranks of the measurements.  torch.distributed only -- NCCL on the GPU box, gloo in the CPU tests
+(tests/test_dist_gloo.py) and when the ranks SHARD one scene.
 
-The per-step path of one scene does not shard (DESIGN.md section "multi-GPU"): each rank owns an
-independent scene on its own device, there is no data-path collective, and torch.distributed is
-used only for the barrier around the timed region and for the max-over-ranks / sum-over-ranks of
-the measurements.  NCCL on the GPU box, gloo in the CPU tests (tests/test_dist_gloo.py).
+Two ways to use several GPUs (DESIGN.md section "Multi-GPU"):
+  * sharded (bench.py default): every rank holds the same scene; the rows of the PCG solve and the contact-detection /
+    line-search queries are split over the ranks INSIDE the backend (csrc/dist.hpp: NVLink peer memory + NCCL).  This module
+    then only carries the NCCL id, the IPC handles and the timing reductions over gloo.
+  * replicas (bench.py --replicas; the right mode for scenes below ~1 M vertices): each rank owns an independent scene on its
+    own device and there is no data-path collective at all.
 """
 import os
 

@@ -53,6 +53,7 @@ void apply_dirichlet(State &s) {
         s.force.p[3 * size_t(i)] = e.x - t.x; s.force.p[3 * size_t(i) + 1] = e.y - t.y; s.force.p[3 * size_t(i) + 2] = e.z - t.z;
     }
 }
+bool pcg_schwarz_served() { return false; } // the emulated build solves with block-Jacobi only
 SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *) {
     const unsigned n = s.nv;
     std::vector<double> D(size_t(9) * n);
