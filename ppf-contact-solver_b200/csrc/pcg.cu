@@ -830,14 +830,17 @@ __device__ __forceinline__ float cg_alpha(double pap_sum, double abs_sum, double
 // Cost per iteration: one 16-byte reduction per row in k_update (restriction), two small kernels over the aggregates, one
 // 16-byte gather per row in k_direction -- about +6 % of the iteration's bytes; prototype (scipy, same matrices): 187 -> 105
 // iterations at V = 65 k, 377 -> 188 at V = 259 k.  Single GPU only (several ranks fall back to block-Jacobi and say so).
-static constexpr int MAS_SHIFT = 4;
+static constexpr unsigned MAS_GROUP = 16;
 static constexpr int MAS_MAX_LEVELS = 8;
+static constexpr unsigned MAS_NONE = 0xFFFFFFFFu;
 struct MasView {
     int L;                               // levels in use (0 = off)
     unsigned nl[MAS_MAX_LEVELS + 1];     // aggregates on level l = 1..L
-    unsigned off[MAS_MAX_LEVELS + 1];    // flat offset of level l in Dsum / Dinv / R
-    const unsigned *agg1;                // level-1 aggregate of every vertex
+    unsigned off[MAS_MAX_LEVELS + 1];    // flat offset of level l in parent / crange / Dsum / Dinv / R
+    const unsigned *agg1;                // level-1 aggregate of every vertex, MAS_NONE = not aggregated (rod / loose vertices)
     const unsigned char *mask;           // pinned vertices (left out)
+    const unsigned *parent;              // flat: aggregate on the next level (levels 1 .. L-1)
+    const uint2 *crange;                 // flat: (first child, child count) on the level below (levels 2 .. L)
     float *Dsum, *Dinv;                  // 6 floats per aggregate (00, 11, 22, 01, 02, 12)
     float4 *R;                           // restricted residual per aggregate, all levels
     float4 *E;                           // total correction per level-1 aggregate
@@ -848,7 +851,8 @@ struct Mas {
     bool on = false;                     // this solve uses it
     MasView v = {};
     unsigned total = 0;
-    DBuf<unsigned> agg1, done;
+    DBuf<unsigned> agg1, parent, done;
+    DBuf<uint2> crange;
     DBuf<float> Dsum, Dinv;
     DBuf<float4> Rv, Ev;
 };
@@ -858,76 +862,131 @@ static unsigned mas_expand_bits(unsigned v) {
     v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu; v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
     return v;
 }
-// once per scene: Morton order of the start positions -> nested aggregates
+// Once per scene: the aggregate hierarchy.  Shell vertices only (rods and loose vertices keep plain block-Jacobi: a piecewise-
+// constant mode over vertices that no face connects is not a useful coarse space), never across connected components of the
+// face graph (two cloths that merely touch are not one aggregate); inside a component the vertices are taken in Morton order
+// of their start positions, 16 per level-1 aggregate, and every further level groups 16 consecutive aggregates of the level
+// below -- until a component is down to one aggregate.
 static void mas_init(State &s) {
-    const unsigned n = s.nv;
+    const unsigned n = s.nv, nf = s.nf;
     const float *x = reinterpret_cast<const float *>(s.host.vertex.curr.data);
+    const unsigned *face = reinterpret_cast<const unsigned *>(s.host.mesh.mesh.face.data);
+    std::vector<unsigned> root(n);
+    for (unsigned i = 0; i < n; ++i) root[i] = i;
+    auto find = [&](unsigned v) { while (root[v] != v) { root[v] = root[root[v]]; v = root[v]; } return v; };
+    std::vector<unsigned char> in_face(n, 0);
+    for (unsigned f = 0; f < nf; ++f) {
+        const unsigned a = face[3 * size_t(f)], b = face[3 * size_t(f) + 1], c = face[3 * size_t(f) + 2];
+        in_face[a] = in_face[b] = in_face[c] = 1;
+        const unsigned ra = find(a), rb = find(b);
+        if (ra != rb) root[std::max(ra, rb)] = std::min(ra, rb);
+        const unsigned r2 = find(a), rc = find(c);
+        if (r2 != rc) root[std::max(r2, rc)] = std::min(r2, rc);
+    }
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (unsigned i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], x[3 * size_t(i) + k]); hi[k] = std::max(hi[k], x[3 * size_t(i) + k]); }
-    std::vector<unsigned long long> key(n);
+    struct Key { unsigned comp, code, v; };
+    std::vector<Key> key;
+    key.reserve(n);
     for (unsigned i = 0; i < n; ++i) {
+        if (!in_face[i]) continue;
         unsigned q[3];
         for (int k = 0; k < 3; ++k) {
             const float ext = hi[k] - lo[k];
             const float sc = ext > 1e-10f ? 1023.0f / ext : 0.0f;
             q[k] = (unsigned)std::min(1023.0f, std::max(0.0f, (x[3 * size_t(i) + k] - lo[k]) * sc));
         }
-        const unsigned code = mas_expand_bits(q[0]) | (mas_expand_bits(q[1]) << 1) | (mas_expand_bits(q[2]) << 2);
-        key[i] = ((unsigned long long)code << 32) | i; // ties broken by the index
+        key.push_back(Key{find(i), mas_expand_bits(q[0]) | (mas_expand_bits(q[1]) << 1) | (mas_expand_bits(q[2]) << 2), i}); // component = its smallest vertex
     }
-    std::sort(key.begin(), key.end());
-    std::vector<unsigned> agg1(n);
-    for (unsigned r = 0; r < n; ++r) agg1[unsigned(key[r] & 0xFFFFFFFFu)] = r >> MAS_SHIFT;
+    std::sort(key.begin(), key.end(), [](const Key &a, const Key &b) { return a.comp != b.comp ? a.comp < b.comp : (a.code != b.code ? a.code < b.code : a.v < b.v); });
+    std::vector<unsigned> agg1(n, MAS_NONE), comp_of; // comp_of: component of every aggregate of the current level
+    {
+        unsigned count = 0;
+        for (size_t r = 0; r < key.size(); ++r) {
+            if (r == 0 || key[r].comp != key[r - 1].comp || count == MAS_GROUP) { comp_of.push_back(key[r].comp); count = 0; }
+            agg1[key[r].v] = (unsigned)comp_of.size() - 1;
+            ++count;
+        }
+    }
     MasView &v = M.v;
     v = MasView{};
-    unsigned nl = (n + (1u << MAS_SHIFT) - 1) >> MAS_SHIFT, off = 0;
+    std::vector<unsigned> parent;  // flat
+    std::vector<uint2> crange;     // flat
     int L = 0;
-    while (L < MAS_MAX_LEVELS) {
+    unsigned off = 0;
+    while (!comp_of.empty()) {
         ++L;
-        v.nl[L] = nl; v.off[L] = off;
-        off += nl;
-        if (nl <= 1) break;
-        nl = (nl + (1u << MAS_SHIFT) - 1) >> MAS_SHIFT;
+        v.nl[L] = (unsigned)comp_of.size(); v.off[L] = off;
+        off += v.nl[L];
+        parent.resize(off, MAS_NONE);
+        crange.resize(off, make_uint2(0, 0));
+        bool single = true; // every component is one aggregate on this level
+        for (size_t i = 1; i < comp_of.size(); ++i) single = single && comp_of[i] != comp_of[i - 1];
+        if (single || L == MAS_MAX_LEVELS) break;
+        std::vector<unsigned> next;
+        unsigned count = 0;
+        for (size_t i = 0; i < comp_of.size(); ++i) {
+            if (i == 0 || comp_of[i] != comp_of[i - 1] || count == MAS_GROUP) { next.push_back(comp_of[i]); count = 0; }
+            parent[v.off[L] + i] = (unsigned)next.size() - 1;
+            ++count;
+        }
+        // child ranges of the next level (children are consecutive)
+        std::vector<uint2> cr(next.size(), make_uint2(0, 0));
+        for (size_t i = 0; i < comp_of.size(); ++i) {
+            uint2 &c = cr[parent[v.off[L] + i]];
+            if (c.y == 0) c.x = (unsigned)i;
+            ++c.y;
+        }
+        crange.resize(off + next.size());
+        for (size_t j = 0; j < next.size(); ++j) crange[off + j] = cr[j];
+        comp_of.swap(next);
     }
     v.L = L;
     M.total = off;
+    if (!L) { M.ready = true; return; } // no shell vertices: nothing to aggregate
+    parent.resize(off, MAS_NONE); crange.resize(off, make_uint2(0, 0));
     M.agg1.upload(agg1.data(), n, s.stream);
+    M.parent.upload(parent.data(), off, s.stream);
+    M.crange.upload(crange.data(), off, s.stream);
     M.Dsum.reserve(size_t(6) * off); M.Dinv.reserve(size_t(6) * off); M.Rv.reserve(off); M.Ev.reserve(v.nl[1]); M.done.reserve(4);
     CUDA_OK(cudaMemsetAsync(M.Rv.p, 0, sizeof(float4) * off, s.stream));
     CUDA_OK(cudaMemsetAsync(M.done.p, 0, 4 * sizeof(unsigned), s.stream));
     CUDA_OK(cudaStreamSynchronize(s.stream));
-    v.agg1 = M.agg1.p; v.Dsum = M.Dsum.p; v.Dinv = M.Dinv.p; v.R = M.Rv.p; v.E = M.Ev.p; v.done = M.done.p;
+    v.agg1 = M.agg1.p; v.parent = M.parent.p; v.crange = M.crange.p; v.Dsum = M.Dsum.p; v.Dinv = M.Dinv.p; v.R = M.Rv.p; v.E = M.Ev.p; v.done = M.done.p;
     M.ready = true;
-    log_info("pcg: multilevel additive preconditioner: %d levels over %u vertices (%u aggregates of <= 16 on level 1)", L, n, v.nl[1]);
+    log_info("pcg: multilevel additive preconditioner: %d levels, %u / %u / ... / %u aggregates over %zu shell vertices", L, v.nl[1], L > 1 ? v.nl[2] : 0u, v.nl[L],
+             key.size());
 }
 
-// first level on which vertices with level-1 aggregates ia, ib share an aggregate
-__device__ __forceinline__ int mas_first_common_level(unsigned ia, unsigned ib) {
-    const unsigned x = ia ^ ib;
-    return x == 0 ? 1 : 2 + (31 - __clz(x)) / MAS_SHIFT;
-}
 __device__ __forceinline__ void mas_add6(float *dst, float s00, float s11, float s22, float s01, float s02, float s12) {
     atomicAdd(dst + 0, s00); atomicAdd(dst + 1, s11); atomicAdd(dst + 2, s22); atomicAdd(dst + 3, s01); atomicAdd(dst + 4, s02); atomicAdd(dst + 5, s12);
 }
-// every stored strictly-upper block (a, b, B) stands for B at (a, b) and B^T at (b, a): the aggregate sum gets B + B^T
+// every stored strictly-upper block (a, b, B) stands for B at (a, b) and B^T at (b, a): the aggregate sum gets B + B^T, on the
+// first level where a and b share an aggregate (the levels above get it through k_mas_up)
 __global__ void k_mas_offdiag(MasView v, unsigned nnz, const unsigned *__restrict__ row, const unsigned *__restrict__ col, const float *__restrict__ val,
                               size_t plane) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     const unsigned a = row[k], b = col[k];
     if (v.mask[a] || v.mask[b]) return;
-    const unsigned ia = v.agg1[a], ib = v.agg1[b];
-    const int l = mas_first_common_level(ia, ib);
-    if (l > v.L) return;
+    unsigned ia = v.agg1[a], ib = v.agg1[b];
+    if (ia == MAS_NONE || ib == MAS_NONE) return;
+    int l = 1;
+    while (ia != ib) {
+        if (l == v.L) return; // different components
+        ia = v.parent[v.off[l] + ia];
+        ib = v.parent[v.off[l] + ib];
+        ++l;
+    }
     float h[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) h[e] = val[size_t(e) * plane + k];
-    mas_add6(v.Dsum + size_t(6) * (v.off[l] + (ia >> (MAS_SHIFT * (l - 1)))), 2.0f * h[0], 2.0f * h[4], 2.0f * h[8], h[3] + h[1], h[6] + h[2], h[7] + h[5]);
+    mas_add6(v.Dsum + size_t(6) * (v.off[l] + ia), 2.0f * h[0], 2.0f * h[4], 2.0f * h[8], h[3] + h[1], h[6] + h[2], h[7] + h[5]);
 }
 __global__ void k_mas_diag(MasView v, unsigned n, const float *__restrict__ D) {
     const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n || v.mask[a]) return;
+    if (a >= n || v.mask[a] || v.agg1[a] == MAS_NONE) return;
     mas_add6(v.Dsum + size_t(6) * v.agg1[a], D[a], D[size_t(n) + a], D[2 * size_t(n) + a], D[3 * size_t(n) + a], D[4 * size_t(n) + a], D[5 * size_t(n) + a]);
 }
 // level l (>= 2): add the sums of the children (complete by now) to the blocks that first meet on this level
@@ -938,8 +997,8 @@ __global__ void k_mas_up(MasView v, int l) {
     float *dst = v.Dsum + size_t(6) * (v.off[l] + I);
 #pragma unroll
     for (int e = 0; e < 6; ++e) acc[e] = dst[e];
-    const unsigned c0 = I << MAS_SHIFT, c1 = min(c0 + (1u << MAS_SHIFT), v.nl[l - 1]);
-    for (unsigned c = c0; c < c1; ++c) {
+    const uint2 cr = v.crange[v.off[l] + I];
+    for (unsigned c = cr.x; c < cr.x + cr.y; ++c) {
         const float *src = v.Dsum + size_t(6) * (v.off[l - 1] + c);
 #pragma unroll
         for (int e = 0; e < 6; ++e) acc[e] += src[e];
@@ -965,8 +1024,8 @@ __global__ void __launch_bounds__(256) k_mas_restrict_up(MasView v) {
     const unsigned I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I < v.nl[2]) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const unsigned c0 = I << MAS_SHIFT, c1 = min(c0 + (1u << MAS_SHIFT), v.nl[1]);
-        for (unsigned c = c0; c < c1; ++c) { const float4 r = v.R[v.off[1] + c]; acc.x += r.x; acc.y += r.y; acc.z += r.z; }
+        const uint2 cr = v.crange[v.off[2] + I];
+        for (unsigned c = cr.x; c < cr.x + cr.y; ++c) { const float4 r = v.R[v.off[1] + c]; acc.x += r.x; acc.y += r.y; acc.z += r.z; }
         v.R[v.off[2] + I] = acc;
     }
     if (v.L < 3) return;
@@ -981,8 +1040,8 @@ __global__ void __launch_bounds__(256) k_mas_restrict_up(MasView v) {
     for (int l = 3; l <= v.L; ++l) {
         for (unsigned J = threadIdx.x; J < v.nl[l]; J += blockDim.x) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const unsigned c0 = J << MAS_SHIFT, c1 = min(c0 + (1u << MAS_SHIFT), v.nl[l - 1]);
-            for (unsigned c = c0; c < c1; ++c) { const float4 r = __ldcg(v.R + v.off[l - 1] + c); acc.x += r.x; acc.y += r.y; acc.z += r.z; } // written by other CTAs: L2
+            const uint2 cr = v.crange[v.off[l] + J];
+            for (unsigned c = cr.x; c < cr.x + cr.y; ++c) { const float4 r = __ldcg(v.R + v.off[l - 1] + c); acc.x += r.x; acc.y += r.y; acc.z += r.z; } // written by other CTAs: L2
             v.R[v.off[l] + J] = acc;
         }
         __threadfence_block();
@@ -996,8 +1055,10 @@ __global__ void __launch_bounds__(256) k_mas_correct(MasView v, CgScalars *sc, i
     if (I < v.nl[1]) {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 r1 = v.R[v.off[1] + I];
+        unsigned up = I;
         for (int l = 1; l <= v.L; ++l) {
-            const unsigned J = v.off[l] + (I >> (MAS_SHIFT * (l - 1)));
+            const unsigned J = v.off[l] + up;
+            if (l < v.L) up = v.parent[J];
             const float4 r = l == 1 ? r1 : v.R[J];
             const float *m = v.Dinv + size_t(6) * J;
             e.x += m[0] * r.x + m[3] * r.y + m[4] * r.z;
@@ -1030,7 +1091,7 @@ __global__ void k_residual_init_a(unsigned n, const float4 *__restrict__ y, floa
         st_planes(r, n, a, ra);
         const float4 za = sym6_mul(Pinv, n, a, ra);
         st_planes(z, n, a, za);
-        if (!v.mask[a]) red_add_v4(v.R + v.agg1[a], ra.x, ra.y, ra.z);
+        if (!v.mask[a] && v.agg1[a] != MAS_NONE) red_add_v4(v.R + v.agg1[a], ra.x, ra.y, ra.z);
         rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
         err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
     }
@@ -1042,7 +1103,7 @@ __global__ void k_residual_init_b(unsigned n, const float *__restrict__ z, float
     float dot = 0.f, absdot = 0.f;
     for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
         float4 za = ld_planes(z, n, a);
-        if (!v.mask[a]) { const float4 e = v.E[v.agg1[a]]; za.x += e.x; za.y += e.y; za.z += e.z; }
+        if (!v.mask[a] && v.agg1[a] != MAS_NONE) { const float4 e = v.E[v.agg1[a]]; za.x += e.x; za.y += e.y; za.z += e.z; }
         p[a] = za;
         const float4 w = sym6_mul(D, n, a, za);
         y[a] = w;
@@ -1089,7 +1150,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
         st_planes(r, n, a, ra);
         const float4 za = sym6_apply(Ma, ra);
         st_planes(z, n, a, za);
-        if (mv.L && !mv.mask[a]) red_add_v4(mv.R + mv.agg1[a], ra.x, ra.y, ra.z); // restriction to the level-1 aggregates
+        if (mv.L && !mv.mask[a] && mv.agg1[a] != MAS_NONE) red_add_v4(mv.R + mv.agg1[a], ra.x, ra.y, ra.z); // restriction to the level-1 aggregates
         rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
         err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
         if (two) {
@@ -1097,7 +1158,7 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
             st_planes(r, n, b, rb);
             const float4 zb = sym6_apply(Mb, rb);
             st_planes(z, n, b, zb);
-            if (mv.L && !mv.mask[b]) red_add_v4(mv.R + mv.agg1[b], rb.x, rb.y, rb.z);
+            if (mv.L && !mv.mask[b] && mv.agg1[b] != MAS_NONE) red_add_v4(mv.R + mv.agg1[b], rb.x, rb.y, rb.z);
             rz += rb.x * zb.x + rb.y * zb.y + rb.z * zb.z;
             err += fabsf(rb.x) + fabsf(rb.y) + fabsf(rb.z);
         }
@@ -1172,8 +1233,8 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
         Sym6 Db = {};
         if (two) { zb = ld_planes(z, n, b); pb = p[b]; xb = ld_planes(x, n, b); Db = ld_sym6(D, n, b); }
         if (mv.L) { // coarse-level corrections of the multilevel preconditioner: z = Pinv r + E[aggregate]
-            if (!mv.mask[a]) { const float4 e = mv.E[mv.agg1[a]]; za.x += e.x; za.y += e.y; za.z += e.z; }
-            if (two && !mv.mask[b]) { const float4 e = mv.E[mv.agg1[b]]; zb.x += e.x; zb.y += e.y; zb.z += e.z; }
+            if (!mv.mask[a] && mv.agg1[a] != MAS_NONE) { const float4 e = mv.E[mv.agg1[a]]; za.x += e.x; za.y += e.y; za.z += e.z; }
+            if (two && !mv.mask[b] && mv.agg1[b] != MAS_NONE) { const float4 e = mv.E[mv.agg1[b]]; zb.x += e.x; zb.y += e.y; zb.z += e.z; }
         }
         finish_row(a, za, pa, xa, Da);
         if (two) finish_row(b, zb, pb, xb, Db);
@@ -1885,7 +1946,8 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     M.on = prm.precond == PPF_PRECOND_SCHWARZ && !g_dist.on() && !mas_off;
     if (M.on) {
         if (!M.ready) mas_init(s);
-        mas_build(s);
+        if (M.v.L == 0) M.on = false; // a scene without shell faces: plain block-Jacobi IS this preconditioner
+        else mas_build(s);
     }
 
     // ---- setup: r = b - A x0, z = P r, p = z, y = D p, rz0, err0 ----
