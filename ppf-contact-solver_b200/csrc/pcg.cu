@@ -1080,20 +1080,41 @@ __global__ void __launch_bounds__(256) k_mas_correct(MasView v, CgScalars *sc, i
         if (threadIdx.x == 0 && t != 0.f) atomicAdd(&sc->rzerr[slot][0], (double)t);
     }
 }
+// Restriction R[aggregate] += r with fewer atomics: in mesh order a 4 x 4 Morton patch shows up as runs of consecutive rows, so the
+// lanes of a warp that hold the same aggregate in a row are summed with a segmented shuffle scan (like the SpMV's row runs) and
+// the last lane of each run issues one 16-byte reduction.  All 32 lanes must call it (agg = MAS_NONE: nothing to add).
+__device__ __forceinline__ void mas_restrict_warp(float4 *R, unsigned agg, float rx, float ry, float rz) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned ga = __shfl_up_sync(0xffffffffu, agg, o);
+        const float t0 = __shfl_up_sync(0xffffffffu, rx, o), t1 = __shfl_up_sync(0xffffffffu, ry, o), t2 = __shfl_up_sync(0xffffffffu, rz, o);
+        if (lane >= (unsigned)o && ga == agg) { rx += t0; ry += t1; rz += t2; }
+    }
+    const unsigned next = __shfl_down_sync(0xffffffffu, agg, 1);
+    if (agg != MAS_NONE && (lane == 31 || next != agg)) red_add_v4(R + agg, rx, ry, rz);
+}
+
 // setup with the multilevel preconditioner, first half: r = b - A x0, z0 = Pinv r, restriction, r.z0 and |r|_1
 __global__ void k_residual_init_a(unsigned n, const float4 *__restrict__ y, float *__restrict__ r, float *__restrict__ z, const float *__restrict__ Pinv,
                                   CgScalars *sc, MasView v) {
     float rz = 0.f, err = 0.f;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        float4 ra = ld_planes(r, n, a);
-        const float4 ya = y[a];
-        ra.x -= ya.x; ra.y -= ya.y; ra.z -= ya.z;
-        st_planes(r, n, a, ra);
-        const float4 za = sym6_mul(Pinv, n, a, ra);
-        st_planes(z, n, a, za);
-        if (!v.mask[a] && v.agg1[a] != MAS_NONE) red_add_v4(v.R + v.agg1[a], ra.x, ra.y, ra.z);
-        rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
-        err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+    const unsigned n_pad = (n + 31u) & ~31u; // warp-uniform trip count: the restriction shuffles across the warp
+    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n_pad; a += gridDim.x * blockDim.x) {
+        unsigned agg = MAS_NONE;
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a < n) {
+            ra = ld_planes(r, n, a);
+            const float4 ya = y[a];
+            ra.x -= ya.x; ra.y -= ya.y; ra.z -= ya.z;
+            st_planes(r, n, a, ra);
+            const float4 za = sym6_mul(Pinv, n, a, ra);
+            st_planes(z, n, a, za);
+            if (!v.mask[a]) agg = v.agg1[a];
+            rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
+            err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+        }
+        mas_restrict_warp(v.R, agg, ra.x, ra.y, ra.z);
     }
     block_accumulate2(rz, err, &sc->rzerr[0][0], &sc->rzerr[0][1]);
 }
@@ -1137,30 +1158,38 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
     // two rows per thread per trip: the vector kernels were latency bound (ncu: long-scoreboard stalls at 55 % of DRAM
     // peak), so both rows' loads are in flight before the first dependent store
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi; a += 2 * stride) {
+    // trip counts are warp-uniform (hi padded to a whole warp, lanes past hi idle): the restriction of the multilevel
+    // preconditioner shuffles across the warp
+    const unsigned hi_pad = lo + (((hi - lo) + 31u) & ~31u);
+    for (unsigned a = lo + blockIdx.x * blockDim.x + threadIdx.x; a < hi_pad; a += 2 * stride) {
         const unsigned b = a + stride;
-        const bool two = b < hi;
-        const float4 ya = y[a];
-        float4 ra = ld_planes(r, n, a);
-        const Sym6 Ma = ld_sym6(Pinv, n, a);
-        float4 yb = make_float4(0.f, 0.f, 0.f, 0.f), rb = yb;
-        Sym6 Mb = {};
+        const bool one = a < hi, two = b < hi;
+        float4 ya = make_float4(0.f, 0.f, 0.f, 0.f), ra = ya, yb = ya, rb = ya;
+        Sym6 Ma = {}, Mb = {};
+        if (one) { ya = y[a]; ra = ld_planes(r, n, a); Ma = ld_sym6(Pinv, n, a); }
         if (two) { yb = y[b]; rb = ld_planes(r, n, b); Mb = ld_sym6(Pinv, n, b); }
-        ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
-        st_planes(r, n, a, ra);
-        const float4 za = sym6_apply(Ma, ra);
-        st_planes(z, n, a, za);
-        if (mv.L && !mv.mask[a] && mv.agg1[a] != MAS_NONE) red_add_v4(mv.R + mv.agg1[a], ra.x, ra.y, ra.z); // restriction to the level-1 aggregates
-        rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
-        err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+        unsigned agg_a = MAS_NONE, agg_b = MAS_NONE;
+        if (one) {
+            ra.x -= alpha * ya.x; ra.y -= alpha * ya.y; ra.z -= alpha * ya.z;
+            st_planes(r, n, a, ra);
+            const float4 za = sym6_apply(Ma, ra);
+            st_planes(z, n, a, za);
+            if (mv.L && !mv.mask[a]) agg_a = mv.agg1[a];
+            rz += ra.x * za.x + ra.y * za.y + ra.z * za.z;
+            err += fabsf(ra.x) + fabsf(ra.y) + fabsf(ra.z);
+        }
         if (two) {
             rb.x -= alpha * yb.x; rb.y -= alpha * yb.y; rb.z -= alpha * yb.z;
             st_planes(r, n, b, rb);
             const float4 zb = sym6_apply(Mb, rb);
             st_planes(z, n, b, zb);
-            if (mv.L && !mv.mask[b] && mv.agg1[b] != MAS_NONE) red_add_v4(mv.R + mv.agg1[b], rb.x, rb.y, rb.z);
+            if (mv.L && !mv.mask[b]) agg_b = mv.agg1[b];
             rz += rb.x * zb.x + rb.y * zb.y + rb.z * zb.z;
             err += fabsf(rb.x) + fabsf(rb.y) + fabsf(rb.z);
+        }
+        if (mv.L) { // restriction to the level-1 aggregates (b < hi_pad is warp-uniform: stride is a multiple of 32)
+            mas_restrict_warp(mv.R, agg_a, ra.x, ra.y, ra.z);
+            if (b < hi_pad) mas_restrict_warp(mv.R, agg_b, rb.x, rb.y, rb.z);
         }
     }
     block_accumulate2(rz, err, &sc->rzerr[par ^ 1][0], &sc->rzerr[par ^ 1][1]);
