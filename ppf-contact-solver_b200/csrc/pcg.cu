@@ -1085,14 +1085,19 @@ __global__ void __launch_bounds__(256) k_mas_correct(MasView v, CgScalars *sc, i
 // the last lane of each run issues one 16-byte reduction.  All 32 lanes must call it (agg = MAS_NONE: nothing to add).
 __device__ __forceinline__ void mas_restrict_warp(float4 *R, unsigned agg, float rx, float ry, float rz) {
     const unsigned lane = threadIdx.x & 31;
+    // runs of equal aggregates among ADJACENT lanes; the same aggregate may come back later in the warp (rows of two
+    // neighbouring grid lines interleave in the frontend's numbering: A B A B ...), so a run is delimited by head flags and
+    // not by comparing keys at a distance
+    const unsigned prev = __shfl_up_sync(0xffffffffu, agg, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != agg);
+    const unsigned start = 31u - __clz(heads & (0xFFFFFFFFu >> (31u - lane))); // first lane of this lane's run
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const unsigned ga = __shfl_up_sync(0xffffffffu, agg, o);
         const float t0 = __shfl_up_sync(0xffffffffu, rx, o), t1 = __shfl_up_sync(0xffffffffu, ry, o), t2 = __shfl_up_sync(0xffffffffu, rz, o);
-        if (lane >= (unsigned)o && ga == agg) { rx += t0; ry += t1; rz += t2; }
+        if (lane >= start + (unsigned)o) { rx += t0; ry += t1; rz += t2; }
     }
-    const unsigned next = __shfl_down_sync(0xffffffffu, agg, 1);
-    if (agg != MAS_NONE && (lane == 31 || next != agg)) red_add_v4(R + agg, rx, ry, rz);
+    const bool last = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    if (agg != MAS_NONE && last) red_add_v4(R + agg, rx, ry, rz);
 }
 
 // setup with the multilevel preconditioner, first half: r = b - A x0, z0 = Pinv r, restriction, r.z0 and |r|_1
