@@ -32,13 +32,16 @@ extern Dist g_dist;
 // read into their p arrays and the last CTA raises / awaits epoch flags.  NCCL remains for the
 // once-per-solve operations and as the fallback (PPF_B200_DIST_NCCL=1 or no peer mapping: all-gather of p).
 constexpr int PPF_MAX_RANKS = 8;
-struct Mail { double v[2]; unsigned long long epoch; unsigned long long pad; };
+// A mailbox carries two doubles as FOUR 8-byte words, each = (32 bits of payload | 32-bit epoch): an aligned 8-byte store is
+// a single transaction on NVLink, so every word proves its own validity and neither side needs a fence (the scheme of NCCL's
+// LL protocol).  w[0], w[1] = low / high half of v[0]; w[2], w[3] = of v[1].
+struct Mail { unsigned long long w[4]; };
 struct CommBuf {
     Mail mail[2][2][PPF_MAX_RANKS];      // [slot: 0 p.Ap|abs, 1 r.z|err][parity][source rank]
     unsigned long long halo_flag[PPF_MAX_RANKS]; // [q]: epoch of the last push of p rows received from rank q
     unsigned long long red_epoch[2];     // local counters (never reset, identical on all ranks by construction)
     unsigned long long halo_epoch;
-    unsigned long long sum_ready[2];     // local: epoch of the last all-rank sum that CTA 0 of the consuming kernel has formed (pcg.cu)
+    Mail sum_ll[2];                      // local: the all-rank sum CTA 0 of the consuming kernel has formed, handed to the other CTAs the same way
 };
 struct PeerView {
     CommBuf *comm[PPF_MAX_RANKS];        // comm[r]: rank r's mailbox buffer mapped into this process (own buffer at [rank])
