@@ -53,6 +53,10 @@ int ppfh_set_param_flag(Session *s, const char *name, int value) {
     if (std::string(name) == "precond") { s->b.param.precond = value ? PPF_PRECOND_SCHWARZ : PPF_PRECOND_BLOCKJACOBI; return 1; } // 0 block-Jacobi, 1 Schwarz (data.hpp:83)
     return 0;
 }
+// the DataSet's inv_rest2x2 (4 floats per face) -- starting point of an update_rest_shape in the tests
+void ppfh_inv_rest(Session *s, float *out) {
+    if (!s->b.inv_rest2x2.empty()) memcpy(out, s->b.inv_rest2x2.data(), s->b.inv_rest2x2.size() * sizeof(s->b.inv_rest2x2[0]));
+}
 int ppfh_load_state(Session *s, const char *path) {
     double t; float prev_dt;
     std::vector<float> c, p;

@@ -231,6 +231,48 @@ class Session:
         frag = self._sym("oracle_fetch_fragile", *fetch_t)
         return total, [self._pair_list(fetch, k) for k in range(4)], [self._pair_list(frag, k) for k in range(4)]
 
+    # ---- the remaining per-step entry points of the ABI (main.cu:2079-2228), called the way backend.rs calls them ----
+    def override_velocity(self, indices, v, dt):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        fn = self._sym("override_velocity", None, ctypes.c_void_p, ctypes.c_uint, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float)
+        fn(idx.ctypes.data_as(ctypes.c_void_p), idx.size, float(v[0]), float(v[1]), float(v[2]), float(dt))
+
+    def override_angular_velocity(self, indices, omega, center, dt):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        fn = self._sym("override_angular_velocity", None, ctypes.c_void_p, ctypes.c_uint, *([ctypes.c_float] * 7))
+        fn(idx.ctypes.data_as(ctypes.c_void_p), idx.size, float(omega[0]), float(omega[1]), float(omega[2]), float(center[0]), float(center[1]),
+           float(center[2]), float(dt))
+
+    def gather_current_positions(self, indices):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        out = np.zeros((idx.size, 3), np.float32)
+        fn = self._sym("gather_current_positions", None, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p)
+        fn(idx.ctypes.data_as(ctypes.c_void_p), idx.size, out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def inv_rest(self):
+        """the DataSet's inv_rest2x2 (n_face x 4 floats, column-major 2x2) as the host holds it"""
+        out = np.zeros((self.n_face, 4), np.float32)
+        self.h.ppfh_inv_rest(self.p, out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    def update_rest_shape(self, inv_rest2x2=None, exclude_face=None):
+        class Vec(ctypes.Structure):  # K/vec/vec.hpp:79-83 {T* data; u32 size; u32 allocated}
+            _fields_ = [("data", ctypes.c_void_p), ("size", ctypes.c_uint), ("allocated", ctypes.c_uint)]
+
+        class Upd(ctypes.Structure):  # PpfRestShapeUpdate, 64 bytes
+            _fields_ = [("inv_rest2x2", Vec), ("inv_rest3x3", Vec), ("exclude_face", Vec), ("exclude_tet", Vec)]
+        u = Upd()
+        keep = []
+        if inv_rest2x2 is not None:
+            a = np.ascontiguousarray(inv_rest2x2, np.float32); keep.append(a)
+            u.inv_rest2x2 = Vec(a.ctypes.data, a.shape[0], a.shape[0])
+        if exclude_face is not None:
+            b = np.ascontiguousarray(exclude_face, np.uint8); keep.append(b)
+            u.exclude_face = Vec(b.ctypes.data, b.size, b.size)
+        fn = self._sym("update_rest_shape", None, ctypes.c_void_p)
+        fn(ctypes.byref(u))
+
     def intersection_records(self):
         """fetch_intersection_records (main.cu:2341) of the last intersection check: list of
         (type, elem0, elem1, positions[(n0 + n1) x 3]) sorted by (type, elem0, elem1) -- the slot order is atomics order."""

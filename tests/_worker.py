@@ -55,6 +55,8 @@ def run(job):
     if job.get("detect") == "state":
         x0, _ = s.fetch()
         _pairs(s, x0, res, "state", job.get("detect_twice"))
+    if job.get("abi_calls"):  # the per-step entry points a host may call between steps (main.cu:2079-2228), before the steps of this job
+        _abi_calls(s, job["abi_calls"], res)
     oks, walls = [], []
     for _ in range(job.get("steps", 1)):
         ok, ms = s.step()
@@ -82,6 +84,28 @@ def run(job):
         res["fix_index"], res["fix_target"] = s.fix_targets()
     np.savez(os.path.join(out, "result.npz"), **res)
     return res
+
+
+def _abi_calls(s, calls, res):
+    """calls: list of [name, args...] -- override_velocity [idx, v, dt], override_angular_velocity [idx, omega, center, dt],
+    gather [idx] (result stored), update_rest_shape [scale or None, exclude list or None]; the state right after is recorded"""
+    for k, c in enumerate(calls):
+        name = c[0]
+        if name == "override_velocity":
+            s.override_velocity(c[1], c[2], c[3])
+        elif name == "override_angular_velocity":
+            s.override_angular_velocity(c[1], c[2], c[3], c[4])
+        elif name == "gather":
+            res["gather%d" % k] = s.gather_current_positions(c[1])
+        elif name == "update_rest_shape":
+            inv = s.inv_rest() * np.float32(c[1]) if c[1] is not None else None
+            ex = None
+            if c[2] is not None:
+                ex = np.zeros(s.n_face, np.uint8); ex[np.asarray(c[2], np.int64)] = 1
+            s.update_rest_shape(inv, ex)
+        else:
+            raise ValueError(name)
+    res["after_calls_curr"], res["after_calls_prev"] = s.fetch()
 
 
 def read_pair_dump(path):
