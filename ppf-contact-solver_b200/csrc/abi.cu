@@ -157,7 +157,15 @@ void upload_dataset(State &s) {
         refuse("B200 backend: slot-replay tables are required (stitch_hess_slots)");
     if (prm.disable_pin_dof_removal) refuse("B200 backend: barrier-held fix pins (disable_pin_dof_removal) are not implemented");
     if (d.translation_lock.size) refuse("B200 backend: translation/rotation locks are not implemented");
-    if (d.statistics_contact_count.size) refuse("B200 backend: per-object contact statistics (statistics_contact_count) are not implemented");
+    // per-object contact statistics (S/statistics.rs configure_dataset): optional; every array is empty without the session input
+    s.n_stat_obj = d.statistics_contact_count.size;
+    if (s.n_stat_obj) {
+        if (d.statistics_object_index.size != nv) fatal(4, "statistics_object_index has %u entries for %u vertices", d.statistics_object_index.size, nv);
+        s.stat_obj.upload(d.statistics_object_index.data, nv, q);
+        if (d.statistics_static_object_index.size) s.stat_sobj.upload(d.statistics_static_object_index.data, d.statistics_static_object_index.size, q);
+        s.stat_count.reserve(s.n_stat_obj);
+        s.stat_count.zero(s.n_stat_obj, q);
+    }
     for (unsigned i = 0; i < d.grain_inv_inertia.size; ++i)
         if (d.grain_inv_inertia.data[i] > 0.0f) refuse("B200 backend: SAND grains are not implemented");
     if (nf != d.shell_face_count || s.nsv != nv) refuse("B200 backend: solid (tet) surfaces and interior vertices are not implemented (shell faces and rods only)");
@@ -529,6 +537,8 @@ PPF_EXPORT void fetch(void) {
     CUDA_OK(cudaStreamSynchronize(q));
     k_unpack4<<<div_up(nv, 256), 256, 0, q>>>(s.prev.p, s.dx.p, nv);
     CUDA_OK(cudaMemcpyAsync(s.host.vertex.prev.data, s.dx.p, size_t(12) * nv, cudaMemcpyDeviceToHost, q));
+    if (s.n_stat_obj) // main.cu:1933-1936: the per-object contact counts of the last contact assembly
+        CUDA_OK(cudaMemcpyAsync(s.host.statistics_contact_count.data, s.stat_count.p, sizeof(unsigned) * s.n_stat_obj, cudaMemcpyDeviceToHost, q));
     CUDA_OK(cudaStreamSynchronize(q));
     LAUNCH_COUNT(2);
 }

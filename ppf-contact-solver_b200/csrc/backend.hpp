@@ -200,6 +200,9 @@ struct State {
     std::vector<unsigned> h_cw_dmap, h_cw_counts;
     std::vector<float> h_cw_windows;
     bool has_cw = false, cw_uploaded = false;
+    // per-object contact statistics (DataSet.statistics_*; recorded per contact assembly, copied back by fetch())
+    DBuf<unsigned> stat_obj, stat_sobj, stat_count;   // object of every vertex / of every static-mesh vertex (0xFFFFFFFF = none), contacts per object
+    unsigned n_stat_obj = 0;
     std::vector<PpfIntersectionRecord> h_isect;
     unsigned h_isect_count = 0;
 

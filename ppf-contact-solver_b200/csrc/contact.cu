@@ -241,6 +241,23 @@ struct Ctx {
     float *force;
 };
 
+// per-object contact statistics (contact.cu:379-430 of the reference): a contact between objects a and b counts once for each of
+// them, once in total when both sides belong to the same object; 0xFFFFFFFF = the vertex belongs to no object
+struct StatView {
+    const unsigned *obj, *sobj; // per vertex / per static-mesh vertex
+    unsigned *count;            // per object, null = statistics off
+    unsigned n_obj;
+};
+__device__ __forceinline__ void stat_record(const StatView &st, unsigned oa, unsigned ob) {
+    if (oa != 0xFFFFFFFFu && oa < st.n_obj) atomicAdd(st.count + oa, 1u);
+    if (ob != 0xFFFFFFFFu && ob != oa && ob < st.n_obj) atomicAdd(st.count + ob, 1u);
+}
+static StatView make_stat_view(State &s) {
+    StatView st;
+    st.obj = s.stat_obj.p; st.sobj = s.stat_sobj.p; st.count = s.n_stat_obj ? s.stat_count.p : nullptr; st.n_obj = s.n_stat_obj;
+    return st;
+}
+
 template <int N> struct Prox {
     unsigned idx[N];
     float w[N];
@@ -421,6 +438,19 @@ template <int N> __device__ __forceinline__ unsigned emit_keys(const Ctx &c, con
             if (fixed_find(c, i, j) == 0xFFFFFFFFu) keys[n++] = ((unsigned long long)i << shift) | j;
         }
     return n;
+}
+
+// one count per accepted pair, attributed through the vertices the reference names (contact.cu:617, 722, 800, 879)
+template <int KIND> __global__ void __launch_bounds__(256) k_stats(Ctx c, StatView st, const uint2 *pairs, unsigned n) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint2 pr = pairs[t];
+    unsigned va, vb;
+    if (KIND == 0) { va = pr.x; vb = c.face[pr.y].x; }
+    else if (KIND == 1) { va = pr.x; vb = c.edge[pr.y].x; }
+    else if (KIND == 2) { va = pr.x; vb = pr.y; }
+    else { va = c.edge[pr.x].x; vb = c.edge[pr.y].x; }
+    stat_record(st, st.obj[va], st.obj[vb]);
 }
 
 template <int KIND> __global__ void __launch_bounds__(256) k_keys(Ctx c, const uint2 *pairs, unsigned n, unsigned long long *out, unsigned *counter, unsigned shift) {
@@ -696,6 +726,15 @@ unsigned assemble_contact(State &s, float dt, const PpfParamSet &prm, unsigned &
     // ---- detect ----
     unsigned hc[4];
     const unsigned total = detect_contacts(s, prm, hc);
+    if (s.n_stat_obj) { // the counts were reset by the step (main.cu:825); collision mesh and colliders add to them afterwards
+        const StatView st = make_stat_view(s);
+        const Ctx cs = make_ctx(s, prm);
+        if (hc[0]) k_stats<0><<<div_up(hc[0], 256), 256, 0, q>>>(cs, st, s.pairs[0].pairs.p, hc[0]);
+        if (hc[1]) k_stats<1><<<div_up(hc[1], 256), 256, 0, q>>>(cs, st, s.pairs[1].pairs.p, hc[1]);
+        if (hc[2]) k_stats<2><<<div_up(hc[2], 256), 256, 0, q>>>(cs, st, s.pairs[2].pairs.p, hc[2]);
+        if (hc[3]) k_stats<3><<<div_up(hc[3], 256), 256, 0, q>>>(cs, st, s.pairs[3].pairs.p, hc[3]);
+        LAUNCH_COUNT(4);
+    }
     Ctx c = make_ctx(s, prm);
     const auto t1 = now();
 
@@ -917,7 +956,7 @@ __global__ void __launch_bounds__(128) k_collider(unsigned nsv, const float4 *__
                                                   const float *__restrict__ fx_el, const unsigned *__restrict__ diag_slot,
                                                   const PpfSphere *__restrict__ spheres, unsigned n_sphere, const PpfFloor *__restrict__ floors,
                                                   unsigned n_floor, int friction_mode, float friction_eps, float constraint_tol,
-                                                  float *__restrict__ force, float *__restrict__ fx_val, unsigned *counter) {
+                                                  float *__restrict__ force, float *__restrict__ fx_val, unsigned *counter, StatView stat) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned count = 0;
     if (i < nsv && fix_index[i] == 0) {
@@ -931,6 +970,7 @@ __global__ void __launch_bounds__(128) k_collider(unsigned nsv, const float4 *__
             ColliderOut o;
             collider_vertex(x, x - ld3c(curr, i), cp.w, cp.z, Hii, spheres, n_sphere, floors, n_floor, friction_mode, friction_eps, constraint_tol, o);
             count = o.count;
+            if (count && stat.count && stat.obj[i] != 0xFFFFFFFFu && stat.obj[i] < stat.n_obj) atomicAdd(stat.count + stat.obj[i], count); // record_analytic_contact per contact
             if (count) { // one thread owns vertex i in this kernel, but the contact kernels may still be adding to it
                 float *fo = force + size_t(3) * i;
                 if (o.f.x) atomicAdd(fo + 0, o.f.x);
@@ -970,7 +1010,7 @@ unsigned assemble_colliders(State &s, const PpfParamSet &prm) {
     unsigned *cnt = s.counters.p + 30;
     CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), q));
     k_collider<<<div_up(s.nsv, 128), 128, 0, q>>>(s.nsv, s.eval_x.p, s.curr.p, s.vcp.p, s.fix_index.p, s.fx_el.p, s.fx_diag_slot.p, s.spheres.p, s.nsphere,
-                                                  s.floors.p, s.nfloor, (int)prm.friction_mode, prm.friction_eps, prm.constraint_tol, s.force.p, s.fx_val.p, cnt);
+                                                  s.floors.p, s.nfloor, (int)prm.friction_mode, prm.friction_eps, prm.constraint_tol, s.force.p, s.fx_val.p, cnt, make_stat_view(s));
     LAUNCH_COUNT(1);
     unsigned h = 0;
     CUDA_OK(cudaMemcpyAsync(&h, cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, q));
@@ -1013,9 +1053,11 @@ struct CmArgs {
     const unsigned *fix_index;
     const unsigned char *active; // collision windows (see BpArgs)
     unsigned *counter;           // [0] contact count, [1] traversal error
+    StatView stat;               // per-object contact statistics (count == null: off)
 };
 static CmArgs make_cm_args(State &s, unsigned *counter) {
     CmArgs A;
+    A.stat = make_stat_view(s);
     A.sface = view_of(s.cm_bvh_face); A.sedge = view_of(s.cm_bvh_edge); A.svert = view_of(s.cm_bvh_vert);
     A.sx = s.cm_x.p; A.svcp = s.cm_vcp.p; A.secp = s.cm_ecp.p; A.sfcp = s.cm_fcp.p; A.sfaces = s.cm_face.p; A.sedges = s.cm_edge.p;
     A.fix_index = s.fix_index.p;
@@ -1081,6 +1123,7 @@ __global__ void __launch_bounds__(128) k_cm_vertex(Ctx c, CmArgs A, unsigned nsv
                                combine_friction(cp.z, sp.z, c.friction_mode), cp.w, Hii, c.friction_eps, o)) return;
         const unsigned idx[1] = {i};
         cm_scatter<1>(c, idx, o);
+        if (A.stat.count) stat_record(A.stat, A.stat.obj[i], A.stat.sobj ? A.stat.sobj[f.x] : 0xFFFFFFFFu); // contact.cu:956
         ++count;
     });
     cm_count(A, count, ok);
@@ -1113,6 +1156,7 @@ __global__ void __launch_bounds__(128) k_cm_edge(Ctx c, CmArgs A, unsigned ne) {
         if (!cmesh_edge_edge(P, Ps, ld3c(A.sx, se.x), ld3c(A.sx, se.y), cp.y + sp.y, 0.5f * (cp.x + sp.x), combine_friction(cp.z, sp.z, c.friction_mode),
                              vmass, B, c.friction_eps, o)) return;
         cm_scatter<2>(c, idx, o);
+        if (A.stat.count) stat_record(A.stat, A.stat.obj[ev.x], A.stat.sobj ? A.stat.sobj[se.x] : 0xFFFFFFFFu); // contact.cu:1146
         ++count;
     });
     cm_count(A, count, ok);
@@ -1144,6 +1188,7 @@ __global__ void __launch_bounds__(128) k_cm_face(Ctx c, CmArgs A, unsigned nf) {
         if (!cmesh_face_vertex(ld3c(A.sx, vi), X, Xs, cp.y + sp.y, 0.5f * (cp.x + sp.x), combine_friction(cp.z, sp.z, c.friction_mode), vmass, B,
                                c.friction_eps, o)) return;
         cm_scatter<3>(c, idx, o);
+        if (A.stat.count) stat_record(A.stat, A.stat.obj[fv.x], A.stat.sobj ? A.stat.sobj[vi] : 0xFFFFFFFFu); // contact.cu:1051
         ++count;
     });
     cm_count(A, count, ok);

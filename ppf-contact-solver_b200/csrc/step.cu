@@ -277,6 +277,7 @@ void step_advance(State &s, PpfStepResult *out) {
         logging.pop();
         unsigned num_contact = 0, max_nnz_row = 0;
         float dyn_consumed = 0.0f;
+        if (s.n_stat_obj) CUDA_OK(cudaMemsetAsync(s.stat_count.p, 0, sizeof(unsigned) * s.n_stat_obj, q)); // main.cu:825
         logging.push("asm contact");
         if (!prm.disable_contact) {
             EvTimer tc(q);

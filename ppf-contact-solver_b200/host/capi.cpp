@@ -53,6 +53,25 @@ int ppfh_set_param_flag(Session *s, const char *name, int value) {
     if (std::string(name) == "precond") { s->b.param.precond = value ? PPF_PRECOND_SCHWARZ : PPF_PRECOND_BLOCKJACOBI; return 1; } // 0 block-Jacobi, 1 Schwarz (data.hpp:83)
     return 0;
 }
+// Per-object contact statistics, the way S/statistics.rs configure_dataset wires them from a session's statistics input: one
+// object per scene object (vert_dmap), the static collision mesh as one more object; call before ppfh_init.  Returns the
+// number of objects.  ppfh_statistics copies the counts fetch() brought back.
+unsigned ppfh_enable_statistics(Session *s) {
+    Built &b = s->b;
+    const unsigned n_dyn = (unsigned)b.spec.objects.size();
+    const unsigned n_static = b.dataset.constraint.mesh.vertex.size;
+    b.stat_obj = b.vert_dmap;
+    b.stat_sobj.assign(n_static, n_dyn);
+    b.stat_count.assign(n_dyn + (n_static ? 1u : 0u), 0u);
+    b.dataset.statistics_object_index.data = b.stat_obj.data(); b.dataset.statistics_object_index.size = b.dataset.statistics_object_index.allocated = (unsigned)b.stat_obj.size();
+    b.dataset.statistics_static_object_index.data = b.stat_sobj.data(); b.dataset.statistics_static_object_index.size = b.dataset.statistics_static_object_index.allocated = (unsigned)b.stat_sobj.size();
+    b.dataset.statistics_contact_count.data = b.stat_count.data(); b.dataset.statistics_contact_count.size = b.dataset.statistics_contact_count.allocated = (unsigned)b.stat_count.size();
+    return (unsigned)b.stat_count.size();
+}
+unsigned ppfh_statistics(Session *s, unsigned *out) {
+    if (out && !s->b.stat_count.empty()) memcpy(out, s->b.stat_count.data(), s->b.stat_count.size() * sizeof(unsigned));
+    return (unsigned)s->b.stat_count.size();
+}
 // the DataSet's inv_rest2x2 (4 floats per face) -- starting point of an update_rest_shape in the tests
 void ppfh_inv_rest(Session *s, float *out) {
     if (!s->b.inv_rest2x2.empty()) memcpy(out, s->b.inv_rest2x2.data(), s->b.inv_rest2x2.size() * sizeof(s->b.inv_rest2x2[0]));

@@ -169,6 +169,8 @@ struct Built {
     std::vector<char> type_face, type_vertex, type_hinge;
     // zero-filled per-vertex grain arrays (builder.rs:748-762) etc.
     std::vector<PpfVec3f> zero3; std::vector<float> zero1; std::vector<PpfMat3x3f> zero9;
+    // per-object contact statistics (S/statistics.rs configure_dataset): filled by enable_statistics(), empty otherwise
+    std::vector<unsigned> stat_obj, stat_sobj, stat_count;
     std::vector<unsigned> lock_index;
     // flattened VecVec storage
     OwnedVecVec<unsigned> f_v_face, f_v_hinge, f_v_edge, f_v_rod, f_hinge_face, f_edge_face, f_fixed;

@@ -78,7 +78,7 @@ def host():
 class Session:
     """One scene + one backend library (one per process: the backends keep global state)."""
 
-    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None, allow_init_failure=False, param_flags=None):
+    def __init__(self, scene, n=0, lib=LIB_OURS, log_dir=None, state=None, cg_tol=0.0, cg_max_iter=0, shard=None, allow_init_failure=False, param_flags=None, statistics=False):
         """shard = (rank, world, nccl_id_bytes[, allgather]): row-shard the PCG solve of this scene over `world`
         GPUs (every rank builds the same scene; see csrc/dist.hpp).  `allgather(bytes) -> [bytes per rank]` is
         the launcher's object all-gather; with it the ranks also exchange CUDA IPC handles and the per-iteration
@@ -97,6 +97,7 @@ class Session:
         for name, value in (param_flags or {}).items():
             if not self.h.ppfh_set_param_flag(self.p, name.encode(), ctypes.c_int(int(value))):
                 raise RuntimeError("unknown ParamSet flag %s" % name)
+        self.n_stat_objects = int(self.h.ppfh_enable_statistics(self.p)) if statistics else 0
         if state is not None and not self.h.ppfh_load_state(self.p, state.encode()):
             raise RuntimeError("cannot load state %s" % state)
         if not self.h.ppfh_open(self.p, lib.encode()):
@@ -272,6 +273,14 @@ class Session:
             u.exclude_face = Vec(b.ctypes.data, b.size, b.size)
         fn = self._sym("update_rest_shape", None, ctypes.c_void_p)
         fn(ctypes.byref(u))
+
+    def statistics(self):
+        """per-object contact counts of the last contact assembly (DataSet.statistics_contact_count, brought back by fetch())"""
+        self.fetch(want=False)
+        out = np.zeros(self.n_stat_objects, np.uint32)
+        if self.n_stat_objects:
+            self.h.ppfh_statistics(self.p, out.ctypes.data_as(ctypes.c_void_p))
+        return out
 
     def intersection_records(self):
         """fetch_intersection_records (main.cu:2341) of the last intersection check: list of

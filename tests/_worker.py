@@ -43,7 +43,7 @@ def run(job):
     else:
         os.environ.pop("PPF_DUMP_PAIRS_DIR", None)
     s = ppf_b200.Session(job["scene"], n=job.get("n", 0), lib=lib, log_dir=os.path.join(out, "logs"), state=job.get("state"),
-                         allow_init_failure=bool(job.get("allow_init_failure")), param_flags=job.get("param_flags"))
+                         allow_init_failure=bool(job.get("allow_init_failure")), param_flags=job.get("param_flags"), statistics=bool(job.get("statistics")))
     res = {"counts": np.array([s.n_vert, s.n_face, s.n_edge, s.n_hinge, s.n_fix], np.int64)}
     if job.get("allow_init_failure"):   # positive path of the intersection check: initialize() may refuse the start state
         rec = s.intersection_records()
@@ -77,6 +77,8 @@ def run(job):
         res["stats_json"] = np.array(json.dumps(st))
     if job.get("detect") == "final":
         _pairs(s, curr, res, "final", job.get("detect_twice"))
+    if job.get("statistics"):
+        res["statistics"] = s.statistics()
     if job.get("dump_pairs"):
         for k, p in enumerate(read_pair_dump(os.path.join(out, "pairs_0.bin"))):
             res["ref_pairs%d" % k] = p
