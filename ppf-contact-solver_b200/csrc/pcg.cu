@@ -116,7 +116,8 @@ static size_t round_cap(size_t n) { return (n + SPMV_CHUNK - 1) / SPMV_CHUNK * S
 //   PPF_B200_L2_PERSIST = y (default) | yp (window over p and y, hit ratio = set-aside / window) | 0 (off, for A/B timing)
 static void pcg_l2_policy(State &s) {
     if (const char *e = getenv("PPF_B200_L2_STREAM")) P.evict_first = e[0] != '0';
-    if (const char *e = getenv("PPF_B200_SPMV")) P.spmv_variant = strcmp(e, "direct1") == 0 ? 1 : (strcmp(e, "direct2") == 0 ? 2 : 0);
+    if (const char *e = getenv("PPF_B200_SPMV"))
+        P.spmv_variant = strcmp(e, "direct1") == 0 ? 1 : (strcmp(e, "direct2") == 0 ? 2 : (strcmp(e, "cpasync2") == 0 ? 3 : (strcmp(e, "cpasync3") == 0 ? 4 : 0)));
     const char *mode = getenv("PPF_B200_L2_PERSIST");
     if (mode && mode[0] == '0') return;
     const bool both = mode && strcmp(mode, "yp") == 0;
@@ -795,6 +796,108 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
             publish_partial(pv, sc, 0, par);
         }
     }
+}
+
+// ---- the staged product with the stages filled by cp.async (LDGSTS) instead of bulk copies (one rank; A/B variant) ----
+// ncu on k_spmv_staged: the L1 data pipe is the busiest unit (80 % of its wavefront peak) and ~22 of its ~75 wavefronts per 32
+// blocks are the bulk copies writing shared memory at 64 B per wavefront.  Sixteen-byte cp.async writes a warp's 512 B as four
+// 128-byte wavefronts -- half the count -- at the price of issue slots in the compute warps (6 instructions per thread per chunk).
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, unsigned long long pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int STAGES>
+__global__ void __launch_bounds__(SPMV_T, 4) k_spmv_cpasync(unsigned k_begin, unsigned k_first, unsigned nnz, const unsigned *__restrict__ row,
+                                                           const unsigned *__restrict__ col, const float *__restrict__ val, size_t plane,
+                                                           const float4 *__restrict__ p, float4 *__restrict__ y, CgScalars *sc, int with_dots, int evict_first) {
+    if (with_dots && sc->status != ST_RUNNING) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const unsigned c_begin = k_begin / SPMV_CHUNK;
+    const unsigned n_list = (nnz + SPMV_CHUNK - 1) / SPMV_CHUNK - c_begin;
+    const unsigned long long pol = l2_stream_policy(evict_first);
+    constexpr unsigned VEC_PER_ARRAY = SPMV_CHUNK / 4;                 // 16-byte pieces per array per chunk
+    constexpr unsigned VEC_PER_STAGE = SPMV_ARRAYS * VEC_PER_ARRAY;    // 1408
+    auto fill = [&](int st, unsigned ci) {
+        unsigned *dst = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
+        const size_t base = size_t(c_begin + ci) * SPMV_CHUNK;
+#pragma unroll
+        for (unsigned v = tid; v < VEC_PER_STAGE; v += SPMV_T) {
+            const unsigned arr = v / VEC_PER_ARRAY, off = (v % VEC_PER_ARRAY) * 4;
+            const void *src = arr == 0 ? (const void *)(row + base + off) : (arr == 1 ? (const void *)(col + base + off) : (const void *)(val + size_t(arr - 2) * plane + base + off));
+            cp_async16(dst + arr * SPMV_CHUNK + off, src, pol);
+        }
+    };
+    for (int st = 0; st < STAGES; ++st) {
+        const unsigned c = blockIdx.x + unsigned(st) * gridDim.x;
+        if (c < n_list) fill(st, c);
+        cp_async_commit(); // one group per stage slot, empty or not: the wait below counts groups
+    }
+    float dot = 0.f, absdot = 0.f;
+    unsigned it = 0;
+    for (unsigned chunk = blockIdx.x; chunk < n_list; chunk += gridDim.x, ++it) {
+        const int st = int(it % STAGES);
+        cp_async_wait<STAGES - 1>();
+        __syncthreads();
+        const unsigned *sm = stage_base + size_t(st) * (SPMV_ARRAYS * SPMV_CHUNK);
+        unsigned a[SPMV_U], b[SPMV_U];
+        float h[SPMV_U][9];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            const unsigned j = u * SPMV_T + tid;
+            a[u] = sm[j];
+            b[u] = sm[SPMV_CHUNK + j];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) h[u][e] = __uint_as_float(sm[(2 + e) * SPMV_CHUNK + j]);
+        }
+        __syncthreads(); // every thread holds its blocks in registers: the stage can be refilled
+        {
+            const unsigned nc = chunk + unsigned(STAGES) * gridDim.x;
+            if (nc < n_list) fill(st, nc);
+            cp_async_commit();
+        }
+        const size_t k0 = size_t(c_begin + chunk) * SPMV_CHUNK;
+        bool on[SPMV_U];
+        float4 pa[SPMV_U], pb[SPMV_U];
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            on[u] = k0 + u * SPMV_T + tid < nnz && k0 + u * SPMV_T + tid >= k_first;
+            if (!on[u]) { a[u] = 0xFFFFFFFFu; b[u] = 0; }
+            pa[u] = on[u] ? p[a[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            pb[u] = on[u] ? p[b[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < SPMV_U; ++u) {
+            const float *hh = h[u];
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            if (on[u]) {
+                red_add_v4(y + b[u], hh[0] * pa[u].x + hh[1] * pa[u].y + hh[2] * pa[u].z, hh[3] * pa[u].x + hh[4] * pa[u].y + hh[5] * pa[u].z,
+                           hh[6] * pa[u].x + hh[7] * pa[u].y + hh[8] * pa[u].z);
+                s0 = hh[0] * pb[u].x + hh[3] * pb[u].y + hh[6] * pb[u].z;
+                s1 = hh[1] * pb[u].x + hh[4] * pb[u].y + hh[7] * pb[u].z;
+                s2 = hh[2] * pb[u].x + hh[5] * pb[u].y + hh[8] * pb[u].z;
+                const float term = 2.0f * (pa[u].x * s0 + pa[u].y * s1 + pa[u].z * s2);
+                dot += term;
+                absdot += fabsf(term);
+            }
+            const unsigned ra_self = a[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned ra = __shfl_up_sync(0xffffffffu, ra_self, o);
+                const float t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+                if (lane >= (unsigned)o && ra == ra_self) { s0 += t0; s1 += t1; s2 += t2; }
+            }
+            const unsigned next = __shfl_down_sync(0xffffffffu, ra_self, 1);
+            if (on[u] && (lane == 31 || next != ra_self)) red_add_v4(y + ra_self, s0, s1, s2);
+        }
+    }
+    cp_async_wait<0>();
+    if (!with_dots) return;
+    const int par = sc->iter & 1;
+    block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
 }
 
 __device__ __forceinline__ float4 sym6_mul(const float *__restrict__ M, size_t n, size_t i, const float4 v) {
@@ -1797,6 +1900,26 @@ static void launch_spmv(State &s, const float4 *p, float4 *y, int with_dots) {
         return;
     }
     if (g_dist.on()) { launch_spmv_chunks(s, p, y, with_dots, with_dots && R.push ? 1 : 0); return; }
+    if (P.spmv_variant >= 3) { // one rank: stages filled by cp.async (PPF_B200_SPMV=cpasync2|cpasync3)
+        const unsigned k_begin = R.kf_first / SPMV_CHUNK * SPMV_CHUNK;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_OK(cudaFuncSetAttribute(k_spmv_cpasync<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SPMV_STAGE_BYTES)));
+            CUDA_OK(cudaFuncSetAttribute(k_spmv_cpasync<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * SPMV_STAGE_BYTES)));
+            attr_set = true;
+        }
+        if (P.spmv_variant == 3) {
+            const unsigned grid = std::min((unsigned)sms * 4u, div_up(R.kf_end - k_begin, SPMV_CHUNK));
+            k_spmv_cpasync<2><<<grid, SPMV_T, 2 * SPMV_STAGE_BYTES, s.stream>>>(k_begin, R.kf_first, R.kf_end, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots, P.evict_first);
+        } else {
+            const unsigned grid = std::min((unsigned)sms * 3u, div_up(R.kf_end - k_begin, SPMV_CHUNK));
+            k_spmv_cpasync<3><<<grid, SPMV_T, 3 * SPMV_STAGE_BYTES, s.stream>>>(k_begin, R.kf_first, R.kf_end, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots, P.evict_first);
+        }
+        return;
+    }
     if (P.spmv_variant) { // one rank: the register-pipelined kernel (PPF_B200_SPMV=direct1|direct2|staged)
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -1914,10 +2037,11 @@ static void pcg_tune(State &s) {
     P.spmv_grid = grid_save;
     {
         const int keep = P.spmv_variant;
-        for (int v : {1, 2}) {
+        for (int v : {1, 2, 3, 4}) {
             P.spmv_variant = v;
             char nm[64];
-            snprintf(nm, sizeof(nm), "spmv register-pipelined U=%d", v);
+            if (v <= 2) snprintf(nm, sizeof(nm), "spmv register-pipelined U=%d", v);
+            else snprintf(nm, sizeof(nm), "spmv cp.async stages=%d", v - 1);
             time_it(nm, 40.0 * nnz + 24.0 * n, [&] { launch_spmv(s, P.p.p, P.y.p, 1); });
         }
         P.spmv_variant = keep;
