@@ -802,8 +802,9 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
 // ncu on k_spmv_staged: the L1 data pipe is the busiest unit (80 % of its wavefront peak) and ~22 of its ~75 wavefronts per 32
 // blocks are the bulk copies writing shared memory at 64 B per wavefront.  Sixteen-byte cp.async writes a warp's 512 B as four
 // 128-byte wavefronts -- half the count -- at the price of issue slots in the compute warps (6 instructions per thread per chunk).
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, unsigned long long pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, unsigned long long pol, int hinted) {
+    if (hinted) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -828,7 +829,7 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_cpasync(unsigned k_begin, un
         for (unsigned v = tid; v < VEC_PER_STAGE; v += SPMV_T) {
             const unsigned arr = v / VEC_PER_ARRAY, off = (v % VEC_PER_ARRAY) * 4;
             const void *src = arr == 0 ? (const void *)(row + base + off) : (arr == 1 ? (const void *)(col + base + off) : (const void *)(val + size_t(arr - 2) * plane + base + off));
-            cp_async16(dst + arr * SPMV_CHUNK + off, src, pol);
+            cp_async16(dst + arr * SPMV_CHUNK + off, src, pol, 0); // the hinted form raised 'illegal instruction' on a B200 when issued from the refill loop
         }
     };
     for (int st = 0; st < STAGES; ++st) {
