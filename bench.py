@@ -124,6 +124,22 @@ def cpu_baseline(scene, n, full_v):
         return dict(base, value=None, sample="oracle run failed: %s" % e)
 
 
+def schwarz_line(args):
+    """The same workload with ParamSet.precond = Schwarz (this backend's multilevel additive aggregation preconditioner, DESIGN.md
+    section 4), run in a child process after the timed region of the headline.  NOT the parity configuration and not part of
+    `value`: it is reported beside it because it is the algorithmic lever on the iteration count."""
+    try:
+        cmd = [sys.executable, os.path.abspath(__file__), "--scene", args.scene, "--n", str(args.n), "--steps", "3", "--warmup", "3", "--precond", "1", "--no-extra"]
+        if args.state:
+            cmd += ["--state", args.state]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        return {"ms_per_step": d["ms_per_step"], "value": d["value"], "unit": d["unit"], "steps": d["steps"], "pcg_iters_per_solve": d["work"]["pcg_iters_per_solve"],
+                "newton_solves": d["work"]["newton_solves"], "note": "precond = Schwarz (own multilevel additive preconditioner); not the parity configuration"}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "note": "schwarz-mode run failed: %s" % e}
+
+
 def cpu_baseline_worker(args):
     import ppf_b200
 
@@ -164,6 +180,7 @@ def main():
     ap.add_argument("--state", default=None, help="start from a saved state (ppf_host --save-every / Session.save_state) instead of t=0, e.g. a contact-rich window")
     ap.add_argument("--precond", type=int, default=0, help="ParamSet.precond: 0 block-Jacobi (the reference's default and the parity configuration), 1 Schwarz")
     ap.add_argument("--replicas", action="store_true", help="N > 1: run N independent scenes (weak scaling) instead of sharding ONE scene's PCG rows over the GPUs")
+    ap.add_argument("--no-extra", action="store_true", help="skip cpu_baseline and the Schwarz-mode line (used by the child run that measures the latter)")
     ap.add_argument("--cpu-baseline-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--full-v", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -344,7 +361,10 @@ def main():
                             "traffic": traffic, "peak_source": how, "us_per_launch": us, "n_row": n_row, "n_off": n_off,
                             "bytes_per_launch": bytes_per_launch}
     if WORLD == 1:
-        line["cpu_baseline"] = cpu_baseline(args.scene, args.n, s.n_vert)
+        if not args.no_extra:
+            line["cpu_baseline"] = cpu_baseline(args.scene, args.n, s.n_vert)
+        if not args.precond and not args.no_extra:
+            line["schwarz_mode"] = schwarz_line(args)
     print(json.dumps(line))
 
 
