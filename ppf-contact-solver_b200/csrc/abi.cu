@@ -14,6 +14,7 @@ namespace ppf {
 State g;
 unsigned long long g_launches = 0;
 unsigned long long g_dev_alloc = 0, g_dev_free = 0;
+cudaStream_t g_alloc_stream = nullptr;
 }
 using namespace ppf;
 
@@ -469,6 +470,18 @@ PPF_EXPORT bool initialize(PpfDataSet *dataset, PpfParamSet *param) {
     if (props.major != 10) fatal(PPF_FATAL_CUDA_DRIVER, "this backend is built for sm_100a (B200) only; found compute capability %d.%d", props.major, props.minor);
     State &s = g;
     if (!s.stream) CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (!g_alloc_stream && !getenv("PPF_B200_PLAIN_MALLOC")) { // stream-ordered growth of the buffers (backend.hpp DBuf); keep freed blocks in the pool
+        int dev_id = 0, pools = 0;
+        cudaGetDevice(&dev_id);
+        cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, dev_id);
+        cudaMemPool_t pool;
+        if (pools && cudaDeviceGetDefaultMemPool(&pool, dev_id) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            g_alloc_stream = s.stream;
+        }
+        cudaGetLastError();
+    }
     s.host = *dataset;
     s.param = param;
     // a second initialize() in the same process starts a new session: nothing of the previous scene may leak into its first step

@@ -12,6 +12,7 @@
 //     tables of the DataSet address it directly); the PCG works on a packed, permuted copy
 //     (pcg.cu) built once per Newton iteration.
 #pragma once
+#include <algorithm>
 #include "../../include/ppf_abi.h"
 #include "vecmath.cuh"
 #include <cuda_runtime.h>
@@ -38,32 +39,53 @@ extern unsigned long long g_dev_alloc, g_dev_free; // cudaMalloc / cudaFree call
 
 inline unsigned div_up(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
 
-// grow-only device buffer (steady state performs no cudaMalloc, like the reference's pool)
+// Grow-only device buffer.  Buffers that follow the contact set (candidates, pairs, keys, the dynamic matrix, the packed block
+// list) keep growing while contacts build up, and plain cudaFree + cudaMalloc of a few hundred MB stalls for milliseconds --
+// once for half a second in the twist scene -- with a device-wide synchronisation each time.  Growth therefore goes through the
+// stream-ordered allocator on the backend stream (cudaMallocAsync from the default pool with an unlimited release threshold:
+// freed blocks are reused, nothing goes back to the driver, no implicit synchronisation) and at least doubles the capacity.
+// `plain` buffers (exported through CUDA IPC to the peer ranks) stay on cudaMalloc.
+extern cudaStream_t g_alloc_stream; // the backend stream once it exists (abi.cu); null: cudaMalloc
 template <class T> struct DBuf {
     T *p = nullptr;
     size_t cap = 0;
-    void reserve(size_t n) {
+    bool plain = false;      // force cudaMalloc (IPC-exported memory)
+    bool from_pool = false;  // p came from cudaMallocAsync
+    static T *alloc(size_t count, bool plain_, bool &pool) {
+        T *q = nullptr;
+        pool = !plain_ && g_alloc_stream != nullptr;
+        if (pool) CUDA_OK(cudaMallocAsync(&q, count * sizeof(T), g_alloc_stream));
+        else CUDA_OK(cudaMalloc(&q, count * sizeof(T)));
+        ++g_dev_alloc;
+        return q;
+    }
+    void release() {
+        if (!p) return;
+        if (from_pool && g_alloc_stream) CUDA_OK(cudaFreeAsync(p, g_alloc_stream));
+        else CUDA_OK(cudaFree(p));
+        ++g_dev_free;
+        p = nullptr;
+    }
+    void reserve(size_t n) { // contents are lost when it grows
         if (n > cap) {
-            if (p) { CUDA_OK(cudaFree(p)); ++g_dev_free; }
-            size_t want = n + n / 4 + 16;
-            CUDA_OK(cudaMalloc(&p, want * sizeof(T)));
-            ++g_dev_alloc;
+            release();
+            const size_t want = std::max(n + n / 4 + 16, cap ? 2 * cap : size_t(0));
+            p = alloc(want, plain, from_pool);
             cap = want;
         }
     }
     void reserve_keep(size_t n, cudaStream_t s) { // grow preserving contents
         if (n > cap) {
-            size_t want = n + n / 2 + 16;
-            T *q = nullptr;
-            CUDA_OK(cudaMalloc(&q, want * sizeof(T)));
-            ++g_dev_alloc;
+            const size_t want = std::max(n + n / 2 + 16, 2 * cap);
+            bool pool = false;
+            T *q = alloc(want, plain, pool);
             if (p) {
                 CUDA_OK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
-                CUDA_OK(cudaStreamSynchronize(s));
-                CUDA_OK(cudaFree(p));
-                ++g_dev_free;
+                if (!(from_pool && g_alloc_stream == s)) CUDA_OK(cudaStreamSynchronize(s)); // a stream-ordered free on s needs no wait
+                release();
             }
             p = q;
+            from_pool = pool;
             cap = want;
         }
     }
@@ -72,7 +94,7 @@ template <class T> struct DBuf {
         if (n) CUDA_OK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s));
     }
     void zero(size_t n, cudaStream_t s) { if (n) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
-    void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void free() { release(); cap = 0; }
 };
 
 struct Bvh {

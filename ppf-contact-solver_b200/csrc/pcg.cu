@@ -73,7 +73,7 @@ struct PackedMatrix {
     DBuf<CgScalars> sc;
     cudaAccessPolicyWindow l2win = {}; // persisting-L2 window over y (and p), also stamped on the graph's kernel nodes
     bool l2win_on = false;
-    unsigned loop_grid = 0;          // k_pcg_loop: co-resident grid (pcg_loop_ready)
+    unsigned loop_grid = 0, loop_grid_max = 0; // k_pcg_loop: grid in use / largest co-resident grid (pcg_loop_ready)
     DBuf<unsigned> loop_bar;         // its grid barrier: [0] arrivals, [1] generation
     int spmv_variant = 0;            // 0 staged (bulk copies through shared memory), 1 / 2 register-pipelined with 1 / 2 blocks per thread
     int evict_first = 1;             // matrix stream loaded with L2::evict_first (PPF_B200_L2_STREAM=0: evict_normal, for A/B timing)
@@ -196,6 +196,7 @@ static void pcg_init(State &s) {
     P.x.reserve(size_t(3) * n); P.r.reserve(size_t(3) * n); P.z.reserve(size_t(3) * n);
     // p and y share ONE allocation (p first: its IPC handle is exported to the peers, dist.cu) so that one L2 access-policy
     // window can cover them; P.p / P.y are non-owning views of it
+    P.py.plain = true; // its IPC handle goes to the peer ranks: plain cudaMalloc memory
     P.py.reserve(2 * P.n_pad);
     P.p.p = P.py.p; P.p.cap = P.n_pad;
     P.y.p = P.py.p + P.n_pad; P.y.cap = P.n_pad;
@@ -2079,8 +2080,11 @@ static bool pcg_loop_ready() {
     per_sm = std::min(per_sm, 4);
     if (const char *e = getenv("PPF_B200_LOOP_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
     P.loop_grid = (unsigned)(sms * per_sm);
+    P.loop_grid_max = P.loop_grid;
+    if (const char *e = getenv("PPF_B200_LOOP_GRID")) P.loop_grid = std::max(1u, std::min(P.loop_grid, (unsigned)atoi(e)));
     P.loop_bar.reserve(4);
-    CUDA_OK(cudaMemset(P.loop_bar.p, 0, 4 * sizeof(unsigned)));
+    CUDA_OK(cudaMemsetAsync(P.loop_bar.p, 0, 4 * sizeof(unsigned), g.stream));
+    CUDA_OK(cudaStreamSynchronize(g.stream));
     log_info("pcg: iteration loop in one cooperative kernel, %u CTAs (%d per SM)", P.loop_grid, per_sm);
     state = 1;
     return true;

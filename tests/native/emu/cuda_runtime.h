@@ -92,3 +92,13 @@ static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { std::memset(p, 0, sizeof(*p)); std::strcpy(p->name, "emulated"); p->major = 10; p->multiProcessorCount = 148; return cudaSuccess; }
+// stream-ordered allocator (backend.hpp DBuf): the host has one heap; memory pools are reported as unsupported so that the
+// emulated build keeps cudaMalloc
+typedef void *cudaMemPool_t;
+enum { cudaDevAttrMemoryPoolsSupported = 115, cudaMemPoolAttrReleaseThreshold = 4 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *p, int) { *p = nullptr; return 1; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMallocAsync(T **p, size_t n, cudaStream_t) { return cudaMalloc(reinterpret_cast<void **>(p), n); }
+static inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
