@@ -55,6 +55,10 @@ struct CgScalars {                 // device-resident control block
     float last_resid;
     unsigned done_counter;         // k_direction's last-CTA detection
     unsigned done_spmv, done_update; // same for the kernels that publish a partial sum to the peers
+    // extent of this solve's block list, read by the SpMV on the device: the captured iteration graph then holds no
+    // per-solve number and survives from one Newton solve to the next (contact scenes change nnz with every assembly;
+    // re-capturing and re-instantiating 96 kernel nodes per solve was up to 15 % of a five-twist solve)
+    unsigned spmv_first, spmv_end, spmv_n_desc;
 };
 
 struct ChunkDesc { unsigned base, first, end; }; // stage blocks [base, base + SPMV_CHUNK), use those in [first, end)
@@ -699,6 +703,10 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
                                                           const float4 *__restrict__ p, float4 *__restrict__ y, CgScalars *sc, int with_dots,
                                                           PeerView pv, int publish, int evict_first) {
     if (with_dots && sc->status != ST_RUNNING) return;
+    if (n_desc == 0xFFFFFFFFu) { // the extent of the list comes from the control block (launches captured in the iteration graph)
+        n_desc = sc->spmv_n_desc; k_first = sc->spmv_first; nnz = sc->spmv_end;
+        k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + size_t(SPMV_STAGES) * SPMV_STAGE_BYTES);
@@ -1876,6 +1884,11 @@ static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const 
         attr_set = true;
     }
     const unsigned k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
+    if (with_dots) { // captured in the iteration graph: extent from the control block, grid independent of it
+        k_spmv_staged<<<P.spmv_grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0xFFFFFFFFu, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
+                                                                    PeerView{}, 0, P.evict_first);
+        return;
+    }
     const unsigned grid = std::min(P.spmv_grid, div_up(k_end - k_begin, SPMV_CHUNK));
     k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0u, k_begin, k_first, k_end, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
                                                          PeerView{}, 0, P.evict_first);
@@ -1887,8 +1900,8 @@ static void launch_spmv_chunks(State &s, const float4 *p, float4 *y, int with_do
         CUDA_OK(cudaFuncSetAttribute(k_spmv_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_SMEM));
         attr_set = true;
     }
-    const unsigned grid = std::max(1u, std::min(P.spmv_grid, R.n_chunks));
-    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
+    const unsigned grid = with_dots ? P.spmv_grid : std::max(1u, std::min(P.spmv_grid, R.n_chunks));
+    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, with_dots ? 0xFFFFFFFFu : R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
                                                          dist_peers(), publish, P.evict_first);
 }
 
@@ -2028,6 +2041,7 @@ static void pcg_tune(State &s) {
     };
     CgScalars h{};
     h.status = ST_RUNNING; h.tol = 0.f; h.max_iter = 1 << 30; h.err0 = 1.0; h.rzerr[0][0] = h.rzerr[1][0] = 1.0; h.acc[0][0] = h.acc[1][0] = 1e30;
+    h.spmv_first = R.kf_first; h.spmv_end = R.kf_end; h.spmv_n_desc = R.n_chunks;
     cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q);
     const unsigned grid_save = P.spmv_grid;
     for (unsigned g : {148u * 2, 148u * 3, 148u * 4}) {
@@ -2132,6 +2146,7 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     init.tol = prm.cg_tol;
     init.max_iter = (int)prm.cg_max_iter;
     init.status = ST_RUNNING;
+    init.spmv_first = R.kf_first; init.spmv_end = R.kf_end; init.spmv_n_desc = R.n_chunks;
     CUDA_OK(cudaMemcpyAsync(P.sc.p, &init, sizeof(init), cudaMemcpyHostToDevice, q));
     k_load<<<gv_full, PCG_BLOCK, 0, q>>>(n, s.force.p, s.dx.p, P.r.p, P.x.p, P.p.p, P.y.p, P.D.p);
     {
@@ -2183,8 +2198,12 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     // batch early-exits (~10 us per iteration), so small systems use short batches and large ones long ones
     const int ITER_PER_GRAPH = n >= 500000u ? 32 : 8; // even: the iteration parity inside a batch is known on the host
     const unsigned nnz = P.nnz_f + P.nnz_d;
-    const unsigned long long part_sig = (unsigned long long)R.kd_first ^ ((unsigned long long)R.kd_end << 20) ^ ((unsigned long long)R.n_foreign << 40) ^
-                                        (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7) ^ (M.on ? 1ull << 62 : 0ull);
+    // what the captured launches depend on: pointers (buffers may be re-allocated when the contact set grows), the exchange mode and
+    // the preconditioner -- NOT the extent of the block list, which the SpMV reads from the control block
+    const unsigned long long part_sig = (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7) ^ (M.on ? 1ull << 62 : 0ull) ^
+                                        ((unsigned long long)(uintptr_t)P.chunks.p << 3) ^ ((unsigned long long)(uintptr_t)P.row.p >> 4) ^
+                                        ((unsigned long long)(uintptr_t)P.mask.p << 11) ^ ((unsigned long long)P.cap << 17) ^ (unsigned long long)R.lo ^ ((unsigned long long)R.hi << 32) ^
+                                        (P.spmv_variant ? (unsigned long long)nnz * 0x9E3779B97F4A7C15ull : 0ull); // the A/B SpMV variants take the extent as a launch parameter
     // ---- PPF_B200_PCG_LOOP=1: the whole loop in one cooperative kernel (k_pcg_loop) instead of the graph of three kernels per
     //      iteration.  Measured on a B200 (profiles/r02_pcg_loop_vs_graph.json): correct, but SLOWER -- a software barrier over
     //      592 CTAs costs more than a kernel boundary inside a CUDA graph (large-twist 274.8 vs 264.9 us per iteration, twist
@@ -2206,7 +2225,7 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
         A.pv = dist_peers(); A.push_mask = p2p_now ? P.mask.p : nullptr;
     }
     if (!use_loop)
-    if (P.exec && (P.graph_iters != ITER_PER_GRAPH || P.graph_nnz != nnz || P.graph_val != (const void *)P.val.p || P.graph_part != part_sig)) { // kernel parameters changed: re-capture
+    if (P.exec && (P.graph_iters != ITER_PER_GRAPH || P.graph_val != (const void *)P.val.p || P.graph_part != part_sig)) { // kernel parameters changed: re-capture
         cudaGraphExecDestroy(P.exec); cudaGraphDestroy(P.graph);
         P.exec = nullptr; P.graph = nullptr;
     }
