@@ -90,6 +90,7 @@ struct PackedMatrix {
     int *h_status = nullptr;         // pinned mirror of {iter, status, last_resid}
     unsigned grid = 0;               // persistent grid size of the vector kernels
     unsigned spmv_grid = 0;          // persistent grid of the staged SpMV (SMs x resident CTAs)
+    unsigned graph_spmv_grid = 0;    // grid of the SpMV launches inside the iteration graph: the list length rounded up to a bucket of 64 chunks
     unsigned rpr = 0;                // rows per rank (dist.hpp)
     unsigned n_foreign_fixed = 0;    // foreign blocks of the fixed segment (see Part)
     DBuf<unsigned> foreign;          // list positions of this rank's foreign blocks: fixed ones first, then this solve's dynamic ones
@@ -714,6 +715,13 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
     const unsigned c_begin = k_begin / SPMV_CHUNK;
     const unsigned n_list = chunks ? n_desc : (nnz + SPMV_CHUNK - 1) / SPMV_CHUNK - c_begin;
     auto desc = [&](unsigned ci) { return chunks ? chunks[ci] : ChunkDesc{(c_begin + ci) * SPMV_CHUNK, k_first, nnz}; };
+    if (blockIdx.x >= n_list) { // nothing to stream (the captured grid is sized for a bucket of list lengths): only count as finished
+        if (with_dots && publish && tid == 0 && atomicAdd(&sc->done_spmv, 1u) == gridDim.x - 1) {
+            sc->done_spmv = 0;
+            publish_partial(pv, sc, 0, sc->iter & 1);
+        }
+        return;
+    }
     if (tid == 0) {
         for (int st = 0; st < SPMV_STAGES; ++st) mbar_init(&full[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1884,8 +1892,8 @@ static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const 
         attr_set = true;
     }
     const unsigned k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
-    if (with_dots) { // captured in the iteration graph: extent from the control block, grid independent of it
-        k_spmv_staged<<<P.spmv_grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0xFFFFFFFFu, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
+    if (with_dots) { // captured in the iteration graph: extent from the control block, grid from the bucket the list length falls in
+        k_spmv_staged<<<P.graph_spmv_grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0xFFFFFFFFu, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
                                                                     PeerView{}, 0, P.evict_first);
         return;
     }
@@ -1900,7 +1908,7 @@ static void launch_spmv_chunks(State &s, const float4 *p, float4 *y, int with_do
         CUDA_OK(cudaFuncSetAttribute(k_spmv_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_SMEM));
         attr_set = true;
     }
-    const unsigned grid = with_dots ? P.spmv_grid : std::max(1u, std::min(P.spmv_grid, R.n_chunks));
+    const unsigned grid = with_dots ? P.graph_spmv_grid : std::max(1u, std::min(P.spmv_grid, R.n_chunks));
     k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, with_dots ? 0xFFFFFFFFu : R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
                                                          dist_peers(), publish, P.evict_first);
 }
@@ -2045,12 +2053,12 @@ static void pcg_tune(State &s) {
     cudaMemcpyAsync(P.sc.p, &h, sizeof(h), cudaMemcpyHostToDevice, q);
     const unsigned grid_save = P.spmv_grid;
     for (unsigned g : {148u * 2, 148u * 3, 148u * 4}) {
-        P.spmv_grid = g;
+        P.spmv_grid = P.graph_spmv_grid = g;
         char nm[64];
         snprintf(nm, sizeof(nm), "spmv staged grid=%u", g);
         time_it(nm, 40.0 * nnz + 24.0 * n, [&] { launch_spmv(s, P.p.p, P.y.p, 1); });
     }
-    P.spmv_grid = grid_save;
+    P.spmv_grid = P.graph_spmv_grid = grid_save;
     {
         const int keep = P.spmv_variant;
         for (int v : {1, 2, 3, 4}) {
@@ -2198,12 +2206,17 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     // batch early-exits (~10 us per iteration), so small systems use short batches and large ones long ones
     const int ITER_PER_GRAPH = n >= 500000u ? 32 : 8; // even: the iteration parity inside a batch is known on the host
     const unsigned nnz = P.nnz_f + P.nnz_d;
+    static const bool spmv_legacy = getenv("PPF_B200_SPMV_LEGACY") != nullptr;
+    {   // a grid larger than the list only adds idle CTAs; one that follows the list exactly would re-capture the graph at every solve
+        const unsigned n_list = g_dist.on() ? R.n_chunks : div_up(R.kf_end - R.kf_first / SPMV_CHUNK * SPMV_CHUNK, SPMV_CHUNK);
+        P.graph_spmv_grid = std::min(P.spmv_grid, std::max(1u, div_up(n_list, 64u) * 64u));
+    }
     // what the captured launches depend on: pointers (buffers may be re-allocated when the contact set grows), the exchange mode and
     // the preconditioner -- NOT the extent of the block list, which the SpMV reads from the control block
     const unsigned long long part_sig = (R.push ? 1ull << 63 : 0ull) ^ ((unsigned long long)(uintptr_t)P.foreign.p << 7) ^ (M.on ? 1ull << 62 : 0ull) ^
                                         ((unsigned long long)(uintptr_t)P.chunks.p << 3) ^ ((unsigned long long)(uintptr_t)P.row.p >> 4) ^
                                         ((unsigned long long)(uintptr_t)P.mask.p << 11) ^ ((unsigned long long)P.cap << 17) ^ (unsigned long long)R.lo ^ ((unsigned long long)R.hi << 32) ^
-                                        (P.spmv_variant ? (unsigned long long)nnz * 0x9E3779B97F4A7C15ull : 0ull); // the A/B SpMV variants take the extent as a launch parameter
+                                        (P.spmv_variant || spmv_legacy ? (unsigned long long)nnz * 0x9E3779B97F4A7C15ull : 0ull) ^ ((unsigned long long)P.graph_spmv_grid << 50); // the A/B SpMV variants take the extent as a launch parameter
     // ---- PPF_B200_PCG_LOOP=1: the whole loop in one cooperative kernel (k_pcg_loop) instead of the graph of three kernels per
     //      iteration.  Measured on a B200 (profiles/r02_pcg_loop_vs_graph.json): correct, but SLOWER -- a software barrier over
     //      592 CTAs costs more than a kernel boundary inside a CUDA graph (large-twist 274.8 vs 264.9 us per iteration, twist
