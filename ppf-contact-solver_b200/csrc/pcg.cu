@@ -56,10 +56,32 @@ struct CgScalars {                 // device-resident control block
     unsigned done_counter;         // k_direction's last-CTA detection
     unsigned done_spmv, done_update; // same for the kernels that publish a partial sum to the peers
     // extent of this solve's block list, read by the SpMV on the device: the captured iteration graph then holds no
-    // per-solve number and survives from one Newton solve to the next (contact scenes change nnz with every assembly;
-    // re-capturing and re-instantiating 96 kernel nodes per solve was up to 15 % of a five-twist solve)
-    unsigned spmv_first, spmv_end, spmv_n_desc;
+    // per-solve number and survives from one Newton solve to the next (contact scenes change nnz with every assembly, which
+    // used to re-capture and re-instantiate the graph at every solve)
+    unsigned spmv_first, spmv_end, spmv_n_desc, spmv_pad; // one 16-byte read
 };
+static_assert(sizeof(CgScalars) == 128 && offsetof(CgScalars, iter) == 72 && offsetof(CgScalars, spmv_first) == 112, "the iteration kernels read the control block as aligned words");
+
+// What the iteration kernels need from the control block when they start: its first 96 bytes.  At small sizes these kernels last a
+// few microseconds, and a chain of dependent reads (status -> iter -> the sums of that parity -> r.z of that parity) was a visible
+// share of that: twelve lanes read the words in ONE request into shared memory instead.
+struct CgHead {
+    double acc[2][2], rzerr[2][2], err0;
+    int iter, status, breakdown;
+    float break_val, tol;
+    int max_iter;
+};
+static_assert(sizeof(CgHead) == 96 && offsetof(CgHead, iter) == offsetof(CgScalars, iter) && offsetof(CgHead, max_iter) == offsetof(CgScalars, max_iter), "CgHead mirrors the head of CgScalars");
+
+// Programmatic dependent launch between the kernels of the iteration graph (PPF_B200_PDL=0 turns the launch attribute off; the
+// instructions are then no-ops).  Every chained kernel starts with pdl_enter(): wait until the kernel before it has completed and
+// its writes are visible, then allow the kernel after it to be scheduled -- its CTAs take the slots this grid frees as it drains
+// and sit in their own wait, so a kernel boundary costs the drain of the last CTA instead of drain + launch latency.  The wait
+// comes before ANY early return: completion is then transitive along the chain.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 struct ChunkDesc { unsigned base, first, end; }; // stage blocks [base, base + SPMV_CHUNK), use those in [first, end)
 
@@ -87,9 +109,12 @@ struct PackedMatrix {
     const void *graph_val = nullptr;
     unsigned long long graph_part = 0;
     int graph_iters = 0;
-    int *h_status = nullptr;         // pinned mirror of {iter, status, last_resid}
+    int *h_status = nullptr;         // pinned, two slots of 8 words: {iter, status, breakdown, break_val, tol, max_iter, last_resid} per polled batch
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    bool poll_ahead = true;          // queue batch k + 1 before reading batch k's verdict (PPF_B200_POLL_AHEAD=0: off)
     unsigned grid = 0;               // persistent grid size of the vector kernels
     unsigned spmv_grid = 0;          // persistent grid of the staged SpMV (SMs x resident CTAs)
+    bool pdl = true;                 // programmatic dependent launch along the iteration chain (PPF_B200_PDL=0: off)
     unsigned graph_spmv_grid = 0;    // grid of the SpMV launches inside the iteration graph: the list length rounded up to a bucket of 64 chunks
     unsigned rpr = 0;                // rows per rank (dist.hpp)
     unsigned n_foreign_fixed = 0;    // foreign blocks of the fixed segment (see Part)
@@ -208,7 +233,9 @@ static void pcg_init(State &s) {
     pcg_l2_policy(s);
     if (world > 1) s.dx.reserve_keep(size_t(3) * P.n_pad, q); // the solved step is all-gathered in place, in equal slices
     P.sc.reserve(1);
-    CUDA_OK(cudaMallocHost(&P.h_status, 64));
+    if (!P.h_status) CUDA_OK(cudaMallocHost(&P.h_status, 64));
+    for (auto &e : P.poll_ev) if (!e) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char *e = getenv("PPF_B200_POLL_AHEAD")) P.poll_ahead = atoi(e) != 0;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -216,6 +243,10 @@ static void pcg_init(State &s) {
     if (const char *e = getenv("PPF_B200_PCG_GRID")) P.grid = (unsigned)atoi(e);
     P.spmv_grid = (unsigned)sms * 4u;
     if (const char *e = getenv("PPF_B200_SPMV_GRID")) P.spmv_grid = (unsigned)atoi(e);
+    // measured on one B200 (profiles/r02_pdl_poll_ahead.json): the chained launch pays where kernel boundaries are a visible share of the
+    // iteration; the bandwidth-bound sizes (32 iterations per graph) gain nothing from it and stay on plain launches
+    P.pdl = n < 500000u && world == 1;
+    if (const char *e = getenv("PPF_B200_PDL")) P.pdl = atoi(e) != 0;
     P.ready = true;
 }
 
@@ -395,6 +426,13 @@ __global__ void k_pack_diag(unsigned n, const unsigned *__restrict__ diag_slot, 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.0f) : "memory");
+}
+
+// snapshot of the control block's head as the kernel before left it (L2 read: the block is written by other kernels and by atomics)
+__device__ __forceinline__ const CgHead &load_head(const CgScalars *sc, unsigned long long *s_head) {
+    if (threadIdx.x < 12) s_head[threadIdx.x] = __ldcg(reinterpret_cast<const unsigned long long *>(sc) + threadIdx.x);
+    __syncthreads();
+    return *reinterpret_cast<const CgHead *>(s_head);
 }
 
 // one double atomic per CTA for each of two partial sums
@@ -703,10 +741,17 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
                                                           const unsigned *__restrict__ col, const float *__restrict__ val, size_t plane,
                                                           const float4 *__restrict__ p, float4 *__restrict__ y, CgScalars *sc, int with_dots,
                                                           PeerView pv, int publish, int evict_first) {
-    if (with_dots && sc->status != ST_RUNNING) return;
-    if (n_desc == 0xFFFFFFFFu) { // the extent of the list comes from the control block (launches captured in the iteration graph)
-        n_desc = sc->spmv_n_desc; k_first = sc->spmv_first; nnz = sc->spmv_end;
-        k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
+    int par = 0;
+    if (with_dots) { // a kernel of the iteration chain: status, parity and the extent of the block list in two independent reads
+        pdl_enter();
+        const int2 is = __ldcg(reinterpret_cast<const int2 *>(&sc->iter));
+        const uint4 ext = __ldcg(reinterpret_cast<const uint4 *>(&sc->spmv_first));
+        if (is.y != ST_RUNNING) return;
+        par = is.x & 1;
+        if (n_desc == 0xFFFFFFFFu) { // launches captured in the iteration graph carry no per-solve number
+            k_first = ext.x; nnz = ext.y; n_desc = ext.z;
+            k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
+        }
     }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned *stage_base = reinterpret_cast<unsigned *>(smem_raw);
@@ -718,7 +763,7 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
     if (blockIdx.x >= n_list) { // nothing to stream (the captured grid is sized for a bucket of list lengths): only count as finished
         if (with_dots && publish && tid == 0 && atomicAdd(&sc->done_spmv, 1u) == gridDim.x - 1) {
             sc->done_spmv = 0;
-            publish_partial(pv, sc, 0, sc->iter & 1);
+            publish_partial(pv, sc, 0, par);
         }
         return;
     }
@@ -804,7 +849,6 @@ __global__ void __launch_bounds__(SPMV_T, 4) k_spmv_staged(const ChunkDesc *__re
         }
     }
     if (!with_dots) return;
-    const int par = sc->iter & 1;
     block_accumulate2(dot, absdot, &sc->acc[par][0], &sc->acc[par][1]);
     if (publish && tid == 0) { // thread 0 issued this CTA's atomics above
         __threadfence();
@@ -1282,8 +1326,11 @@ __global__ void k_residual_init_b(unsigned n, const float *__restrict__ z, float
 __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, unsigned hi, const float4 *__restrict__ y, float *__restrict__ r,
                                                       float *__restrict__ z, const float *__restrict__ Pinv, CgScalars *sc, PeerView pv, int fused,
                                                       MasView mv) {
-    if (sc->status != ST_RUNNING) return;
-    const int par = sc->iter & 1;
+    pdl_enter();
+    __shared__ unsigned long long s_head[12];
+    const CgHead &H = load_head(sc, s_head);
+    if (H.status != ST_RUNNING) return;
+    const int par = H.iter & 1;
     __shared__ double s_sum[2];
     __shared__ int s_ok;
     if (fused) { // p.Ap | sum|terms| of all ranks, from the mailboxes the SpMV kernels filled
@@ -1292,11 +1339,10 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
             if (blockIdx.x == 0 && !s_ok) sc->status = ST_PEER_TIMEOUT;
         }
         __syncthreads();
-    } else if (threadIdx.x == 0) { s_sum[0] = sc->acc[par][0]; s_sum[1] = sc->acc[par][1]; }
-    if (!fused) __syncthreads();
+    }
     int verdict;
     float pAp;
-    const float alpha = cg_alpha(s_sum[0], s_sum[1], sc->rzerr[par][0], verdict, pAp);
+    const float alpha = cg_alpha(fused ? s_sum[0] : H.acc[par][0], fused ? s_sum[1] : H.acc[par][1], H.rzerr[par][0], verdict, pAp);
     float rz = 0.f, err = 0.f;
     // two rows per thread per trip: the vector kernels were latency bound (ncu: long-scoreboard stalls at 55 % of DRAM
     // peak), so both rows' loads are in flight before the first dependent store
@@ -1357,20 +1403,23 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_update(unsigned n, unsigned lo, u
 __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo, unsigned hi, const float *__restrict__ z, float4 *__restrict__ p,
                                                          float4 *__restrict__ y, float *__restrict__ x, const float *__restrict__ D, CgScalars *sc,
                                                          PeerView pv, const unsigned *__restrict__ push_mask, MasView mv) {
-    if (sc->status != ST_RUNNING) return;
-    const int par = sc->iter & 1;
+    pdl_enter();
+    __shared__ unsigned long long s_head[12];
+    const CgHead &H = load_head(sc, s_head);
+    if (H.status != ST_RUNNING) return;
+    const int par = H.iter & 1;
     __shared__ double s_rz[2];
     __shared__ int s_ok;
     if (push_mask) { // r.z | |r|_1 of all ranks, from the mailboxes k_update filled (fused sums come with the peer path)
         if (threadIdx.x == 0) {
             s_ok = gather_sum(pv, 1, par ^ 1, s_rz, sc->rzerr[par ^ 1]) ? 1 : 0;
         }
-    } else if (threadIdx.x == 0) { s_rz[0] = sc->rzerr[par ^ 1][0]; s_rz[1] = sc->rzerr[par ^ 1][1]; s_ok = 1; }
+    } else if (threadIdx.x == 0) { s_rz[0] = H.rzerr[par ^ 1][0]; s_rz[1] = H.rzerr[par ^ 1][1]; s_ok = 1; }
     __syncthreads();
     int verdict;
     float pAp;
-    const float alpha = cg_alpha(sc->acc[par][0], sc->acc[par][1], sc->rzerr[par][0], verdict, pAp);
-    const float rz0 = (float)sc->rzerr[par][0], rz1 = (float)s_rz[0];
+    const float alpha = cg_alpha(H.acc[par][0], H.acc[par][1], H.rzerr[par][0], verdict, pAp);
+    const float rz0 = (float)H.rzerr[par][0], rz1 = (float)s_rz[0];
     const float beta = rz0 > 0.0f ? rz1 / rz0 : 0.0f;
     float dot = 0.f, absdot = 0.f;
     const unsigned stride = gridDim.x * blockDim.x;
@@ -1423,16 +1472,16 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_direction(unsigned n, unsigned lo
     __syncthreads();
     if (last && threadIdx.x == 0) {
         sc->done_counter = 0;
-        const int it = sc->iter + 1;
-        const double reresid = s_rz[1] / sc->err0;
+        const int it = H.iter + 1;
+        const double reresid = s_rz[1] / H.err0;
         sc->last_resid = (float)reresid;
         int st = ST_RUNNING;
-        if (reresid < (double)sc->tol) st = ST_CONVERGED;
-        else if (sc->breakdown == 1) st = ST_TRUNCATED;
-        else if (sc->breakdown == 2) st = ST_FATAL_PAP;
+        if (reresid < (double)H.tol) st = ST_CONVERGED;
+        else if (H.breakdown == 1) st = ST_TRUNCATED; // latched by this iteration's update kernel, i.e. before this kernel started
+        else if (H.breakdown == 2) st = ST_FATAL_PAP;
         else if (!(rz0 > 0.0f)) st = ST_FATAL_RZ;
         else if (!isfinite(reresid)) st = ST_NONFINITE;
-        else if (it >= sc->max_iter) st = ST_CAP;
+        else if (it >= H.max_iter) st = ST_CAP;
         if (!s_ok) st = ST_PEER_TIMEOUT;
         sc->rzerr[par][0] = 0.0; // slots the NEXT iteration's update kernel accumulates into
         sc->rzerr[par][1] = 0.0;
@@ -1884,6 +1933,18 @@ static void pcg_partition(State &s) {
                 R.lo, R.hi, R.kf_first, R.kf_end, P.nnz_f, R.kd_first - P.nnz_f, R.kd_end - P.nnz_f, P.nnz_d, R.n_foreign, P.n_foreign_fixed, (int)R.push);
 }
 
+// launch of a kernel of the iteration chain (see pdl_enter): with P.pdl the launch may be scheduled before its predecessor has drained
+template <typename... K, typename... A>
+static void launch_chained(void (*kern)(K...), unsigned grid, unsigned block, size_t smem, cudaStream_t q, A &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = q;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = P.pdl ? 1 : 0;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...));
+}
+
 static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const float4 *p, float4 *y, int with_dots) {
     if (k_end <= k_first) return;
     static bool attr_set = false;
@@ -1893,8 +1954,8 @@ static void launch_spmv_range(State &s, unsigned k_first, unsigned k_end, const 
     }
     const unsigned k_begin = k_first / SPMV_CHUNK * SPMV_CHUNK;
     if (with_dots) { // captured in the iteration graph: extent from the control block, grid from the bucket the list length falls in
-        k_spmv_staged<<<P.graph_spmv_grid, SPMV_T, SPMV_SMEM, s.stream>>>(nullptr, 0xFFFFFFFFu, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
-                                                                    PeerView{}, 0, P.evict_first);
+        launch_chained(k_spmv_staged, P.graph_spmv_grid, SPMV_T, SPMV_SMEM, s.stream, (const ChunkDesc *)nullptr, 0xFFFFFFFFu, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p,
+                       P.cap, p, y, P.sc.p, with_dots, PeerView{}, 0, P.evict_first);
         return;
     }
     const unsigned grid = std::min(P.spmv_grid, div_up(k_end - k_begin, SPMV_CHUNK));
@@ -1909,7 +1970,12 @@ static void launch_spmv_chunks(State &s, const float4 *p, float4 *y, int with_do
         attr_set = true;
     }
     const unsigned grid = with_dots ? P.graph_spmv_grid : std::max(1u, std::min(P.spmv_grid, R.n_chunks));
-    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, with_dots ? 0xFFFFFFFFu : R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
+    if (with_dots) {
+        launch_chained(k_spmv_staged, grid, SPMV_T, SPMV_SMEM, s.stream, (const ChunkDesc *)P.chunks.p, 0xFFFFFFFFu, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y,
+                       P.sc.p, with_dots, dist_peers(), publish, P.evict_first);
+        return;
+    }
+    k_spmv_staged<<<grid, SPMV_T, SPMV_SMEM, s.stream>>>(P.chunks.p, R.n_chunks, 0u, 0u, 0u, R.lo, R.hi, P.row.p, P.col.p, P.val.p, P.cap, p, y, P.sc.p, with_dots,
                                                          dist_peers(), publish, P.evict_first);
 }
 
@@ -1999,12 +2065,13 @@ static void issue_iteration(State &s, int parity, cudaEvent_t *ev = nullptr) {
     mark(1);
     if (!p2p) dist_allreduce_sum_f64(&P.sc.p->acc[parity][0], 2, s.stream); // peer path: published by the SpMV, summed by k_update
     mark(2);
-    k_update<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.y.p, P.r.p, P.z.p, P.Pinv.p, P.sc.p, pv, p2p ? 1 : 0, mv);
+    launch_chained(k_update, gv, PCG_BLOCK, 0, s.stream, n, R.lo, R.hi, (const float4 *)P.y.p, P.r.p, P.z.p, (const float *)P.Pinv.p, P.sc.p, pv, p2p ? 1 : 0, mv);
     if (M.on) mas_coarse(s, 0);
     mark(3);
     if (!p2p) dist_allreduce_sum_f64(&P.sc.p->rzerr[parity ^ 1][0], 2, s.stream); // peer path: published by k_update, summed by k_direction
     mark(4);
-    k_direction<<<gv, PCG_BLOCK, 0, s.stream>>>(n, R.lo, R.hi, P.z.p, P.p.p, P.y.p, P.x.p, P.D.p, P.sc.p, pv, p2p ? P.mask.p : nullptr, mv);
+    launch_chained(k_direction, gv, PCG_BLOCK, 0, s.stream, n, R.lo, R.hi, (const float *)P.z.p, P.p.p, P.y.p, P.x.p, (const float *)P.D.p, P.sc.p, pv,
+                   (const unsigned *)(p2p ? P.mask.p : nullptr), mv);
     if (!p2p) exchange_p(s);
     mark(5);
 }
@@ -2270,22 +2337,38 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
     CUDA_OK(cudaEventRecord(e0, q));
     int status = ST_RUNNING, iter = 0;
     float resid = 0.f;
-    while (status == ST_RUNNING) {
+    // One batch = one graph launch, then {iter, status, ..., last_resid} (28 contiguous bytes of the control block) copied to a pinned
+    // slot.  The host reads batch k's verdict while batch k + 1 is already queued, so the GPU does not idle for the ~15 us of a status
+    // poll (8 % of a solve at 8 iterations per batch); the batch issued after the verdict fell costs one early-exit launch per kernel --
+    // every kernel of the chain returns at once when status != RUNNING, so iter / status / the solution stay what the verdict said.
+    auto issue_batch = [&](int slot) {
         if (use_loop) {
             LoopArgs A = loop_args;
             void *params[] = {&A};
             CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_pcg_loop, dim3(P.loop_grid), dim3(SPMV_T), params, SPMV_SMEM, q));
             LAUNCH_COUNT(1);
         } else {
-        CUDA_OK(cudaGraphLaunch(P.exec, q));
-        LAUNCH_COUNT((M.on ? 5 : 3) * ITER_PER_GRAPH);
+            CUDA_OK(cudaGraphLaunch(P.exec, q));
+            LAUNCH_COUNT((M.on ? 5 : 3) * ITER_PER_GRAPH);
         }
-        CUDA_OK(cudaMemcpyAsync(P.h_status, &P.sc.p->iter, 2 * sizeof(int), cudaMemcpyDeviceToHost, q));
-        CUDA_OK(cudaMemcpyAsync(P.h_status + 2, &P.sc.p->last_resid, sizeof(float), cudaMemcpyDeviceToHost, q));
-        CUDA_OK(cudaStreamSynchronize(q));
-        iter = P.h_status[0];
-        status = P.h_status[1];
-        memcpy(&resid, P.h_status + 2, sizeof(float));
+        CUDA_OK(cudaMemcpyAsync(P.h_status + 8 * slot, &P.sc.p->iter, 7 * sizeof(int), cudaMemcpyDeviceToHost, q));
+        CUDA_OK(cudaEventRecord(P.poll_ev[slot], q));
+    };
+    auto read_batch = [&](int slot) {
+        CUDA_OK(cudaEventSynchronize(P.poll_ev[slot]));
+        const int *h = P.h_status + 8 * slot;
+        iter = h[0];
+        status = h[1];
+        memcpy(&resid, h + 6, sizeof(float));
+    };
+    static_assert(offsetof(CgScalars, last_resid) - offsetof(CgScalars, iter) == 6 * sizeof(int), "the status poll copies iter .. last_resid as 7 words");
+    const bool ahead = !use_loop && P.poll_ahead;
+    issue_batch(0);
+    for (int k = 0;; ++k) {
+        if (ahead) issue_batch((k + 1) & 1);
+        read_batch(k & 1);
+        if (status != ST_RUNNING) break;
+        if (!ahead) issue_batch((k + 1) & 1);
     }
     CUDA_OK(cudaEventRecord(e1, q));
     CUDA_OK(cudaEventSynchronize(e1));
