@@ -104,6 +104,7 @@ struct Bvh {
     DBuf<int> parent;           // per node
     DBuf<float4> lo, hi;        // per node AABB (xyz)
     DBuf<float4> ulo, uhi;      // per node interval of sweep displacements t_max*(x1-x0) (relative-motion sweeps only)
+    DBuf<float4> pack;          // per internal node, 128 bytes: its two children's (lo, hi, ulo, uhi); lo.w carries the child's node id
     DBuf<unsigned> flag;        // bottom-up arrival counters
     int root = 0;
 };

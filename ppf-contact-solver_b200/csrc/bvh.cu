@@ -127,7 +127,7 @@ struct LeafParams {
 // With ulo/uhi the leaf box is the box at x0 and the node additionally carries the component-wise
 // interval of its vertices' sweep displacements extrapolate*(x1-x0) (see bvh_query_relative).
 __global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_sorted, const int2 *child, const int *parent,
-                      float4 *lo, float4 *hi, unsigned *flag, float4 *ulo, float4 *uhi) {
+                      float4 *lo, float4 *hi, unsigned *flag, float4 *ulo, float4 *uhi, float4 *pack) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const unsigned prim = prim_sorted[k];
@@ -174,12 +174,21 @@ __global__ void k_fit(int kind, unsigned n, LeafParams P, const unsigned *prim_s
         const int other = (c.x == node) ? c.y : c.x;
         // the sibling subtree's box was published before its atomicAdd; read through L2
         const float4 olo = __ldcg(lo + other), ohi = __ldcg(hi + other);
+        // the traversal record of p (bvh.cuh): both children's boxes as they stand, ids in lo.w -- written before the merge below
+        float4 *rec = pack + 8 * size_t(p);
+        const int mine = (c.x == node) ? 0 : 4, theirs = 4 - mine;
+        rec[mine + 0] = make_float4(blo.x, blo.y, blo.z, __uint_as_float((unsigned)node));
+        rec[mine + 1] = bhi;
+        rec[theirs + 0] = make_float4(olo.x, olo.y, olo.z, __uint_as_float((unsigned)other));
+        rec[theirs + 1] = ohi;
         blo = make_float4(fminf(blo.x, olo.x), fminf(blo.y, olo.y), fminf(blo.z, olo.z), 0.f);
         bhi = make_float4(fmaxf(bhi.x, ohi.x), fmaxf(bhi.y, ohi.y), fmaxf(bhi.z, ohi.z), 0.f);
         lo[p] = blo;
         hi[p] = bhi;
         if (rel) {
             const float4 qlo = __ldcg(ulo + other), qhi = __ldcg(uhi + other);
+            rec[mine + 2] = dlo; rec[mine + 3] = dhi;
+            rec[theirs + 2] = qlo; rec[theirs + 3] = qhi;
             dlo = make_float4(fminf(dlo.x, qlo.x), fminf(dlo.y, qlo.y), fminf(dlo.z, qlo.z), 0.f);
             dhi = make_float4(fmaxf(dhi.x, qhi.x), fmaxf(dhi.y, qhi.y), fmaxf(dhi.z, qhi.z), 0.f);
             ulo[p] = dlo;
@@ -194,8 +203,9 @@ static void fit_leaves(State &s, Bvh &b, int kind, const LeafParams &P, bool rel
     if (b.n == 0) return;
     if (relative) { b.ulo.reserve(2 * size_t(b.n)); b.uhi.reserve(2 * size_t(b.n)); }
     if (b.n > 1) CUDA_OK(cudaMemsetAsync(b.flag.p, 0, sizeof(unsigned) * (b.n - 1), s.stream));
+    b.pack.reserve(8 * size_t(b.n));
     k_fit<<<div_up(b.n, 256), 256, 0, s.stream>>>(kind, b.n, P, b.prim_sorted.p, b.child.p, b.parent.p, b.lo.p, b.hi.p, b.flag.p,
-                                                   relative ? b.ulo.p : nullptr, relative ? b.uhi.p : nullptr);
+                                                   relative ? b.ulo.p : nullptr, relative ? b.uhi.p : nullptr, b.pack.p);
     LAUNCH_COUNT(1);
 }
 static void fit(State &s, Bvh &b, int kind, const float4 *x0, const float4 *x1, float extrapolate, bool relative = false) {

@@ -10,9 +10,15 @@ struct BvhView {
     const float4 *lo, *hi;    // node boxes
     const unsigned *prim;     // sorted leaf k -> primitive index
     const float4 *ulo, *uhi;  // node displacement intervals (valid after bvh_refit_relative)
+    // What a traversal reads: per internal node ONE 128-byte record with both children's boxes -- [0..3] left (lo, hi, ulo, uhi),
+    // [4..7] right -- and the children's node ids in the .w of the two lo entries.  A visit is then a single cache line and a single
+    // memory latency; with the per-node arrays above it was the child pair first and then up to eight sectors in four arrays
+    // (the arrays remain: the bottom-up fit merges through them, and the root box is tested from them).
+    const float4 *pack;
 };
 
-inline BvhView view_of(const Bvh &b) { return BvhView{b.n, b.child.p, b.lo.p, b.hi.p, b.prim_sorted.p, b.ulo.p, b.uhi.p}; }
+inline BvhView view_of(const Bvh &b) { return BvhView{b.n, b.child.p, b.lo.p, b.hi.p, b.prim_sorted.p, b.ulo.p, b.uhi.p, b.pack.p}; }
+__device__ __forceinline__ int pack_child(const float4 lo) { return (int)__float_as_uint(lo.w); }
 
 struct Box {
     float lx, ly, lz, hx, hy, hz;
@@ -37,9 +43,11 @@ template <class F> __device__ __forceinline__ bool bvh_query(const BvhView &b, c
     const int first_leaf = (int)b.n - 1;
     while (sp) {
         const int node = stack[--sp];
-        const int2 c = b.child[node];
-        const bool hit_l = box_overlap(q, b.lo[c.x], b.hi[c.x]);
-        const bool hit_r = box_overlap(q, b.lo[c.y], b.hi[c.y]);
+        const float4 *rec = b.pack + 8 * size_t(node);
+        const float4 l_lo = rec[0], l_hi = rec[1], r_lo = rec[4], r_hi = rec[5];
+        const int2 c = make_int2(pack_child(l_lo), pack_child(r_lo));
+        const bool hit_l = box_overlap(q, l_lo, l_hi);
+        const bool hit_r = box_overlap(q, r_lo, r_hi);
         if (hit_l) {
             if (c.x >= first_leaf) f(b.prim[c.x - first_leaf]);
             else stack[sp++] = c.x;
@@ -87,9 +95,11 @@ template <class F> __device__ __forceinline__ bool bvh_query_relative(const BvhV
     const int first_leaf = (int)b.n - 1;
     while (sp) {
         const int node = stack[--sp];
-        const int2 c = b.child[node];
-        const bool hit_l = box_overlap_relative(q, u, b.lo[c.x], b.hi[c.x], b.ulo[c.x], b.uhi[c.x]);
-        const bool hit_r = box_overlap_relative(q, u, b.lo[c.y], b.hi[c.y], b.ulo[c.y], b.uhi[c.y]);
+        const float4 *rec = b.pack + 8 * size_t(node);
+        const float4 l_lo = rec[0], l_hi = rec[1], l_ulo = rec[2], l_uhi = rec[3], r_lo = rec[4], r_hi = rec[5], r_ulo = rec[6], r_uhi = rec[7];
+        const int2 c = make_int2(pack_child(l_lo), pack_child(r_lo));
+        const bool hit_l = box_overlap_relative(q, u, l_lo, l_hi, l_ulo, l_uhi);
+        const bool hit_r = box_overlap_relative(q, u, r_lo, r_hi, r_ulo, r_uhi);
         if (hit_l) {
             if (c.x >= first_leaf) f(b.prim[c.x - first_leaf]);
             else stack[sp++] = c.x;
