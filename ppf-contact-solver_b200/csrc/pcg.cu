@@ -105,7 +105,6 @@ struct PackedMatrix {
     int evict_first = 1;             // matrix stream loaded with L2::evict_first (PPF_B200_L2_STREAM=0: evict_normal, for A/B timing)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    unsigned graph_nnz = ~0u;
     const void *graph_val = nullptr;
     unsigned long long graph_part = 0;
     int graph_iters = 0;
@@ -2327,7 +2326,6 @@ SolveResult pcg_solve(State &s, const PpfParamSet &prm, const unsigned char *dof
             }
         }
         CUDA_OK(cudaGraphInstantiate(&P.exec, P.graph, 0ull));
-        P.graph_nnz = nnz;
         P.graph_val = (const void *)P.val.p;
         P.graph_part = part_sig;
         P.graph_iters = ITER_PER_GRAPH;
