@@ -144,6 +144,16 @@ static size_t round_cap(size_t n) { return (n + SPMV_CHUNK - 1) / SPMV_CHUNK * S
 // does not push out p (gathered by the SpMV right after k_direction wrote it) either.
 //   PPF_B200_L2_PERSIST = y (default) | yp (window over p and y, hit ratio = set-aside / window) | 0 (off, for A/B timing)
 static void pcg_l2_policy(State &s) {
+    // A system that fits the L2 as a whole (twist: 47 MB of blocks + 30 MB of vectors) should stay there from one iteration to the
+    // next: the hint is for matrix streams that cannot (measured, profiles/r02_pdl_poll_ahead.json: twist SpMV alone 16.5 us
+    // with the hint, 14.5 without; five-twist and hang indifferent; large-twist indifferent to the hint alone)
+    {
+        int dev = 0, l2 = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        const size_t ranks = g_dist.on() ? size_t(g_dist.world) : 1; // a rank streams its share of the rows
+        P.evict_first = (size_t(44) * P.nnz_f + size_t(200) * P.n) / ranks > size_t(l2) * 3 / 4;
+    }
     if (const char *e = getenv("PPF_B200_L2_STREAM")) P.evict_first = e[0] != '0';
     if (const char *e = getenv("PPF_B200_SPMV"))
         P.spmv_variant = strcmp(e, "direct1") == 0 ? 1 : (strcmp(e, "direct2") == 0 ? 2 : (strcmp(e, "cpasync2") == 0 ? 3 : (strcmp(e, "cpasync3") == 0 ? 4 : 0)));
